@@ -1,0 +1,440 @@
+"""CPU restatement of the reference's own hot-path code (EGNN / SchNet / TFN / MACE).
+
+ORACLE / TEST INFRASTRUCTURE ONLY (see oracle/__init__.py).  Every function
+cites the reference file:line it follows.  Parameter names and shapes equal the
+reference modules', so a reference ``state_dict`` loads unchanged; the golden
+vectors in tests/golden/ (made by running the unmodified reference under
+oracle/shims) pin this file.
+
+Written functionally on purpose: each layer is a pure function of
+``(params, inputs)`` plus a thin ``nn.Module`` that owns the parameters.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional
+
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+from .thirdparty import o3
+from .thirdparty.e3nn_nn import BatchNorm as E3BatchNorm
+from .thirdparty.e3nn_nn import Gate as E3Gate
+from .thirdparty.e3nn_nn import Activation as E3Activation
+from .thirdparty.einsum import contract
+from .thirdparty.pyg import SchNet as _PygSchNet
+from .thirdparty.pyg import global_add_pool, global_mean_pool
+from .thirdparty.scatter import scatter
+
+_ACT = {"relu": nn.ReLU, "swish": nn.SiLU}
+_NORM = {"layer": nn.LayerNorm, "batch": nn.BatchNorm1d}
+_POOL = {"sum": global_add_pool, "mean": global_mean_pool}
+
+
+# =========================================================================== #
+# EGNN   (models/layers/egnn_layer.py:7-89, models/egnn.py:8-87)
+# =========================================================================== #
+def _mlp(dims_in: int, d: int, act: str, norm: str, tail: Optional[int] = None) -> nn.Sequential:
+    """Linear-norm-act-Linear(-norm-act | ->tail)  (egnn_layer.py:28-48)."""
+    mods: List[nn.Module] = [nn.Linear(dims_in, d), _NORM[norm](d), _ACT[act]()]
+    if tail is None:
+        mods += [nn.Linear(d, d), _NORM[norm](d), _ACT[act]()]
+    else:
+        mods += [nn.Linear(d, tail)]
+    return nn.Sequential(*mods)
+
+
+def egnn_edge_message(layer: "EGNNLayer", h, pos, edge_index):
+    """egnn_layer.py:62-72 with PyG's gather (A.2): j = edge_index[0], i = edge_index[1]."""
+    j, i = edge_index[0], edge_index[1]
+    delta = pos[i] - pos[j]
+    dist = delta.norm(dim=-1, keepdim=True)
+    m = layer.mlp_msg(torch.cat([h[i], h[j], dist], dim=-1))
+    return m, delta * layer.mlp_pos(m)
+
+
+class EGNNLayer(nn.Module):
+    def __init__(self, emb_dim, activation="relu", norm="layer", aggr="add"):
+        super().__init__()
+        self.emb_dim, self.aggr = emb_dim, aggr
+        self.mlp_msg = _mlp(2 * emb_dim + 1, emb_dim, activation, norm)
+        self.mlp_pos = _mlp(emb_dim, emb_dim, activation, norm, tail=1)
+        self.mlp_upd = _mlp(2 * emb_dim, emb_dim, activation, norm)
+
+    def forward(self, h, pos, edge_index):
+        m, shift = egnn_edge_message(self, h, pos, edge_index)
+        idx = edge_index[1]
+        # egnn_layer.py:77,79 (no dim_size: rows = idx.max()+1, SURVEY A.1 gotcha)
+        m_aggr = scatter(m, idx, dim=-2, reduce=self.aggr)
+        p_aggr = scatter(shift, idx, dim=-2, reduce="mean")
+        # egnn_layer.py:84-85
+        return self.mlp_upd(torch.cat([h, m_aggr], dim=-1)), pos + p_aggr
+
+
+class MPNNLayer(nn.Module):
+    """egnn_layer.py:92-155 (same scatter, no geometry)."""
+
+    def __init__(self, emb_dim, activation="relu", norm="layer", aggr="add"):
+        super().__init__()
+        self.emb_dim, self.aggr = emb_dim, aggr
+        self.mlp_msg = _mlp(2 * emb_dim, emb_dim, activation, norm)
+        self.mlp_upd = _mlp(2 * emb_dim, emb_dim, activation, norm)
+
+    def forward(self, h, edge_index):
+        j, i = edge_index[0], edge_index[1]
+        m = self.mlp_msg(torch.cat([h[i], h[j]], dim=-1))
+        return self.mlp_upd(torch.cat([h, scatter(m, i, dim=-2, reduce=self.aggr)], dim=-1))
+
+
+class EGNNModel(nn.Module):
+    def __init__(self, num_layers=5, emb_dim=128, in_dim=1, out_dim=1, activation="relu", norm="layer",
+                 aggr="sum", pool="sum", residual=True, equivariant_pred=False):
+        super().__init__()
+        self.equivariant_pred, self.residual = equivariant_pred, residual
+        self.emb_in = nn.Embedding(in_dim, emb_dim)
+        self.convs = nn.ModuleList([EGNNLayer(emb_dim, activation, norm, aggr) for _ in range(num_layers)])
+        self.pool = _POOL[pool]
+        if equivariant_pred:
+            self.pred = nn.Linear(emb_dim + 3, out_dim)
+        else:
+            self.pred = nn.Sequential(nn.Linear(emb_dim, emb_dim), nn.ReLU(), nn.Linear(emb_dim, out_dim))
+
+    def forward(self, batch):
+        # egnn.py:66-87
+        h, pos = self.emb_in(batch.atoms), batch.pos
+        for conv in self.convs:
+            dh, pos = conv(h, pos, batch.edge_index)
+            h = h + dh if self.residual else dh
+        feats = torch.cat([h, pos], dim=-1) if self.equivariant_pred else h
+        return self.pred(self.pool(feats, batch.batch))
+
+
+# =========================================================================== #
+# SchNet   (models/schnet.py:9-80 over PyG 2.3.1 SchNet)
+# =========================================================================== #
+class SchNetModel(_PygSchNet):
+    def __init__(self, hidden_channels=128, in_dim=1, out_dim=1, num_filters=128, num_layers=6,
+                 num_gaussians=50, cutoff=10, max_num_neighbors=32, pool="sum"):
+        super().__init__(hidden_channels, num_filters, num_layers, num_gaussians, cutoff,
+                         interaction_graph=None, max_num_neighbors=max_num_neighbors, readout=pool)
+        self.pool = _POOL[pool]
+        self.lin2 = nn.Linear(hidden_channels // 2, out_dim)  # schnet.py:60 (default init)
+
+    def forward(self, batch):
+        # schnet.py:62-80
+        h = self.embedding(batch.atoms)
+        row, col = batch.edge_index
+        d = (batch.pos[row] - batch.pos[col]).norm(dim=-1)
+        rbf = self.distance_expansion(d)
+        for block in self.interactions:
+            h = h + block(h, batch.edge_index, d, rbf)
+        out = self.pool(h, batch.batch)
+        return self.lin2(self.act(self.lin1(out)))
+
+
+# =========================================================================== #
+# Radial basis   (models/mace_modules/radial.py:12-81, blocks.py:84-96)
+# =========================================================================== #
+def bessel_basis(x: torch.Tensor, r_max: float, num_basis: int) -> torch.Tensor:
+    """radial.py:20-29,44-46: sqrt(2/r_max) * sin(n*pi*x/r_max) / x, n = 1..num_basis."""
+    w = (math.pi / r_max) * torch.linspace(1.0, num_basis, num_basis, dtype=x.dtype, device=x.device)
+    pref = torch.tensor(math.sqrt(2.0 / r_max), dtype=x.dtype, device=x.device)
+    return pref * (torch.sin(w * x) / x)
+
+
+def polynomial_cutoff(x: torch.Tensor, r_max: float, p: float) -> torch.Tensor:
+    """radial.py:71-78."""
+    p = torch.tensor(float(p), dtype=x.dtype, device=x.device)
+    r = torch.tensor(float(r_max), dtype=x.dtype, device=x.device)
+    u = x / r
+    env = (1.0 - ((p + 1.0) * (p + 2.0) / 2.0) * torch.pow(u, p)
+           + p * (p + 2.0) * torch.pow(u, p + 1) - (p * (p + 1.0) / 2) * torch.pow(u, p + 2))
+    return env * (x < r)
+
+
+class RadialEmbeddingBlock(nn.Module):
+    def __init__(self, r_max: float, num_bessel: int, num_polynomial_cutoff: int):
+        super().__init__()
+        self.r_max, self.num_bessel, self.p = float(r_max), num_bessel, num_polynomial_cutoff
+        self.out_dim = num_bessel
+
+    def forward(self, edge_lengths):  # [E,1] -> [E,num_bessel]
+        return bessel_basis(edge_lengths, self.r_max, self.num_bessel) * polynomial_cutoff(
+            edge_lengths, self.r_max, self.p)
+
+
+# =========================================================================== #
+# Irreps helpers   (models/mace_modules/irreps_tools.py:64-97)
+# =========================================================================== #
+def irreps2gate(irreps):
+    """irreps_tools.py:82-97: split into (scalars 0e, gates one-0e-per-gated-channel, gated l>0 or odd)."""
+    irreps = o3.Irreps(irreps)
+    scal = o3.Irreps([(m, ir) for m, ir in irreps if ir.l == 0 and ir.p == 1]).simplify()
+    gated = o3.Irreps([(m, ir) for m, ir in irreps if not (ir.l == 0 and ir.p == 1)]).simplify()
+    gates = o3.Irreps([(m, "0e") for m, _ in gated]).simplify() if gated.dim > 0 else o3.Irreps([])
+    return scal, gates, gated
+
+
+def reshape_irreps_fn(x: torch.Tensor, irreps) -> torch.Tensor:
+    """irreps_tools.py:69-79: [N, sum mul*d] -> [N, mul, sum d]."""
+    out, ix = [], 0
+    for mul, ir in o3.Irreps(irreps):
+        out.append(x[:, ix:ix + mul * ir.dim].reshape(x.shape[0], mul, ir.dim))
+        ix += mul * ir.dim
+    return torch.cat(out, dim=-1)
+
+
+class reshape_irreps(nn.Module):
+    def __init__(self, irreps):
+        super().__init__()
+        self.irreps = o3.Irreps(irreps)
+
+    def forward(self, x):
+        return reshape_irreps_fn(x, self.irreps)
+
+
+# =========================================================================== #
+# TFN conv layer   (models/layers/tfn_layer.py:8-93)
+# =========================================================================== #
+class TensorProductConvLayer(nn.Module):
+    def __init__(self, in_irreps, out_irreps, sh_irreps, edge_feats_dim, mlp_dim, aggr="add",
+                 batch_norm=False, gate=False):
+        super().__init__()
+        self.in_irreps, self.sh_irreps = o3.Irreps(str(in_irreps)), o3.Irreps(str(sh_irreps))
+        out_irreps = o3.Irreps(str(out_irreps))
+        self.aggr = aggr
+        self.gate = None
+        if gate:  # tfn_layer.py:45-63
+            scal, gates, gated = irreps2gate(out_irreps)
+            if gated.num_irreps == 0:
+                self.gate = E3Activation(out_irreps, acts=[F.silu])
+            else:
+                self.gate = E3Gate(scal, [F.silu for _ in scal], gates, [torch.sigmoid for _ in gates], gated)
+                out_irreps = self.gate.irreps_in
+        self.out_irreps = out_irreps
+        self.tp = o3.FullyConnectedTensorProduct(self.in_irreps, self.sh_irreps, out_irreps, shared_weights=False)
+        self.fc = nn.Sequential(nn.Linear(edge_feats_dim, mlp_dim), nn.ReLU(), nn.Linear(mlp_dim, self.tp.weight_numel))
+        self.batch_norm = E3BatchNorm(out_irreps) if batch_norm else None
+
+    def forward(self, node_attr, edge_index, edge_sh, edge_feat):
+        src, dst = edge_index  # tfn_layer.py:83: gather at ei[1], reduce at ei[0]
+        msg = self.tp(node_attr[dst], edge_sh, self.fc(edge_feat))
+        out = scatter(msg, src, dim=0, reduce=self.aggr)
+        if self.gate is not None:
+            out = self.gate(out)
+        if self.batch_norm is not None:
+            out = self.batch_norm(out)
+        return out
+
+
+def first_node_pooling(x, batch, size=None):
+    """models/tfn.py:13-40: picks the first node of every graph except graph 0's
+    (the comparison ``batch - shifted == 1`` is False at index 0, where shifted = -1
+    ... it is True: 0 - (-1) == 1), i.e. the first node of every graph."""
+    shifted = torch.cat([batch[-1:], batch[:-1]])
+    shifted[0] = -1
+    return x[(batch - shifted) == 1]
+
+
+def edge_geometry(pos, edge_index, sh_mod, radial_mod):
+    """models/tfn.py:171-175 == models/mace.py:170-174."""
+    vec = pos[edge_index[0]] - pos[edge_index[1]]
+    length = torch.linalg.norm(vec, dim=-1, keepdim=True)
+    return sh_mod(vec), radial_mod(length)
+
+
+class _EquivariantBase(nn.Module):
+    def _common(self, r_max, num_bessel, num_polynomial_cutoff, max_ell, emb_dim, hidden_irreps, in_dim, out_dim,
+                equivariant_pred):
+        self.radial_embedding = RadialEmbeddingBlock(r_max, num_bessel, num_polynomial_cutoff)
+        self.sh_irreps = o3.Irreps.spherical_harmonics(max_ell)
+        self.spherical_harmonics = o3.SphericalHarmonics(self.sh_irreps, normalize=True, normalization="component")
+        self.emb_in = nn.Embedding(in_dim, emb_dim)
+        if hidden_irreps is None:
+            hidden_irreps = (self.sh_irreps * emb_dim).sort()[0].simplify()
+        self.hidden_irreps = o3.Irreps(str(hidden_irreps))
+        if equivariant_pred:
+            self.pred = nn.Linear(self.hidden_irreps.dim, out_dim)
+        else:
+            self.pred = nn.Sequential(nn.Linear(emb_dim, emb_dim), nn.ReLU(), nn.Linear(emb_dim, out_dim))
+
+
+class TFNModel(_EquivariantBase):
+    def __init__(self, r_max=10.0, num_bessel=8, num_polynomial_cutoff=5, max_ell=2, num_layers=5, emb_dim=64,
+                 hidden_irreps=None, mlp_dim=256, in_dim=1, out_dim=1, aggr="sum", pool="first", gate=True,
+                 batch_norm=False, residual=True, equivariant_pred=False):
+        super().__init__()
+        self.emb_dim, self.residual, self.equivariant_pred = emb_dim, residual, equivariant_pred
+        self._common(r_max, num_bessel, num_polynomial_cutoff, max_ell, emb_dim, hidden_irreps, in_dim, out_dim,
+                     equivariant_pred)
+        ins = [o3.Irreps(f"{emb_dim}x0e")] + [self.hidden_irreps] * (num_layers - 1)
+        self.convs = nn.ModuleList([
+            TensorProductConvLayer(i, self.hidden_irreps, self.sh_irreps, num_bessel, mlp_dim, aggr, batch_norm, gate)
+            for i in ins])
+        self.pool = {**_POOL, "first": first_node_pooling}[pool]
+
+    def forward(self, batch):
+        # tfn.py:166-190
+        h = self.emb_in(batch.atoms)
+        sh, rbf = edge_geometry(batch.pos, batch.edge_index, self.spherical_harmonics, self.radial_embedding)
+        for conv in self.convs:
+            upd = conv(h, batch.edge_index, sh, rbf)
+            h = upd + F.pad(h, (0, upd.shape[-1] - h.shape[-1])) if self.residual else upd
+        out = self.pool(h, batch.batch)
+        if not self.equivariant_pred:
+            out = out[:, :self.emb_dim]
+        return self.pred(out)
+
+
+# =========================================================================== #
+# MACE   (models/mace.py:16-190, blocks.py:99-135, symmetric_contraction.py, cg.py)
+# =========================================================================== #
+def _wigner_nj(irrepss, dtype):
+    """cg.py:19-88 ('component' normalisation, no mid filter): iterated real-CG coupling.
+    Returns a list of (ir_out, basis tensor [d_out, dim, ..., dim]) sorted by ir_out (stable)."""
+    irrepss = [o3.Irreps(i) for i in irrepss]
+    if len(irrepss) == 1:
+        (irreps,) = irrepss
+        eye, ret, i = torch.eye(irreps.dim, dtype=dtype), [], 0
+        for mul, ir in irreps:
+            for _ in range(mul):
+                ret.append((ir, eye[i:i + ir.dim]))
+                i += ir.dim
+        return ret
+    *left, right = irrepss
+    ret = []
+    for ir_left, C_left in _wigner_nj(left, dtype):
+        i = 0
+        for mul, ir in right:
+            for ir_out in ir_left * ir:
+                C = o3.wigner_3j(ir_out.l, ir_left.l, ir.l, dtype=dtype) * ir_out.dim ** 0.5
+                C = torch.einsum("jk,ijl->ikl", C_left.flatten(1), C)
+                C = C.reshape(ir_out.dim, *(x.dim for x in left), ir.dim)
+                for u in range(mul):
+                    E = torch.zeros(ir_out.dim, *(x.dim for x in left), right.dim, dtype=dtype)
+                    E[..., i + u * ir.dim:i + (u + 1) * ir.dim] = C
+                    ret.append((ir_out, E))
+            i += mul * ir.dim
+    return sorted(ret, key=lambda t: t[0])
+
+
+def u_matrix_real(irreps_in, ir_out, correlation: int, dtype=None) -> torch.Tensor:
+    """cg.py:91-133 for a single output irrep: stack of all coupling paths into
+    ``ir_out``, shape [d_out, dim^nu, k] squeezed when d_out == 1."""
+    dtype = dtype or torch.get_default_dtype()
+    ir_out = o3.Irrep(ir_out)
+    basis = [B for ir, B in _wigner_nj([o3.Irreps(irreps_in)] * correlation, dtype) if ir == ir_out]
+    return torch.stack([b.squeeze() for b in basis], dim=-1)
+
+
+class Contraction(nn.Module):
+    """symmetric_contraction.py:88-188, element_dependent=False branch."""
+
+    def __init__(self, irreps_in, irrep_out, correlation: int):
+        super().__init__()
+        irreps_in = o3.Irreps(irreps_in)
+        self.num_features = irreps_in.count((0, 1))
+        coupling = o3.Irreps([ir for _, ir in irreps_in])
+        self.correlation = correlation
+        self.weights = nn.ParameterDict()
+        for nu in range(1, correlation + 1):
+            U = u_matrix_real(coupling, irrep_out, nu)
+            self.register_buffer(f"U_matrix_{nu}", U)
+            k = U.shape[-1]
+            self.weights[str(nu)] = nn.Parameter(torch.randn(k, self.num_features) / k)
+
+    def forward(self, x, y=None):
+        nu = self.correlation
+        out = contract("...ik,kc,bci->bc...", getattr(self, f"U_matrix_{nu}"), self.weights[str(nu)], x)
+        for nu in range(self.correlation - 1, 0, -1):
+            c = contract("...k,kc->c...", getattr(self, f"U_matrix_{nu}"), self.weights[str(nu)]) + out
+            out = contract("bc...i,bci->bc...", c, x)
+        return out.reshape(out.shape[0], -1)
+
+
+class SymmetricContraction(nn.Module):
+    """symmetric_contraction.py:21-85."""
+
+    def __init__(self, irreps_in, irreps_out, correlation, element_dependent=False, num_elements=None, **_):
+        super().__init__()
+        assert not element_dependent, "reference uses element_dependent=False (models/mace.py:119)"
+        self.irreps_in, self.irreps_out = o3.Irreps(str(irreps_in)), o3.Irreps(str(irreps_out))
+        self.contractions = nn.ModuleDict({
+            str(mi): Contraction(self.irreps_in, mi.ir, correlation) for mi in self.irreps_out})
+
+    def forward(self, x, y=None):
+        return torch.cat([self.contractions[str(mi)](x, y) for mi in self.irreps_out], dim=-1)
+
+
+class EquivariantProductBasisBlock(nn.Module):
+    """blocks.py:99-135."""
+
+    def __init__(self, node_feats_irreps, target_irreps, correlation, element_dependent=True, use_sc=True,
+                 batch_norm=False, num_elements=None):
+        super().__init__()
+        self.use_sc = use_sc
+        self.symmetric_contractions = SymmetricContraction(node_feats_irreps, target_irreps, correlation,
+                                                           element_dependent=element_dependent,
+                                                           num_elements=num_elements)
+        self.linear = o3.Linear(target_irreps, target_irreps)
+        self.batch_norm = E3BatchNorm(target_irreps) if batch_norm else None
+
+    def forward(self, node_feats, sc, node_attrs=None):
+        out = self.linear(self.symmetric_contractions(node_feats, node_attrs))
+        if self.batch_norm is not None:
+            out = self.batch_norm(out)
+        return out + sc if self.use_sc else out
+
+
+class MACEModel(_EquivariantBase):
+    def __init__(self, r_max=10.0, num_bessel=8, num_polynomial_cutoff=5, max_ell=2, correlation=3, num_layers=5,
+                 emb_dim=64, hidden_irreps=None, mlp_dim=256, in_dim=1, out_dim=1, aggr="sum", pool="sum",
+                 batch_norm=True, residual=True, equivariant_pred=False):
+        super().__init__()
+        self.emb_dim, self.residual, self.equivariant_pred = emb_dim, residual, equivariant_pred
+        self._common(r_max, num_bessel, num_polynomial_cutoff, max_ell, emb_dim, hidden_irreps, in_dim, out_dim,
+                     equivariant_pred)
+        ins = [o3.Irreps(f"{emb_dim}x0e")] + [self.hidden_irreps] * (num_layers - 1)
+        self.convs = nn.ModuleList([
+            TensorProductConvLayer(i, self.hidden_irreps, self.sh_irreps, num_bessel, mlp_dim, aggr, batch_norm, False)
+            for i in ins])
+        self.reshapes = nn.ModuleList([reshape_irreps(self.hidden_irreps) for _ in ins])
+        self.prods = nn.ModuleList([
+            EquivariantProductBasisBlock(self.hidden_irreps, self.hidden_irreps, correlation, element_dependent=False,
+                                         num_elements=in_dim, use_sc=residual) for _ in ins])
+        self.pool = _POOL[pool]
+
+    def forward(self, batch):
+        # mace.py:165-190
+        h = self.emb_in(batch.atoms)
+        sh, rbf = edge_geometry(batch.pos, batch.edge_index, self.spherical_harmonics, self.radial_embedding)
+        for conv, reshape, prod in zip(self.convs, self.reshapes, self.prods):
+            upd = conv(h, batch.edge_index, sh, rbf)
+            sc = F.pad(h, (0, upd.shape[-1] - h.shape[-1]))
+            h = prod(reshape(upd), sc, None)
+        out = self.pool(h, batch.batch)
+        if not self.equivariant_pred:
+            out = out[:, :self.emb_dim]
+        return self.pred(out)
+
+
+# =========================================================================== #
+# Fixtures from the reference experiments
+# =========================================================================== #
+def create_kchains(k: int):
+    """experiments/kchains.ipynb:71-107: two (k+2)-node chains whose k centre nodes sit at
+    (0, 5i, 0); the first end node is at (-4,-3,0) in graph 0 and (+4,-3,0) in graph 1;
+    positions are centred on their mean; edges are the undirected chain."""
+    from .thirdparty.pyg import Data, to_undirected
+    assert k >= 2
+    n = k + 2
+    chain = to_undirected(torch.stack([torch.arange(0, n - 1), torch.arange(1, n)]).long())
+    graphs = []
+    for label, x0 in enumerate((-4.0, 4.0)):
+        pos = torch.tensor([[x0, -3.0, 0.0]] + [[0.0, 5.0 * i, 0.0] for i in range(k)]
+                           + [[4.0, 5.0 * (k - 1) + 3.0, 0.0]], dtype=torch.float32)
+        pos = pos - pos.mean(dim=0)
+        graphs.append(Data(atoms=torch.zeros(n, dtype=torch.long), edge_index=chain.clone(), pos=pos,
+                           y=torch.tensor([label])))
+    return graphs
