@@ -1,0 +1,19 @@
+"""gmp_b200 -- B200-native geometric message passing (hot path of NW-JEFF/Geometric-Message-Passing).
+
+Layout
+  csrc/        hand-written sm_100a CUDA kernels + the C ABI (include/gmp_b200.h -> libgmp_b200.so)
+  _lib.py      ctypes binding of that ABI (no fallback: missing library = error)
+  graph.py     radius_graph (torch_cluster canonical order), CSR / Graph cache
+  scatter.py   torch_scatter.scatter replacements (deterministic segmented reductions)
+  schnet.py    SchNet InteractionBlock / CFConv / SchNetModel     (models/schnet.py)
+  egnn.py      EGNNLayer / MPNNLayer / EGNNModel                   (models/layers/egnn_layer.py, models/egnn.py)
+  tfn.py       TensorProductConvLayer / TFNModel                   (models/layers/tfn_layer.py, models/tfn.py)
+  mace.py      SymmetricContraction / EquivariantProductBasisBlock / MACEModel (models/mace_modules, models/mace.py)
+"""
+from . import _lib  # noqa: F401
+from .graph import CSR, Graph, build_csr, get_graph, radius_graph  # noqa: F401
+from .scatter import scatter, scatter_mean, scatter_sum, segment_reduce  # noqa: F401
+from .schnet import (CFConv, GaussianSmearing, InteractionBlock, SchNetModel, ShiftedSoftplus,  # noqa: F401
+                     edge_length, global_add_pool, global_mean_pool)
+
+__version__ = "0.1.0"

@@ -1,0 +1,193 @@
+// Deterministic, atomics-free segmented reductions over a CSR (torch_scatter replacements) and the
+// K0 "gather x multiply -> segmented sum" kernel.  HBM-bound: one warp per destination row, float4
+// lanes across the feature dimension, 4 neighbour rows in flight per lane.
+#include "common.cuh"
+
+namespace gmp {
+
+template <bool HAS_W, bool GATHER>
+__global__ void __launch_bounds__(256)
+segsum_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, const int32_t* __restrict__ perm,
+              const float* __restrict__ x, const float* __restrict__ w, float* __restrict__ out, int64_t n, int F,
+              int mean) {
+    const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (row >= n) return;
+    const int b = __ldg(rowptr + row), e = __ldg(rowptr + row + 1);
+    const float scale = (mean && e > b) ? 1.0f / (float)(e - b) : 1.0f;
+    for (int f = lane * 4; f < F; f += 128) {
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        int k = b;
+        for (; k + 4 <= e; k += 4) {
+            float4 xv[4], wv[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int64_t srow = GATHER ? (int64_t)__ldg(col + k + u) : (perm ? (int64_t)__ldg(perm + k + u) : (int64_t)(k + u));
+                xv[u] = ldg4(x + srow * F + f);
+                if (HAS_W) {
+                    const int64_t wrow = perm ? (int64_t)__ldg(perm + k + u) : (int64_t)(k + u);
+                    wv[u] = ldg4(w + wrow * F + f);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (HAS_W) {
+                    acc.x = fmaf(xv[u].x, wv[u].x, acc.x); acc.y = fmaf(xv[u].y, wv[u].y, acc.y);
+                    acc.z = fmaf(xv[u].z, wv[u].z, acc.z); acc.w = fmaf(xv[u].w, wv[u].w, acc.w);
+                } else {
+                    acc.x += xv[u].x; acc.y += xv[u].y; acc.z += xv[u].z; acc.w += xv[u].w;
+                }
+            }
+        }
+        for (; k < e; ++k) {
+            const int64_t srow = GATHER ? (int64_t)__ldg(col + k) : (perm ? (int64_t)__ldg(perm + k) : (int64_t)k);
+            const float4 xv = ldg4(x + srow * F + f);
+            if (HAS_W) {
+                const int64_t wrow = perm ? (int64_t)__ldg(perm + k) : (int64_t)k;
+                const float4 wv = ldg4(w + wrow * F + f);
+                acc.x = fmaf(xv.x, wv.x, acc.x); acc.y = fmaf(xv.y, wv.y, acc.y);
+                acc.z = fmaf(xv.z, wv.z, acc.z); acc.w = fmaf(xv.w, wv.w, acc.w);
+            } else {
+                acc.x += xv.x; acc.y += xv.y; acc.z += xv.z; acc.w += xv.w;
+            }
+        }
+        acc.x *= scale; acc.y *= scale; acc.z *= scale; acc.w *= scale;
+        *reinterpret_cast<float4*>(out + row * F + f) = acc;
+    }
+}
+
+// narrow features (F not a multiple of 4, e.g. the EGNN coordinate update F = 3): one thread per (row, f)
+__global__ void segsum_narrow_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ perm,
+                                     const float* __restrict__ src, float* __restrict__ out, int64_t n, int F, int mean) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n * F) return;
+    const int64_t row = t / F;
+    const int f = (int)(t - row * F);
+    const int b = rowptr[row], e = rowptr[row + 1];
+    float acc = 0.f;
+    for (int k = b; k < e; ++k) acc += src[(int64_t)(perm ? perm[k] : k) * F + f];
+    if (mean && e > b) acc /= (float)(e - b);
+    out[t] = acc;
+}
+
+__global__ void gather_rows_kernel(const int32_t* __restrict__ idx, const float* __restrict__ x, float* __restrict__ out,
+                                   int64_t rows, int F4) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= rows * F4) return;
+    const int64_t r = t / F4;
+    const int f = (int)(t - r * F4);
+    reinterpret_cast<float4*>(out)[t] = __ldg(reinterpret_cast<const float4*>(x) + (int64_t)idx[r] * F4 + f);
+}
+
+__global__ void gather_rows_scalar_kernel(const int32_t* __restrict__ idx, const float* __restrict__ x,
+                                          float* __restrict__ out, int64_t rows, int F) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= rows * F) return;
+    const int64_t r = t / F;
+    out[t] = x[(int64_t)idx[r] * F + (t - r * F)];
+}
+
+__global__ void reduce_partials_kernel(const float* __restrict__ part, int nparts, int64_t len, float* __restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= len) return;
+    float acc = 0.f;
+    for (int p = 0; p < nparts; ++p) acc += part[(int64_t)p * len + i];  // fixed order: deterministic
+    out[i] = acc;
+}
+
+__global__ void edge_length_kernel(const float* __restrict__ pos, const int64_t* __restrict__ src,
+                                   const int64_t* __restrict__ dst, int64_t E, float* __restrict__ dist) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= E) return;
+    const int64_t a = src[e], b = dst[e];
+    const float dx = pos[3 * a] - pos[3 * b], dy = pos[3 * a + 1] - pos[3 * b + 1], dz = pos[3 * a + 2] - pos[3 * b + 2];
+    dist[e] = sqrtf(dx * dx + dy * dy + dz * dz);
+}
+
+// dpos[i] = sum_{e: src=i} g u_e - sum_{e: dst=i} g u_e ; one thread per node, both CSRs walked in order
+__global__ void edge_length_bwd_kernel(const float* __restrict__ pos, const int64_t* __restrict__ src,
+                                       const int64_t* __restrict__ dst, const float* __restrict__ g,
+                                       const int32_t* __restrict__ rp_s, const int32_t* __restrict__ pm_s,
+                                       const int32_t* __restrict__ rp_d, const int32_t* __restrict__ pm_d, int64_t n,
+                                       float* __restrict__ dpos) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float ax = 0.f, ay = 0.f, az = 0.f;
+    for (int pass = 0; pass < 2; ++pass) {
+        const int32_t* rp = pass ? rp_d : rp_s;
+        const int32_t* pm = pass ? pm_d : pm_s;
+        const float sgn = pass ? -1.f : 1.f;
+        for (int k = rp[i]; k < rp[i + 1]; ++k) {
+            const int64_t e = pm ? pm[k] : k;
+            const int64_t a = src[e], b = dst[e];
+            const float dx = pos[3 * a] - pos[3 * b], dy = pos[3 * a + 1] - pos[3 * b + 1], dz = pos[3 * a + 2] - pos[3 * b + 2];
+            const float d = sqrtf(dx * dx + dy * dy + dz * dz);
+            // torch.norm backward: grad * x / norm, with the subgradient 0 at norm == 0
+            const float s = d > 0.f ? sgn * g[e] / d : 0.f;
+            ax = fmaf(s, dx, ax); ay = fmaf(s, dy, ay); az = fmaf(s, dz, az);
+        }
+    }
+    dpos[3 * i] = ax; dpos[3 * i + 1] = ay; dpos[3 * i + 2] = az;
+}
+
+}  // namespace gmp
+
+using namespace gmp;
+
+extern "C" {
+
+int gmp_segment_reduce_f32(const int32_t* rowptr, const int32_t* perm, const float* src, float* out, int64_t n,
+                           int32_t F, int32_t mean, gmp_stream_t stream) {
+    GMP_REQUIRE(rowptr && out && n >= 0 && F > 0, "segment_reduce: bad arguments");
+    if (n == 0) return GMP_OK;
+    if (F % 4 == 0) {
+        segsum_kernel<false, false><<<(unsigned)ceil_div(n * 32, 256), 256, 0, stream>>>(rowptr, nullptr, perm, src, nullptr, out, n, F, mean);
+    } else {
+        segsum_narrow_kernel<<<(unsigned)ceil_div(n * F, 256), 256, 0, stream>>>(rowptr, perm, src, out, n, F, mean);
+    }
+    return check_launch("segment_reduce");
+}
+
+int gmp_gather_mul_segsum_f32(const int32_t* rowptr, const int32_t* col, const int32_t* perm, const float* x,
+                              const float* w, float* out, int64_t n, int32_t F, gmp_stream_t stream) {
+    GMP_REQUIRE(rowptr && col && x && out && n >= 0 && F > 0 && F % 4 == 0, "gather_mul_segsum: bad arguments (F % 4 == 0)");
+    if (n == 0) return GMP_OK;
+    const unsigned grid = (unsigned)ceil_div(n * 32, 256);
+    if (w) segsum_kernel<true, true><<<grid, 256, 0, stream>>>(rowptr, col, perm, x, w, out, n, F, 0);
+    else segsum_kernel<false, true><<<grid, 256, 0, stream>>>(rowptr, col, perm, x, nullptr, out, n, F, 0);
+    return check_launch("gather_mul_segsum");
+}
+
+int gmp_gather_rows_f32(const int32_t* idx, const float* x, float* out, int64_t num_rows, int32_t F, gmp_stream_t stream) {
+    GMP_REQUIRE(num_rows == 0 || (idx && x && out && F > 0), "gather_rows: bad arguments");
+    if (num_rows == 0) return GMP_OK;
+    if (F % 4 == 0) gather_rows_kernel<<<(unsigned)ceil_div(num_rows * (F / 4), 256), 256, 0, stream>>>(idx, x, out, num_rows, F / 4);
+    else gather_rows_scalar_kernel<<<(unsigned)ceil_div(num_rows * F, 256), 256, 0, stream>>>(idx, x, out, num_rows, F);
+    return check_launch("gather_rows");
+}
+
+int gmp_reduce_partials_f32(const float* part, int32_t nparts, int64_t len, float* out, gmp_stream_t stream) {
+    GMP_REQUIRE(part && out && nparts >= 1 && len >= 0, "reduce_partials: bad arguments");
+    if (len == 0) return GMP_OK;
+    reduce_partials_kernel<<<(unsigned)ceil_div(len, 256), 256, 0, stream>>>(part, nparts, len, out);
+    return check_launch("reduce_partials");
+}
+
+int gmp_edge_length_fwd(const float* pos, const int64_t* src, const int64_t* dst, int64_t num_edges, float* dist,
+                        gmp_stream_t stream) {
+    GMP_REQUIRE(num_edges == 0 || (pos && src && dst && dist), "edge_length_fwd: bad arguments");
+    if (num_edges == 0) return GMP_OK;
+    edge_length_kernel<<<(unsigned)ceil_div(num_edges, 256), 256, 0, stream>>>(pos, src, dst, num_edges, dist);
+    return check_launch("edge_length_kernel");
+}
+
+int gmp_edge_length_bwd(const float* pos, const int64_t* src, const int64_t* dst, const float* g_dist,
+                        const int32_t* rowptr_s, const int32_t* perm_s, const int32_t* rowptr_d, const int32_t* perm_d,
+                        int64_t n, float* dpos, gmp_stream_t stream) {
+    GMP_REQUIRE(pos && src && dst && g_dist && rowptr_s && rowptr_d && dpos, "edge_length_bwd: bad arguments");
+    if (n == 0) return GMP_OK;
+    edge_length_bwd_kernel<<<(unsigned)ceil_div(n, 128), 128, 0, stream>>>(pos, src, dst, g_dist, rowptr_s, perm_s, rowptr_d, perm_d, n, dpos);
+    return check_launch("edge_length_bwd_kernel");
+}
+
+}  // extern "C"

@@ -1,0 +1,172 @@
+"""Graph construction and CSR views on the GPU (host side of csrc/graph.cu).
+
+``radius_graph`` mirrors ``torch_cluster.radius_graph`` (argument names, canonical CUDA edge order,
+``max_num_neighbors`` truncation); the reference never calls it (models/schnet.py:66-72 bypasses
+PyG's interaction graph) but BASELINE.json's north star requires it bit-exact.
+
+``CSR`` is the destination-sorted view every fused layer aggregates over: edges stably sorted by
+their aggregation index, so the segmented reduction is deterministic and needs no atomics
+(replaces torch_scatter's atomicAdd at models/layers/egnn_layer.py:77,79 and tfn_layer.py:87).
+"""
+from __future__ import annotations
+
+import weakref
+from dataclasses import dataclass
+from typing import Dict, Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import call, ptr
+
+
+def _i32(n, device):
+    return torch.empty(n, dtype=torch.int32, device=device)
+
+
+def exclusive_scan(counts: torch.Tensor) -> torch.Tensor:
+    """int32[n] -> int64[n+1] exclusive prefix sum on the GPU."""
+    n = counts.numel()
+    out = torch.empty(n + 1, dtype=torch.int64, device=counts.device)
+    ws = torch.empty((n + 1023) // 1024 + 1, dtype=torch.int64, device=counts.device)
+    call("gmp_exclusive_scan_i32", ptr(counts), n, ptr(out), ptr(ws))
+    return out
+
+
+def radius_graph(x: torch.Tensor, r: float, batch: Optional[torch.Tensor] = None, loop: bool = False,
+                 max_num_neighbors: int = 32, flow: str = "source_to_target",
+                 method: str = "auto") -> torch.Tensor:
+    """edge_index [2, E] int64 = [src; dst], dst-major, src ascending (torch_cluster CUDA order).
+
+    method: "brute" scans each example in index order (torch_cluster's own algorithm);
+            "cells" uses a uniform cell list (single example only; same output bit for bit);
+            "auto" picks cells for one example with more than 4096 nodes."""
+    assert flow == "source_to_target"
+    assert x.dim() == 2 and x.shape[1] == 3 and x.dtype == torch.float32, "pos must be float32 [N,3]"
+    x = x.contiguous()
+    n, dev = x.shape[0], x.device
+    if batch is None:
+        gptr = torch.tensor([0, n], dtype=torch.int64, device=dev)
+        ngraphs = 1
+    else:
+        assert batch.numel() == n
+        ngraphs = int(batch.max().item()) + 1 if n else 1
+        counts = torch.bincount(batch, minlength=ngraphs)
+        gptr = torch.zeros(ngraphs + 1, dtype=torch.int64, device=dev)
+        gptr[1:] = torch.cumsum(counts, 0)
+    if method == "auto":
+        method = "cells" if (ngraphs == 1 and n > 4096) else "brute"
+    deg = _i32(n, dev)
+    if method == "brute":
+        call("gmp_radius_graph_count", ptr(x), ptr(gptr), ngraphs, n, float(r), max_num_neighbors, int(loop), ptr(deg))
+        rowptr = exclusive_scan(deg)
+        E = int(rowptr[-1].item())
+        ei = torch.empty(2, E, dtype=torch.int64, device=dev)
+        if E:
+            call("gmp_radius_graph_fill", ptr(x), ptr(gptr), ngraphs, n, float(r), max_num_neighbors, int(loop),
+                 ptr(rowptr), ptr(ei[0]), ptr(ei[1]))
+        return ei
+    assert ngraphs == 1, "the cell-list path handles a single example"
+    import ctypes as C
+    lo = x.min(dim=0).values.cpu()
+    hi = x.max(dim=0).values.cpu()
+    cell = float(r) * 1.0001  # > r so that fp rounding of the cell coordinate can never hide a neighbour
+    dims = [max(1, int((float(hi[k]) - float(lo[k])) / cell) + 1) for k in range(3)]
+    origin = (C.c_float * 3)(*[float(v) for v in lo])
+    cdims = (C.c_int32 * 3)(*dims)
+    ncells = dims[0] * dims[1] * dims[2]
+    cell_of, cell_nodes = _i32(n, dev), _i32(n, dev)
+    cell_start, cursor = _i32(ncells + 1, dev), _i32(ncells, dev)
+    call("gmp_cells_build", ptr(x), n, cell, origin, cdims, ptr(cell_of), ptr(cell_start), ptr(cell_nodes), ptr(cursor))
+    call("gmp_radius_cells_count", ptr(x), n, float(r), cell, origin, cdims, ptr(cell_start), ptr(cell_nodes),
+         max_num_neighbors, int(loop), ptr(deg))
+    rowptr = exclusive_scan(deg)
+    E = int(rowptr[-1].item())
+    ei = torch.empty(2, E, dtype=torch.int64, device=dev)
+    if E:
+        call("gmp_radius_cells_fill", ptr(x), n, float(r), cell, origin, cdims, ptr(cell_start), ptr(cell_nodes),
+             max_num_neighbors, int(loop), ptr(rowptr), ptr(ei[0]), ptr(ei[1]))
+    return ei
+
+
+@dataclass
+class CSR:
+    """Edges stably sorted by `index` (the aggregation side); `col` is the other endpoint."""
+    rowptr: torch.Tensor          # int32 [n+1]
+    col: torch.Tensor             # int32 [E]   gather-side node of sorted edge k
+    perm: Optional[torch.Tensor]  # int32 [E]   position of sorted edge k in the caller's edge order (None = identity)
+    n: int
+    E: int
+
+    @property
+    def perm_ptr(self):
+        return ptr(self.perm)
+
+    def row_ids(self) -> torch.Tensor:
+        """int32[E]: aggregation row of each sorted edge."""
+        deg = (self.rowptr[1:] - self.rowptr[:-1]).long()
+        return torch.repeat_interleave(torch.arange(self.n, device=self.rowptr.device, dtype=torch.int32), deg)
+
+
+def build_csr(index: torch.Tensor, other: torch.Tensor, n: int) -> CSR:
+    """Stable counting sort of the edges by `index` (int64[E]); `other` is the opposite endpoint."""
+    assert index.dtype == torch.int64 and other.dtype == torch.int64
+    index, other = index.contiguous(), other.contiguous()
+    E, dev = index.numel(), index.device
+    counts = _i32(max(n, 1), dev)
+    call("gmp_csr_count", ptr(index), E, n, ptr(counts))
+    rowptr = exclusive_scan(counts[:n]).to(torch.int32)
+    flag = _i32(1, dev)
+    call("gmp_index_is_sorted", ptr(index), E, ptr(flag))
+    col = _i32(E, dev)
+    if int(flag.item()) == 1:
+        perm = None
+    else:
+        perm, tmp, cursor = _i32(E, dev), _i32(E, dev), _i32(max(n, 1), dev)
+        call("gmp_csr_fill", ptr(index), E, n, ptr(rowptr), ptr(cursor), ptr(tmp), ptr(perm))
+    call("gmp_gather_i64_to_i32", ptr(other), ptr(perm), E, ptr(col))
+    return CSR(rowptr, col, perm, n, E)
+
+
+class Graph:
+    """Both sorted views of one edge_index, built lazily and cached per edge_index tensor.
+
+    by_dst: rows = edge_index[1] (EGNN / SchNet aggregate here, PyG flow source_to_target)
+    by_src: rows = edge_index[0] (TFN / MACE aggregate here, models/layers/tfn_layer.py:83-87;
+            also the transposed pass of the EGNN / SchNet backward)."""
+
+    def __init__(self, edge_index: torch.Tensor, n: int):
+        assert edge_index.dim() == 2 and edge_index.shape[0] == 2 and edge_index.dtype == torch.int64
+        self.edge_index = edge_index.contiguous()
+        self.n = n
+        self.E = edge_index.shape[1]
+        self._by_dst: Optional[CSR] = None
+        self._by_src: Optional[CSR] = None
+
+    @property
+    def by_dst(self) -> CSR:
+        if self._by_dst is None:
+            self._by_dst = build_csr(self.edge_index[1], self.edge_index[0], self.n)
+        return self._by_dst
+
+    @property
+    def by_src(self) -> CSR:
+        if self._by_src is None:
+            self._by_src = build_csr(self.edge_index[0], self.edge_index[1], self.n)
+        return self._by_src
+
+
+_GRAPH_CACHE: Dict[Tuple, Graph] = {}
+
+
+def get_graph(edge_index: torch.Tensor, n: int) -> Graph:
+    """Graph for this edge_index, cached on (storage pointer, shape, version, n) so that the layers of a
+    model, which all receive the same tensor, sort it once."""
+    key = (edge_index.data_ptr(), tuple(edge_index.shape), edge_index._version, n, str(edge_index.device))
+    g = _GRAPH_CACHE.get(key)
+    if g is None or g.edge_index.data_ptr() != edge_index.contiguous().data_ptr():
+        if len(_GRAPH_CACHE) > 16:
+            _GRAPH_CACHE.clear()
+        g = Graph(edge_index, n)
+        _GRAPH_CACHE[key] = g
+    return g

@@ -1,0 +1,234 @@
+"""SchNet on the fused CFConv kernels: drop-in for ``models/schnet.py`` and the PyG 2.3.1 blocks it
+instantiates (``InteractionBlock``, ``CFConv``, ``GaussianSmearing``, ``ShiftedSoftplus``).
+
+Constructor arguments, attribute names and ``state_dict`` keys equal the reference's, so a reference
+checkpoint loads unchanged.  The per-edge filter ``W_e = mlp(rbf_e) * C(d_e)`` and the message
+``x1[src] * W_e`` are produced and reduced inside one kernel (csrc/schnet.cu); nothing per-edge
+except the scalar distance is ever stored.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Optional
+
+import torch
+from torch import nn
+from torch.nn import Embedding, Linear, ModuleList, Sequential
+
+from . import _lib
+from ._lib import SchnetFilter, call, ptr
+from .graph import Graph, get_graph
+from .scatter import scatter
+
+_PREC = {"fp32": _lib.FP32_STRICT, "bf16": _lib.BF16_TC}
+
+
+class ShiftedSoftplus(nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.shift = math.log(2.0)
+
+    def forward(self, x):
+        return torch.nn.functional.softplus(x) - self.shift
+
+
+class SmearedDistance:
+    """Marker passed as ``edge_attr``: 'the Gaussian expansion of edge_weight by this module'.
+    Lets InteractionBlock recompute the 50 RBF values in-kernel (4 B/edge) instead of reading a
+    materialised [E,50] tensor (200 B/edge) -- same numbers, the layer API is unchanged."""
+
+    def __init__(self, smearing: "GaussianSmearing"):
+        self.smearing = smearing
+
+
+class GaussianSmearing(nn.Module):
+    def __init__(self, start: float = 0.0, stop: float = 5.0, num_gaussians: int = 50):
+        super().__init__()
+        offset = torch.linspace(start, stop, num_gaussians)
+        self.coeff = -0.5 / (offset[1] - offset[0]).item() ** 2
+        self.register_buffer("offset", offset)
+
+    def forward(self, dist):
+        dist = dist.view(-1, 1) - self.offset.view(1, -1)
+        return torch.exp(self.coeff * torch.pow(dist, 2))
+
+    def lazy(self) -> SmearedDistance:
+        return SmearedDistance(self)
+
+
+class _EdgeLength(torch.autograd.Function):
+    """d_e = ||pos[row_e] - pos[col_e]||  (models/schnet.py:66-67) with an atomics-free backward."""
+
+    @staticmethod
+    def forward(ctx, pos, graph: Graph):
+        pos = pos.contiguous()
+        ei = graph.edge_index
+        d = torch.empty(graph.E, dtype=pos.dtype, device=pos.device)
+        call("gmp_edge_length_fwd", ptr(pos), ptr(ei[0]), ptr(ei[1]), graph.E, ptr(d))
+        ctx.graph = graph
+        ctx.save_for_backward(pos)
+        return d
+
+    @staticmethod
+    def backward(ctx, g):
+        (pos,) = ctx.saved_tensors
+        graph: Graph = ctx.graph
+        ei, s, d = graph.edge_index, graph.by_src, graph.by_dst
+        dpos = torch.empty_like(pos)
+        call("gmp_edge_length_bwd", ptr(pos), ptr(ei[0]), ptr(ei[1]), ptr(g.contiguous()), ptr(s.rowptr), s.perm_ptr,
+             ptr(d.rowptr), d.perm_ptr, graph.n, ptr(dpos))
+        return dpos, None
+
+
+def edge_length(pos: torch.Tensor, graph: Graph) -> torch.Tensor:
+    return _EdgeLength.apply(pos, graph)
+
+
+class _CFConvFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x1, edge_weight, edge_attr, w1, b1, w2, b2, graph: Graph, cutoff, offset, coeff, precision):
+        x1, edge_weight = x1.contiguous(), edge_weight.contiguous()
+        edge_attr = None if edge_attr is None else edge_attr.contiguous()
+        w1, b1, w2, b2 = (t.contiguous() for t in (w1, b1, w2, b2))
+        filt = SchnetFilter(ptr(w1), ptr(b1), ptr(w2), ptr(b2), w1.shape[1], w1.shape[0], float(cutoff),
+                            ptr(offset), float(coeff))
+        csr = graph.by_dst
+        agg = torch.empty(graph.n, w1.shape[0], dtype=x1.dtype, device=x1.device)
+        call("gmp_schnet_cfconv_fwd", ptr(csr.rowptr), ptr(csr.col), csr.perm_ptr, graph.n, graph.E, ptr(edge_weight),
+             ptr(edge_attr), ptr(x1), C.byref(filt), ptr(agg), precision)
+        ctx.save_for_backward(x1, edge_weight, edge_attr if edge_attr is not None else x1.new_empty(0), w1, b1, w2, b2, offset)
+        ctx.graph, ctx.meta, ctx.has_attr = graph, (float(cutoff), float(coeff), precision), edge_attr is not None
+        return agg
+
+    @staticmethod
+    def backward(ctx, g):
+        x1, ew, ea, w1, b1, w2, b2, offset = ctx.saved_tensors
+        ea = ea if ctx.has_attr else None
+        graph: Graph = ctx.graph
+        cutoff, coeff, precision = ctx.meta
+        g = g.contiguous()
+        F, G = w1.shape
+        filt = SchnetFilter(ptr(w1), ptr(b1), ptr(w2), ptr(b2), G, F, cutoff, ptr(offset), coeff)
+        need = ctx.needs_input_grad
+        dx1 = None
+        if need[0]:
+            # d agg / d x1 is the same fused op over the transposed (src-sorted) CSR with g in place of x1
+            t = graph.by_src
+            dx1 = torch.empty_like(x1)
+            call("gmp_schnet_cfconv_fwd", ptr(t.rowptr), ptr(t.col), t.perm_ptr, graph.n, graph.E, ptr(ew), ptr(ea),
+                 ptr(g), C.byref(filt), ptr(dx1), precision)
+        csr = graph.by_dst
+        lib = _lib.lib()
+        nparts, plen = lib.gmp_schnet_bwd_num_parts(graph.E), lib.gmp_schnet_bwd_part_len(G, F)
+        parts = torch.empty(nparts, plen, dtype=g.dtype, device=g.device)
+        d_ew = torch.zeros_like(ew) if need[1] else None
+        d_ea = torch.zeros_like(ea) if (need[2] and ea is not None) else None
+        call("gmp_schnet_cfconv_bwd", ptr(csr.rowptr), ptr(csr.col), csr.perm_ptr, graph.n, graph.E, ptr(ew), ptr(ea),
+             ptr(x1), C.byref(filt), ptr(g), ptr(parts), ptr(d_ew), ptr(d_ea), precision)
+        red = torch.empty(plen, dtype=g.dtype, device=g.device)
+        call("gmp_reduce_partials_f32", ptr(parts), nparts, plen, ptr(red))
+        o = 0
+        dw1 = red[o:o + F * 64].view(F, 64)[:, :G].contiguous(); o += F * 64
+        db1 = red[o:o + F]; o += F
+        dw2 = red[o:o + F * F].view(F, F); o += F * F
+        db2 = red[o:o + F]
+        return dx1, d_ew, d_ea, dw1, db1, dw2, db2, None, None, None, None, None
+
+
+class CFConv(nn.Module):
+    """PyG ``CFConv`` (aggr='add', flow source_to_target): gather x1[edge_index[0]], reduce at edge_index[1]."""
+
+    def __init__(self, in_channels, out_channels, num_filters, nn_, cutoff, precision: str = "fp32"):
+        super().__init__()
+        self.lin1 = Linear(in_channels, num_filters, bias=False)
+        self.lin2 = Linear(num_filters, out_channels)
+        self.nn = nn_
+        self.cutoff = cutoff
+        self.precision = precision
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        torch.nn.init.xavier_uniform_(self.lin1.weight)
+        torch.nn.init.xavier_uniform_(self.lin2.weight)
+        self.lin2.bias.data.fill_(0)
+
+    def forward(self, x, edge_index, edge_weight, edge_attr):
+        graph = get_graph(edge_index, x.shape[0])
+        x1 = self.lin1(x)
+        lin_a, lin_b = self.nn[0], self.nn[2]
+        if isinstance(edge_attr, SmearedDistance):
+            sm = edge_attr.smearing
+            attr, offset, coeff = None, sm.offset, sm.coeff
+        else:
+            attr, offset, coeff = edge_attr, x1.new_zeros(1), 0.0
+        agg = _CFConvFn.apply(x1, edge_weight, attr, lin_a.weight, lin_a.bias, lin_b.weight, lin_b.bias, graph,
+                              self.cutoff, offset, coeff, _PREC[self.precision])
+        return self.lin2(agg)
+
+
+class InteractionBlock(nn.Module):
+    def __init__(self, hidden_channels, num_gaussians, num_filters, cutoff, precision: str = "fp32"):
+        super().__init__()
+        self.mlp = Sequential(Linear(num_gaussians, num_filters), ShiftedSoftplus(), Linear(num_filters, num_filters))
+        self.conv = CFConv(hidden_channels, hidden_channels, num_filters, self.mlp, cutoff, precision)
+        self.act = ShiftedSoftplus()
+        self.lin = Linear(hidden_channels, hidden_channels)
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        torch.nn.init.xavier_uniform_(self.mlp[0].weight)
+        self.mlp[0].bias.data.fill_(0)
+        torch.nn.init.xavier_uniform_(self.mlp[2].weight)
+        self.mlp[2].bias.data.fill_(0)
+        self.conv.reset_parameters()
+        torch.nn.init.xavier_uniform_(self.lin.weight)
+        self.lin.bias.data.fill_(0)
+
+    def forward(self, x, edge_index, edge_weight, edge_attr):
+        x = self.conv(x, edge_index, edge_weight, edge_attr)
+        x = self.act(x)
+        return self.lin(x)
+
+
+def global_add_pool(x, batch, size: Optional[int] = None):
+    size = int(batch.max().item()) + 1 if size is None else size
+    return scatter(x, batch, dim=0, dim_size=size, reduce="sum")
+
+
+def global_mean_pool(x, batch, size: Optional[int] = None):
+    size = int(batch.max().item()) + 1 if size is None else size
+    return scatter(x, batch, dim=0, dim_size=size, reduce="mean")
+
+
+class SchNetModel(nn.Module):
+    """models/schnet.py:9-80 (a PyG ``SchNet`` subclass there); same constructor, attributes and forward(batch)."""
+
+    def __init__(self, hidden_channels: int = 128, in_dim: int = 1, out_dim: int = 1, num_filters: int = 128,
+                 num_layers: int = 6, num_gaussians: int = 50, cutoff: float = 10, max_num_neighbors: int = 32,
+                 pool: str = "sum", precision: str = "fp32"):
+        super().__init__()
+        self.hidden_channels, self.num_filters = hidden_channels, num_filters
+        self.num_interactions, self.num_gaussians, self.cutoff = num_layers, num_gaussians, cutoff
+        self.embedding = Embedding(100, hidden_channels, padding_idx=0)
+        self.distance_expansion = GaussianSmearing(0.0, cutoff, num_gaussians)
+        self.interactions = ModuleList(
+            [InteractionBlock(hidden_channels, num_gaussians, num_filters, cutoff, precision) for _ in range(num_layers)])
+        self.lin1 = Linear(hidden_channels, hidden_channels // 2)
+        self.act = ShiftedSoftplus()
+        torch.nn.init.xavier_uniform_(self.lin1.weight)
+        self.lin1.bias.data.fill_(0)
+        self.pool = {"mean": global_mean_pool, "sum": global_add_pool}[pool]
+        self.lin2 = Linear(hidden_channels // 2, out_dim)
+
+    def forward(self, batch):
+        h = self.embedding(batch.atoms)
+        graph = get_graph(batch.edge_index, h.shape[0])
+        edge_weight = edge_length(batch.pos, graph)
+        edge_attr = self.distance_expansion.lazy()
+        for interaction in self.interactions:
+            h = h + interaction(h, batch.edge_index, edge_weight, edge_attr)
+        out = self.pool(h, batch.batch)
+        out = self.lin1(out)
+        out = self.act(out)
+        return self.lin2(out)

@@ -1,0 +1,180 @@
+/* gmp_b200.h -- C ABI of the B200-native geometric message-passing core (libgmp_b200.so).
+ *
+ * This is the drop-in boundary for the hot path of NW-JEFF/Geometric-Message-Passing
+ * (per-edge geometric message + scatter-sum aggregation inside the EGNN / SchNet / TFN / MACE
+ * layers).  The reference has no FFI of its own: the native arithmetic on this path is reached
+ * through third-party wheels.  Each entry point below names the reference call site (file:line
+ * under /root/reference) whose third-party call it replaces.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless marked "host";
+ *   - no allocation inside the library: callers pass outputs and workspaces;
+ *   - all work is enqueued on `stream` (a cudaStream_t); nothing synchronises unless documented;
+ *   - return value: GMP_OK (0) or a negative gmp_status; gmp_last_error() gives the message;
+ *   - "CSR" = (rowptr int32[n+1], col int32[E], perm int32[E]): edges stably sorted by their
+ *     aggregation index; col[k] is the gather-side node of sorted edge k, perm[k] its position in
+ *     the caller's original edge_index.  Aggregation is a deterministic, atomics-free segmented
+ *     reduction over this order.
+ *   - fp32 row-major tensors; nn.Linear weights keep PyTorch's [out_features, in_features] layout.
+ */
+#ifndef GMP_B200_H
+#define GMP_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st* gmp_stream_t; /* == cudaStream_t */
+
+enum gmp_status {
+    GMP_OK = 0,
+    GMP_ERR_INVALID_ARGUMENT = -1,
+    GMP_ERR_CUDA = -2,
+    GMP_ERR_UNSUPPORTED = -3
+};
+
+/* precision modes of the fused edge kernels */
+enum gmp_precision {
+    GMP_FP32_STRICT = 0, /* fp32 FFMA on CUDA cores: matches the reference layers to 1e-5 relative */
+    GMP_BF16_TC = 1      /* bf16 operands on tcgen05 tensor cores, fp32 accumulate in TMEM: 1e-2 relative */
+};
+
+int gmp_version(void);
+const char* gmp_last_error(void); /* host string, valid until the next failing call on this thread */
+
+/* ============================================================================================ */
+/* Graph construction (integer path, bit-exact)                                                  */
+/* ============================================================================================ */
+
+/* torch_cluster.radius_graph in its CUDA canonical order (never called by the reference itself --
+ * models/schnet.py:66-72 bypasses PyG's RadiusInteractionGraph -- but required by BASELINE.json).
+ * One query per node, candidates scanned in ascending index order inside the node's own example,
+ * fp32 squared distance accumulated x,y,z with FMA contraction, strict `<  r*r`, at most
+ * max_num_neighbors (+1 when loop == 0, for the self match) hits kept, self loops then dropped.
+ * Two phases so that the caller can size the edge list:
+ *   count: deg[i]  = number of edges whose destination is i
+ *   fill : writes edge_src / edge_dst (int64, dst-major, src ascending) using rowptr = exclusive
+ *          scan of deg (rowptr[n] = E).
+ * graph_ptr: int64[num_graphs+1], node ranges of the examples (batch must be sorted). */
+int gmp_radius_graph_count(const float* pos, const int64_t* graph_ptr, int64_t num_graphs, int64_t n,
+                           float r, int32_t max_num_neighbors, int32_t loop, int32_t* deg,
+                           gmp_stream_t stream);
+int gmp_radius_graph_fill(const float* pos, const int64_t* graph_ptr, int64_t num_graphs, int64_t n,
+                          float r, int32_t max_num_neighbors, int32_t loop, const int64_t* rowptr,
+                          int64_t* edge_src, int64_t* edge_dst, gmp_stream_t stream);
+
+/* Same result for ONE large example (BASELINE config 5) through a uniform cell list of edge >= r.
+ * cell_of int32[n] and cell_start int32[ncells+1] / cell_nodes int32[n] are produced by
+ * gmp_cells_build; origin/dims are host arrays (dims[0]*dims[1]*dims[2] = ncells).
+ * max_num_neighbors semantics are identical (lowest indices first), so the output equals the
+ * brute-force entry points bit for bit. */
+int gmp_cells_build(const float* pos, int64_t n, float cell, const float* origin_host, const int32_t* dims_host,
+                    int32_t* cell_of, int32_t* cell_start, int32_t* cell_nodes, int32_t* cursor_ws,
+                    gmp_stream_t stream);
+int gmp_radius_cells_count(const float* pos, int64_t n, float r, float cell, const float* origin_host,
+                           const int32_t* dims_host, const int32_t* cell_start, const int32_t* cell_nodes,
+                           int32_t max_num_neighbors, int32_t loop, int32_t* deg, gmp_stream_t stream);
+int gmp_radius_cells_fill(const float* pos, int64_t n, float r, float cell, const float* origin_host,
+                          const int32_t* dims_host, const int32_t* cell_start, const int32_t* cell_nodes,
+                          int32_t max_num_neighbors, int32_t loop, const int64_t* rowptr,
+                          int64_t* edge_src, int64_t* edge_dst, gmp_stream_t stream);
+
+/* exclusive prefix sum, int32 -> int64, out has n+1 entries (out[n] = total). ws: int64[ceil(n/1024)+1]. */
+int gmp_exclusive_scan_i32(const int32_t* in, int64_t n, int64_t* out, int64_t* ws, gmp_stream_t stream);
+
+/* Stable counting sort of edges by an int64 index (replaces the implicit ordering torch_scatter's
+ * atomics ignore: models/layers/egnn_layer.py:77,79; models/layers/tfn_layer.py:87).
+ *   count : counts[i] = #edges with index == i                  (counts must hold n int32)
+ *   fill  : perm = stable argsort(index)  given rowptr = exclusive scan of counts (int32[n+1]);
+ *           cursor_ws int32[n], tmp_ws int32[E] are scratch.
+ *   gather_i64_to_i32: out[k] = (int32) src[perm[k]]   (builds `col` from the other edge_index row)
+ *   is_sorted: *flag (device int32) = 1 iff index is non-decreasing. */
+int gmp_csr_count(const int64_t* index, int64_t num_edges, int64_t n, int32_t* counts, gmp_stream_t stream);
+int gmp_csr_fill(const int64_t* index, int64_t num_edges, int64_t n, const int32_t* rowptr, int32_t* cursor_ws,
+                 int32_t* tmp_ws, int32_t* perm, gmp_stream_t stream);
+int gmp_gather_i64_to_i32(const int64_t* src, const int32_t* perm, int64_t num_edges, int32_t* out,
+                          gmp_stream_t stream);
+int gmp_index_is_sorted(const int64_t* index, int64_t num_edges, int32_t* flag, gmp_stream_t stream);
+
+/* ============================================================================================ */
+/* Segmented reductions (torch_scatter.scatter / scatter_sum)                      */
+/* ============================================================================================ */
+
+/* out[r,:] = reduce_{k in [rowptr[r], rowptr[r+1])} src[perm ? perm[k] : k, :]     reduce = sum | mean.
+ * Rows without edges are written as zeros (dim_size = n semantics).  F % 4 == 0.
+ * Replaces torch_scatter.scatter at models/layers/egnn_layer.py:77,79,147 and tfn_layer.py:87. */
+int gmp_segment_reduce_f32(const int32_t* rowptr, const int32_t* perm, const float* src, float* out,
+                           int64_t n, int32_t F, int32_t mean, gmp_stream_t stream);
+
+/* K0: out[r,:] = sum_k x[col[k],:] * (w ? w[perm ? perm[k] : k, :] : 1).  The CFConv message with a
+ * materialised filter (PyG CFConv.message, called at models/schnet.py:72).  F % 4 == 0. */
+int gmp_gather_mul_segsum_f32(const int32_t* rowptr, const int32_t* col, const int32_t* perm, const float* x,
+                              const float* w, float* out, int64_t n, int32_t F, gmp_stream_t stream);
+
+/* out[k,:] = x[idx[k],:]  (backward of the reductions above; PyG propagate's index_select). */
+int gmp_gather_rows_f32(const int32_t* idx, const float* x, float* out, int64_t num_rows, int32_t F,
+                        gmp_stream_t stream);
+
+/* deterministic sum of `nparts` partial buffers of `len` floats each: out[i] = sum_p part[p*len+i]. */
+int gmp_reduce_partials_f32(const float* part, int32_t nparts, int64_t len, float* out, gmp_stream_t stream);
+
+/* Edge lengths and their backward (models/schnet.py:66-67; models/tfn.py:171-172):
+ *   fwd: dist[e] = || pos[src[e]] - pos[dst[e]] ||_2            (edge order of the caller)
+ *   bwd: dpos[i] = sum_{e: src=i} g[e] u_e - sum_{e: dst=i} g[e] u_e,  u_e = (pos_src-pos_dst)/dist
+ *        through the two CSRs (rows = src with perm_s, rows = dst with perm_d); no atomics. */
+int gmp_edge_length_fwd(const float* pos, const int64_t* src, const int64_t* dst, int64_t num_edges, float* dist,
+                        gmp_stream_t stream);
+int gmp_edge_length_bwd(const float* pos, const int64_t* src, const int64_t* dst, const float* g_dist,
+                        const int32_t* rowptr_s, const int32_t* perm_s, const int32_t* rowptr_d,
+                        const int32_t* perm_d, int64_t n, float* dpos, gmp_stream_t stream);
+
+/* ============================================================================================ */
+/* SchNet continuous-filter convolution (PyG InteractionBlock/CFConv called at models/schnet.py:72)*/
+/* ============================================================================================ */
+typedef struct gmp_schnet_filter {
+    const float* w1; /* [F, G]   mlp.0.weight */
+    const float* b1; /* [F]      mlp.0.bias   */
+    const float* w2; /* [F, F]   mlp.2.weight */
+    const float* b2; /* [F]      mlp.2.bias   */
+    int32_t num_gaussians; /* G <= 64 */
+    int32_t num_filters;   /* F in {64, 128} */
+    float cutoff;          /* C(d) = 0.5 (cos(d pi / cutoff) + 1), no mask (PyG CFConv) */
+    /* GaussianSmearing: rbf_k = exp(gauss_coeff * (d - gauss_offset[k])^2), gauss_offset = device float[G]
+     * (the module's `offset` buffer, so the fp32 linspace values are the reference's own).
+     * Used only when edge_attr == NULL (the fused path recomputes the expansion from d). */
+    const float* gauss_offset;
+    float gauss_coeff;
+} gmp_schnet_filter;
+
+/* agg[r,:] = sum_{k in row r} x1[col[k],:] * ( (ssp(rbf_k W1^T + b1) W2^T + b2) * C(d_k) )
+ *   edge_weight: float[E] distances in the caller's edge order (read through perm)
+ *   edge_attr  : float[E,G] in the caller's edge order, or NULL to recompute the Gaussian expansion
+ * Per-edge filters never touch HBM.  Calling it with the transposed CSR and the output gradient in
+ * place of x1 yields the gradient w.r.t. x1 (the message is symmetric in the two factors). */
+int gmp_schnet_cfconv_fwd(const int32_t* rowptr, const int32_t* col, const int32_t* perm, int64_t n,
+                          int64_t num_edges, const float* edge_weight, const float* edge_attr, const float* x1,
+                          const gmp_schnet_filter* filt /* host */, float* agg, int32_t precision,
+                          gmp_stream_t stream);
+
+/* number of partial-gradient slots (CTAs) gmp_schnet_cfconv_bwd writes for E edges */
+int32_t gmp_schnet_bwd_num_parts(int64_t num_edges);
+/* floats per slot: F*64 + F + F*F + F  (dW1 padded to 64 columns | db1 | dW2 | db2) */
+int64_t gmp_schnet_bwd_part_len(int32_t num_gaussians, int32_t num_filters);
+
+/* Filter-side backward over the dst-sorted CSR given g_agg = dL/dagg [n,F]:
+ *   wgrad_parts[p] : per-CTA partial sums of (dW1 [F,Gp], db1 [F], dW2 [F,F], db2 [F]); reduce with
+ *                    gmp_reduce_partials_f32 (deterministic).
+ *   d_edge_weight  : float[E] (caller's edge order) or NULL;  d_edge_attr: float[E,G] or NULL
+ *                    (when edge_attr == NULL the chain through the Gaussian expansion is folded into
+ *                    d_edge_weight instead). */
+int gmp_schnet_cfconv_bwd(const int32_t* rowptr, const int32_t* col, const int32_t* perm, int64_t n,
+                          int64_t num_edges, const float* edge_weight, const float* edge_attr, const float* x1,
+                          const gmp_schnet_filter* filt /* host */, const float* g_agg, float* wgrad_parts,
+                          float* d_edge_weight, float* d_edge_attr, int32_t precision, gmp_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GMP_B200_H */

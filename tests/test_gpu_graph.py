@@ -1,0 +1,108 @@
+"""GPU: graph construction and CSR sort, bit-exact against the numpy oracle (integer path)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle.thirdparty import cluster
+
+pytestmark = pytest.mark.gpu
+
+
+def _cloud(n, box, seed):
+    g = torch.Generator().manual_seed(seed)
+    return torch.rand(n, 3, generator=g) * box
+
+
+def _margin_ok(pos, batch, r, ulps=8):
+    """No pair within a few ulp of r^2: then the edge set cannot depend on rounding conventions."""
+    p = pos.numpy()
+    ok = True
+    for b in np.unique(batch):
+        q = p[batch == b]
+        d = cluster.sqdist_f32(q[None], q[:, None])
+        ok &= not np.any(np.abs(d - np.float32(r * r)) <= ulps * np.spacing(np.float32(r * r)))
+    return ok
+
+
+@pytest.mark.parametrize("graphs,nodes,box,r,maxnb", [(8, 32, 8.0, 5.0, 32), (4, 64, 4.0, 2.0, 64), (1, 1, 1.0, 1.0, 4),
+                                                      (3, 50, 2.0, 1.9, 8), (6, 20, 3.0, 1.0, 32)])
+def test_radius_graph_bruteforce_bit_exact(graphs, nodes, box, r, maxnb):
+    import gmp_b200
+    pos = _cloud(graphs * nodes, box, 7)
+    batch = torch.arange(graphs).repeat_interleave(nodes)
+    assert _margin_ok(pos, batch.numpy(), r)
+    ref = cluster.radius_graph(pos.numpy(), r, batch.numpy(), False, maxnb)
+    got = gmp_b200.radius_graph(pos.cuda(), r, batch.cuda(), max_num_neighbors=maxnb, method="brute")
+    assert got.dtype == torch.int64 and np.array_equal(got.cpu().numpy(), ref)
+    ref_l = cluster.radius_graph(pos.numpy(), r, batch.numpy(), True, maxnb)
+    got_l = gmp_b200.radius_graph(pos.cuda(), r, batch.cuda(), loop=True, max_num_neighbors=maxnb, method="brute")
+    assert np.array_equal(got_l.cpu().numpy(), ref_l)
+
+
+@pytest.mark.parametrize("n,box,r,maxnb", [(3000, 10.0, 1.0, 64), (2500, 6.0, 1.0, 8), (500, 1.5, 1.0, 128)])
+def test_radius_graph_cells_equals_bruteforce(n, box, r, maxnb):
+    import gmp_b200
+    pos = _cloud(n, box, 11)
+    ref = cluster.radius_graph(pos.numpy(), r, None, False, maxnb)
+    got = gmp_b200.radius_graph(pos.cuda(), r, None, max_num_neighbors=maxnb, method="cells")
+    brute = gmp_b200.radius_graph(pos.cuda(), r, None, max_num_neighbors=maxnb, method="brute")
+    assert torch.equal(got, brute)
+    assert np.array_equal(got.cpu().numpy(), ref)
+
+
+def test_radius_graph_empty_and_isolated():
+    import gmp_b200
+    pos = torch.tensor([[0.0, 0, 0], [10.0, 0, 0], [20.0, 0, 0]]).cuda()
+    ei = gmp_b200.radius_graph(pos, 1.0, None)
+    assert ei.shape == (2, 0)
+
+
+@pytest.mark.parametrize("E,n,seed", [(0, 5, 0), (1, 1, 1), (1000, 37, 2), (5000, 4000, 3), (4096, 3, 4)])
+def test_csr_stable_sort_bit_exact(E, n, seed):
+    import gmp_b200
+    g = torch.Generator().manual_seed(seed)
+    idx = torch.randint(0, n, (E,), generator=g)
+    other = torch.randint(0, n, (E,), generator=g)
+    rowptr, perm = cluster.csr_from_coo(idx.numpy(), n)
+    csr = gmp_b200.build_csr(idx.cuda(), other.cuda(), n)
+    assert np.array_equal(csr.rowptr.cpu().numpy(), rowptr)
+    got_perm = np.arange(E, dtype=np.int32) if csr.perm is None else csr.perm.cpu().numpy()
+    assert np.array_equal(got_perm, perm)
+    assert np.array_equal(csr.col.cpu().numpy(), other.numpy()[perm].astype(np.int32))
+    # size-independent property: sortedness + permutation
+    assert np.all(np.diff(idx.numpy()[got_perm]) >= 0) and np.array_equal(np.sort(got_perm), np.arange(E))
+
+
+def test_csr_sorted_input_is_identity():
+    import gmp_b200
+    pos = _cloud(256, 4.0, 5).cuda()
+    ei = gmp_b200.radius_graph(pos, 1.2, None)
+    g = gmp_b200.get_graph(ei, 256)
+    assert g.by_dst.perm is None  # radius_graph output is already dst-major
+    s = g.by_src
+    # symmetric graph: the src-sorted view has the same row structure
+    assert torch.equal(s.rowptr, g.by_dst.rowptr) and torch.equal(s.col, g.by_dst.col)
+
+
+@pytest.mark.parametrize("F,reduce", [(128, "sum"), (64, "mean"), (3, "mean"), (1, "sum"), (576, "sum")])
+def test_scatter_matches_oracle(F, reduce):
+    import gmp_b200
+    from oracle.thirdparty.scatter import scatter as oscatter
+    g = torch.Generator().manual_seed(F)
+    E, n = 3000, 257
+    idx = torch.randint(0, n - 5, (E,), generator=g)  # last rows empty -> zeros with dim_size
+    src = torch.randn(E, F, generator=g)
+    ref = oscatter(src.double(), idx, dim=0, dim_size=n, reduce=reduce)
+    s = src.cuda().requires_grad_(True)
+    out = gmp_b200.scatter(s, idx.cuda(), dim=0, dim_size=n, reduce=reduce)
+    assert out.shape == (n, F)
+    assert (out.detach().cpu().double() - ref).abs().max() <= 1e-5 * max(1.0, ref.abs().max().item())
+    out2 = gmp_b200.scatter(s, idx.cuda(), dim=0, dim_size=n, reduce=reduce)
+    assert torch.equal(out, out2)  # deterministic, bit for bit
+    cot = torch.randn(n, F, generator=g)
+    (gs,) = torch.autograd.grad((out * cot.cuda()).sum(), s)
+    sr = src.double().requires_grad_(True)
+    (gr,) = torch.autograd.grad((oscatter(sr, idx, dim=0, dim_size=n, reduce=reduce) * cot.double()).sum(), sr)
+    assert (gs.cpu().double() - gr).abs().max() <= 1e-6 * max(1.0, gr.abs().max().item())
+    # no dim_size: rows = index.max()+1 (torch_scatter semantics)
+    assert gmp_b200.scatter(s, idx.cuda(), dim=0, reduce=reduce).shape[0] == int(idx.max()) + 1
