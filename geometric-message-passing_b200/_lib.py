@@ -16,7 +16,14 @@ LIB_PATH = os.path.join(_PKG, "libgmp_b200.so")
 FP32_STRICT, BF16_TC = 0, 1
 
 _lib = None
-launches = 0  # number of C-ABI compute calls issued (bench.py reports kernels from here)
+launches = 0  # number of C-ABI compute calls issued
+_kernels = 0  # number of CUDA kernels those calls launched (bench.py's gpu_launches)
+# kernels launched per entry point (default 1); memsets are not counted
+_KERNELS_PER_CALL = {"gmp_exclusive_scan_i32": 3, "gmp_csr_fill": 2, "gmp_cells_build": 3}
+
+
+def kernel_launches() -> int:
+    return _kernels
 
 P, I32, I64, F32 = C.c_void_p, C.c_int32, C.c_int64, C.c_float
 
@@ -93,9 +100,10 @@ def stream():
 
 def call(name: str, *args):
     """Invoke a status-returning entry point on the current torch stream; raise on failure."""
-    global launches
+    global launches, _kernels
     l = lib()
     rc = getattr(l, name)(*args, stream())
     launches += 1
+    _kernels += _KERNELS_PER_CALL.get(name, 1)
     if rc != 0:
         raise GmpError(f"{name} failed ({rc}): {l.gmp_last_error().decode()}")

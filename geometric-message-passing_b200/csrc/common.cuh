@@ -75,40 +75,40 @@ __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-
 
 // ---------------------------------------------------------------------------------------------
 // 64-row SIMT tile GEMMs for 256-thread CTAs.  All operands live in shared memory, fp32.
-//   thread (tx = tid & 15, ty = tid >> 4) owns rows ty*4 + i (i < 4) and CPT = NCOL/16 columns.
+//   thread (tx = tid & 15, ty = tid >> 4) owns rows ty*RPT + i (i < RPT; tile = 16*RPT rows) and
+//   CPT = NCOL/16 columns.
 //   K must be a multiple of 4 and every row start 16-byte aligned.
 // ---------------------------------------------------------------------------------------------
-template <int NCOL>
+template <int NCOL, int RPT = 4>
 struct Frag {
     static constexpr int CPT = NCOL / 16;
-    float v[4][CPT];
+    static constexpr int ROWS = 16 * RPT;  // rows of the tile
+    float v[RPT][CPT];
     __device__ __forceinline__ void zero() {
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
+        for (int i = 0; i < RPT; ++i)
 #pragma unroll
             for (int j = 0; j < CPT; ++j) v[i][j] = 0.f;
     }
 };
 
 // column owned by slot j:  NT layout -> tx + 16 j ;  NN layout -> 4*tx + (j&3) + 64*(j>>2)
-template <int NCOL> __device__ __forceinline__ int col_nt(int tx, int j) { return tx + 16 * j; }
-template <int NCOL> __device__ __forceinline__ int col_nn(int tx, int j) { return 4 * tx + (j & 3) + 64 * (j >> 2); }
 
 // C[r][c] += sum_k A[r][k] * B[c][k]          (B is [NCOL][K], K contiguous: nn.Linear weight layout)
-template <int NCOL>
-__device__ __forceinline__ void gemm_nt(Frag<NCOL>& acc, const float* __restrict__ A, int lda,
+template <int NCOL, int RPT>
+__device__ __forceinline__ void gemm_nt(Frag<NCOL, RPT>& acc, const float* __restrict__ A, int lda,
                                         const float* __restrict__ B, int ldb, int K) {
-    constexpr int CPT = Frag<NCOL>::CPT;
+    constexpr int CPT = Frag<NCOL, RPT>::CPT;
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-    const float* a0 = A + (ty * 4) * lda;
+    const float* a0 = A + (ty * RPT) * lda;
     for (int k = 0; k < K; k += 4) {
-        float4 a[4], b[CPT];
+        float4 a[RPT], b[CPT];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) a[i] = *reinterpret_cast<const float4*>(a0 + i * lda + k);
+        for (int i = 0; i < RPT; ++i) a[i] = *reinterpret_cast<const float4*>(a0 + i * lda + k);
 #pragma unroll
         for (int j = 0; j < CPT; ++j) b[j] = *reinterpret_cast<const float4*>(B + (tx + 16 * j) * ldb + k);
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
+        for (int i = 0; i < RPT; ++i)
 #pragma unroll
             for (int j = 0; j < CPT; ++j) {
                 acc.v[i][j] = fmaf(a[i].x, b[j].x, acc.v[i][j]);
@@ -120,17 +120,17 @@ __device__ __forceinline__ void gemm_nt(Frag<NCOL>& acc, const float* __restrict
 }
 
 // C[r][c] += sum_k A[r][k] * B[k][c]          (B is [K][NCOL], NCOL contiguous)
-template <int NCOL>
-__device__ __forceinline__ void gemm_nn(Frag<NCOL>& acc, const float* __restrict__ A, int lda,
+template <int NCOL, int RPT>
+__device__ __forceinline__ void gemm_nn(Frag<NCOL, RPT>& acc, const float* __restrict__ A, int lda,
                                         const float* __restrict__ B, int ldb, int K) {
-    constexpr int CPT = Frag<NCOL>::CPT;
+    constexpr int CPT = Frag<NCOL, RPT>::CPT;
     static_assert(CPT % 4 == 0, "gemm_nn needs NCOL multiple of 64");
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-    const float* a0 = A + (ty * 4) * lda;
+    const float* a0 = A + (ty * RPT) * lda;
     for (int k = 0; k < K; k += 4) {
-        float4 a[4];
+        float4 a[RPT];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) a[i] = *reinterpret_cast<const float4*>(a0 + i * lda + k);
+        for (int i = 0; i < RPT; ++i) a[i] = *reinterpret_cast<const float4*>(a0 + i * lda + k);
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk) {
             float4 b[CPT / 4];
@@ -138,7 +138,7 @@ __device__ __forceinline__ void gemm_nn(Frag<NCOL>& acc, const float* __restrict
             for (int q = 0; q < CPT / 4; ++q)
                 b[q] = *reinterpret_cast<const float4*>(B + (k + kk) * ldb + 4 * tx + 64 * q);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
+            for (int i = 0; i < RPT; ++i) {
                 const float av = kk == 0 ? a[i].x : kk == 1 ? a[i].y : kk == 2 ? a[i].z : a[i].w;
 #pragma unroll
                 for (int q = 0; q < CPT / 4; ++q) {
@@ -152,23 +152,23 @@ __device__ __forceinline__ void gemm_nn(Frag<NCOL>& acc, const float* __restrict
     }
 }
 
-template <int NCOL>
-__device__ __forceinline__ void store_nt(const Frag<NCOL>& acc, float* __restrict__ C, int ldc) {
+template <int NCOL, int RPT>
+__device__ __forceinline__ void store_nt(const Frag<NCOL, RPT>& acc, float* __restrict__ C, int ldc) {
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < RPT; ++i)
 #pragma unroll
-        for (int j = 0; j < Frag<NCOL>::CPT; ++j) C[(ty * 4 + i) * ldc + tx + 16 * j] = acc.v[i][j];
+        for (int j = 0; j < Frag<NCOL, RPT>::CPT; ++j) C[(ty * RPT + i) * ldc + tx + 16 * j] = acc.v[i][j];
 }
 
-template <int NCOL>
-__device__ __forceinline__ void store_nn(const Frag<NCOL>& acc, float* __restrict__ C, int ldc) {
+template <int NCOL, int RPT>
+__device__ __forceinline__ void store_nn(const Frag<NCOL, RPT>& acc, float* __restrict__ C, int ldc) {
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < RPT; ++i)
 #pragma unroll
-        for (int q = 0; q < Frag<NCOL>::CPT / 4; ++q)
-            *reinterpret_cast<float4*>(C + (ty * 4 + i) * ldc + 4 * tx + 64 * q) =
+        for (int q = 0; q < Frag<NCOL, RPT>::CPT / 4; ++q)
+            *reinterpret_cast<float4*>(C + (ty * RPT + i) * ldc + 4 * tx + 64 * q) =
                 make_float4(acc.v[i][4 * q], acc.v[i][4 * q + 1], acc.v[i][4 * q + 2], acc.v[i][4 * q + 3]);
 }
 

@@ -76,7 +76,7 @@ def test_csr_stable_sort_bit_exact(E, n, seed):
 def test_csr_sorted_input_is_identity():
     import gmp_b200
     pos = _cloud(256, 4.0, 5).cuda()
-    ei = gmp_b200.radius_graph(pos, 1.2, None)
+    ei = gmp_b200.radius_graph(pos, 1.2, None, max_num_neighbors=128)  # no truncation -> symmetric
     g = gmp_b200.get_graph(ei, 256)
     assert g.by_dst.perm is None  # radius_graph output is already dst-major
     s = g.by_src
