@@ -16,4 +16,6 @@ from .scatter import scatter, scatter_mean, scatter_sum, segment_reduce  # noqa:
 from .schnet import (CFConv, GaussianSmearing, InteractionBlock, SchNetModel, ShiftedSoftplus,  # noqa: F401
                      edge_length, global_add_pool, global_mean_pool)
 
+from .egnn import EGNNLayer, EGNNModel, MPNNLayer  # noqa: F401
+
 __version__ = "0.1.0"

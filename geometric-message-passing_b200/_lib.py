@@ -33,6 +33,11 @@ class SchnetFilter(C.Structure):
                 ("cutoff", F32), ("gauss_offset", P), ("gauss_coeff", F32)]
 
 
+class EgnnParams(C.Structure):
+    _fields_ = [(k, P) for k in ("wd", "ln1_g", "ln1_b", "w1", "b1", "ln2_g", "ln2_b", "w2", "b2", "ln3_g", "ln3_b",
+                                 "w3", "b3")] + [("d", I32), ("act", I32), ("ln_eps", F32), ("aggr_mean", I32)]
+
+
 _SIGS = {
     "gmp_radius_graph_count": [P, P, I64, I64, F32, I32, I32, P, P],
     "gmp_radius_graph_fill": [P, P, I64, I64, F32, I32, I32, P, P, P, P],
@@ -52,9 +57,12 @@ _SIGS = {
     "gmp_edge_length_bwd": [P, P, P, P, P, P, P, P, I64, P, P],
     "gmp_schnet_cfconv_fwd": [P, P, P, I64, I64, P, P, P, P, P, I32, P],
     "gmp_schnet_cfconv_bwd": [P, P, P, I64, I64, P, P, P, P, P, P, P, P, I32, P],
+    "gmp_egnn_edge_fwd": [P, P, I64, I64, P, P, P, P, P, P, I32, P],
+    "gmp_egnn_edge_bwd": [P, P, P, I64, I64, P, P, P, P, P, P, I32, P, P, P, I32, P],
 }
 _PLAIN = {"gmp_version": (I32, []), "gmp_last_error": (C.c_char_p, []),
-          "gmp_schnet_bwd_num_parts": (I32, [I64]), "gmp_schnet_bwd_part_len": (I64, [I32, I32])}
+          "gmp_schnet_bwd_num_parts": (I32, [I64]), "gmp_schnet_bwd_part_len": (I64, [I32, I32]),
+          "gmp_egnn_bwd_num_parts": (I32, [I64]), "gmp_egnn_bwd_part_len": (I64, [I32])}
 
 
 def exported_symbols():

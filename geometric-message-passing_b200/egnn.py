@@ -1,0 +1,167 @@
+"""EGNN on the fused edge kernel: drop-in for ``models/layers/egnn_layer.py`` and ``models/egnn.py``.
+
+Same constructor arguments, attribute names and ``state_dict`` keys as the reference modules.  The
+edge side (gather, relative vector and distance, the three LayerNorm'd edge Linears, coordinate
+scaling, sum / mean aggregation) is one kernel forward and two recompute passes backward
+(csrc/egnn.cu); the node side (``mlp_upd``, the two halves of ``mlp_msg``'s first Linear) is plain
+library GEMMs with autograd.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+from torch import nn
+from torch.nn import Linear, ReLU, Sequential, SiLU
+from torch.nn import functional as F
+
+from . import _lib
+from ._lib import EgnnParams, GmpError, call, ptr
+from .graph import Graph, get_graph
+from .scatter import scatter, segment_reduce
+from .schnet import global_add_pool, global_mean_pool
+
+_PREC = {"fp32": _lib.FP32_STRICT, "bf16": _lib.BF16_TC}
+
+
+def _params_struct(tensors, d, act, eps, aggr_mean):
+    return EgnnParams(*[ptr(t) for t in tensors], d, act, eps, aggr_mean)
+
+
+class _EGNNEdgeFn(torch.autograd.Function):
+    """(P, Q, pos, 13 edge-MLP tensors) -> (msg_aggr [N,d], pos_aggr [N,3])."""
+
+    @staticmethod
+    def forward(ctx, P, Q, pos, graph: Graph, act: int, eps: float, aggr_mean: int, precision: int, *w):
+        P, Q, pos = P.contiguous(), Q.contiguous(), pos.contiguous()
+        w = tuple(t.contiguous() for t in w)
+        d = P.shape[1]
+        prm = _params_struct(w, d, act, eps, aggr_mean)
+        csr = graph.by_dst
+        msg = torch.empty(graph.n, d, dtype=P.dtype, device=P.device)
+        pag = torch.empty(graph.n, 3, dtype=P.dtype, device=P.device)
+        call("gmp_egnn_edge_fwd", ptr(csr.rowptr), ptr(csr.col), graph.n, graph.E, ptr(P), ptr(Q), ptr(pos),
+             C.byref(prm), ptr(msg), ptr(pag), precision)
+        ctx.save_for_backward(P, Q, pos, *w)
+        ctx.graph, ctx.meta = graph, (act, eps, aggr_mean, precision)
+        return msg, pag
+
+    @staticmethod
+    def backward(ctx, g_msg, g_pos):
+        P, Q, pos, *w = ctx.saved_tensors
+        graph: Graph = ctx.graph
+        act, eps, aggr_mean, precision = ctx.meta
+        d = P.shape[1]
+        g_msg, g_pos = g_msg.contiguous(), g_pos.contiguous()
+        prm = _params_struct(w, d, act, eps, aggr_mean)
+        lib = _lib.lib()
+        nparts, plen = lib.gmp_egnn_bwd_num_parts(graph.E), lib.gmp_egnn_bwd_part_len(d)
+        parts = torch.empty(nparts, plen, dtype=P.dtype, device=P.device)
+        dP, dQ = torch.empty_like(P), torch.empty_like(Q)
+        dpos_i, dpos_j = torch.empty_like(pos), torch.empty_like(pos)
+        cd, cs = graph.by_dst, graph.by_src
+        call("gmp_egnn_edge_bwd", ptr(cd.rowptr), ptr(cd.col), ptr(cd.rowptr), graph.n, graph.E, ptr(P), ptr(Q), ptr(pos),
+             C.byref(prm), ptr(g_msg), ptr(g_pos), 0, ptr(dP), ptr(dpos_i), ptr(parts), precision)
+        call("gmp_egnn_edge_bwd", ptr(cs.rowptr), ptr(cs.col), ptr(cd.rowptr), graph.n, graph.E, ptr(P), ptr(Q), ptr(pos),
+             C.byref(prm), ptr(g_msg), ptr(g_pos), 1, ptr(dQ), ptr(dpos_j), None, precision)
+        red = torch.empty(plen, dtype=P.dtype, device=P.device)
+        call("gmp_reduce_partials_f32", ptr(parts), nparts, plen, ptr(red))
+        dd = d * d
+        vec = red[2 * dd:]
+        v = lambda k: vec[k * d:(k + 1) * d]
+        # order of *w: wd, ln1_g, ln1_b, w1, b1, ln2_g, ln2_b, w2, b2, ln3_g, ln3_b, w3, b3
+        grads_w = (v(9), v(2), v(3), red[:dd].view(d, d), v(0), v(4), v(5), red[dd:2 * dd].view(d, d), v(1), v(6), v(7),
+                   v(8).view_as(w[11]), vec[10 * d:10 * d + 1].view_as(w[12]))
+        return (dP, dQ, dpos_i + dpos_j, None, None, None, None, None, *grads_w)
+
+
+class EGNNLayer(nn.Module):
+    """E(n) Equivariant GNN layer (models/layers/egnn_layer.py:7-89)."""
+
+    def __init__(self, emb_dim, activation="relu", norm="layer", aggr="add", precision: str = "fp32"):
+        super().__init__()
+        if norm != "layer":
+            raise NotImplementedError("gmp_b200.EGNNLayer fuses LayerNorm; norm='batch' needs statistics over all "
+                                      "edges before the second Linear and is not built (DESIGN.md, out of scope)")
+        if aggr not in ("add", "sum", "mean"):
+            raise NotImplementedError(f"aggr={aggr!r}: the fused reduction implements add/sum/mean")
+        self.emb_dim, self.aggr, self.precision = emb_dim, aggr, precision
+        self._act_id = {"relu": 0, "swish": 1}[activation]
+        self.activation = {"swish": SiLU(), "relu": ReLU()}[activation]
+        self.norm = torch.nn.LayerNorm
+        self.mlp_msg = Sequential(Linear(2 * emb_dim + 1, emb_dim), self.norm(emb_dim), self.activation,
+                                  Linear(emb_dim, emb_dim), self.norm(emb_dim), self.activation)
+        self.mlp_pos = Sequential(Linear(emb_dim, emb_dim), self.norm(emb_dim), self.activation, Linear(emb_dim, 1))
+        self.mlp_upd = Sequential(Linear(2 * emb_dim, emb_dim), self.norm(emb_dim), self.activation,
+                                  Linear(emb_dim, emb_dim), self.norm(emb_dim), self.activation)
+
+    def forward(self, h, pos, edge_index):
+        d = self.emb_dim
+        graph = get_graph(edge_index, h.shape[0])
+        lin0 = self.mlp_msg[0]
+        W0 = lin0.weight
+        P = F.linear(h, W0[:, :d], lin0.bias)          # h_i half (+ bias)
+        Q = F.linear(h, W0[:, d:2 * d])                # h_j half
+        wd = W0[:, 2 * d]                              # distance column
+        ln1, lin1, ln2 = self.mlp_msg[1], self.mlp_msg[3], self.mlp_msg[4]
+        lin2, ln3, lin3 = self.mlp_pos[0], self.mlp_pos[1], self.mlp_pos[3]
+        msg_aggr, pos_aggr = _EGNNEdgeFn.apply(
+            P, Q, pos, graph, self._act_id, float(ln1.eps), int(self.aggr == "mean"), _PREC[self.precision],
+            wd, ln1.weight, ln1.bias, lin1.weight, lin1.bias, ln2.weight, ln2.bias, lin2.weight, lin2.bias,
+            ln3.weight, ln3.bias, lin3.weight, lin3.bias)
+        upd_out = self.mlp_upd(torch.cat([h, msg_aggr], dim=-1))
+        return upd_out, pos + pos_aggr
+
+    def __repr__(self) -> str:
+        return f"{self.__class__.__name__}(emb_dim={self.emb_dim}, aggr={self.aggr})"
+
+
+class MPNNLayer(nn.Module):
+    """Vanilla message-passing layer (models/layers/egnn_layer.py:92-155): the same scatter without geometry.
+    Not fused (a by-product of the EGNN path): node rows are gathered, the MLP is library GEMMs, the
+    aggregation is the deterministic segmented reduction."""
+
+    def __init__(self, emb_dim, activation="relu", norm="layer", aggr="add"):
+        super().__init__()
+        self.emb_dim, self.aggr = emb_dim, aggr
+        act = {"swish": SiLU(), "relu": ReLU()}[activation]
+        nrm = {"layer": torch.nn.LayerNorm, "batch": torch.nn.BatchNorm1d}[norm]
+        self.mlp_msg = Sequential(Linear(2 * emb_dim, emb_dim), nrm(emb_dim), act, Linear(emb_dim, emb_dim), nrm(emb_dim), act)
+        self.mlp_upd = Sequential(Linear(2 * emb_dim, emb_dim), nrm(emb_dim), act, Linear(emb_dim, emb_dim), nrm(emb_dim), act)
+
+    def forward(self, h, edge_index):
+        graph = get_graph(edge_index, h.shape[0])
+        msg = self.mlp_msg(torch.cat([h[edge_index[1]], h[edge_index[0]]], dim=-1))
+        aggr = segment_reduce(msg, graph.by_dst, self.aggr)
+        return self.mlp_upd(torch.cat([h, aggr], dim=-1))
+
+
+class EGNNModel(nn.Module):
+    """models/egnn.py:8-87."""
+
+    def __init__(self, num_layers: int = 5, emb_dim: int = 128, in_dim: int = 1, out_dim: int = 1,
+                 activation: str = "relu", norm: str = "layer", aggr: str = "sum", pool: str = "sum",
+                 residual: bool = True, equivariant_pred: bool = False, precision: str = "fp32"):
+        super().__init__()
+        self.equivariant_pred, self.residual = equivariant_pred, residual
+        self.emb_in = torch.nn.Embedding(in_dim, emb_dim)
+        self.convs = torch.nn.ModuleList([EGNNLayer(emb_dim, activation, norm, aggr, precision) for _ in range(num_layers)])
+        self.pool = {"mean": global_mean_pool, "sum": global_add_pool}[pool]
+        if equivariant_pred:
+            self.pred = torch.nn.Linear(emb_dim + 3, out_dim)
+        else:
+            self.pred = torch.nn.Sequential(torch.nn.Linear(emb_dim, emb_dim), torch.nn.ReLU(),
+                                            torch.nn.Linear(emb_dim, out_dim))
+
+    def forward(self, batch):
+        h = self.emb_in(batch.atoms)
+        pos = batch.pos
+        for conv in self.convs:
+            h_update, pos_update = conv(h, pos, batch.edge_index)
+            h = h + h_update if self.residual else h_update
+            pos = pos_update
+        if not self.equivariant_pred:
+            out = self.pool(h, batch.batch)
+        else:
+            out = self.pool(torch.cat([h, pos], dim=-1), batch.batch)
+        return self.pred(out)

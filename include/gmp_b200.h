@@ -174,6 +174,52 @@ int gmp_schnet_cfconv_bwd(const int32_t* rowptr, const int32_t* col, const int32
                           const gmp_schnet_filter* filt /* host */, const float* g_agg, float* wgrad_parts,
                           float* d_edge_weight, float* d_edge_attr, int32_t precision, gmp_stream_t stream);
 
+/* ============================================================================================ */
+/* EGNN edge path (models/layers/egnn_layer.py:62-80: message + aggregate, fused)                 */
+/* ============================================================================================ */
+typedef struct gmp_egnn_edge_params {
+    const float* wd;    /* [d]    mlp_msg.0.weight[:, 2d]   (the distance column of the first Linear) */
+    const float* ln1_g; /* [d]    mlp_msg.1.weight */
+    const float* ln1_b; /* [d]    mlp_msg.1.bias   */
+    const float* w1;    /* [d,d]  mlp_msg.3.weight */
+    const float* b1;    /* [d]    mlp_msg.3.bias   */
+    const float* ln2_g; /* [d]    mlp_msg.4.weight */
+    const float* ln2_b; /* [d]    mlp_msg.4.bias   */
+    const float* w2;    /* [d,d]  mlp_pos.0.weight */
+    const float* b2;    /* [d]    mlp_pos.0.bias   */
+    const float* ln3_g; /* [d]    mlp_pos.1.weight */
+    const float* ln3_b; /* [d]    mlp_pos.1.bias   */
+    const float* w3;    /* [d]    mlp_pos.3.weight (shape [1,d]) */
+    const float* b3;    /* [1]    mlp_pos.3.bias   */
+    int32_t d;          /* emb_dim in {64, 128} */
+    int32_t act;        /* 0 = relu, 1 = swish (SiLU) */
+    float ln_eps;       /* LayerNorm eps (1e-5) */
+    int32_t aggr_mean;  /* message aggregation: 0 = sum/add, 1 = mean (coordinates always use mean) */
+} gmp_egnn_edge_params;
+
+/* P = h W0[:, :d]^T + b0 and Q = h W0[:, d:2d]^T are the two node-side halves of mlp_msg's first Linear
+ * (cat[h_i, h_j, dist] is never built).  CSR rows = edge_index[1] (i), col = edge_index[0] (j).
+ *   msg_aggr[i,:] = reduce_e m_e ,  pos_aggr[i,:] = mean_e (pos_i - pos_j) * mlp_pos(m_e)            */
+int gmp_egnn_edge_fwd(const int32_t* rowptr, const int32_t* col, int64_t n, int64_t num_edges, const float* P,
+                      const float* Q, const float* pos, const gmp_egnn_edge_params* prm /* host */,
+                      float* msg_aggr, float* pos_aggr, int32_t precision, gmp_stream_t stream);
+
+int32_t gmp_egnn_bwd_num_parts(int64_t num_edges);
+/* floats per slot: dW1 d*d | dW2 d*d | db1 | db2 | dln1_g | dln1_b | dln2_g | dln2_b | dln3_g | dln3_b | dw3 | dwd
+ * (d each) | db3 (1) | 3 pad  = 2 d^2 + 10 d + 4 */
+int64_t gmp_egnn_bwd_part_len(int32_t d);
+
+/* Backward of gmp_egnn_edge_fwd given g_msg = dL/dmsg_aggr [n,d] and g_pos = dL/dpos_aggr [n,3]; the
+ * forward is recomputed per tile.  Run it twice:
+ *   src_pass = 0: (rowptr, col) = dst-sorted CSR -> d_node = dL/dP, d_pos = the pos_i part, wgrad_parts
+ *   src_pass = 1: (rowptr, col) = src-sorted CSR (rows j, col i) -> d_node = dL/dQ, d_pos = the pos_j part
+ * dst_rowptr is always the dst-sorted rowptr (in-degrees for the mean).  dL/dpos = sum of both d_pos. */
+int gmp_egnn_edge_bwd(const int32_t* rowptr, const int32_t* col, const int32_t* dst_rowptr, int64_t n,
+                      int64_t num_edges, const float* P, const float* Q, const float* pos,
+                      const gmp_egnn_edge_params* prm /* host */, const float* g_msg, const float* g_pos,
+                      int32_t src_pass, float* d_node, float* d_pos, float* wgrad_parts, int32_t precision,
+                      gmp_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
