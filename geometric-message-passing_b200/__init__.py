@@ -17,5 +17,8 @@ from .schnet import (CFConv, GaussianSmearing, InteractionBlock, SchNetModel, Sh
                      edge_length, global_add_pool, global_mean_pool)
 
 from .egnn import EGNNLayer, EGNNModel, MPNNLayer  # noqa: F401
+from .irreps import Irreps  # noqa: F401
+from .tfn import (BatchNorm, Gate, RadialEmbeddingBlock, SphericalHarmonics, TensorProductConvLayer,  # noqa: F401
+                  TensorProductPlan, TFNModel, edge_geometry, first_node_pooling)
 
 __version__ = "0.1.0"

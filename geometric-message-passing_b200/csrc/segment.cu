@@ -130,6 +130,45 @@ __global__ void edge_length_bwd_kernel(const float* __restrict__ pos, const int6
     dpos[3 * i] = ax; dpos[3 * i + 1] = ay; dpos[3 * i + 2] = az;
 }
 
+// TFN / MACE edge prologue (models/tfn.py:171-175): relative vector, length, real spherical harmonics
+// (e3nn 'component' normalisation, unit-normalised direction, l <= 2) and Bessel x polynomial-cutoff radial basis.
+__global__ void edge_geometry_kernel(const float* __restrict__ pos, const int64_t* __restrict__ src,
+                                     const int64_t* __restrict__ dst, int64_t E, int lmax, float r_max, int nb, float p,
+                                     float* __restrict__ sh, float* __restrict__ rbf) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= E) return;
+    const int64_t a = src[e], b = dst[e];
+    const float vx = pos[3 * a] - pos[3 * b], vy = pos[3 * a + 1] - pos[3 * b + 1], vz = pos[3 * a + 2] - pos[3 * b + 2];
+    const float len = sqrtf(vx * vx + vy * vy + vz * vz);
+    const float inv = 1.0f / fmaxf(len, 1e-12f);  // F.normalize
+    const float x = vx * inv, y = vy * inv, z = vz * inv;
+    const int S = (lmax + 1) * (lmax + 1);
+    float* o = sh + e * S;
+    o[0] = 1.0f;
+    if (lmax >= 1) {
+        const float s3 = 1.7320508075688772f;
+        o[1] = s3 * x; o[2] = s3 * y; o[3] = s3 * z;
+    }
+    if (lmax >= 2) {
+        const float s3 = 1.7320508075688772f, s5 = 2.23606797749979f;
+        const float x2z2 = x * x + z * z;
+        o[4] = s5 * (s3 * x * z);
+        o[5] = s5 * (s3 * x * y);
+        o[6] = s5 * (y * y - 0.5f * x2z2);
+        o[7] = s5 * (s3 * y * z);
+        o[8] = s5 * ((s3 / 2.0f) * (z * z - x * x));
+    }
+    const float u = len / r_max;
+    const float env = 1.0f - ((p + 1.0f) * (p + 2.0f) / 2.0f) * powf(u, p) + p * (p + 2.0f) * powf(u, p + 1.0f) -
+                      (p * (p + 1.0f) / 2.0f) * powf(u, p + 2.0f);
+    const float cut = len < r_max ? env : 0.0f;
+    const float pref = sqrtf(2.0f / r_max);
+    for (int k = 0; k < nb; ++k) {
+        const float w = (3.14159265358979323846f / r_max) * (float)(k + 1);
+        rbf[e * nb + k] = pref * (sinf(w * len) / len) * cut;
+    }
+}
+
 }  // namespace gmp
 
 using namespace gmp;
@@ -179,6 +218,18 @@ int gmp_edge_length_fwd(const float* pos, const int64_t* src, const int64_t* dst
     if (num_edges == 0) return GMP_OK;
     edge_length_kernel<<<(unsigned)ceil_div(num_edges, 256), 256, 0, stream>>>(pos, src, dst, num_edges, dist);
     return check_launch("edge_length_kernel");
+}
+
+int gmp_edge_geometry_fwd(const float* pos, const int64_t* src, const int64_t* dst, int64_t num_edges, int32_t max_ell,
+                          float r_max, int32_t num_bessel, float poly_p, float* edge_sh, float* edge_feat,
+                          gmp_stream_t stream) {
+    GMP_REQUIRE(num_edges == 0 || (pos && src && dst && edge_sh && edge_feat), "edge_geometry_fwd: bad arguments");
+    GMP_REQUIRE(max_ell >= 0 && max_ell <= 2, "edge_geometry_fwd: max_ell must be <= 2 (got %d)", max_ell);
+    GMP_REQUIRE(num_bessel >= 1 && r_max > 0.f, "edge_geometry_fwd: bad radial basis");
+    if (num_edges == 0) return GMP_OK;
+    edge_geometry_kernel<<<(unsigned)ceil_div(num_edges, 256), 256, 0, stream>>>(pos, src, dst, num_edges, max_ell, r_max,
+                                                                               num_bessel, poly_p, edge_sh, edge_feat);
+    return check_launch("edge_geometry_kernel");
 }
 
 int gmp_edge_length_bwd(const float* pos, const int64_t* src, const int64_t* dst, const float* g_dist,

@@ -1,0 +1,422 @@
+"""TFN / MACE tensor-product convolution on the fused kernels: drop-in for
+``models/layers/tfn_layer.py`` (``TensorProductConvLayer``), ``models/tfn.py`` (``TFNModel``) and the e3nn
+pieces they instantiate (``FullyConnectedTensorProduct`` with per-edge weights, ``Gate``, ``BatchNorm``,
+``SphericalHarmonics``), plus ``RadialEmbeddingBlock`` (models/mace_modules/blocks.py:84-96).
+
+``fc(edge_feat)`` -- the [E, weight_numel] tensor that dominates the reference layer -- is generated slice by
+slice in shared memory and consumed in place (csrc/tpconv.cu).  Irreps arguments may be e3nn ``Irreps`` objects
+or their strings.  ``state_dict`` keys: ``fc.0.*``, ``fc.2.*``, ``batch_norm.{weight,bias,running_mean,running_var}``.
+"""
+from __future__ import annotations
+
+import math
+from typing import List, Optional
+
+import numpy as np
+import torch
+from torch import nn
+from torch.nn import functional as F
+
+from . import _lib
+from ._lib import GmpError, call, ptr
+from .graph import Graph, get_graph
+from .irreps import NORM2MOM, Irreps, TPPath, fctp_paths, gate_split, hidden_irreps, wigner_3j
+from .schnet import global_add_pool, global_mean_pool
+
+_PREC = {"fp32": _lib.FP32_STRICT, "bf16": _lib.BF16_TC}
+_SLICE = 128
+
+
+# ------------------------------------------------------------------------------------------------
+# node-side equivariant non-linearities (elementwise; plain torch ops)
+# ------------------------------------------------------------------------------------------------
+class Gate(nn.Module):
+    """e3nn.nn.Gate with silu scalars / sigmoid gates (models/layers/tfn_layer.py:45-63): input laid out as
+    [scalars | gates | gated]; out = [silu(s) * c_silu | gated_u * sigmoid(gate_u) * c_sigmoid]."""
+
+    def __init__(self, irreps_scalars, irreps_gates, irreps_gated):
+        super().__init__()
+        self.irreps_scalars, self.irreps_gates, self.irreps_gated = Irreps(irreps_scalars), Irreps(irreps_gates), Irreps(irreps_gated)
+        assert self.irreps_gates.num_irreps == self.irreps_gated.num_irreps
+        self.irreps_in = (self.irreps_scalars + self.irreps_gates + self.irreps_gated).simplify()
+        self.irreps_out = (self.irreps_scalars + self.irreps_gated)
+        expand = []
+        g = 0
+        for m, ir in self.irreps_gated:
+            for _ in range(m):
+                expand += [g] * ir.dim
+                g += 1
+        self.register_buffer("_expand", torch.tensor(expand, dtype=torch.long), persistent=False)
+
+    def forward(self, x):
+        ns, ng = self.irreps_scalars.dim, self.irreps_gates.dim
+        s, g, v = x[..., :ns], x[..., ns:ns + ng], x[..., ns + ng:]
+        s = F.silu(s) * NORM2MOM["silu"]
+        if ng == 0:
+            return s
+        g = torch.sigmoid(g) * NORM2MOM["sigmoid"]
+        return torch.cat([s, v * g.index_select(-1, self._expand)], dim=-1)
+
+
+class ScalarActivation(nn.Module):
+    """e3nn.nn.Activation(out_irreps, [silu]) for an all-scalar output (tfn_layer.py:52-53)."""
+
+    def forward(self, x):
+        return F.silu(x) * NORM2MOM["silu"]
+
+
+class BatchNorm(nn.Module):
+    """e3nn.nn.BatchNorm(irreps) (eps 1e-5, momentum 0.1, affine, reduce='mean', 'component').
+    `process_group`: when set (graph-sharded data parallel), batch statistics are all-reduced so that the result
+    equals the single-process reference."""
+
+    def __init__(self, irreps, eps=1e-5, momentum=0.1, affine=True, process_group=None):
+        super().__init__()
+        self.irreps = Irreps(irreps)
+        self.eps, self.momentum, self.affine = eps, momentum, affine
+        self.process_group = process_group
+        num_scalar = sum(m for m, ir in self.irreps if ir.l == 0 and ir.p == 1)
+        num_features = self.irreps.num_irreps
+        self.register_buffer("running_mean", torch.zeros(num_scalar))
+        self.register_buffer("running_var", torch.ones(num_features))
+        if affine:
+            self.weight = nn.Parameter(torch.ones(num_features))
+            self.bias = nn.Parameter(torch.zeros(num_scalar))
+
+    def _mean0(self, t: torch.Tensor, count: int) -> torch.Tensor:
+        """mean over dim 0, across ranks when a process group is attached."""
+        if self.process_group is None:
+            return t.mean(0)
+        import torch.distributed as dist
+        s = t.sum(0)
+        n = torch.tensor([float(count)], device=t.device, dtype=t.dtype)
+        s, n = dist.nn.functional.all_reduce(s, group=self.process_group), dist.nn.functional.all_reduce(n, group=self.process_group)
+        return s / n
+
+    def forward(self, x):
+        B = x.shape[0]
+        new_means, new_vars, fields = [], [], []
+        ix = irm = irv = iw = ib = 0
+        for mul, ir in self.irreps:
+            d = ir.dim
+            field = x[:, ix:ix + mul * d].reshape(B, mul, d)
+            ix += mul * d
+            scalar = ir.l == 0 and ir.p == 1
+            if scalar:
+                if self.training:
+                    mean = self._mean0(field.reshape(B, mul), B)
+                    new_means.append((1 - self.momentum) * self.running_mean[irm:irm + mul] + self.momentum * mean.detach())
+                else:
+                    mean = self.running_mean[irm:irm + mul]
+                irm += mul
+                field = field - mean.reshape(1, mul, 1)
+            if self.training:
+                norm = self._mean0(field.pow(2).mean(2), B)
+                new_vars.append((1 - self.momentum) * self.running_var[irv:irv + mul] + self.momentum * norm.detach())
+            else:
+                norm = self.running_var[irv:irv + mul]
+            irv += mul
+            scale = (norm + self.eps).pow(-0.5)
+            if self.affine:
+                scale = scale * self.weight[iw:iw + mul]
+                iw += mul
+            field = field * scale.reshape(1, mul, 1)
+            if self.affine and scalar:
+                field = field + self.bias[ib:ib + mul].reshape(mul, 1)
+                ib += mul
+            fields.append(field.reshape(B, mul * d))
+        if self.training:
+            with torch.no_grad():
+                if new_means:
+                    self.running_mean.copy_(torch.cat(new_means))
+                self.running_var.copy_(torch.cat(new_vars))
+        return torch.cat(fields, dim=1)
+
+
+# ------------------------------------------------------------------------------------------------
+# edge prologue
+# ------------------------------------------------------------------------------------------------
+class RadialEmbeddingBlock(nn.Module):
+    """models/mace_modules/blocks.py:84-96 (BesselBasis x PolynomialCutoff, radial.py)."""
+
+    def __init__(self, r_max: float, num_bessel: int, num_polynomial_cutoff: int):
+        super().__init__()
+        self.r_max, self.num_bessel, self.p = float(r_max), int(num_bessel), float(num_polynomial_cutoff)
+        self.out_dim = num_bessel
+
+    def forward(self, edge_lengths: torch.Tensor) -> torch.Tensor:  # [E,1] -> [E,num_bessel]
+        x = edge_lengths
+        w = (math.pi / self.r_max) * torch.linspace(1.0, self.num_bessel, self.num_bessel, dtype=x.dtype, device=x.device)
+        bessel = math.sqrt(2.0 / self.r_max) * (torch.sin(w * x) / x)
+        u, p = x / self.r_max, self.p
+        env = (1.0 - ((p + 1.0) * (p + 2.0) / 2.0) * torch.pow(u, p) + p * (p + 2.0) * torch.pow(u, p + 1)
+               - (p * (p + 1.0) / 2) * torch.pow(u, p + 2))
+        return bessel * (env * (x < self.r_max))
+
+
+class SphericalHarmonics(nn.Module):
+    """e3nn.o3.SphericalHarmonics(irreps.spherical_harmonics(l), normalize=True, normalization='component'), l <= 2."""
+
+    def __init__(self, max_ell: int):
+        super().__init__()
+        if max_ell > 2:
+            raise NotImplementedError("spherical harmonics are built for max_ell <= 2 (the BASELINE configs)")
+        self.max_ell = max_ell
+        self.irreps_out = Irreps.spherical_harmonics(max_ell)
+
+    def forward(self, v: torch.Tensor) -> torch.Tensor:
+        v = F.normalize(v, dim=-1)
+        x, y, z = v[..., 0], v[..., 1], v[..., 2]
+        out = [torch.ones_like(x)]
+        if self.max_ell >= 1:
+            s3 = math.sqrt(3.0)
+            out += [s3 * x, s3 * y, s3 * z]
+        if self.max_ell >= 2:
+            s3, s5 = math.sqrt(3.0), math.sqrt(5.0)
+            out += [s5 * s3 * x * z, s5 * s3 * x * y, s5 * (y * y - 0.5 * (x * x + z * z)), s5 * s3 * y * z,
+                    s5 * (s3 / 2.0) * (z * z - x * x)]
+        return torch.stack(out, dim=-1)
+
+
+def edge_geometry(pos: torch.Tensor, edge_index: torch.Tensor, max_ell: int, radial: RadialEmbeddingBlock):
+    """(edge_sh [E,(L+1)^2], edge_feats [E,num_bessel]) in one kernel (models/tfn.py:171-175)."""
+    if pos.requires_grad:
+        raise NotImplementedError("gradients w.r.t. positions through the TFN/MACE edge prologue are not built "
+                                  "(the reference trains without them)")
+    pos, ei = pos.contiguous(), edge_index.contiguous()
+    E = ei.shape[1]
+    sh = torch.empty(E, (max_ell + 1) ** 2, dtype=pos.dtype, device=pos.device)
+    rbf = torch.empty(E, radial.num_bessel, dtype=pos.dtype, device=pos.device)
+    call("gmp_edge_geometry_fwd", ptr(pos), ptr(ei[0]), ptr(ei[1]), E, max_ell, radial.r_max, radial.num_bessel, radial.p,
+         ptr(sh), ptr(rbf))
+    return sh, rbf
+
+
+# ------------------------------------------------------------------------------------------------
+# tensor-product tables
+# ------------------------------------------------------------------------------------------------
+def _pow2_chunk(m: int, cap: int = 64) -> int:
+    c = 1
+    while c * 2 <= cap and m % (c * 2) == 0:
+        c *= 2
+    return c
+
+
+class TensorProductPlan:
+    """Device tables for the contract / wgrad kernels of one FullyConnectedTensorProduct(in, sh, out)."""
+
+    def __init__(self, irreps_in, irreps_sh, irreps_out):
+        self.irreps_in, self.irreps_sh, self.irreps_out = Irreps(irreps_in), Irreps(irreps_sh), Irreps(irreps_out)
+        self.paths, self.weight_numel = fctp_paths(self.irreps_in, self.irreps_sh, self.irreps_out)
+        for p in self.paths:
+            if max(p.l_in, p.l_out) > 2 or p.l_sh > 3:
+                raise NotImplementedError("fused tensor product: irreps up to l = 2 (sh up to l = 3)")
+            if p.mul_in > 128 and _pow2_chunk(p.mul_in) < 8:
+                raise NotImplementedError("fused tensor product: multiplicities need a power-of-two factor >= 8 above 128")
+        cg: List[np.ndarray] = []
+        off = 0
+
+        def add_cg(t: np.ndarray) -> int:
+            nonlocal off
+            cg.append(t.astype(np.float32).reshape(-1))
+            o = off
+            off += t.size
+            return o
+
+        fwd_cg = [add_cg(p.coeff * wigner_3j(p.l_in, p.l_sh, p.l_out)) for p in self.paths]                     # [i][j][k]
+        bwd_cg = [add_cg(p.coeff * wigner_3j(p.l_in, p.l_sh, p.l_out).transpose(2, 1, 0)) for p in self.paths]  # [k][j][i]
+        self.fwd = self._contract_tables(
+            [(m, ir.dim, o) for (m, ir), o in zip(self.irreps_out, self.irreps_out.offsets())],
+            lambda p: p.i_out,
+            lambda p, k: dict(w_off=p.w_off, stride_a=p.mul_out, stride_b=1, MA=p.mul_in, v_off=p.in_off, DA=2 * p.l_in + 1,
+                              sh_off=p.sh_off, DS=2 * p.l_sh + 1, cg_off=fwd_cg[k]))
+        self.bwd = self._contract_tables(
+            [(m, ir.dim, o) for (m, ir), o in zip(self.irreps_in, self.irreps_in.offsets())],
+            lambda p: p.i_in,
+            lambda p, k: dict(w_off=p.w_off, stride_a=1, stride_b=p.mul_out, MA=p.mul_out, v_off=p.out_off, DA=2 * p.l_out + 1,
+                              sh_off=p.sh_off, DS=2 * p.l_sh + 1, cg_off=bwd_cg[k]))
+        units = []
+        for k, p in enumerate(self.paths):
+            rows = p.mul_in * p.mul_out
+            for r0 in range(0, rows, 64):
+                units.append([p.w_off + r0, min(64, rows - r0), r0, p.mul_out, p.in_off, 2 * p.l_in + 1, p.out_off,
+                              2 * p.l_out + 1, p.sh_off, 2 * p.l_sh + 1, fwd_cg[k], 0])
+        self.wunits = np.asarray(units, dtype=np.int32).reshape(-1, 12)
+        self.cg = np.concatenate(cg) if cg else np.zeros(1, np.float32)
+        self._dev = {}
+
+    def _contract_tables(self, blocks, block_of, pass_of):
+        passes, blks, unit = [], [], 0
+        for bi, (MB, DB, r_off) in enumerate(blocks):
+            mine = [(k, p) for k, p in enumerate(self.paths) if block_of(p) == bi]
+            begin = len(passes)
+            mcs = []
+            for k, p in mine:
+                d = pass_of(p, k)
+                MC = _pow2_chunk(d["MA"])
+                mcs.append(MC)
+                for a0 in range(0, d["MA"], MC):
+                    passes.append([d["w_off"], d["stride_a"], d["stride_b"], a0, MC, d["v_off"], d["DA"], d["sh_off"],
+                                   d["DS"], d["cg_off"], 0, 0])
+            WS = max(1, min(16, 80 // DB, _SLICE // max(mcs) if mcs else 16, MB))
+            blks.append([r_off, MB, DB, WS, begin, len(passes), unit, 0])
+            unit += (MB + WS - 1) // WS
+        return dict(passes=np.asarray(passes, dtype=np.int32).reshape(-1, 12), blocks=np.asarray(blks, dtype=np.int32).reshape(-1, 8),
+                    nblocks=len(blks), nunits=unit)
+
+    def device(self, dev):
+        key = str(dev)
+        if key not in self._dev:
+            t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+            self._dev[key] = dict(cg=t(self.cg), wunits=t(self.wunits),
+                                  fwd_passes=t(self.fwd["passes"]), fwd_blocks=t(self.fwd["blocks"]),
+                                  bwd_passes=t(self.bwd["passes"]), bwd_blocks=t(self.bwd["blocks"]))
+        return self._dev[key]
+
+
+class _TPConvFn(torch.autograd.Function):
+    """(node_attr, edge_sh, edge_feat, fc weights) -> sum_{e: edge_index[0][e] = n} TP(node_attr[edge_index[1][e]], sh_e; fc(feat_e))."""
+
+    @staticmethod
+    def forward(ctx, x, edge_sh, edge_feat, w1, b1, w2, b2, graph: Graph, plan: TensorProductPlan, precision: int):
+        x, edge_sh, edge_feat = x.contiguous(), edge_sh.contiguous(), edge_feat.contiguous()
+        w1, b1, w2, b2 = (t.contiguous() for t in (w1, b1, w2, b2))
+        d = plan.device(x.device)
+        csr = graph.by_src  # rows = edge_index[0] (aggregation), col = edge_index[1] (gather)
+        out = torch.empty(graph.n, plan.irreps_out.dim, dtype=x.dtype, device=x.device)
+        H, R, S = w1.shape[0], w1.shape[1], edge_sh.shape[1]
+        call("gmp_tp_contract", ptr(csr.rowptr), ptr(csr.col), csr.perm_ptr, graph.n, graph.E, ptr(x), x.shape[1], ptr(out),
+             out.shape[1], ptr(edge_sh), S, ptr(edge_feat), R, ptr(w1), ptr(b1), ptr(w2), ptr(b2), H, ptr(d["fwd_passes"]),
+             ptr(d["fwd_blocks"]), plan.fwd["nblocks"], plan.fwd["nunits"], ptr(d["cg"]), precision)
+        ctx.save_for_backward(x, edge_sh, edge_feat, w1, b1, w2, b2)
+        ctx.graph, ctx.plan, ctx.precision = graph, plan, precision
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        x, edge_sh, edge_feat, w1, b1, w2, b2 = ctx.saved_tensors
+        graph, plan, precision = ctx.graph, ctx.plan, ctx.precision
+        if ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:
+            raise NotImplementedError("gradients w.r.t. edge_sh / edge_feat are not built into the fused tensor-product "
+                                      "convolution (the reference never needs them: positions carry no gradient)")
+        g = g.contiguous()
+        d = plan.device(x.device)
+        H, R, S = w1.shape[0], w1.shape[1], edge_sh.shape[1]
+        dx = None
+        if ctx.needs_input_grad[0]:
+            t = graph.by_dst  # rows = edge_index[1] (where node_attr was gathered), col = edge_index[0]
+            dx = torch.empty_like(x)
+            call("gmp_tp_contract", ptr(t.rowptr), ptr(t.col), t.perm_ptr, graph.n, graph.E, ptr(g), g.shape[1], ptr(dx),
+                 dx.shape[1], ptr(edge_sh), S, ptr(edge_feat), R, ptr(w1), ptr(b1), ptr(w2), ptr(b2), H, ptr(d["bwd_passes"]),
+                 ptr(d["bwd_blocks"]), plan.bwd["nblocks"], plan.bwd["nunits"], ptr(d["cg"]), precision)
+        csr = graph.by_src
+        nunits = plan.wunits.shape[0]
+        plen = _lib.lib().gmp_tp_wgrad_part_len(H)
+        dW2, db2 = torch.empty_like(w2), torch.empty_like(b2)
+        parts = torch.empty(max(nunits, 1), plen, dtype=x.dtype, device=x.device)
+        call("gmp_tp_wgrad", ptr(csr.rowptr), ptr(csr.col), csr.perm_ptr, graph.n, graph.E, ptr(x), x.shape[1], ptr(g), g.shape[1],
+             ptr(edge_sh), S, ptr(edge_feat), R, ptr(w1), ptr(b1), ptr(w2), H, ptr(d["wunits"]), nunits, ptr(d["cg"]), ptr(dW2),
+             ptr(db2), ptr(parts), precision)
+        red = torch.empty(plen, dtype=x.dtype, device=x.device)
+        call("gmp_reduce_partials_f32", ptr(parts), nunits, plen, ptr(red))
+        dW1 = red[:H * 16].view(H, 16)[:, :R].contiguous()
+        db1 = red[H * 16:H * 16 + H]
+        return dx, None, None, dW1, db1, dW2, db2, None, None, None
+
+
+class _TPInfo(nn.Module):
+    """Stands where e3nn's FullyConnectedTensorProduct module sits (``layer.tp``): no parameters
+    (shared_weights=False), exposes weight_numel and the instruction list."""
+
+    def __init__(self, plan: TensorProductPlan):
+        super().__init__()
+        self.plan = plan
+        self.weight_numel = plan.weight_numel
+        self.instructions = plan.paths
+
+    def extra_repr(self):
+        return f"{self.plan.irreps_in} x {self.plan.irreps_sh} -> {self.plan.irreps_out} | {len(self.plan.paths)} paths | {self.weight_numel} weights"
+
+
+class TensorProductConvLayer(nn.Module):
+    """models/layers/tfn_layer.py:8-93."""
+
+    def __init__(self, in_irreps, out_irreps, sh_irreps, edge_feats_dim, mlp_dim, aggr="add", batch_norm=False, gate=False,
+                 precision: str = "fp32"):
+        super().__init__()
+        self.in_irreps, self.sh_irreps = Irreps(str(in_irreps)), Irreps(str(sh_irreps))
+        out_irreps = Irreps(str(out_irreps))
+        self.edge_feats_dim, self.aggr, self.precision = edge_feats_dim, aggr, precision
+        if aggr not in ("add", "sum", "mean"):
+            raise NotImplementedError(f"aggr={aggr!r}: the fused reduction implements add/sum/mean")
+        if gate:
+            scal, gates, gated = gate_split(out_irreps)
+            if gated.num_irreps == 0:
+                self.gate = ScalarActivation()
+            else:
+                self.gate = Gate(scal, gates, gated)
+                out_irreps = self.gate.irreps_in
+        else:
+            self.gate = None
+        self.out_irreps = out_irreps
+        self.tp = _TPInfo(TensorProductPlan(self.in_irreps, self.sh_irreps, out_irreps))
+        self.fc = nn.Sequential(nn.Linear(edge_feats_dim, mlp_dim), nn.ReLU(), nn.Linear(mlp_dim, self.tp.weight_numel))
+        self.batch_norm = BatchNorm(out_irreps) if batch_norm else None
+
+    def forward(self, node_attr, edge_index, edge_sh, edge_feat):
+        graph = get_graph(edge_index, node_attr.shape[0])
+        out = _TPConvFn.apply(node_attr, edge_sh, edge_feat, self.fc[0].weight, self.fc[0].bias, self.fc[2].weight,
+                              self.fc[2].bias, graph, self.tp.plan, _PREC[self.precision])
+        if self.aggr == "mean":
+            rp = graph.by_src.rowptr
+            out = out / (rp[1:] - rp[:-1]).clamp(min=1).to(out.dtype).unsqueeze(1)
+        if self.gate is not None:
+            out = self.gate(out)
+        if self.batch_norm is not None:
+            out = self.batch_norm(out)
+        return out
+
+
+def first_node_pooling(x, batch, size=None):
+    """models/tfn.py:13-40: the first node of every graph."""
+    shifted = torch.cat([batch[-1:], batch[:-1]])
+    shifted[0] = -1
+    return x[(batch - shifted) == 1]
+
+
+class TFNModel(nn.Module):
+    """models/tfn.py:42-190."""
+
+    def __init__(self, r_max: float = 10.0, num_bessel: int = 8, num_polynomial_cutoff: int = 5, max_ell: int = 2,
+                 num_layers: int = 5, emb_dim: int = 64, hidden_irreps=None, mlp_dim: int = 256, in_dim: int = 1,
+                 out_dim: int = 1, aggr: str = "sum", pool: str = "first", gate: bool = True, batch_norm: bool = False,
+                 residual: bool = True, equivariant_pred: bool = False, precision: str = "fp32"):
+        super().__init__()
+        self.r_max, self.max_ell, self.num_layers, self.emb_dim, self.mlp_dim = r_max, max_ell, num_layers, emb_dim, mlp_dim
+        self.residual, self.batch_norm, self.gate, self.equivariant_pred = residual, batch_norm, gate, equivariant_pred
+        self.radial_embedding = RadialEmbeddingBlock(r_max, num_bessel, num_polynomial_cutoff)
+        sh_irreps = Irreps.spherical_harmonics(max_ell)
+        self.spherical_harmonics = SphericalHarmonics(max_ell)
+        self.emb_in = torch.nn.Embedding(in_dim, emb_dim)
+        hidden = hidden_irreps(max_ell, emb_dim) if hidden_irreps is None else Irreps(str(hidden_irreps))
+        self.hidden_irreps = hidden
+        ins = [Irreps(f"{emb_dim}x0e")] + [hidden] * (num_layers - 1)
+        self.convs = torch.nn.ModuleList([
+            TensorProductConvLayer(i, hidden, sh_irreps, self.radial_embedding.out_dim, mlp_dim, aggr, batch_norm, gate, precision)
+            for i in ins])
+        self.pool = {"mean": global_mean_pool, "sum": global_add_pool, "first": first_node_pooling}[pool]
+        if equivariant_pred:
+            self.pred = torch.nn.Linear(hidden.dim, out_dim)
+        else:
+            self.pred = torch.nn.Sequential(torch.nn.Linear(emb_dim, emb_dim), torch.nn.ReLU(), torch.nn.Linear(emb_dim, out_dim))
+
+    def forward(self, batch):
+        h = self.emb_in(batch.atoms)
+        edge_sh, edge_feats = edge_geometry(batch.pos, batch.edge_index, self.max_ell, self.radial_embedding)
+        for conv in self.convs:
+            h_update = conv(h, batch.edge_index, edge_sh, edge_feats)
+            h = h_update + F.pad(h, (0, h_update.shape[-1] - h.shape[-1])) if self.residual else h_update
+        out = self.pool(h, batch.batch)
+        if not self.equivariant_pred:
+            out = out[:, :self.emb_dim]
+        return self.pred(out)

@@ -130,6 +130,13 @@ int gmp_edge_length_bwd(const float* pos, const int64_t* src, const int64_t* dst
                         const int32_t* rowptr_s, const int32_t* perm_s, const int32_t* rowptr_d,
                         const int32_t* perm_d, int64_t n, float* dpos, gmp_stream_t stream);
 
+/* TFN / MACE edge prologue (models/tfn.py:171-175 == models/mace.py:170-174), one pass over the edges:
+ *   vec = pos[src] - pos[dst];  edge_sh [E,(L+1)^2] = e3nn SphericalHarmonics(normalize=True, 'component'), L <= 2;
+ *   edge_feat [E,num_bessel] = BesselBasis(|vec|) * PolynomialCutoff(|vec|; r_max, p)  (models/mace_modules/radial.py). */
+int gmp_edge_geometry_fwd(const float* pos, const int64_t* src, const int64_t* dst, int64_t num_edges,
+                          int32_t max_ell, float r_max, int32_t num_bessel, float poly_p, float* edge_sh,
+                          float* edge_feat, gmp_stream_t stream);
+
 /* ============================================================================================ */
 /* SchNet continuous-filter convolution (PyG InteractionBlock/CFConv called at models/schnet.py:72)*/
 /* ============================================================================================ */
@@ -219,6 +226,38 @@ int gmp_egnn_edge_bwd(const int32_t* rowptr, const int32_t* col, const int32_t* 
                       const gmp_egnn_edge_params* prm /* host */, const float* g_msg, const float* g_pos,
                       int32_t src_pass, float* d_node, float* d_pos, float* wgrad_parts, int32_t precision,
                       gmp_stream_t stream);
+
+/* ============================================================================================ */
+/* TFN / MACE tensor-product convolution (models/layers/tfn_layer.py:82-87)                       */
+/* ============================================================================================ */
+
+/* One contraction kernel serves the forward and the feature gradient (csrc/tpconv.cu):
+ *   res[n, block] (+)= sum_{e in CSR row n} sum_a T_e[a,b] * ( sum_iA V[col_e][v_off + a*DA + iA] * Z_e[iA,kB] )
+ * with T_e = fc(edge_feat_e) generated slice by slice in shared memory (the [E, weight_numel] tensor of the
+ * reference never exists) and Z_e[iA,kB] = sum_j sh_e[j] * cg[iA][j][kB].
+ *   forward   : CSR rows = edge_index[0] (aggregation), col = edge_index[1]; V = node_attr, res = TP output
+ *   d/d node  : CSR rows = edge_index[1], col = edge_index[0];               V = dL/dout,  res = dL/dnode_attr
+ * `passes` / `blocks` are device arrays of the 12-int32 / 8-int32 records documented in csrc/tpconv.cu
+ * (struct TpPass / TpBlock), built once per layer by the host (gmp_b200/tfn.py) from the e3nn instruction
+ * list; `cg` is the float table they index.  fc = Linear(R,H) -> ReLU -> Linear(H,numel): w1 [H,R], b1 [H],
+ * w2 [numel,H], b2 [numel].  edge_sh [E,S] and edge_feat [E,R] are in the caller's edge order (perm). */
+int gmp_tp_contract(const int32_t* rowptr, const int32_t* col, const int32_t* perm, int64_t n, int64_t num_edges,
+                    const float* V, int32_t v_len, float* res, int32_t r_len, const float* edge_sh, int32_t S,
+                    const float* edge_feat, int32_t R, const float* w1, const float* b1, const float* w2,
+                    const float* b2, int32_t H, const void* passes, const void* blocks, int32_t nblocks,
+                    int32_t nunits, const float* cg, int32_t precision, gmp_stream_t stream);
+int64_t gmp_tp_contract_smem_bytes(int32_t H, int32_t R);
+
+/* Weight gradient of fc given g = dL/d(TP output) [n, g_len]: a CTA owns 64 rows of w2 (`units`: device array of
+ * 12-int32 TpWUnit records) and streams all edges (CSR rows = edge_index[0], col = edge_index[1]).
+ *   dW2 [numel,H], db2 [numel] are written directly; dW1/db1 come as per-unit partials
+ *   w1_parts [nunits, H*16 + H] (dW1 padded to 16 columns | db1) to be summed by gmp_reduce_partials_f32. */
+int gmp_tp_wgrad(const int32_t* rowptr, const int32_t* col, const int32_t* perm, int64_t n, int64_t num_edges,
+                 const float* x, int32_t x_len, const float* g, int32_t g_len, const float* edge_sh, int32_t S,
+                 const float* edge_feat, int32_t R, const float* w1, const float* b1, const float* w2, int32_t H,
+                 const void* units, int32_t nunits, const float* cg, float* dW2, float* db2, float* w1_parts,
+                 int32_t precision, gmp_stream_t stream);
+int64_t gmp_tp_wgrad_part_len(int32_t H);
 
 #ifdef __cplusplus
 }

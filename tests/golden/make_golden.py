@@ -247,9 +247,9 @@ def main():
 
     # ---- whole models, small --------------------------------------------------------------------
     d = random_clouds(4, 10, 3.0, 2.0, 25)
-    for tag, cls, ctor in (("tfn_model", TFNModel, dict(r_max=2.0, max_ell=2, num_layers=2, emb_dim=4, mlp_dim=32, out_dim=2)),
+    for tag, cls, ctor in (("tfn_model", TFNModel, dict(r_max=2.0, max_ell=2, num_layers=2, emb_dim=4, mlp_dim=64, out_dim=2)),
                            ("mace_model", MACEModel, dict(r_max=2.0, max_ell=2, correlation=3, num_layers=2,
-                                                          emb_dim=4, mlp_dim=32, out_dim=2))):
+                                                          emb_dim=4, mlp_dim=64, out_dim=2))):
         torch.manual_seed(26)
         m = cls(**ctor)
         m.train()
