@@ -20,5 +20,7 @@ from .egnn import EGNNLayer, EGNNModel, MPNNLayer  # noqa: F401
 from .irreps import Irreps  # noqa: F401
 from .tfn import (BatchNorm, Gate, RadialEmbeddingBlock, SphericalHarmonics, TensorProductConvLayer,  # noqa: F401
                   TensorProductPlan, TFNModel, edge_geometry, first_node_pooling)
+from .mace import (Contraction, EquivariantLinear, EquivariantProductBasisBlock, MACEModel,  # noqa: F401
+                   SymmetricContraction, reshape_irreps)
 
 __version__ = "0.1.0"

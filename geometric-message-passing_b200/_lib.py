@@ -61,12 +61,14 @@ _SIGS = {
     "gmp_egnn_edge_fwd": [P, P, I64, I64, P, P, P, P, P, P, I32, P],
     "gmp_egnn_edge_bwd": [P, P, P, I64, I64, P, P, P, P, P, P, I32, P, P, P, I32, P],
     "gmp_tp_contract": [P, P, P, I64, I64, P, I32, P, I32, P, I32, P, I32, P, P, P, P, I32, P, P, I32, I32, P, I32, P],
+    "gmp_symcontract_fwd": [P, P, P, P, I64, I32, I32, I32, I32, P, I32, P],
+    "gmp_symcontract_bwd": [P, P, P, P, I64, I32, I32, I32, I32, P, I32, P, P, P],
     "gmp_tp_wgrad": [P, P, P, I64, I64, P, I32, P, I32, P, I32, P, I32, P, P, P, I32, P, I32, P, P, P, P, I32, P],
 }
 _PLAIN = {"gmp_version": (I32, []), "gmp_last_error": (C.c_char_p, []),
           "gmp_schnet_bwd_num_parts": (I32, [I64]), "gmp_schnet_bwd_part_len": (I64, [I32, I32]),
           "gmp_egnn_bwd_num_parts": (I32, [I64]), "gmp_egnn_bwd_part_len": (I64, [I32]),
-          "gmp_tp_contract_smem_bytes": (I64, [I32, I32]), "gmp_tp_wgrad_part_len": (I64, [I32])}
+          "gmp_tp_contract_smem_bytes": (I64, [I32, I32]), "gmp_symcontract_bwd_num_parts": (I32, [I64]), "gmp_tp_wgrad_part_len": (I64, [I32])}
 
 
 def exported_symbols():

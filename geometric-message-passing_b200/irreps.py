@@ -206,3 +206,66 @@ def gate_split(irreps) -> Tuple[Irreps, Irreps, Irreps]:
 
 # e3nn normalize2mom constants (1 / sqrt(E_{z~N(0,1)} f(z)^2), e3nn's seeded 1e6-sample estimate)
 NORM2MOM = {"silu": 1.6791767923989418, "sigmoid": 1.8467055342154763}
+
+
+# ------------------------------------------------------------------------------------------------
+# MACE generalised Clebsch-Gordan ("U matrices", models/mace_modules/cg.py:19-133) and their symmetric
+# monomial form
+# ------------------------------------------------------------------------------------------------
+def _coupled_bases(irreps_list: List[Irreps]):
+    """Iterated coupling of the components of irreps_list[0] x ... x irreps_list[-1] ('component' normalisation).
+    Returns [(Irrep, basis [d_out, dim_1, ..., dim_n])], stably sorted by (l, p) at every level, as the reference does."""
+    if len(irreps_list) == 1:
+        (irreps,) = irreps_list
+        eye, out, i = np.eye(irreps.dim), [], 0
+        for mul, ir in irreps:
+            for _ in range(mul):
+                out.append((ir, eye[i:i + ir.dim]))
+                i += ir.dim
+        return out
+    *left, right = irreps_list
+    out = []
+    for ir_left, C_left in _coupled_bases(left):
+        i = 0
+        for mul, ir in right:
+            for l in range(abs(ir_left.l - ir.l), ir_left.l + ir.l + 1):
+                ir_out = Irrep(l, ir_left.p * ir.p)
+                C = wigner_3j(ir_out.l, ir_left.l, ir.l) * math.sqrt(ir_out.dim)
+                C = np.einsum("jk,ijl->ikl", C_left.reshape(C_left.shape[0], -1), C)
+                C = C.reshape((ir_out.dim,) + tuple(x.dim for x in left) + (ir.dim,))
+                for u in range(mul):
+                    E = np.zeros((ir_out.dim,) + tuple(x.dim for x in left) + (right.dim,))
+                    E[..., i + u * ir.dim:i + (u + 1) * ir.dim] = C
+                    out.append((ir_out, E))
+            i += mul * ir.dim
+    return sorted(out, key=lambda t: (t[0].l, t[0].p))  # Python's sort is stable, like the reference's
+
+
+def u_matrix_real(irreps_in, ir_out: Irrep, correlation: int) -> np.ndarray:
+    """U_nu for one output irrep: [d_out, dim, ..., dim (nu times), k] (not squeezed), float64."""
+    irreps_in = Irreps(irreps_in)
+    bases = [B for ir, B in _coupled_bases([irreps_in] * correlation) if ir == ir_out]
+    return np.stack(bases, axis=-1)
+
+
+def monomials(D: int, nu: int) -> np.ndarray:
+    """Symmetric monomials of degree 1..nu in D variables as index triples padded with D (the constant 1)."""
+    out = []
+    for deg in range(1, nu + 1):
+        if deg == 1:
+            out += [(i, D, D) for i in range(D)]
+        elif deg == 2:
+            out += [(i, j, D) for i in range(D) for j in range(i, D)]
+        else:
+            out += [(i, j, k) for i in range(D) for j in range(i, D) for k in range(j, D)]
+    return np.asarray(out, dtype=np.int32)
+
+
+def symmetrise_u(U: np.ndarray, nu: int, D: int) -> np.ndarray:
+    """Sum a U_nu [d_out, D^nu, k] over index permutations onto the degree-nu monomials: [d_out, n_mono(nu), k]."""
+    mons = [m for m in monomials(D, nu) if (m != D).sum() == nu]
+    index = {tuple(m[:nu]): n for n, m in enumerate(mons)}
+    out = np.zeros((U.shape[0], len(mons), U.shape[-1]))
+    for idx in np.ndindex(*([D] * nu)):
+        out[:, index[tuple(sorted(idx))], :] += U[(slice(None),) + idx + (slice(None),)]
+    return out

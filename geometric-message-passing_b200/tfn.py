@@ -20,7 +20,8 @@ from torch.nn import functional as F
 from . import _lib
 from ._lib import GmpError, call, ptr
 from .graph import Graph, get_graph
-from .irreps import NORM2MOM, Irreps, TPPath, fctp_paths, gate_split, hidden_irreps, wigner_3j
+from .irreps import NORM2MOM, Irreps, TPPath, fctp_paths, gate_split, wigner_3j
+from .irreps import hidden_irreps as default_hidden_irreps
 from .schnet import global_add_pool, global_mean_pool
 
 _PREC = {"fp32": _lib.FP32_STRICT, "bf16": _lib.BF16_TC}
@@ -398,7 +399,7 @@ class TFNModel(nn.Module):
         sh_irreps = Irreps.spherical_harmonics(max_ell)
         self.spherical_harmonics = SphericalHarmonics(max_ell)
         self.emb_in = torch.nn.Embedding(in_dim, emb_dim)
-        hidden = hidden_irreps(max_ell, emb_dim) if hidden_irreps is None else Irreps(str(hidden_irreps))
+        hidden = default_hidden_irreps(max_ell, emb_dim) if hidden_irreps is None else Irreps(str(hidden_irreps))
         self.hidden_irreps = hidden
         ins = [Irreps(f"{emb_dim}x0e")] + [hidden] * (num_layers - 1)
         self.convs = torch.nn.ModuleList([

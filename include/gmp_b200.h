@@ -259,6 +259,25 @@ int gmp_tp_wgrad(const int32_t* rowptr, const int32_t* col, const int32_t* perm,
                  int32_t precision, gmp_stream_t stream);
 int64_t gmp_tp_wgrad_part_len(int32_t H);
 
+/* ============================================================================================ */
+/* MACE symmetric contraction (models/mace_modules/symmetric_contraction.py:169-185)              */
+/* ============================================================================================ */
+
+/* out[b, C*off(K) + c*d(K) + k(K)] = sum_m coef[c][K][m] * x[b,c,i1(m)] * x[b,c,i2(m)] * x[b,c,i3(m)]
+ *   x    [N, C, D]   node features after reshape_irreps (models/mace_modules/irreps_tools.py:69-79), D <= 15
+ *   coef [C, K, M]   U matrices folded with the per-channel weights over the symmetric monomial basis (host, autograd)
+ *   mono [M, 3]      component indices, value D = the constant 1 (pads monomials of degree < 3); M <= 256
+ *   out_map [K, 3]   (component offset of the output irrep block, its dim d, local k), K <= 16
+ * Replaces the three opt_einsum.contract calls per output irrep of Contraction.forward. */
+int gmp_symcontract_fwd(const float* x, const float* coef, const int32_t* mono, const int32_t* out_map,
+                        int64_t num_nodes, int32_t C, int32_t D, int32_t K, int32_t M, float* out, int32_t out_len,
+                        gmp_stream_t stream);
+/* dx [N,C,D] and per-block partials dcoef_parts [nparts, C, K, M] (sum with gmp_reduce_partials_f32). */
+int32_t gmp_symcontract_bwd_num_parts(int64_t num_nodes);
+int gmp_symcontract_bwd(const float* x, const float* coef, const int32_t* mono, const int32_t* out_map,
+                        int64_t num_nodes, int32_t C, int32_t D, int32_t K, int32_t M, const float* g_out,
+                        int32_t out_len, float* dx, float* dcoef_parts, gmp_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
