@@ -419,6 +419,10 @@ static int launch_bwd(const SchnetArgs& a, bool has_attr, bool need, const float
     return need ? launch_bwd_t<F, false, true>(a, g, parts, d_ew, d_ea, s) : launch_bwd_t<F, false, false>(a, g, parts, d_ew, d_ea, s);
 }
 
+int schnet_fwd_tc_launch(const int32_t* rowptr, const int32_t* col, const int32_t* perm, int64_t n, int64_t E,
+                         const float* ew, const float* ea, const float* x1, const gmp_schnet_filter* f, float* agg,
+                         cudaStream_t stream);  // schnet_tc.cu
+
 }  // namespace gmp
 
 using namespace gmp;
@@ -441,11 +445,9 @@ int gmp_schnet_cfconv_fwd(const int32_t* rowptr, const int32_t* col, const int32
     if (int rc = schnet_check(filt, n, num_edges)) return rc;
     GMP_REQUIRE(rowptr && agg && (num_edges == 0 || (col && edge_weight && x1)), "schnet_cfconv_fwd: NULL pointer");
     GMP_REQUIRE(edge_attr || filt->gauss_offset, "schnet_cfconv_fwd: need edge_attr or gauss_offset");
-    if (precision != GMP_FP32_STRICT) {
-        set_error("schnet_cfconv_fwd: precision mode %d is not built into this library", precision);
-        return GMP_ERR_UNSUPPORTED;
-    }
+    GMP_REQUIRE(precision == GMP_FP32_STRICT || precision == GMP_BF16_TC, "schnet_cfconv_fwd: unknown precision mode %d", precision);
     if (n == 0) return GMP_OK;
+    if (precision == GMP_BF16_TC) return schnet_fwd_tc_launch(rowptr, col, perm, n, num_edges, edge_weight, edge_attr, x1, filt, agg, stream);
     const SchnetArgs a = make_args(rowptr, col, perm, n, num_edges, edge_weight, edge_attr, x1, filt);
     return filt->num_filters == 128 ? launch_fwd<128>(a, edge_attr != nullptr, agg, stream)
                                     : launch_fwd<64>(a, edge_attr != nullptr, agg, stream);
@@ -459,10 +461,8 @@ int gmp_schnet_cfconv_bwd(const int32_t* rowptr, const int32_t* col, const int32
     GMP_REQUIRE(rowptr && g_agg && wgrad_parts && (num_edges == 0 || (col && edge_weight && x1)), "schnet_cfconv_bwd: NULL pointer");
     GMP_REQUIRE(edge_attr || filt->gauss_offset, "schnet_cfconv_bwd: need edge_attr or gauss_offset");
     GMP_REQUIRE(!d_edge_attr || edge_attr, "schnet_cfconv_bwd: d_edge_attr requested without edge_attr");
-    if (precision != GMP_FP32_STRICT) {
-        set_error("schnet_cfconv_bwd: precision mode %d is not built into this library", precision);
-        return GMP_ERR_UNSUPPORTED;
-    }
+    // the filter-side backward has no tensor-core variant in this build: GMP_BF16_TC runs the fp32 kernel here
+    GMP_REQUIRE(precision == GMP_FP32_STRICT || precision == GMP_BF16_TC, "schnet_cfconv_bwd: unknown precision mode %d", precision);
     const SchnetArgs a = make_args(rowptr, col, perm, n, num_edges, edge_weight, edge_attr, x1, filt);
     const bool need = d_edge_weight != nullptr || d_edge_attr != nullptr;
     return filt->num_filters == 128 ? launch_bwd<128>(a, edge_attr != nullptr, need, g_agg, wgrad_parts, d_edge_weight, d_edge_attr, stream)

@@ -181,6 +181,10 @@ int gmp_schnet_cfconv_bwd(const int32_t* rowptr, const int32_t* col, const int32
                           const gmp_schnet_filter* filt /* host */, const float* g_agg, float* wgrad_parts,
                           float* d_edge_weight, float* d_edge_attr, int32_t precision, gmp_stream_t stream);
 
+/* Hardware self test of the tcgen05 path: out[128,128] = bf16(A[128,K]) x bf16(B[128,K])^T with fp32 accumulation
+ * in TMEM, through the same shared-memory descriptors and 128-byte swizzle the fused kernels use.  K in {64, 128}. */
+int gmp_umma_selftest(const float* A, const float* B, float* out, int32_t K, gmp_stream_t stream);
+
 /* ============================================================================================ */
 /* EGNN edge path (models/layers/egnn_layer.py:62-80: message + aggregate, fused)                 */
 /* ============================================================================================ */

@@ -1,0 +1,53 @@
+"""GPU: the tcgen05 / TMEM path.  (1) hardware self test of the hand-built UMMA descriptors and 128-byte swizzle;
+(2) the bf16 tensor-core CFConv forward against the fp32-strict kernel: 1e-2 normwise relative, the tolerance
+BASELINE.json states for bf16 MLP inputs."""
+import ctypes as C
+
+import pytest
+import torch
+
+from tests.helpers import random_clouds, rel_err
+
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(120)]
+
+
+@pytest.mark.parametrize("K", [64, 128])
+def test_umma_selftest(K):
+    from gmp_b200._lib import call, ptr
+    g = torch.Generator().manual_seed(K)
+    A = torch.randn(128, K, generator=g).cuda()
+    B = torch.randn(128, K, generator=g).cuda()
+    out = torch.zeros(128, 128, device="cuda")
+    call("gmp_umma_selftest", ptr(A), ptr(B), ptr(out), K)
+    torch.cuda.synchronize()
+    ref = A.bfloat16().double() @ B.bfloat16().double().T
+    assert rel_err(out, ref) <= 1e-5
+
+
+@pytest.mark.parametrize("graphs,nodes,lazy", [(64, 32, True), (9, 21, False)])
+def test_cfconv_bf16_tc_vs_fp32(graphs, nodes, lazy):
+    import gmp_b200
+    d = random_clouds(graphs, nodes, 8.0, 5.0, 500 + graphs, max_nb=32)
+    ei, pos = d["edge_index"].cuda(), d["pos"].cuda()
+    torch.manual_seed(0)
+    m32 = gmp_b200.InteractionBlock(128, 50, 128, 5.0).cuda()
+    with torch.no_grad():
+        for p in m32.parameters():
+            if p.dim() == 1:
+                p.normal_(0, 0.3)
+    m16 = gmp_b200.InteractionBlock(128, 50, 128, 5.0, precision="bf16").cuda()
+    m16.load_state_dict(m32.state_dict())
+    sm = gmp_b200.GaussianSmearing(0.0, 5.0, 50).cuda()
+    x = torch.randn(pos.shape[0], 128, device="cuda")
+    ew = (pos[ei[0]] - pos[ei[1]]).norm(dim=-1)
+    attr = sm.lazy() if lazy else sm(ew)
+    x32, x16 = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
+    o32, o16 = m32(x32, ei, ew, attr), m16(x16, ei, ew, attr)
+    assert rel_err(o16, o32) <= 1e-2
+    cot = torch.randn_like(o32)
+    g32 = torch.autograd.grad((o32 * cot).sum(), [x32] + list(m32.parameters()))
+    g16 = torch.autograd.grad((o16 * cot).sum(), [x16] + list(m16.parameters()))
+    for a, b in zip(g16, g32):
+        assert rel_err(a, b) <= 1e-2
+    # deterministic
+    assert torch.equal(o16, m16(x16, ei, ew, attr))
