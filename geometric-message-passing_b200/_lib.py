@@ -59,6 +59,7 @@ _SIGS = {
     "gmp_schnet_cfconv_fwd": [P, P, P, I64, I64, P, P, P, P, P, I32, P],
     "gmp_schnet_cfconv_bwd": [P, P, P, I64, I64, P, P, P, P, P, P, P, P, I32, P],
     "gmp_umma_selftest": [P, P, P, I32, P],
+    "gmp_umma_selftest_mn": [P, P, P, I32, P],
     "gmp_egnn_edge_fwd": [P, P, I64, I64, P, P, P, P, P, P, I32, P],
     "gmp_egnn_edge_bwd": [P, P, P, I64, I64, P, P, P, P, P, P, I32, P, P, P, I32, P],
     "gmp_tp_contract": [P, P, P, I64, I64, P, I32, P, I32, P, I32, P, I32, P, P, P, P, I32, P, P, I32, I32, P, I32, P],

@@ -21,8 +21,8 @@ constexpr int kTcRange = 2048;  // edges per work range (16 tiles)
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128, 1) umma_selftest_kernel(const float* __restrict__ A, const float* __restrict__ B,
                                                                float* __restrict__ out, int K) {
-    extern __shared__ __align__(1024) uint8_t smraw[];
-    uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smraw) + 1023) & ~uintptr_t(1023));
+    extern __shared__ __align__(16) uint8_t smraw[];
+    uint8_t* sm = smraw + ((1024u - (smem_u32(smraw) & 1023u)) & 1023u);
     uint8_t* sA = sm;               // K/64 slabs of [128][64] bf16
     uint8_t* sB = sm + 32768;
     __shared__ uint64_t bar;
@@ -68,6 +68,57 @@ __global__ void __launch_bounds__(128, 1) umma_selftest_kernel(const float* __re
     if (warp == 0) tmem_dealloc<128>(tm);
 }
 
+// self test, MN-major operands: out[128][N] = sum_k bf16(A[k][m]) * bf16(B[k][n]),  A [128 k][128 m], B [128 k][N], N in {64,128}
+__global__ void __launch_bounds__(128, 1) umma_selftest_mn_kernel(const float* __restrict__ A, const float* __restrict__ B,
+                                                                  float* __restrict__ out, int N) {
+    extern __shared__ __align__(16) uint8_t smraw[];
+    uint8_t* sm = smraw + ((1024u - (smem_u32(smraw) & 1023u)) & 1023u);
+    uint8_t* sA = sm;               // 2 slabs [128 k][64 m]
+    uint8_t* sB = sm + 32768;       // N/64 slabs [128 k][64 n]
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tmem_base;
+    const int t = threadIdx.x, warp = t >> 5;  // thread t stores tile row k = t
+    for (int sl = 0; sl < 2; ++sl)
+        for (int ch = 0; ch < 8; ++ch) {
+            uint32_t pa[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) pa[j] = pack_bf16(A[t * 128 + sl * 64 + ch * 8 + 2 * j], A[t * 128 + sl * 64 + ch * 8 + 2 * j + 1]);
+            *reinterpret_cast<uint4*>(sA + sl * 16384 + sw128_chunk_off(t, ch)) = make_uint4(pa[0], pa[1], pa[2], pa[3]);
+        }
+    for (int sl = 0; sl < N / 64; ++sl)
+        for (int ch = 0; ch < 8; ++ch) {
+            uint32_t pb[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) pb[j] = pack_bf16(B[t * N + sl * 64 + ch * 8 + 2 * j], B[t * N + sl * 64 + ch * 8 + 2 * j + 1]);
+            *reinterpret_cast<uint4*>(sB + sl * 16384 + sw128_chunk_off(t, ch)) = make_uint4(pb[0], pb[1], pb[2], pb[3]);
+        }
+    if (t == 0) {
+        mbar_init(&bar, 1);
+        fence_mbar_init();
+    }
+    if (warp == 0) tmem_alloc<128>(&tmem_base);
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tm = tmem_base;
+    if (t == 0) {
+        umma_tile_mn(tm, smem_u32(sA), 16384, smem_u32(sB), 16384, 128, umma_idesc_bf16(128, N, true, true), false);
+        umma_commit(&bar);
+    }
+    mbar_wait(&bar, 0);
+    tc_fence_after();
+    for (int c0 = 0; c0 < N; c0 += 32) {
+        float v[32];
+        tmem_ld32(tm + ((uint32_t)(warp * 32) << 16) + c0, v);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) out[t * N + c0 + j] = v[j];
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc<128>(tm);
+}
+
 // ------------------------------------------------------------------------------------------------
 // fused forward
 // ------------------------------------------------------------------------------------------------
@@ -83,40 +134,53 @@ struct TcArgs {
 
 // shared-memory map (bytes from the 1024-aligned base), F = 128
 constexpr int kLdX = 132;                       // fp32 row stride of the X / message tile (conflict-free float4 rows)
+constexpr int kXBytes = kTcTile * kLdX * 4;     // 66 KB
 constexpr int oW1b = 0;                         // [128][64] bf16  16 KB
 constexpr int oW2b = oW1b + 16384;              // 2 x [128][64]   32 KB
-constexpr int oA1 = oW2b + 32768;               // [128][64]       16 KB
-constexpr int oA2 = oA1 + 16384;                // 2 x [128][64]   32 KB
-constexpr int oXt = oA2 + 32768;                // [128][132] fp32 66 KB
-constexpr int oBias = oXt + kTcTile * kLdX * 4; // b1[128], b2[128], goff[64]
-constexpr int oScal = oBias + (128 + 128 + 64) * 4;  // d[128], C[128]
-constexpr int oInts = oScal + 2 * 128 * 4;      // src[128], eid[128]
-constexpr int oBar = oInts + 2 * 128 * 4;       // 2 mbarriers + tmem ptr
+constexpr int oA2 = oW2b + 32768;               // 2 x [128][64]   32 KB   (h1; slab 0 doubles as A1 = rbf tile)
+constexpr int oA1 = oA2;                        // rbf tile is dead once GEMM1 has completed
+constexpr int oXt = oA2 + 32768;                // 2 x [128][132] fp32 (double-buffered gather / message tile)
+constexpr int oBias = oXt + 2 * kXBytes;        // b1[128], b2[128], goff[64]
+constexpr int oScal = oBias + (128 + 128 + 64) * 4;  // 2 x { d[128], C[128] }
+constexpr int oInts = oScal + 2 * 2 * 128 * 4;  // 2 x { src[128], eid[128], rowid[128] }
+constexpr int kIntsBytes = 3 * 128 * 4;
+constexpr int oBar = oInts + 2 * kIntsBytes;    // 2 mbarriers + tmem ptr
 constexpr int kTcSmem = oBar + 64 + 1024;       // + alignment slack
 
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float lg2_approx(float x) {
+    float y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+// softplus(x) - ln2 = ln2 * log2(1 + 2^(x log2 e)) - ln2 ; the clamp keeps 2^y finite (x <= 87 is exact to fp32)
 __device__ __forceinline__ float ssp_fast(float x) {
-    // softplus(x) - ln2 = ln2 * (log2(1 + 2^(x log2 e)) - 1); ex2/lg2 approximations (rel. err ~1e-7 << bf16)
-    const float e = exp2f(x * 1.4426950408889634f);
-    const float sp = x > 15.f ? x : 0.6931471805599453f * __log2f(1.0f + e);
-    return sp - 0.6931471805599453f;
+    const float e = ex2_approx(fminf(x * 1.4426950408889634f, 126.f));
+    return fmaf(0.6931471805599453f, lg2_approx(1.0f + e), -0.6931471805599453f);
 }
 
+// Software pipeline per CTA (tiles i of one work range; buffers indexed by i & 1):
+//   [barrier: A1(i) ready]  GEMM1 | publish scalars(i+1) | epilogue 1 -> A2 | GEMM2 | issue gather(i+1), wait gather(i) |
+//   epilogue 2 (message tile in place) | warps 0-3: column walkers(i)   ||   warps 4-7: rbf(i+1) -> A1
 template <bool HAS_ATTR>
 __global__ void __launch_bounds__(256, 1) schnet_fwd_tc_kernel(TcArgs a, float* __restrict__ agg) {
     constexpr int F = 128;
-    extern __shared__ __align__(1024) uint8_t smraw[];
-    uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smraw) + 1023) & ~uintptr_t(1023));
-    float* Xt = reinterpret_cast<float*>(sm + oXt);
+    extern __shared__ __align__(16) uint8_t smraw[];
+    // align to 1024 B by offsetting the shared array itself (keeps the shared address space for LDS/STS)
+    uint8_t* sm = smraw + ((1024u - (smem_u32(smraw) & 1023u)) & 1023u);
     float* b1s = reinterpret_cast<float*>(sm + oBias);
     float* b2s = b1s + 128;
     float* goff = b2s + 128;
-    float* ds = reinterpret_cast<float*>(sm + oScal);
-    float* Cs = ds + 128;
-    int* srcs = reinterpret_cast<int*>(sm + oInts);
-    int* eids = srcs + 128;
     uint64_t* bars = reinterpret_cast<uint64_t*>(sm + oBar);
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(sm + oBar + 32);
     const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+    auto Xbuf = [&](int b) { return reinterpret_cast<float*>(sm + oXt + b * kXBytes); };
+    auto dsb = [&](int b) { return reinterpret_cast<float*>(sm + oScal + b * 1024); };          // d[128], C[128]
+    auto isb = [&](int b) { return reinterpret_cast<int*>(sm + oInts + b * kIntsBytes); };      // src, eid, rowid
 
     // ---- one-time setup: weights -> bf16 swizzled K-major, barriers, TMEM
     for (int x = t; x < 128 * 8; x += 256) {  // W1 [f][g], g padded to 64
@@ -139,7 +203,8 @@ __global__ void __launch_bounds__(256, 1) schnet_fwd_tc_kernel(TcArgs a, float* 
         b1s[t] = __ldg(a.b1 + t);
         b2s[t] = __ldg(a.b2 + t);
     }
-    if (t < 64) goff[t] = (!HAS_ATTR && t < a.G) ? __ldg(a.goff + t) : 0.f;
+    // Gaussian centres; padding columns get a far-away centre so that their basis value underflows to exactly 0
+    if (t < 64) goff[t] = (!HAS_ATTR && t < a.G) ? __ldg(a.goff + t) : 1.0e18f;
     if (t == 0) {
         mbar_init(&bars[0], 1);
         mbar_init(&bars[1], 1);
@@ -156,75 +221,109 @@ __global__ void __launch_bounds__(256, 1) schnet_fwd_tc_kernel(TcArgs a, float* 
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;  // TMEM lanes this warp may read
     const int row = (warp & 3) * 32 + lane;                        // tile row (edge) owned in the epilogues
     const int chalf = warp >> 2;                                   // column half [64*chalf, 64*chalf + 64)
+    const float cw = 3.14159265358979323846f / a.cutoff;
+    const float c2 = a.gcoeff * 1.4426950408889634f;               // exp(c u^2) = 2^(c2 u^2)
     uint32_t phase = 0;
+
+    struct Pre { int src, eid, rowid; float d; };
+    // edge scalars of one tile: loads (registers) and publication (smem) are split so the latency overlaps compute
+    auto load_scalars = [&](int64_t e0, int cnt, int r0, int r1) {
+        Pre p{0, 0, r1, 0.f};
+        if (t < cnt) {
+            const int64_t k = e0 + t;
+            p.eid = a.perm ? __ldg(a.perm + k) : (int)k;
+            p.src = __ldg(a.col + k);
+            p.d = __ldg(a.ew + p.eid);
+            int lo = r0, hi = r1;  // CSR row of edge k: last row whose first edge is <= k
+            while (hi - lo > 1) {
+                const int mid = (lo + hi) >> 1;
+                if ((int64_t)__ldg(a.rowptr + mid) <= k) lo = mid; else hi = mid;
+            }
+            p.rowid = lo;
+        }
+        return p;
+    };
+    auto publish_scalars = [&](const Pre& p, int cnt, int b) {
+        float* d = dsb(b);
+        int* is = isb(b);
+        d[t] = t < cnt ? p.d : 1.0e18f;  // padded rows: every Gaussian underflows to 0
+        d[128 + t] = t < cnt ? 0.5f * (__cosf(p.d * cw) + 1.0f) : 0.f;
+        is[t] = p.src;
+        is[128 + t] = p.eid;
+        is[256 + t] = p.rowid;
+    };
+    auto issue_gather = [&](int cnt, int b) {
+        float* X = Xbuf(b);
+        const int* srcs = isb(b);
+        for (int x = t; x < kTcTile * 32; x += 256) {
+            const int r = x >> 5, c = x & 31;
+            if (r < cnt) __pipeline_memcpy_async(X + r * kLdX + 4 * c, a.x1 + (int64_t)srcs[r] * F + 4 * c, 16);
+            else *reinterpret_cast<float4*>(X + r * kLdX + 4 * c) = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        __pipeline_commit();
+    };
+    // radial-basis tile of buffer b -> A1 (bf16, swizzled), computed by `nthr` threads with local index `tl`
+    auto rbf_tile = [&](int b, int cnt, int tl, int nthr) {
+        const float* ds = dsb(b);
+        const int* eids = isb(b) + 128;
+        for (int x = tl; x < kTcTile * 8; x += nthr) {  // (row, 16-byte chunk)
+            const int r = x >> 3, ch = x & 7;
+            float v[8];
+            if (HAS_ATTR) {
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const int g = ch * 8 + q;
+                    v[q] = (r < cnt && g < a.G) ? __ldg(a.ea + (int64_t)eids[r] * a.G + g) : 0.f;
+                }
+            } else {
+                const float d = ds[r];
+                const float4 o0 = *reinterpret_cast<const float4*>(goff + ch * 8), o1 = *reinterpret_cast<const float4*>(goff + ch * 8 + 4);
+                const float off[8] = {o0.x, o0.y, o0.z, o0.w, o1.x, o1.y, o1.z, o1.w};
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const float u = d - off[q];
+                    v[q] = ex2_approx(c2 * u * u);
+                }
+            }
+            *reinterpret_cast<uint4*>(sm + oA1 + sw128_chunk_off(r, ch)) =
+                make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+        }
+        fence_proxy_async();
+    };
 
     for (int rg = blockIdx.x; rg < a.nranges; rg += gridDim.x) {
         const int r0 = lower_bound_row(a.rowptr, (int)a.n, (int64_t)rg * kTcRange);
         const int r1 = (rg + 1 == a.nranges) ? (int)a.n : lower_bound_row(a.rowptr, (int)a.n, (int64_t)(rg + 1) * kTcRange);
         if (r0 >= r1) continue;
         const int64_t eb = __ldg(a.rowptr + r0), ee = __ldg(a.rowptr + r1);
-        int cur = r0;
-        int64_t row_end = __ldg(a.rowptr + r0 + 1);
+        int cur = r0;      // walker state (threads < 128): row being accumulated and its running sum
         float acc = 0.f;
-        for (int64_t e0 = eb; e0 < ee; e0 += kTcTile) {
+        int buf = 0;
+        __syncthreads();   // previous range fully drained (shared buffers reusable)
+        if (eb < ee) {     // prologue: scalars, gather and radial basis of the first tile
+            const int cnt0 = (int)min((int64_t)kTcTile, ee - eb);
+            if (t < kTcTile) publish_scalars(load_scalars(eb, cnt0, r0, r1), cnt0, 0);
+            __syncthreads();
+            issue_gather(cnt0, 0);
+            rbf_tile(0, cnt0, t, 256);
+        }
+        for (int64_t e0 = eb; e0 < ee; e0 += kTcTile, buf ^= 1) {
             const int cnt = (int)min((int64_t)kTcTile, ee - e0);
-            // ---- S1: per-edge scalars
-            if (t < kTcTile) {
-                float d = 0.f, C = 0.f;
-                int src = 0, eid = 0;
-                if (t < cnt) {
-                    const int64_t k = e0 + t;
-                    eid = a.perm ? __ldg(a.perm + k) : (int)k;
-                    src = __ldg(a.col + k);
-                    d = __ldg(a.ew + eid);
-                    C = 0.5f * (__cosf(d * 3.14159265358979323846f / a.cutoff) + 1.0f);
-                }
-                ds[t] = d; Cs[t] = C; srcs[t] = src; eids[t] = eid;
-            }
-            __syncthreads();
-            // ---- S2: async gather of the x1 rows
-            for (int x = t; x < kTcTile * 32; x += 256) {
-                const int r = x >> 5, c = x & 31;
-                if (r < cnt) __pipeline_memcpy_async(Xt + r * kLdX + 4 * c, a.x1 + (int64_t)srcs[r] * F + 4 * c, 16);
-                else *reinterpret_cast<float4*>(Xt + r * kLdX + 4 * c) = make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-            __pipeline_commit();
-            // ---- S3: radial basis tile -> A1 (bf16, swizzled).  thread = (row t/2, 4 chunks)
-            {
-                const int r = t >> 1, h = t & 1;
-                const float d = ds[r];
-                const bool valid = r < cnt;
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int ch = h * 4 + j;
-                    float v[8];
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        const int g = ch * 8 + q;
-                        float val = 0.f;
-                        if (valid && g < a.G) {
-                            if (HAS_ATTR) {
-                                val = __ldg(a.ea + (int64_t)eids[r] * a.G + g);
-                            } else {
-                                const float u = d - goff[g];
-                                val = __expf(a.gcoeff * u * u);
-                            }
-                        }
-                        v[q] = val;
-                    }
-                    *reinterpret_cast<uint4*>(sm + oA1 + sw128_chunk_off(r, ch)) =
-                        make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
-                }
-            }
-            fence_proxy_async();
-            __syncthreads();
-            // ---- S4: GEMM1  D1 = rbf W1^T
+            const bool has_next = e0 + kTcTile < ee;
+            const int cnt_next = has_next ? (int)min((int64_t)kTcTile, ee - e0 - kTcTile) : 0;
+            Pre nxt{0, 0, r1, 0.f};
+            if (has_next && t < kTcTile) nxt = load_scalars(e0 + kTcTile, cnt_next, r0, r1);
+            const float* ds = dsb(buf);
+            float* Xt = Xbuf(buf);
+            __syncthreads();  // A1(i) complete (written during the previous walker phase / prologue)
+            // ---- GEMM1  D1 = rbf W1^T
             if (t == 0) {
                 tc_fence_after();
                 umma_tile(tmD1, smem_u32(sm + oA1), 16384, smem_u32(sm + oW1b), 16384, 64, idesc);
                 umma_commit(&bars[0]);
             }
-            // ---- S5: epilogue 1: h1 = ssp(D1 + b1) -> A2 (bf16, swizzled)
+            if (has_next && t < kTcTile) publish_scalars(nxt, cnt_next, buf ^ 1);
+            // ---- epilogue 1: h1 = ssp(D1 + b1) -> A2 (bf16, swizzled; slab 0 overwrites the rbf tile GEMM1 has consumed)
             mbar_wait(&bars[0], phase);
             tc_fence_after();
 #pragma unroll
@@ -244,20 +343,26 @@ __global__ void __launch_bounds__(256, 1) schnet_fwd_tc_kernel(TcArgs a, float* 
             }
             tc_fence_before();
             fence_proxy_async();
-            __syncthreads();
-            // ---- S6: GEMM2  D2 = h1 W2^T
+            __syncthreads();  // also publishes the next tile's scalars
+            // ---- GEMM2  D2 = h1 W2^T
             if (t == 0) {
                 tc_fence_after();
                 umma_tile(tmD2, smem_u32(sm + oA2), 16384, smem_u32(sm + oW2b), 16384, 128, idesc);
                 umma_commit(&bars[1]);
             }
-            // ---- S7: epilogue 2: message = (D2 + b2) * C * x1[src]  (in place over the gathered tile)
-            __pipeline_wait_prior(0);
+            // ---- prefetch: gather of the next tile into the other X buffer
+            if (has_next) {
+                issue_gather(cnt_next, buf ^ 1);
+                __pipeline_wait_prior(1);  // everything but the gather just issued: this tile's rows have landed
+            } else {
+                __pipeline_wait_prior(0);
+            }
             __syncthreads();
+            // ---- epilogue 2: message = (D2 + b2) * C * x1[src]  (in place over the gathered tile)
             mbar_wait(&bars[1], phase);
             tc_fence_after();
             {
-                const float C = Cs[row];
+                const float C = ds[128 + row];
 #pragma unroll
                 for (int part = 0; part < 2; ++part) {
                     float v[32];
@@ -278,20 +383,33 @@ __global__ void __launch_bounds__(256, 1) schnet_fwd_tc_kernel(TcArgs a, float* 
             tc_fence_before();
             __syncthreads();
             phase ^= 1;
-            // ---- S8: segmented sum by column threads
             if (t < F) {
-                for (int k = 0; k < cnt; ++k) {
-                    const int64_t e = e0 + k;
-                    while (e >= row_end) {
-                        agg[(int64_t)cur * F + t] = acc;
-                        acc = 0.f;
-                        ++cur;
-                        row_end = __ldg(a.rowptr + cur + 1);
+                // ---- warps 0-3: segmented sum, thread = feature column; row ids come from shared memory
+                const int* rid = isb(buf) + 256;
+                for (int k0 = 0; k0 < cnt; k0 += 8) {
+                    float v[8];
+                    int r[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) v[j] = Xt[(k0 + j) * kLdX + t];     // rows >= cnt are zero / stale but unused
+                    const int4 ra = *reinterpret_cast<const int4*>(rid + k0), rb = *reinterpret_cast<const int4*>(rid + k0 + 4);
+                    r[0] = ra.x; r[1] = ra.y; r[2] = ra.z; r[3] = ra.w; r[4] = rb.x; r[5] = rb.y; r[6] = rb.z; r[7] = rb.w;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        if (k0 + j < cnt) {
+                            if (r[j] != cur) {  // row change: store the finished row, zero-fill rows without edges
+                                agg[(int64_t)cur * F + t] = acc;
+                                for (int z = cur + 1; z < r[j]; ++z) agg[(int64_t)z * F + t] = 0.f;
+                                acc = 0.f;
+                                cur = r[j];
+                            }
+                            acc += v[j];
+                        }
                     }
-                    acc += Xt[k * kLdX + t];
                 }
+            } else if (has_next) {
+                // ---- warps 4-7: radial basis of the next tile -> A1 (GEMM2 has completed: A2 slab 0 is free)
+                rbf_tile(buf ^ 1, cnt_next, t - 128, 128);
             }
-            __syncthreads();
         }
         if (t < F) {
             while (cur < r1) {
@@ -336,4 +454,12 @@ extern "C" int gmp_umma_selftest(const float* A, const float* B, float* out, int
     GMP_CUDA(cudaFuncSetAttribute(umma_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     umma_selftest_kernel<<<1, 128, smem, stream>>>(A, B, out, K);
     return check_launch("umma_selftest_kernel");
+}
+
+extern "C" int gmp_umma_selftest_mn(const float* A, const float* B, float* out, int32_t N, gmp_stream_t stream) {
+    GMP_REQUIRE(A && B && out && (N == 64 || N == 128), "umma_selftest_mn: N must be 64 or 128");
+    const int smem = 65536 + 1024;
+    GMP_CUDA(cudaFuncSetAttribute(umma_selftest_mn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    umma_selftest_mn_kernel<<<1, 128, smem, stream>>>(A, B, out, N);
+    return check_launch("umma_selftest_mn_kernel");
 }

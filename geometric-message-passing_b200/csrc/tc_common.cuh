@@ -74,11 +74,25 @@ __device__ __forceinline__ uint64_t umma_desc_k128(uint32_t smem_addr) {
     return d;
 }
 
+// Shared-memory operand, MN-major, 128-byte swizzle: the tile is stored as [K rows][64 bf16 along M/N] slabs
+// (row = 128 B, 8-row groups 1024 B apart = stride byte offset; slabs of 64 M/N elements `lbo` bytes apart =
+// leading byte offset).  The same bytes read through umma_desc_k128 are the transposed operand.
+__device__ __forceinline__ uint64_t umma_desc_mn128(uint32_t smem_addr, uint32_t lbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
 // Instruction descriptor, kind::f16: bf16 x bf16 -> fp32, both operands K-major, M x N tile.
 //   [4,6) D format = 1 (f32) | [7,10) A format = 1 (bf16) | [10,13) B format = 1 (bf16) | bit 15/16 A/B major = 0 (K) |
 //   [17,23) N >> 3 | [24,29) M >> 4
-__device__ __forceinline__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+__device__ __forceinline__ constexpr uint32_t umma_idesc_bf16(int M, int N, bool a_mn = false, bool b_mn = false) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
+           ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
 // D[tmem] (+)= A[smem] * B[smem]^T, issued by ONE thread
@@ -113,6 +127,15 @@ __device__ __forceinline__ void umma_tile(uint32_t d_tmem, uint32_t a_base, uint
         const uint32_t bo = b_base + (k >> 6) * b_slab + ((k & 63) >> 4) * 32;
         umma_bf16(d_tmem, umma_desc_k128(ao), umma_desc_k128(bo), idesc, (k > 0 || accumulate_first) ? 1u : 0u);
     }
+}
+
+// D[M x N] (+)= sum over K = 16*nk tile rows of A[k][m] * B[k][n]: both operands stored [K rows][M or N] (MN-major),
+// slabs of 64 columns `a_lbo` / `b_lbo` bytes apart; a K step of 16 rows advances the start address by 2048 B.
+__device__ __forceinline__ void umma_tile_mn(uint32_t d_tmem, uint32_t a_base, uint32_t a_lbo, uint32_t b_base, uint32_t b_lbo,
+                                             int K, uint32_t idesc, bool accumulate_first) {
+    for (int k = 0; k < K; k += 16)
+        umma_bf16(d_tmem, umma_desc_mn128(a_base + (k >> 3) * 1024, a_lbo), umma_desc_mn128(b_base + (k >> 3) * 1024, b_lbo), idesc,
+                  (k > 0 || accumulate_first) ? 1u : 0u);
 }
 
 }  // namespace tc

@@ -184,6 +184,9 @@ int gmp_schnet_cfconv_bwd(const int32_t* rowptr, const int32_t* col, const int32
 /* Hardware self test of the tcgen05 path: out[128,128] = bf16(A[128,K]) x bf16(B[128,K])^T with fp32 accumulation
  * in TMEM, through the same shared-memory descriptors and 128-byte swizzle the fused kernels use.  K in {64, 128}. */
 int gmp_umma_selftest(const float* A, const float* B, float* out, int32_t K, gmp_stream_t stream);
+/* Same for MN-major (transposed) operands: out[128,N] = sum_k bf16(A[k,m]) * bf16(B[k,n]), A [128,128], B [128,N], N in {64,128}
+ * (the layout the weight-gradient GEMMs consume). */
+int gmp_umma_selftest_mn(const float* A, const float* B, float* out, int32_t N, gmp_stream_t stream);
 
 /* ============================================================================================ */
 /* EGNN edge path (models/layers/egnn_layer.py:62-80: message + aggregate, fused)                 */

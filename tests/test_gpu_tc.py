@@ -24,6 +24,19 @@ def test_umma_selftest(K):
     assert rel_err(out, ref) <= 1e-5
 
 
+@pytest.mark.parametrize("N", [64, 128])
+def test_umma_selftest_mn_major(N):
+    from gmp_b200._lib import call, ptr
+    g = torch.Generator().manual_seed(N)
+    A = torch.randn(128, 128, generator=g).cuda()   # [k, m]
+    B = torch.randn(128, N, generator=g).cuda()     # [k, n]
+    out = torch.zeros(128, N, device="cuda")
+    call("gmp_umma_selftest_mn", ptr(A), ptr(B), ptr(out), N)
+    torch.cuda.synchronize()
+    ref = A.bfloat16().double().T @ B.bfloat16().double()
+    assert rel_err(out, ref) <= 1e-5
+
+
 @pytest.mark.parametrize("graphs,nodes,lazy", [(64, 32, True), (9, 21, False)])
 def test_cfconv_bf16_tc_vs_fp32(graphs, nodes, lazy):
     import gmp_b200
