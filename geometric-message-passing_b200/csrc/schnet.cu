@@ -422,6 +422,9 @@ static int launch_bwd(const SchnetArgs& a, bool has_attr, bool need, const float
 int schnet_fwd_tc_launch(const int32_t* rowptr, const int32_t* col, const int32_t* perm, int64_t n, int64_t E,
                          const float* ew, const float* ea, const float* x1, const gmp_schnet_filter* f, float* agg,
                          cudaStream_t stream);  // schnet_tc.cu
+int schnet_bwd_tc_launch(const int32_t* rowptr, const int32_t* col, const int32_t* perm, int64_t n, int64_t E,
+                         const float* ew, const float* ea, const float* x1, const gmp_schnet_filter* f, const float* g_agg,
+                         float* parts, int nparts, cudaStream_t stream);  // schnet_tc.cu
 
 }  // namespace gmp
 
@@ -461,10 +464,14 @@ int gmp_schnet_cfconv_bwd(const int32_t* rowptr, const int32_t* col, const int32
     GMP_REQUIRE(rowptr && g_agg && wgrad_parts && (num_edges == 0 || (col && edge_weight && x1)), "schnet_cfconv_bwd: NULL pointer");
     GMP_REQUIRE(edge_attr || filt->gauss_offset, "schnet_cfconv_bwd: need edge_attr or gauss_offset");
     GMP_REQUIRE(!d_edge_attr || edge_attr, "schnet_cfconv_bwd: d_edge_attr requested without edge_attr");
-    // the filter-side backward has no tensor-core variant in this build: GMP_BF16_TC runs the fp32 kernel here
     GMP_REQUIRE(precision == GMP_FP32_STRICT || precision == GMP_BF16_TC, "schnet_cfconv_bwd: unknown precision mode %d", precision);
     const SchnetArgs a = make_args(rowptr, col, perm, n, num_edges, edge_weight, edge_attr, x1, filt);
     const bool need = d_edge_weight != nullptr || d_edge_attr != nullptr;
+    // tensor-core variant: weight gradients only, F = 128, G <= 63 (column 63 of the basis tile carries the bias sums);
+    // gradients w.r.t. the edge inputs run the fp32 kernel in either mode
+    if (precision == GMP_BF16_TC && !need && filt->num_filters == 128 && filt->num_gaussians <= 63 && num_edges > 0)
+        return schnet_bwd_tc_launch(rowptr, col, perm, n, num_edges, edge_weight, edge_attr, x1, filt, g_agg, wgrad_parts,
+                                    gmp_schnet_bwd_num_parts(num_edges), stream);
     return filt->num_filters == 128 ? launch_bwd<128>(a, edge_attr != nullptr, need, g_agg, wgrad_parts, d_edge_weight, d_edge_attr, stream)
                                     : launch_bwd<64>(a, edge_attr != nullptr, need, g_agg, wgrad_parts, d_edge_weight, d_edge_attr, stream);
 }

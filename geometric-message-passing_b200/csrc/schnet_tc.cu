@@ -424,6 +424,327 @@ __global__ void __launch_bounds__(256, 1) schnet_fwd_tc_kernel(TcArgs a, float* 
     if (warp == 0) tmem_dealloc<256>(tm);
 }
 
+// ------------------------------------------------------------------------------------------------
+// filter-side backward on tcgen05 (weight gradients only; d edge_weight / d edge_attr use the fp32 kernel)
+//
+// Per 128-edge tile (e = tile row = TMEM lane; all shared operand tiles are [e][feature] bf16, 128B-swizzled, so the
+// same bytes serve as K-major A of the "per-edge" GEMMs and as MN-major operands of the "sum over edges" GEMMs):
+//   GEMM1  D1  = R W1^T                      (pre1; R = radial basis with a ones column at g = 63)
+//   P      = x1[src] * g[dst] * C            (dpre2, SIMT)            H = ssp(D1 + b1)   (h1)
+//   GEMM3  D3  = P W2                        (dh1)
+//   acc    dW2 += P^T H ,  db2|. += P^T R    (column 63 of R is 1 -> db2)            [TMEM accumulators, whole kernel]
+//   Q      = D3 * sigmoid(pre1)              (dpre1, written over P)
+//   acc    dW1|db1 += Q^T R                  (column 63 -> db1)
+// TMEM: D1 128 | D3 128 | dW2 128 | dW1 64 | db2 64 = 512 columns.
+// ------------------------------------------------------------------------------------------------
+constexpr int bW1b = 0;                          // [128 f][64 g]        16 KB
+constexpr int bW2T = bW1b + 16384;               // 2 x [128 f][64 f']   32 KB  (W2 transposed)
+constexpr int bR = bW2T + 32768;                 // 2 x [128 e][64 g]    32 KB  (double buffered)
+constexpr int bP = bR + 32768;                   // 2 x [128 e][64 f']   32 KB  (dpre2, then dpre1)
+constexpr int bH = bP + 32768;                   // 2 x [128 e][64 f]    32 KB  (h1)
+constexpr int bX = bH + 32768;                   // [128][132] fp32      66 KB
+constexpr int bBias = bX + kXBytes;              // b1[128], goff[64]
+constexpr int bScal = bBias + (128 + 64) * 4;    // 2 x { d[128], C[128] }
+constexpr int bInts = bScal + 2 * 1024;          // 2 x { src[128], eid[128], rowid[128] }
+constexpr int bBar = bInts + 2 * kIntsBytes;     // 3 mbarriers + tmem ptr
+constexpr int kTcBwdSmem = bBar + 64 + 1024;
+
+template <bool HAS_ATTR>
+__global__ void __launch_bounds__(256, 1)
+schnet_bwd_tc_kernel(TcArgs a, const float* __restrict__ g_agg, float* __restrict__ parts) {
+    constexpr int F = 128;
+    extern __shared__ __align__(16) uint8_t smraw[];
+    uint8_t* sm = smraw + ((1024u - (smem_u32(smraw) & 1023u)) & 1023u);
+    float* b1s = reinterpret_cast<float*>(sm + bBias);
+    float* goff = b1s + 128;
+    float* Xt = reinterpret_cast<float*>(sm + bX);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sm + bBar);
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(sm + bBar + 32);
+    const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+    auto dsb = [&](int b) { return reinterpret_cast<float*>(sm + bScal + b * 1024); };
+    auto isb = [&](int b) { return reinterpret_cast<int*>(sm + bInts + b * kIntsBytes); };
+
+    for (int x = t; x < 128 * 8; x += 256) {  // W1 [f][g] K-major, g padded to 64 with zeros
+        const int f = x >> 3, ch = x & 7;
+        uint32_t p[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int g0 = ch * 8 + 2 * j;
+            p[j] = pack_bf16(g0 < a.G ? __ldg(a.w1 + f * a.G + g0) : 0.f, g0 + 1 < a.G ? __ldg(a.w1 + f * a.G + g0 + 1) : 0.f);
+        }
+        *reinterpret_cast<uint4*>(sm + bW1b + sw128_chunk_off(f, ch)) = make_uint4(p[0], p[1], p[2], p[3]);
+    }
+    for (int x = t; x < 128 * 16; x += 256) {  // W2T [f][f'] = W2[f'][f], K = f' in two slabs
+        const int f = x >> 4, ch16 = x & 15, kb = ch16 >> 3, ch = ch16 & 7;
+        float v[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) v[q] = __ldg(a.w2 + (int64_t)(kb * 64 + ch * 8 + q) * F + f);
+        *reinterpret_cast<uint4*>(sm + bW2T + kb * 16384 + sw128_chunk_off(f, ch)) =
+            make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+    }
+    if (t < 128) b1s[t] = __ldg(a.b1 + t);
+    if (t < 64) goff[t] = (!HAS_ATTR && t < a.G) ? __ldg(a.goff + t) : 1.0e18f;
+    if (t == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        mbar_init(&bars[2], 1);
+        fence_mbar_init();
+    }
+    if (warp == 0) tmem_alloc<512>(tmem_ptr);
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tm = *tmem_ptr;
+    const uint32_t tmD1 = tm, tmD3 = tm + 128, tmW2 = tm + 256, tmW1 = tm + 384, tmB2 = tm + 448;
+    const uint32_t id_kk = umma_idesc_bf16(128, 128), id_mn128 = umma_idesc_bf16(128, 128, true, true),
+                   id_mn64 = umma_idesc_bf16(128, 64, true, true);
+    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+    const int row = (warp & 3) * 32 + lane;
+    const int chalf = warp >> 2;
+    const float cw = 3.14159265358979323846f / a.cutoff;
+    const float c2 = a.gcoeff * 1.4426950408889634f;
+    uint32_t it = 0;  // tiles processed by this CTA (mbarrier phase = it & 1)
+
+    struct Pre { int src, eid, rowid; float d; };
+    auto load_scalars = [&](int64_t e0, int cnt, int r0, int r1) {
+        Pre p{0, 0, r0, 0.f};
+        if (t < cnt) {
+            const int64_t k = e0 + t;
+            p.eid = a.perm ? __ldg(a.perm + k) : (int)k;
+            p.src = __ldg(a.col + k);
+            p.d = __ldg(a.ew + p.eid);
+            int lo = r0, hi = r1;
+            while (hi - lo > 1) {
+                const int mid = (lo + hi) >> 1;
+                if ((int64_t)__ldg(a.rowptr + mid) <= k) lo = mid; else hi = mid;
+            }
+            p.rowid = lo;
+        }
+        return p;
+    };
+    auto publish_scalars = [&](const Pre& p, int cnt, int b) {
+        float* d = dsb(b);
+        int* is = isb(b);
+        d[t] = t < cnt ? p.d : 1.0e18f;
+        d[128 + t] = t < cnt ? 0.5f * (__cosf(p.d * cw) + 1.0f) : 0.f;
+        is[t] = p.src;
+        is[128 + t] = p.eid;
+        is[256 + t] = p.rowid;
+    };
+    auto issue_gather = [&](int cnt, int b) {
+        const int* srcs = isb(b);
+        for (int x = t; x < kTcTile * 32; x += 256) {
+            const int r = x >> 5, c = x & 31;
+            if (r < cnt) __pipeline_memcpy_async(Xt + r * kLdX + 4 * c, a.x1 + (int64_t)srcs[r] * F + 4 * c, 16);
+            else *reinterpret_cast<float4*>(Xt + r * kLdX + 4 * c) = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        __pipeline_commit();
+    };
+    auto rbf_tile = [&](int b, int cnt) {  // -> R[b], with a ones column at g = 63
+        const float* ds = dsb(b);
+        const int* eids = isb(b) + 128;
+        for (int x = t; x < kTcTile * 8; x += 256) {
+            const int r = x >> 3, ch = x & 7;
+            float v[8];
+            if (HAS_ATTR) {
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const int g = ch * 8 + q;
+                    v[q] = (r < cnt && g < a.G) ? __ldg(a.ea + (int64_t)eids[r] * a.G + g) : 0.f;
+                }
+            } else {
+                const float d = ds[r];
+                const float4 o0 = *reinterpret_cast<const float4*>(goff + ch * 8), o1 = *reinterpret_cast<const float4*>(goff + ch * 8 + 4);
+                const float off[8] = {o0.x, o0.y, o0.z, o0.w, o1.x, o1.y, o1.z, o1.w};
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const float u = d - off[q];
+                    v[q] = ex2_approx(c2 * u * u);
+                }
+            }
+            if (ch == 7) v[7] = 1.0f;
+            *reinterpret_cast<uint4*>(sm + bR + b * 16384 + sw128_chunk_off(r, ch)) =
+                make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+        }
+        fence_proxy_async();
+    };
+
+    for (int rg = blockIdx.x; rg < a.nranges; rg += gridDim.x) {
+        const int r0 = lower_bound_row(a.rowptr, (int)a.n, (int64_t)rg * kTcRange);
+        const int r1 = (rg + 1 == a.nranges) ? (int)a.n : lower_bound_row(a.rowptr, (int)a.n, (int64_t)(rg + 1) * kTcRange);
+        if (r0 >= r1) continue;
+        const int64_t eb = __ldg(a.rowptr + r0), ee = __ldg(a.rowptr + r1);
+        if (eb >= ee) continue;
+        int buf = 0;
+        if (it > 0) {  // the previous range's last dW1 MMA still reads P and R[.]: drain it before reusing the buffers
+            mbar_wait(&bars[2], (it - 1) & 1);
+            tc_fence_after();
+        }
+        __syncthreads();
+        {
+            const int cnt0 = (int)min((int64_t)kTcTile, ee - eb);
+            if (t < kTcTile) publish_scalars(load_scalars(eb, cnt0, r0, r1), cnt0, 0);
+            __syncthreads();
+            issue_gather(cnt0, 0);
+            rbf_tile(0, cnt0);
+        }
+        bool drained = true;  // no dW1 MMA outstanding on P / R[buf ^ 1]
+        for (int64_t e0 = eb; e0 < ee; e0 += kTcTile, buf ^= 1, ++it) {
+            const int cnt = (int)min((int64_t)kTcTile, ee - e0);
+            const bool has_next = e0 + kTcTile < ee;
+            const int cnt_next = has_next ? (int)min((int64_t)kTcTile, ee - e0 - kTcTile) : 0;
+            const uint32_t ph = it & 1;
+            Pre nxt{0, 0, r0, 0.f};
+            if (has_next && t < kTcTile) nxt = load_scalars(e0 + kTcTile, cnt_next, r0, r1);
+            if (!drained) {  // dW1 MMA of the previous tile (reads P as Q and R[buf ^ 1])
+                mbar_wait(&bars[2], (it - 1) & 1);
+                tc_fence_after();
+            }
+            __pipeline_wait_prior(0);  // x1 rows of this tile
+            __syncthreads();           // [A] R[buf], X, scalars(buf) complete
+            const uint32_t Rb = smem_u32(sm + bR + buf * 16384), Pb = smem_u32(sm + bP), Hb = smem_u32(sm + bH);
+            if (t == 0) {
+                tc_fence_after();
+                umma_tile(tmD1, Rb, 16384, smem_u32(sm + bW1b), 16384, 64, id_kk);
+                umma_commit(&bars[0]);
+            }
+            // ---- P = x1[src] * g[dst] * C   (bf16, [e][f'])
+            {
+                const float C = dsb(buf)[128 + row];
+                const float* grow = g_agg + (int64_t)isb(buf)[256 + row] * F;
+#pragma unroll
+                for (int ch = 0; ch < 8; ++ch) {
+                    const int c = chalf * 64 + ch * 8;
+                    const float4 x0 = *reinterpret_cast<const float4*>(Xt + row * kLdX + c), x1v = *reinterpret_cast<const float4*>(Xt + row * kLdX + c + 4);
+                    float4 g0 = make_float4(0.f, 0.f, 0.f, 0.f), g1 = g0;
+                    if (row < cnt) {
+                        g0 = ldg4(grow + c);
+                        g1 = ldg4(grow + c + 4);
+                    }
+                    *reinterpret_cast<uint4*>(sm + bP + chalf * 16384 + sw128_chunk_off(row, ch)) =
+                        make_uint4(pack_bf16(x0.x * g0.x * C, x0.y * g0.y * C), pack_bf16(x0.z * g0.z * C, x0.w * g0.w * C),
+                                   pack_bf16(x1v.x * g1.x * C, x1v.y * g1.y * C), pack_bf16(x1v.z * g1.z * C, x1v.w * g1.w * C));
+                }
+            }
+            if (has_next && t < kTcTile) publish_scalars(nxt, cnt_next, buf ^ 1);
+            // ---- H = ssp(D1 + b1)   (bf16, [e][f])
+            mbar_wait(&bars[0], ph);
+            tc_fence_after();
+#pragma unroll
+            for (int part = 0; part < 2; ++part) {
+                float v[32];
+                const int c0 = chalf * 64 + part * 32;
+                tmem_ld32(tmD1 + lane_base + c0, v);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = ssp_fast(v[j] + b1s[c0 + j]);
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    *reinterpret_cast<uint4*>(sm + bH + chalf * 16384 + sw128_chunk_off(row, part * 4 + q)) =
+                        make_uint4(pack_bf16(v[8 * q], v[8 * q + 1]), pack_bf16(v[8 * q + 2], v[8 * q + 3]),
+                                   pack_bf16(v[8 * q + 4], v[8 * q + 5]), pack_bf16(v[8 * q + 6], v[8 * q + 7]));
+            }
+            tc_fence_before();
+            fence_proxy_async();
+            __syncthreads();  // [B] P, H complete; X consumed; next scalars published
+            if (t == 0) {
+                tc_fence_after();
+                umma_tile(tmD3, Pb, 16384, smem_u32(sm + bW2T), 16384, 128, id_kk);       // dh1 = P W2
+                umma_tile_mn(tmW2, Pb, 16384, Hb, 16384, 128, id_mn128, it > 0);            // dW2 += P^T H
+                umma_tile_mn(tmB2, Pb, 16384, Rb, 16384, 128, id_mn64, it > 0);             // [. | db2] += P^T R
+                umma_commit(&bars[1]);
+            }
+            if (has_next) issue_gather(cnt_next, buf ^ 1);
+            // ---- Q = D3 * sigmoid(pre1), sigmoid from h1: 1 - exp(-softplus) = 1 - 0.5 * 2^(-h1 log2 e)
+            mbar_wait(&bars[1], ph);
+            tc_fence_after();
+#pragma unroll
+            for (int part = 0; part < 2; ++part) {
+                float v[32];
+                const int c0 = chalf * 64 + part * 32;
+                tmem_ld32(tmD3 + lane_base + c0, v);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const uint32_t off = chalf * 16384 + sw128_chunk_off(row, part * 4 + q);
+                    const uint4 hp = *reinterpret_cast<const uint4*>(sm + bH + off);
+                    const uint32_t hw[4] = {hp.x, hp.y, hp.z, hp.w};
+                    uint32_t o[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const __nv_bfloat162 hb = *reinterpret_cast<const __nv_bfloat162*>(&hw[j]);
+                        const float2 hf = __bfloat1622float2(hb);
+                        const float s0 = fmaf(-0.5f, ex2_approx(-1.4426950408889634f * hf.x), 1.0f);
+                        const float s1 = fmaf(-0.5f, ex2_approx(-1.4426950408889634f * hf.y), 1.0f);
+                        o[j] = pack_bf16(v[8 * q + 2 * j] * s0, v[8 * q + 2 * j + 1] * s1);
+                    }
+                    *reinterpret_cast<uint4*>(sm + bP + off) = make_uint4(o[0], o[1], o[2], o[3]);
+                }
+            }
+            tc_fence_before();
+            fence_proxy_async();
+            __syncthreads();  // [C] Q complete
+            if (t == 0) {
+                tc_fence_after();
+                umma_tile_mn(tmW1, Pb, 16384, Rb, 16384, 128, id_mn64, it > 0);             // [dW1 | db1] += Q^T R
+                umma_commit(&bars[2]);
+            }
+            drained = false;
+            if (has_next) rbf_tile(buf ^ 1, cnt_next);  // R[buf ^ 1] was last read by the tile before this one (drained above)
+        }
+    }
+    // ---- drain, then write this CTA's partial gradients: [dW1 F x 64 | db1 F | dW2 F x F | db2 F]
+    float* my = parts + (int64_t)blockIdx.x * (F * 64 + F + F * F + F);
+    if (it > 0) {
+        mbar_wait(&bars[2], (it - 1) & 1);
+        tc_fence_after();
+        for (int c0 = chalf * 64; c0 < chalf * 64 + 64; c0 += 32) {  // dW2[f' = row][f]
+            float v[32];
+            tmem_ld32(tmW2 + lane_base + c0, v);
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+                *reinterpret_cast<float4*>(my + F * 64 + F + row * F + c0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        }
+        {   // dW1[f = row][g] (32 columns per warp half); column 63 = db1
+            float v[32];
+            const int c0 = chalf * 32;
+            tmem_ld32(tmW1 + lane_base + c0, v);
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+                *reinterpret_cast<float4*>(my + row * 64 + c0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            if (chalf == 1) my[F * 64 + row] = v[31];
+        }
+        if (chalf == 1) {  // db2[f' = row] = column 63 of the P^T R accumulator
+            float v[32];
+            tmem_ld32(tmB2 + lane_base + 32, v);
+            my[F * 64 + F + F * F + row] = v[31];
+        }
+    } else {
+        for (int x = t; x < F * 64 + F + F * F + F; x += 256) my[x] = 0.f;
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc<512>(tm);
+}
+
+int schnet_bwd_tc_launch(const int32_t* rowptr, const int32_t* col, const int32_t* perm, int64_t n, int64_t E,
+                         const float* ew, const float* ea, const float* x1, const gmp_schnet_filter* f, const float* g_agg,
+                         float* parts, int nparts, cudaStream_t stream) {
+    TcArgs a;
+    a.rowptr = rowptr; a.col = col; a.perm = perm; a.n = n; a.E = E; a.ew = ew; a.ea = ea; a.x1 = x1;
+    a.w1 = f->w1; a.b1 = f->b1; a.w2 = f->w2; a.b2 = f->b2; a.goff = f->gauss_offset;
+    a.G = f->num_gaussians; a.cutoff = f->cutoff; a.gcoeff = f->gauss_coeff;
+    a.nranges = (int)(E > 0 ? ceil_div(E, kTcRange) : 1);
+    const int grid = nparts;  // the caller sized the partial buffer with gmp_schnet_bwd_num_parts
+    if (ea) {
+        GMP_CUDA(cudaFuncSetAttribute(schnet_bwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcBwdSmem));
+        schnet_bwd_tc_kernel<true><<<grid, 256, kTcBwdSmem, stream>>>(a, g_agg, parts);
+    } else {
+        GMP_CUDA(cudaFuncSetAttribute(schnet_bwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcBwdSmem));
+        schnet_bwd_tc_kernel<false><<<grid, 256, kTcBwdSmem, stream>>>(a, g_agg, parts);
+    }
+    return check_launch("schnet_bwd_tc_kernel");
+}
+
 int schnet_fwd_tc_launch(const int32_t* rowptr, const int32_t* col, const int32_t* perm, int64_t n, int64_t E,
                          const float* ew, const float* ea, const float* x1, const gmp_schnet_filter* f, float* agg,
                          cudaStream_t stream) {
