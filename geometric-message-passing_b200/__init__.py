@@ -23,4 +23,14 @@ from .tfn import (BatchNorm, Gate, RadialEmbeddingBlock, SphericalHarmonics, Ten
 from .mace import (Contraction, EquivariantLinear, EquivariantProductBasisBlock, MACEModel,  # noqa: F401
                    SymmetricContraction, reshape_irreps)
 
+
+def set_fast_matmul(enabled: bool = True) -> None:
+    """Node-side `nn.Linear` layers are plain library GEMMs (cuBLAS).  In precision="bf16" runs they may use TF32
+    tensor cores (10-bit mantissa, well inside that mode's 1e-2 tolerance); the fp32-strict mode must keep this off.
+    This flips PyTorch's process-wide matmul precision switch."""
+    import torch
+    torch.backends.cuda.matmul.allow_tf32 = bool(enabled)
+    torch.backends.cudnn.allow_tf32 = bool(enabled)
+
+
 __version__ = "0.1.0"

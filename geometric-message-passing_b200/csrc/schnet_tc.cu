@@ -234,7 +234,10 @@ __global__ void __launch_bounds__(256, 1) schnet_fwd_tc_kernel(TcArgs a, float* 
             p.eid = a.perm ? __ldg(a.perm + k) : (int)k;
             p.src = __ldg(a.col + k);
             p.d = __ldg(a.ew + p.eid);
-            int lo = r0, hi = r1;  // CSR row of edge k: last row whose first edge is <= k
+        }
+        {   // CSR row of the edge (last row whose first edge is <= k); padding slots repeat the last valid edge's row
+            const int64_t k = e0 + min(t, cnt - 1);
+            int lo = r0, hi = r1;
             while (hi - lo > 1) {
                 const int mid = (lo + hi) >> 1;
                 if ((int64_t)__ldg(a.rowptr + mid) <= k) lo = mid; else hi = mid;
@@ -384,18 +387,21 @@ __global__ void __launch_bounds__(256, 1) schnet_fwd_tc_kernel(TcArgs a, float* 
             __syncthreads();
             phase ^= 1;
             if (t < F) {
-                // ---- warps 0-3: segmented sum, thread = feature column; row ids come from shared memory
+                // ---- warps 0-3: segmented sum, thread = feature column; row ids come from shared memory.
+                // Groups of 8 edges: when the whole group still belongs to the open row (the common case) it is a
+                // branch-free tree add; otherwise edge by edge.  Padding rows hold zeros and repeat the last row id.
                 const int* rid = isb(buf) + 256;
                 for (int k0 = 0; k0 < cnt; k0 += 8) {
                     float v[8];
-                    int r[8];
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) v[j] = Xt[(k0 + j) * kLdX + t];     // rows >= cnt are zero / stale but unused
+                    for (int j = 0; j < 8; ++j) v[j] = Xt[(k0 + j) * kLdX + t];
                     const int4 ra = *reinterpret_cast<const int4*>(rid + k0), rb = *reinterpret_cast<const int4*>(rid + k0 + 4);
-                    r[0] = ra.x; r[1] = ra.y; r[2] = ra.z; r[3] = ra.w; r[4] = rb.x; r[5] = rb.y; r[6] = rb.z; r[7] = rb.w;
+                    if (rb.w == cur) {
+                        acc += ((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7]));
+                    } else {
+                        const int r[8] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        if (k0 + j < cnt) {
+                        for (int j = 0; j < 8; ++j) {
                             if (r[j] != cur) {  // row change: store the finished row, zero-fill rows without edges
                                 agg[(int64_t)cur * F + t] = acc;
                                 for (int z = cur + 1; z < r[j]; ++z) agg[(int64_t)z * F + t] = 0.f;

@@ -157,16 +157,18 @@ class Graph:
 
 
 _GRAPH_CACHE: Dict[Tuple, Graph] = {}
+_GRAPH_CACHE_SIZE = 4  # a training step touches one or two graphs; a small cache lets the allocator recycle their buffers
 
 
 def get_graph(edge_index: torch.Tensor, n: int) -> Graph:
     """Graph for this edge_index, cached on (storage pointer, shape, version, n) so that the layers of a
-    model, which all receive the same tensor, sort it once."""
+    model, which all receive the same tensor, sort it once.  The cache keeps the tensor alive, so the pointer
+    cannot be recycled for a different edge list while its entry exists."""
     key = (edge_index.data_ptr(), tuple(edge_index.shape), edge_index._version, n, str(edge_index.device))
     g = _GRAPH_CACHE.get(key)
-    if g is None or g.edge_index.data_ptr() != edge_index.contiguous().data_ptr():
-        if len(_GRAPH_CACHE) > 16:
-            _GRAPH_CACHE.clear()
+    if g is None:
+        while len(_GRAPH_CACHE) >= _GRAPH_CACHE_SIZE:
+            _GRAPH_CACHE.pop(next(iter(_GRAPH_CACHE)))  # oldest entry
         g = Graph(edge_index, n)
         _GRAPH_CACHE[key] = g
     return g

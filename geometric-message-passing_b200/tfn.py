@@ -88,10 +88,10 @@ class BatchNorm(nn.Module):
         """mean over dim 0, across ranks when a process group is attached."""
         if self.process_group is None:
             return t.mean(0)
-        import torch.distributed as dist
+        import torch.distributed.nn.functional as dist_fn  # autograd-aware collectives
         s = t.sum(0)
         n = torch.tensor([float(count)], device=t.device, dtype=t.dtype)
-        s, n = dist.nn.functional.all_reduce(s, group=self.process_group), dist.nn.functional.all_reduce(n, group=self.process_group)
+        s, n = dist_fn.all_reduce(s, group=self.process_group), dist_fn.all_reduce(n, group=self.process_group)
         return s / n
 
     def forward(self, x):
