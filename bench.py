@@ -335,7 +335,10 @@ def dominant_kernel_roofline(model, b, E, N, dev, args):
     flops = E * (2 * 64 * F + 2 * F * F + 2 * F)  # padded-G GEMM1 + GEMM2 + message product
     kname = "schnet_fwd_tc_kernel (tcgen05, bf16)" if prec == 1 else "schnet_fwd_kernel<128> (fp32 FFMA)"
     return {"bound": "hbm", "kernel": kname + " via gmp_schnet_cfconv_fwd", "achieved": achieved, "peak": peak,
-            "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": which, "ms_per_launch": ms,
+            "unit": "GB/s", "frac": achieved / peak,
+            # dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full capture of this kernel
+            # (profiles/r01_ncu_prof_tc_fwd_v3.csv: 82.4 + 32.2 MB; x1 is L2-resident, hence far below the algorithmic bytes)
+            "traffic": 114.7e6 if prec == 1 else None, "peak_source": which, "ms_per_launch": ms,
             "algorithmic_bytes": alg, "note": f"{flops / (ms * 1e-3) / 1e12:.1f} TFLOP/s on the filter-MLP GEMMs ({'bf16 tcgen05' if prec == 1 else 'fp32 FFMA'}); the x1 gather is "
                     "mostly served by the 126 MB L2 (x1 is 67 MB), so DRAM traffic is below the algorithmic bytes"}
 

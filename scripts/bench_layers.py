@@ -1,0 +1,90 @@
+"""Per-layer forward+backward timings of the other fused layers (fp32-strict kernels) at the BASELINE config shapes
+(reduced graph counts where the full size would take minutes in fp32).  Prints one JSON line per layer.
+usage: python scripts/bench_layers.py [egnn] [tfn] [mace] [symc]"""
+import json
+import os
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+
+import gmp_b200
+
+dev = torch.device("cuda")
+which = sys.argv[1:] or ["egnn", "tfn", "mace", "symc"]
+
+
+def timeit(fn, warm=2, reps=5):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(reps):
+        fn()
+    e.record()
+    torch.cuda.synchronize()
+    return s.elapsed_time(e) / reps
+
+
+def clouds(graphs, nodes, box, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    pos = (torch.rand(graphs * nodes, 3, generator=g) * box).to(dev)
+    batch = torch.arange(graphs).repeat_interleave(nodes).to(dev)
+    return pos, batch
+
+
+if "egnn" in which:
+    # config 5 geometry: density 8 / unit volume, r = 1 (~31 neighbours), one connected cube; N = 2^18 here
+    n_side = 32.0
+    g = torch.Generator().manual_seed(0)
+    pos = (torch.rand(2 ** 18, 3, generator=g) * n_side).to(dev)
+    ei = gmp_b200.radius_graph(pos, 1.0, None, max_num_neighbors=128)
+    N, E = pos.shape[0], ei.shape[1]
+    layer = gmp_b200.EGNNLayer(128).to(dev)
+    h = torch.randn(N, 128, device=dev, requires_grad=True)
+    p = pos.clone().requires_grad_(True)
+
+    def step():
+        layer.zero_grad(set_to_none=True)
+        out, pp = layer(h, p, ei)
+        (out.sum() + pp.sum()).backward()
+    ms = timeit(step)
+    flops = 3 * (E * (2 * 2 * 128 * 128 + 4 * 128) + N * 6 * 128 * 128)  # fused form: two 128x128 edge GEMMs
+    print(json.dumps({"layer": "EGNNLayer(128) fp32-strict", "workload": f"one radius graph N={N} E={E} (config-5 geometry)",
+                      "ms_fwd_bwd": ms, "edges_per_s": E / (ms * 1e-3), "tflops_fp32": flops / (ms * 1e-3) / 1e12}))
+
+for name, C, graphs in (("tfn", 64, 64), ("mace", 128, 32)):
+    if name not in which:
+        continue
+    pos, batch = clouds(graphs, 64, 4.0)
+    ei = gmp_b200.radius_graph(pos, 2.0, batch, max_num_neighbors=64)
+    N, E = pos.shape[0], ei.shape[1]
+    hid = f"{C}x0e+{C}x1o+{C}x2e"
+    conv = gmp_b200.TensorProductConvLayer(hid, hid, "1x0e+1x1o+1x2e", 8, 256, gate=(name == "tfn"), batch_norm=(name == "mace")).to(dev)
+    sh, ft = gmp_b200.edge_geometry(pos, ei, 2, gmp_b200.RadialEmbeddingBlock(2.0, 8, 5))
+    x = torch.randn(N, 9 * C, device=dev, requires_grad=True)
+
+    def step():
+        conv.zero_grad(set_to_none=True)
+        conv(x, ei, sh, ft).sum().backward()
+    ms = timeit(step, warm=1, reps=3)
+    wn = conv.tp.weight_numel
+    print(json.dumps({"layer": f"TensorProductConvLayer C={C} ({name} config, layer>=1) fp32-strict",
+                      "workload": f"{graphs} clouds x 64 nodes, N={N} E={E}, weight_numel={wn}", "ms_fwd_bwd": ms,
+                      "edges_per_s": E / (ms * 1e-3), "tflops_fp32": 4 * 2 * 256 * wn * E / (ms * 1e-3) / 1e12}))
+
+if "symc" in which:
+    N, C = 65536, 128
+    ir = f"{C}x0e+{C}x1o+{C}x2e"
+    blk = gmp_b200.EquivariantProductBasisBlock(ir, ir, 3, element_dependent=False, use_sc=True).to(dev)
+    x = torch.randn(N, C, 9, device=dev, requires_grad=True)
+    sc = torch.randn(N, 9 * C, device=dev)
+
+    def step():
+        blk.zero_grad(set_to_none=True)
+        blk(x, sc, None).sum().backward()
+    ms = timeit(step)
+    print(json.dumps({"layer": "EquivariantProductBasisBlock C=128 corr=3 (config 4 node side)", "workload": f"N={N}",
+                      "ms_fwd_bwd": ms, "nodes_per_s": N / (ms * 1e-3)}))
