@@ -1,0 +1,183 @@
+"""Multi-GPU for the two workload shapes of SURVEY.md §8e (the reference itself has no distributed code).
+
+1. Batched small graphs (configs 2-4): shard by graph, no data-path collective; gradients are all-reduced after
+   backward (`allreduce_gradients`), e3nn BatchNorm statistics through `gmp_b200.BatchNorm(process_group=...)`.
+
+2. One large radius graph (config 5): partition by destination node.  Nodes are sorted along x and cut into `world`
+   contiguous slabs; rank p owns the destination rows of slab p and needs, as message sources, the nodes of other slabs
+   within `r` of its boundaries (the halo).  Because everything is sorted by x, what rank p sends to rank q is one
+   contiguous range of its owned rows, so packing is a slice, the exchange is grouped point-to-point send/recv
+   (ncclSend/ncclRecv under NCCL, also available under gloo for the CPU tests), and the backward adds the returned
+   halo gradients onto those ranges in fixed rank order -- deterministic, no atomics.
+   Local numbering is [left halo | owned | right halo], i.e. ascending global order, so the local radius graph lists
+   every owned row's neighbours in the same order as the single-GPU graph: the partitioned reduction is the same sum.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import List, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def allreduce_gradients(params, group=None) -> Optional[torch.Tensor]:
+    """Sum the gradients of `params` across ranks through one flat buffer; writes the sums back in place."""
+    grads = [p.grad for p in params if p.grad is not None]
+    if not grads or not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return None
+    flat = torch.cat([g.reshape(-1) for g in grads])
+    dist.all_reduce(flat, group=group)
+    off = 0
+    for g in grads:
+        g.copy_(flat[off:off + g.numel()].view_as(g))
+        off += g.numel()
+    return flat
+
+
+@dataclass
+class SlabPartition:
+    rank: int
+    world: int
+    n_global: int
+    own_lo: int               # owned nodes are global (x-sorted) indices [own_lo, own_hi)
+    own_hi: int
+    n_left: int               # halo nodes with smaller / larger global index
+    n_right: int
+    send_ranges: List[Tuple[int, int]]   # per peer q: slice [a, b) of the OWNED rows this rank sends to q
+    recv_counts: List[int]               # per peer q: rows received from q (q < rank -> left halo, q > rank -> right halo)
+    local_global: torch.Tensor           # int64 [n_local]: global index of every local node (ascending)
+
+    @property
+    def n_own(self) -> int:
+        return self.own_hi - self.own_lo
+
+    @property
+    def n_local(self) -> int:
+        return self.n_left + self.n_own + self.n_right
+
+    @property
+    def own_slice(self) -> slice:
+        return slice(self.n_left, self.n_left + self.n_own)
+
+
+def slab_partition(x_sorted: torch.Tensor, r: float, rank: int, world: int) -> SlabPartition:
+    """`x_sorted`: the x coordinates of ALL nodes in ascending order (every rank passes the same array).
+    Equal-count slabs; the halo window of a slab is [x_first_owned - r, x_last_owned + r]."""
+    n = x_sorted.numel()
+    bounds = [(n * p) // world for p in range(world + 1)]
+    xs = x_sorted.detach().double().cpu()
+
+    def window(p):
+        lo, hi = bounds[p], bounds[p + 1]
+        if hi == lo:
+            return lo, lo
+        a = int(torch.searchsorted(xs, xs[lo] - r, right=False))
+        b = int(torch.searchsorted(xs, xs[hi - 1] + r, right=True))
+        return a, b  # global index window [a, b) that slab p needs (includes its own nodes)
+
+    wins = [window(p) for p in range(world)]
+    own_lo, own_hi = bounds[rank], bounds[rank + 1]
+    a, b = wins[rank]
+    n_left, n_right = own_lo - a, b - own_hi
+    send, recv = [], []
+    for q in range(world):
+        if q == rank:
+            send.append((0, 0))
+            recv.append(0)
+            continue
+        qa, qb = wins[q]
+        s_lo, s_hi = max(own_lo, qa), min(own_hi, qb)     # my owned nodes inside q's window
+        send.append((s_lo - own_lo, max(s_hi, s_lo) - own_lo) if s_hi > s_lo else (0, 0))
+        r_lo, r_hi = max(bounds[q], a), min(bounds[q + 1], b)  # q's owned nodes inside my window
+        recv.append(max(r_hi - r_lo, 0))
+    assert sum(recv[:rank]) == n_left and sum(recv[rank + 1:]) == n_right
+    local_global = torch.arange(a, b, dtype=torch.int64, device=x_sorted.device)
+    return SlabPartition(rank, world, n, own_lo, own_hi, n_left, n_right, send, recv, local_global)
+
+
+class _HaloExchange(torch.autograd.Function):
+    """owned rows [n_own, F] -> local rows [n_left + n_own + n_right, F] (halo rows filled from their owners)."""
+
+    @staticmethod
+    def forward(ctx, x_own: torch.Tensor, part: SlabPartition, group):
+        ctx.part, ctx.group = part, group
+        x_own = x_own.contiguous()
+        F = x_own.shape[1:]
+        recv = [x_own.new_empty((c,) + tuple(F)) for c in part.recv_counts]
+        ops = []
+        for q in range(part.world):
+            a, b = part.send_ranges[q]
+            if b > a:
+                ops.append(dist.P2POp(dist.isend, x_own[a:b].contiguous(), q, group=group))
+            if part.recv_counts[q] > 0:
+                ops.append(dist.P2POp(dist.irecv, recv[q], q, group=group))
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+        return torch.cat(recv[:part.rank] + [x_own] + recv[part.rank + 1:], dim=0)
+
+    @staticmethod
+    def backward(ctx, g_local: torch.Tensor):
+        part: SlabPartition = ctx.part
+        g_local = g_local.contiguous()
+        g_own = g_local[part.own_slice].clone()
+        # halo gradients travel back to their owners, which add them onto the rows they had sent (fixed rank order)
+        back = [g_own.new_empty((part.send_ranges[q][1] - part.send_ranges[q][0],) + tuple(g_own.shape[1:])) for q in range(part.world)]
+        ops, off = [], 0
+        for q in range(part.world):
+            c = part.recv_counts[q]
+            if q == part.rank:
+                off += part.n_own
+                continue
+            if c > 0:
+                ops.append(dist.P2POp(dist.isend, g_local[off:off + c].contiguous(), q, group=ctx.group))
+            off += c
+            if back[q].shape[0] > 0:
+                ops.append(dist.P2POp(dist.irecv, back[q], q, group=ctx.group))
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+        for q in range(part.world):
+            a, b = part.send_ranges[q]
+            if b > a:
+                g_own[a:b] += back[q]
+        return g_own, None, None
+
+
+def halo_exchange(x_own: torch.Tensor, part: SlabPartition, group=None) -> torch.Tensor:
+    if part.world == 1:
+        return x_own
+    return _HaloExchange.apply(x_own, part, group)
+
+
+def local_radius_graph(pos_local: torch.Tensor, r: float, part: SlabPartition, max_num_neighbors: int = 128) -> torch.Tensor:
+    """Radius graph over the local node set, keeping the edges whose destination is owned (local numbering).
+    Identical, row by row, to the owned rows of the single-GPU graph as long as no row is truncated."""
+    from .graph import radius_graph
+    ei = radius_graph(pos_local, r, None, max_num_neighbors=max_num_neighbors)
+    keep = (ei[1] >= part.n_left) & (ei[1] < part.n_left + part.n_own)
+    return ei[:, keep].contiguous()
+
+
+class PartitionedEGNN(torch.nn.Module):
+    """The layer loop of EGNNModel (models/egnn.py:71-79) on a destination-partitioned graph: per layer one halo
+    exchange of (h, pos) forward and one of their gradients backward; the layer itself is the unchanged fused
+    EGNNLayer applied to the local node set."""
+
+    def __init__(self, num_layers: int = 4, emb_dim: int = 128, activation: str = "relu", aggr: str = "sum",
+                 residual: bool = True, precision: str = "fp32"):
+        super().__init__()
+        from .egnn import EGNNLayer
+        self.residual = residual
+        self.convs = torch.nn.ModuleList([EGNNLayer(emb_dim, activation, "layer", aggr, precision) for _ in range(num_layers)])
+
+    def forward(self, h_own, pos_own, edge_index_local, part: SlabPartition, group=None):
+        own = part.own_slice
+        for conv in self.convs:
+            h_loc = halo_exchange(h_own, part, group)
+            pos_loc = halo_exchange(pos_own, part, group)
+            h_upd, pos_upd = conv(h_loc, pos_loc, edge_index_local)
+            h_own = h_own + h_upd[own] if self.residual else h_upd[own]
+            pos_own = pos_upd[own]
+        return h_own, pos_own
