@@ -1,0 +1,661 @@
+// TFN / MACE tensor-product convolution on the 5th-generation tensor cores (GMP_BF16_TC), models/layers/tfn_layer.py:82-87.
+//
+//   T_e[a,b] = sum_h hid_e[h] * W2[(a,b),h]          bf16 x bf16 -> fp32, tcgen05.mma, accumulators in TMEM
+//   res_e[b,k] = sum_a T_e[a,b] * Y_e[a,k]           fp32 FFMA by the epilogue warps straight out of TMEM
+//   res[n]     = sum_{e in CSR row n} res_e          fp32, walker warps, fixed order, no atomics
+//
+// (a = summed multiplicity index, b = kept multiplicity index: forward a = u, b = w; feature gradient a = w, b = u.)
+// The [E, weight_numel] tensor of the reference (272 KB / 704 KB per edge at the BASELINE configs) lives only as
+// 128 x 256 fp32 tiles in tensor memory.  The CTA is EDGE-stationary: it keeps one 128-edge tile of the hidden layer
+// (bf16, 64 KB, UMMA K-major 128B-swizzle image prepared by tp_pack_hid_kernel) in shared memory and streams every
+// 256-column slice of W2 ("N-tile", images prepared by tp_pack_w2_kernel, L2-resident) through a 4-slot ring with
+// cp.async.bulk; per (tile, path, range of a) the geometric factor Y (or the gathered row itself when that is the
+// smaller side) is built once into a thread-private shared-memory scratch and reused by every N-tile of the path.
+// Warp roles (384 threads): 0-7 epilogue (thread = edge = TMEM lane; warps 0-3 take columns 0-127, 4-7 columns
+// 128-255 of each N-tile), 8-9 walker (segmented row sums + read-modify-write of rows this CTA owns), 10 bulk-copy
+// producer, 11 MMA issuer.  fc's second bias never enters the MMA: sum_e sum_a b2[a,b] Y_e[a,k] is linear in
+// YS[n] = sum_e Y_e, which tp_ysum_kernel aggregates per node (fp32) and a node-level GEMM finishes on the host side.
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace gmp {
+
+using namespace tc;
+
+constexpr int kET = 128;        // edges per tile
+constexpr int kStage = 16384;   // bytes of one [128 rows][64 bf16] swizzled slab
+constexpr int kNB = 4;          // W2 ring slots
+constexpr int kFBytes = 49152;  // factor scratch
+constexpr int kOLd = 41;        // fp32 row stride of the per-edge result tile (odd: conflict-free)
+constexpr int kTcThreads = 384;  // 12 warps = 3 per scheduler: 16384 / 96 = 170 registers per thread
+constexpr int kEpiThreads = 256, kWalkThreads = 64;
+
+// One (path, range of the summed index) group: the factor built for it serves nslices * nsub N-tiles.
+struct TcYGroup {
+    int32_t v_off, DA, DB, DS;        // gathered block offset / irrep dims of the gathered, kept and sh sides
+    int32_t sh_off, cg_off, A0, AR;   // sh block, CG table (Zc[iA][j][kB], coefficient folded in), a in [A0, A0+AR)
+    int32_t r_off, MB, nslices, nsub; // result block offset, kept multiplicity, kept slices, N-tiles per slice
+};
+// One N-tile = 256 generated weights per edge: column c = a_loc * WS + b  (WS = 32 when DB == 1 <= DA, else 8)
+struct TcNTile {
+    int32_t w_off, stride_a, stride_b, a_begin;  // W2 row = w_off + (a_begin + a_loc) * stride_a + (b0 + b) * stride_b
+    int32_t a_end, b0, b_end, WS;
+};
+// gathered blocks for tp_ysum_kernel
+struct TcYPath {
+    int32_t v_off, DA, DB, MA;     // YS[n][y_off + a*DB + k] = sum_e sum_i V[col_e][v_off + a*DA + i] Z_e[i][k]
+    int32_t y_off, z_off, pad0, pad1;
+};
+struct TcZEntry { int32_t sh_off, DS, cg_base, cg_stride; };  // Z[z] = sum_j sh[sh_off + j] * cg[cg_base + j*cg_stride]
+
+// ------------------------------------------------------------------------------------------------
+// operand images
+// ------------------------------------------------------------------------------------------------
+// hid = relu(W1 feat + b1) for the 128 edges of a tile (CSR order), bf16, as KS = H/64 swizzled K-major slabs
+__global__ void __launch_bounds__(256) tp_pack_hid_kernel(const int32_t* __restrict__ perm, int64_t E, const float* __restrict__ feat,
+                                                          int R, const float* __restrict__ w1, const float* __restrict__ b1, int H,
+                                                          uint8_t* __restrict__ img) {
+    extern __shared__ __align__(16) float smf[];
+    float* w1s = smf;            // [H][R]
+    float* b1s = w1s + H * R;    // [H]
+    float* fs = b1s + H;         // [128][R]
+    const int t = threadIdx.x;
+    const int64_t e0 = (int64_t)blockIdx.x * kET;
+    for (int x = t; x < H * R; x += 256) w1s[x] = __ldg(w1 + x);
+    for (int x = t; x < H; x += 256) b1s[x] = __ldg(b1 + x);
+    for (int x = t; x < kET * R; x += 256) {
+        const int r = x / R, c = x - r * R;
+        const int64_t k = e0 + r;
+        float v = 0.f;
+        if (k < E) v = __ldg(feat + (int64_t)(perm ? __ldg(perm + k) : (int)k) * R + c);
+        fs[x] = v;
+    }
+    __syncthreads();
+    const int CH = H / 8;  // 16-byte chunks per row
+    uint8_t* dst = img + (int64_t)blockIdx.x * (H / 64) * kStage;
+    for (int x = t; x < kET * CH; x += 256) {
+        const int r = x / CH, cg = x - r * CH;
+        const bool live = e0 + r < E;
+        float v[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const int h = cg * 8 + q;
+            float acc = b1s[h];
+            for (int c = 0; c < R; ++c) acc = fmaf(w1s[h * R + c], fs[r * R + c], acc);
+            v[q] = live ? fmaxf(acc, 0.f) : 0.f;
+        }
+        *reinterpret_cast<uint4*>(dst + (cg >> 3) * kStage + sw128_chunk_off(r, cg & 7)) =
+            make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+    }
+}
+
+// W2 slices in N-tile order: stage s = half * KS + ks holds rows (columns of T) [128*half, 128*half+128) x K slab ks
+__global__ void __launch_bounds__(256) tp_pack_w2_kernel(const float* __restrict__ w2, int H, const TcNTile* __restrict__ tiles,
+                                                         uint8_t* __restrict__ img) {
+    const int KS = H / 64;
+    const int nt = blockIdx.x / (2 * KS), s = blockIdx.x - nt * 2 * KS;
+    const int half = s / KS, ks = s - half * KS;
+    const TcNTile T = tiles[nt];
+    uint8_t* dst = img + (int64_t)blockIdx.x * kStage;
+    for (int x = threadIdx.x; x < 128 * 8; x += 256) {
+        const int rr = x >> 3, ch = x & 7;
+        const int c = half * 128 + rr;
+        const int al = c / T.WS, b = c - al * T.WS;
+        const int a = T.a_begin + al, bb = T.b0 + b;
+        uint4 o = make_uint4(0u, 0u, 0u, 0u);
+        if (a < T.a_end && bb < T.b_end) {
+            const float* src = w2 + ((int64_t)T.w_off + (int64_t)a * T.stride_a + (int64_t)bb * T.stride_b) * H + ks * 64 + ch * 8;
+            const float4 lo = ldg4(src), hi = ldg4(src + 4);
+            o = make_uint4(pack_bf16(lo.x, lo.y), pack_bf16(lo.z, lo.w), pack_bf16(hi.x, hi.y), pack_bf16(hi.z, hi.w));
+        }
+        *reinterpret_cast<uint4*>(dst + sw128_chunk_off(rr, ch)) = o;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// YS[n][y_off_p + a*DB + k] = sum_{e in row n} sum_i V[col_e][v_off_p + a*DA + i] * Z^p_e[i][k]      (fp32)
+// ------------------------------------------------------------------------------------------------
+constexpr int kYsPairs = 12;  // (path, a) pairs per thread
+constexpr int kYsMaxZ = 256;
+
+struct YsArgs {
+    const int32_t *rowptr, *col, *perm;
+    int64_t n;
+    const float* V;
+    int32_t v_len;
+    const float* sh;
+    int32_t S;
+    const TcYPath* paths;
+    int32_t npaths, npairs;
+    const TcZEntry* zent;
+    int32_t nz;
+    const float* cg;
+    float* YS;
+    int32_t y_len;
+};
+
+__global__ void __launch_bounds__(128) tp_ysum_kernel(YsArgs a) {
+    __shared__ float Zs[kYsMaxZ];
+    __shared__ TcYPath ps[32];
+    const int t = threadIdx.x;
+    if (t < a.npaths) ps[t] = a.paths[t];
+    __syncthreads();
+    // this thread's pairs: flat index f = t + 128*j over the concatenation of the paths' a ranges
+    int pp[kYsPairs], pa[kYsPairs];
+#pragma unroll
+    for (int j = 0; j < kYsPairs; ++j) {
+        int f = t + 128 * j, p = -1, aa = 0;
+        if (f < a.npairs) {
+            p = 0;
+            while (f >= ps[p].MA) { f -= ps[p].MA; ++p; }
+            aa = f;
+        }
+        pp[j] = p;
+        pa[j] = aa;
+    }
+    for (int64_t row = blockIdx.x; row < a.n; row += gridDim.x) {
+        float acc[kYsPairs][5];
+#pragma unroll
+        for (int j = 0; j < kYsPairs; ++j)
+#pragma unroll
+            for (int k = 0; k < 5; ++k) acc[j][k] = 0.f;
+        const int64_t eb = __ldg(a.rowptr + row), ee = __ldg(a.rowptr + row + 1);
+        for (int64_t e = eb; e < ee; ++e) {
+            const int64_t eid = a.perm ? __ldg(a.perm + e) : e;
+            const float* vrow = a.V + (int64_t)__ldg(a.col + e) * a.v_len;
+            __syncthreads();
+            for (int z = t; z < a.nz; z += 128) {
+                const TcZEntry ze = a.zent[z];
+                float s = 0.f;
+                for (int j = 0; j < ze.DS; ++j) s = fmaf(__ldg(a.sh + eid * a.S + ze.sh_off + j), __ldg(a.cg + ze.cg_base + j * ze.cg_stride), s);
+                Zs[z] = s;
+            }
+            __syncthreads();
+#pragma unroll
+            for (int j = 0; j < kYsPairs; ++j) {
+                if (pp[j] < 0) continue;
+                const TcYPath P = ps[pp[j]];
+                const float* x = vrow + P.v_off + pa[j] * P.DA;
+                const float* Z = Zs + P.z_off;
+                for (int i = 0; i < P.DA; ++i) {
+                    const float xv = __ldg(x + i);
+#pragma unroll
+                    for (int k = 0; k < 5; ++k)
+                        if (k < P.DB) acc[j][k] = fmaf(xv, Z[i * P.DB + k], acc[j][k]);
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < kYsPairs; ++j) {
+            if (pp[j] < 0) continue;
+            const TcYPath P = ps[pp[j]];
+            float* y = a.YS + row * a.y_len + P.y_off + pa[j] * P.DB;
+#pragma unroll
+            for (int k = 0; k < 5; ++k)
+                if (k < P.DB) y[k] = acc[j][k];
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// main kernel
+// ------------------------------------------------------------------------------------------------
+struct TcTpArgs {
+    const int32_t *rowptr, *col, *perm;
+    int64_t n, E;
+    const float* V;
+    int32_t v_len;
+    float* res;
+    int32_t r_len;
+    float* head;           // [nchunks][r_len]: partial sums of a chunk's leading edges whose row started in an earlier chunk
+    const float* sh;
+    int32_t S;
+    const uint8_t* hid_img;
+    const uint8_t* w2_img;
+    const TcYGroup* yg;
+    int32_t nyg, NT, KS;
+    const float* cg;
+    int64_t ntiles;
+};
+
+// shared-memory map (bytes from the 1024-aligned base)
+constexpr int oA = 0;                            // hid tile, up to 4 slabs
+constexpr int oB = 65536;                        // W2 ring
+constexpr int oF = oB + kNB * kStage;            // factor scratch: F[(aidx*W + word)*256 + g*128 + e]
+constexpr int oO = oF + kFBytes;                 // 2 planes x [128][41] fp32
+constexpr int oSeg = oO + 2 * kET * kOLd * 4;    // srow[128] | seg_start[132] | seg_row[128] | wcount[4]
+constexpr int oBar2 = oSeg + (128 + 132 + 128 + 4) * 4;
+// barriers: 0 A_full, 1 A_empty, 2..5 B_full, 6..9 B_empty, 10..13 T_full[buf*2+half], 14..15 T_empty[buf]
+constexpr int kTcTpSmem = oBar2 + 16 * 8 + 16 + 1024;
+
+__device__ __forceinline__ float bf_lo(uint32_t w) { return __uint_as_float(w << 16); }
+__device__ __forceinline__ float bf_hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
+
+struct EpiCtx {
+    const TcTpArgs* a;
+    uint8_t* sm;
+    uint64_t* bars;
+    uint32_t tm, lane_base;
+    int e, g;          // tile row (= TMEM lane) and column half
+    bool valid;
+    int64_t eid;
+    int gnode;
+    uint32_t gi;       // N-tile counter (all tiles)
+};
+
+// One y-group for compile-time irrep dimensions DA (gathered) / DB (kept).
+//   DA >= DB: the factor is Y[a][k] = sum_i x[a][i] Z[i][k]  (M = DB values per a), results come out directly;
+//   DA <  DB: the factor is x[a][i] itself (M = DA values), r[b][i] = sum_a T x, and out[b][k] = sum_i r[b][i] Z[i][k] at the flush.
+template <int DA, int DB>
+__device__ __forceinline__ void tc_ygroup(EpiCtx& c, const TcYGroup& G) {
+    constexpr bool XM = DA < DB;
+    constexpr int M = XM ? DA : DB;
+    constexpr int WS = (!XM && DB == 1) ? 32 : 8;
+    constexpr int MC = 256 / WS, HA = MC / 2;
+    constexpr int W = (M + 1) / 2;
+    const TcTpArgs& a = *c.a;
+    uint32_t* F = reinterpret_cast<uint32_t*>(c.sm + oF) + c.g * 128 + c.e;
+    // ---- Z[i][k] = sum_j sh[j] Zc[i][j][k]
+    float Z[DA][DB];
+    {
+        float sb[5];
+#pragma unroll
+        for (int j = 0; j < 5; ++j) sb[j] = (c.valid && j < G.DS) ? __ldg(a.sh + c.eid * a.S + G.sh_off + j) : 0.f;
+#pragma unroll
+        for (int i = 0; i < DA; ++i)
+#pragma unroll
+            for (int k = 0; k < DB; ++k) {
+                float s = 0.f;
+#pragma unroll
+                for (int j = 0; j < 5; ++j)
+                    if (j < G.DS) s = fmaf(sb[j], __ldg(a.cg + G.cg_off + (i * G.DS + j) * DB + k), s);
+                Z[i][k] = s;
+            }
+    }
+    // ---- factor for this thread's a's: sub-chunk q, local a in [g*HA, g*HA + HA)
+    {
+        const float* xrow = a.V + (int64_t)c.gnode * a.v_len + G.v_off;
+        const bool vec_ok = ((a.v_len | G.v_off) & 3) == 0;
+        for (int q = 0; q < G.nsub; ++q)
+            for (int a4 = 0; a4 < HA; a4 += 4) {
+                const int al0 = q * MC + c.g * HA + a4;  // relative to A0
+                float xs[4 * DA];
+                if (c.valid && vec_ok && al0 + 4 <= G.AR) {
+                    const float4* p = reinterpret_cast<const float4*>(xrow + (int64_t)(G.A0 + al0) * DA);
+#pragma unroll
+                    for (int v = 0; v < DA; ++v) {
+                        const float4 f = __ldg(p + v);
+                        xs[4 * v] = f.x; xs[4 * v + 1] = f.y; xs[4 * v + 2] = f.z; xs[4 * v + 3] = f.w;
+                    }
+                } else {
+#pragma unroll
+                    for (int v = 0; v < 4 * DA; ++v)
+                        xs[v] = (c.valid && al0 + v / DA < G.AR) ? __ldg(xrow + (int64_t)(G.A0 + al0) * DA + v) : 0.f;
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    float y[M];
+                    if constexpr (XM) {
+#pragma unroll
+                        for (int i = 0; i < M; ++i) y[i] = xs[j * DA + i];
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < M; ++k) {
+                            float s = 0.f;
+#pragma unroll
+                            for (int i = 0; i < DA; ++i) s = fmaf(xs[j * DA + i], Z[i][k], s);
+                            y[k] = s;
+                        }
+                    }
+                    uint32_t* dst = F + ((q * HA + a4 + j) * W) * 256;
+                    if constexpr (M == 1) dst[0] = __float_as_uint(y[0]);
+                    if constexpr (M == 3) { dst[0] = pack_bf16(y[0], y[1]); dst[256] = pack_bf16(y[2], 0.f); }
+                    if constexpr (M == 5) { dst[0] = pack_bf16(y[0], y[1]); dst[256] = pack_bf16(y[2], y[3]); dst[512] = pack_bf16(y[4], 0.f); }
+                }
+            }
+    }
+    // ---- N-tiles: kept slices x sub-chunks of the summed index
+    for (int sl = 0; sl < G.nslices; ++sl) {
+        float r[WS * M];
+#pragma unroll
+        for (int x = 0; x < WS * M; ++x) r[x] = 0.f;
+        for (int q = 0; q < G.nsub; ++q) {
+            const uint32_t buf = c.gi & 1u;
+            mbar_wait(&c.bars[10 + buf * 2 + c.g], (c.gi >> 1) & 1u);
+            tc_fence_after();
+            const uint32_t tb = c.tm + c.lane_base + buf * 256 + c.g * 128;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float v[32];
+                tmem_ld32(tb + 32 * j, v);
+                if constexpr (WS == 32) {
+                    const float y = __uint_as_float(F[(q * HA + j) * 256]);
+#pragma unroll
+                    for (int b = 0; b < 32; ++b) r[b] = fmaf(v[b], y, r[b]);
+                } else {
+#pragma unroll
+                    for (int aa = 0; aa < 4; ++aa) {
+                        const uint32_t* src = F + ((q * HA + 4 * j + aa) * W) * 256;
+                        float y[M];
+                        if constexpr (M == 1) y[0] = __uint_as_float(src[0]);
+                        if constexpr (M == 3) { const uint32_t w0 = src[0], w1 = src[256]; y[0] = bf_lo(w0); y[1] = bf_hi(w0); y[2] = bf_lo(w1); }
+                        if constexpr (M == 5) {
+                            const uint32_t w0 = src[0], w1 = src[256], w2 = src[512];
+                            y[0] = bf_lo(w0); y[1] = bf_hi(w0); y[2] = bf_lo(w1); y[3] = bf_hi(w1); y[4] = bf_lo(w2);
+                        }
+#pragma unroll
+                        for (int b = 0; b < 8; ++b)
+#pragma unroll
+                            for (int k = 0; k < M; ++k) r[b * M + k] = fmaf(v[aa * 8 + b], y[k], r[b * M + k]);
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(&c.bars[14 + buf]);
+            ++c.gi;
+        }
+        // ---- flush: per-edge results of this kept slice -> O plane g
+        bar_sync_named(2, kEpiThreads + kWalkThreads);  // O free
+        float* O = reinterpret_cast<float*>(c.sm + oO) + (c.g * kET + c.e) * kOLd;
+        if constexpr (!XM) {
+#pragma unroll
+            for (int x = 0; x < WS * M; ++x) O[x] = r[x];
+        } else {
+#pragma unroll
+            for (int b = 0; b < 8; ++b)
+#pragma unroll
+                for (int k = 0; k < DB; ++k) {
+                    float s = 0.f;
+#pragma unroll
+                    for (int i = 0; i < M; ++i) s = fmaf(r[b * M + i], Z[i][k], s);
+                    O[b * DB + k] = s;
+                }
+        }
+        bar_arrive_named(1, kEpiThreads + kWalkThreads);  // O full
+    }
+}
+
+__global__ void __launch_bounds__(kTcThreads, 1) tp_contract_tc_kernel(TcTpArgs a) {
+    extern __shared__ __align__(16) uint8_t smraw[];
+    uint8_t* sm = smraw + ((1024u - (smem_u32(smraw) & 1023u)) & 1023u);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sm + oBar2);
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(sm + oBar2 + 16 * 8);
+    const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+    const int KS = a.KS, NST = 2 * KS;
+
+    if (t == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        for (int s = 0; s < kNB; ++s) { mbar_init(&bars[2 + s], 1); mbar_init(&bars[6 + s], 1); }
+        for (int s = 0; s < 4; ++s) mbar_init(&bars[10 + s], 1);
+        mbar_init(&bars[14], kEpiThreads);
+        mbar_init(&bars[15], kEpiThreads);
+        fence_mbar_init();
+    }
+    if (warp == 11) tmem_alloc<512>(tmem_ptr);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tm = *tmem_ptr;
+
+    const int64_t t0 = (a.ntiles * blockIdx.x) / gridDim.x, t1 = (a.ntiles * (blockIdx.x + 1)) / gridDim.x;
+
+    if (warp < 8) {
+        // ================= epilogue: thread = edge of the tile = TMEM lane =================
+        EpiCtx c;
+        c.a = &a; c.sm = sm; c.bars = bars; c.tm = tm;
+        c.lane_base = (uint32_t)((warp & 3) * 32) << 16;
+        c.e = (warp & 3) * 32 + lane;
+        c.g = warp >> 2;
+        c.gi = 0;
+        for (int64_t tile = t0; tile < t1; ++tile) {
+            const int64_t k = tile * kET + c.e;
+            c.valid = k < a.E;
+            c.eid = 0; c.gnode = 0;
+            if (c.valid) {
+                c.eid = a.perm ? __ldg(a.perm + k) : k;
+                c.gnode = __ldg(a.col + k);
+            }
+            for (int y = 0; y < a.nyg; ++y) {
+                const TcYGroup G = a.yg[y];
+                switch (G.DA * 8 + G.DB) {
+                    case 1 * 8 + 1: tc_ygroup<1, 1>(c, G); break;
+                    case 3 * 8 + 1: tc_ygroup<3, 1>(c, G); break;
+                    case 5 * 8 + 1: tc_ygroup<5, 1>(c, G); break;
+                    case 3 * 8 + 3: tc_ygroup<3, 3>(c, G); break;
+                    case 5 * 8 + 3: tc_ygroup<5, 3>(c, G); break;
+                    case 5 * 8 + 5: tc_ygroup<5, 5>(c, G); break;
+                    case 1 * 8 + 3: tc_ygroup<1, 3>(c, G); break;
+                    case 1 * 8 + 5: tc_ygroup<1, 5>(c, G); break;
+                    default: tc_ygroup<3, 5>(c, G); break;
+                }
+            }
+        }
+    } else if (warp < 10) {
+        // ================= walker: segmented sums of the per-edge results, rows owned by this CTA =================
+        const int wt = t - 256;
+        int* srow = reinterpret_cast<int*>(sm + oSeg);
+        int* seg_start = srow + 128;
+        int* seg_row = seg_start + 132;
+        int* wcount = seg_row + 128;
+        const float* O0 = reinterpret_cast<const float*>(sm + oO);
+        const float* O1 = O0 + kET * kOLd;
+        const int64_t chunk_e0 = t0 * kET;
+        for (int64_t tile = t0; tile < t1; ++tile) {
+            {   // row of every edge of the tile (padding slots repeat the last edge's row), then the segment table;
+                // thread wt looks after edges wt and wt + 64: block blk = pass * 2 + (warp - 8) covers 32 consecutive edges
+                int myrow[2];
+#pragma unroll
+                for (int ps = 0; ps < 2; ++ps) {
+                    int64_t k = tile * kET + ps * 64 + wt;
+                    if (k > a.E - 1) k = a.E - 1;
+                    int lo = 0, hi = (int)a.n;  // last row with rowptr[row] <= k
+                    while (hi - lo > 1) {
+                        const int mid = (lo + hi) >> 1;
+                        if ((int64_t)__ldg(a.rowptr + mid) <= k) lo = mid; else hi = mid;
+                    }
+                    myrow[ps] = lo;
+                    srow[ps * 64 + wt] = lo;
+                }
+                bar_sync_named(3, kWalkThreads);
+                bool flag[2];
+                unsigned bal[2];
+#pragma unroll
+                for (int ps = 0; ps < 2; ++ps) {
+                    const int e = ps * 64 + wt;
+                    flag[ps] = e == 0 || srow[e - 1] != myrow[ps];
+                    bal[ps] = __ballot_sync(0xffffffffu, flag[ps]);
+                    if (lane == 0) wcount[ps * 2 + (warp - 8)] = __popc(bal[ps]);
+                }
+                bar_sync_named(3, kWalkThreads);
+                int total = 0;
+#pragma unroll
+                for (int w = 0; w < 4; ++w) total += wcount[w];
+#pragma unroll
+                for (int ps = 0; ps < 2; ++ps) {
+                    const int blk = ps * 2 + (warp - 8);
+                    int base = 0;
+#pragma unroll
+                    for (int w = 0; w < 4; ++w)
+                        if (w < blk) base += wcount[w];
+                    if (flag[ps]) {
+                        const int idx = base + __popc(bal[ps] & ((1u << lane) - 1u));
+                        seg_start[idx] = ps * 64 + wt;
+                        seg_row[idx] = myrow[ps];
+                    }
+                }
+                if (wt == 0) { seg_start[total] = kET; seg_start[131] = total; }
+                bar_sync_named(3, kWalkThreads);
+            }
+            const int nseg = seg_start[131];
+            const bool head0 = (int64_t)__ldg(a.rowptr + seg_row[0]) < chunk_e0;
+            for (int y = 0; y < a.nyg; ++y) {
+                const TcYGroup G = a.yg[y];
+                const int WS = (G.DA >= G.DB && G.DB == 1) ? 32 : 8;
+                for (int sl = 0; sl < G.nslices; ++sl) {
+                    const int nb = min(WS, G.MB - sl * WS);
+                    const int nv = nb * G.DB;
+                    const int cbase = G.r_off + sl * WS * G.DB;
+                    bar_arrive_named(2, kEpiThreads + kWalkThreads);  // O free
+                    bar_sync_named(1, kEpiThreads + kWalkThreads);    // O full
+                    for (int p = wt; p < nseg * nv; p += kWalkThreads) {
+                        const int s = p / nv, cc = p - s * nv;
+                        const int b = seg_start[s], e = seg_start[s + 1];
+                        float sum = 0.f;
+                        for (int x = b; x < e; ++x) sum += O0[x * kOLd + cc] + O1[x * kOLd + cc];
+                        float* dst = (s == 0 && head0) ? a.head + (int64_t)blockIdx.x * a.r_len + cbase + cc
+                                                       : a.res + (int64_t)seg_row[s] * a.r_len + cbase + cc;
+                        *dst += sum;
+                    }
+                }
+            }
+            bar_sync_named(3, kWalkThreads);  // seg table reusable
+        }
+    } else if (warp == 10) {
+        // ================= producer: bulk copies of the hidden tile and the W2 stages =================
+        if (lane == 0) {
+            uint32_t si = 0, ti = 0;
+            for (int64_t tile = t0; tile < t1; ++tile, ++ti) {
+                mbar_wait(&bars[1], (ti & 1u) ^ 1u);
+                mbar_expect_tx(&bars[0], (uint32_t)(KS * kStage));
+                for (int ks = 0; ks < KS; ++ks)
+                    bulk_g2s(sm + oA + ks * kStage, a.hid_img + (tile * KS + ks) * (int64_t)kStage, kStage, &bars[0]);
+                const int nstage = a.NT * NST;
+                for (int s = 0; s < nstage; ++s, ++si) {
+                    const uint32_t slot = si % kNB, ph = (si / kNB) & 1u;
+                    mbar_wait(&bars[6 + slot], ph ^ 1u);
+                    mbar_expect_tx(&bars[2 + slot], kStage);
+                    bulk_g2s(sm + oB + slot * kStage, a.w2_img + (int64_t)s * kStage, kStage, &bars[2 + slot]);
+                }
+            }
+        }
+    } else {
+        // ================= MMA issuer =================
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc_bf16(128, 128);
+            uint32_t si = 0, ti = 0, gi = 0;
+            for (int64_t tile = t0; tile < t1; ++tile, ++ti) {
+                mbar_wait(&bars[0], ti & 1u);
+                tc_fence_after();
+                for (int nt = 0; nt < a.NT; ++nt, ++gi) {
+                    const uint32_t buf = gi & 1u;
+                    mbar_wait(&bars[14 + buf], ((gi >> 1) & 1u) ^ 1u);
+                    tc_fence_after();
+                    for (int s = 0; s < NST; ++s, ++si) {
+                        const uint32_t slot = si % kNB, ph = (si / kNB) & 1u;
+                        const int half = s / KS, ks = s - half * KS;
+                        mbar_wait(&bars[2 + slot], ph);
+                        tc_fence_after();
+                        const uint32_t d = tm + buf * 256 + half * 128;
+                        const uint32_t ab = smem_u32(sm + oA + ks * kStage), bb = smem_u32(sm + oB + slot * kStage);
+#pragma unroll
+                        for (int k16 = 0; k16 < 4; ++k16)
+                            umma_bf16(d, umma_desc_k128(ab + k16 * 32), umma_desc_k128(bb + k16 * 32), idesc, (ks | k16) ? 1u : 0u);
+                        umma_commit(&bars[6 + slot]);
+                        if (ks == KS - 1) umma_commit(&bars[10 + buf * 2 + half]);
+                    }
+                }
+                umma_commit(&bars[1]);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 11) tmem_dealloc<512>(tm);
+}
+
+// rows that straddle a chunk boundary: add the later chunks' head partials in chunk order
+__global__ void tp_tc_fixup_kernel(const int32_t* __restrict__ rowptr, int64_t n, int64_t E, int64_t ntiles, int nchunks,
+                                   const float* __restrict__ head, float* __restrict__ res, int r_len) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= r_len) return;
+    for (int ch = 1; ch < nchunks; ++ch) {
+        const int64_t e0 = ((ntiles * ch) / nchunks) * kET;
+        if (e0 >= E) break;
+        int lo = 0, hi = (int)n;
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if ((int64_t)__ldg(rowptr + mid) <= e0) lo = mid; else hi = mid;
+        }
+        if ((int64_t)__ldg(rowptr + lo) < e0) res[(int64_t)lo * r_len + c] += head[(int64_t)ch * r_len + c];
+    }
+}
+
+}  // namespace gmp
+
+using namespace gmp;
+
+extern "C" {
+
+int32_t gmp_tp_tc_num_chunks(int64_t num_edges) {
+    const int64_t nt = ceil_div(num_edges, kET);
+    return (int32_t)(nt < num_sms() ? (nt < 1 ? 1 : nt) : num_sms());
+}
+
+int64_t gmp_tp_tc_hid_bytes(int64_t num_edges, int32_t H) { return ceil_div(num_edges, kET) * (H / 64) * (int64_t)kStage; }
+int64_t gmp_tp_tc_w2_bytes(int32_t ntiles, int32_t H) { return (int64_t)ntiles * 2 * (H / 64) * (int64_t)kStage; }
+
+int gmp_tp_tc_pack_hid(const int32_t* perm, int64_t num_edges, const float* edge_feat, int32_t R, const float* w1, const float* b1,
+                       int32_t H, void* hid_img, gmp_stream_t stream) {
+    GMP_REQUIRE(edge_feat && w1 && b1 && hid_img, "tp_tc_pack_hid: NULL pointer");
+    GMP_REQUIRE(H >= 64 && H <= 256 && H % 64 == 0, "tp_tc_pack_hid: mlp_dim must be 64, 128, 192 or 256 (got %d)", H);
+    GMP_REQUIRE(R >= 1 && R <= 16, "tp_tc_pack_hid: edge_feats_dim in [1, 16] (got %d)", R);
+    if (num_edges == 0) return GMP_OK;
+    const size_t smem = (size_t)(H * R + H + kET * R) * sizeof(float);
+    tp_pack_hid_kernel<<<(unsigned)ceil_div(num_edges, kET), 256, smem, stream>>>(perm, num_edges, edge_feat, R, w1, b1, H, (uint8_t*)hid_img);
+    return check_launch("tp_pack_hid_kernel");
+}
+
+int gmp_tp_tc_pack_w2(const float* w2, int32_t H, const void* ntile_table, int32_t ntiles, void* w2_img, gmp_stream_t stream) {
+    GMP_REQUIRE(w2 && ntile_table && w2_img, "tp_tc_pack_w2: NULL pointer");
+    GMP_REQUIRE(H >= 64 && H <= 256 && H % 64 == 0, "tp_tc_pack_w2: mlp_dim must be 64, 128, 192 or 256 (got %d)", H);
+    if (ntiles == 0) return GMP_OK;
+    tp_pack_w2_kernel<<<(unsigned)(ntiles * 2 * (H / 64)), 256, 0, stream>>>(w2, H, (const TcNTile*)ntile_table, (uint8_t*)w2_img);
+    return check_launch("tp_pack_w2_kernel");
+}
+
+int gmp_tp_ysum(const int32_t* rowptr, const int32_t* col, const int32_t* perm, int64_t n, int64_t num_edges, const float* V,
+                int32_t v_len, const float* edge_sh, int32_t S, const void* ypaths, int32_t npaths, int32_t npairs,
+                const void* zentries, int32_t nz, const float* cg, float* YS, int32_t y_len, gmp_stream_t stream) {
+    GMP_REQUIRE(rowptr && ypaths && zentries && cg && YS, "tp_ysum: NULL pointer");
+    GMP_REQUIRE(num_edges == 0 || (col && V && edge_sh), "tp_ysum: NULL edge/feature pointer");
+    GMP_REQUIRE(npaths <= 32 && nz <= kYsMaxZ && npairs <= 128 * kYsPairs,
+                "tp_ysum: at most 32 paths, %d geometric factors and %d (path, multiplicity) pairs", kYsMaxZ, 128 * kYsPairs);
+    if (n == 0) return GMP_OK;
+    YsArgs a;
+    a.rowptr = rowptr; a.col = col; a.perm = perm; a.n = n; a.V = V; a.v_len = v_len; a.sh = edge_sh; a.S = S;
+    a.paths = (const TcYPath*)ypaths; a.npaths = npaths; a.npairs = npairs; a.zent = (const TcZEntry*)zentries; a.nz = nz;
+    a.cg = cg; a.YS = YS; a.y_len = y_len;
+    const int64_t grid = n < 16ll * num_sms() ? n : 16ll * num_sms();
+    tp_ysum_kernel<<<(unsigned)grid, 128, 0, stream>>>(a);
+    return check_launch("tp_ysum_kernel");
+}
+
+int gmp_tp_tc_contract(const int32_t* rowptr, const int32_t* col, const int32_t* perm, int64_t n, int64_t num_edges, const float* V,
+                       int32_t v_len, float* res, int32_t r_len, float* head, const float* edge_sh, int32_t S, const void* hid_img,
+                       const void* w2_img, const void* ygroups, int32_t nyg, int32_t ntiles_n, int32_t H, const float* cg,
+                       gmp_stream_t stream) {
+    GMP_REQUIRE(rowptr && res && head && ygroups && cg, "tp_tc_contract: NULL pointer");
+    GMP_REQUIRE(num_edges == 0 || (col && V && edge_sh && hid_img && w2_img), "tp_tc_contract: NULL edge/feature pointer");
+    GMP_REQUIRE(H >= 64 && H <= 256 && H % 64 == 0, "tp_tc_contract: mlp_dim must be 64, 128, 192 or 256 (got %d)", H);
+    GMP_REQUIRE(n >= 0 && n < (1ll << 31) && num_edges >= 0 && num_edges < (1ll << 31), "tp_tc_contract: sizes out of range");
+    GMP_CUDA(cudaMemsetAsync(res, 0, (size_t)n * r_len * sizeof(float), stream));
+    if (n == 0 || num_edges == 0 || nyg == 0) return GMP_OK;
+    const int nchunks = gmp_tp_tc_num_chunks(num_edges);
+    GMP_CUDA(cudaMemsetAsync(head, 0, (size_t)nchunks * r_len * sizeof(float), stream));
+    TcTpArgs a;
+    a.rowptr = rowptr; a.col = col; a.perm = perm; a.n = n; a.E = num_edges; a.V = V; a.v_len = v_len; a.res = res; a.r_len = r_len;
+    a.head = head; a.sh = edge_sh; a.S = S; a.hid_img = (const uint8_t*)hid_img; a.w2_img = (const uint8_t*)w2_img;
+    a.yg = (const TcYGroup*)ygroups; a.nyg = nyg; a.NT = ntiles_n; a.KS = H / 64; a.cg = cg; a.ntiles = ceil_div(num_edges, kET);
+    GMP_CUDA(cudaFuncSetAttribute(tp_contract_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcTpSmem));
+    tp_contract_tc_kernel<<<nchunks, kTcThreads, kTcTpSmem, stream>>>(a);
+    int rc = check_launch("tp_contract_tc_kernel");
+    if (rc != GMP_OK) return rc;
+    if (nchunks > 1) {
+        tp_tc_fixup_kernel<<<(unsigned)ceil_div(r_len, 128), 128, 0, stream>>>(rowptr, n, num_edges, a.ntiles, nchunks, head, res, r_len);
+        rc = check_launch("tp_tc_fixup_kernel");
+    }
+    return rc;
+}
+
+}  // extern "C"

@@ -244,6 +244,15 @@ class TensorProductPlan:
                               2 * p.l_out + 1, p.sh_off, 2 * p.l_sh + 1, fwd_cg[k], 0])
         self.wunits = np.asarray(units, dtype=np.int32).reshape(-1, 12)
         self.cg = np.concatenate(cg) if cg else np.zeros(1, np.float32)
+        # tensor-core path (csrc/tpconv_tc.cu): a = summed multiplicity index, b = kept one
+        self.tc_fwd = self._tc_tables([
+            dict(w_off=p.w_off, stride_a=p.mul_out, stride_b=1, MA=p.mul_in, MB=p.mul_out, v_off=p.in_off, DA=2 * p.l_in + 1,
+                 DB=2 * p.l_out + 1, sh_off=p.sh_off, DS=2 * p.l_sh + 1, cg_off=fwd_cg[k], r_off=p.out_off)
+            for k, p in enumerate(self.paths)])
+        self.tc_bwd = self._tc_tables([
+            dict(w_off=p.w_off, stride_a=1, stride_b=p.mul_out, MA=p.mul_out, MB=p.mul_in, v_off=p.out_off, DA=2 * p.l_out + 1,
+                 DB=2 * p.l_in + 1, sh_off=p.sh_off, DS=2 * p.l_sh + 1, cg_off=bwd_cg[k], r_off=p.in_off)
+            for k, p in enumerate(self.paths)])
         self._dev = {}
 
     def _contract_tables(self, blocks, block_of, pass_of):
@@ -265,14 +274,86 @@ class TensorProductPlan:
         return dict(passes=np.asarray(passes, dtype=np.int32).reshape(-1, 12), blocks=np.asarray(blks, dtype=np.int32).reshape(-1, 8),
                     nblocks=len(blks), nunits=unit)
 
+    @staticmethod
+    def _tc_tables(roles):
+        """y-groups (path x range of the summed index), N-tiles (256 generated weights each, in the order the
+        kernel consumes them), and the per-path tables of the bias term (struct layouts: csrc/tpconv_tc.cu)."""
+        ygroups, ntiles, ypaths, zent, bias = [], [], [], [], []
+        y_off = z_off = 0
+        for r in roles:
+            DA, DB, MA, MB = r["DA"], r["DB"], r["MA"], r["MB"]
+            xm = DA < DB
+            M = DA if xm else DB
+            WS = 32 if (not xm and DB == 1) else 8
+            MC = 256 // WS
+            AR = 64 if M == 1 else 32
+            for A0 in range(0, MA, AR):
+                ARv = min(AR, MA - A0)
+                nsub, nslices = -(-ARv // MC), -(-MB // WS)
+                ygroups.append([r["v_off"], DA, DB, r["DS"], r["sh_off"], r["cg_off"], A0, ARv, r["r_off"], MB, nslices, nsub])
+                for sl in range(nslices):
+                    for q in range(nsub):
+                        ntiles.append([r["w_off"], r["stride_a"], r["stride_b"], A0 + q * MC, A0 + ARv, sl * WS, MB, WS])
+            ypaths.append([r["v_off"], DA, DB, MA, y_off, z_off, 0, 0])
+            for i in range(DA):
+                for k in range(DB):
+                    zent.append([r["sh_off"], r["DS"], r["cg_off"] + i * r["DS"] * DB + k, DB])
+            bias.append(dict(y_off=y_off, MA=MA, MB=MB, DB=DB, r_off=r["r_off"], w_off=r["w_off"], stride_a=r["stride_a"],
+                             stride_b=r["stride_b"]))
+            y_off += MA * DB
+            z_off += DA * DB
+        i32 = lambda a, w: np.asarray(a, dtype=np.int32).reshape(-1, w)
+        return dict(ygroups=i32(ygroups, 12), ntiles=i32(ntiles, 8), ypaths=i32(ypaths, 8), zent=i32(zent, 4), bias=bias,
+                    y_len=y_off, npairs=sum(r["MA"] for r in roles))
+
     def device(self, dev):
         key = str(dev)
         if key not in self._dev:
             t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
-            self._dev[key] = dict(cg=t(self.cg), wunits=t(self.wunits),
-                                  fwd_passes=t(self.fwd["passes"]), fwd_blocks=t(self.fwd["blocks"]),
-                                  bwd_passes=t(self.bwd["passes"]), bwd_blocks=t(self.bwd["blocks"]))
+            d = dict(cg=t(self.cg), wunits=t(self.wunits),
+                     fwd_passes=t(self.fwd["passes"]), fwd_blocks=t(self.fwd["blocks"]),
+                     bwd_passes=t(self.bwd["passes"]), bwd_blocks=t(self.bwd["blocks"]))
+            for name, tab in (("tc_fwd", self.tc_fwd), ("tc_bwd", self.tc_bwd)):
+                for k in ("ygroups", "ntiles", "ypaths", "zent"):
+                    d[f"{name}_{k}"] = t(tab[k])
+            self._dev[key] = d
         return self._dev[key]
+
+
+def _tc_contract(csr, n, E, V, r_len, edge_sh, edge_feat, w1, b1, w2, b2, plan: "TensorProductPlan", which: str, d):
+    """res[n] = sum_{e in CSR row n} sum_a (T_e[a,b] + b2[a,b]) Y_e[a,k] on the tensor cores (bf16 operands, fp32
+    accumulation): gmp_tp_tc_contract for the T part, gmp_tp_ysum + node-level GEMMs (cuBLAS) for the bias part."""
+    tab = plan.tc_fwd if which == "tc_fwd" else plan.tc_bwd
+    L = _lib.lib()
+    H, R, S = w1.shape[0], w1.shape[1], edge_sh.shape[1]
+    if H % 64 != 0 or H > 256:
+        raise NotImplementedError("precision='bf16': mlp_dim must be 64, 128, 192 or 256")
+    dev = V.device
+    res = torch.empty(n, r_len, dtype=torch.float32, device=dev)
+    NT = tab["ntiles"].shape[0]
+    hid_img = torch.empty(max(int(L.gmp_tp_tc_hid_bytes(E, H)), 16), dtype=torch.uint8, device=dev)
+    w2_img = torch.empty(max(int(L.gmp_tp_tc_w2_bytes(NT, H)), 16), dtype=torch.uint8, device=dev)
+    head = torch.empty(int(L.gmp_tp_tc_num_chunks(E)), r_len, dtype=torch.float32, device=dev)
+    call("gmp_tp_tc_pack_hid", csr.perm_ptr, E, ptr(edge_feat), R, ptr(w1), ptr(b1), H, ptr(hid_img))
+    call("gmp_tp_tc_pack_w2", ptr(w2), H, ptr(d[which + "_ntiles"]), NT, ptr(w2_img))
+    call("gmp_tp_tc_contract", ptr(csr.rowptr), ptr(csr.col), csr.perm_ptr, n, E, ptr(V), V.shape[1], ptr(res), r_len, ptr(head),
+         ptr(edge_sh), S, ptr(hid_img), ptr(w2_img), ptr(d[which + "_ygroups"]), tab["ygroups"].shape[0], NT, H, ptr(d["cg"]))
+    ys = _tc_ysum(csr, n, E, V, edge_sh, tab, which, d)
+    for bs in tab["bias"]:
+        Bm = b2.as_strided((bs["MA"], bs["MB"]), (bs["stride_a"], bs["stride_b"]), b2.storage_offset() + bs["w_off"])
+        ysp = ys[:, bs["y_off"]:bs["y_off"] + bs["MA"] * bs["DB"]].view(n, bs["MA"], bs["DB"])
+        blk = res[:, bs["r_off"]:bs["r_off"] + bs["MB"] * bs["DB"]].view(n, bs["MB"], bs["DB"])
+        blk += torch.einsum("nak,ab->nbk", ysp, Bm)
+    return res
+
+
+def _tc_ysum(csr, n, E, V, edge_sh, tab, which, d):
+    """YS[n][path, a, k] = sum_{e in row n} sum_i V[col_e][a, i] Z_e[i, k]  (fp32; the bias term and db2 are linear in it)."""
+    ys = torch.empty(n, max(tab["y_len"], 1), dtype=torch.float32, device=V.device)
+    call("gmp_tp_ysum", ptr(csr.rowptr), ptr(csr.col), csr.perm_ptr, n, E, ptr(V), V.shape[1], ptr(edge_sh), edge_sh.shape[1],
+         ptr(d[which + "_ypaths"]), tab["ypaths"].shape[0], tab["npairs"], ptr(d[which + "_zent"]), tab["zent"].shape[0],
+         ptr(d["cg"]), ptr(ys), ys.shape[1])
+    return ys
 
 
 class _TPConvFn(torch.autograd.Function):
@@ -284,13 +365,15 @@ class _TPConvFn(torch.autograd.Function):
         w1, b1, w2, b2 = (t.contiguous() for t in (w1, b1, w2, b2))
         d = plan.device(x.device)
         csr = graph.by_src  # rows = edge_index[0] (aggregation), col = edge_index[1] (gather)
-        out = torch.empty(graph.n, plan.irreps_out.dim, dtype=x.dtype, device=x.device)
         H, R, S = w1.shape[0], w1.shape[1], edge_sh.shape[1]
+        ctx.save_for_backward(x, edge_sh, edge_feat, w1, b1, w2, b2)
+        ctx.graph, ctx.plan, ctx.precision = graph, plan, precision
+        if precision == _lib.BF16_TC:
+            return _tc_contract(csr, graph.n, graph.E, x, plan.irreps_out.dim, edge_sh, edge_feat, w1, b1, w2, b2, plan, "tc_fwd", d)
+        out = torch.empty(graph.n, plan.irreps_out.dim, dtype=x.dtype, device=x.device)
         call("gmp_tp_contract", ptr(csr.rowptr), ptr(csr.col), csr.perm_ptr, graph.n, graph.E, ptr(x), x.shape[1], ptr(out),
              out.shape[1], ptr(edge_sh), S, ptr(edge_feat), R, ptr(w1), ptr(b1), ptr(w2), ptr(b2), H, ptr(d["fwd_passes"]),
              ptr(d["fwd_blocks"]), plan.fwd["nblocks"], plan.fwd["nunits"], ptr(d["cg"]), precision)
-        ctx.save_for_backward(x, edge_sh, edge_feat, w1, b1, w2, b2)
-        ctx.graph, ctx.plan, ctx.precision = graph, plan, precision
         return out
 
     @staticmethod
@@ -306,10 +389,13 @@ class _TPConvFn(torch.autograd.Function):
         dx = None
         if ctx.needs_input_grad[0]:
             t = graph.by_dst  # rows = edge_index[1] (where node_attr was gathered), col = edge_index[0]
-            dx = torch.empty_like(x)
-            call("gmp_tp_contract", ptr(t.rowptr), ptr(t.col), t.perm_ptr, graph.n, graph.E, ptr(g), g.shape[1], ptr(dx),
-                 dx.shape[1], ptr(edge_sh), S, ptr(edge_feat), R, ptr(w1), ptr(b1), ptr(w2), ptr(b2), H, ptr(d["bwd_passes"]),
-                 ptr(d["bwd_blocks"]), plan.bwd["nblocks"], plan.bwd["nunits"], ptr(d["cg"]), precision)
+            if precision == _lib.BF16_TC:
+                dx = _tc_contract(t, graph.n, graph.E, g, x.shape[1], edge_sh, edge_feat, w1, b1, w2, b2, plan, "tc_bwd", d)
+            else:
+                dx = torch.empty_like(x)
+                call("gmp_tp_contract", ptr(t.rowptr), ptr(t.col), t.perm_ptr, graph.n, graph.E, ptr(g), g.shape[1], ptr(dx),
+                     dx.shape[1], ptr(edge_sh), S, ptr(edge_feat), R, ptr(w1), ptr(b1), ptr(w2), ptr(b2), H, ptr(d["bwd_passes"]),
+                     ptr(d["bwd_blocks"]), plan.bwd["nblocks"], plan.bwd["nunits"], ptr(d["cg"]), precision)
         csr = graph.by_src
         nunits = plan.wunits.shape[0]
         plen = _lib.lib().gmp_tp_wgrad_part_len(H)
@@ -317,7 +403,7 @@ class _TPConvFn(torch.autograd.Function):
         parts = torch.empty(max(nunits, 1), plen, dtype=x.dtype, device=x.device)
         call("gmp_tp_wgrad", ptr(csr.rowptr), ptr(csr.col), csr.perm_ptr, graph.n, graph.E, ptr(x), x.shape[1], ptr(g), g.shape[1],
              ptr(edge_sh), S, ptr(edge_feat), R, ptr(w1), ptr(b1), ptr(w2), H, ptr(d["wunits"]), nunits, ptr(d["cg"]), ptr(dW2),
-             ptr(db2), ptr(parts), precision)
+             ptr(db2), ptr(parts), _lib.FP32_STRICT)
         red = torch.empty(plen, dtype=x.dtype, device=x.device)
         call("gmp_reduce_partials_f32", ptr(parts), nunits, plen, ptr(red))
         dW1 = red[:H * 16].view(H, 16)[:, :R].contiguous()

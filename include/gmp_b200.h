@@ -266,6 +266,34 @@ int gmp_tp_wgrad(const int32_t* rowptr, const int32_t* col, const int32_t* perm,
                  int32_t precision, gmp_stream_t stream);
 int64_t gmp_tp_wgrad_part_len(int32_t H);
 
+/* ---- GMP_BF16_TC variant of the same layer (csrc/tpconv_tc.cu): fc's second Linear runs on tcgen05 (bf16 operands,
+ * fp32 accumulation in tensor memory; 1e-2 relative), the generated weights are consumed out of tensor memory.
+ * The operands are staged once per call as UMMA shared-memory images:
+ *   hid_img : relu(w1 edge_feat + b1) of every 128-edge tile of the CSR order, bf16  (gmp_tp_tc_hid_bytes bytes)
+ *   w2_img  : the rows of w2 of every 256-column "N-tile", bf16, in consumption order (gmp_tp_tc_w2_bytes bytes)
+ * `ntile_table` [ntiles_n] (8 int32, struct TcNTile) and `ygroups` [nyg] (12 int32, struct TcYGroup) are device
+ * tables built by the host from the e3nn instruction list (gmp_b200/tfn.py).  `res` [n, r_len] is overwritten;
+ * `head` [gmp_tp_tc_num_chunks(E), r_len] is scratch.  fc's second bias is NOT applied here: it contributes
+ * sum_a b2[a,b] YS[n][a,k] with YS from gmp_tp_ysum (fp32), a node-level GEMM the caller adds. */
+int32_t gmp_tp_tc_num_chunks(int64_t num_edges);
+int64_t gmp_tp_tc_hid_bytes(int64_t num_edges, int32_t H);
+int64_t gmp_tp_tc_w2_bytes(int32_t ntiles_n, int32_t H);
+int gmp_tp_tc_pack_hid(const int32_t* perm, int64_t num_edges, const float* edge_feat, int32_t R, const float* w1,
+                       const float* b1, int32_t H, void* hid_img, gmp_stream_t stream);
+int gmp_tp_tc_pack_w2(const float* w2, int32_t H, const void* ntile_table, int32_t ntiles_n, void* w2_img,
+                      gmp_stream_t stream);
+int gmp_tp_tc_contract(const int32_t* rowptr, const int32_t* col, const int32_t* perm, int64_t n, int64_t num_edges,
+                       const float* V, int32_t v_len, float* res, int32_t r_len, float* head, const float* edge_sh,
+                       int32_t S, const void* hid_img, const void* w2_img, const void* ygroups, int32_t nyg,
+                       int32_t ntiles_n, int32_t H, const float* cg, gmp_stream_t stream);
+/* YS[n][y_off_p + a*DB_p + k] = sum_{e in CSR row n} sum_i V[col_e][v_off_p + a*DA_p + i] * Z^p_e[i][k], fp32:
+ * the node-level aggregate in which both the bias term of the layer and db2 are linear.
+ * `ypaths` [npaths] (8 int32, struct TcYPath), `zentries` [nz] (4 int32, struct TcZEntry); npairs = sum_p MA_p. */
+int gmp_tp_ysum(const int32_t* rowptr, const int32_t* col, const int32_t* perm, int64_t n, int64_t num_edges,
+                const float* V, int32_t v_len, const float* edge_sh, int32_t S, const void* ypaths, int32_t npaths,
+                int32_t npairs, const void* zentries, int32_t nz, const float* cg, float* YS, int32_t y_len,
+                gmp_stream_t stream);
+
 /* ============================================================================================ */
 /* MACE symmetric contraction (models/mace_modules/symmetric_contraction.py:169-185)              */
 /* ============================================================================================ */

@@ -64,3 +64,35 @@ def test_cfconv_bf16_tc_vs_fp32(graphs, nodes, lazy):
         assert rel_err(a, b) <= 1e-2
     # deterministic
     assert torch.equal(o16, m16(x16, ei, ew, attr))
+
+
+@pytest.mark.parametrize("C,gate,graphs,nodes,shuffle,mlp", [(64, True, 6, 24, True, 256), (16, False, 3, 12, False, 64),
+                                                            (128, False, 40, 16, False, 256)])
+def test_tp_conv_bf16_tc_vs_fp32(C, gate, graphs, nodes, shuffle, mlp):
+    """TFN / MACE tensor-product convolution: tcgen05 path (bf16 operands of fc's second Linear, bf16 factor) against
+    the fp32-strict kernels, forward, d/d node_attr and parameter gradients: 1e-2 normwise relative."""
+    import gmp_b200
+    d = random_clouds(graphs, nodes, 3.0, 1.9, 700 + C)
+    ei, pos = d["edge_index"], d["pos"]
+    if shuffle:
+        ei = ei[:, torch.randperm(ei.shape[1], generator=torch.Generator().manual_seed(1))]
+    ei, pos = ei.cuda(), pos.cuda()
+    hid, sh_ir = f"{C}x0e+{C}x1o+{C}x2e", "1x0e+1x1o+1x2e"
+    torch.manual_seed(C)
+    m32 = gmp_b200.TensorProductConvLayer(hid, hid, sh_ir, 8, mlp, gate=gate).cuda()
+    with torch.no_grad():
+        m32.fc[2].bias.normal_(0, 0.05)
+    m16 = gmp_b200.TensorProductConvLayer(hid, hid, sh_ir, 8, mlp, gate=gate, precision="bf16").cuda()
+    m16.load_state_dict(m32.state_dict())
+    esh, eft = gmp_b200.edge_geometry(pos, ei, 2, gmp_b200.RadialEmbeddingBlock(2.0, 8, 5))
+    x = torch.randn(pos.shape[0], 9 * C, device="cuda")
+    x32, x16 = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
+    o32, o16 = m32(x32, ei, esh, eft), m16(x16, ei, esh, eft)
+    torch.cuda.synchronize()
+    assert rel_err(o16, o32) <= 1e-2
+    cot = torch.randn_like(o32)
+    g32 = torch.autograd.grad((o32 * cot).sum(), [x32] + list(m32.parameters()))
+    g16 = torch.autograd.grad((o16 * cot).sum(), [x16] + list(m16.parameters()))
+    for a, b, name in zip(g16, g32, ["node_attr"] + [k for k, _ in m32.named_parameters()]):
+        assert rel_err(a, b) <= 1e-2, name
+    assert torch.equal(o16, m16(x16, ei, esh, eft))  # deterministic

@@ -78,3 +78,63 @@ def test_gate_batchnorm_radial_sh_modules_match_oracle():
     rad = gmp_b200.RadialEmbeddingBlock(2.0, 8, 5)
     assert (rad(vec.norm(dim=-1, keepdim=True)) - fx["outputs"]["rbf"]).abs().max() < 2e-6
     assert (gmp_b200.SphericalHarmonics(2)(vec) - fx["outputs"]["sh"]).abs().max() < 2e-6
+
+
+def _emulate_tc_contract(tab, cg, rowidx, colidx, V, sh, T, b2, n, r_len):
+    """numpy restatement of what csrc/tpconv_tc.cu computes from the host tables: N-tile columns -> W2 rows,
+    factor per y-group, per-edge results summed into rows; plus the bias term through YS (gmp_tp_ysum + GEMM)."""
+    res = np.zeros((n, r_len))
+    E = len(rowidx)
+    nt_iter = iter(tab["ntiles"])
+    for (v_off, DA, DB, DS, sh_off, cg_off, A0, AR, r_off, MB, nslices, nsub) in tab["ygroups"]:
+        Zc = cg[cg_off:cg_off + DA * DS * DB].reshape(DA, DS, DB)
+        Z = np.einsum("ej,ijk->eik", sh[:, sh_off:sh_off + DS], Zc)
+        WS = 32 if (DA >= DB and DB == 1) else 8
+        for sl in range(nslices):
+            for q in range(nsub):
+                w_off, sa, sb, a_begin, a_end, b0, b_end, ws = next(nt_iter)
+                assert ws == WS and b0 == sl * WS and a_begin == A0 + q * (256 // WS) and a_end == A0 + AR and b_end == MB
+                for c in range(256):
+                    a, b = a_begin + c // WS, b0 + c % WS
+                    if a >= a_end or b >= b_end:
+                        continue
+                    y = np.einsum("ei,eik->ek", V[colidx, v_off + a * DA:v_off + (a + 1) * DA], Z)
+                    np.add.at(res, (rowidx[:, None], (r_off + b * DB + np.arange(DB))[None, :]), T[:, w_off + a * sa + b * sb, None] * y)
+    assert next(nt_iter, None) is None
+    # bias: YS[n][path][a][k], then sum_a b2[a,b] YS[n,a,k]
+    for (v_off, DA, DB, MA, y_off, z_off, _, _), bs in zip(tab["ypaths"], tab["bias"]):
+        zs = tab["zent"][z_off:z_off + DA * DB]
+        Z = np.stack([sum(sh[:, so + j] * cg[base + j * st] for j in range(ds)) for so, ds, base, st in zs], 1).reshape(E, DA, DB)
+        Ye = np.einsum("eai,eik->eak", V[colidx, v_off:v_off + MA * DA].reshape(E, MA, DA), Z)
+        YS = np.zeros((n, MA, DB))
+        np.add.at(YS, rowidx, Ye)
+        Bm = np.array([[b2[bs["w_off"] + a * bs["stride_a"] + b * bs["stride_b"]] for b in range(bs["MB"])] for a in range(MA)])
+        res[:, bs["r_off"]:bs["r_off"] + bs["MB"] * DB] += np.einsum("nak,ab->nbk", YS, Bm).reshape(n, -1)
+    return res
+
+
+@pytest.mark.parametrize("cin,cout", [("8x0e+8x1o+8x2e", "24x0e+8x1o+8x2e"), ("40x0e+12x1o", "12x0e+40x1o+4x2e")])
+def test_tc_tables_reproduce_the_tensor_product(cin, cout):
+    """The tensor-core decomposition (y-groups, N-tiles, YS bias term) is exact algebra: forward and feature gradient."""
+    import gmp_b200
+    sh_ir = "1x0e+1x1o+1x2e"
+    plan = gmp_b200.TensorProductPlan(cin, sh_ir, cout)
+    tp = o3.FullyConnectedTensorProduct(cin, sh_ir, cout, shared_weights=False)
+    g = torch.Generator().manual_seed(5)
+    n, E = 7, 23
+    src, dst = torch.randint(0, n, (E,), generator=g), torch.randint(0, n, (E,), generator=g)
+    x = torch.randn(n, plan.irreps_in.dim, dtype=torch.float64, generator=g).requires_grad_(True)
+    sh = torch.randn(E, 9, dtype=torch.float64, generator=g)
+    T = torch.randn(E, plan.weight_numel, dtype=torch.float64, generator=g)
+    b2 = torch.randn(plan.weight_numel, dtype=torch.float64, generator=g)
+    tp = tp.double()
+    out = torch.zeros(n, plan.irreps_out.dim, dtype=torch.float64).index_add_(0, src, tp(x[dst], sh, T + b2))
+    cot = torch.randn(out.shape, dtype=torch.float64, generator=g)
+    (dx,) = torch.autograd.grad((out * cot).sum(), [x])
+    cg = plan.cg.astype(np.float64)
+    mine = _emulate_tc_contract(plan.tc_fwd, cg, src.numpy(), dst.numpy(), x.detach().numpy(), sh.numpy(), T.numpy(), b2.numpy(),
+                                n, plan.irreps_out.dim)
+    assert np.abs(mine - out.detach().numpy()).max() <= 1e-5 * np.abs(out.detach().numpy()).max()
+    mine_dx = _emulate_tc_contract(plan.tc_bwd, cg, dst.numpy(), src.numpy(), cot.numpy(), sh.numpy(), T.numpy(), b2.numpy(),
+                                   n, plan.irreps_in.dim)
+    assert np.abs(mine_dx - dx.numpy()).max() <= 1e-5 * np.abs(dx.numpy()).max()
