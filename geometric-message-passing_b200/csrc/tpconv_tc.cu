@@ -243,6 +243,101 @@ struct EpiCtx {
     uint32_t gi;       // N-tile counter (all tiles)
 };
 
+// Z[i][k] = sum_j sh_e[sh_off + j] * Zc[i][j][k]   (Zc = CG block with the path coefficient folded in)
+template <int DA, int DB>
+__device__ __forceinline__ void tc_compute_z(const float* __restrict__ sh_row, const float* __restrict__ cg, int DS, bool valid,
+                                             float (&Z)[DA][DB]) {
+    float sb[5];
+#pragma unroll
+    for (int j = 0; j < 5; ++j) sb[j] = (valid && j < DS) ? __ldg(sh_row + j) : 0.f;
+#pragma unroll
+    for (int i = 0; i < DA; ++i)
+#pragma unroll
+        for (int k = 0; k < DB; ++k) {
+            float s = 0.f;
+#pragma unroll
+            for (int j = 0; j < 5; ++j)
+                if (j < DS) s = fmaf(sb[j], __ldg(cg + (i * DS + j) * DB + k), s);
+            Z[i][k] = s;
+        }
+}
+
+// factor of one a from the gathered components x[0..DA): Y[k] = sum_i x[i] Z[i][k] when DA >= DB, else x itself
+template <int DA, int DB>
+__device__ __forceinline__ void tc_factor(const float* x, const float (&Z)[DA][DB], float (&y)[(DA < DB) ? DA : DB]) {
+    constexpr bool XM = DA < DB;
+    constexpr int M = XM ? DA : DB;
+    if constexpr (XM) {
+#pragma unroll
+        for (int i = 0; i < M; ++i) y[i] = x[i];
+    } else {
+#pragma unroll
+        for (int k = 0; k < M; ++k) {
+            float s = 0.f;
+#pragma unroll
+            for (int i = 0; i < DA; ++i) s = fmaf(x[i], Z[i][k], s);
+            y[k] = s;
+        }
+    }
+}
+
+// 4 consecutive a's of the gathered row -> xs[4*DA]  (a0 relative to the y-group's A0; zeros beyond AR / for padding edges)
+template <int DA>
+__device__ __forceinline__ void tc_load_x4(const float* __restrict__ xrow, int A0, int AR, int al0, bool valid, bool vec_ok,
+                                           float (&xs)[4 * DA]) {
+    if (valid && vec_ok && al0 + 4 <= AR) {
+        const float4* p = reinterpret_cast<const float4*>(xrow + (int64_t)(A0 + al0) * DA);
+#pragma unroll
+        for (int v = 0; v < DA; ++v) {
+            const float4 f = __ldg(p + v);
+            xs[4 * v] = f.x; xs[4 * v + 1] = f.y; xs[4 * v + 2] = f.z; xs[4 * v + 3] = f.w;
+        }
+    } else {
+#pragma unroll
+        for (int v = 0; v < 4 * DA; ++v) xs[v] = (valid && al0 + v / DA < AR) ? __ldg(xrow + (int64_t)(A0 + al0) * DA + v) : 0.f;
+    }
+}
+
+template <int M>
+__device__ __forceinline__ void tc_store_factor(uint32_t* dst, const float (&y)[M]) {
+    if constexpr (M == 1) dst[0] = __float_as_uint(y[0]);
+    if constexpr (M == 3) { dst[0] = pack_bf16(y[0], y[1]); dst[256] = pack_bf16(y[2], 0.f); }
+    if constexpr (M == 5) { dst[0] = pack_bf16(y[0], y[1]); dst[256] = pack_bf16(y[2], y[3]); dst[512] = pack_bf16(y[4], 0.f); }
+}
+template <int M>
+__device__ __forceinline__ void tc_load_factor(const uint32_t* src, float (&y)[M]) {
+    if constexpr (M == 1) y[0] = __uint_as_float(src[0]);
+    if constexpr (M == 3) { const uint32_t w0 = src[0], w1 = src[256]; y[0] = bf_lo(w0); y[1] = bf_hi(w0); y[2] = bf_lo(w1); }
+    if constexpr (M == 5) {
+        const uint32_t w0 = src[0], w1 = src[256], w2 = src[512];
+        y[0] = bf_lo(w0); y[1] = bf_hi(w0); y[2] = bf_lo(w1); y[3] = bf_hi(w1); y[4] = bf_lo(w2);
+    }
+}
+
+// factor scratch of one y-group for this thread's a's (sub-chunk q, local a in [g*HA, g*HA + HA)):
+// F[((q*HA + a_local) * W + word) * 256]  (F already offset by g*128 + e)
+template <int DA, int DB>
+__device__ __forceinline__ void tc_build_factor(uint32_t* F, const float* __restrict__ xrow, int v_len, const TcYGroup& G, int g,
+                                                bool valid, const float (&Z)[DA][DB]) {
+    constexpr bool XM = DA < DB;
+    constexpr int M = XM ? DA : DB;
+    constexpr int WS = (!XM && DB == 1) ? 32 : 8;
+    constexpr int MC = 256 / WS, HA = MC / 2;
+    constexpr int W = (M + 1) / 2;
+    const bool vec_ok = ((v_len | G.v_off) & 3) == 0;
+    for (int q = 0; q < G.nsub; ++q)
+        for (int a4 = 0; a4 < HA; a4 += 4) {
+            float xs[4 * DA];
+            tc_load_x4<DA>(xrow, G.A0, G.AR, q * MC + g * HA + a4, valid, vec_ok, xs);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float y[M];
+                tc_factor<DA, DB>(xs + j * DA, Z, y);
+                tc_store_factor<M>(F + ((q * HA + a4 + j) * W) * 256, y);
+            }
+        }
+}
+
 // One y-group for compile-time irrep dimensions DA (gathered) / DB (kept).
 //   DA >= DB: the factor is Y[a][k] = sum_i x[a][i] Z[i][k]  (M = DB values per a), results come out directly;
 //   DA <  DB: the factor is x[a][i] itself (M = DA values), r[b][i] = sum_a T x, and out[b][k] = sum_i r[b][i] Z[i][k] at the flush.
@@ -255,65 +350,9 @@ __device__ __forceinline__ void tc_ygroup(EpiCtx& c, const TcYGroup& G) {
     constexpr int W = (M + 1) / 2;
     const TcTpArgs& a = *c.a;
     uint32_t* F = reinterpret_cast<uint32_t*>(c.sm + oF) + c.g * 128 + c.e;
-    // ---- Z[i][k] = sum_j sh[j] Zc[i][j][k]
     float Z[DA][DB];
-    {
-        float sb[5];
-#pragma unroll
-        for (int j = 0; j < 5; ++j) sb[j] = (c.valid && j < G.DS) ? __ldg(a.sh + c.eid * a.S + G.sh_off + j) : 0.f;
-#pragma unroll
-        for (int i = 0; i < DA; ++i)
-#pragma unroll
-            for (int k = 0; k < DB; ++k) {
-                float s = 0.f;
-#pragma unroll
-                for (int j = 0; j < 5; ++j)
-                    if (j < G.DS) s = fmaf(sb[j], __ldg(a.cg + G.cg_off + (i * G.DS + j) * DB + k), s);
-                Z[i][k] = s;
-            }
-    }
-    // ---- factor for this thread's a's: sub-chunk q, local a in [g*HA, g*HA + HA)
-    {
-        const float* xrow = a.V + (int64_t)c.gnode * a.v_len + G.v_off;
-        const bool vec_ok = ((a.v_len | G.v_off) & 3) == 0;
-        for (int q = 0; q < G.nsub; ++q)
-            for (int a4 = 0; a4 < HA; a4 += 4) {
-                const int al0 = q * MC + c.g * HA + a4;  // relative to A0
-                float xs[4 * DA];
-                if (c.valid && vec_ok && al0 + 4 <= G.AR) {
-                    const float4* p = reinterpret_cast<const float4*>(xrow + (int64_t)(G.A0 + al0) * DA);
-#pragma unroll
-                    for (int v = 0; v < DA; ++v) {
-                        const float4 f = __ldg(p + v);
-                        xs[4 * v] = f.x; xs[4 * v + 1] = f.y; xs[4 * v + 2] = f.z; xs[4 * v + 3] = f.w;
-                    }
-                } else {
-#pragma unroll
-                    for (int v = 0; v < 4 * DA; ++v)
-                        xs[v] = (c.valid && al0 + v / DA < G.AR) ? __ldg(xrow + (int64_t)(G.A0 + al0) * DA + v) : 0.f;
-                }
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    float y[M];
-                    if constexpr (XM) {
-#pragma unroll
-                        for (int i = 0; i < M; ++i) y[i] = xs[j * DA + i];
-                    } else {
-#pragma unroll
-                        for (int k = 0; k < M; ++k) {
-                            float s = 0.f;
-#pragma unroll
-                            for (int i = 0; i < DA; ++i) s = fmaf(xs[j * DA + i], Z[i][k], s);
-                            y[k] = s;
-                        }
-                    }
-                    uint32_t* dst = F + ((q * HA + a4 + j) * W) * 256;
-                    if constexpr (M == 1) dst[0] = __float_as_uint(y[0]);
-                    if constexpr (M == 3) { dst[0] = pack_bf16(y[0], y[1]); dst[256] = pack_bf16(y[2], 0.f); }
-                    if constexpr (M == 5) { dst[0] = pack_bf16(y[0], y[1]); dst[256] = pack_bf16(y[2], y[3]); dst[512] = pack_bf16(y[4], 0.f); }
-                }
-            }
-    }
+    tc_compute_z<DA, DB>(a.sh + c.eid * a.S + G.sh_off, a.cg + G.cg_off, G.DS, c.valid, Z);
+    tc_build_factor<DA, DB>(F, a.V + (int64_t)c.gnode * a.v_len + G.v_off, a.v_len, G, c.g, c.valid, Z);
     // ---- N-tiles: kept slices x sub-chunks of the summed index
     for (int sl = 0; sl < G.nslices; ++sl) {
         float r[WS * M];
@@ -337,12 +376,7 @@ __device__ __forceinline__ void tc_ygroup(EpiCtx& c, const TcYGroup& G) {
                     for (int aa = 0; aa < 4; ++aa) {
                         const uint32_t* src = F + ((q * HA + 4 * j + aa) * W) * 256;
                         float y[M];
-                        if constexpr (M == 1) y[0] = __uint_as_float(src[0]);
-                        if constexpr (M == 3) { const uint32_t w0 = src[0], w1 = src[256]; y[0] = bf_lo(w0); y[1] = bf_hi(w0); y[2] = bf_lo(w1); }
-                        if constexpr (M == 5) {
-                            const uint32_t w0 = src[0], w1 = src[256], w2 = src[512];
-                            y[0] = bf_lo(w0); y[1] = bf_hi(w0); y[2] = bf_lo(w1); y[3] = bf_hi(w1); y[4] = bf_lo(w2);
-                        }
+                        tc_load_factor<M>(src, y);
 #pragma unroll
                         for (int b = 0; b < 8; ++b)
 #pragma unroll
@@ -564,6 +598,442 @@ __global__ void __launch_bounds__(kTcThreads, 1) tp_contract_tc_kernel(TcTpArgs 
     if (warp == 11) tmem_dealloc<512>(tm);
 }
 
+// ------------------------------------------------------------------------------------------------
+// weight-gradient side.  dT_e[a,b] = sum_k g[row_e][b,k] * Y_e[a,k] is generated on the CUDA cores, written as a bf16
+// UMMA operand image [128 edges][256 columns] (row = edge, 128B swizzle: K-major for dhid = dT W2, the same bytes
+// are the MN-major operand of dW2 = dT^T hid), and both products accumulate in tensor memory:
+//   tp_dhid_tc_kernel : edge-stationary, D[128 e][H]    += dT[e, N-tile] * W2[N-tile, :]  over every N-tile
+//   tp_dw2_tc_kernel  : weight-stationary, D[256 c][H]  += dT[:, c]^T * hid[:, :]         over every edge tile
+// ------------------------------------------------------------------------------------------------
+// WS elements of one a:  dT[b] = sum_m r[b*M+m] * y[m]  ->  16-byte chunks of row e starting at column c0
+template <int M, int WS>
+__device__ __forceinline__ void tc_dt_store(uint8_t* A, int e, int c0, const float (&r)[WS * M], const float (&y)[M]) {
+#pragma unroll
+    for (int ch = 0; ch < WS / 8; ++ch) {
+        float d[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            float s = 0.f;
+#pragma unroll
+            for (int m = 0; m < M; ++m) s = fmaf(r[(ch * 8 + q) * M + m], y[m], s);
+            d[q] = s;
+        }
+        const int c = c0 + ch * 8;
+        *reinterpret_cast<uint4*>(A + (c >> 6) * kStage + sw128_chunk_off(e, (c & 63) >> 3)) =
+            make_uint4(pack_bf16(d[0], d[1]), pack_bf16(d[2], d[3]), pack_bf16(d[4], d[5]), pack_bf16(d[6], d[7]));
+    }
+}
+
+// r[b][m] of a kept slice from the row node's gradient: g values (DA >= DB, m = k) or their contraction with Z (m = i)
+template <int DA, int DB, int WS>
+__device__ __forceinline__ void tc_load_gside(const float* __restrict__ grow, int nb, bool valid, const float (&Z)[DA][DB],
+                                              float (&r)[WS * ((DA < DB) ? DA : DB)]) {
+    constexpr bool XM = DA < DB;
+    constexpr int M = XM ? DA : DB;
+#pragma unroll
+    for (int b = 0; b < WS; ++b) {
+        float gv[DB];
+#pragma unroll
+        for (int k = 0; k < DB; ++k) gv[k] = (valid && b < nb) ? __ldg(grow + b * DB + k) : 0.f;
+        if constexpr (XM) {
+#pragma unroll
+            for (int i = 0; i < M; ++i) {
+                float s = 0.f;
+#pragma unroll
+                for (int k = 0; k < DB; ++k) s = fmaf(gv[k], Z[i][k], s);
+                r[b * M + i] = s;
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < M; ++k) r[b * M + k] = gv[k];
+        }
+    }
+}
+
+struct TcDhArgs {
+    const int32_t *rowptr, *col, *perm;
+    int64_t n, E;
+    const float* x;
+    int32_t x_len;
+    const float* g;
+    int32_t g_len;
+    const float* sh;
+    int32_t S;
+    const float* feat;
+    int32_t R;
+    const float *w1, *b1;
+    const uint8_t* w2_img;
+    const TcYGroup* yg;
+    int32_t nyg, NT, KS;
+    const float* cg;
+    float* dpre;       // [E, H] in the caller's edge order: dL/d(pre-activation of fc's hidden layer)
+    int64_t ntiles;
+};
+
+constexpr int oDhA = 0;                       // dT tile: 4 slabs
+constexpr int oDhB = 65536;                   // W2 ring
+constexpr int oDhF = oDhB + kNB * kStage;     // factor scratch
+constexpr int oDhW = oDhF + kFBytes;          // w1 [H][R] | b1 [H]
+constexpr int oDhBar = oDhW + (256 * 16 + 256) * 4;
+// barriers: 0..3 B_full, 4..7 B_empty, 8..9 A_full[half], 10..11 A_empty[half], 12 D_full, 13 D_empty
+constexpr int kTcDhSmem = oDhBar + 14 * 8 + 16 + 1024;
+constexpr int kGenThreads = 320;  // warps 0-7 generate, 8 bulk-copy producer, 9 MMA issuer
+
+struct DhCtx {
+    const TcDhArgs* a;
+    uint8_t* sm;
+    uint64_t* bars;
+    int e, g;
+    bool valid;
+    int64_t eid;
+    int gnode, rowid;
+    uint32_t gi;
+};
+
+template <int DA, int DB>
+__device__ __forceinline__ void dh_ygroup(DhCtx& c, const TcYGroup& G) {
+    constexpr bool XM = DA < DB;
+    constexpr int M = XM ? DA : DB;
+    constexpr int WS = (!XM && DB == 1) ? 32 : 8;
+    constexpr int MC = 256 / WS, HA = MC / 2;
+    constexpr int W = (M + 1) / 2;
+    const TcDhArgs& a = *c.a;
+    uint32_t* F = reinterpret_cast<uint32_t*>(c.sm + oDhF) + c.g * 128 + c.e;
+    uint8_t* A = c.sm + oDhA;
+    float Z[DA][DB];
+    tc_compute_z<DA, DB>(a.sh + c.eid * a.S + G.sh_off, a.cg + G.cg_off, G.DS, c.valid, Z);
+    tc_build_factor<DA, DB>(F, a.x + (int64_t)c.gnode * a.x_len + G.v_off, a.x_len, G, c.g, c.valid, Z);
+    for (int sl = 0; sl < G.nslices; ++sl) {
+        float r[WS * M];
+        tc_load_gside<DA, DB, WS>(a.g + (int64_t)c.rowid * a.g_len + G.r_off + sl * WS * DB, min(WS, G.MB - sl * WS), c.valid, Z, r);
+        for (int q = 0; q < G.nsub; ++q) {
+            mbar_wait(&c.bars[10 + c.g], (c.gi & 1u) ^ 1u);  // the MMAs that read this half of the previous dT tile are done
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if constexpr (WS == 32) {
+                    float y[1];
+                    tc_load_factor<1>(F + (q * HA + j) * 256, y);
+                    tc_dt_store<1, 32>(A, c.e, c.g * 128 + j * 32, r, y);
+                } else {
+#pragma unroll
+                    for (int aa = 0; aa < 4; ++aa) {
+                        float y[M];
+                        tc_load_factor<M>(F + ((q * HA + 4 * j + aa) * W) * 256, y);
+                        tc_dt_store<M, 8>(A, c.e, c.g * 128 + (4 * j + aa) * 8, r, y);
+                    }
+                }
+            }
+            fence_proxy_async();
+            mbar_arrive(&c.bars[8 + c.g]);
+            ++c.gi;
+        }
+    }
+}
+
+#define GMP_TC_DISPATCH(FN, ...)                                  \
+    switch (G.DA * 8 + G.DB) {                                    \
+        case 1 * 8 + 1: FN<1, 1>(__VA_ARGS__); break;             \
+        case 3 * 8 + 1: FN<3, 1>(__VA_ARGS__); break;             \
+        case 5 * 8 + 1: FN<5, 1>(__VA_ARGS__); break;             \
+        case 3 * 8 + 3: FN<3, 3>(__VA_ARGS__); break;             \
+        case 5 * 8 + 3: FN<5, 3>(__VA_ARGS__); break;             \
+        case 5 * 8 + 5: FN<5, 5>(__VA_ARGS__); break;             \
+        case 1 * 8 + 3: FN<1, 3>(__VA_ARGS__); break;             \
+        case 1 * 8 + 5: FN<1, 5>(__VA_ARGS__); break;             \
+        default: FN<3, 5>(__VA_ARGS__); break;                    \
+    }
+
+// last CSR row whose first edge is <= k
+__device__ __forceinline__ int row_of_edge(const int32_t* __restrict__ rowptr, int n, int64_t k) {
+    int lo = 0, hi = n;
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if ((int64_t)__ldg(rowptr + mid) <= k) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+__global__ void __launch_bounds__(kGenThreads, 1) tp_dhid_tc_kernel(TcDhArgs a) {
+    extern __shared__ __align__(16) uint8_t smraw[];
+    uint8_t* sm = smraw + ((1024u - (smem_u32(smraw) & 1023u)) & 1023u);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sm + oDhBar);
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(sm + oDhBar + 14 * 8);
+    float* w1s = reinterpret_cast<float*>(sm + oDhW);
+    const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+    const int KS = a.KS, NST = 2 * KS, H = 64 * KS, R = a.R;
+    float* b1s = w1s + H * R;
+    for (int x = t; x < H * R; x += kGenThreads) w1s[x] = __ldg(a.w1 + x);
+    for (int x = t; x < H; x += kGenThreads) b1s[x] = __ldg(a.b1 + x);
+    if (t == 0) {
+        for (int s = 0; s < kNB; ++s) { mbar_init(&bars[s], 1); mbar_init(&bars[4 + s], 1); }
+        mbar_init(&bars[8], 128); mbar_init(&bars[9], 128);
+        mbar_init(&bars[10], 1); mbar_init(&bars[11], 1);
+        mbar_init(&bars[12], 1); mbar_init(&bars[13], kEpiThreads);
+        fence_mbar_init();
+    }
+    if (warp == 9) tmem_alloc<256>(tmem_ptr);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tm = *tmem_ptr;
+    const int64_t t0 = (a.ntiles * blockIdx.x) / gridDim.x, t1 = (a.ntiles * (blockIdx.x + 1)) / gridDim.x;
+
+    if (warp < 8) {
+        DhCtx c;
+        c.a = &a; c.sm = sm; c.bars = bars;
+        c.e = (warp & 3) * 32 + lane;
+        c.g = warp >> 2;
+        c.gi = 0;
+        const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+        uint32_t ti = 0;
+        for (int64_t tile = t0; tile < t1; ++tile, ++ti) {
+            const int64_t k = tile * kET + c.e;
+            c.valid = k < a.E;
+            c.eid = 0; c.gnode = 0; c.rowid = 0;
+            if (c.valid) {
+                c.eid = a.perm ? __ldg(a.perm + k) : k;
+                c.gnode = __ldg(a.col + k);
+                c.rowid = row_of_edge(a.rowptr, (int)a.n, k);
+            }
+            for (int y = 0; y < a.nyg; ++y) {
+                const TcYGroup G = a.yg[y];
+                GMP_TC_DISPATCH(dh_ygroup, c, G)
+            }
+            // ---- dhid of the tile: relu mask (pre-activation recomputed in fp32), store in the caller's edge order
+            mbar_wait(&bars[12], ti & 1u);
+            tc_fence_after();
+            float f[16];
+#pragma unroll
+            for (int q = 0; q < 16; ++q) f[q] = (c.valid && q < R) ? __ldg(a.feat + c.eid * R + q) : 0.f;
+            const int hh = H / 2;
+            for (int cc = 0; cc < hh; cc += 32) {
+                float v[32];
+                const int h0 = c.g * hh + cc;
+                tmem_ld32(tm + lane_base + h0, v);
+                if (c.valid) {
+                    float* dst = a.dpre + c.eid * H + h0;
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        float o[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const int h = h0 + j + u;
+                            float pre = b1s[h];
+#pragma unroll
+                            for (int q = 0; q < 16; ++q)
+                                if (q < R) pre = fmaf(w1s[h * R + q], f[q], pre);
+                            o[u] = pre > 0.f ? v[j + u] : 0.f;
+                        }
+                        *reinterpret_cast<float4*>(dst + j) = make_float4(o[0], o[1], o[2], o[3]);
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(&bars[13]);
+        }
+    } else if (warp == 8) {
+        if (lane == 0) {
+            uint32_t si = 0;
+            for (int64_t tile = t0; tile < t1; ++tile) {
+                const int nstage = a.NT * NST;
+                for (int s = 0; s < nstage; ++s, ++si) {
+                    const uint32_t slot = si % kNB, ph = (si / kNB) & 1u;
+                    mbar_wait(&bars[4 + slot], ph ^ 1u);
+                    mbar_expect_tx(&bars[slot], kStage);
+                    bulk_g2s(sm + oDhB + slot * kStage, a.w2_img + (int64_t)s * kStage, kStage, &bars[slot]);
+                }
+            }
+        }
+    } else {
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc_bf16(128, 64, false, true);
+            uint32_t si = 0, ti = 0, gi = 0;
+            for (int64_t tile = t0; tile < t1; ++tile, ++ti) {
+                mbar_wait(&bars[13], (ti & 1u) ^ 1u);  // the previous tile's dhid has been read out of tensor memory
+                tc_fence_after();
+                for (int nt = 0; nt < a.NT; ++nt, ++gi) {
+                    for (int s = 0; s < NST; ++s, ++si) {
+                        const uint32_t slot = si % kNB, ph = (si / kNB) & 1u;
+                        const int half = s / KS, ks = s - half * KS;
+                        if (ks == 0) {
+                            mbar_wait(&bars[8 + half], gi & 1u);
+                            tc_fence_after();
+                        }
+                        mbar_wait(&bars[slot], ph);
+                        tc_fence_after();
+                        const uint32_t bb = smem_u32(sm + oDhB + slot * kStage);
+#pragma unroll
+                        for (int k16 = 0; k16 < 8; ++k16) {
+                            const uint32_t ab = smem_u32(sm + oDhA + (2 * half + (k16 >> 2)) * kStage) + (k16 & 3) * 32;
+                            umma_bf16(tm + ks * 64, umma_desc_k128(ab), umma_desc_mn128(bb + k16 * 2048, kStage), idesc,
+                                      (nt | half | k16) ? 1u : 0u);
+                        }
+                        umma_commit(&bars[4 + slot]);
+                        if (ks == KS - 1) umma_commit(&bars[10 + half]);
+                    }
+                }
+                umma_commit(&bars[12]);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 9) tmem_dealloc<256>(tm);
+}
+
+// one N-tile of W2 rows with everything the generator needs
+struct TcWTile {
+    int32_t w_off, stride_a, stride_b, a_begin, a_end, b0, b_end, WS;
+    int32_t v_off, DA, DB, DS, sh_off, cg_off, r_off, pad;
+};
+
+struct TcDwArgs {
+    const int32_t *rowptr, *col, *perm;
+    int64_t n, E;
+    const float* x;
+    int32_t x_len;
+    const float* g;
+    int32_t g_len;
+    const float* sh;
+    int32_t S;
+    const uint8_t* hid_img;
+    const TcWTile* wt;
+    int32_t KS;
+    const float* cg;
+    float* dW2;
+    int64_t ntiles;
+};
+
+constexpr int oDwH = 0;                // hid tiles, 2 x 64 KB
+constexpr int oDwA = 131072;           // dT tile
+constexpr int oDwBar = oDwA + 65536;   // 0,1 hid_full | 2,3 hid_empty | 4,5 A_full[half] | 6,7 A_empty[half] | 8 D_full
+constexpr int kTcDwSmem = oDwBar + 9 * 8 + 16 + 1024;
+
+template <int DA, int DB>
+__device__ __forceinline__ void dw_generate(const TcDwArgs& a, const TcWTile& T, uint8_t* sm, uint64_t* bars, int e, int g) {
+    constexpr bool XM = DA < DB;
+    constexpr int M = XM ? DA : DB;
+    constexpr int WS = (!XM && DB == 1) ? 32 : 8;
+    constexpr int MC = 256 / WS, HA = MC / 2;
+    uint8_t* A = sm + oDwA;
+    const bool vec_ok = ((a.x_len | T.v_off) & 3) == 0;
+    const int AR = T.a_end - T.a_begin, nb = min(WS, T.b_end - T.b0);
+    uint32_t ti = 0;
+    for (int64_t tile = 0; tile < a.ntiles; ++tile, ++ti) {
+        const int64_t k = tile * kET + e;
+        const bool valid = k < a.E;
+        int64_t eid = 0;
+        int gnode = 0, rowid = 0;
+        if (valid) {
+            eid = a.perm ? __ldg(a.perm + k) : k;
+            gnode = __ldg(a.col + k);
+            rowid = row_of_edge(a.rowptr, (int)a.n, k);
+        }
+        float Z[DA][DB];
+        tc_compute_z<DA, DB>(a.sh + eid * a.S + T.sh_off, a.cg + T.cg_off, T.DS, valid, Z);
+        float r[WS * M];
+        tc_load_gside<DA, DB, WS>(a.g + (int64_t)rowid * a.g_len + T.r_off + T.b0 * DB, nb, valid, Z, r);
+        const float* xrow = a.x + (int64_t)gnode * a.x_len + T.v_off;
+        mbar_wait(&bars[6 + g], (ti & 1u) ^ 1u);
+#pragma unroll
+        for (int a4 = 0; a4 < HA; a4 += 4) {
+            float xs[4 * DA];
+            tc_load_x4<DA>(xrow, T.a_begin, AR, g * HA + a4, valid, vec_ok, xs);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float y[M];
+                tc_factor<DA, DB>(xs + j * DA, Z, y);
+                tc_dt_store<M, WS>(A, e, g * 128 + (a4 + j) * WS, r, y);
+            }
+        }
+        fence_proxy_async();
+        mbar_arrive(&bars[4 + g]);
+    }
+}
+
+__global__ void __launch_bounds__(kGenThreads, 1) tp_dw2_tc_kernel(TcDwArgs a) {
+    extern __shared__ __align__(16) uint8_t smraw[];
+    uint8_t* sm = smraw + ((1024u - (smem_u32(smraw) & 1023u)) & 1023u);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sm + oDwBar);
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(sm + oDwBar + 9 * 8);
+    const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+    const int KS = a.KS, H = 64 * KS;
+    const TcWTile T = a.wt[blockIdx.x];
+    if (t == 0) {
+        mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_init(&bars[2], 1); mbar_init(&bars[3], 1);
+        mbar_init(&bars[4], 128); mbar_init(&bars[5], 128); mbar_init(&bars[6], 1); mbar_init(&bars[7], 1);
+        mbar_init(&bars[8], 1);
+        fence_mbar_init();
+    }
+    if (warp == 9) tmem_alloc<512>(tmem_ptr);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tm = *tmem_ptr;
+
+    if (warp < 8) {
+        const int e = (warp & 3) * 32 + lane, g = warp >> 2;
+        {
+            const TcWTile& G = T;
+            GMP_TC_DISPATCH(dw_generate, a, T, sm, bars, e, g)
+        }
+        // ---- D half g, lane = column c of the N-tile = one row of W2
+        mbar_wait(&bars[8], 0);
+        tc_fence_after();
+        const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+        const int c = g * 128 + e;
+        const int al = c / T.WS, b = c - al * T.WS;
+        const int aa = T.a_begin + al, bb = T.b0 + b;
+        const bool live = aa < T.a_end && bb < T.b_end;
+        float* dst = a.dW2 + ((int64_t)T.w_off + (int64_t)aa * T.stride_a + (int64_t)bb * T.stride_b) * H;
+        for (int cc = 0; cc < H; cc += 32) {
+            float v[32];
+            tmem_ld32(tm + lane_base + g * H + cc, v);
+            if (live) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dst + cc + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            }
+        }
+    } else if (warp == 8) {
+        if (lane == 0) {
+            uint32_t ti = 0;
+            for (int64_t tile = 0; tile < a.ntiles; ++tile, ++ti) {
+                const uint32_t buf = ti & 1u;
+                mbar_wait(&bars[2 + buf], ((ti >> 1) & 1u) ^ 1u);
+                mbar_expect_tx(&bars[buf], (uint32_t)(KS * kStage));
+                for (int ks = 0; ks < KS; ++ks)
+                    bulk_g2s(sm + oDwH + buf * 65536 + ks * kStage, a.hid_img + (tile * KS + ks) * (int64_t)kStage, kStage, &bars[buf]);
+            }
+        }
+    } else {
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc_bf16(128, H, true, true);
+            uint32_t ti = 0;
+            for (int64_t tile = 0; tile < a.ntiles; ++tile, ++ti) {
+                const uint32_t buf = ti & 1u;
+                mbar_wait(&bars[buf], (ti >> 1) & 1u);
+                tc_fence_after();
+                const uint32_t hb = smem_u32(sm + oDwH + buf * 65536);
+                for (int half = 0; half < 2; ++half) {
+                    mbar_wait(&bars[4 + half], ti & 1u);
+                    tc_fence_after();
+                    const uint32_t ab = smem_u32(sm + oDwA + 2 * half * kStage);
+#pragma unroll
+                    for (int k16 = 0; k16 < 8; ++k16)
+                        umma_bf16(tm + half * H, umma_desc_mn128(ab + k16 * 2048, kStage), umma_desc_mn128(hb + k16 * 2048, kStage), idesc,
+                                  (ti | k16) ? 1u : 0u);
+                    umma_commit(&bars[6 + half]);
+                }
+                umma_commit(&bars[2 + buf]);
+            }
+            umma_commit(&bars[8]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 9) tmem_dealloc<512>(tm);
+}
+
 // rows that straddle a chunk boundary: add the later chunks' head partials in chunk order
 __global__ void tp_tc_fixup_kernel(const int32_t* __restrict__ rowptr, int64_t n, int64_t E, int64_t ntiles, int nchunks,
                                    const float* __restrict__ head, float* __restrict__ res, int r_len) {
@@ -656,6 +1126,46 @@ int gmp_tp_tc_contract(const int32_t* rowptr, const int32_t* col, const int32_t*
         rc = check_launch("tp_tc_fixup_kernel");
     }
     return rc;
+}
+
+int gmp_tp_tc_dhid(const int32_t* rowptr, const int32_t* col, const int32_t* perm, int64_t n, int64_t num_edges, const float* x,
+                   int32_t x_len, const float* g, int32_t g_len, const float* edge_sh, int32_t S, const float* edge_feat, int32_t R,
+                   const float* w1, const float* b1, const void* w2_img, const void* ygroups, int32_t nyg, int32_t ntiles_n, int32_t H,
+                   const float* cg, float* dpre, gmp_stream_t stream) {
+    GMP_REQUIRE(rowptr && ygroups && cg && w1 && b1 && dpre, "tp_tc_dhid: NULL pointer");
+    GMP_REQUIRE(num_edges == 0 || (col && x && g && edge_sh && edge_feat && w2_img), "tp_tc_dhid: NULL edge/feature pointer");
+    GMP_REQUIRE(H >= 64 && H <= 256 && H % 64 == 0, "tp_tc_dhid: mlp_dim must be 64, 128, 192 or 256 (got %d)", H);
+    GMP_REQUIRE(R >= 1 && R <= 16, "tp_tc_dhid: edge_feats_dim in [1, 16] (got %d)", R);
+    if (n == 0 || num_edges == 0) return GMP_OK;
+    if (nyg == 0 || ntiles_n == 0) {
+        GMP_CUDA(cudaMemsetAsync(dpre, 0, (size_t)num_edges * H * sizeof(float), stream));
+        return GMP_OK;
+    }
+    TcDhArgs a;
+    a.rowptr = rowptr; a.col = col; a.perm = perm; a.n = n; a.E = num_edges; a.x = x; a.x_len = x_len; a.g = g; a.g_len = g_len;
+    a.sh = edge_sh; a.S = S; a.feat = edge_feat; a.R = R; a.w1 = w1; a.b1 = b1; a.w2_img = (const uint8_t*)w2_img;
+    a.yg = (const TcYGroup*)ygroups; a.nyg = nyg; a.NT = ntiles_n; a.KS = H / 64; a.cg = cg; a.dpre = dpre;
+    a.ntiles = ceil_div(num_edges, kET);
+    const int grid = gmp_tp_tc_num_chunks(num_edges);
+    GMP_CUDA(cudaFuncSetAttribute(tp_dhid_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcDhSmem));
+    tp_dhid_tc_kernel<<<grid, kGenThreads, kTcDhSmem, stream>>>(a);
+    return check_launch("tp_dhid_tc_kernel");
+}
+
+int gmp_tp_tc_dw2(const int32_t* rowptr, const int32_t* col, const int32_t* perm, int64_t n, int64_t num_edges, const float* x,
+                  int32_t x_len, const float* g, int32_t g_len, const float* edge_sh, int32_t S, const void* hid_img,
+                  const void* wtile_table, int32_t ntiles_n, int32_t H, const float* cg, float* dW2, gmp_stream_t stream) {
+    GMP_REQUIRE(rowptr && wtile_table && cg && dW2, "tp_tc_dw2: NULL pointer");
+    GMP_REQUIRE(num_edges == 0 || (col && x && g && edge_sh && hid_img), "tp_tc_dw2: NULL edge/feature pointer");
+    GMP_REQUIRE(H >= 64 && H <= 256 && H % 64 == 0, "tp_tc_dw2: mlp_dim must be 64, 128, 192 or 256 (got %d)", H);
+    if (ntiles_n == 0) return GMP_OK;
+    TcDwArgs a;
+    a.rowptr = rowptr; a.col = col; a.perm = perm; a.n = n; a.E = num_edges; a.x = x; a.x_len = x_len; a.g = g; a.g_len = g_len;
+    a.sh = edge_sh; a.S = S; a.hid_img = (const uint8_t*)hid_img; a.wt = (const TcWTile*)wtile_table; a.KS = H / 64; a.cg = cg;
+    a.dW2 = dW2; a.ntiles = ceil_div(num_edges, kET);
+    GMP_CUDA(cudaFuncSetAttribute(tp_dw2_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcDwSmem));
+    tp_dw2_tc_kernel<<<ntiles_n, kGenThreads, kTcDwSmem, stream>>>(a);
+    return check_launch("tp_dw2_tc_kernel");
 }
 
 }  // extern "C"

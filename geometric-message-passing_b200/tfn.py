@@ -278,7 +278,7 @@ class TensorProductPlan:
     def _tc_tables(roles):
         """y-groups (path x range of the summed index), N-tiles (256 generated weights each, in the order the
         kernel consumes them), and the per-path tables of the bias term (struct layouts: csrc/tpconv_tc.cu)."""
-        ygroups, ntiles, ypaths, zent, bias = [], [], [], [], []
+        ygroups, ntiles, wtiles, ypaths, zent, bias = [], [], [], [], [], []
         y_off = z_off = 0
         for r in roles:
             DA, DB, MA, MB = r["DA"], r["DB"], r["MA"], r["MB"]
@@ -294,6 +294,7 @@ class TensorProductPlan:
                 for sl in range(nslices):
                     for q in range(nsub):
                         ntiles.append([r["w_off"], r["stride_a"], r["stride_b"], A0 + q * MC, A0 + ARv, sl * WS, MB, WS])
+                        wtiles.append(ntiles[-1] + [r["v_off"], DA, DB, r["DS"], r["sh_off"], r["cg_off"], r["r_off"], 0])
             ypaths.append([r["v_off"], DA, DB, MA, y_off, z_off, 0, 0])
             for i in range(DA):
                 for k in range(DB):
@@ -303,7 +304,7 @@ class TensorProductPlan:
             y_off += MA * DB
             z_off += DA * DB
         i32 = lambda a, w: np.asarray(a, dtype=np.int32).reshape(-1, w)
-        return dict(ygroups=i32(ygroups, 12), ntiles=i32(ntiles, 8), ypaths=i32(ypaths, 8), zent=i32(zent, 4), bias=bias,
+        return dict(ygroups=i32(ygroups, 12), ntiles=i32(ntiles, 8), wtiles=i32(wtiles, 16), ypaths=i32(ypaths, 8), zent=i32(zent, 4), bias=bias,
                     y_len=y_off, npairs=sum(r["MA"] for r in roles))
 
     def device(self, dev):
@@ -314,30 +315,38 @@ class TensorProductPlan:
                      fwd_passes=t(self.fwd["passes"]), fwd_blocks=t(self.fwd["blocks"]),
                      bwd_passes=t(self.bwd["passes"]), bwd_blocks=t(self.bwd["blocks"]))
             for name, tab in (("tc_fwd", self.tc_fwd), ("tc_bwd", self.tc_bwd)):
-                for k in ("ygroups", "ntiles", "ypaths", "zent"):
+                for k in ("ygroups", "ntiles", "wtiles", "ypaths", "zent"):
                     d[f"{name}_{k}"] = t(tab[k])
             self._dev[key] = d
         return self._dev[key]
 
 
-def _tc_contract(csr, n, E, V, r_len, edge_sh, edge_feat, w1, b1, w2, b2, plan: "TensorProductPlan", which: str, d):
+def _tc_images(csr, E, edge_feat, w1, b1, w2, tab, which, d):
+    """bf16 UMMA operand images: the hidden layer of fc per 128-edge tile of `csr`'s order, and w2 per N-tile."""
+    L = _lib.lib()
+    H, R = w1.shape[0], w1.shape[1]
+    if H % 64 != 0 or H > 256:
+        raise NotImplementedError("precision='bf16': mlp_dim must be 64, 128, 192 or 256")
+    NT = tab["ntiles"].shape[0]
+    hid_img = torch.empty(max(int(L.gmp_tp_tc_hid_bytes(E, H)), 16), dtype=torch.uint8, device=w1.device)
+    w2_img = torch.empty(max(int(L.gmp_tp_tc_w2_bytes(NT, H)), 16), dtype=torch.uint8, device=w1.device)
+    call("gmp_tp_tc_pack_hid", csr.perm_ptr, E, ptr(edge_feat), R, ptr(w1), ptr(b1), H, ptr(hid_img))
+    call("gmp_tp_tc_pack_w2", ptr(w2), H, ptr(d[which + "_ntiles"]), NT, ptr(w2_img))
+    return hid_img, w2_img
+
+
+def _tc_contract(csr, n, E, V, r_len, edge_sh, edge_feat, w1, b1, w2, b2, plan: "TensorProductPlan", which: str, d, images=None):
     """res[n] = sum_{e in CSR row n} sum_a (T_e[a,b] + b2[a,b]) Y_e[a,k] on the tensor cores (bf16 operands, fp32
     accumulation): gmp_tp_tc_contract for the T part, gmp_tp_ysum + node-level GEMMs (cuBLAS) for the bias part."""
     tab = plan.tc_fwd if which == "tc_fwd" else plan.tc_bwd
     L = _lib.lib()
-    H, R, S = w1.shape[0], w1.shape[1], edge_sh.shape[1]
-    if H % 64 != 0 or H > 256:
-        raise NotImplementedError("precision='bf16': mlp_dim must be 64, 128, 192 or 256")
-    dev = V.device
-    res = torch.empty(n, r_len, dtype=torch.float32, device=dev)
-    NT = tab["ntiles"].shape[0]
-    hid_img = torch.empty(max(int(L.gmp_tp_tc_hid_bytes(E, H)), 16), dtype=torch.uint8, device=dev)
-    w2_img = torch.empty(max(int(L.gmp_tp_tc_w2_bytes(NT, H)), 16), dtype=torch.uint8, device=dev)
-    head = torch.empty(int(L.gmp_tp_tc_num_chunks(E)), r_len, dtype=torch.float32, device=dev)
-    call("gmp_tp_tc_pack_hid", csr.perm_ptr, E, ptr(edge_feat), R, ptr(w1), ptr(b1), H, ptr(hid_img))
-    call("gmp_tp_tc_pack_w2", ptr(w2), H, ptr(d[which + "_ntiles"]), NT, ptr(w2_img))
+    H, S = w1.shape[0], edge_sh.shape[1]
+    hid_img, w2_img = images if images is not None else _tc_images(csr, E, edge_feat, w1, b1, w2, tab, which, d)
+    res = torch.empty(n, r_len, dtype=torch.float32, device=V.device)
+    head = torch.empty(int(L.gmp_tp_tc_num_chunks(E)), r_len, dtype=torch.float32, device=V.device)
     call("gmp_tp_tc_contract", ptr(csr.rowptr), ptr(csr.col), csr.perm_ptr, n, E, ptr(V), V.shape[1], ptr(res), r_len, ptr(head),
-         ptr(edge_sh), S, ptr(hid_img), ptr(w2_img), ptr(d[which + "_ygroups"]), tab["ygroups"].shape[0], NT, H, ptr(d["cg"]))
+         ptr(edge_sh), S, ptr(hid_img), ptr(w2_img), ptr(d[which + "_ygroups"]), tab["ygroups"].shape[0], tab["ntiles"].shape[0], H,
+         ptr(d["cg"]))
     ys = _tc_ysum(csr, n, E, V, edge_sh, tab, which, d)
     for bs in tab["bias"]:
         Bm = b2.as_strided((bs["MA"], bs["MB"]), (bs["stride_a"], bs["stride_b"]), b2.storage_offset() + bs["w_off"])
@@ -345,6 +354,33 @@ def _tc_contract(csr, n, E, V, r_len, edge_sh, edge_feat, w1, b1, w2, b2, plan: 
         blk = res[:, bs["r_off"]:bs["r_off"] + bs["MB"] * bs["DB"]].view(n, bs["MB"], bs["DB"])
         blk += torch.einsum("nak,ab->nbk", ysp, Bm)
     return res
+
+
+def _tc_wgrad(graph, x, g, edge_sh, edge_feat, w1, b1, w2, b2, plan: "TensorProductPlan", d):
+    """Parameter gradients of fc on the tensor cores: dW2 = dT^T hid (gmp_tp_tc_dw2), dhid = dT W2 (gmp_tp_tc_dhid,
+    masked by the ReLU and written as dL/d(pre-activation) per edge), db2 through the node-level aggregate YS,
+    dW1 / db1 as plain GEMM / column sum of the pre-activation gradient."""
+    tab, csr = plan.tc_fwd, graph.by_src
+    n, E, H, R, S = graph.n, graph.E, w1.shape[0], w1.shape[1], edge_sh.shape[1]
+    hid_img, w2_img = _tc_images(csr, E, edge_feat, w1, b1, w2, tab, "tc_fwd", d)
+    NT = tab["ntiles"].shape[0]
+    dpre = torch.zeros(E, H, dtype=torch.float32, device=x.device) if E == 0 else torch.empty(E, H, dtype=torch.float32, device=x.device)
+    call("gmp_tp_tc_dhid", ptr(csr.rowptr), ptr(csr.col), csr.perm_ptr, n, E, ptr(x), x.shape[1], ptr(g), g.shape[1], ptr(edge_sh), S,
+         ptr(edge_feat), R, ptr(w1), ptr(b1), ptr(w2_img), ptr(d["tc_fwd_ygroups"]), tab["ygroups"].shape[0], NT, H, ptr(d["cg"]),
+         ptr(dpre))
+    dW2 = torch.empty_like(w2) if E > 0 else torch.zeros_like(w2)
+    if E > 0:
+        call("gmp_tp_tc_dw2", ptr(csr.rowptr), ptr(csr.col), csr.perm_ptr, n, E, ptr(x), x.shape[1], ptr(g), g.shape[1], ptr(edge_sh), S,
+             ptr(hid_img), ptr(d["tc_fwd_wtiles"]), NT, H, ptr(d["cg"]), ptr(dW2))
+    ys = _tc_ysum(csr, n, E, x, edge_sh, tab, "tc_fwd", d)
+    db2 = torch.zeros_like(b2)
+    for bs in tab["bias"]:
+        ysp = ys[:, bs["y_off"]:bs["y_off"] + bs["MA"] * bs["DB"]].view(n, bs["MA"], bs["DB"])
+        gb = g[:, bs["r_off"]:bs["r_off"] + bs["MB"] * bs["DB"]].view(n, bs["MB"], bs["DB"])
+        db2.as_strided((bs["MA"], bs["MB"]), (bs["stride_a"], bs["stride_b"]), bs["w_off"]).copy_(torch.einsum("nak,nbk->ab", ysp, gb))
+    dW1 = dpre.t() @ edge_feat
+    db1 = dpre.sum(0)
+    return dW1, db1, dW2, db2
 
 
 def _tc_ysum(csr, n, E, V, edge_sh, tab, which, d):
@@ -396,6 +432,9 @@ class _TPConvFn(torch.autograd.Function):
                 call("gmp_tp_contract", ptr(t.rowptr), ptr(t.col), t.perm_ptr, graph.n, graph.E, ptr(g), g.shape[1], ptr(dx),
                      dx.shape[1], ptr(edge_sh), S, ptr(edge_feat), R, ptr(w1), ptr(b1), ptr(w2), ptr(b2), H, ptr(d["bwd_passes"]),
                      ptr(d["bwd_blocks"]), plan.bwd["nblocks"], plan.bwd["nunits"], ptr(d["cg"]), precision)
+        if precision == _lib.BF16_TC:
+            dW1, db1, dW2, db2 = _tc_wgrad(graph, x, g, edge_sh, edge_feat, w1, b1, w2, b2, plan, d)
+            return dx, None, None, dW1, db1, dW2, db2, None, None, None
         csr = graph.by_src
         nunits = plan.wunits.shape[0]
         plen = _lib.lib().gmp_tp_wgrad_part_len(H)

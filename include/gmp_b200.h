@@ -286,6 +286,21 @@ int gmp_tp_tc_contract(const int32_t* rowptr, const int32_t* col, const int32_t*
                        const float* V, int32_t v_len, float* res, int32_t r_len, float* head, const float* edge_sh,
                        int32_t S, const void* hid_img, const void* w2_img, const void* ygroups, int32_t nyg,
                        int32_t ntiles_n, int32_t H, const float* cg, gmp_stream_t stream);
+/* Parameter gradients of fc on the tensor cores (CSR rows = edge_index[0], col = edge_index[1]; x gathered at col,
+ * g = dL/d(TP output) read at the row node; tables of the forward orientation):
+ *   gmp_tp_tc_dhid : dpre[e, :] = relu'(pre_e) * sum_c dT_e[c] w2[c, :]   (caller's edge order; dW1 = dpre^T edge_feat,
+ *                    db1 = column sums follow as plain GEMM / reduction)
+ *   gmp_tp_tc_dw2  : dW2[c, :] = sum_e dT_e[c] hid_e[:]; `wtile_table` [ntiles_n] (16 int32, struct TcWTile), one CTA each
+ * dT_e[(a,b)] = sum_k g[row_e][b,k] Y_e[a,k] is generated per tile as a bf16 UMMA operand and never stored. */
+int gmp_tp_tc_dhid(const int32_t* rowptr, const int32_t* col, const int32_t* perm, int64_t n, int64_t num_edges,
+                   const float* x, int32_t x_len, const float* g, int32_t g_len, const float* edge_sh, int32_t S,
+                   const float* edge_feat, int32_t R, const float* w1, const float* b1, const void* w2_img,
+                   const void* ygroups, int32_t nyg, int32_t ntiles_n, int32_t H, const float* cg, float* dpre,
+                   gmp_stream_t stream);
+int gmp_tp_tc_dw2(const int32_t* rowptr, const int32_t* col, const int32_t* perm, int64_t n, int64_t num_edges,
+                  const float* x, int32_t x_len, const float* g, int32_t g_len, const float* edge_sh, int32_t S,
+                  const void* hid_img, const void* wtile_table, int32_t ntiles_n, int32_t H, const float* cg,
+                  float* dW2, gmp_stream_t stream);
 /* YS[n][y_off_p + a*DB_p + k] = sum_{e in CSR row n} sum_i V[col_e][v_off_p + a*DA_p + i] * Z^p_e[i][k], fp32:
  * the node-level aggregate in which both the bias term of the layer and db2 are linear.
  * `ypaths` [npaths] (8 int32, struct TcYPath), `zentries` [nz] (4 int32, struct TcZEntry); npairs = sum_p MA_p. */
