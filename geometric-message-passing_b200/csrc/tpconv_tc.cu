@@ -35,6 +35,7 @@ struct TcYGroup {
     int32_t v_off, DA, DB, DS;        // gathered block offset / irrep dims of the gathered, kept and sh sides
     int32_t sh_off, cg_off, A0, AR;   // sh block, CG table (Zc[iA][j][kB], coefficient folded in), a in [A0, A0+AR)
     int32_t r_off, MB, nslices, nsub; // result block offset, kept multiplicity, kept slices, N-tiles per slice
+    int32_t nt_begin, pad0, pad1, pad2;  // first N-tile of the group in the w2 image
 };
 // One N-tile = 256 generated weights per edge: column c = a_loc * WS + b  (WS = 32 when DB == 1 <= DA, else 8)
 struct TcNTile {
@@ -433,6 +434,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) tp_contract_tc_kernel(TcTpArgs 
     const uint32_t tm = *tmem_ptr;
 
     const int64_t t0 = (a.ntiles * blockIdx.x) / gridDim.x, t1 = (a.ntiles * (blockIdx.x + 1)) / gridDim.x;
+    // every CTA walks the y-groups cyclically from its own starting point, so that at any moment the CTAs stream
+    // different parts of the (L2-resident) w2 image instead of all hammering the same lines
+    const int y_start = (int)(((int64_t)a.nyg * blockIdx.x) / gridDim.x);
 
     if (warp < 8) {
         // ================= epilogue: thread = edge of the tile = TMEM lane =================
@@ -450,8 +454,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) tp_contract_tc_kernel(TcTpArgs 
                 c.eid = a.perm ? __ldg(a.perm + k) : k;
                 c.gnode = __ldg(a.col + k);
             }
-            for (int y = 0; y < a.nyg; ++y) {
-                const TcYGroup G = a.yg[y];
+            for (int yy = 0; yy < a.nyg; ++yy) {
+                const TcYGroup G = a.yg[(y_start + yy) % a.nyg];
                 switch (G.DA * 8 + G.DB) {
                     case 1 * 8 + 1: tc_ygroup<1, 1>(c, G); break;
                     case 3 * 8 + 1: tc_ygroup<3, 1>(c, G); break;
@@ -523,8 +527,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) tp_contract_tc_kernel(TcTpArgs 
             }
             const int nseg = seg_start[131];
             const bool head0 = (int64_t)__ldg(a.rowptr + seg_row[0]) < chunk_e0;
-            for (int y = 0; y < a.nyg; ++y) {
-                const TcYGroup G = a.yg[y];
+            for (int yy = 0; yy < a.nyg; ++yy) {
+                const TcYGroup G = a.yg[(y_start + yy) % a.nyg];
                 const int WS = (G.DA >= G.DB && G.DB == 1) ? 32 : 8;
                 for (int sl = 0; sl < G.nslices; ++sl) {
                     const int nb = min(WS, G.MB - sl * WS);
@@ -554,43 +558,50 @@ __global__ void __launch_bounds__(kTcThreads, 1) tp_contract_tc_kernel(TcTpArgs 
                 mbar_expect_tx(&bars[0], (uint32_t)(KS * kStage));
                 for (int ks = 0; ks < KS; ++ks)
                     bulk_g2s(sm + oA + ks * kStage, a.hid_img + (tile * KS + ks) * (int64_t)kStage, kStage, &bars[0]);
-                const int nstage = a.NT * NST;
-                for (int s = 0; s < nstage; ++s, ++si) {
-                    const uint32_t slot = si % kNB, ph = (si / kNB) & 1u;
-                    mbar_wait(&bars[6 + slot], ph ^ 1u);
-                    mbar_expect_tx(&bars[2 + slot], kStage);
-                    bulk_g2s(sm + oB + slot * kStage, a.w2_img + (int64_t)s * kStage, kStage, &bars[2 + slot]);
+                for (int yy = 0; yy < a.nyg; ++yy) {
+                    const TcYGroup G = a.yg[(y_start + yy) % a.nyg];
+                    const uint8_t* src = a.w2_img + (int64_t)G.nt_begin * NST * kStage;
+                    const int nstage = G.nslices * G.nsub * NST;
+                    for (int s = 0; s < nstage; ++s, ++si) {
+                        const uint32_t slot = si % kNB, ph = (si / kNB) & 1u;
+                        mbar_wait(&bars[6 + slot], ph ^ 1u);
+                        mbar_expect_tx(&bars[2 + slot], kStage);
+                        bulk_g2s(sm + oB + slot * kStage, src + (int64_t)s * kStage, kStage, &bars[2 + slot]);
+                    }
                 }
             }
         }
     } else {
-        // ================= MMA issuer =================
-        if (lane == 0) {
-            const uint32_t idesc = umma_idesc_bf16(128, 128);
-            uint32_t si = 0, ti = 0, gi = 0;
-            for (int64_t tile = t0; tile < t1; ++tile, ++ti) {
-                mbar_wait(&bars[0], ti & 1u);
-                tc_fence_after();
-                for (int nt = 0; nt < a.NT; ++nt, ++gi) {
-                    const uint32_t buf = gi & 1u;
-                    mbar_wait(&bars[14 + buf], ((gi >> 1) & 1u) ^ 1u);
-                    tc_fence_after();
-                    for (int s = 0; s < NST; ++s, ++si) {
+        // ================= MMA issuer: the whole warp runs the loop, one elected lane issues =================
+        const uint32_t idesc = umma_idesc_bf16(128, 128);
+        const uint64_t adesc0 = umma_desc_k128(smem_u32(sm + oA)), bdesc0 = umma_desc_k128(smem_u32(sm + oB));
+        uint32_t si = 0, ti = 0, gi = 0;
+        for (int64_t tile = t0; tile < t1; ++tile, ++ti) {
+            mbar_wait(&bars[0], ti & 1u);
+            for (int nt = 0; nt < a.NT; ++nt, ++gi) {
+                const uint32_t buf = gi & 1u;
+                mbar_wait(&bars[14 + buf], ((gi >> 1) & 1u) ^ 1u);
+                for (int half = 0; half < 2; ++half) {
+                    const uint32_t d = tm + buf * 256 + half * 128;
+                    for (int ks = 0; ks < KS; ++ks, ++si) {
                         const uint32_t slot = si % kNB, ph = (si / kNB) & 1u;
-                        const int half = s / KS, ks = s - half * KS;
                         mbar_wait(&bars[2 + slot], ph);
                         tc_fence_after();
-                        const uint32_t d = tm + buf * 256 + half * 128;
-                        const uint32_t ab = smem_u32(sm + oA + ks * kStage), bb = smem_u32(sm + oB + slot * kStage);
-#pragma unroll
-                        for (int k16 = 0; k16 < 4; ++k16)
-                            umma_bf16(d, umma_desc_k128(ab + k16 * 32), umma_desc_k128(bb + k16 * 32), idesc, (ks | k16) ? 1u : 0u);
-                        umma_commit(&bars[6 + slot]);
-                        if (ks == KS - 1) umma_commit(&bars[10 + buf * 2 + half]);
+                        if (elect_one()) {
+                            const uint64_t ad = adesc0 + (uint64_t)(ks * (kStage >> 4)), bd = bdesc0 + (uint64_t)(slot * (kStage >> 4));
+                            umma_bf16(d, ad, bd, idesc, ks ? 1u : 0u);
+                            umma_bf16(d, ad + 2, bd + 2, idesc, 1u);
+                            umma_bf16(d, ad + 4, bd + 4, idesc, 1u);
+                            umma_bf16(d, ad + 6, bd + 6, idesc, 1u);
+                            umma_commit(&bars[6 + slot]);
+                            if (ks == KS - 1) umma_commit(&bars[10 + buf * 2 + half]);
+                        }
+                        __syncwarp();
                     }
                 }
-                umma_commit(&bars[1]);
             }
+            if (elect_one()) umma_commit(&bars[1]);
+            __syncwarp();
         }
     }
     tc_fence_before();
@@ -777,6 +788,7 @@ __global__ void __launch_bounds__(kGenThreads, 1) tp_dhid_tc_kernel(TcDhArgs a) 
     tc_fence_after();
     const uint32_t tm = *tmem_ptr;
     const int64_t t0 = (a.ntiles * blockIdx.x) / gridDim.x, t1 = (a.ntiles * (blockIdx.x + 1)) / gridDim.x;
+    const int y_start = (int)(((int64_t)a.nyg * blockIdx.x) / gridDim.x);  // see tp_contract_tc_kernel
 
     if (warp < 8) {
         DhCtx c;
@@ -795,8 +807,8 @@ __global__ void __launch_bounds__(kGenThreads, 1) tp_dhid_tc_kernel(TcDhArgs a) 
                 c.gnode = __ldg(a.col + k);
                 c.rowid = row_of_edge(a.rowptr, (int)a.n, k);
             }
-            for (int y = 0; y < a.nyg; ++y) {
-                const TcYGroup G = a.yg[y];
+            for (int yy = 0; yy < a.nyg; ++yy) {
+                const TcYGroup G = a.yg[(y_start + yy) % a.nyg];
                 GMP_TC_DISPATCH(dh_ygroup, c, G)
             }
             // ---- dhid of the tile: relu mask (pre-activation recomputed in fp32), store in the caller's edge order
@@ -835,45 +847,49 @@ __global__ void __launch_bounds__(kGenThreads, 1) tp_dhid_tc_kernel(TcDhArgs a) 
         if (lane == 0) {
             uint32_t si = 0;
             for (int64_t tile = t0; tile < t1; ++tile) {
-                const int nstage = a.NT * NST;
-                for (int s = 0; s < nstage; ++s, ++si) {
-                    const uint32_t slot = si % kNB, ph = (si / kNB) & 1u;
-                    mbar_wait(&bars[4 + slot], ph ^ 1u);
-                    mbar_expect_tx(&bars[slot], kStage);
-                    bulk_g2s(sm + oDhB + slot * kStage, a.w2_img + (int64_t)s * kStage, kStage, &bars[slot]);
+                for (int yy = 0; yy < a.nyg; ++yy) {
+                    const TcYGroup G = a.yg[(y_start + yy) % a.nyg];
+                    const uint8_t* src = a.w2_img + (int64_t)G.nt_begin * NST * kStage;
+                    const int nstage = G.nslices * G.nsub * NST;
+                    for (int s = 0; s < nstage; ++s, ++si) {
+                        const uint32_t slot = si % kNB, ph = (si / kNB) & 1u;
+                        mbar_wait(&bars[4 + slot], ph ^ 1u);
+                        mbar_expect_tx(&bars[slot], kStage);
+                        bulk_g2s(sm + oDhB + slot * kStage, src + (int64_t)s * kStage, kStage, &bars[slot]);
+                    }
                 }
             }
         }
     } else {
-        if (lane == 0) {
-            const uint32_t idesc = umma_idesc_bf16(128, 64, false, true);
-            uint32_t si = 0, ti = 0, gi = 0;
-            for (int64_t tile = t0; tile < t1; ++tile, ++ti) {
-                mbar_wait(&bars[13], (ti & 1u) ^ 1u);  // the previous tile's dhid has been read out of tensor memory
-                tc_fence_after();
-                for (int nt = 0; nt < a.NT; ++nt, ++gi) {
-                    for (int s = 0; s < NST; ++s, ++si) {
+        const uint32_t idesc = umma_idesc_bf16(128, 64, false, true);
+        const uint64_t adesc0 = umma_desc_k128(smem_u32(sm + oDhA)), bdesc0 = umma_desc_mn128(smem_u32(sm + oDhB), kStage);
+        uint32_t si = 0, ti = 0, gi = 0;
+        for (int64_t tile = t0; tile < t1; ++tile, ++ti) {
+            mbar_wait(&bars[13], (ti & 1u) ^ 1u);  // the previous tile's dhid has been read out of tensor memory
+            for (int nt = 0; nt < a.NT; ++nt, ++gi) {
+                for (int half = 0; half < 2; ++half) {
+                    mbar_wait(&bars[8 + half], gi & 1u);
+                    for (int ks = 0; ks < KS; ++ks, ++si) {
                         const uint32_t slot = si % kNB, ph = (si / kNB) & 1u;
-                        const int half = s / KS, ks = s - half * KS;
-                        if (ks == 0) {
-                            mbar_wait(&bars[8 + half], gi & 1u);
-                            tc_fence_after();
-                        }
                         mbar_wait(&bars[slot], ph);
                         tc_fence_after();
-                        const uint32_t bb = smem_u32(sm + oDhB + slot * kStage);
+                        if (elect_one()) {
+                            // A: dT slabs 2*half, 2*half+1 (K = 128 columns of this half); B: stage rows = K, 64 h columns
+                            const uint64_t ad = adesc0 + (uint64_t)(2 * half * (kStage >> 4)), bd = bdesc0 + (uint64_t)(slot * (kStage >> 4));
+                            const uint32_t d = tm + ks * 64;
 #pragma unroll
-                        for (int k16 = 0; k16 < 8; ++k16) {
-                            const uint32_t ab = smem_u32(sm + oDhA + (2 * half + (k16 >> 2)) * kStage) + (k16 & 3) * 32;
-                            umma_bf16(tm + ks * 64, umma_desc_k128(ab), umma_desc_mn128(bb + k16 * 2048, kStage), idesc,
-                                      (nt | half | k16) ? 1u : 0u);
+                            for (int k16 = 0; k16 < 8; ++k16)
+                                umma_bf16(d, ad + (uint64_t)((k16 >> 2) * (kStage >> 4) + (k16 & 3) * 2), bd + (uint64_t)(k16 * (2048 >> 4)), idesc,
+                                          (nt | half | k16) ? 1u : 0u);
+                            umma_commit(&bars[4 + slot]);
+                            if (ks == KS - 1) umma_commit(&bars[10 + half]);
                         }
-                        umma_commit(&bars[4 + slot]);
-                        if (ks == KS - 1) umma_commit(&bars[10 + half]);
+                        __syncwarp();
                     }
                 }
-                umma_commit(&bars[12]);
             }
+            if (elect_one()) umma_commit(&bars[12]);
+            __syncwarp();
         }
     }
     tc_fence_before();
@@ -919,7 +935,9 @@ __device__ __forceinline__ void dw_generate(const TcDwArgs& a, const TcWTile& T,
     const bool vec_ok = ((a.x_len | T.v_off) & 3) == 0;
     const int AR = T.a_end - T.a_begin, nb = min(WS, T.b_end - T.b0);
     uint32_t ti = 0;
-    for (int64_t tile = 0; tile < a.ntiles; ++tile, ++ti) {
+    const int64_t tile0 = (a.ntiles * blockIdx.x) / gridDim.x;  // every CTA starts elsewhere in the hid image (L2 spread)
+    for (int64_t tt = 0; tt < a.ntiles; ++tt, ++ti) {
+        const int64_t tile = (tile0 + tt) % a.ntiles;
         const int64_t k = tile * kET + e;
         const bool valid = k < a.E;
         int64_t eid = 0;
@@ -997,7 +1015,9 @@ __global__ void __launch_bounds__(kGenThreads, 1) tp_dw2_tc_kernel(TcDwArgs a) {
     } else if (warp == 8) {
         if (lane == 0) {
             uint32_t ti = 0;
-            for (int64_t tile = 0; tile < a.ntiles; ++tile, ++ti) {
+            const int64_t tile0 = (a.ntiles * blockIdx.x) / gridDim.x;
+            for (int64_t tt = 0; tt < a.ntiles; ++tt, ++ti) {
+                const int64_t tile = (tile0 + tt) % a.ntiles;
                 const uint32_t buf = ti & 1u;
                 mbar_wait(&bars[2 + buf], ((ti >> 1) & 1u) ^ 1u);
                 mbar_expect_tx(&bars[buf], (uint32_t)(KS * kStage));
@@ -1006,28 +1026,28 @@ __global__ void __launch_bounds__(kGenThreads, 1) tp_dw2_tc_kernel(TcDwArgs a) {
             }
         }
     } else {
-        if (lane == 0) {
-            const uint32_t idesc = umma_idesc_bf16(128, H, true, true);
-            uint32_t ti = 0;
-            for (int64_t tile = 0; tile < a.ntiles; ++tile, ++ti) {
-                const uint32_t buf = ti & 1u;
-                mbar_wait(&bars[buf], (ti >> 1) & 1u);
+        const uint32_t idesc = umma_idesc_bf16(128, H, true, true);
+        const uint64_t adesc0 = umma_desc_mn128(smem_u32(sm + oDwA), kStage), bdesc0 = umma_desc_mn128(smem_u32(sm + oDwH), kStage);
+        uint32_t ti = 0;
+        for (int64_t tile = 0; tile < a.ntiles; ++tile, ++ti) {
+            const uint32_t buf = ti & 1u;
+            mbar_wait(&bars[buf], (ti >> 1) & 1u);
+            for (int half = 0; half < 2; ++half) {
+                mbar_wait(&bars[4 + half], ti & 1u);
                 tc_fence_after();
-                const uint32_t hb = smem_u32(sm + oDwH + buf * 65536);
-                for (int half = 0; half < 2; ++half) {
-                    mbar_wait(&bars[4 + half], ti & 1u);
-                    tc_fence_after();
-                    const uint32_t ab = smem_u32(sm + oDwA + 2 * half * kStage);
+                if (elect_one()) {
+                    const uint64_t ad = adesc0 + (uint64_t)(2 * half * (kStage >> 4)), bd = bdesc0 + (uint64_t)(buf * (65536 >> 4));
 #pragma unroll
                     for (int k16 = 0; k16 < 8; ++k16)
-                        umma_bf16(tm + half * H, umma_desc_mn128(ab + k16 * 2048, kStage), umma_desc_mn128(hb + k16 * 2048, kStage), idesc,
-                                  (ti | k16) ? 1u : 0u);
+                        umma_bf16(tm + half * H, ad + (uint64_t)(k16 * (2048 >> 4)), bd + (uint64_t)(k16 * (2048 >> 4)), idesc, (ti | k16) ? 1u : 0u);
                     umma_commit(&bars[6 + half]);
+                    if (half == 1) umma_commit(&bars[2 + buf]);
                 }
-                umma_commit(&bars[2 + buf]);
+                __syncwarp();
             }
-            umma_commit(&bars[8]);
         }
+        if (elect_one()) umma_commit(&bars[8]);
+        __syncwarp();
     }
     tc_fence_before();
     __syncthreads();
@@ -1035,20 +1055,23 @@ __global__ void __launch_bounds__(kGenThreads, 1) tp_dw2_tc_kernel(TcDwArgs a) {
 }
 
 // rows that straddle a chunk boundary: add the later chunks' head partials in chunk order
-__global__ void tp_tc_fixup_kernel(const int32_t* __restrict__ rowptr, int64_t n, int64_t E, int64_t ntiles, int nchunks,
-                                   const float* __restrict__ head, float* __restrict__ res, int r_len) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= r_len) return;
-    for (int ch = 1; ch < nchunks; ++ch) {
+__global__ void __launch_bounds__(128) tp_tc_fixup_kernel(const int32_t* __restrict__ rowptr, int64_t n, int64_t E, int64_t ntiles, int nchunks,
+                                                          const float* __restrict__ head, float* __restrict__ res, int r_len) {
+    __shared__ int hrow[1024];  // row that chunk ch's head belongs to, or -1
+    for (int ch = threadIdx.x; ch < nchunks; ch += 128) {
         const int64_t e0 = ((ntiles * ch) / nchunks) * kET;
-        if (e0 >= E) break;
-        int lo = 0, hi = (int)n;
-        while (hi - lo > 1) {
-            const int mid = (lo + hi) >> 1;
-            if ((int64_t)__ldg(rowptr + mid) <= e0) lo = mid; else hi = mid;
+        int row = -1;
+        if (ch > 0 && e0 < E) {
+            const int lo = row_of_edge(rowptr, (int)n, e0);
+            if ((int64_t)__ldg(rowptr + lo) < e0) row = lo;
         }
-        if ((int64_t)__ldg(rowptr + lo) < e0) res[(int64_t)lo * r_len + c] += head[(int64_t)ch * r_len + c];
+        hrow[ch] = row;
     }
+    __syncthreads();
+    const int c = blockIdx.x * 128 + threadIdx.x;
+    if (c >= r_len) return;
+    for (int ch = 1; ch < nchunks; ++ch)
+        if (hrow[ch] >= 0) res[(int64_t)hrow[ch] * r_len + c] += head[(int64_t)ch * r_len + c];
 }
 
 }  // namespace gmp

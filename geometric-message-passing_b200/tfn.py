@@ -290,7 +290,8 @@ class TensorProductPlan:
             for A0 in range(0, MA, AR):
                 ARv = min(AR, MA - A0)
                 nsub, nslices = -(-ARv // MC), -(-MB // WS)
-                ygroups.append([r["v_off"], DA, DB, r["DS"], r["sh_off"], r["cg_off"], A0, ARv, r["r_off"], MB, nslices, nsub])
+                ygroups.append([r["v_off"], DA, DB, r["DS"], r["sh_off"], r["cg_off"], A0, ARv, r["r_off"], MB, nslices, nsub,
+                                len(ntiles), 0, 0, 0])
                 for sl in range(nslices):
                     for q in range(nsub):
                         ntiles.append([r["w_off"], r["stride_a"], r["stride_b"], A0 + q * MC, A0 + ARv, sl * WS, MB, WS])
@@ -304,7 +305,7 @@ class TensorProductPlan:
             y_off += MA * DB
             z_off += DA * DB
         i32 = lambda a, w: np.asarray(a, dtype=np.int32).reshape(-1, w)
-        return dict(ygroups=i32(ygroups, 12), ntiles=i32(ntiles, 8), wtiles=i32(wtiles, 16), ypaths=i32(ypaths, 8), zent=i32(zent, 4), bias=bias,
+        return dict(ygroups=i32(ygroups, 16), ntiles=i32(ntiles, 8), wtiles=i32(wtiles, 16), ypaths=i32(ypaths, 8), zent=i32(zent, 4), bias=bias,
                     y_len=y_off, npairs=sum(r["MA"] for r in roles))
 
     def device(self, dev):

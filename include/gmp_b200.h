@@ -271,7 +271,7 @@ int64_t gmp_tp_wgrad_part_len(int32_t H);
  * The operands are staged once per call as UMMA shared-memory images:
  *   hid_img : relu(w1 edge_feat + b1) of every 128-edge tile of the CSR order, bf16  (gmp_tp_tc_hid_bytes bytes)
  *   w2_img  : the rows of w2 of every 256-column "N-tile", bf16, in consumption order (gmp_tp_tc_w2_bytes bytes)
- * `ntile_table` [ntiles_n] (8 int32, struct TcNTile) and `ygroups` [nyg] (12 int32, struct TcYGroup) are device
+ * `ntile_table` [ntiles_n] (8 int32, struct TcNTile) and `ygroups` [nyg] (16 int32, struct TcYGroup) are device
  * tables built by the host from the e3nn instruction list (gmp_b200/tfn.py).  `res` [n, r_len] is overwritten;
  * `head` [gmp_tp_tc_num_chunks(E), r_len] is scratch.  fc's second bias is NOT applied here: it contributes
  * sum_a b2[a,b] YS[n][a,k] with YS from gmp_tp_ysum (fp32), a node-level GEMM the caller adds. */

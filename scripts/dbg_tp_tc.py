@@ -51,7 +51,18 @@ def run(C, graphs, nodes, mlp=256, gate=True, time_it=False, bwd=True):
 
 if __name__ == "__main__":
     mode = sys.argv[1] if len(sys.argv) > 1 else "check"
-    if mode == "check":
+    if mode == "prof":
+        C = int(sys.argv[2]) if len(sys.argv) > 2 else 64
+        d = random_clouds(256 if C == 64 else 128, 64, 4.0, 2.0, 700 + C)
+        ei, pos = d["edge_index"].cuda(), d["pos"].cuda()
+        hid = f"{C}x0e+{C}x1o+{C}x2e"
+        m = gmp_b200.TensorProductConvLayer(hid, hid, "1x0e+1x1o+1x2e", 8, 256, gate=C == 64, precision="bf16").cuda()
+        esh, eft = gmp_b200.edge_geometry(pos, ei, 2, gmp_b200.RadialEmbeddingBlock(2.0, 8, 5))
+        x = torch.randn(pos.shape[0], 9 * C, device="cuda", requires_grad=True)
+        for _ in range(2):
+            m(x, ei, esh, eft).square().sum().backward()
+        torch.cuda.synchronize()
+    elif mode == "check":
         run(16, 3, 12, mlp=64, gate=False)
         run(64, 6, 24)
         run(128, 40, 16, gate=False)

@@ -86,7 +86,7 @@ def _emulate_tc_contract(tab, cg, rowidx, colidx, V, sh, T, b2, n, r_len):
     res = np.zeros((n, r_len))
     E = len(rowidx)
     nt_iter = iter(tab["ntiles"])
-    for (v_off, DA, DB, DS, sh_off, cg_off, A0, AR, r_off, MB, nslices, nsub) in tab["ygroups"]:
+    for (v_off, DA, DB, DS, sh_off, cg_off, A0, AR, r_off, MB, nslices, nsub, nt_begin, _, _, _) in tab["ygroups"]:
         Zc = cg[cg_off:cg_off + DA * DS * DB].reshape(DA, DS, DB)
         Z = np.einsum("ej,ijk->eik", sh[:, sh_off:sh_off + DS], Zc)
         WS = 32 if (DA >= DB and DB == 1) else 8
