@@ -29,6 +29,7 @@ constexpr int kFBytes = 49152;  // factor scratch
 constexpr int kOLd = 41;        // fp32 row stride of the per-edge result tile (odd: conflict-free)
 constexpr int kTcThreads = 384;  // 12 warps = 3 per scheduler: 16384 / 96 = 170 registers per thread
 constexpr int kEpiThreads = 256, kWalkThreads = 64;
+constexpr int kWalkBatch = 6;   // (segment, column) pairs a walker thread keeps in flight
 
 // One (path, range of the summed index) group: the factor built for it serves nslices * nsub N-tiles.
 struct TcYGroup {
@@ -479,6 +480,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tp_contract_tc_kernel(TcTpArgs 
         const float* O0 = reinterpret_cast<const float*>(sm + oO);
         const float* O1 = O0 + kET * kOLd;
         const int64_t chunk_e0 = t0 * kET;
+        if (t0 < t1) bar_arrive_named(2, kEpiThreads + kWalkThreads);  // O starts free
         for (int64_t tile = t0; tile < t1; ++tile) {
             {   // row of every edge of the tile (padding slots repeat the last edge's row), then the segment table;
                 // thread wt looks after edges wt and wt + 64: block blk = pass * 2 + (warp - 8) covers 32 consecutive edges
@@ -534,16 +536,41 @@ __global__ void __launch_bounds__(kTcThreads, 1) tp_contract_tc_kernel(TcTpArgs 
                     const int nb = min(WS, G.MB - sl * WS);
                     const int nv = nb * G.DB;
                     const int cbase = G.r_off + sl * WS * G.DB;
-                    bar_arrive_named(2, kEpiThreads + kWalkThreads);  // O free
-                    bar_sync_named(1, kEpiThreads + kWalkThreads);    // O full
-                    for (int p = wt; p < nseg * nv; p += kWalkThreads) {
-                        const int s = p / nv, cc = p - s * nv;
-                        const int b = seg_start[s], e = seg_start[s + 1];
-                        float sum = 0.f;
-                        for (int x = b; x < e; ++x) sum += O0[x * kOLd + cc] + O1[x * kOLd + cc];
-                        float* dst = (s == 0 && head0) ? a.head + (int64_t)blockIdx.x * a.r_len + cbase + cc
-                                                       : a.res + (int64_t)seg_row[s] * a.r_len + cbase + cc;
-                        *dst += sum;
+                    const int npairs = nseg * nv;
+                    bar_sync_named(1, kEpiThreads + kWalkThreads);  // O full
+                    bar_sync_named(3, kWalkThreads);                // the previous flush's stores are visible to all walkers
+                    // (segment, column) pairs in batches: the old values are requested first (L2 latency overlaps the
+                    // shared-memory sums), and O is handed back to the epilogue before the stores
+                    for (int p0 = 0; p0 < npairs || p0 == 0; p0 += kWalkThreads * kWalkBatch) {
+                        float* dst[kWalkBatch];
+                        float old[kWalkBatch], sum[kWalkBatch];
+#pragma unroll
+                        for (int j = 0; j < kWalkBatch; ++j) {
+                            const int p = p0 + j * kWalkThreads + wt;
+                            dst[j] = nullptr;
+                            old[j] = 0.f;
+                            if (p < npairs) {
+                                const int sg = p / nv, cc = p - sg * nv;
+                                dst[j] = (sg == 0 && head0) ? a.head + (int64_t)blockIdx.x * a.r_len + cbase + cc
+                                                            : a.res + (int64_t)seg_row[sg] * a.r_len + cbase + cc;
+                                old[j] = __ldcg(dst[j]);
+                            }
+                        }
+#pragma unroll
+                        for (int j = 0; j < kWalkBatch; ++j) {
+                            const int p = p0 + j * kWalkThreads + wt;
+                            float acc = 0.f;
+                            if (p < npairs) {
+                                const int sg = p / nv, cc = p - sg * nv;
+                                const int b = seg_start[sg], e = seg_start[sg + 1];
+                                for (int x = b; x < e; ++x) acc += O0[x * kOLd + cc] + O1[x * kOLd + cc];
+                            }
+                            sum[j] = acc;
+                        }
+                        if (p0 + kWalkThreads * kWalkBatch >= npairs) bar_arrive_named(2, kEpiThreads + kWalkThreads);  // O free
+#pragma unroll
+                        for (int j = 0; j < kWalkBatch; ++j)
+                            if (dst[j]) *dst[j] = old[j] + sum[j];
                     }
                 }
             }
@@ -581,6 +608,28 @@ __global__ void __launch_bounds__(kTcThreads, 1) tp_contract_tc_kernel(TcTpArgs 
             for (int nt = 0; nt < a.NT; ++nt, ++gi) {
                 const uint32_t buf = gi & 1u;
                 mbar_wait(&bars[14 + buf], ((gi >> 1) & 1u) ^ 1u);
+                if (KS == 4) {
+                    // 8 stages = two revolutions of the 4-slot ring: slot and phase of every stage are compile-time constants
+#pragma unroll
+                    for (int s = 0; s < 8; ++s) {
+                        const int half = s >> 2, ks = s & 3;
+                        mbar_wait(&bars[2 + ks], (uint32_t)half);
+                        tc_fence_after();
+                        if (elect_one()) {
+                            const uint32_t d = tm + buf * 256 + half * 128;
+                            const uint64_t ad = adesc0 + (uint64_t)(ks * (kStage >> 4)), bd = bdesc0 + (uint64_t)(ks * (kStage >> 4));
+                            umma_bf16(d, ad, bd, idesc, ks ? 1u : 0u);
+                            umma_bf16(d, ad + 2, bd + 2, idesc, 1u);
+                            umma_bf16(d, ad + 4, bd + 4, idesc, 1u);
+                            umma_bf16(d, ad + 6, bd + 6, idesc, 1u);
+                            umma_commit(&bars[6 + ks]);
+                            if (ks == 3) umma_commit(&bars[10 + buf * 2 + half]);
+                        }
+                        __syncwarp();
+                    }
+                    si += 8;
+                    continue;
+                }
                 for (int half = 0; half < 2; ++half) {
                     const uint32_t d = tm + buf * 256 + half * 128;
                     for (int ks = 0; ks < KS; ++ks, ++si) {
@@ -867,6 +916,28 @@ __global__ void __launch_bounds__(kGenThreads, 1) tp_dhid_tc_kernel(TcDhArgs a) 
         for (int64_t tile = t0; tile < t1; ++tile, ++ti) {
             mbar_wait(&bars[13], (ti & 1u) ^ 1u);  // the previous tile's dhid has been read out of tensor memory
             for (int nt = 0; nt < a.NT; ++nt, ++gi) {
+                if (KS == 4) {
+#pragma unroll
+                    for (int s = 0; s < 8; ++s) {
+                        const int half = s >> 2, ks = s & 3;
+                        if (ks == 0) mbar_wait(&bars[8 + half], gi & 1u);
+                        mbar_wait(&bars[ks], (uint32_t)half);
+                        tc_fence_after();
+                        if (elect_one()) {
+                            const uint64_t ad = adesc0 + (uint64_t)(2 * half * (kStage >> 4)), bd = bdesc0 + (uint64_t)(ks * (kStage >> 4));
+                            const uint32_t d = tm + ks * 64;
+#pragma unroll
+                            for (int k16 = 0; k16 < 8; ++k16)
+                                umma_bf16(d, ad + (uint64_t)((k16 >> 2) * (kStage >> 4) + (k16 & 3) * 2), bd + (uint64_t)(k16 * (2048 >> 4)), idesc,
+                                          (nt | half | k16) ? 1u : 0u);
+                            umma_commit(&bars[4 + ks]);
+                            if (ks == 3) umma_commit(&bars[10 + half]);
+                        }
+                        __syncwarp();
+                    }
+                    si += 8;
+                    continue;
+                }
                 for (int half = 0; half < 2; ++half) {
                     mbar_wait(&bars[8 + half], gi & 1u);
                     for (int ks = 0; ks < KS; ++ks, ++si) {
