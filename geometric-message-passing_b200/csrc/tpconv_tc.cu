@@ -711,7 +711,7 @@ __device__ __forceinline__ void tc_load_gside(const float* __restrict__ grow, in
 }
 
 struct TcDhArgs {
-    const int32_t *rowptr, *col, *perm;
+    const int32_t *rowptr, *col, *perm, *rowid;
     int64_t n, E;
     const float* x;
     int32_t x_len;
@@ -854,7 +854,7 @@ __global__ void __launch_bounds__(kGenThreads, 1) tp_dhid_tc_kernel(TcDhArgs a) 
             if (c.valid) {
                 c.eid = a.perm ? __ldg(a.perm + k) : k;
                 c.gnode = __ldg(a.col + k);
-                c.rowid = row_of_edge(a.rowptr, (int)a.n, k);
+                c.rowid = __ldg(a.rowid + k);
             }
             for (int yy = 0; yy < a.nyg; ++yy) {
                 const TcYGroup G = a.yg[(y_start + yy) % a.nyg];
@@ -975,7 +975,7 @@ struct TcWTile {
 };
 
 struct TcDwArgs {
-    const int32_t *rowptr, *col, *perm;
+    const int32_t *rowptr, *col, *perm, *rowid;
     int64_t n, E;
     const float* x;
     int32_t x_len;
@@ -987,8 +987,9 @@ struct TcDwArgs {
     const TcWTile* wt;
     int32_t KS;
     const float* cg;
-    float* dW2;
-    int64_t ntiles;
+    float* dW2;        // [ngroups][numel][H]: one partial per edge group (summed by the caller when ngroups > 1)
+    int64_t ntiles, numel;
+    int32_t NT, ngroups;
 };
 
 constexpr int oDwH = 0;                // hid tiles, 2 x 64 KB
@@ -1006,33 +1007,50 @@ __device__ __forceinline__ void dw_generate(const TcDwArgs& a, const TcWTile& T,
     const bool vec_ok = ((a.x_len | T.v_off) & 3) == 0;
     const int AR = T.a_end - T.a_begin, nb = min(WS, T.b_end - T.b0);
     uint32_t ti = 0;
-    const int64_t tile0 = (a.ntiles * blockIdx.x) / gridDim.x;  // every CTA starts elsewhere in the hid image (L2 spread)
-    for (int64_t tt = 0; tt < a.ntiles; ++tt, ++ti) {
-        const int64_t tile = (tile0 + tt) % a.ntiles;
-        const int64_t k = tile * kET + e;
-        const bool valid = k < a.E;
-        int64_t eid = 0;
-        int gnode = 0, rowid = 0;
-        if (valid) {
-            eid = a.perm ? __ldg(a.perm + k) : k;
-            gnode = __ldg(a.col + k);
-            rowid = row_of_edge(a.rowptr, (int)a.n, k);
+    // this CTA's edge group, walked cyclically from a CTA-specific starting tile (spreads the L2 traffic of the hid image)
+    const int nt = blockIdx.x / a.ngroups, grp = blockIdx.x - nt * a.ngroups;
+    const int64_t g0 = (a.ntiles * grp) / a.ngroups, g1 = (a.ntiles * (grp + 1)) / a.ngroups, glen = g1 - g0;
+    const int64_t rot = (glen * nt) / a.NT;
+    // edge scalars are fetched one tile ahead
+    int64_t eid_n = 0;
+    int gnode_n = 0, rowid_n = 0;
+    auto fetch = [&](int64_t tt) {
+        const int64_t k = (g0 + (rot + tt) % glen) * kET + e;
+        eid_n = 0; gnode_n = 0; rowid_n = 0;
+        if (tt < glen && k < a.E) {
+            eid_n = a.perm ? __ldg(a.perm + k) : k;
+            gnode_n = __ldg(a.col + k);
+            rowid_n = __ldg(a.rowid + k);
         }
+        return tt < glen && k < a.E;
+    };
+    bool valid_n = glen > 0 ? fetch(0) : false;
+    for (int64_t tt = 0; tt < glen; ++tt, ++ti) {
+        const bool valid = valid_n;
+        const int64_t eid = eid_n;
+        const int gnode = gnode_n, rowid = rowid_n;
+        valid_n = fetch(tt + 1);
         float Z[DA][DB];
         tc_compute_z<DA, DB>(a.sh + eid * a.S + T.sh_off, a.cg + T.cg_off, T.DS, valid, Z);
         float r[WS * M];
         tc_load_gside<DA, DB, WS>(a.g + (int64_t)rowid * a.g_len + T.r_off + T.b0 * DB, nb, valid, Z, r);
         const float* xrow = a.x + (int64_t)gnode * a.x_len + T.v_off;
+        float xs[4 * DA];
+        tc_load_x4<DA>(xrow, T.a_begin, AR, g * HA, valid, vec_ok, xs);  // in flight while waiting for the buffer
         mbar_wait(&bars[6 + g], (ti & 1u) ^ 1u);
 #pragma unroll
         for (int a4 = 0; a4 < HA; a4 += 4) {
-            float xs[4 * DA];
-            tc_load_x4<DA>(xrow, T.a_begin, AR, g * HA + a4, valid, vec_ok, xs);
+            float xn[4 * DA];
+            if (a4 + 4 < HA) tc_load_x4<DA>(xrow, T.a_begin, AR, g * HA + a4 + 4, valid, vec_ok, xn);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 float y[M];
                 tc_factor<DA, DB>(xs + j * DA, Z, y);
                 tc_dt_store<M, WS>(A, e, g * 128 + (a4 + j) * WS, r, y);
+            }
+            if (a4 + 4 < HA) {
+#pragma unroll
+                for (int v = 0; v < 4 * DA; ++v) xs[v] = xn[v];
             }
         }
         fence_proxy_async();
@@ -1047,7 +1065,7 @@ __global__ void __launch_bounds__(kGenThreads, 1) tp_dw2_tc_kernel(TcDwArgs a) {
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(sm + oDwBar + 9 * 8);
     const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
     const int KS = a.KS, H = 64 * KS;
-    const TcWTile T = a.wt[blockIdx.x];
+    const TcWTile T = a.wt[blockIdx.x / a.ngroups];
     if (t == 0) {
         mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_init(&bars[2], 1); mbar_init(&bars[3], 1);
         mbar_init(&bars[4], 128); mbar_init(&bars[5], 128); mbar_init(&bars[6], 1); mbar_init(&bars[7], 1);
@@ -1074,21 +1092,26 @@ __global__ void __launch_bounds__(kGenThreads, 1) tp_dw2_tc_kernel(TcDwArgs a) {
         const int al = c / T.WS, b = c - al * T.WS;
         const int aa = T.a_begin + al, bb = T.b0 + b;
         const bool live = aa < T.a_end && bb < T.b_end;
-        float* dst = a.dW2 + ((int64_t)T.w_off + (int64_t)aa * T.stride_a + (int64_t)bb * T.stride_b) * H;
+        const int grp = blockIdx.x % a.ngroups;
+        const bool any = (a.ntiles * (grp + 1)) / a.ngroups > (a.ntiles * grp) / a.ngroups;  // an empty group wrote nothing to D
+        float* dst = a.dW2 + ((int64_t)(blockIdx.x % a.ngroups) * a.numel + (int64_t)T.w_off + (int64_t)aa * T.stride_a + (int64_t)bb * T.stride_b) * H;
         for (int cc = 0; cc < H; cc += 32) {
             float v[32];
             tmem_ld32(tm + lane_base + g * H + cc, v);
             if (live) {
 #pragma unroll
-                for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dst + cc + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                for (int j = 0; j < 32; j += 4)
+                    *reinterpret_cast<float4*>(dst + cc + j) = any ? make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
         }
     } else if (warp == 8) {
         if (lane == 0) {
             uint32_t ti = 0;
-            const int64_t tile0 = (a.ntiles * blockIdx.x) / gridDim.x;
-            for (int64_t tt = 0; tt < a.ntiles; ++tt, ++ti) {
-                const int64_t tile = (tile0 + tt) % a.ntiles;
+            const int nt = blockIdx.x / a.ngroups, grp = blockIdx.x - nt * a.ngroups;
+            const int64_t g0 = (a.ntiles * grp) / a.ngroups, g1 = (a.ntiles * (grp + 1)) / a.ngroups, glen = g1 - g0;
+            const int64_t rot = (glen * nt) / a.NT;
+            for (int64_t tt = 0; tt < glen; ++tt, ++ti) {
+                const int64_t tile = g0 + (rot + tt) % glen;
                 const uint32_t buf = ti & 1u;
                 mbar_wait(&bars[2 + buf], ((ti >> 1) & 1u) ^ 1u);
                 mbar_expect_tx(&bars[buf], (uint32_t)(KS * kStage));
@@ -1100,7 +1123,9 @@ __global__ void __launch_bounds__(kGenThreads, 1) tp_dw2_tc_kernel(TcDwArgs a) {
         const uint32_t idesc = umma_idesc_bf16(128, H, true, true);
         const uint64_t adesc0 = umma_desc_mn128(smem_u32(sm + oDwA), kStage), bdesc0 = umma_desc_mn128(smem_u32(sm + oDwH), kStage);
         uint32_t ti = 0;
-        for (int64_t tile = 0; tile < a.ntiles; ++tile, ++ti) {
+        const int grp = blockIdx.x % a.ngroups;
+        const int64_t glen = (a.ntiles * (grp + 1)) / a.ngroups - (a.ntiles * grp) / a.ngroups;
+        for (int64_t tt = 0; tt < glen; ++tt, ++ti) {
             const uint32_t buf = ti & 1u;
             mbar_wait(&bars[buf], (ti >> 1) & 1u);
             for (int half = 0; half < 2; ++half) {
@@ -1222,12 +1247,12 @@ int gmp_tp_tc_contract(const int32_t* rowptr, const int32_t* col, const int32_t*
     return rc;
 }
 
-int gmp_tp_tc_dhid(const int32_t* rowptr, const int32_t* col, const int32_t* perm, int64_t n, int64_t num_edges, const float* x,
+int gmp_tp_tc_dhid(const int32_t* rowptr, const int32_t* col, const int32_t* perm, const int32_t* rowid, int64_t n, int64_t num_edges, const float* x,
                    int32_t x_len, const float* g, int32_t g_len, const float* edge_sh, int32_t S, const float* edge_feat, int32_t R,
                    const float* w1, const float* b1, const void* w2_img, const void* ygroups, int32_t nyg, int32_t ntiles_n, int32_t H,
                    const float* cg, float* dpre, gmp_stream_t stream) {
     GMP_REQUIRE(rowptr && ygroups && cg && w1 && b1 && dpre, "tp_tc_dhid: NULL pointer");
-    GMP_REQUIRE(num_edges == 0 || (col && x && g && edge_sh && edge_feat && w2_img), "tp_tc_dhid: NULL edge/feature pointer");
+    GMP_REQUIRE(num_edges == 0 || (col && rowid && x && g && edge_sh && edge_feat && w2_img), "tp_tc_dhid: NULL edge/feature pointer");
     GMP_REQUIRE(H >= 64 && H <= 256 && H % 64 == 0, "tp_tc_dhid: mlp_dim must be 64, 128, 192 or 256 (got %d)", H);
     GMP_REQUIRE(R >= 1 && R <= 16, "tp_tc_dhid: edge_feats_dim in [1, 16] (got %d)", R);
     if (n == 0 || num_edges == 0) return GMP_OK;
@@ -1236,7 +1261,7 @@ int gmp_tp_tc_dhid(const int32_t* rowptr, const int32_t* col, const int32_t* per
         return GMP_OK;
     }
     TcDhArgs a;
-    a.rowptr = rowptr; a.col = col; a.perm = perm; a.n = n; a.E = num_edges; a.x = x; a.x_len = x_len; a.g = g; a.g_len = g_len;
+    a.rowptr = rowptr; a.col = col; a.perm = perm; a.rowid = rowid; a.n = n; a.E = num_edges; a.x = x; a.x_len = x_len; a.g = g; a.g_len = g_len;
     a.sh = edge_sh; a.S = S; a.feat = edge_feat; a.R = R; a.w1 = w1; a.b1 = b1; a.w2_img = (const uint8_t*)w2_img;
     a.yg = (const TcYGroup*)ygroups; a.nyg = nyg; a.NT = ntiles_n; a.KS = H / 64; a.cg = cg; a.dpre = dpre;
     a.ntiles = ceil_div(num_edges, kET);
@@ -1246,19 +1271,21 @@ int gmp_tp_tc_dhid(const int32_t* rowptr, const int32_t* col, const int32_t* per
     return check_launch("tp_dhid_tc_kernel");
 }
 
-int gmp_tp_tc_dw2(const int32_t* rowptr, const int32_t* col, const int32_t* perm, int64_t n, int64_t num_edges, const float* x,
-                  int32_t x_len, const float* g, int32_t g_len, const float* edge_sh, int32_t S, const void* hid_img,
-                  const void* wtile_table, int32_t ntiles_n, int32_t H, const float* cg, float* dW2, gmp_stream_t stream) {
+int gmp_tp_tc_dw2(const int32_t* rowptr, const int32_t* col, const int32_t* perm, const int32_t* rowid, int64_t n, int64_t num_edges,
+                  const float* x, int32_t x_len, const float* g, int32_t g_len, const float* edge_sh, int32_t S, const void* hid_img,
+                  const void* wtile_table, int32_t ntiles_n, int32_t H, const float* cg, int64_t numel, int32_t ngroups, float* dW2,
+                  gmp_stream_t stream) {
     GMP_REQUIRE(rowptr && wtile_table && cg && dW2, "tp_tc_dw2: NULL pointer");
-    GMP_REQUIRE(num_edges == 0 || (col && x && g && edge_sh && hid_img), "tp_tc_dw2: NULL edge/feature pointer");
+    GMP_REQUIRE(num_edges == 0 || (col && rowid && x && g && edge_sh && hid_img), "tp_tc_dw2: NULL edge/feature pointer");
+    GMP_REQUIRE(ngroups >= 1 && ngroups <= 64, "tp_tc_dw2: ngroups in [1, 64] (got %d)", ngroups);
     GMP_REQUIRE(H >= 64 && H <= 256 && H % 64 == 0, "tp_tc_dw2: mlp_dim must be 64, 128, 192 or 256 (got %d)", H);
     if (ntiles_n == 0) return GMP_OK;
     TcDwArgs a;
-    a.rowptr = rowptr; a.col = col; a.perm = perm; a.n = n; a.E = num_edges; a.x = x; a.x_len = x_len; a.g = g; a.g_len = g_len;
+    a.rowptr = rowptr; a.col = col; a.perm = perm; a.rowid = rowid; a.n = n; a.E = num_edges; a.x = x; a.x_len = x_len; a.g = g; a.g_len = g_len;
     a.sh = edge_sh; a.S = S; a.hid_img = (const uint8_t*)hid_img; a.wt = (const TcWTile*)wtile_table; a.KS = H / 64; a.cg = cg;
-    a.dW2 = dW2; a.ntiles = ceil_div(num_edges, kET);
+    a.dW2 = dW2; a.ntiles = ceil_div(num_edges, kET); a.numel = numel; a.NT = ntiles_n; a.ngroups = ngroups;
     GMP_CUDA(cudaFuncSetAttribute(tp_dw2_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcDwSmem));
-    tp_dw2_tc_kernel<<<ntiles_n, kGenThreads, kTcDwSmem, stream>>>(a);
+    tp_dw2_tc_kernel<<<ntiles_n * ngroups, kGenThreads, kTcDwSmem, stream>>>(a);
     return check_launch("tp_dw2_tc_kernel");
 }
 

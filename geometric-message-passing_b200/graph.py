@@ -103,9 +103,12 @@ class CSR:
         return ptr(self.perm)
 
     def row_ids(self) -> torch.Tensor:
-        """int32[E]: aggregation row of each sorted edge."""
-        deg = (self.rowptr[1:] - self.rowptr[:-1]).long()
-        return torch.repeat_interleave(torch.arange(self.n, device=self.rowptr.device, dtype=torch.int32), deg)
+        """int32[E]: aggregation row of each sorted edge (cached)."""
+        if getattr(self, "_row_ids", None) is None:
+            deg = (self.rowptr[1:] - self.rowptr[:-1]).long()
+            self._row_ids = torch.repeat_interleave(
+                torch.arange(self.n, device=self.rowptr.device, dtype=torch.int32), deg).contiguous()
+        return self._row_ids
 
 
 def build_csr(index: torch.Tensor, other: torch.Tensor, n: int) -> CSR:

@@ -366,13 +366,21 @@ def _tc_wgrad(graph, x, g, edge_sh, edge_feat, w1, b1, w2, b2, plan: "TensorProd
     hid_img, w2_img = _tc_images(csr, E, edge_feat, w1, b1, w2, tab, "tc_fwd", d)
     NT = tab["ntiles"].shape[0]
     dpre = torch.zeros(E, H, dtype=torch.float32, device=x.device) if E == 0 else torch.empty(E, H, dtype=torch.float32, device=x.device)
-    call("gmp_tp_tc_dhid", ptr(csr.rowptr), ptr(csr.col), csr.perm_ptr, n, E, ptr(x), x.shape[1], ptr(g), g.shape[1], ptr(edge_sh), S,
+    rowid = csr.row_ids()
+    call("gmp_tp_tc_dhid", ptr(csr.rowptr), ptr(csr.col), csr.perm_ptr, ptr(rowid), n, E, ptr(x), x.shape[1], ptr(g), g.shape[1], ptr(edge_sh), S,
          ptr(edge_feat), R, ptr(w1), ptr(b1), ptr(w2_img), ptr(d["tc_fwd_ygroups"]), tab["ygroups"].shape[0], NT, H, ptr(d["cg"]),
          ptr(dpre))
-    dW2 = torch.empty_like(w2) if E > 0 else torch.zeros_like(w2)
     if E > 0:
-        call("gmp_tp_tc_dw2", ptr(csr.rowptr), ptr(csr.col), csr.perm_ptr, n, E, ptr(x), x.shape[1], ptr(g), g.shape[1], ptr(edge_sh), S,
-             ptr(hid_img), ptr(d["tc_fwd_wtiles"]), NT, H, ptr(d["cg"]), ptr(dW2))
+        # edge groups: the grid NT * G should fill whole waves of SMs (each CTA needs a full SM)
+        sms = torch.cuda.get_device_properties(x.device).multi_processor_count
+        ntile_e = -(-E // 128)
+        G = min(range(1, max(1, min(8, ntile_e // 32)) + 1), key=lambda k: (-(-NT * k // sms)) / k)
+        parts = torch.empty(G, w2.shape[0], H, dtype=torch.float32, device=x.device)
+        call("gmp_tp_tc_dw2", ptr(csr.rowptr), ptr(csr.col), csr.perm_ptr, ptr(rowid), n, E, ptr(x), x.shape[1], ptr(g), g.shape[1],
+             ptr(edge_sh), S, ptr(hid_img), ptr(d["tc_fwd_wtiles"]), NT, H, ptr(d["cg"]), w2.shape[0], G, ptr(parts))
+        dW2 = parts[0] if G == 1 else parts.sum(0)
+    else:
+        dW2 = torch.zeros_like(w2)
     ys = _tc_ysum(csr, n, E, x, edge_sh, tab, "tc_fwd", d)
     db2 = torch.zeros_like(b2)
     for bs in tab["bias"]:

@@ -292,15 +292,18 @@ int gmp_tp_tc_contract(const int32_t* rowptr, const int32_t* col, const int32_t*
  *                    db1 = column sums follow as plain GEMM / reduction)
  *   gmp_tp_tc_dw2  : dW2[c, :] = sum_e dT_e[c] hid_e[:]; `wtile_table` [ntiles_n] (16 int32, struct TcWTile), one CTA each
  * dT_e[(a,b)] = sum_k g[row_e][b,k] Y_e[a,k] is generated per tile as a bf16 UMMA operand and never stored. */
-int gmp_tp_tc_dhid(const int32_t* rowptr, const int32_t* col, const int32_t* perm, int64_t n, int64_t num_edges,
-                   const float* x, int32_t x_len, const float* g, int32_t g_len, const float* edge_sh, int32_t S,
-                   const float* edge_feat, int32_t R, const float* w1, const float* b1, const void* w2_img,
+int gmp_tp_tc_dhid(const int32_t* rowptr, const int32_t* col, const int32_t* perm, const int32_t* rowid, int64_t n,
+                   int64_t num_edges, const float* x, int32_t x_len, const float* g, int32_t g_len, const float* edge_sh,
+                   int32_t S, const float* edge_feat, int32_t R, const float* w1, const float* b1, const void* w2_img,
                    const void* ygroups, int32_t nyg, int32_t ntiles_n, int32_t H, const float* cg, float* dpre,
                    gmp_stream_t stream);
-int gmp_tp_tc_dw2(const int32_t* rowptr, const int32_t* col, const int32_t* perm, int64_t n, int64_t num_edges,
-                  const float* x, int32_t x_len, const float* g, int32_t g_len, const float* edge_sh, int32_t S,
-                  const void* hid_img, const void* wtile_table, int32_t ntiles_n, int32_t H, const float* cg,
-                  float* dW2, gmp_stream_t stream);
+/* rowid int32[E]: CSR row of every sorted edge.  dW2 [ngroups][numel][H]: the edge tiles are split into `ngroups`
+ * contiguous groups (grid = ntiles_n * ngroups CTAs, chosen by the caller to fill whole waves of SMs); each group
+ * writes its own partial, the caller sums them in group order. */
+int gmp_tp_tc_dw2(const int32_t* rowptr, const int32_t* col, const int32_t* perm, const int32_t* rowid, int64_t n,
+                  int64_t num_edges, const float* x, int32_t x_len, const float* g, int32_t g_len, const float* edge_sh,
+                  int32_t S, const void* hid_img, const void* wtile_table, int32_t ntiles_n, int32_t H, const float* cg,
+                  int64_t numel, int32_t ngroups, float* dW2, gmp_stream_t stream);
 /* YS[n][y_off_p + a*DB_p + k] = sum_{e in CSR row n} sum_i V[col_e][v_off_p + a*DA_p + i] * Z^p_e[i][k], fp32:
  * the node-level aggregate in which both the bias term of the layer and db2 are linear.
  * `ypaths` [npaths] (8 int32, struct TcYPath), `zentries` [nz] (4 int32, struct TcZEntry); npairs = sum_p MA_p. */
