@@ -63,7 +63,10 @@ __global__ void __launch_bounds__(256) tp_pack_hid_kernel(const int32_t* __restr
     float* fs = b1s + H;         // [128][R]
     const int t = threadIdx.x;
     const int64_t e0 = (int64_t)blockIdx.x * kET;
-    for (int x = t; x < H * R; x += 256) w1s[x] = __ldg(w1 + x);
+    for (int x = t; x < H * R; x += 256) {  // transposed: w1s[c][h], so that a thread's 8 consecutive h are two float4
+        const int h = x / R, c = x - h * R;
+        w1s[c * H + h] = __ldg(w1 + x);
+    }
     for (int x = t; x < H; x += 256) b1s[x] = __ldg(b1 + x);
     for (int x = t; x < kET * R; x += 256) {
         const int r = x / R, c = x - r * R;
@@ -80,12 +83,15 @@ __global__ void __launch_bounds__(256) tp_pack_hid_kernel(const int32_t* __restr
         const bool live = e0 + r < E;
         float v[8];
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-            const int h = cg * 8 + q;
-            float acc = b1s[h];
-            for (int c = 0; c < R; ++c) acc = fmaf(w1s[h * R + c], fs[r * R + c], acc);
-            v[q] = live ? fmaxf(acc, 0.f) : 0.f;
+        for (int q = 0; q < 8; ++q) v[q] = b1s[cg * 8 + q];
+        for (int c = 0; c < R; ++c) {
+            const float f = fs[r * R + c];
+            const float4 wa = *reinterpret_cast<const float4*>(w1s + c * H + cg * 8), wb = *reinterpret_cast<const float4*>(w1s + c * H + cg * 8 + 4);
+            v[0] = fmaf(wa.x, f, v[0]); v[1] = fmaf(wa.y, f, v[1]); v[2] = fmaf(wa.z, f, v[2]); v[3] = fmaf(wa.w, f, v[3]);
+            v[4] = fmaf(wb.x, f, v[4]); v[5] = fmaf(wb.y, f, v[5]); v[6] = fmaf(wb.z, f, v[6]); v[7] = fmaf(wb.w, f, v[7]);
         }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) v[q] = live ? fmaxf(v[q], 0.f) : 0.f;
         *reinterpret_cast<uint4*>(dst + (cg >> 3) * kStage + sw128_chunk_off(r, cg & 7)) =
             make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
     }
@@ -119,6 +125,7 @@ __global__ void __launch_bounds__(256) tp_pack_w2_kernel(const float* __restrict
 // ------------------------------------------------------------------------------------------------
 constexpr int kYsPairs = 12;  // (path, a) pairs per thread
 constexpr int kYsMaxZ = 256;
+constexpr int kYsEB = 4;      // edges per synchronisation
 
 struct YsArgs {
     const int32_t *rowptr, *col, *perm;
@@ -137,7 +144,8 @@ struct YsArgs {
 };
 
 __global__ void __launch_bounds__(128) tp_ysum_kernel(YsArgs a) {
-    __shared__ float Zs[kYsMaxZ];
+    __shared__ float Zs[kYsEB][kYsMaxZ];
+    __shared__ const float* vrows[kYsEB];
     __shared__ TcYPath ps[32];
     const int t = threadIdx.x;
     if (t < a.npaths) ps[t] = a.paths[t];
@@ -162,28 +170,32 @@ __global__ void __launch_bounds__(128) tp_ysum_kernel(YsArgs a) {
 #pragma unroll
             for (int k = 0; k < 5; ++k) acc[j][k] = 0.f;
         const int64_t eb = __ldg(a.rowptr + row), ee = __ldg(a.rowptr + row + 1);
-        for (int64_t e = eb; e < ee; ++e) {
-            const int64_t eid = a.perm ? __ldg(a.perm + e) : e;
-            const float* vrow = a.V + (int64_t)__ldg(a.col + e) * a.v_len;
+        for (int64_t e0 = eb; e0 < ee; e0 += kYsEB) {
+            const int cnt = (int)min((int64_t)kYsEB, ee - e0);
             __syncthreads();
-            for (int z = t; z < a.nz; z += 128) {
-                const TcZEntry ze = a.zent[z];
-                float s = 0.f;
-                for (int j = 0; j < ze.DS; ++j) s = fmaf(__ldg(a.sh + eid * a.S + ze.sh_off + j), __ldg(a.cg + ze.cg_base + j * ze.cg_stride), s);
-                Zs[z] = s;
+            for (int z = t; z < a.nz * cnt; z += 128) {
+                const int q = z / a.nz, zz = z - q * a.nz;
+                const int64_t eid = a.perm ? __ldg(a.perm + e0 + q) : e0 + q;
+                const TcZEntry ze = a.zent[zz];
+                float sacc = 0.f;
+                for (int j = 0; j < ze.DS; ++j) sacc = fmaf(__ldg(a.sh + eid * a.S + ze.sh_off + j), __ldg(a.cg + ze.cg_base + j * ze.cg_stride), sacc);
+                Zs[q][zz] = sacc;
             }
+            if (t < cnt) vrows[t] = a.V + (int64_t)__ldg(a.col + e0 + t) * a.v_len;
             __syncthreads();
 #pragma unroll
             for (int j = 0; j < kYsPairs; ++j) {
                 if (pp[j] < 0) continue;
                 const TcYPath P = ps[pp[j]];
-                const float* x = vrow + P.v_off + pa[j] * P.DA;
-                const float* Z = Zs + P.z_off;
-                for (int i = 0; i < P.DA; ++i) {
-                    const float xv = __ldg(x + i);
+                for (int q = 0; q < cnt; ++q) {
+                    const float* x = vrows[q] + P.v_off + pa[j] * P.DA;
+                    const float* Z = Zs[q] + P.z_off;
+                    for (int i = 0; i < P.DA; ++i) {
+                        const float xv = __ldg(x + i);
 #pragma unroll
-                    for (int k = 0; k < 5; ++k)
-                        if (k < P.DB) acc[j][k] = fmaf(xv, Z[i * P.DB + k], acc[j][k]);
+                        for (int k = 0; k < 5; ++k)
+                            if (k < P.DB) acc[j][k] = fmaf(xv, Z[i * P.DB + k], acc[j][k]);
+                    }
                 }
             }
         }

@@ -354,17 +354,18 @@ def _tc_contract(csr, n, E, V, r_len, edge_sh, edge_feat, w1, b1, w2, b2, plan: 
         ysp = ys[:, bs["y_off"]:bs["y_off"] + bs["MA"] * bs["DB"]].view(n, bs["MA"], bs["DB"])
         blk = res[:, bs["r_off"]:bs["r_off"] + bs["MB"] * bs["DB"]].view(n, bs["MB"], bs["DB"])
         blk += torch.einsum("nak,ab->nbk", ysp, Bm)
-    return res
+    return res, hid_img, ys
 
 
-def _tc_wgrad(graph, x, g, edge_sh, edge_feat, w1, b1, w2, b2, plan: "TensorProductPlan", d):
+def _tc_wgrad(graph, x, g, edge_sh, edge_feat, w1, b1, w2, b2, plan: "TensorProductPlan", d, hid_img, ys):
     """Parameter gradients of fc on the tensor cores: dW2 = dT^T hid (gmp_tp_tc_dw2), dhid = dT W2 (gmp_tp_tc_dhid,
     masked by the ReLU and written as dL/d(pre-activation) per edge), db2 through the node-level aggregate YS,
     dW1 / db1 as plain GEMM / column sum of the pre-activation gradient."""
     tab, csr = plan.tc_fwd, graph.by_src
     n, E, H, R, S = graph.n, graph.E, w1.shape[0], w1.shape[1], edge_sh.shape[1]
-    hid_img, w2_img = _tc_images(csr, E, edge_feat, w1, b1, w2, tab, "tc_fwd", d)
     NT = tab["ntiles"].shape[0]
+    w2_img = torch.empty(max(int(_lib.lib().gmp_tp_tc_w2_bytes(NT, H)), 16), dtype=torch.uint8, device=x.device)
+    call("gmp_tp_tc_pack_w2", ptr(w2), H, ptr(d["tc_fwd_ntiles"]), NT, ptr(w2_img))
     dpre = torch.zeros(E, H, dtype=torch.float32, device=x.device) if E == 0 else torch.empty(E, H, dtype=torch.float32, device=x.device)
     rowid = csr.row_ids()
     call("gmp_tp_tc_dhid", ptr(csr.rowptr), ptr(csr.col), csr.perm_ptr, ptr(rowid), n, E, ptr(x), x.shape[1], ptr(g), g.shape[1], ptr(edge_sh), S,
@@ -381,7 +382,6 @@ def _tc_wgrad(graph, x, g, edge_sh, edge_feat, w1, b1, w2, b2, plan: "TensorProd
         dW2 = parts[0] if G == 1 else parts.sum(0)
     else:
         dW2 = torch.zeros_like(w2)
-    ys = _tc_ysum(csr, n, E, x, edge_sh, tab, "tc_fwd", d)
     db2 = torch.zeros_like(b2)
     for bs in tab["bias"]:
         ysp = ys[:, bs["y_off"]:bs["y_off"] + bs["MA"] * bs["DB"]].view(n, bs["MA"], bs["DB"])
@@ -414,7 +414,10 @@ class _TPConvFn(torch.autograd.Function):
         ctx.save_for_backward(x, edge_sh, edge_feat, w1, b1, w2, b2)
         ctx.graph, ctx.plan, ctx.precision = graph, plan, precision
         if precision == _lib.BF16_TC:
-            return _tc_contract(csr, graph.n, graph.E, x, plan.irreps_out.dim, edge_sh, edge_feat, w1, b1, w2, b2, plan, "tc_fwd", d)
+            # the hidden-layer image (bf16, E x mlp_dim) and the node aggregate YS are kept for the weight-gradient kernels
+            out, ctx.hid_img, ctx.ys = _tc_contract(csr, graph.n, graph.E, x, plan.irreps_out.dim, edge_sh, edge_feat, w1, b1, w2, b2,
+                                                    plan, "tc_fwd", d)
+            return out
         out = torch.empty(graph.n, plan.irreps_out.dim, dtype=x.dtype, device=x.device)
         call("gmp_tp_contract", ptr(csr.rowptr), ptr(csr.col), csr.perm_ptr, graph.n, graph.E, ptr(x), x.shape[1], ptr(out),
              out.shape[1], ptr(edge_sh), S, ptr(edge_feat), R, ptr(w1), ptr(b1), ptr(w2), ptr(b2), H, ptr(d["fwd_passes"]),
@@ -435,14 +438,15 @@ class _TPConvFn(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             t = graph.by_dst  # rows = edge_index[1] (where node_attr was gathered), col = edge_index[0]
             if precision == _lib.BF16_TC:
-                dx = _tc_contract(t, graph.n, graph.E, g, x.shape[1], edge_sh, edge_feat, w1, b1, w2, b2, plan, "tc_bwd", d)
+                dx = _tc_contract(t, graph.n, graph.E, g, x.shape[1], edge_sh, edge_feat, w1, b1, w2, b2, plan, "tc_bwd", d)[0]
             else:
                 dx = torch.empty_like(x)
                 call("gmp_tp_contract", ptr(t.rowptr), ptr(t.col), t.perm_ptr, graph.n, graph.E, ptr(g), g.shape[1], ptr(dx),
                      dx.shape[1], ptr(edge_sh), S, ptr(edge_feat), R, ptr(w1), ptr(b1), ptr(w2), ptr(b2), H, ptr(d["bwd_passes"]),
                      ptr(d["bwd_blocks"]), plan.bwd["nblocks"], plan.bwd["nunits"], ptr(d["cg"]), precision)
         if precision == _lib.BF16_TC:
-            dW1, db1, dW2, db2 = _tc_wgrad(graph, x, g, edge_sh, edge_feat, w1, b1, w2, b2, plan, d)
+            dW1, db1, dW2, db2 = _tc_wgrad(graph, x, g, edge_sh, edge_feat, w1, b1, w2, b2, plan, d, ctx.hid_img, ctx.ys)
+            ctx.hid_img = ctx.ys = None
             return dx, None, None, dW1, db1, dW2, db2, None, None, None
         csr = graph.by_src
         nunits = plan.wunits.shape[0]
