@@ -1,6 +1,7 @@
-"""Per-layer forward+backward timings of the other fused layers (fp32-strict kernels) at the BASELINE config shapes
-(reduced graph counts where the full size would take minutes in fp32).  Prints one JSON line per layer.
-usage: python scripts/bench_layers.py [egnn] [tfn] [mace] [symc]"""
+"""Per-layer forward+backward timings of the fused layers at the BASELINE config shapes: fp32-strict kernels (reduced
+graph counts where the full size would take minutes) and the tcgen05 path (precision="bf16", full config sizes).
+Prints one JSON line per layer.
+usage: python scripts/bench_layers.py [egnn] [tfn] [mace] [tfn_tc] [mace_tc] [symc]"""
 import json
 import os
 import sys
@@ -74,6 +75,41 @@ for name, C, graphs in (("tfn", 64, 64), ("mace", 128, 32)):
     print(json.dumps({"layer": f"TensorProductConvLayer C={C} ({name} config, layer>=1) fp32-strict",
                       "workload": f"{graphs} clouds x 64 nodes, N={N} E={E}, weight_numel={wn}", "ms_fwd_bwd": ms,
                       "edges_per_s": E / (ms * 1e-3), "tflops_fp32": 4 * 2 * 256 * wn * E / (ms * 1e-3) / 1e12}))
+
+PEAK_TF = 1366.5  # MEASURED_PEAKS.json bf16_tflops_sustained (kernels timed inside a long step)
+for name, C, graphs in (("tfn_tc", 64, 2048), ("mace_tc", 128, 1024)):
+    if name not in which:
+        continue
+    pos, batch = clouds(graphs, 64, 4.0)
+    ei = gmp_b200.radius_graph(pos, 2.0, batch, max_num_neighbors=64)
+    N, E = pos.shape[0], ei.shape[1]
+    hid = f"{C}x0e+{C}x1o+{C}x2e"
+    conv = gmp_b200.TensorProductConvLayer(hid, hid, "1x0e+1x1o+1x2e", 8, 256, gate=(name == "tfn_tc"), batch_norm=(name == "mace_tc"),
+                                           precision="bf16").to(dev)
+    sh, ft = gmp_b200.edge_geometry(pos, ei, 2, gmp_b200.RadialEmbeddingBlock(2.0, 8, 5))
+    x = torch.randn(N, 9 * C, device=dev, requires_grad=True)
+
+    def fwd():
+        return conv(x, ei, sh, ft)
+
+    def step():
+        conv.zero_grad(set_to_none=True)
+        fwd().sum().backward()
+    with torch.no_grad():
+        ms_f = timeit(fwd, warm=2, reps=5)
+    ms = timeit(step, warm=2, reps=5)
+    wn = conv.tp.weight_numel
+    gemm = 2 * 256 * wn * E  # one pass of fc's second Linear
+    print(json.dumps({"layer": f"TensorProductConvLayer C={C} ({name[:-3]} config, layer>=1) bf16 tcgen05 (1e-2)",
+                      "workload": f"{graphs} clouds x 64 nodes (BASELINE config size), N={N} E={E}, weight_numel={wn}",
+                      "ms_fwd": ms_f, "ms_fwd_bwd": ms, "edges_per_s": E / (ms * 1e-3), "edges_per_s_fwd": E / (ms_f * 1e-3),
+                      "tflops_fwd": gemm / (ms_f * 1e-3) / 1e12,
+                      "tflops_fwd_bwd_algorithmic_3x": 3 * gemm / (ms * 1e-3) / 1e12,
+                      "tflops_fwd_bwd_executed_4x": 4 * gemm / (ms * 1e-3) / 1e12,
+                      "roofline": {"bound": "tensor", "peak": PEAK_TF, "unit": "TFLOP/s", "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained",
+                                   "frac_fwd": gemm / (ms_f * 1e-3) / 1e12 / PEAK_TF,
+                                   "frac_fwd_bwd_algorithmic": 3 * gemm / (ms * 1e-3) / 1e12 / PEAK_TF,
+                                   "frac_fwd_bwd_executed": 4 * gemm / (ms * 1e-3) / 1e12 / PEAK_TF}}))
 
 if "symc" in which:
     N, C = 65536, 128
