@@ -40,8 +40,14 @@ class _EGNNEdgeFn(torch.autograd.Function):
         csr = graph.by_dst
         msg = torch.empty(graph.n, d, dtype=P.dtype, device=P.device)
         pag = torch.empty(graph.n, 3, dtype=P.dtype, device=P.device)
-        call("gmp_egnn_edge_fwd", ptr(csr.rowptr), ptr(csr.col), graph.n, graph.E, ptr(P), ptr(Q), ptr(pos),
-             C.byref(prm), ptr(msg), ptr(pag), precision)
+        if precision == _lib.BF16_TC:
+            if d != 128:
+                raise NotImplementedError("precision='bf16': the tensor-core EGNN kernels are built for emb_dim = 128")
+            call("gmp_egnn_tc_edge_fwd", ptr(csr.rowptr), ptr(csr.col), ptr(csr.row_ids()), graph.n, graph.E, ptr(P),
+                 ptr(Q.to(torch.bfloat16)), ptr(pos), C.byref(prm), ptr(msg), ptr(pag))
+        else:
+            call("gmp_egnn_edge_fwd", ptr(csr.rowptr), ptr(csr.col), graph.n, graph.E, ptr(P), ptr(Q), ptr(pos),
+                 C.byref(prm), ptr(msg), ptr(pag), precision)
         ctx.save_for_backward(P, Q, pos, *w)
         ctx.graph, ctx.meta = graph, (act, eps, aggr_mean, precision)
         return msg, pag
@@ -55,15 +61,23 @@ class _EGNNEdgeFn(torch.autograd.Function):
         g_msg, g_pos = g_msg.contiguous(), g_pos.contiguous()
         prm = _params_struct(w, d, act, eps, aggr_mean)
         lib = _lib.lib()
-        nparts, plen = lib.gmp_egnn_bwd_num_parts(graph.E), lib.gmp_egnn_bwd_part_len(d)
+        tc = precision == _lib.BF16_TC
+        nparts = lib.gmp_egnn_tc_bwd_num_parts(graph.E) if tc else lib.gmp_egnn_bwd_num_parts(graph.E)
+        plen = lib.gmp_egnn_bwd_part_len(d)
         parts = torch.empty(nparts, plen, dtype=P.dtype, device=P.device)
         dP, dQ = torch.empty_like(P), torch.empty_like(Q)
         dpos_i, dpos_j = torch.empty_like(pos), torch.empty_like(pos)
         cd, cs = graph.by_dst, graph.by_src
-        call("gmp_egnn_edge_bwd", ptr(cd.rowptr), ptr(cd.col), ptr(cd.rowptr), graph.n, graph.E, ptr(P), ptr(Q), ptr(pos),
-             C.byref(prm), ptr(g_msg), ptr(g_pos), 0, ptr(dP), ptr(dpos_i), ptr(parts), precision)
-        call("gmp_egnn_edge_bwd", ptr(cs.rowptr), ptr(cs.col), ptr(cd.rowptr), graph.n, graph.E, ptr(P), ptr(Q), ptr(pos),
-             C.byref(prm), ptr(g_msg), ptr(g_pos), 1, ptr(dQ), ptr(dpos_j), None, precision)
+        if tc:
+            call("gmp_egnn_tc_edge_bwd", ptr(cd.rowptr), ptr(cd.col), ptr(cd.row_ids()), ptr(cd.rowptr), graph.n, graph.E, ptr(P),
+                 ptr(Q.to(torch.bfloat16)), ptr(pos), C.byref(prm), ptr(g_msg), ptr(g_pos), 0, ptr(dP), ptr(dpos_i), ptr(parts))
+            call("gmp_egnn_tc_edge_bwd", ptr(cs.rowptr), ptr(cs.col), ptr(cs.row_ids()), ptr(cd.rowptr), graph.n, graph.E, ptr(Q),
+                 ptr(P.to(torch.bfloat16)), ptr(pos), C.byref(prm), ptr(g_msg), ptr(g_pos), 1, ptr(dQ), ptr(dpos_j), ptr(parts))
+        else:
+            call("gmp_egnn_edge_bwd", ptr(cd.rowptr), ptr(cd.col), ptr(cd.rowptr), graph.n, graph.E, ptr(P), ptr(Q), ptr(pos),
+                 C.byref(prm), ptr(g_msg), ptr(g_pos), 0, ptr(dP), ptr(dpos_i), ptr(parts), precision)
+            call("gmp_egnn_edge_bwd", ptr(cs.rowptr), ptr(cs.col), ptr(cd.rowptr), graph.n, graph.E, ptr(P), ptr(Q), ptr(pos),
+                 C.byref(prm), ptr(g_msg), ptr(g_pos), 1, ptr(dQ), ptr(dpos_j), None, precision)
         red = torch.empty(plen, dtype=P.dtype, device=P.device)
         call("gmp_reduce_partials_f32", ptr(parts), nparts, plen, ptr(red))
         dd = d * d

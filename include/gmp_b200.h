@@ -234,6 +234,25 @@ int gmp_egnn_edge_bwd(const int32_t* rowptr, const int32_t* col, const int32_t* 
                       int32_t src_pass, float* d_node, float* d_pos, float* wgrad_parts, int32_t precision,
                       gmp_stream_t stream);
 
+/* ---- GMP_BF16_TC variant (csrc/egnn_tc.cu, emb_dim = 128): both edge GEMMs on tcgen05 (bf16 operands, fp32 accumulation
+ * in tensor memory), 128-edge tiles; 1e-2 relative.  rowid int32[E] = CSR row of every sorted edge.  The col-side
+ * operand is read as bf16 rows (256 B per edge instead of 512): Q_bf16 = bf16(Q) prepared by the caller. */
+int gmp_egnn_tc_edge_fwd(const int32_t* rowptr, const int32_t* col, const int32_t* rowid, int64_t n, int64_t num_edges,
+                         const float* P, const void* Q_bf16, const float* pos,
+                         const gmp_egnn_edge_params* prm /* host */, float* msg_aggr, float* pos_aggr,
+                         gmp_stream_t stream);
+/* Backward, two recompute passes as gmp_egnn_edge_bwd.  row_operand (fp32) / col_operand_bf16 are P / bf16(Q) in the
+ * dst pass (src_pass = 0) and Q / bf16(P) in the src pass.  Both passes write per-CTA partials into the SAME
+ * wgrad_parts [gmp_egnn_tc_bwd_num_parts(E)][gmp_egnn_bwd_part_len(128)]: the dst pass the two weight matrices
+ * (dpre^T a1, dpre^T m accumulated in tensor memory), the src pass the ten vectors (column sums through the tensor
+ * core) and db3; sum them with gmp_reduce_partials_f32. */
+int32_t gmp_egnn_tc_bwd_num_parts(int64_t num_edges);
+int gmp_egnn_tc_edge_bwd(const int32_t* rowptr, const int32_t* col, const int32_t* rowid, const int32_t* dst_rowptr,
+                         int64_t n, int64_t num_edges, const float* row_operand, const void* col_operand_bf16,
+                         const float* pos, const gmp_egnn_edge_params* prm /* host */, const float* g_msg,
+                         const float* g_pos, int32_t src_pass, float* d_node, float* d_pos, float* wgrad_parts,
+                         gmp_stream_t stream);
+
 /* ============================================================================================ */
 /* TFN / MACE tensor-product convolution (models/layers/tfn_layer.py:82-87)                       */
 /* ============================================================================================ */
