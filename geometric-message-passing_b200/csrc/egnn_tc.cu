@@ -306,6 +306,35 @@ __device__ __forceinline__ float img_at(const uint8_t* img, int r, int col) {
     return __uint_as_float((uint32_t)h << 16);
 }
 
+// Segmented sums of one value column over the tile's edge slots, in groups of 8: a plain tree add while the group stays in
+// the open row (the common case), edge by edge across a row change.  rid = CSR row of every slot; get(k) = value of slot k;
+// flush(row, sum) stores a finished row (rows without edges are flushed with 0).
+template <class Get, class Flush>
+__device__ __forceinline__ void gx_walk(const int* __restrict__ rid, int cnt, int& cur, float& acc, Get get, Flush flush) {
+    for (int k0 = 0; k0 < cnt; k0 += 8) {
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = (k0 + j < cnt) ? get(k0 + j) : 0.f;
+        if (rid[min(k0 + 7, cnt - 1)] == cur) {
+            acc += ((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7]));
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                if (k0 + j < cnt) {
+                    const int r = rid[k0 + j];
+                    if (r != cur) {
+                        flush(cur, acc);
+                        for (int z = cur + 1; z < r; ++z) flush(z, 0.f);
+                        acc = 0.f;
+                        cur = r;
+                    }
+                    acc += v[j];
+                }
+            }
+        }
+    }
+}
+
 template <int ACT>
 __global__ void __launch_bounds__(256, 1) egnn_fwd_tc_kernel(EgnnTcArgs a, float* __restrict__ msg_aggr, float* __restrict__ pos_aggr) {
     extern __shared__ __align__(16) uint8_t smraw[];
@@ -319,41 +348,32 @@ __global__ void __launch_bounds__(256, 1) egnn_fwd_tc_kernel(EgnnTcArgs a, float
         if (r0 >= r1) continue;
         const int64_t eb = __ldg(a.rowptr + r0), ee = __ldg(a.rowptr + r1);
         int cur = r0;
-        int64_t row_beg = eb, row_end = __ldg(a.rowptr + r0 + 1);
         float acc = 0.f;
         const int role = t < kGF ? 0 : (t < kGF + 3 ? 1 : 2);  // 0: feature column, 1: coordinate, 2: idle
         const int comp = t - kGF;
+        auto flush = [&](int row, float v) {
+            const float deg = (float)(__ldg(a.rowptr + row + 1) - __ldg(a.rowptr + row));
+            if (role == 0) msg_aggr[(int64_t)row * kGF + t] = (a.aggr_mean && deg > 0.f) ? v / deg : v;
+            else pos_aggr[(int64_t)row * 3 + comp] = deg > 0.f ? v / deg : 0.f;
+        };
         for (int64_t e0 = eb; e0 < ee; e0 += kGT) {
             const int cnt = (int)min((int64_t)kGT, ee - e0);
             egnn_tc_tile_forward<ACT, false>(c, a, e0, cnt);
-            if (role != 2) {
-                for (int tt = 0; tt < cnt; ++tt) {
-                    const int64_t ed = e0 + tt;
-                    while (ed >= row_end) {
-                        const float deg = (float)(row_end - row_beg);
-                        if (role == 0) msg_aggr[(int64_t)cur * kGF + t] = (a.aggr_mean && deg > 0.f) ? acc / deg : acc;
-                        else pos_aggr[(int64_t)cur * 3 + comp] = deg > 0.f ? acc / deg : 0.f;
-                        acc = 0.f;
-                        ++cur;
-                        row_beg = row_end;
-                        row_end = __ldg(a.rowptr + cur + 1);
-                    }
-                    if (role == 0) acc += img_at(sm + oGM, tt, t);
-                    else acc += c.sc[(TS_DX + comp) * kGT + tt] * c.sc[TS_S * kGT + tt];
-                }
+            if (role == 0) {
+                // element (slot k, column t) of the swizzled m image: chunk index XOR (k & 7), 128 B per slot
+                const uint8_t* base = sm + oGM + (t >> 6) * 16384 + (t & 7) * 2;
+                const int ch = (t & 63) >> 3;
+                gx_walk(c.ints, cnt, cur, acc,
+                        [&](int k) { return __uint_as_float((uint32_t)(*reinterpret_cast<const uint16_t*>(base + k * 128 + ((ch ^ (k & 7)) << 4))) << 16); },
+                        flush);
+            } else if (role == 1) {
+                gx_walk(c.ints, cnt, cur, acc, [&](int k) { return c.sc[(TS_DX + comp) * kGT + k] * c.sc[TS_S * kGT + k]; }, flush);
             }
             __syncthreads();  // the tile buffers are free again
         }
         if (role != 2) {
-            while (cur < r1) {
-                const float deg = (float)(row_end - row_beg);
-                if (role == 0) msg_aggr[(int64_t)cur * kGF + t] = (a.aggr_mean && deg > 0.f) ? acc / deg : acc;
-                else pos_aggr[(int64_t)cur * 3 + comp] = deg > 0.f ? acc / deg : 0.f;
-                acc = 0.f;
-                ++cur;
-                row_beg = row_end;
-                if (cur < r1) row_end = __ldg(a.rowptr + cur + 1);
-            }
+            flush(cur, acc);
+            for (int z = cur + 1; z < r1; ++z) flush(z, 0.f);
         }
     }
     tc_fence_before();
@@ -421,10 +441,13 @@ egnn_bwd_tc_kernel(EgnnTcArgs a, const float* __restrict__ g_msg, const float* _
         if (r0 >= r1) continue;
         const int64_t eb = __ldg(a.rowptr + r0), ee = __ldg(a.rowptr + r1);
         int cur = r0;
-        int64_t row_end = __ldg(a.rowptr + r0 + 1);
         float acc = 0.f;
         const int role = t < kGF ? 0 : (t < kGF + 3 ? 1 : 2);
         const int comp = t - kGF;
+        auto flush = [&](int row, float v) {
+            if (role == 0) dnode[(int64_t)row * kGF + t] = v;
+            else dpos[(int64_t)row * 3 + comp] = SRC ? -v : v;
+        };
         for (int64_t e0 = eb; e0 < ee; e0 += kGT) {
             const int cnt = (int)min((int64_t)kGT, ee - e0);
             egnn_tc_tile_forward<ACT, SRC>(c, a, e0, cnt);
@@ -658,34 +681,18 @@ egnn_bwd_tc_kernel(EgnnTcArgs a, const float* __restrict__ g_msg, const float* _
             }
             acc_w = true;
             // ---- segmented sums over the CSR rows: d(pre1) -> dP (dst pass) / dQ (src pass); d(delta) -> dpos
-            if (role != 2) {
-                for (int tt = 0; tt < cnt; ++tt) {
-                    const int64_t ed = e0 + tt;
-                    while (ed >= row_end) {
-                        if (role == 0) dnode[(int64_t)cur * kGF + t] = acc;
-                        else dpos[(int64_t)cur * 3 + comp] = SRC ? -acc : acc;
-                        acc = 0.f;
-                        ++cur;
-                        row_end = __ldg(a.rowptr + cur + 1);
-                    }
-                    if (role == 0) {
-                        const uint16_t hv = *reinterpret_cast<const uint16_t*>(sm + oGG + tt * kGLd + t * 2);
-                        acc += __uint_as_float((uint32_t)hv << 16);
-                    } else {
-                        acc += sc[(TS_GX + comp) * kGT + tt];
-                    }
-                }
+            if (role == 0) {
+                gx_walk(c.ints, cnt, cur, acc,
+                        [&](int k) { return __uint_as_float((uint32_t)(*reinterpret_cast<const uint16_t*>(sm + oGG + k * kGLd + t * 2)) << 16); }, flush);
+            } else if (role == 1) {
+                gx_walk(c.ints, cnt, cur, acc, [&](int k) { return sc[(TS_GX + comp) * kGT + k]; }, flush);
             }
             if (SRC) gx_mma_wait(c);
             __syncthreads();
         }
         if (role != 2) {
-            while (cur < r1) {
-                if (role == 0) dnode[(int64_t)cur * kGF + t] = acc;
-                else dpos[(int64_t)cur * 3 + comp] = SRC ? -acc : acc;
-                acc = 0.f;
-                ++cur;
-            }
+            flush(cur, acc);
+            for (int z = cur + 1; z < r1; ++z) flush(z, 0.f);
         }
     }
     // ---- per-CTA partial parameter gradients out of tensor memory (zeros when this CTA saw no tile)

@@ -69,3 +69,12 @@ if __name__ == "__main__":
         check("swish", "mean", n=1000, side=5.0, bwd=len(sys.argv) > 2)
     else:
         timing(bwd=len(sys.argv) > 2)
+    if mode == "prof":
+        pos, ei = make(32.0, 2 ** 18)
+        m = gmp_b200.EGNNLayer(128, precision="bf16").cuda()
+        h = torch.randn(pos.shape[0], 128, device="cuda", requires_grad=True)
+        p = pos.clone().requires_grad_(True)
+        for _ in range(2):
+            o, q = m(h, p, ei)
+            (o.sum() + q.sum()).backward()
+        torch.cuda.synchronize()

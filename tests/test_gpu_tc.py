@@ -96,3 +96,46 @@ def test_tp_conv_bf16_tc_vs_fp32(C, gate, graphs, nodes, shuffle, mlp):
     for a, b, name in zip(g16, g32, ["node_attr"] + [k for k, _ in m32.named_parameters()]):
         assert rel_err(a, b) <= 1e-2, name
     assert torch.equal(o16, m16(x16, ei, esh, eft))  # deterministic
+
+
+def _l2_rel(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+@pytest.mark.parametrize("act,aggr,n,side", [("swish", "mean", 1000, 5.0), ("swish", "add", 3000, 7.0), ("relu", "add", 3000, 7.0)])
+def test_egnn_bf16_tc_vs_fp32(act, aggr, n, side):
+    """EGNN layer, tcgen05 edge kernels (forward + both backward passes) against the fp32-strict kernels.
+    Smooth activation: every output and gradient within 1e-2 (normwise, max).  ReLU: the forward holds 1e-2; its
+    gradients are compared in the L2 norm with a 0.1 bound, because a bf16-level perturbation of a pre-activation that
+    sits at the kink flips that unit's derivative -- the fp32 reference shows the same sensitivity (mlp_upd, a pure
+    fp32 torch path, moves by 2-3e-2 when its input moves by 2e-3)."""
+    import gmp_b200
+    g = torch.Generator().manual_seed(n)
+    pos = (torch.rand(n, 3, generator=g) * side).cuda()
+    ei = gmp_b200.radius_graph(pos, 1.0, None, max_num_neighbors=128)
+    torch.manual_seed(1)
+    m32 = gmp_b200.EGNNLayer(128, activation=act, aggr=aggr).cuda()
+    with torch.no_grad():
+        for p in m32.parameters():
+            if p.dim() == 1:
+                p.add_(torch.randn_like(p) * 0.2)
+    m16 = gmp_b200.EGNNLayer(128, activation=act, aggr=aggr, precision="bf16").cuda()
+    m16.load_state_dict(m32.state_dict())
+    h = torch.randn(n, 128, device="cuda")
+    h32, h16 = h.clone().requires_grad_(True), h.clone().requires_grad_(True)
+    p32, p16 = pos.clone().requires_grad_(True), pos.clone().requires_grad_(True)
+    o32, q32 = m32(h32, p32, ei)
+    o16, q16 = m16(h16, p16, ei)
+    assert rel_err(o16, o32) <= 1e-2 and rel_err(q16 - pos, q32 - pos) <= 1e-2
+    c1, c2 = torch.randn_like(o32), torch.randn_like(q32)
+    g32 = torch.autograd.grad((o32 * c1).sum() + (q32 * c2).sum(), [h32, p32] + list(m32.parameters()))
+    g16 = torch.autograd.grad((o16 * c1).sum() + (q16 * c2).sum(), [h16, p16] + list(m16.parameters()))
+    names = ["h", "pos"] + [k for k, _ in m32.named_parameters()]
+    for a, b, k in zip(g16, g32, names):
+        if act == "swish":
+            assert rel_err(a, b) <= 1e-2, k
+        else:
+            assert _l2_rel(a, b) <= 0.1, k
+    o16b, q16b = m16(h16, p16, ei)
+    assert torch.equal(o16, o16b) and torch.equal(q16, q16b)  # deterministic
