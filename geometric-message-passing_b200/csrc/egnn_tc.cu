@@ -3,8 +3,8 @@
 // Same mathematics and work decomposition as egnn.cu (pre1 = P[i] + Q[j] + dist * wd, three LayerNorm'd stages, whole CSR
 // rows per work range, two recompute passes backward), with 128-edge tiles and both 128 x 128 edge GEMMs -- and in the
 // backward their data- and weight-gradient GEMMs -- on tcgen05.mma with fp32 accumulators in tensor memory:
-//   a thread owns (edge row e = TMEM lane, column half hf): it reads its 64 pre-activations straight out of tensor
-//   memory, LayerNorm statistics are completed by exchanging two partial sums with the thread that owns the other half,
+//   a thread owns (edge row e = TMEM lane, column quarter hf): it reads its 32 pre-activations straight out of tensor
+//   memory, LayerNorm statistics are completed by exchanging two partial sums with the threads that own the other quarters,
 //   and the next operand (bf16, 128B-swizzled K-major image, row = edge) is written in place for the next MMA.
 // The gathered operand (Q[j] in the dst pass, P[i] in the src pass) is read as bf16 rows with cp.async (256 B per edge);
 // the row-constant operand is read in fp32.  bf16 operands / fp32 accumulation: 1e-2 relative (tests/test_gpu_tc.py).
@@ -20,6 +20,9 @@ using namespace tc;
 constexpr int kGF = 128;         // emb_dim
 constexpr int kGT = 128;         // edges per tile
 constexpr int kGRange = 2048;    // edges per work range (whole rows)
+constexpr int kGQ = 4;          // column quarters: a thread owns (edge row, 32 columns); 16 warps per CTA
+constexpr int kGCW = 32;        // columns per thread
+constexpr int kGThreads = 512;
 constexpr int kGLd = 272;        // byte stride of a bf16 row in the gather tile (conflict-free 16-byte chunks per row)
 
 struct EgnnTcArgs {
@@ -44,8 +47,8 @@ constexpr int oGOnes = oGG + kGT * kGLd;       // 4 KB of bf16 ones (column sums
 constexpr int oGVec = oGOnes + 4096;           // wd g1 be1 b1 g2 be2 b2 g3 be3 w3
 constexpr int oGSc = oGVec + 10 * kGF * 4;     // per-edge scalars [16][128]
 constexpr int oGInt = oGSc + 16 * kGT * 4;     // rrow[128] gcol[128] inode[128]
-constexpr int oGRed = oGInt + 3 * kGT * 4;     // partial-sum exchange: 2 buffers x [2 halves][128] float2
-constexpr int oGBar = oGRed + 2 * 2 * kGT * 8; // mbarrier + tmem pointer
+constexpr int oGRed = oGInt + 3 * kGT * 4;     // partial-sum exchange: 2 buffers x [4 quarters][128] float2
+constexpr int oGBar = oGRed + 2 * kGQ * kGT * 8; // mbarrier + tmem pointer
 constexpr int kEgnnTcSmem = oGBar + 64 + 1024;
 
 enum { TV_WD = 0, TV_G1, TV_BE1, TV_B1, TV_G2, TV_BE2, TV_B2, TV_G3, TV_BE3, TV_W3 };
@@ -70,14 +73,20 @@ struct GCtx {
     int t, warp, e, hf;
 };
 
-// complete a per-row partial (two floats per half) with the thread that owns the other column half
+// complete a per-row partial (two floats per quarter) with the threads that own the other column quarters
 __device__ __forceinline__ float2 gx_exchange(GCtx& c, float a, float b) {
-    float2* red = reinterpret_cast<float2*>(c.sm + oGRed) + (c.xb & 1u) * 2 * kGT;
+    float2* red = reinterpret_cast<float2*>(c.sm + oGRed) + (c.xb & 1u) * kGQ * kGT;
     red[c.hf * kGT + c.e] = make_float2(a, b);
-    __syncthreads();
-    const float2 o = red[(c.hf ^ 1) * kGT + c.e];
+    bar_sync_named(1 + (c.warp & 3), 32 * kGQ);  // only the four warps that share these 32 rows (w, w+4, w+8, w+12) meet here
+    float2 tot = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int p = 0; p < kGQ; ++p) {  // fixed order: every quarter computes the same bits
+        const float2 o = red[p * kGT + c.e];
+        tot.x += o.x;
+        tot.y += o.y;
+    }
     ++c.xb;
-    return make_float2(a + o.x, b + o.y);
+    return tot;
 }
 
 __device__ __forceinline__ void unpack8(const uint4 u, float (&f)[8]) {
@@ -97,17 +106,16 @@ __device__ __forceinline__ void gx_mma_wait(GCtx& c) {
     tc_fence_after();
 }
 
-// 64 accumulator columns of this thread's row: columns [64*hf, 64*hf + 64) of the 128-column block at `tcol`
-__device__ __forceinline__ void gx_ld64(const GCtx& c, uint32_t tcol, float (&v)[64]) {
-    tmem_ld32(c.tm + c.lane_base + tcol + 64 * c.hf, *reinterpret_cast<float(*)[32]>(&v[0]));
-    tmem_ld32(c.tm + c.lane_base + tcol + 64 * c.hf + 32, *reinterpret_cast<float(*)[32]>(&v[32]));
+// this thread's 32 accumulator columns: [32*hf, 32*hf + 32) of the 128-column block at `tcol`
+__device__ __forceinline__ void gx_ld64(const GCtx& c, uint32_t tcol, float (&v)[kGCW]) {
+    tmem_ld32(c.tm + c.lane_base + tcol + kGCW * c.hf, v);
 }
 
-// LayerNorm statistics of the row from this half's 64 values (single pass, completed across the halves)
-__device__ __forceinline__ void gx_stats(GCtx& c, const float (&x)[64], float eps, float& mean, float& rstd) {
+// LayerNorm statistics of the row from this quarter's 32 values (single pass, completed across the quarters)
+__device__ __forceinline__ void gx_stats(GCtx& c, const float (&x)[kGCW], float eps, float& mean, float& rstd) {
     float s = 0.f, q = 0.f;
 #pragma unroll
-    for (int k = 0; k < 64; ++k) { s += x[k]; q = fmaf(x[k], x[k], q); }
+    for (int k = 0; k < kGCW; ++k) { s += x[k]; q = fmaf(x[k], x[k], q); }
     const float2 tot = gx_exchange(c, s, q);
     mean = tot.x * (1.f / kGF);
     const float var = fmaxf(tot.y * (1.f / kGF) - mean * mean, 0.f);
@@ -142,7 +150,7 @@ __device__ __forceinline__ void egnn_tc_tile_forward(GCtx& c, const EgnnTcArgs& 
     }
     __syncthreads();
     // ---- gather: bf16 rows of the col-side operand
-    for (int x = t; x < kGT * 16; x += 256) {
+    for (int x = t; x < kGT * 16; x += kGThreads) {
         const int r = x >> 4, ch = x & 15;
         uint8_t* dst = sm + oGG + r * kGLd + ch * 16;
         if (r < cnt) __pipeline_memcpy_async(dst, a.gath + (int64_t)c.ints[kGT + r] * kGF + ch * 8, 16);
@@ -153,14 +161,14 @@ __device__ __forceinline__ void egnn_tc_tile_forward(GCtx& c, const EgnnTcArgs& 
     __syncthreads();
     // ---- stage 1: pre1 = gathered + row operand + dist * wd -> LN1 -> xhat1 (G, in place), a1 (A1)
     {
-        float x[64];
+        float x[kGCW];
         const float dist = sc[TS_DIST * kGT + e];
-        const float4* rp = reinterpret_cast<const float4*>(a.rowt + (int64_t)c.ints[e] * kGF + 64 * hf);
-        const float4* wd4 = reinterpret_cast<const float4*>(vec + TV_WD * kGF + 64 * hf);
+        const float4* rp = reinterpret_cast<const float4*>(a.rowt + (int64_t)c.ints[e] * kGF + kGCW * hf);
+        const float4* wd4 = reinterpret_cast<const float4*>(vec + TV_WD * kGF + kGCW * hf);
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
+        for (int q = 0; q < 4; ++q) {
             float g[8];
-            unpack8(*reinterpret_cast<const uint4*>(sm + oGG + e * kGLd + (8 * hf + q) * 16), g);
+            unpack8(*reinterpret_cast<const uint4*>(sm + oGG + e * kGLd + (4 * hf + q) * 16), g);
             const float4 r0 = __ldg(rp + 2 * q), r1 = __ldg(rp + 2 * q + 1), w0 = wd4[2 * q], w1 = wd4[2 * q + 1];
             x[8 * q + 0] = g[0] + r0.x + dist * w0.x; x[8 * q + 1] = g[1] + r0.y + dist * w0.y;
             x[8 * q + 2] = g[2] + r0.z + dist * w0.z; x[8 * q + 3] = g[3] + r0.w + dist * w0.w;
@@ -171,16 +179,16 @@ __device__ __forceinline__ void egnn_tc_tile_forward(GCtx& c, const EgnnTcArgs& 
         gx_stats(c, x, a.eps, mean, rstd);
         if (hf == 0) sc[TS_R1 * kGT + e] = rstd;
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
+        for (int q = 0; q < 4; ++q) {
             float xh[8], a1[8];
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
-                const int col = 64 * hf + 8 * q + u;
+                const int col = kGCW * hf + 8 * q + u;
                 xh[u] = (x[8 * q + u] - mean) * rstd;
                 a1[u] = tact<ACT>(fmaf(xh[u], vec[TV_G1 * kGF + col], vec[TV_BE1 * kGF + col]));
             }
-            *reinterpret_cast<uint4*>(sm + oGG + e * kGLd + (8 * hf + q) * 16) = pack8(xh);
-            *reinterpret_cast<uint4*>(sm + oGA1 + hf * 16384 + sw128_chunk_off(e, q)) = pack8(a1);
+            *reinterpret_cast<uint4*>(sm + oGG + e * kGLd + (4 * hf + q) * 16) = pack8(xh);
+            *reinterpret_cast<uint4*>(sm + oGA1 + (hf >> 1) * 16384 + sw128_chunk_off(e, (hf & 1) * 4 + q)) = pack8(a1);
         }
     }
     fence_proxy_async();
@@ -198,22 +206,22 @@ __device__ __forceinline__ void egnn_tc_tile_forward(GCtx& c, const EgnnTcArgs& 
     gx_mma_wait(c);
     // ---- stage 2: pre2 = D1 + b1 -> LN2 -> m (M)
     {
-        float x[64];
+        float x[kGCW];
         gx_ld64(c, 0, x);
 #pragma unroll
-        for (int k = 0; k < 64; ++k) x[k] += vec[TV_B1 * kGF + 64 * hf + k];
+        for (int k = 0; k < kGCW; ++k) x[k] += vec[TV_B1 * kGF + kGCW * hf + k];
         float mean, rstd;
         gx_stats(c, x, a.eps, mean, rstd);
         if (hf == 0) { sc[TS_M2 * kGT + e] = mean; sc[TS_R2 * kGT + e] = rstd; }
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
+        for (int q = 0; q < 4; ++q) {
             float m[8];
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
-                const int col = 64 * hf + 8 * q + u;
+                const int col = kGCW * hf + 8 * q + u;
                 m[u] = tact<ACT>(fmaf((x[8 * q + u] - mean) * rstd, vec[TV_G2 * kGF + col], vec[TV_BE2 * kGF + col]));
             }
-            *reinterpret_cast<uint4*>(sm + oGM + hf * 16384 + sw128_chunk_off(e, q)) = pack8(m);
+            *reinterpret_cast<uint4*>(sm + oGM + (hf >> 1) * 16384 + sw128_chunk_off(e, (hf & 1) * 4 + q)) = pack8(m);
         }
     }
     fence_proxy_async();
@@ -230,16 +238,16 @@ __device__ __forceinline__ void egnn_tc_tile_forward(GCtx& c, const EgnnTcArgs& 
     gx_mma_wait(c);
     // ---- stage 3: pre3 = D2 + b2 -> LN3 -> s = act(.) . w3 + b3
     {
-        float x[64];
+        float x[kGCW];
         gx_ld64(c, 128, x);
 #pragma unroll
-        for (int k = 0; k < 64; ++k) x[k] += vec[TV_B2 * kGF + 64 * hf + k];
+        for (int k = 0; k < kGCW; ++k) x[k] += vec[TV_B2 * kGF + kGCW * hf + k];
         float mean, rstd;
         gx_stats(c, x, a.eps, mean, rstd);
         float dot = 0.f;
 #pragma unroll
-        for (int k = 0; k < 64; ++k) {
-            const int col = 64 * hf + k;
+        for (int k = 0; k < kGCW; ++k) {
+            const int col = kGCW * hf + k;
             dot = fmaf(tact<ACT>(fmaf((x[k] - mean) * rstd, vec[TV_G3 * kGF + col], vec[TV_BE3 * kGF + col])), vec[TV_W3 * kGF + col], dot);
         }
         const float2 tot = gx_exchange(c, dot, 0.f);
@@ -257,7 +265,7 @@ __device__ __forceinline__ void egnn_tc_tile_forward(GCtx& c, const EgnnTcArgs& 
 template <int NCOLS>
 __device__ __forceinline__ void egnn_tc_setup(GCtx& c, const EgnnTcArgs& a, uint8_t* sm) {
     const int t = threadIdx.x;
-    for (int x = t; x < kGF * 16; x += 256) {
+    for (int x = t; x < kGF * 16; x += kGThreads) {
         const int f = x >> 4, ch16 = x & 15, kb = ch16 >> 3, ch = ch16 & 7;
         {
             const float4 lo = ldg4(a.w1 + f * kGF + kb * 64 + ch * 8), hi = ldg4(a.w1 + f * kGF + kb * 64 + ch * 8 + 4);
@@ -272,8 +280,8 @@ __device__ __forceinline__ void egnn_tc_setup(GCtx& c, const EgnnTcArgs& a, uint
     }
     float* vec = reinterpret_cast<float*>(sm + oGVec);
     const float* vecs[10] = {a.wd, a.g1, a.be1, a.b1, a.g2, a.be2, a.b2, a.g3, a.be3, a.w3};
-    for (int i = t; i < 10 * kGF; i += 256) vec[i] = __ldg(vecs[i / kGF] + (i % kGF));
-    for (int i = t; i < 2048; i += 256) reinterpret_cast<uint16_t*>(sm + oGOnes)[i] = 0x3f80;  // bf16 1.0
+    for (int i = t; i < 10 * kGF; i += kGThreads) vec[i] = __ldg(vecs[i / kGF] + (i % kGF));
+    for (int i = t; i < 2048; i += kGThreads) reinterpret_cast<uint16_t*>(sm + oGOnes)[i] = 0x3f80;  // bf16 1.0
     uint64_t* bar = reinterpret_cast<uint64_t*>(sm + oGBar);
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(sm + oGBar + 16);
     if (t == 0) {
@@ -336,7 +344,7 @@ __device__ __forceinline__ void gx_walk(const int* __restrict__ rid, int cnt, in
 }
 
 template <int ACT>
-__global__ void __launch_bounds__(256, 1) egnn_fwd_tc_kernel(EgnnTcArgs a, float* __restrict__ msg_aggr, float* __restrict__ pos_aggr) {
+__global__ void __launch_bounds__(kGThreads, 1) egnn_fwd_tc_kernel(EgnnTcArgs a, float* __restrict__ msg_aggr, float* __restrict__ pos_aggr) {
     extern __shared__ __align__(16) uint8_t smraw[];
     uint8_t* sm = smraw + ((1024u - (smem_u32(smraw) & 1023u)) & 1023u);
     GCtx c;
@@ -422,7 +430,7 @@ __device__ __forceinline__ void gx_colsum(const GCtx& c, int vidx, int a_off, bo
 enum { VG_DB1 = 0, VG_DB2, VG_DG1, VG_DBE1, VG_DG2, VG_DBE2, VG_DG3, VG_DBE3, VG_DW3, VG_DWD };
 
 template <int ACT, bool SRC>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(kGThreads, 1)
 egnn_bwd_tc_kernel(EgnnTcArgs a, const float* __restrict__ g_msg, const float* __restrict__ g_pos, float* __restrict__ dnode,
                    float* __restrict__ dpos, float* __restrict__ parts) {
     extern __shared__ __align__(16) uint8_t smraw[];
@@ -473,21 +481,21 @@ egnn_bwd_tc_kernel(EgnnTcArgs a, const float* __restrict__ g_msg, const float* _
             if (SRC && hf == 0 && live) db3 += ds;
             // ================= stage 3 backward =================
             if (SRC) {  // first the two tiles that do not need the row statistics of dy: ds * a3 (dw3) and dy (dbe3)
-                float x[64];
+                float x[kGCW];
                 gx_ld64(c, 128, x);
                 const float mean = sc[TS_M3 * kGT + e], rstd = sc[TS_R3 * kGT + e];
 #pragma unroll
-                for (int q = 0; q < 8; ++q) {
+                for (int q = 0; q < 4; ++q) {
                     float ta[8], tb[8];
 #pragma unroll
                     for (int u = 0; u < 8; ++u) {
-                        const int col = 64 * hf + 8 * q + u;
+                        const int col = kGCW * hf + 8 * q + u;
                         const float y = fmaf((x[8 * q + u] + vec[TV_B2 * kGF + col] - mean) * rstd, vec[TV_G3 * kGF + col], vec[TV_BE3 * kGF + col]);
                         ta[u] = live ? ds * tact<ACT>(y) : 0.f;
                         tb[u] = live ? ds * vec[TV_W3 * kGF + col] * tdact<ACT>(y) : 0.f;
                     }
-                    *reinterpret_cast<uint4*>(sm + oGA1 + hf * 16384 + sw128_chunk_off(e, q)) = pack8(ta);
-                    *reinterpret_cast<uint4*>(sm + oGM + hf * 16384 + sw128_chunk_off(e, q)) = pack8(tb);
+                    *reinterpret_cast<uint4*>(sm + oGA1 + (hf >> 1) * 16384 + sw128_chunk_off(e, (hf & 1) * 4 + q)) = pack8(ta);
+                    *reinterpret_cast<uint4*>(sm + oGM + (hf >> 1) * 16384 + sw128_chunk_off(e, (hf & 1) * 4 + q)) = pack8(tb);
                 }
                 gx_issue_begin(c);
                 if (c.warp == 0) {
@@ -502,16 +510,16 @@ egnn_bwd_tc_kernel(EgnnTcArgs a, const float* __restrict__ g_msg, const float* _
                 gx_mma_wait(c);
             }
             {
-                float x[64], d[64];
+                float x[kGCW], d[kGCW];
                 gx_ld64(c, 128, x);
                 const float mean = sc[TS_M3 * kGT + e], rstd = sc[TS_R3 * kGT + e];
                 float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-                for (int q = 0; q < 8; ++q) {
+                for (int q = 0; q < 4; ++q) {
                     float tg[8];
 #pragma unroll
                     for (int u = 0; u < 8; ++u) {
-                        const int k = 8 * q + u, col = 64 * hf + k;
+                        const int k = 8 * q + u, col = kGCW * hf + k;
                         const float xh = (x[k] + vec[TV_B2 * kGF + col] - mean) * rstd;
                         const float y = fmaf(xh, vec[TV_G3 * kGF + col], vec[TV_BE3 * kGF + col]);
                         const float dy = ds * vec[TV_W3 * kGF + col] * tdact<ACT>(y);
@@ -521,17 +529,17 @@ egnn_bwd_tc_kernel(EgnnTcArgs a, const float* __restrict__ g_msg, const float* _
                         s1 += d[k];
                         s2 = fmaf(d[k], xh, s2);
                     }
-                    if (SRC) *reinterpret_cast<uint4*>(sm + oGA1 + hf * 16384 + sw128_chunk_off(e, q)) = pack8(tg);
+                    if (SRC) *reinterpret_cast<uint4*>(sm + oGA1 + (hf >> 1) * 16384 + sw128_chunk_off(e, (hf & 1) * 4 + q)) = pack8(tg);
                 }
                 const float2 tot = gx_exchange(c, s1, s2);
                 s1 = tot.x * (1.f / kGF);
                 s2 = tot.y * (1.f / kGF);
 #pragma unroll
-                for (int q = 0; q < 8; ++q) {
+                for (int q = 0; q < 4; ++q) {
                     float o[8];
 #pragma unroll
                     for (int u = 0; u < 8; ++u) o[u] = live ? rstd * (d[8 * q + u] - s1 - x[8 * q + u] * s2) : 0.f;
-                    *reinterpret_cast<uint4*>(sm + oGDT + hf * 16384 + sw128_chunk_off(e, q)) = pack8(o);
+                    *reinterpret_cast<uint4*>(sm + oGDT + (hf >> 1) * 16384 + sw128_chunk_off(e, (hf & 1) * 4 + q)) = pack8(o);
                 }
             }
             gx_issue_begin(c);
@@ -552,14 +560,14 @@ egnn_bwd_tc_kernel(EgnnTcArgs a, const float* __restrict__ g_msg, const float* _
             gx_mma_wait(c);
             // ================= stage 2 backward =================
             {
-                float x[64], d[64];
+                float x[kGCW], d[kGCW];
                 gx_ld64(c, 0, x);      // pre2 - b1
                 gx_ld64(c, 128, d);    // dm
                 const float mean = sc[TS_M2 * kGT + e], rstd = sc[TS_R2 * kGT + e], scale = sc[TS_SCALE * kGT + e];
-                const float4* gm = reinterpret_cast<const float4*>(g_msg + (int64_t)c.ints[2 * kGT + e] * kGF + 64 * hf);
+                const float4* gm = reinterpret_cast<const float4*>(g_msg + (int64_t)c.ints[2 * kGT + e] * kGF + kGCW * hf);
                 float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-                for (int q = 0; q < 8; ++q) {
+                for (int q = 0; q < 4; ++q) {
                     float tg[8], tb[8], up[8];
                     if (live) {
                         const float4 u0 = __ldg(gm + 2 * q), u1 = __ldg(gm + 2 * q + 1);
@@ -570,7 +578,7 @@ egnn_bwd_tc_kernel(EgnnTcArgs a, const float* __restrict__ g_msg, const float* _
                     }
 #pragma unroll
                     for (int u = 0; u < 8; ++u) {
-                        const int k = 8 * q + u, col = 64 * hf + k;
+                        const int k = 8 * q + u, col = kGCW * hf + k;
                         const float xh = (x[k] + vec[TV_B1 * kGF + col] - mean) * rstd;
                         const float y = fmaf(xh, vec[TV_G2 * kGF + col], vec[TV_BE2 * kGF + col]);
                         const float dy = live ? (d[k] + up[u] * scale) * tdact<ACT>(y) : 0.f;
@@ -582,19 +590,19 @@ egnn_bwd_tc_kernel(EgnnTcArgs a, const float* __restrict__ g_msg, const float* _
                         s2 = fmaf(d[k], xh, s2);
                     }
                     if (SRC) {
-                        *reinterpret_cast<uint4*>(sm + oGA1 + hf * 16384 + sw128_chunk_off(e, q)) = pack8(tg);
-                        *reinterpret_cast<uint4*>(sm + oGM + hf * 16384 + sw128_chunk_off(e, q)) = pack8(tb);
+                        *reinterpret_cast<uint4*>(sm + oGA1 + (hf >> 1) * 16384 + sw128_chunk_off(e, (hf & 1) * 4 + q)) = pack8(tg);
+                        *reinterpret_cast<uint4*>(sm + oGM + (hf >> 1) * 16384 + sw128_chunk_off(e, (hf & 1) * 4 + q)) = pack8(tb);
                     }
                 }
                 const float2 tot = gx_exchange(c, s1, s2);
                 s1 = tot.x * (1.f / kGF);
                 s2 = tot.y * (1.f / kGF);
 #pragma unroll
-                for (int q = 0; q < 8; ++q) {
+                for (int q = 0; q < 4; ++q) {
                     float o[8];
 #pragma unroll
                     for (int u = 0; u < 8; ++u) o[u] = live ? rstd * (d[8 * q + u] - s1 - x[8 * q + u] * s2) : 0.f;
-                    *reinterpret_cast<uint4*>(sm + oGDT + hf * 16384 + sw128_chunk_off(e, q)) = pack8(o);
+                    *reinterpret_cast<uint4*>(sm + oGDT + (hf >> 1) * 16384 + sw128_chunk_off(e, (hf & 1) * 4 + q)) = pack8(o);
                 }
             }
             gx_issue_begin(c);
@@ -616,17 +624,17 @@ egnn_bwd_tc_kernel(EgnnTcArgs a, const float* __restrict__ g_msg, const float* _
             gx_mma_wait(c);
             // ================= stage 1 backward =================
             {
-                float x[64], d[64];
+                float x[kGCW], d[kGCW];
                 gx_ld64(c, 0, d);  // da1
                 const float rstd = sc[TS_R1 * kGT + e], dist = sc[TS_DIST * kGT + e];
                 float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-                for (int q = 0; q < 8; ++q) {
+                for (int q = 0; q < 4; ++q) {
                     float xh[8], tg[8], tb[8];
-                    unpack8(*reinterpret_cast<const uint4*>(sm + oGG + e * kGLd + (8 * hf + q) * 16), xh);
+                    unpack8(*reinterpret_cast<const uint4*>(sm + oGG + e * kGLd + (4 * hf + q) * 16), xh);
 #pragma unroll
                     for (int u = 0; u < 8; ++u) {
-                        const int k = 8 * q + u, col = 64 * hf + k;
+                        const int k = 8 * q + u, col = kGCW * hf + k;
                         const float y = fmaf(xh[u], vec[TV_G1 * kGF + col], vec[TV_BE1 * kGF + col]);
                         const float dy = live ? d[k] * tdact<ACT>(y) : 0.f;
                         tg[u] = dy * xh[u];
@@ -637,8 +645,8 @@ egnn_bwd_tc_kernel(EgnnTcArgs a, const float* __restrict__ g_msg, const float* _
                         s2 = fmaf(d[k], xh[u], s2);
                     }
                     if (SRC) {
-                        *reinterpret_cast<uint4*>(sm + oGA1 + hf * 16384 + sw128_chunk_off(e, q)) = pack8(tg);
-                        *reinterpret_cast<uint4*>(sm + oGM + hf * 16384 + sw128_chunk_off(e, q)) = pack8(tb);
+                        *reinterpret_cast<uint4*>(sm + oGA1 + (hf >> 1) * 16384 + sw128_chunk_off(e, (hf & 1) * 4 + q)) = pack8(tg);
+                        *reinterpret_cast<uint4*>(sm + oGM + (hf >> 1) * 16384 + sw128_chunk_off(e, (hf & 1) * 4 + q)) = pack8(tb);
                     }
                 }
                 const float2 tot = gx_exchange(c, s1, s2);
@@ -646,16 +654,16 @@ egnn_bwd_tc_kernel(EgnnTcArgs a, const float* __restrict__ g_msg, const float* _
                 s2 = tot.y * (1.f / kGF);
                 float dd = 0.f;
 #pragma unroll
-                for (int q = 0; q < 8; ++q) {
+                for (int q = 0; q < 4; ++q) {
                     float o[8], od[8];
 #pragma unroll
                     for (int u = 0; u < 8; ++u) {
                         o[u] = live ? rstd * (d[8 * q + u] - s1 - x[8 * q + u] * s2) : 0.f;
                         od[u] = dist * o[u];
-                        dd = fmaf(o[u], vec[TV_WD * kGF + 64 * hf + 8 * q + u], dd);
+                        dd = fmaf(o[u], vec[TV_WD * kGF + kGCW * hf + 8 * q + u], dd);
                     }
-                    *reinterpret_cast<uint4*>(sm + oGG + e * kGLd + (8 * hf + q) * 16) = pack8(o);   // dpre1, for the column walkers
-                    if (SRC) *reinterpret_cast<uint4*>(sm + oGDT + hf * 16384 + sw128_chunk_off(e, q)) = pack8(od);
+                    *reinterpret_cast<uint4*>(sm + oGG + e * kGLd + (4 * hf + q) * 16) = pack8(o);   // dpre1, for the column walkers
+                    if (SRC) *reinterpret_cast<uint4*>(sm + oGDT + (hf >> 1) * 16384 + sw128_chunk_off(e, (hf & 1) * 4 + q)) = pack8(od);
                 }
                 const float2 dt = gx_exchange(c, dd, 0.f);
                 if (hf == 0) {
@@ -701,16 +709,16 @@ egnn_bwd_tc_kernel(EgnnTcArgs a, const float* __restrict__ g_msg, const float* _
     tc_fence_after();
     if (!SRC) {
         for (int w = 0; w < 2; ++w) {  // lane = output feature (row of W), columns = input features
-            float v[64];
+            float v[kGCW];
             gx_ld64(c, 256 + 128 * w, v);
-            float* dst = my + (int64_t)w * kGF * kGF + e * kGF + 64 * hf;
+            float* dst = my + (int64_t)w * kGF * kGF + e * kGF + kGCW * hf;
 #pragma unroll
-            for (int j = 0; j < 64; j += 4)
+            for (int j = 0; j < kGCW; j += 4)
                 *reinterpret_cast<float4*>(dst + j) = acc_w ? make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
     } else {
         float* vout = my + 2 * kGF * kGF;
-        for (int p = hf; p < 5; p += 2) {  // lane = feature column; vectors 2p and 2p+1 sit in accumulator columns 0 and 16
+        for (int p = hf; p < 5; p += kGQ) {  // lane = feature column; vectors 2p and 2p+1 sit in accumulator columns 0 and 16
             float v[32];
             tmem_ld32(c.tm + c.lane_base + 256 + 32 * p, v);
             vout[(2 * p) * kGF + e] = acc_w ? v[0] : 0.f;
@@ -770,10 +778,10 @@ int gmp_egnn_tc_edge_fwd(const int32_t* rowptr, const int32_t* col, const int32_
     const int grid = a.nranges < num_sms() ? a.nranges : num_sms();
     if (prm->act) {
         GMP_CUDA(cudaFuncSetAttribute(egnn_fwd_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kEgnnTcSmem));
-        egnn_fwd_tc_kernel<1><<<grid, 256, kEgnnTcSmem, stream>>>(a, msg_aggr, pos_aggr);
+        egnn_fwd_tc_kernel<1><<<grid, kGThreads, kEgnnTcSmem, stream>>>(a, msg_aggr, pos_aggr);
     } else {
         GMP_CUDA(cudaFuncSetAttribute(egnn_fwd_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kEgnnTcSmem));
-        egnn_fwd_tc_kernel<0><<<grid, 256, kEgnnTcSmem, stream>>>(a, msg_aggr, pos_aggr);
+        egnn_fwd_tc_kernel<0><<<grid, kGThreads, kEgnnTcSmem, stream>>>(a, msg_aggr, pos_aggr);
     }
     return check_launch("egnn_fwd_tc_kernel");
 }
@@ -796,7 +804,7 @@ int gmp_egnn_tc_edge_bwd(const int32_t* rowptr, const int32_t* col, const int32_
 #define GMP_EGNN_TC_BWD(A_, S_)                                                                                              \
     {                                                                                                                        \
         GMP_CUDA(cudaFuncSetAttribute(egnn_bwd_tc_kernel<A_, S_>, cudaFuncAttributeMaxDynamicSharedMemorySize, kEgnnTcSmem)); \
-        egnn_bwd_tc_kernel<A_, S_><<<grid, 256, kEgnnTcSmem, stream>>>(a, g_msg, g_pos, d_node, d_pos, wgrad_parts);         \
+        egnn_bwd_tc_kernel<A_, S_><<<grid, kGThreads, kEgnnTcSmem, stream>>>(a, g_msg, g_pos, d_node, d_pos, wgrad_parts);         \
     }
     if (prm->act) { if (src_pass) GMP_EGNN_TC_BWD(1, true) else GMP_EGNN_TC_BWD(1, false) }
     else { if (src_pass) GMP_EGNN_TC_BWD(0, true) else GMP_EGNN_TC_BWD(0, false) }
