@@ -136,6 +136,40 @@ class _CFConvFn(torch.autograd.Function):
         return dx1, d_ew, d_ea, dw1, db1, dw2, db2, None, None, None, None, None
 
 
+class _NodeLinearFn(torch.autograd.Function):
+    """y = x W^T + b with the parameter gradients (dW = g^T x, db = column sums of g: reductions over all nodes with
+    a 128 x 128 result) taken by gmp_linear_wgrad_tc: rows split over all SMs, bf16 operands on tcgen05, fp32 partials
+    summed in a fixed order.  The forward and dL/dx stay library GEMMs."""
+
+    @staticmethod
+    def forward(ctx, x, w, b):
+        ctx.save_for_backward(x, w)
+        ctx.has_bias = b is not None
+        return torch.nn.functional.linear(x, w, b)
+
+    @staticmethod
+    def backward(ctx, g):
+        x, w = ctx.saved_tensors
+        g = g.contiguous()
+        dx = g @ w if ctx.needs_input_grad[0] else None
+        out_f, in_f = w.shape
+        n = x.shape[0]
+        nparts, plen = _lib.lib().gmp_linear_wgrad_num_parts(n), out_f * in_f + out_f
+        parts = torch.empty(nparts, plen, dtype=g.dtype, device=g.device)
+        call("gmp_linear_wgrad_tc", ptr(g), ptr(x.contiguous()), n, out_f, in_f, ptr(parts))
+        red = torch.empty(plen, dtype=g.dtype, device=g.device)
+        call("gmp_reduce_partials_f32", ptr(parts), nparts, plen, ptr(red))
+        return dx, red[:out_f * in_f].view(out_f, in_f), (red[out_f * in_f:] if ctx.has_bias else None)
+
+
+def node_linear(lin: Linear, x: torch.Tensor, precision: str) -> torch.Tensor:
+    """nn.Linear on node rows; in the bf16 mode its weight / bias gradients come from the tensor-core reduction kernel."""
+    if (precision == "bf16" and x.is_cuda and x.dim() == 2 and x.shape[0] > 0 and x.dtype == torch.float32
+            and lin.out_features == 128 and lin.in_features in (64, 128)):
+        return _NodeLinearFn.apply(x, lin.weight, lin.bias)
+    return lin(x)
+
+
 class CFConv(nn.Module):
     """PyG ``CFConv`` (aggr='add', flow source_to_target): gather x1[edge_index[0]], reduce at edge_index[1]."""
 
@@ -155,7 +189,7 @@ class CFConv(nn.Module):
 
     def forward(self, x, edge_index, edge_weight, edge_attr):
         graph = get_graph(edge_index, x.shape[0])
-        x1 = self.lin1(x)
+        x1 = node_linear(self.lin1, x, self.precision)
         lin_a, lin_b = self.nn[0], self.nn[2]
         if isinstance(edge_attr, SmearedDistance):
             sm = edge_attr.smearing
@@ -164,7 +198,7 @@ class CFConv(nn.Module):
             attr, offset, coeff = edge_attr, x1.new_zeros(1), 0.0
         agg = _CFConvFn.apply(x1, edge_weight, attr, lin_a.weight, lin_a.bias, lin_b.weight, lin_b.bias, graph,
                               self.cutoff, offset, coeff, _PREC[self.precision])
-        return self.lin2(agg)
+        return node_linear(self.lin2, agg, self.precision)
 
 
 class InteractionBlock(nn.Module):
@@ -188,7 +222,7 @@ class InteractionBlock(nn.Module):
     def forward(self, x, edge_index, edge_weight, edge_attr):
         x = self.conv(x, edge_index, edge_weight, edge_attr)
         x = self.act(x)
-        return self.lin(x)
+        return node_linear(self.lin, x, self.conv.precision)
 
 
 def global_add_pool(x, batch, size: Optional[int] = None):

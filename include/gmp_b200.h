@@ -188,6 +188,14 @@ int gmp_umma_selftest(const float* A, const float* B, float* out, int32_t K, gmp
  * (the layout the weight-gradient GEMMs consume). */
 int gmp_umma_selftest_mn(const float* A, const float* B, float* out, int32_t N, gmp_stream_t stream);
 
+/* Parameter gradients of a node-side nn.Linear (PyG CFConv.lin1 / lin2, InteractionBlock.lin; called at
+ * models/schnet.py:72) in the GMP_BF16_TC mode: dW [out,in] = g^T x and db [out] = column sums of g, g [n,out], x [n,in],
+ * out = 128, in in {64,128}.  Rows are split over the SMs; parts [gmp_linear_wgrad_num_parts(n)][out*in + out] holds
+ * one partial (dW | db) per CTA: sum them with gmp_reduce_partials_f32. */
+int32_t gmp_linear_wgrad_num_parts(int64_t n);
+int gmp_linear_wgrad_tc(const float* g, const float* x, int64_t n, int32_t out_dim, int32_t in_dim, float* parts,
+                        gmp_stream_t stream);
+
 /* ============================================================================================ */
 /* EGNN edge path (models/layers/egnn_layer.py:62-80: message + aggregate, fused)                 */
 /* ============================================================================================ */
