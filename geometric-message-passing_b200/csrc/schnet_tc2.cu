@@ -1,0 +1,436 @@
+// SchNet CFConv forward, pipelined (GMP_BF16_TC, F = 128, lazily recomputed Gaussian basis): the warp-specialised
+// successor of schnet_fwd_tc_kernel.  Per tile of <= 128 destination-sorted edges (and <= 32 distinct rows):
+//
+//   warps 0-3   meta : edge scalars, cosine cutoff, row segments; cp.async gather of the bf16 x1[src] rows straight into
+//                      the swizzled operand image; Gaussian basis -> A1 (bf16)
+//   warp  12    MMA  : G1 = rbf W1^T -> D1;  G2 = h1 W2^T -> D2;  G3 = msg^T S -> D3   (tcgen05, accumulators in TMEM)
+//   warps 4-7   epi1 : D1 + b1 -> shifted softplus -> h1 (bf16) -> A2
+//   warps 8-11  epi2 : (D2 + b2) * C * x1[src] -> msg (bf16, in place over the gathered rows) and the one-hot
+//                      row-membership tile S; then, one tile behind, D3[c, seg] -> agg[row(seg), c] += ...
+//
+// The segmented sum over the destination rows is the third MMA: D3[c][s] = sum_e msg[e][c] * S[e][s] with S[e][s] = 1
+// when edge e belongs to the s-th row of the tile (both operands are read as MN-major images whose rows are edges).
+// Every (row, column) of agg is only ever touched by the one thread that owns the column in the one CTA that owns the
+// edge range, in tile order: deterministic, no atomics; agg is zeroed first and rows that straddle a CTA boundary go
+// through the head buffer + tp_tc_fixup_kernel-style fix-up (gmp_schnet_cfconv_fwd_tc2 does both).
+// Stages double-buffered: A1, gathered rows / msg, D1, D3; single: A2 (released per K slab), S, D2.
+#include <cuda_pipeline.h>
+
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace gmp {
+
+using namespace tc;
+
+constexpr int kS2Threads = 416;   // 13 warps
+constexpr int kS2MaxSeg = 32;
+
+struct Tc2Args {
+    const int32_t *rowptr, *col, *perm, *rowid;
+    int64_t n, E;
+    const float* ew;                 // [E] distances, caller's edge order
+    const __nv_bfloat16* x1;         // [n,128] bf16
+    const float *w1, *b1, *w2, *b2, *goff;
+    int G;
+    float cutoff, gcoeff;
+    float* agg;                      // [n,128], zeroed
+    float* head;                     // [gridDim.x,128], zeroed
+};
+
+// shared-memory map (bytes from the 1024-aligned base)
+constexpr int o2W1 = 0;                     // [128][64]  bf16 image, 16 KB
+constexpr int o2W2 = 16384;                 // 2 slabs [128][64], 32 KB
+constexpr int o2A1 = 49152;                 // 2 stages x 16 KB
+constexpr int o2A2 = o2A1 + 2 * 16384;      // 32 KB
+constexpr int o2X = o2A2 + 32768;           // 2 stages x 32 KB: gathered rows -> msg
+constexpr int o2S = o2X + 2 * 32768;        // 16 KB (rows of 128 B, first 64 B used: 32 segments)
+constexpr int o2Vec = o2S + 16384;          // b1[128] b2[128] goff[64]
+constexpr int o2Meta = o2Vec + 320 * 4;     // 2 x { C[128] f32, seg[128] i32, seg_row[32] i32, cnt, nseg, head0, pad }
+constexpr int kMetaBytes = (128 + 128 + 32 + 4) * 4;
+constexpr int o2Tmp = o2Meta + 2 * kMetaBytes;   // meta scratch: wcount[4], first-overflow[4]
+constexpr int o2Bar = o2Tmp + 64;
+// barriers
+enum { B_A1F = 0, B_A1E = 2, B_XF = 4, B_D1F = 6, B_D1E = 8, B_A2F = 10, B_A2E = 11, B_D2F = 13, B_D2E = 14, B_MSGF = 15,
+       B_D3F = 17, B_D3E = 19, B_DONE = 21, B_COUNT = 23 };
+constexpr int kTc2Smem = o2Bar + B_COUNT * 8 + 16 + 1024;
+
+__device__ __forceinline__ float ex2a(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float lg2a(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+// softplus(x) - ln 2
+__device__ __forceinline__ float ssp2(float x) {
+    const float e = ex2a(fminf(x * 1.4426950408889634f, 126.f));
+    return fmaf(0.6931471805599453f, lg2a(1.0f + e), -0.6931471805599453f);
+}
+__device__ __forceinline__ void cp_async_arrive(uint64_t* bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+struct Meta {
+    float C[128];
+    int seg[128];
+    int seg_row[32];
+    int cnt, nseg, head0, pad;
+};
+
+__global__ void __launch_bounds__(512, 1) schnet_fwd_tc2_kernel(Tc2Args a) {  // 512: caps the registers at 128 (one scheduler hosts 4 of the 13 warps)
+    extern __shared__ __align__(16) uint8_t smraw[];
+    uint8_t* sm = smraw + ((1024u - (smem_u32(smraw) & 1023u)) & 1023u);
+    float* b1s = reinterpret_cast<float*>(sm + o2Vec);
+    float* b2s = b1s + 128;
+    float* goff = b2s + 128;
+    Meta* meta = reinterpret_cast<Meta*>(sm + o2Meta);
+    int* tmp = reinterpret_cast<int*>(sm + o2Tmp);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sm + o2Bar);
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(sm + o2Bar + B_COUNT * 8);
+    const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+
+    // ---- setup: weights -> bf16 images, vectors, barriers, tensor memory
+    for (int x = t; x < 128 * 8; x += kS2Threads) {  // W1 [f][g], g padded to 64
+        const int f = x >> 3, ch = x & 7;
+        uint32_t p[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int g0 = ch * 8 + 2 * j;
+            p[j] = pack_bf16(g0 < a.G ? __ldg(a.w1 + f * a.G + g0) : 0.f, g0 + 1 < a.G ? __ldg(a.w1 + f * a.G + g0 + 1) : 0.f);
+        }
+        *reinterpret_cast<uint4*>(sm + o2W1 + sw128_chunk_off(f, ch)) = make_uint4(p[0], p[1], p[2], p[3]);
+    }
+    for (int x = t; x < 128 * 16; x += kS2Threads) {  // W2 [f'][f], two K slabs
+        const int f = x >> 4, ch16 = x & 15, kb = ch16 >> 3, ch = ch16 & 7;
+        const float4 lo = ldg4(a.w2 + f * 128 + kb * 64 + ch * 8), hi = ldg4(a.w2 + f * 128 + kb * 64 + ch * 8 + 4);
+        *reinterpret_cast<uint4*>(sm + o2W2 + kb * 16384 + sw128_chunk_off(f, ch)) =
+            make_uint4(pack_bf16(lo.x, lo.y), pack_bf16(lo.z, lo.w), pack_bf16(hi.x, hi.y), pack_bf16(hi.z, hi.w));
+    }
+    if (t < 128) { b1s[t] = __ldg(a.b1 + t); b2s[t] = __ldg(a.b2 + t); }
+    if (t < 64) goff[t] = t < a.G ? __ldg(a.goff + t) : 1.0e18f;  // padding columns: the Gaussian underflows to exactly 0
+    if (t == 0) {
+        const int c128[] = {B_A1F, B_A1F + 1, B_D1E, B_D1E + 1, B_A2F, B_D2E, B_MSGF, B_MSGF + 1, B_D3E, B_D3E + 1, B_DONE, B_DONE + 1, B_XF, B_XF + 1};
+        for (int i = 0; i < B_COUNT; ++i) mbar_init(&bars[i], 1);
+        for (int i = 0; i < 14; ++i) mbar_init(&bars[c128[i]], 128);
+        fence_mbar_init();
+    }
+    if (warp == 12) tmem_alloc<512>(tmem_ptr);
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tm = *tmem_ptr;
+    const uint32_t tmD1 = tm, tmD2 = tm + 256, tmD3 = tm + 384;  // D1[p] = tmD1 + 128 p, D3[p] = tmD3 + 32 p
+
+    const int64_t e_begin = (a.E * blockIdx.x) / gridDim.x, e_end = (a.E * (blockIdx.x + 1)) / gridDim.x;
+
+    if (warp < 4) {
+        // ===================== meta: thread = edge slot =====================
+        const int e = t;
+        const float cw = 3.14159265358979323846f / a.cutoff;
+        const float c2 = a.gcoeff * 1.4426950408889634f;
+        int64_t e_cur = e_begin;
+        uint32_t tc = 0;
+        for (;; ++tc) {
+            const uint32_t p = tc & 1u, par = (tc >> 1) & 1u;
+            mbar_wait(&bars[B_DONE + p], par ^ 1u);   // tile tc-2 read out: its meta block is free
+            mbar_wait(&bars[B_D3F + p], par ^ 1u);    // G3 of tile tc-2 has read the msg image: the row stage is free
+            mbar_wait(&bars[B_A1E + p], par ^ 1u);    // G1 of tile tc-2 has read A1[p]
+            Meta& M = meta[p];
+            const int64_t remain = e_end - e_cur;
+            if (remain <= 0) {  // sentinel tile: wakes every consumer, cnt = 0
+                if (e == 0) { M.cnt = 0; M.nseg = 0; }
+                cp_async_arrive(&bars[B_XF + p]);
+                mbar_arrive(&bars[B_A1F + p]);
+                break;
+            }
+            int cnt = (int)min((int64_t)128, remain);
+            const int64_t k = e_cur + min(e, cnt - 1);
+            const int rid = __ldg(a.rowid + k);
+            const bool flag = e < cnt && (e == 0 || __ldg(a.rowid + k - 1) != rid);
+            const unsigned bal = __ballot_sync(0xffffffffu, flag);
+            if (lane == 0) tmp[warp] = __popc(bal);
+            bar_sync_named(1, 128);
+            int base = 0;
+#pragma unroll
+            for (int w = 0; w < 4; ++w)
+                if (w < warp) base += tmp[w];
+            int seg = base + __popc(bal & ((2u << lane) - 1u)) - 1;   // 0-based segment of this slot
+            // at most 32 rows per tile: cut the tile in front of the 33rd row
+            const unsigned over = __ballot_sync(0xffffffffu, e < cnt && seg >= kS2MaxSeg);
+            if (lane == 0) tmp[4 + warp] = over ? warp * 32 + (__ffs(over) - 1) : 128;
+            bar_sync_named(1, 128);
+            cnt = min(cnt, min(min(tmp[4], tmp[5]), min(tmp[6], tmp[7])));
+            const bool valid = e < cnt;
+            int src = 0;
+            float d = 1.0e18f, C = 0.f;
+            if (valid) {
+                const int64_t kk = e_cur + e;
+                const int eid = a.perm ? __ldg(a.perm + kk) : (int)kk;
+                src = __ldg(a.col + kk);
+                d = __ldg(a.ew + eid);
+                C = 0.5f * (__cosf(d * cw) + 1.0f);
+            }
+            M.C[e] = C;
+            M.seg[e] = valid ? seg : -1;
+            if (flag && seg < kS2MaxSeg && valid) M.seg_row[seg] = rid;
+            if (e == cnt - 1) { M.cnt = cnt; M.nseg = seg + 1; }
+            if (e == 0) M.head0 = (int64_t)__ldg(a.rowptr + rid) < e_begin ? 1 : 0;
+            // gather x1[src] (bf16, 16 chunks of 16 B) into the swizzled row image
+            uint8_t* xs = sm + o2X + p * 32768;
+            if (valid) {
+                const __nv_bfloat16* row = a.x1 + (int64_t)src * 128;
+#pragma unroll
+                for (int ch = 0; ch < 16; ++ch)
+                    __pipeline_memcpy_async(xs + (ch >> 3) * 16384 + sw128_chunk_off(e, ch & 7), row + ch * 8, 16);
+            } else {
+#pragma unroll
+                for (int ch = 0; ch < 16; ++ch)
+                    *reinterpret_cast<uint4*>(xs + (ch >> 3) * 16384 + sw128_chunk_off(e, ch & 7)) = make_uint4(0u, 0u, 0u, 0u);
+            }
+            cp_async_arrive(&bars[B_XF + p]);   // fires when this thread's copies have landed (also publishes the meta block)
+            // Gaussian basis -> A1[p]
+            uint8_t* a1 = sm + o2A1 + p * 16384;
+#pragma unroll
+            for (int ch = 0; ch < 8; ++ch) {
+                float v[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const float u = d - goff[ch * 8 + q];
+                    v[q] = ex2a(c2 * u * u);
+                }
+                *reinterpret_cast<uint4*>(a1 + sw128_chunk_off(e, ch)) =
+                    make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+            }
+            fence_proxy_async();
+            mbar_arrive(&bars[B_A1F + p]);
+            e_cur += cnt;
+        }
+    } else if (warp < 8) {
+        // ===================== epilogue 1: h1 = ssp(D1 + b1) -> A2 =====================
+        const int e = t - 128;
+        const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+        for (uint32_t tc = 0;; ++tc) {
+            const uint32_t p = tc & 1u, par = (tc >> 1) & 1u;
+            mbar_wait(&bars[B_A1F + p], par);
+            if (meta[p].cnt == 0) break;
+            mbar_wait(&bars[B_D1F + p], par);
+            tc_fence_after();
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float v[32];
+                tmem_ld32(tmD1 + p * 128 + lane_base + 32 * j, v);
+#pragma unroll
+                for (int q = 0; q < 32; ++q) v[q] = ssp2(v[q] + b1s[32 * j + q]);
+                if ((j & 1) == 0) mbar_wait(&bars[B_A2E + (j >> 1)], (tc & 1u) ^ 1u);  // G2 of the previous tile has read this K slab
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    *reinterpret_cast<uint4*>(sm + o2A2 + (j >> 1) * 16384 + sw128_chunk_off(e, (j & 1) * 4 + q)) =
+                        make_uint4(pack_bf16(v[8 * q], v[8 * q + 1]), pack_bf16(v[8 * q + 2], v[8 * q + 3]),
+                                   pack_bf16(v[8 * q + 4], v[8 * q + 5]), pack_bf16(v[8 * q + 6], v[8 * q + 7]));
+            }
+            tc_fence_before();
+            mbar_arrive(&bars[B_D1E + p]);
+            fence_proxy_async();
+            mbar_arrive(&bars[B_A2F]);
+        }
+    } else if (warp < 12) {
+        // ===================== epilogue 2: msg, one-hot tile; read-out of the previous tile =====================
+        const int e = t - 256;
+        const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+        auto readout = [&](uint32_t tq) {  // D3 of tile tq: lane = feature column e, accumulator column = segment
+            const uint32_t p = tq & 1u;
+            const Meta& M = meta[p];
+            float v[32];
+            tmem_ld32(tmD3 + p * 32 + lane_base, v);
+            tc_fence_before();
+            const int nseg = M.nseg;
+#pragma unroll
+            for (int s = 0; s < kS2MaxSeg; ++s) {
+                if (s < nseg) {
+                    float* dst = (s == 0 && M.head0) ? a.head + (int64_t)blockIdx.x * 128 + e : a.agg + (int64_t)M.seg_row[s] * 128 + e;
+                    *dst += v[s];
+                }
+            }
+            mbar_arrive(&bars[B_D3E + p]);
+            mbar_arrive(&bars[B_DONE + p]);
+        };
+        uint32_t tc = 0;
+        for (;; ++tc) {
+            const uint32_t p = tc & 1u, par = (tc >> 1) & 1u;
+            mbar_wait(&bars[B_A1F + p], par);   // the meta block (plain stores, released by the meta threads' arrive)
+            mbar_wait(&bars[B_XF + p], par);    // the gathered rows (cp.async completion)
+            const Meta& M = meta[p];
+            const int cnt = M.cnt;
+            if (cnt == 0) break;
+            if (tc > 0) {   // read out the previous tile first: releases its meta block early (the meta warps wait for it)
+                mbar_wait(&bars[B_D3F + ((tc - 1) & 1u)], ((tc - 1) >> 1) & 1u);
+                tc_fence_after();
+                readout(tc - 1);
+            }
+            mbar_wait(&bars[B_D2F], tc & 1u);
+            tc_fence_after();
+            const float C = M.C[e];
+            uint8_t* xs = sm + o2X + p * 32768;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float v[32];
+                tmem_ld32(tmD2 + lane_base + 32 * j, v);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    uint4* px = reinterpret_cast<uint4*>(xs + (j >> 1) * 16384 + sw128_chunk_off(e, (j & 1) * 4 + q));
+                    const uint4 xr = *px;
+                    const uint32_t w[4] = {xr.x, xr.y, xr.z, xr.w};
+                    uint32_t o[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int c0 = 32 * j + 8 * q + 2 * u;
+                        const float m0 = (v[8 * q + 2 * u] + b2s[c0]) * C * __uint_as_float(w[u] << 16);
+                        const float m1 = (v[8 * q + 2 * u + 1] + b2s[c0 + 1]) * C * __uint_as_float(w[u] & 0xffff0000u);
+                        o[u] = pack_bf16(m0, m1);   // C = 0 and zero rows for the padding slots
+                    }
+                    *px = make_uint4(o[0], o[1], o[2], o[3]);
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(&bars[B_D2E]);
+            // one-hot row-membership tile (single buffer: G3 of the previous tile has read it -- waited for above)
+            {
+                const int seg = M.seg[e];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    uint32_t o[4] = {0u, 0u, 0u, 0u};
+                    if (seg >= 0 && (seg >> 3) == q) o[(seg & 7) >> 1] = (seg & 1) ? 0x3f800000u : 0x00003f80u;
+                    *reinterpret_cast<uint4*>(sm + o2S + sw128_chunk_off(e, q)) = make_uint4(o[0], o[1], o[2], o[3]);
+                }
+            }
+            fence_proxy_async();
+            mbar_arrive(&bars[B_MSGF + p]);
+        }
+        if (tc > 0) {
+            mbar_wait(&bars[B_D3F + ((tc - 1) & 1u)], ((tc - 1) >> 1) & 1u);
+            tc_fence_after();
+            readout(tc - 1);
+        }
+    } else {
+        // ===================== MMA issuer (whole warp, one elected lane) =====================
+        const uint32_t id1 = umma_idesc_bf16(128, 128), id3 = umma_idesc_bf16(128, 32, true, true);
+        const uint32_t w1b = smem_u32(sm + o2W1), w2b = smem_u32(sm + o2W2), a2b = smem_u32(sm + o2A2), sb = smem_u32(sm + o2S);
+        auto g1 = [&](uint32_t tq) -> bool {  // returns false at the sentinel
+            const uint32_t p = tq & 1u, par = (tq >> 1) & 1u;
+            mbar_wait(&bars[B_A1F + p], par);
+            if (meta[p].cnt == 0) return false;
+            mbar_wait(&bars[B_D1E + p], par ^ 1u);
+            tc_fence_after();
+            if (elect_one()) {
+                umma_tile(tmD1 + p * 128, smem_u32(sm + o2A1 + p * 16384), 16384, w1b, 16384, 64, id1);
+                umma_commit(&bars[B_D1F + p]);
+                umma_commit(&bars[B_A1E + p]);
+            }
+            __syncwarp();
+            return true;
+        };
+        auto g3 = [&](uint32_t tq) {
+            const uint32_t p = tq & 1u, par = (tq >> 1) & 1u;
+            mbar_wait(&bars[B_MSGF + p], par);
+            mbar_wait(&bars[B_D3E + p], par ^ 1u);
+            tc_fence_after();
+            if (elect_one()) {
+                const uint32_t mb = smem_u32(sm + o2X + p * 32768);
+#pragma unroll
+                for (int k16 = 0; k16 < 8; ++k16)
+                    umma_bf16(tmD3 + p * 32, umma_desc_mn128(mb + k16 * 2048, 16384), umma_desc_mn128(sb + k16 * 2048, 16384), id3, k16 ? 1u : 0u);
+                umma_commit(&bars[B_D3F + p]);
+            }
+            __syncwarp();
+        };
+        if (g1(0)) {
+            for (uint32_t tc = 0;; ++tc) {
+                if (tc > 0) g3(tc - 1);          // first: the meta warps need its completion before they can refill the stage
+                const bool more = g1(tc + 1);
+                // G2(tc)
+                mbar_wait(&bars[B_A2F], tc & 1u);
+                mbar_wait(&bars[B_D2E], (tc & 1u) ^ 1u);
+                tc_fence_after();
+                if (elect_one()) {
+#pragma unroll
+                    for (int ks = 0; ks < 2; ++ks) {
+#pragma unroll
+                        for (int k16 = 0; k16 < 4; ++k16)
+                            umma_bf16(tmD2, umma_desc_k128(a2b + ks * 16384 + k16 * 32), umma_desc_k128(w2b + ks * 16384 + k16 * 32), id1,
+                                      (ks | k16) ? 1u : 0u);
+                        umma_commit(&bars[B_A2E + ks]);
+                    }
+                    umma_commit(&bars[B_D2F]);
+                }
+                __syncwarp();
+                if (!more) {
+                    g3(tc);
+                    break;
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 12) tmem_dealloc<512>(tm);
+}
+
+// rows that straddle a CTA boundary: add the later CTAs' head partials in CTA order
+__global__ void __launch_bounds__(128) schnet_tc2_fixup_kernel(const int32_t* __restrict__ rowptr, int64_t n, int64_t E, int nchunks,
+                                                               const float* __restrict__ head, float* __restrict__ agg) {
+    __shared__ int hrow[1024];
+    for (int ch = threadIdx.x; ch < nchunks; ch += 128) {
+        const int64_t e0 = (E * ch) / nchunks, e1 = (E * (ch + 1)) / nchunks;
+        int row = -1;
+        if (ch > 0 && e0 < e1) {
+            int lo = 0, hi = (int)n;
+            while (hi - lo > 1) {
+                const int mid = (lo + hi) >> 1;
+                if ((int64_t)__ldg(rowptr + mid) <= e0) lo = mid; else hi = mid;
+            }
+            if ((int64_t)__ldg(rowptr + lo) < e0) row = lo;
+        }
+        hrow[ch] = row;
+    }
+    __syncthreads();
+    const int c = threadIdx.x;
+    for (int ch = 1; ch < nchunks; ++ch)
+        if (hrow[ch] >= 0) agg[(int64_t)hrow[ch] * 128 + c] += head[(int64_t)ch * 128 + c];
+}
+
+}  // namespace gmp
+
+using namespace gmp;
+
+extern "C" {
+
+int32_t gmp_schnet_tc2_num_chunks(int64_t num_edges) {
+    const int64_t nt = ceil_div(num_edges, 128);
+    return (int32_t)(nt < num_sms() ? (nt < 1 ? 1 : nt) : num_sms());
+}
+
+int gmp_schnet_cfconv_fwd_tc2(const int32_t* rowptr, const int32_t* col, const int32_t* perm, const int32_t* rowid, int64_t n,
+                              int64_t num_edges, const float* edge_weight, const void* x1_bf16, const gmp_schnet_filter* f, float* agg,
+                              float* head, gmp_stream_t stream) {
+    GMP_REQUIRE(rowptr && f && agg && head, "schnet_cfconv_fwd_tc2: NULL pointer");
+    GMP_REQUIRE(num_edges == 0 || (col && rowid && edge_weight && x1_bf16), "schnet_cfconv_fwd_tc2: NULL edge/feature pointer");
+    GMP_REQUIRE(f->num_filters == 128 && f->num_gaussians >= 1 && f->num_gaussians <= 64 && f->gauss_offset,
+                "schnet_cfconv_fwd_tc2: built for 128 filters, <= 64 lazily expanded Gaussians");
+    GMP_REQUIRE(n >= 0 && n < (1ll << 31) && num_edges >= 0 && num_edges < (1ll << 31), "schnet_cfconv_fwd_tc2: sizes out of range");
+    GMP_CUDA(cudaMemsetAsync(agg, 0, (size_t)n * 128 * sizeof(float), stream));
+    if (n == 0 || num_edges == 0) return GMP_OK;
+    const int nchunks = gmp_schnet_tc2_num_chunks(num_edges);
+    GMP_CUDA(cudaMemsetAsync(head, 0, (size_t)nchunks * 128 * sizeof(float), stream));
+    Tc2Args a;
+    a.rowptr = rowptr; a.col = col; a.perm = perm; a.rowid = rowid; a.n = n; a.E = num_edges; a.ew = edge_weight;
+    a.x1 = (const __nv_bfloat16*)x1_bf16; a.w1 = f->w1; a.b1 = f->b1; a.w2 = f->w2; a.b2 = f->b2; a.goff = f->gauss_offset;
+    a.G = f->num_gaussians; a.cutoff = f->cutoff; a.gcoeff = f->gauss_coeff; a.agg = agg; a.head = head;
+    GMP_CUDA(cudaFuncSetAttribute(schnet_fwd_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTc2Smem));
+    schnet_fwd_tc2_kernel<<<nchunks, kS2Threads, kTc2Smem, stream>>>(a);
+    int rc = check_launch("schnet_fwd_tc2_kernel");
+    if (rc != GMP_OK) return rc;
+    if (nchunks > 1) {
+        schnet_tc2_fixup_kernel<<<1, 128, 0, stream>>>(rowptr, n, num_edges, nchunks, head, agg);
+        rc = check_launch("schnet_tc2_fixup_kernel");
+    }
+    return rc;
+}
+
+}  // extern "C"

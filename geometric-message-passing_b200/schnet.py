@@ -85,6 +85,21 @@ def edge_length(pos: torch.Tensor, graph: Graph) -> torch.Tensor:
     return _EdgeLength.apply(pos, graph)
 
 
+def _cfconv_forward(csr, graph, edge_weight, edge_attr, x1, filt, w1, precision):
+    """agg[r] = sum_{e in CSR row r} x1[col_e] * W_e.  bf16 mode with the lazily expanded basis and 128 filters: the
+    pipelined three-MMA kernel (csrc/schnet_tc2.cu); otherwise the fp32 / first tensor-core kernels."""
+    F_, G = w1.shape
+    agg = torch.empty(graph.n, F_, dtype=x1.dtype, device=x1.device)
+    if precision == _lib.BF16_TC and edge_attr is None and F_ == 128 and G <= 64:
+        head = torch.empty(int(_lib.lib().gmp_schnet_tc2_num_chunks(graph.E)), 128, dtype=x1.dtype, device=x1.device)
+        call("gmp_schnet_cfconv_fwd_tc2", ptr(csr.rowptr), ptr(csr.col), csr.perm_ptr, ptr(csr.row_ids()), graph.n, graph.E,
+             ptr(edge_weight), ptr(x1.to(torch.bfloat16)), C.byref(filt), ptr(agg), ptr(head))
+    else:
+        call("gmp_schnet_cfconv_fwd", ptr(csr.rowptr), ptr(csr.col), csr.perm_ptr, graph.n, graph.E, ptr(edge_weight),
+             ptr(edge_attr), ptr(x1), C.byref(filt), ptr(agg), precision)
+    return agg
+
+
 class _CFConvFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x1, edge_weight, edge_attr, w1, b1, w2, b2, graph: Graph, cutoff, offset, coeff, precision):
@@ -94,9 +109,7 @@ class _CFConvFn(torch.autograd.Function):
         filt = SchnetFilter(ptr(w1), ptr(b1), ptr(w2), ptr(b2), w1.shape[1], w1.shape[0], float(cutoff),
                             ptr(offset), float(coeff))
         csr = graph.by_dst
-        agg = torch.empty(graph.n, w1.shape[0], dtype=x1.dtype, device=x1.device)
-        call("gmp_schnet_cfconv_fwd", ptr(csr.rowptr), ptr(csr.col), csr.perm_ptr, graph.n, graph.E, ptr(edge_weight),
-             ptr(edge_attr), ptr(x1), C.byref(filt), ptr(agg), precision)
+        agg = _cfconv_forward(csr, graph, edge_weight, edge_attr, x1, filt, w1, precision)
         ctx.save_for_backward(x1, edge_weight, edge_attr if edge_attr is not None else x1.new_empty(0), w1, b1, w2, b2, offset)
         ctx.graph, ctx.meta, ctx.has_attr = graph, (float(cutoff), float(coeff), precision), edge_attr is not None
         return agg
@@ -115,9 +128,7 @@ class _CFConvFn(torch.autograd.Function):
         if need[0]:
             # d agg / d x1 is the same fused op over the transposed (src-sorted) CSR with g in place of x1
             t = graph.by_src
-            dx1 = torch.empty_like(x1)
-            call("gmp_schnet_cfconv_fwd", ptr(t.rowptr), ptr(t.col), t.perm_ptr, graph.n, graph.E, ptr(ew), ptr(ea),
-                 ptr(g), C.byref(filt), ptr(dx1), precision)
+            dx1 = _cfconv_forward(t, graph, ew, ea, g, filt, w1, precision)
         csr = graph.by_dst
         lib = _lib.lib()
         nparts, plen = lib.gmp_schnet_bwd_num_parts(graph.E), lib.gmp_schnet_bwd_part_len(G, F)

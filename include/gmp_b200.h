@@ -188,6 +188,16 @@ int gmp_umma_selftest(const float* A, const float* B, float* out, int32_t K, gmp
  * (the layout the weight-gradient GEMMs consume). */
 int gmp_umma_selftest_mn(const float* A, const float* B, float* out, int32_t N, gmp_stream_t stream);
 
+/* Pipelined GMP_BF16_TC forward of the same op (csrc/schnet_tc2.cu): warp-specialised (meta / MMA / two epilogue
+ * groups), three tcgen05 products per tile -- the third one is the segmented row sum itself (msg^T x one-hot row
+ * membership).  Restrictions: 128 filters, the Gaussian basis recomputed from edge_weight (edge_attr = NULL path),
+ * x1 passed as bf16 rows.  agg [n,128] is overwritten (zeroed first); head [gmp_schnet_tc2_num_chunks(E),128] is
+ * scratch for rows that straddle a CTA boundary; rowid int32[E] = CSR row of every sorted edge. */
+int32_t gmp_schnet_tc2_num_chunks(int64_t num_edges);
+int gmp_schnet_cfconv_fwd_tc2(const int32_t* rowptr, const int32_t* col, const int32_t* perm, const int32_t* rowid,
+                              int64_t n, int64_t num_edges, const float* edge_weight, const void* x1_bf16,
+                              const gmp_schnet_filter* filter /* host */, float* agg, float* head, gmp_stream_t stream);
+
 /* Parameter gradients of a node-side nn.Linear (PyG CFConv.lin1 / lin2, InteractionBlock.lin; called at
  * models/schnet.py:72) in the GMP_BF16_TC mode: dW [out,in] = g^T x and db [out] = column sums of g, g [n,out], x [n,in],
  * out = 128, in in {64,128}.  Rows are split over the SMs; parts [gmp_linear_wgrad_num_parts(n)][out*in + out] holds
