@@ -3,7 +3,8 @@
 //
 //   warps 0-3   meta : edge scalars, cosine cutoff, row segments; cp.async gather of the bf16 x1[src] rows straight into
 //                      the swizzled operand image; Gaussian basis -> A1 (bf16)
-//   warp  12    MMA  : G1 = rbf W1^T -> D1;  G2 = h1 W2^T -> D2;  G3 = msg^T S -> D3   (tcgen05, accumulators in TMEM)
+//   warps 12-14 MMA  : G1 = rbf W1^T -> D1;  G2 = h1 W2^T -> D2;  G3 = msg^T S -> D3   (tcgen05, accumulators in TMEM;
+//                      one issuing warp per product so that no product waits behind another one's operands)
 //   warps 4-7   epi1 : D1 + b1 -> shifted softplus -> h1 (bf16) -> A2
 //   warps 8-11  epi2 : (D2 + b2) * C * x1[src] -> msg (bf16, in place over the gathered rows) and the one-hot
 //                      row-membership tile S; then, one tile behind, D3[c, seg] -> agg[row(seg), c] += ...
@@ -13,7 +14,7 @@
 // Every (row, column) of agg is only ever touched by the one thread that owns the column in the one CTA that owns the
 // edge range, in tile order: deterministic, no atomics; agg is zeroed first and rows that straddle a CTA boundary go
 // through the head buffer + tp_tc_fixup_kernel-style fix-up (gmp_schnet_cfconv_fwd_tc2 does both).
-// Stages double-buffered: A1, gathered rows / msg, D1, D3; single: A2 (released per K slab), S, D2.
+// Stages: gathered rows / msg, meta blocks and D3 three deep; D1 two deep; A1, A2 (released per K slab), S, D2 single.
 #include <cuda_pipeline.h>
 
 #include "common.cuh"
@@ -23,8 +24,9 @@ namespace gmp {
 
 using namespace tc;
 
-constexpr int kS2Threads = 416;   // 13 warps
+constexpr int kS2Threads = 480;   // 15 warps: meta 0-3, epi1 4-7, epi2 8-11, one MMA-issuing warp per product 12-14
 constexpr int kS2MaxSeg = 32;
+constexpr int kS2Stages = 3;      // gathered-row / msg stages, meta blocks, D3 accumulators
 
 struct Tc2Args {
     const int32_t *rowptr, *col, *perm, *rowid;
@@ -41,26 +43,30 @@ struct Tc2Args {
 // shared-memory map (bytes from the 1024-aligned base)
 constexpr int o2W1 = 0;                     // [128][64]  bf16 image, 16 KB
 constexpr int o2W2 = 16384;                 // 2 slabs [128][64], 32 KB
-constexpr int o2A1 = 49152;                 // 2 stages x 16 KB
-constexpr int o2A2 = o2A1 + 2 * 16384;      // 32 KB
-constexpr int o2X = o2A2 + 32768;           // 2 stages x 32 KB: gathered rows -> msg
-constexpr int o2S = o2X + 2 * 32768;        // 16 KB (rows of 128 B, first 64 B used: 32 segments)
+constexpr int o2A1 = 49152;                 // 16 KB
+constexpr int o2A2 = o2A1 + 16384;          // 32 KB
+constexpr int o2X = o2A2 + 32768;           // 3 stages x 32 KB: gathered rows -> msg
+constexpr int o2S = o2X + kS2Stages * 32768;  // 16 KB (rows of 128 B, first 64 B used: 32 segments)
 constexpr int o2Vec = o2S + 16384;          // b1[128] b2[128] goff[64]
-constexpr int o2Meta = o2Vec + 320 * 4;     // 2 x { C[128] f32, seg[128] i32, seg_row[32] i32, cnt, nseg, head0, pad }
+constexpr int o2Meta = o2Vec + 320 * 4;     // 3 x { C[128] f32, seg[128] i32, seg_row[32] i32, cnt, nseg, head0, pad }
 constexpr int kMetaBytes = (128 + 128 + 32 + 4) * 4;
-constexpr int o2Tmp = o2Meta + 2 * kMetaBytes;   // meta scratch: wcount[4], first-overflow[4]
+constexpr int o2Tmp = o2Meta + kS2Stages * kMetaBytes;   // meta scratch: wcount[4], first-overflow[4]; end-of-stream tile numbers
 constexpr int o2Bar = o2Tmp + 64;
 // barriers
-enum { B_A1F = 0, B_A1E = 2, B_XF = 4, B_D1F = 6, B_D1E = 8, B_A2F = 10, B_A2E = 11, B_D2F = 13, B_D2E = 14, B_MSGF = 15,
-       B_D3F = 17, B_D3E = 19, B_DONE = 21, B_COUNT = 23 };
+enum { B_A1F = 0, B_A1E = 1, B_XF = 2, B_D1F = 5, B_D1E = 7, B_A2F = 9, B_A2E = 10, B_D2F = 12, B_D2E = 13, B_MSGF = 14,
+       B_D3F = 17, B_D3E = 20, B_DONE = 23, B_COUNT = 26 };
 constexpr int kTc2Smem = o2Bar + B_COUNT * 8 + 16 + 1024;
 
 __device__ __forceinline__ float ex2a(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
-__device__ __forceinline__ float lg2a(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
-// softplus(x) - ln 2
+// softplus(x) - ln 2 = max(x, 0) + log1p(exp(-|x|)) - ln 2: one MUFU (ex2) and a degree-5 polynomial for log1p on [0, 1]
+// (Abramowitz & Stegun 4.1.44, |error| <= 1e-5: far inside the bf16 rounding of the result)
 __device__ __forceinline__ float ssp2(float x) {
-    const float e = ex2a(fminf(x * 1.4426950408889634f, 126.f));
-    return fmaf(0.6931471805599453f, lg2a(1.0f + e), -0.6931471805599453f);
+    const float u = ex2a(-fabsf(x) * 1.4426950408889634f);
+    float p = fmaf(u, 0.03215845f, -0.13606275f);
+    p = fmaf(u, p, 0.28947478f);
+    p = fmaf(u, p, -0.49190896f);
+    p = fmaf(u, p, 0.99949556f);
+    return fmaf(u, p, fmaxf(x, 0.f) - 0.6931471805599453f);
 }
 __device__ __forceinline__ void cp_async_arrive(uint64_t* bar) {
     asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -73,7 +79,7 @@ struct Meta {
     int cnt, nseg, head0, pad;
 };
 
-__global__ void __launch_bounds__(512, 1) schnet_fwd_tc2_kernel(Tc2Args a) {  // 512: caps the registers at 128 (one scheduler hosts 4 of the 13 warps)
+__global__ void __launch_bounds__(512, 1) schnet_fwd_tc2_kernel(Tc2Args a) {  // 512: caps the registers at 128 per thread
     extern __shared__ __align__(16) uint8_t smraw[];
     uint8_t* sm = smraw + ((1024u - (smem_u32(smraw) & 1023u)) & 1023u);
     float* b1s = reinterpret_cast<float*>(sm + o2Vec);
@@ -81,6 +87,8 @@ __global__ void __launch_bounds__(512, 1) schnet_fwd_tc2_kernel(Tc2Args a) {  //
     float* goff = b2s + 128;
     Meta* meta = reinterpret_cast<Meta*>(sm + o2Meta);
     int* tmp = reinterpret_cast<int*>(sm + o2Tmp);
+    volatile int* end_g1 = tmp + 8;   // tile number of the end-of-stream marker, passed G1 -> epi1 -> G2
+    volatile int* end_e1 = tmp + 9;
     uint64_t* bars = reinterpret_cast<uint64_t*>(sm + o2Bar);
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(sm + o2Bar + B_COUNT * 8);
     const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
@@ -105,9 +113,13 @@ __global__ void __launch_bounds__(512, 1) schnet_fwd_tc2_kernel(Tc2Args a) {  //
     if (t < 128) { b1s[t] = __ldg(a.b1 + t); b2s[t] = __ldg(a.b2 + t); }
     if (t < 64) goff[t] = t < a.G ? __ldg(a.goff + t) : 1.0e18f;  // padding columns: the Gaussian underflows to exactly 0
     if (t == 0) {
-        const int c128[] = {B_A1F, B_A1F + 1, B_D1E, B_D1E + 1, B_A2F, B_D2E, B_MSGF, B_MSGF + 1, B_D3E, B_D3E + 1, B_DONE, B_DONE + 1, B_XF, B_XF + 1};
+        *end_g1 = -1;
+        *end_e1 = -1;
         for (int i = 0; i < B_COUNT; ++i) mbar_init(&bars[i], 1);
+        const int c128[] = {B_A1F, B_D1E, B_D1E + 1, B_A2F, B_D2E, B_MSGF, B_MSGF + 1, B_MSGF + 2, B_D3E, B_D3E + 1, B_D3E + 2,
+                            B_DONE, B_DONE + 1, B_DONE + 2};
         for (int i = 0; i < 14; ++i) mbar_init(&bars[c128[i]], 128);
+        for (int i = 0; i < kS2Stages; ++i) mbar_init(&bars[B_XF + i], 256);  // 128 cp.async completions + 128 plain arrives
         fence_mbar_init();
     }
     if (warp == 12) tmem_alloc<512>(tmem_ptr);
@@ -116,7 +128,7 @@ __global__ void __launch_bounds__(512, 1) schnet_fwd_tc2_kernel(Tc2Args a) {  //
     __syncthreads();
     tc_fence_after();
     const uint32_t tm = *tmem_ptr;
-    const uint32_t tmD1 = tm, tmD2 = tm + 256, tmD3 = tm + 384;  // D1[p] = tmD1 + 128 p, D3[p] = tmD3 + 32 p
+    const uint32_t tmD1 = tm, tmD2 = tm + 256, tmD3 = tm + 384;  // D1[p] = tmD1 + 128 p, D3[st] = tmD3 + 32 st
 
     const int64_t e_begin = (a.E * blockIdx.x) / gridDim.x, e_end = (a.E * (blockIdx.x + 1)) / gridDim.x;
 
@@ -126,54 +138,59 @@ __global__ void __launch_bounds__(512, 1) schnet_fwd_tc2_kernel(Tc2Args a) {  //
         const float cw = 3.14159265358979323846f / a.cutoff;
         const float c2 = a.gcoeff * 1.4426950408889634f;
         int64_t e_cur = e_begin;
-        uint32_t tc = 0;
-        for (;; ++tc) {
-            const uint32_t p = tc & 1u, par = (tc >> 1) & 1u;
-            mbar_wait(&bars[B_DONE + p], par ^ 1u);   // tile tc-2 read out: its meta block is free
-            mbar_wait(&bars[B_D3F + p], par ^ 1u);    // G3 of tile tc-2 has read the msg image: the row stage is free
-            mbar_wait(&bars[B_A1E + p], par ^ 1u);    // G1 of tile tc-2 has read A1[p]
-            Meta& M = meta[p];
+        for (uint32_t tc = 0;; ++tc) {
+            const uint32_t st = tc % kS2Stages, par = (tc / kS2Stages) & 1u;
             const int64_t remain = e_end - e_cur;
-            if (remain <= 0) {  // sentinel tile: wakes every consumer, cnt = 0
-                if (e == 0) { M.cnt = 0; M.nseg = 0; }
-                cp_async_arrive(&bars[B_XF + p]);
-                mbar_arrive(&bars[B_A1F + p]);
-                break;
-            }
+            // ---- everything that only needs global memory comes first: its latency overlaps the buffer waits below
             int cnt = (int)min((int64_t)128, remain);
-            const int64_t k = e_cur + min(e, cnt - 1);
-            const int rid = __ldg(a.rowid + k);
-            const bool flag = e < cnt && (e == 0 || __ldg(a.rowid + k - 1) != rid);
-            const unsigned bal = __ballot_sync(0xffffffffu, flag);
-            if (lane == 0) tmp[warp] = __popc(bal);
-            bar_sync_named(1, 128);
-            int base = 0;
-#pragma unroll
-            for (int w = 0; w < 4; ++w)
-                if (w < warp) base += tmp[w];
-            int seg = base + __popc(bal & ((2u << lane) - 1u)) - 1;   // 0-based segment of this slot
-            // at most 32 rows per tile: cut the tile in front of the 33rd row
-            const unsigned over = __ballot_sync(0xffffffffu, e < cnt && seg >= kS2MaxSeg);
-            if (lane == 0) tmp[4 + warp] = over ? warp * 32 + (__ffs(over) - 1) : 128;
-            bar_sync_named(1, 128);
-            cnt = min(cnt, min(min(tmp[4], tmp[5]), min(tmp[6], tmp[7])));
-            const bool valid = e < cnt;
-            int src = 0;
+            int rid = 0, seg = 0, src = 0;
+            bool flag = false, valid = false;
             float d = 1.0e18f, C = 0.f;
-            if (valid) {
-                const int64_t kk = e_cur + e;
-                const int eid = a.perm ? __ldg(a.perm + kk) : (int)kk;
-                src = __ldg(a.col + kk);
-                d = __ldg(a.ew + eid);
-                C = 0.5f * (__cosf(d * cw) + 1.0f);
+            if (remain > 0) {
+                const int64_t k = e_cur + min(e, cnt - 1);
+                rid = __ldg(a.rowid + k);
+                flag = e < cnt && (e == 0 || __ldg(a.rowid + k - 1) != rid);
+                const unsigned bal = __ballot_sync(0xffffffffu, flag);
+                if (lane == 0) tmp[warp] = __popc(bal);
+                bar_sync_named(1, 128);
+                int base = 0;
+#pragma unroll
+                for (int w = 0; w < 4; ++w)
+                    if (w < warp) base += tmp[w];
+                seg = base + __popc(bal & ((2u << lane) - 1u)) - 1;   // 0-based segment of this slot
+                // at most 32 rows per tile: cut the tile in front of the 33rd row
+                const unsigned over = __ballot_sync(0xffffffffu, e < cnt && seg >= kS2MaxSeg);
+                if (lane == 0) tmp[4 + warp] = over ? warp * 32 + (__ffs(over) - 1) : 128;
+                bar_sync_named(1, 128);
+                cnt = min(cnt, min(min(tmp[4], tmp[5]), min(tmp[6], tmp[7])));
+                valid = e < cnt;
+                if (valid) {
+                    const int64_t kk = e_cur + e;
+                    const int eid = a.perm ? __ldg(a.perm + kk) : (int)kk;
+                    src = __ldg(a.col + kk);
+                    d = __ldg(a.ew + eid);
+                    C = 0.5f * (__cosf(d * cw) + 1.0f);
+                }
+            }
+            const int head0 = (remain > 0 && e == 0) ? ((int64_t)__ldg(a.rowptr + rid) < e_begin ? 1 : 0) : 0;
+            mbar_wait(&bars[B_DONE + st], par ^ 1u);   // tile tc-3 read out: its meta block is free
+            mbar_wait(&bars[B_D3F + st], par ^ 1u);    // G3 of tile tc-3 has read the msg image: the row stage is free
+            Meta& M = meta[st];
+            if (remain <= 0) {  // end-of-stream marker: cnt = 0
+                if (e == 0) { M.cnt = 0; M.nseg = 0; }
+                cp_async_arrive(&bars[B_XF + st]);
+                mbar_arrive(&bars[B_XF + st]);
+                mbar_wait(&bars[B_A1E], (tc & 1u) ^ 1u);
+                mbar_arrive(&bars[B_A1F]);
+                break;
             }
             M.C[e] = C;
             M.seg[e] = valid ? seg : -1;
             if (flag && seg < kS2MaxSeg && valid) M.seg_row[seg] = rid;
             if (e == cnt - 1) { M.cnt = cnt; M.nseg = seg + 1; }
-            if (e == 0) M.head0 = (int64_t)__ldg(a.rowptr + rid) < e_begin ? 1 : 0;
+            if (e == 0) M.head0 = head0;
             // gather x1[src] (bf16, 16 chunks of 16 B) into the swizzled row image
-            uint8_t* xs = sm + o2X + p * 32768;
+            uint8_t* xs = sm + o2X + st * 32768;
             if (valid) {
                 const __nv_bfloat16* row = a.x1 + (int64_t)src * 128;
 #pragma unroll
@@ -184,22 +201,23 @@ __global__ void __launch_bounds__(512, 1) schnet_fwd_tc2_kernel(Tc2Args a) {  //
                 for (int ch = 0; ch < 16; ++ch)
                     *reinterpret_cast<uint4*>(xs + (ch >> 3) * 16384 + sw128_chunk_off(e, ch & 7)) = make_uint4(0u, 0u, 0u, 0u);
             }
-            cp_async_arrive(&bars[B_XF + p]);   // fires when this thread's copies have landed (also publishes the meta block)
-            // Gaussian basis -> A1[p]
-            uint8_t* a1 = sm + o2A1 + p * 16384;
+            cp_async_arrive(&bars[B_XF + st]);   // fires when this thread's copies have landed
+            mbar_arrive(&bars[B_XF + st]);       // releases the meta block and the zero rows (plain stores)
+            // Gaussian basis -> A1 (single buffer: G1 of the previous tile must have read it)
+            float v[64];
 #pragma unroll
-            for (int ch = 0; ch < 8; ++ch) {
-                float v[8];
-#pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    const float u = d - goff[ch * 8 + q];
-                    v[q] = ex2a(c2 * u * u);
-                }
-                *reinterpret_cast<uint4*>(a1 + sw128_chunk_off(e, ch)) =
-                    make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+            for (int q = 0; q < 64; ++q) {
+                const float u = d - goff[q];
+                v[q] = ex2a(c2 * u * u);
             }
+            mbar_wait(&bars[B_A1E], (tc & 1u) ^ 1u);
+#pragma unroll
+            for (int ch = 0; ch < 8; ++ch)
+                *reinterpret_cast<uint4*>(sm + o2A1 + sw128_chunk_off(e, ch)) =
+                    make_uint4(pack_bf16(v[8 * ch], v[8 * ch + 1]), pack_bf16(v[8 * ch + 2], v[8 * ch + 3]),
+                               pack_bf16(v[8 * ch + 4], v[8 * ch + 5]), pack_bf16(v[8 * ch + 6], v[8 * ch + 7]));
             fence_proxy_async();
-            mbar_arrive(&bars[B_A1F + p]);
+            mbar_arrive(&bars[B_A1F]);
             e_cur += cnt;
         }
     } else if (warp < 8) {
@@ -208,9 +226,12 @@ __global__ void __launch_bounds__(512, 1) schnet_fwd_tc2_kernel(Tc2Args a) {  //
         const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
         for (uint32_t tc = 0;; ++tc) {
             const uint32_t p = tc & 1u, par = (tc >> 1) & 1u;
-            mbar_wait(&bars[B_A1F + p], par);
-            if (meta[p].cnt == 0) break;
             mbar_wait(&bars[B_D1F + p], par);
+            if (*end_g1 == (int)tc) {  // end of stream: pass it on to the G2 warp
+                if (e == 0) *end_e1 = (int)tc;
+                mbar_arrive(&bars[B_A2F]);
+                break;
+            }
             tc_fence_after();
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -235,39 +256,57 @@ __global__ void __launch_bounds__(512, 1) schnet_fwd_tc2_kernel(Tc2Args a) {  //
         const int e = t - 256;
         const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
         auto readout = [&](uint32_t tq) {  // D3 of tile tq: lane = feature column e, accumulator column = segment
-            const uint32_t p = tq & 1u;
-            const Meta& M = meta[p];
+            const uint32_t st = tq % kS2Stages;
+            const Meta& M = meta[st];
             float v[32];
-            tmem_ld32(tmD3 + p * 32 + lane_base, v);
+            tmem_ld32(tmD3 + st * 32 + lane_base, v);
             tc_fence_before();
             const int nseg = M.nseg;
+            const bool h0 = M.head0 != 0;
+            // read-modify-write of the rows of this tile, 8 segments at a time: all old values are requested before the
+            // first store so that the L2 round trips overlap (only this thread ever touches these addresses)
 #pragma unroll
-            for (int s = 0; s < kS2MaxSeg; ++s) {
-                if (s < nseg) {
-                    float* dst = (s == 0 && M.head0) ? a.head + (int64_t)blockIdx.x * 128 + e : a.agg + (int64_t)M.seg_row[s] * 128 + e;
-                    *dst += v[s];
+            for (int s0 = 0; s0 < kS2MaxSeg; s0 += 8) {
+                if (s0 < nseg) {
+                    float* dst[8];
+                    float old[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const int s = s0 + j;
+                        dst[j] = nullptr;
+                        old[j] = 0.f;
+                        if (s < nseg) {
+                            dst[j] = (s == 0 && h0) ? a.head + (int64_t)blockIdx.x * 128 + e : a.agg + (int64_t)M.seg_row[s] * 128 + e;
+                            old[j] = __ldcg(dst[j]);
+                        }
+                    }
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        if (dst[j]) *dst[j] = old[j] + v[s0 + j];
                 }
             }
-            mbar_arrive(&bars[B_D3E + p]);
-            mbar_arrive(&bars[B_DONE + p]);
+            mbar_arrive(&bars[B_D3E + st]);
+            mbar_arrive(&bars[B_DONE + st]);
         };
         uint32_t tc = 0;
         for (;; ++tc) {
-            const uint32_t p = tc & 1u, par = (tc >> 1) & 1u;
-            mbar_wait(&bars[B_A1F + p], par);   // the meta block (plain stores, released by the meta threads' arrive)
-            mbar_wait(&bars[B_XF + p], par);    // the gathered rows (cp.async completion)
-            const Meta& M = meta[p];
+            const uint32_t st = tc % kS2Stages, par = (tc / kS2Stages) & 1u;
+            mbar_wait(&bars[B_XF + st], par);    // gathered rows (cp.async) + meta block (plain stores)
+            const Meta& M = meta[st];
             const int cnt = M.cnt;
-            if (cnt == 0) break;
             if (tc > 0) {   // read out the previous tile first: releases its meta block early (the meta warps wait for it)
-                mbar_wait(&bars[B_D3F + ((tc - 1) & 1u)], ((tc - 1) >> 1) & 1u);
+                mbar_wait(&bars[B_D3F + ((tc - 1) % kS2Stages)], ((tc - 1) / kS2Stages) & 1u);
                 tc_fence_after();
                 readout(tc - 1);
+            }
+            if (cnt == 0) {  // end of stream: wake the G3 warp
+                mbar_arrive(&bars[B_MSGF + st]);
+                break;
             }
             mbar_wait(&bars[B_D2F], tc & 1u);
             tc_fence_after();
             const float C = M.C[e];
-            uint8_t* xs = sm + o2X + p * 32768;
+            uint8_t* xs = sm + o2X + st * 32768;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 float v[32];
@@ -301,70 +340,73 @@ __global__ void __launch_bounds__(512, 1) schnet_fwd_tc2_kernel(Tc2Args a) {  //
                 }
             }
             fence_proxy_async();
-            mbar_arrive(&bars[B_MSGF + p]);
+            mbar_arrive(&bars[B_MSGF + st]);
         }
-        if (tc > 0) {
-            mbar_wait(&bars[B_D3F + ((tc - 1) & 1u)], ((tc - 1) >> 1) & 1u);
-            tc_fence_after();
-            readout(tc - 1);
-        }
-    } else {
-        // ===================== MMA issuer (whole warp, one elected lane) =====================
-        const uint32_t id1 = umma_idesc_bf16(128, 128), id3 = umma_idesc_bf16(128, 32, true, true);
-        const uint32_t w1b = smem_u32(sm + o2W1), w2b = smem_u32(sm + o2W2), a2b = smem_u32(sm + o2A2), sb = smem_u32(sm + o2S);
-        auto g1 = [&](uint32_t tq) -> bool {  // returns false at the sentinel
-            const uint32_t p = tq & 1u, par = (tq >> 1) & 1u;
-            mbar_wait(&bars[B_A1F + p], par);
-            if (meta[p].cnt == 0) return false;
+    } else if (warp == 12) {
+        // ===================== G1 = rbf W1^T (whole warp, one elected lane issues) =====================
+        const uint32_t id1 = umma_idesc_bf16(128, 128);
+        const uint32_t w1b = smem_u32(sm + o2W1), a1b = smem_u32(sm + o2A1);
+        for (uint32_t tc = 0;; ++tc) {
+            const uint32_t p = tc & 1u, par = (tc >> 1) & 1u, st = tc % kS2Stages;
+            mbar_wait(&bars[B_A1F], tc & 1u);
+            if (meta[st].cnt == 0) {  // end of stream: tell epilogue 1
+                if (elect_one()) {
+                    *end_g1 = (int)tc;
+                    __threadfence_block();
+                    mbar_arrive(&bars[B_D1F + p]);
+                }
+                __syncwarp();
+                break;
+            }
             mbar_wait(&bars[B_D1E + p], par ^ 1u);
             tc_fence_after();
             if (elect_one()) {
-                umma_tile(tmD1 + p * 128, smem_u32(sm + o2A1 + p * 16384), 16384, w1b, 16384, 64, id1);
+                umma_tile(tmD1 + p * 128, a1b, 16384, w1b, 16384, 64, id1);
                 umma_commit(&bars[B_D1F + p]);
-                umma_commit(&bars[B_A1E + p]);
+                umma_commit(&bars[B_A1E]);
             }
             __syncwarp();
-            return true;
-        };
-        auto g3 = [&](uint32_t tq) {
-            const uint32_t p = tq & 1u, par = (tq >> 1) & 1u;
-            mbar_wait(&bars[B_MSGF + p], par);
-            mbar_wait(&bars[B_D3E + p], par ^ 1u);
+        }
+    } else if (warp == 13) {
+        // ===================== G2 = h1 W2^T =====================
+        const uint32_t id1 = umma_idesc_bf16(128, 128);
+        const uint32_t w2b = smem_u32(sm + o2W2), a2b = smem_u32(sm + o2A2);
+        for (uint32_t tc = 0;; ++tc) {
+            mbar_wait(&bars[B_A2F], tc & 1u);
+            if (*end_e1 == (int)tc) break;
+            mbar_wait(&bars[B_D2E], (tc & 1u) ^ 1u);
             tc_fence_after();
             if (elect_one()) {
-                const uint32_t mb = smem_u32(sm + o2X + p * 32768);
 #pragma unroll
-                for (int k16 = 0; k16 < 8; ++k16)
-                    umma_bf16(tmD3 + p * 32, umma_desc_mn128(mb + k16 * 2048, 16384), umma_desc_mn128(sb + k16 * 2048, 16384), id3, k16 ? 1u : 0u);
-                umma_commit(&bars[B_D3F + p]);
+                for (int ks = 0; ks < 2; ++ks) {
+#pragma unroll
+                    for (int k16 = 0; k16 < 4; ++k16)
+                        umma_bf16(tmD2, umma_desc_k128(a2b + ks * 16384 + k16 * 32), umma_desc_k128(w2b + ks * 16384 + k16 * 32), id1,
+                                  (ks | k16) ? 1u : 0u);
+                    umma_commit(&bars[B_A2E + ks]);
+                }
+                umma_commit(&bars[B_D2F]);
             }
             __syncwarp();
-        };
-        if (g1(0)) {
-            for (uint32_t tc = 0;; ++tc) {
-                if (tc > 0) g3(tc - 1);          // first: the meta warps need its completion before they can refill the stage
-                const bool more = g1(tc + 1);
-                // G2(tc)
-                mbar_wait(&bars[B_A2F], tc & 1u);
-                mbar_wait(&bars[B_D2E], (tc & 1u) ^ 1u);
-                tc_fence_after();
-                if (elect_one()) {
+        }
+    } else {
+        // ===================== G3 = msg^T S (the segmented row sum) =====================
+        const uint32_t id3 = umma_idesc_bf16(128, 32, true, true);
+        const uint32_t sb = smem_u32(sm + o2S);
+        for (uint32_t tc = 0;; ++tc) {
+            const uint32_t st = tc % kS2Stages, par = (tc / kS2Stages) & 1u;
+            mbar_wait(&bars[B_MSGF + st], par);
+            if (meta[st].cnt == 0) break;
+            mbar_wait(&bars[B_D3E + st], par ^ 1u);
+            tc_fence_after();
+            if (elect_one()) {
+                const uint32_t mb = smem_u32(sm + o2X + st * 32768);
 #pragma unroll
-                    for (int ks = 0; ks < 2; ++ks) {
-#pragma unroll
-                        for (int k16 = 0; k16 < 4; ++k16)
-                            umma_bf16(tmD2, umma_desc_k128(a2b + ks * 16384 + k16 * 32), umma_desc_k128(w2b + ks * 16384 + k16 * 32), id1,
-                                      (ks | k16) ? 1u : 0u);
-                        umma_commit(&bars[B_A2E + ks]);
-                    }
-                    umma_commit(&bars[B_D2F]);
-                }
-                __syncwarp();
-                if (!more) {
-                    g3(tc);
-                    break;
-                }
+                for (int k16 = 0; k16 < 8; ++k16)
+                    umma_bf16(tmD3 + st * 32, umma_desc_mn128(mb + k16 * 2048, 16384), umma_desc_mn128(sb + k16 * 2048, 16384), id3, k16 ? 1u : 0u);
+                umma_commit(&bars[B_D3F + st]);
             }
+            __syncwarp();
         }
     }
     tc_fence_before();
