@@ -3,11 +3,12 @@
 //
 //   warps 0-3   meta : edge scalars, cosine cutoff, row segments; cp.async gather of the bf16 x1[src] rows straight into
 //                      the swizzled operand image; Gaussian basis -> A1 (bf16)
-//   warps 12-14 MMA  : G1 = rbf W1^T -> D1;  G2 = h1 W2^T -> D2;  G3 = msg^T S -> D3   (tcgen05, accumulators in TMEM;
+//   warps 20-22 MMA  : G1 = rbf W1^T -> D1;  G2 = h1 W2^T -> D2;  G3 = msg^T S -> D3   (tcgen05, accumulators in TMEM;
 //                      one issuing warp per product so that no product waits behind another one's operands)
-//   warps 4-7   epi1 : D1 + b1 -> shifted softplus -> h1 (bf16) -> A2
-//   warps 8-11  epi2 : (D2 + b2) * C * x1[src] -> msg (bf16, in place over the gathered rows) and the one-hot
+//   warps 4-11  epi1 : D1 (+ b1, folded into a spare basis column) -> shifted softplus -> h1 (bf16) -> A2
+//   warps 12-19 epi2 : (D2 + b2) * C * x1[src] -> msg (bf16, in place over the gathered rows) and the one-hot
 //                      row-membership tile S; then, one tile behind, D3[c, seg] -> agg[row(seg), c] += ...
+//                      (both epilogues as two groups of four warps: thread = (edge row, 64 columns))
 //
 // The segmented sum over the destination rows is the third MMA: D3[c][s] = sum_e msg[e][c] * S[e][s] with S[e][s] = 1
 // when edge e belongs to the s-th row of the tile (both operands are read as MN-major images whose rows are edges).
@@ -24,7 +25,7 @@ namespace gmp {
 
 using namespace tc;
 
-constexpr int kS2Threads = 480;   // 15 warps: meta 0-3, epi1 4-7, epi2 8-11, one MMA-issuing warp per product 12-14
+constexpr int kS2Threads = 736;   // 23 warps: meta 0-3, epi1 4-11, epi2 12-19 (two groups each: columns 0-63 / 64-127), MMA 20-22
 constexpr int kS2MaxSeg = 32;
 constexpr int kS2Stages = 3;      // gathered-row / msg stages, meta blocks, D3 accumulators
 
@@ -79,7 +80,7 @@ struct Meta {
     int cnt, nseg, head0, pad;
 };
 
-__global__ void __launch_bounds__(512, 1) schnet_fwd_tc2_kernel(Tc2Args a) {  // 512: caps the registers at 128 per thread
+__global__ void __launch_bounds__(768, 1) schnet_fwd_tc2_kernel(Tc2Args a) {  // 768: caps the registers at 80 (6 warps on a scheduler)
     extern __shared__ __align__(16) uint8_t smraw[];
     uint8_t* sm = smraw + ((1024u - (smem_u32(smraw) & 1023u)) & 1023u);
     float* b1s = reinterpret_cast<float*>(sm + o2Vec);
@@ -100,7 +101,10 @@ __global__ void __launch_bounds__(512, 1) schnet_fwd_tc2_kernel(Tc2Args a) {  //
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const int g0 = ch * 8 + 2 * j;
-            p[j] = pack_bf16(g0 < a.G ? __ldg(a.w1 + f * a.G + g0) : 0.f, g0 + 1 < a.G ? __ldg(a.w1 + f * a.G + g0 + 1) : 0.f);
+            // column G (the first padding column, when there is one) carries b1: the basis tile holds a 1 there
+            const float lo = g0 < a.G ? __ldg(a.w1 + f * a.G + g0) : (g0 == a.G ? __ldg(a.b1 + f) : 0.f);
+            const float hi = g0 + 1 < a.G ? __ldg(a.w1 + f * a.G + g0 + 1) : (g0 + 1 == a.G ? __ldg(a.b1 + f) : 0.f);
+            p[j] = pack_bf16(lo, hi);
         }
         *reinterpret_cast<uint4*>(sm + o2W1 + sw128_chunk_off(f, ch)) = make_uint4(p[0], p[1], p[2], p[3]);
     }
@@ -110,19 +114,20 @@ __global__ void __launch_bounds__(512, 1) schnet_fwd_tc2_kernel(Tc2Args a) {  //
         *reinterpret_cast<uint4*>(sm + o2W2 + kb * 16384 + sw128_chunk_off(f, ch)) =
             make_uint4(pack_bf16(lo.x, lo.y), pack_bf16(lo.z, lo.w), pack_bf16(hi.x, hi.y), pack_bf16(hi.z, hi.w));
     }
-    if (t < 128) { b1s[t] = __ldg(a.b1 + t); b2s[t] = __ldg(a.b2 + t); }
+    if (t < 128) { b1s[t] = a.G < 64 ? 0.f : __ldg(a.b1 + t); b2s[t] = __ldg(a.b2 + t); }
     if (t < 64) goff[t] = t < a.G ? __ldg(a.goff + t) : 1.0e18f;  // padding columns: the Gaussian underflows to exactly 0
     if (t == 0) {
         *end_g1 = -1;
         *end_e1 = -1;
         for (int i = 0; i < B_COUNT; ++i) mbar_init(&bars[i], 1);
-        const int c128[] = {B_A1F, B_D1E, B_D1E + 1, B_A2F, B_D2E, B_MSGF, B_MSGF + 1, B_MSGF + 2, B_D3E, B_D3E + 1, B_D3E + 2,
-                            B_DONE, B_DONE + 1, B_DONE + 2};
-        for (int i = 0; i < 14; ++i) mbar_init(&bars[c128[i]], 128);
+        const int c128[] = {B_A1F, B_D3E, B_D3E + 1, B_D3E + 2, B_DONE, B_DONE + 1, B_DONE + 2};
+        for (int i = 0; i < 7; ++i) mbar_init(&bars[c128[i]], 128);
+        const int c256[] = {B_D1E, B_D1E + 1, B_A2F, B_D2E, B_MSGF, B_MSGF + 1, B_MSGF + 2};   // both column groups arrive
+        for (int i = 0; i < 7; ++i) mbar_init(&bars[c256[i]], 256);
         for (int i = 0; i < kS2Stages; ++i) mbar_init(&bars[B_XF + i], 256);  // 128 cp.async completions + 128 plain arrives
         fence_mbar_init();
     }
-    if (warp == 12) tmem_alloc<512>(tmem_ptr);
+    if (warp == 20) tmem_alloc<512>(tmem_ptr);
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
@@ -204,45 +209,46 @@ __global__ void __launch_bounds__(512, 1) schnet_fwd_tc2_kernel(Tc2Args a) {  //
             cp_async_arrive(&bars[B_XF + st]);   // fires when this thread's copies have landed
             mbar_arrive(&bars[B_XF + st]);       // releases the meta block and the zero rows (plain stores)
             // Gaussian basis -> A1 (single buffer: G1 of the previous tile must have read it)
-            float v[64];
-#pragma unroll
-            for (int q = 0; q < 64; ++q) {
-                const float u = d - goff[q];
-                v[q] = ex2a(c2 * u * u);
-            }
             mbar_wait(&bars[B_A1E], (tc & 1u) ^ 1u);
 #pragma unroll
-            for (int ch = 0; ch < 8; ++ch)
+            for (int ch = 0; ch < 8; ++ch) {
+                float v[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const float u = d - goff[ch * 8 + q];
+                    v[q] = (ch * 8 + q == a.G) ? 1.0f : ex2a(c2 * u * u);   // column G = 1: picks up b1 from the W1 image
+                }
                 *reinterpret_cast<uint4*>(sm + o2A1 + sw128_chunk_off(e, ch)) =
-                    make_uint4(pack_bf16(v[8 * ch], v[8 * ch + 1]), pack_bf16(v[8 * ch + 2], v[8 * ch + 3]),
-                               pack_bf16(v[8 * ch + 4], v[8 * ch + 5]), pack_bf16(v[8 * ch + 6], v[8 * ch + 7]));
+                    make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+            }
             fence_proxy_async();
             mbar_arrive(&bars[B_A1F]);
             e_cur += cnt;
         }
-    } else if (warp < 8) {
-        // ===================== epilogue 1: h1 = ssp(D1 + b1) -> A2 =====================
-        const int e = t - 128;
+    } else if (warp < 12) {
+        // ===================== epilogue 1: h1 = ssp(D1 + b1) -> A2; group g owns columns [64 g, 64 g + 64) = K slab g =====================
+        const int e = (warp & 3) * 32 + lane, g = (warp - 4) >> 2;
         const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+        const bool add_b1 = a.G >= 64;   // otherwise b1 came through the spare basis column
         for (uint32_t tc = 0;; ++tc) {
             const uint32_t p = tc & 1u, par = (tc >> 1) & 1u;
             mbar_wait(&bars[B_D1F + p], par);
             if (*end_g1 == (int)tc) {  // end of stream: pass it on to the G2 warp
-                if (e == 0) *end_e1 = (int)tc;
+                if (t == 128) *end_e1 = (int)tc;
                 mbar_arrive(&bars[B_A2F]);
                 break;
             }
             tc_fence_after();
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
+            for (int j = 0; j < 2; ++j) {
                 float v[32];
-                tmem_ld32(tmD1 + p * 128 + lane_base + 32 * j, v);
+                tmem_ld32(tmD1 + p * 128 + lane_base + 64 * g + 32 * j, v);
 #pragma unroll
-                for (int q = 0; q < 32; ++q) v[q] = ssp2(v[q] + b1s[32 * j + q]);
-                if ((j & 1) == 0) mbar_wait(&bars[B_A2E + (j >> 1)], (tc & 1u) ^ 1u);  // G2 of the previous tile has read this K slab
+                for (int q = 0; q < 32; ++q) v[q] = ssp2(add_b1 ? v[q] + b1s[64 * g + 32 * j + q] : v[q]);
+                if (j == 0) mbar_wait(&bars[B_A2E + g], (tc & 1u) ^ 1u);  // G2 of the previous tile has read this K slab
 #pragma unroll
                 for (int q = 0; q < 4; ++q)
-                    *reinterpret_cast<uint4*>(sm + o2A2 + (j >> 1) * 16384 + sw128_chunk_off(e, (j & 1) * 4 + q)) =
+                    *reinterpret_cast<uint4*>(sm + o2A2 + g * 16384 + sw128_chunk_off(e, j * 4 + q)) =
                         make_uint4(pack_bf16(v[8 * q], v[8 * q + 1]), pack_bf16(v[8 * q + 2], v[8 * q + 3]),
                                    pack_bf16(v[8 * q + 4], v[8 * q + 5]), pack_bf16(v[8 * q + 6], v[8 * q + 7]));
             }
@@ -251,9 +257,10 @@ __global__ void __launch_bounds__(512, 1) schnet_fwd_tc2_kernel(Tc2Args a) {  //
             fence_proxy_async();
             mbar_arrive(&bars[B_A2F]);
         }
-    } else if (warp < 12) {
-        // ===================== epilogue 2: msg, one-hot tile; read-out of the previous tile =====================
-        const int e = t - 256;
+    } else if (warp < 20) {
+        // ===================== epilogue 2: msg (group g: columns [64 g, 64 g + 64)); group 0 also writes the one-hot tile,
+        // group 1 reads out the previous tile (lane = feature column) =====================
+        const int e = (warp & 3) * 32 + lane, g = (warp - 12) >> 2;
         const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
         auto readout = [&](uint32_t tq) {  // D3 of tile tq: lane = feature column e, accumulator column = segment
             const uint32_t st = tq % kS2Stages;
@@ -294,10 +301,10 @@ __global__ void __launch_bounds__(512, 1) schnet_fwd_tc2_kernel(Tc2Args a) {  //
             mbar_wait(&bars[B_XF + st], par);    // gathered rows (cp.async) + meta block (plain stores)
             const Meta& M = meta[st];
             const int cnt = M.cnt;
-            if (tc > 0) {   // read out the previous tile first: releases its meta block early (the meta warps wait for it)
+            if (tc > 0) {   // G3 of the previous tile is done: its accumulator can be read out, the one-hot tile rewritten
                 mbar_wait(&bars[B_D3F + ((tc - 1) % kS2Stages)], ((tc - 1) / kS2Stages) & 1u);
                 tc_fence_after();
-                readout(tc - 1);
+                if (g == 1) readout(tc - 1);   // first: releases the meta block early (the meta warps wait for it)
             }
             if (cnt == 0) {  // end of stream: wake the G3 warp
                 mbar_arrive(&bars[B_MSGF + st]);
@@ -308,18 +315,18 @@ __global__ void __launch_bounds__(512, 1) schnet_fwd_tc2_kernel(Tc2Args a) {  //
             const float C = M.C[e];
             uint8_t* xs = sm + o2X + st * 32768;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
+            for (int j = 0; j < 2; ++j) {
                 float v[32];
-                tmem_ld32(tmD2 + lane_base + 32 * j, v);
+                tmem_ld32(tmD2 + lane_base + 64 * g + 32 * j, v);
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
-                    uint4* px = reinterpret_cast<uint4*>(xs + (j >> 1) * 16384 + sw128_chunk_off(e, (j & 1) * 4 + q));
+                    uint4* px = reinterpret_cast<uint4*>(xs + g * 16384 + sw128_chunk_off(e, j * 4 + q));
                     const uint4 xr = *px;
                     const uint32_t w[4] = {xr.x, xr.y, xr.z, xr.w};
                     uint32_t o[4];
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {
-                        const int c0 = 32 * j + 8 * q + 2 * u;
+                        const int c0 = 64 * g + 32 * j + 8 * q + 2 * u;
                         const float m0 = (v[8 * q + 2 * u] + b2s[c0]) * C * __uint_as_float(w[u] << 16);
                         const float m1 = (v[8 * q + 2 * u + 1] + b2s[c0 + 1]) * C * __uint_as_float(w[u] & 0xffff0000u);
                         o[u] = pack_bf16(m0, m1);   // C = 0 and zero rows for the padding slots
@@ -330,7 +337,7 @@ __global__ void __launch_bounds__(512, 1) schnet_fwd_tc2_kernel(Tc2Args a) {  //
             tc_fence_before();
             mbar_arrive(&bars[B_D2E]);
             // one-hot row-membership tile (single buffer: G3 of the previous tile has read it -- waited for above)
-            {
+            if (g == 0) {
                 const int seg = M.seg[e];
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
@@ -342,7 +349,7 @@ __global__ void __launch_bounds__(512, 1) schnet_fwd_tc2_kernel(Tc2Args a) {  //
             fence_proxy_async();
             mbar_arrive(&bars[B_MSGF + st]);
         }
-    } else if (warp == 12) {
+    } else if (warp == 20) {
         // ===================== G1 = rbf W1^T (whole warp, one elected lane issues) =====================
         const uint32_t id1 = umma_idesc_bf16(128, 128);
         const uint32_t w1b = smem_u32(sm + o2W1), a1b = smem_u32(sm + o2A1);
@@ -367,7 +374,7 @@ __global__ void __launch_bounds__(512, 1) schnet_fwd_tc2_kernel(Tc2Args a) {  //
             }
             __syncwarp();
         }
-    } else if (warp == 13) {
+    } else if (warp == 21) {
         // ===================== G2 = h1 W2^T =====================
         const uint32_t id1 = umma_idesc_bf16(128, 128);
         const uint32_t w2b = smem_u32(sm + o2W2), a2b = smem_u32(sm + o2A2);
@@ -411,7 +418,7 @@ __global__ void __launch_bounds__(512, 1) schnet_fwd_tc2_kernel(Tc2Args a) {  //
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 12) tmem_dealloc<512>(tm);
+    if (warp == 20) tmem_dealloc<512>(tm);
 }
 
 // rows that straddle a CTA boundary: add the later CTAs' head partials in CTA order
