@@ -281,7 +281,7 @@ def main_gpu(args):
                     config={"workload": WORKLOAD, "nodes_per_gpu": N, "edges_per_gpu": E, "layers": L,
                             "precision": args.precision,
                             "tolerance_vs_fp32_reference": 1e-2 if args.precision == "bf16" else 1e-5,
-                            "node_side_gemms": "cuBLAS TF32" if args.precision == "bf16" else "cuBLAS fp32", "parallelism": f"graph-sharded x{world}",
+                            "node_side_gemms": "cuBLAS TF32 forward / dx; dW, db on tcgen05 (linear_wgrad_tc_kernel)" if args.precision == "bf16" else "cuBLAS fp32", "parallelism": f"graph-sharded x{world}",
                             "l2": "per-step working set (x1/agg/g rows of 6 layers, >2 GB) exceeds the 126 MB L2"},
                     roofline=roof, cpu_baseline=cpu, fp32_strict=strict,
                     e2e={"value": E_total * L / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
@@ -317,14 +317,22 @@ def dominant_kernel_roofline(model, b, E, N, dev, args):
     x1 = torch.randn(N, F, device=dev)
     agg = torch.empty(N, F, device=dev)
     prec = 0 if args.precision == "fp32" else 1
+    lib = gmp_b200._lib.lib()
+    x1b = x1.to(torch.bfloat16)
+    head = torch.empty(lib.gmp_schnet_tc2_num_chunks(E), F, device=dev)
+    rowid = csr.row_ids()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     times = []
     for it in range(3 + 10):
         flush.zero_()  # write 256 MB > L2 between launches
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s.record()
-        call("gmp_schnet_cfconv_fwd", ptr(csr.rowptr), ptr(csr.col), csr.perm_ptr, N, E, ptr(ew), None, ptr(x1),
-             C.byref(filt), ptr(agg), prec)
+        if prec == 1:   # the entry point the bf16 model path calls (zeroes agg, runs the pipelined kernel and the boundary fix-up)
+            call("gmp_schnet_cfconv_fwd_tc2", ptr(csr.rowptr), ptr(csr.col), csr.perm_ptr, ptr(rowid), N, E, ptr(ew), ptr(x1b),
+                 C.byref(filt), ptr(agg), ptr(head))
+        else:
+            call("gmp_schnet_cfconv_fwd", ptr(csr.rowptr), ptr(csr.col), csr.perm_ptr, N, E, ptr(ew), None, ptr(x1),
+                 C.byref(filt), ptr(agg), prec)
         e.record()
         torch.cuda.synchronize()
         if it >= 3:
@@ -333,14 +341,17 @@ def dominant_kernel_roofline(model, b, E, N, dev, args):
     alg = E * (4 * F + 8) + N * (4 * F + 4)
     achieved = alg / (ms * 1e-3) / 1e9
     flops = E * (2 * 64 * F + 2 * F * F + 2 * F)  # padded-G GEMM1 + GEMM2 + message product
-    kname = "schnet_fwd_tc_kernel (tcgen05, bf16)" if prec == 1 else "schnet_fwd_kernel<128> (fp32 FFMA)"
-    return {"bound": "hbm", "kernel": kname + " via gmp_schnet_cfconv_fwd", "achieved": achieved, "peak": peak,
-            "unit": "GB/s", "frac": achieved / peak,
-            # dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full capture of this kernel
-            # (profiles/r01_ncu_prof_tc_fwd_v3.csv: 82.4 + 32.2 MB; x1 is L2-resident, hence far below the algorithmic bytes)
-            "traffic": 114.7e6 if prec == 1 else None, "peak_source": which, "ms_per_launch": ms,
-            "algorithmic_bytes": alg, "note": f"{flops / (ms * 1e-3) / 1e12:.1f} TFLOP/s on the filter-MLP GEMMs ({'bf16 tcgen05' if prec == 1 else 'fp32 FFMA'}); the x1 gather is "
-                    "mostly served by the 126 MB L2 (x1 is 67 MB), so DRAM traffic is below the algorithmic bytes"}
+    if prec == 1:
+        kname = "schnet_fwd_tc2_kernel (tcgen05, bf16, pipelined; time includes the agg memset and the boundary fix-up) via gmp_schnet_cfconv_fwd_tc2"
+        note = (f"{flops / (ms * 1e-3) / 1e12:.1f} TFLOP/s on the filter-MLP GEMMs (bf16 tcgen05); algorithmic bytes are SURVEY 8d's "
+                "fp32 figure -- the kernel itself gathers x1 as bf16 rows (256 B/edge) and x1 (34 MB) is L2-resident; per ncu the "
+                "kernel is issue-bound (42 % issue slots busy, ALU 24 / XU 21 / FMA 21 / LSU 16 %, tensor 12 %), not HBM-bound")
+    else:
+        kname = "schnet_fwd_kernel<128> (fp32 FFMA) via gmp_schnet_cfconv_fwd"
+        note = f"{flops / (ms * 1e-3) / 1e12:.1f} TFLOP/s on the filter-MLP GEMMs (fp32 FFMA)"
+    return {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            # no --set full capture of the pipelined kernel this round (the source-counter pass did not finish within 10 min)
+            "traffic": None, "peak_source": which, "ms_per_launch": ms, "algorithmic_bytes": alg, "note": note}
 
 
 if __name__ == "__main__":
