@@ -320,10 +320,13 @@ __global__ void __launch_bounds__(256, 1) schnet_fwd_tc_kernel(TcArgs a, float* 
             float* Xt = Xbuf(buf);
             __syncthreads();  // A1(i) complete (written during the previous walker phase / prologue)
             // ---- GEMM1  D1 = rbf W1^T
-            if (t == 0) {
+            if (warp == 0) {  // warp-uniform: one elected lane issues, operands stay in uniform registers
                 tc_fence_after();
-                umma_tile(tmD1, smem_u32(sm + oA1), 16384, smem_u32(sm + oW1b), 16384, 64, idesc);
-                umma_commit(&bars[0]);
+                if (elect_one()) {
+                    umma_tile(tmD1, smem_u32(sm + oA1), 16384, smem_u32(sm + oW1b), 16384, 64, idesc);
+                    umma_commit(&bars[0]);
+                }
+                __syncwarp();
             }
             if (has_next && t < kTcTile) publish_scalars(nxt, cnt_next, buf ^ 1);
             // ---- epilogue 1: h1 = ssp(D1 + b1) -> A2 (bf16, swizzled; slab 0 overwrites the rbf tile GEMM1 has consumed)
@@ -348,10 +351,13 @@ __global__ void __launch_bounds__(256, 1) schnet_fwd_tc_kernel(TcArgs a, float* 
             fence_proxy_async();
             __syncthreads();  // also publishes the next tile's scalars
             // ---- GEMM2  D2 = h1 W2^T
-            if (t == 0) {
+            if (warp == 0) {  // warp-uniform: one elected lane issues, operands stay in uniform registers
                 tc_fence_after();
-                umma_tile(tmD2, smem_u32(sm + oA2), 16384, smem_u32(sm + oW2b), 16384, 128, idesc);
-                umma_commit(&bars[1]);
+                if (elect_one()) {
+                    umma_tile(tmD2, smem_u32(sm + oA2), 16384, smem_u32(sm + oW2b), 16384, 128, idesc);
+                    umma_commit(&bars[1]);
+                }
+                __syncwarp();
             }
             // ---- prefetch: gather of the next tile into the other X buffer
             if (has_next) {
@@ -610,10 +616,13 @@ schnet_bwd_tc_kernel(TcArgs a, const float* __restrict__ g_agg, float* __restric
             __pipeline_wait_prior(0);  // x1 rows of this tile
             __syncthreads();           // [A] R[buf], X, scalars(buf) complete
             const uint32_t Rb = smem_u32(sm + bR + buf * 16384), Pb = smem_u32(sm + bP), Hb = smem_u32(sm + bH);
-            if (t == 0) {
+            if (warp == 0) {  // warp-uniform: one elected lane issues, operands stay in uniform registers
                 tc_fence_after();
-                umma_tile(tmD1, Rb, 16384, smem_u32(sm + bW1b), 16384, 64, id_kk);
-                umma_commit(&bars[0]);
+                if (elect_one()) {
+                    umma_tile(tmD1, Rb, 16384, smem_u32(sm + bW1b), 16384, 64, id_kk);
+                    umma_commit(&bars[0]);
+                }
+                __syncwarp();
             }
             // ---- P = x1[src] * g[dst] * C   (bf16, [e][f'])
             {
@@ -653,12 +662,15 @@ schnet_bwd_tc_kernel(TcArgs a, const float* __restrict__ g_agg, float* __restric
             tc_fence_before();
             fence_proxy_async();
             __syncthreads();  // [B] P, H complete; X consumed; next scalars published
-            if (t == 0) {
+            if (warp == 0) {  // warp-uniform: one elected lane issues, operands stay in uniform registers
                 tc_fence_after();
-                umma_tile(tmD3, Pb, 16384, smem_u32(sm + bW2T), 16384, 128, id_kk);       // dh1 = P W2
-                umma_tile_mn(tmW2, Pb, 16384, Hb, 16384, 128, id_mn128, it > 0);            // dW2 += P^T H
-                umma_tile_mn(tmB2, Pb, 16384, Rb, 16384, 128, id_mn64, it > 0);             // [. | db2] += P^T R
-                umma_commit(&bars[1]);
+                if (elect_one()) {
+                    umma_tile(tmD3, Pb, 16384, smem_u32(sm + bW2T), 16384, 128, id_kk);       // dh1 = P W2
+                    umma_tile_mn(tmW2, Pb, 16384, Hb, 16384, 128, id_mn128, it > 0);            // dW2 += P^T H
+                    umma_tile_mn(tmB2, Pb, 16384, Rb, 16384, 128, id_mn64, it > 0);             // [. | db2] += P^T R
+                    umma_commit(&bars[1]);
+                }
+                __syncwarp();
             }
             if (has_next) issue_gather(cnt_next, buf ^ 1);
             // ---- Q = D3 * sigmoid(pre1), sigmoid from h1: 1 - exp(-softplus) = 1 - 0.5 * 2^(-h1 log2 e)
@@ -689,10 +701,13 @@ schnet_bwd_tc_kernel(TcArgs a, const float* __restrict__ g_agg, float* __restric
             tc_fence_before();
             fence_proxy_async();
             __syncthreads();  // [C] Q complete
-            if (t == 0) {
+            if (warp == 0) {  // warp-uniform: one elected lane issues, operands stay in uniform registers
                 tc_fence_after();
-                umma_tile_mn(tmW1, Pb, 16384, Rb, 16384, 128, id_mn64, it > 0);             // [dW1 | db1] += Q^T R
-                umma_commit(&bars[2]);
+                if (elect_one()) {
+                    umma_tile_mn(tmW1, Pb, 16384, Rb, 16384, 128, id_mn64, it > 0);             // [dW1 | db1] += Q^T R
+                    umma_commit(&bars[2]);
+                }
+                __syncwarp();
             }
             drained = false;
             if (has_next) rbf_tile(buf ^ 1, cnt_next);  // R[buf ^ 1] was last read by the tile before this one (drained above)
