@@ -139,3 +139,38 @@ def test_egnn_bf16_tc_vs_fp32(act, aggr, n, side):
             assert _l2_rel(a, b) <= 0.1, k
     o16b, q16b = m16(h16, p16, ei)
     assert torch.equal(o16, o16b) and torch.equal(q16, q16b)  # deterministic
+
+
+@pytest.mark.parametrize("n,deg,shuffle", [(5000, 2, True), (300, 40, False), (70000, 9, True), (64, 0, False)])
+def test_cfconv_pipelined_forward_edge_cases(n, deg, shuffle):
+    """The pipelined three-MMA CFConv forward (csrc/schnet_tc2.cu) against the fp32 kernel on graphs that exercise its
+    corners: low degree (more than 32 destination rows per 128 edges: tiles are cut), isolated nodes (empty rows),
+    rows straddling tile and CTA boundaries (head buffer + fix-up; 70 000 x 9 edges = enough tiles for every SM),
+    shuffled edge order (perm), high degree (one row spanning tiles), and the empty graph."""
+    import gmp_b200
+    g = torch.Generator().manual_seed(n + deg)
+    E = n * deg
+    dst = torch.randint(0, max(n - n // 7, 1), (E,), generator=g)      # the last n/7 nodes never receive an edge
+    src = torch.randint(0, n, (E,), generator=g)
+    if not shuffle:
+        dst = dst.sort().values
+    ei = torch.stack([src, dst]).cuda()
+    torch.manual_seed(0)
+    m32 = gmp_b200.InteractionBlock(128, 50, 128, 5.0).cuda()
+    with torch.no_grad():
+        for p in m32.parameters():
+            if p.dim() == 1:
+                p.normal_(0, 0.3)
+    m16 = gmp_b200.InteractionBlock(128, 50, 128, 5.0, precision="bf16").cuda()
+    m16.load_state_dict(m32.state_dict())
+    sm = gmp_b200.GaussianSmearing(0.0, 5.0, 50).cuda()
+    x = torch.randn(n, 128, device="cuda")
+    ew = torch.rand(E, generator=g).cuda() * 5.0
+    x32, x16 = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
+    o32, o16 = m32(x32, ei, ew, sm.lazy()), m16(x16, ei, ew, sm.lazy())
+    assert rel_err(o16, o32) <= 1e-2
+    cot = torch.randn_like(o32)
+    (g32,) = torch.autograd.grad((o32 * cot).sum(), [x32])
+    (g16,) = torch.autograd.grad((o16 * cot).sum(), [x16])   # d/dx1 runs the same kernel over the transposed CSR
+    assert rel_err(g16, g32) <= 1e-2
+    assert torch.equal(o16, m16(x16, ei, ew, sm.lazy()))
