@@ -444,6 +444,318 @@ __global__ void __launch_bounds__(128) schnet_tc2_fixup_kernel(const int32_t* __
         if (hrow[ch] >= 0) agg[(int64_t)hrow[ch] * 128 + c] += head[(int64_t)ch * 128 + c];
 }
 
+// ------------------------------------------------------------------------------------------------
+// filter-side backward, pipelined (weight gradients of the filter MLP; GMP_BF16_TC, F = 128, G <= 63, lazy basis).
+// Same mathematics as schnet_bwd_tc_kernel:
+//   G1  D1 = R W1^T (b1 rides in column 63 of the basis tile)       H = ssp(D1)                       (epiH)
+//   P   = x1[src] * g[dst] * C  (over the gathered bf16 rows)                                          (epiP)
+//   G3  D3 = P W2;  dW2 += P^T H;  db2 += P^T 1                                                        (accumulators in TMEM)
+//   Q   = D3 * sigmoid(pre1), sigmoid from h1, written over P                                          (epiQ)
+//   G4  [dW1 | db1] += Q^T R
+// Warps: meta 0-3 | epiP 4-7 | epiH 8-15 | epiQ 16-23 | MMA issue 24 (G1), 25 (G3), 26 (G4).  Stages R, rows/P/Q, H two deep;
+// D1, D3 single.  TMEM: D1 @0 | D3 @128 | dW2 @256 | dW1|db1 @384 (64) | db2 @448 (16).
+// ------------------------------------------------------------------------------------------------
+constexpr int kB2Threads = 864;   // 27 warps
+constexpr int o3W1 = 0;                    // [128 f][64 g], column 63 = b1          16 KB
+constexpr int o3W2T = 16384;               // 2 slabs [128 f][64 f'] (W2 transposed) 32 KB
+constexpr int o3R = o3W2T + 32768;         // 2 x 16 KB basis tiles (ones column at g = 63)
+constexpr int o3X = o3R + 2 * 16384;       // 2 x 32 KB gathered rows -> P -> Q
+constexpr int o3H = o3X + 2 * 32768;       // 2 x 32 KB h1
+constexpr int o3Ones = o3H + 2 * 32768;    // 4 KB of bf16 ones
+constexpr int o3Vec = o3Ones + 4096;       // goff[64]
+constexpr int o3Meta = o3Vec + 256;        // 2 x { C[128] f32, grow[128] i32 }
+constexpr int o3Bar = o3Meta + 2 * 1024;
+enum { C_RF = 0, C_XF = 2, C_PF = 4, C_HF = 6, C_QF = 8, C_DONE = 10, C_D1F = 12, C_D1E = 13, C_D3F = 14, C_D3E = 15, C_COUNT = 16 };
+constexpr int kTc2BwdSmem = o3Bar + C_COUNT * 8 + 16 + 1024;
+
+struct Tc2BwdArgs {
+    Tc2Args f;
+    const float* g_agg;   // [n,128] dL/dagg, read at the destination (CSR row) node
+    float* parts;         // [gridDim.x][128*64 + 128 + 128*128 + 128]
+};
+
+__global__ void __launch_bounds__(896, 1) schnet_bwd_tc2_kernel(Tc2BwdArgs b) {  // 896: caps the registers at 72
+    const Tc2Args& a = b.f;
+    extern __shared__ __align__(16) uint8_t smraw[];
+    uint8_t* sm = smraw + ((1024u - (smem_u32(smraw) & 1023u)) & 1023u);
+    float* goff = reinterpret_cast<float*>(sm + o3Vec);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sm + o3Bar);
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(sm + o3Bar + C_COUNT * 8);
+    const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+    auto metaC = [&](uint32_t p) { return reinterpret_cast<float*>(sm + o3Meta + p * 1024); };
+    auto metaRow = [&](uint32_t p) { return reinterpret_cast<int*>(sm + o3Meta + p * 1024 + 512); };
+
+    for (int x = t; x < 128 * 8; x += kB2Threads) {  // W1 [f][g] K-major, g padded to 64; column 63 = b1
+        const int f = x >> 3, ch = x & 7;
+        uint32_t p[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int g0 = ch * 8 + 2 * j;
+            const float lo = g0 < a.G ? __ldg(a.w1 + f * a.G + g0) : 0.f;
+            const float hi = g0 + 1 < a.G ? __ldg(a.w1 + f * a.G + g0 + 1) : (g0 + 1 == 63 ? __ldg(a.b1 + f) : 0.f);
+            p[j] = pack_bf16(lo, hi);
+        }
+        *reinterpret_cast<uint4*>(sm + o3W1 + sw128_chunk_off(f, ch)) = make_uint4(p[0], p[1], p[2], p[3]);
+    }
+    for (int x = t; x < 128 * 16; x += kB2Threads) {  // W2T [f][f'] = W2[f'][f], K = f' in two slabs
+        const int f = x >> 4, ch16 = x & 15, kb = ch16 >> 3, ch = ch16 & 7;
+        float v[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) v[q] = __ldg(a.w2 + (int64_t)(kb * 64 + ch * 8 + q) * 128 + f);
+        *reinterpret_cast<uint4*>(sm + o3W2T + kb * 16384 + sw128_chunk_off(f, ch)) =
+            make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+    }
+    for (int i = t; i < 2048; i += kB2Threads) reinterpret_cast<uint16_t*>(sm + o3Ones)[i] = 0x3f80;
+    if (t < 64) goff[t] = t < a.G ? __ldg(a.goff + t) : 1.0e18f;
+    if (t == 0) {
+        for (int i = 0; i < C_COUNT; ++i) mbar_init(&bars[i], 1);
+        mbar_init(&bars[C_RF], 128); mbar_init(&bars[C_RF + 1], 128);
+        mbar_init(&bars[C_XF], 256); mbar_init(&bars[C_XF + 1], 256);
+        mbar_init(&bars[C_PF], 128); mbar_init(&bars[C_PF + 1], 128);
+        mbar_init(&bars[C_HF], 256); mbar_init(&bars[C_HF + 1], 256);
+        mbar_init(&bars[C_QF], 256); mbar_init(&bars[C_QF + 1], 256);
+        mbar_init(&bars[C_D1E], 256);
+        mbar_init(&bars[C_D3E], 256);
+        fence_mbar_init();
+    }
+    if (warp == 24) tmem_alloc<512>(tmem_ptr);
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tm = *tmem_ptr;
+    const uint32_t tmD1 = tm, tmD3 = tm + 128, tmW2 = tm + 256, tmW1 = tm + 384, tmB2 = tm + 448;
+
+    const int64_t e_begin = (a.E * blockIdx.x) / gridDim.x, e_end = (a.E * (blockIdx.x + 1)) / gridDim.x;
+    const uint32_t ntile = (uint32_t)((e_end - e_begin + 127) / 128);
+
+    if (warp < 4) {
+        // ===================== meta =====================
+        const int e = t;
+        const float cw = 3.14159265358979323846f / a.cutoff;
+        const float c2 = a.gcoeff * 1.4426950408889634f;
+        for (uint32_t tc = 0; tc < ntile; ++tc) {
+            const uint32_t p = tc & 1u, par = (tc >> 1) & 1u;
+            const int64_t k = e_begin + (int64_t)tc * 128 + e;
+            const bool valid = k < e_end;
+            int src = 0, grow = 0;
+            float d = 1.0e18f, C = 0.f;
+            if (valid) {
+                const int eid = a.perm ? __ldg(a.perm + k) : (int)k;
+                src = __ldg(a.col + k);
+                grow = __ldg(a.rowid + k);
+                d = __ldg(a.ew + eid);
+                C = 0.5f * (__cosf(d * cw) + 1.0f);
+            }
+            mbar_wait(&bars[C_DONE + p], par ^ 1u);   // G4 of tile tc-2 done: every buffer of stage p is free
+            metaC(p)[e] = C;
+            metaRow(p)[e] = grow;
+            uint8_t* xs = sm + o3X + p * 32768;
+            if (valid) {
+                const __nv_bfloat16* row = a.x1 + (int64_t)src * 128;
+#pragma unroll
+                for (int ch = 0; ch < 16; ++ch)
+                    __pipeline_memcpy_async(xs + (ch >> 3) * 16384 + sw128_chunk_off(e, ch & 7), row + ch * 8, 16);
+            } else {
+#pragma unroll
+                for (int ch = 0; ch < 16; ++ch)
+                    *reinterpret_cast<uint4*>(xs + (ch >> 3) * 16384 + sw128_chunk_off(e, ch & 7)) = make_uint4(0u, 0u, 0u, 0u);
+            }
+            cp_async_arrive(&bars[C_XF + p]);
+            mbar_arrive(&bars[C_XF + p]);
+            uint8_t* rs = sm + o3R + p * 16384;
+#pragma unroll
+            for (int ch = 0; ch < 8; ++ch) {
+                float v[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const float u = d - goff[ch * 8 + q];
+                    v[q] = ex2a(c2 * u * u);
+                }
+                if (ch == 7) v[7] = 1.0f;   // ones column: bias of GEMM 1, and the column sums db1 in the dW1 accumulator
+                *reinterpret_cast<uint4*>(rs + sw128_chunk_off(e, ch)) =
+                    make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+            }
+            fence_proxy_async();
+            mbar_arrive(&bars[C_RF + p]);
+        }
+    } else if (warp < 8) {
+        // ===================== epiP: P = x1[src] * g[dst] * C over the gathered rows =====================
+        const int e = t - 128;
+        for (uint32_t tc = 0; tc < ntile; ++tc) {
+            const uint32_t p = tc & 1u, par = (tc >> 1) & 1u;
+            mbar_wait(&bars[C_XF + p], par);
+            const float C = metaC(p)[e];
+            const float4* gr = reinterpret_cast<const float4*>(b.g_agg + (int64_t)metaRow(p)[e] * 128);
+            uint8_t* xs = sm + o3X + p * 32768;
+#pragma unroll
+            for (int ch = 0; ch < 16; ++ch) {
+                uint4* px = reinterpret_cast<uint4*>(xs + (ch >> 3) * 16384 + sw128_chunk_off(e, ch & 7));
+                const uint4 xr = *px;
+                const float4 g0 = __ldg(gr + 2 * ch), g1 = __ldg(gr + 2 * ch + 1);   // C = 0 for the padding slots
+                const uint32_t w[4] = {xr.x, xr.y, xr.z, xr.w};
+                const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+                uint32_t o[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    o[u] = pack_bf16(__uint_as_float(w[u] << 16) * gg[2 * u] * C, __uint_as_float(w[u] & 0xffff0000u) * gg[2 * u + 1] * C);
+                *px = make_uint4(o[0], o[1], o[2], o[3]);
+            }
+            fence_proxy_async();
+            mbar_arrive(&bars[C_PF + p]);
+        }
+    } else if (warp < 16) {
+        // ===================== epiH: h1 = ssp(D1) -> H; group g owns columns [64 g, 64 g + 64) =====================
+        const int e = (warp & 3) * 32 + lane, g = (warp - 8) >> 2;
+        const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+        for (uint32_t tc = 0; tc < ntile; ++tc) {
+            const uint32_t p = tc & 1u;
+            mbar_wait(&bars[C_D1F], tc & 1u);
+            tc_fence_after();
+            uint8_t* hs = sm + o3H + p * 32768 + g * 16384;
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                float v[32];
+                tmem_ld32(tmD1 + lane_base + 64 * g + 32 * j, v);
+                if (j == 1) {   // both loads of this thread are done: G1 of the next tile may overwrite D1
+                    tc_fence_before();
+                    mbar_arrive(&bars[C_D1E]);
+                }
+#pragma unroll
+                for (int q = 0; q < 32; ++q) v[q] = ssp2(v[q]);
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    *reinterpret_cast<uint4*>(hs + sw128_chunk_off(e, j * 4 + q)) =
+                        make_uint4(pack_bf16(v[8 * q], v[8 * q + 1]), pack_bf16(v[8 * q + 2], v[8 * q + 3]),
+                                   pack_bf16(v[8 * q + 4], v[8 * q + 5]), pack_bf16(v[8 * q + 6], v[8 * q + 7]));
+            }
+            fence_proxy_async();
+            mbar_arrive(&bars[C_HF + p]);
+        }
+    } else if (warp < 24) {
+        // ===================== epiQ: Q = D3 * sigmoid(pre1) over P; at the end, the accumulators =====================
+        const int e = (warp & 3) * 32 + lane, g = (warp - 16) >> 2;
+        const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+        for (uint32_t tc = 0; tc < ntile; ++tc) {
+            const uint32_t p = tc & 1u;
+            mbar_wait(&bars[C_D3F], tc & 1u);   // G3 done: D3 ready, P and H no longer read by the tensor core
+            tc_fence_after();
+            uint8_t* hs = sm + o3H + p * 32768 + g * 16384;
+            uint8_t* qs = sm + o3X + p * 32768 + g * 16384;
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                float v[32];
+                tmem_ld32(tmD3 + lane_base + 64 * g + 32 * j, v);
+                if (j == 1) {
+                    tc_fence_before();
+                    mbar_arrive(&bars[C_D3E]);
+                }
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const uint32_t off = sw128_chunk_off(e, j * 4 + q);
+                    const uint4 hp = *reinterpret_cast<const uint4*>(hs + off);
+                    const uint32_t hw[4] = {hp.x, hp.y, hp.z, hp.w};
+                    uint32_t o[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        // sigmoid(pre1) = 1 - exp(-softplus(pre1)) = 1 - 0.5 * 2^(-h1 log2 e)   (h1 = softplus - ln 2)
+                        const float s0 = fmaf(-0.5f, ex2a(-1.4426950408889634f * __uint_as_float(hw[u] << 16)), 1.0f);
+                        const float s1 = fmaf(-0.5f, ex2a(-1.4426950408889634f * __uint_as_float(hw[u] & 0xffff0000u)), 1.0f);
+                        o[u] = pack_bf16(v[8 * q + 2 * u] * s0, v[8 * q + 2 * u + 1] * s1);
+                    }
+                    *reinterpret_cast<uint4*>(qs + off) = make_uint4(o[0], o[1], o[2], o[3]);
+                }
+            }
+            fence_proxy_async();
+            mbar_arrive(&bars[C_QF + p]);
+        }
+        // ---- this CTA's partial gradients: [dW1 128 x 64 | db1 128 | dW2 128 x 128 | db2 128]
+        float* my = b.parts + (int64_t)blockIdx.x * (128 * 64 + 128 + 128 * 128 + 128);
+        if (ntile > 0) {
+            const uint32_t last = ntile - 1;
+            mbar_wait(&bars[C_DONE + (last & 1u)], (last >> 1) & 1u);   // the last G4; everything earlier completed before it
+            tc_fence_after();
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {  // dW2[f' = e][f]
+                float v[32];
+                tmem_ld32(tmW2 + lane_base + 64 * g + 32 * j, v);
+#pragma unroll
+                for (int q = 0; q < 32; q += 4)
+                    *reinterpret_cast<float4*>(my + 128 * 64 + 128 + e * 128 + 64 * g + 32 * j + q) = make_float4(v[q], v[q + 1], v[q + 2], v[q + 3]);
+            }
+            {   // dW1[f = e][g] (32 columns per group); column 63 = db1
+                float v[32];
+                tmem_ld32(tmW1 + lane_base + 32 * g, v);
+#pragma unroll
+                for (int q = 0; q < 32; q += 4)
+                    *reinterpret_cast<float4*>(my + e * 64 + 32 * g + q) = make_float4(v[q], v[q + 1], v[q + 2], v[q + 3]);
+                if (g == 1) my[128 * 64 + e] = v[31];
+            }
+            if (g == 0) {  // db2[f' = e] = column 0 of the P^T 1 accumulator
+                float v[32];
+                tmem_ld32(tmB2 + lane_base, v);
+                my[128 * 64 + 128 + 128 * 128 + e] = v[0];
+            }
+            tc_fence_before();
+        } else {
+            for (int x = t - 512; x < 128 * 64 + 128 + 128 * 128 + 128; x += 256) my[x] = 0.f;
+        }
+    } else if (warp == 24) {
+        // ===================== G1: D1 = R W1^T =====================
+        const uint32_t id = umma_idesc_bf16(128, 128);
+        const uint32_t w1b = smem_u32(sm + o3W1);
+        for (uint32_t tc = 0; tc < ntile; ++tc) {
+            const uint32_t p = tc & 1u, par = (tc >> 1) & 1u;
+            mbar_wait(&bars[C_RF + p], par);
+            mbar_wait(&bars[C_D1E], (tc & 1u) ^ 1u);
+            tc_fence_after();
+            if (elect_one()) {
+                umma_tile(tmD1, smem_u32(sm + o3R + p * 16384), 16384, w1b, 16384, 64, id);
+                umma_commit(&bars[C_D1F]);
+            }
+            __syncwarp();
+        }
+    } else if (warp == 25) {
+        // ===================== G3: D3 = P W2; dW2 += P^T H; db2 += P^T 1 =====================
+        const uint32_t id_kk = umma_idesc_bf16(128, 128), id_mn = umma_idesc_bf16(128, 128, true, true), id_16 = umma_idesc_bf16(128, 16, true, false);
+        const uint32_t w2t = smem_u32(sm + o3W2T);
+        const uint64_t ones = umma_desc_k128(smem_u32(sm + o3Ones));
+        for (uint32_t tc = 0; tc < ntile; ++tc) {
+            const uint32_t p = tc & 1u, par = (tc >> 1) & 1u;
+            mbar_wait(&bars[C_PF + p], par);
+            mbar_wait(&bars[C_HF + p], par);
+            mbar_wait(&bars[C_D3E], (tc & 1u) ^ 1u);
+            tc_fence_after();
+            if (elect_one()) {
+                const uint32_t pb = smem_u32(sm + o3X + p * 32768), hb = smem_u32(sm + o3H + p * 32768);
+                umma_tile(tmD3, pb, 16384, w2t, 16384, 128, id_kk);
+                umma_tile_mn(tmW2, pb, 16384, hb, 16384, 128, id_mn, tc > 0);
+#pragma unroll
+                for (int k16 = 0; k16 < 8; ++k16)
+                    umma_bf16(tmB2, umma_desc_mn128(pb + k16 * 2048, 16384), ones, id_16, (k16 || tc > 0) ? 1u : 0u);
+                umma_commit(&bars[C_D3F]);
+            }
+            __syncwarp();
+        }
+    } else {
+        // ===================== G4: [dW1 | db1] += Q^T R =====================
+        const uint32_t id_64 = umma_idesc_bf16(128, 64, true, true);
+        for (uint32_t tc = 0; tc < ntile; ++tc) {
+            const uint32_t p = tc & 1u, par = (tc >> 1) & 1u;
+            mbar_wait(&bars[C_QF + p], par);
+            tc_fence_after();
+            if (elect_one()) {
+                umma_tile_mn(tmW1, smem_u32(sm + o3X + p * 32768), 16384, smem_u32(sm + o3R + p * 16384), 16384, 128, id_64, tc > 0);
+                umma_commit(&bars[C_DONE + p]);
+            }
+            __syncwarp();
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 24) tmem_dealloc<512>(tm);
+}
+
 }  // namespace gmp
 
 using namespace gmp;
@@ -480,6 +792,25 @@ int gmp_schnet_cfconv_fwd_tc2(const int32_t* rowptr, const int32_t* col, const i
         rc = check_launch("schnet_tc2_fixup_kernel");
     }
     return rc;
+}
+
+int gmp_schnet_cfconv_bwd_tc2(const int32_t* rowptr, const int32_t* col, const int32_t* perm, const int32_t* rowid, int64_t n,
+                              int64_t num_edges, const float* edge_weight, const void* x1_bf16, const gmp_schnet_filter* f,
+                              const float* g_agg, float* wgrad_parts, int32_t nparts, gmp_stream_t stream) {
+    GMP_REQUIRE(rowptr && f && g_agg && wgrad_parts && col && rowid && edge_weight && x1_bf16, "schnet_cfconv_bwd_tc2: NULL pointer");
+    GMP_REQUIRE(f->num_filters == 128 && f->num_gaussians >= 1 && f->num_gaussians <= 63 && f->gauss_offset,
+                "schnet_cfconv_bwd_tc2: built for 128 filters, <= 63 lazily expanded Gaussians");
+    GMP_REQUIRE(num_edges > 0 && num_edges < (1ll << 31) && n < (1ll << 31), "schnet_cfconv_bwd_tc2: sizes out of range");
+    GMP_REQUIRE(nparts >= 1 && nparts <= 1024, "schnet_cfconv_bwd_tc2: nparts in [1, 1024]");
+    Tc2BwdArgs b;
+    Tc2Args& a = b.f;
+    a.rowptr = rowptr; a.col = col; a.perm = perm; a.rowid = rowid; a.n = n; a.E = num_edges; a.ew = edge_weight;
+    a.x1 = (const __nv_bfloat16*)x1_bf16; a.w1 = f->w1; a.b1 = f->b1; a.w2 = f->w2; a.b2 = f->b2; a.goff = f->gauss_offset;
+    a.G = f->num_gaussians; a.cutoff = f->cutoff; a.gcoeff = f->gauss_coeff; a.agg = nullptr; a.head = nullptr;
+    b.g_agg = g_agg; b.parts = wgrad_parts;
+    GMP_CUDA(cudaFuncSetAttribute(schnet_bwd_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTc2BwdSmem));
+    schnet_bwd_tc2_kernel<<<nparts, kB2Threads, kTc2BwdSmem, stream>>>(b);
+    return check_launch("schnet_bwd_tc2_kernel");
 }
 
 }  // extern "C"

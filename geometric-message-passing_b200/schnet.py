@@ -135,8 +135,12 @@ class _CFConvFn(torch.autograd.Function):
         parts = torch.empty(nparts, plen, dtype=g.dtype, device=g.device)
         d_ew = torch.zeros_like(ew) if need[1] else None
         d_ea = torch.zeros_like(ea) if (need[2] and ea is not None) else None
-        call("gmp_schnet_cfconv_bwd", ptr(csr.rowptr), ptr(csr.col), csr.perm_ptr, graph.n, graph.E, ptr(ew), ptr(ea),
-             ptr(x1), C.byref(filt), ptr(g), ptr(parts), ptr(d_ew), ptr(d_ea), precision)
+        if (precision == _lib.BF16_TC and ea is None and d_ew is None and d_ea is None and F == 128 and G <= 63 and graph.E > 0):
+            call("gmp_schnet_cfconv_bwd_tc2", ptr(csr.rowptr), ptr(csr.col), csr.perm_ptr, ptr(csr.row_ids()), graph.n, graph.E,
+                 ptr(ew), ptr(x1.to(torch.bfloat16)), C.byref(filt), ptr(g), ptr(parts), nparts)
+        else:
+            call("gmp_schnet_cfconv_bwd", ptr(csr.rowptr), ptr(csr.col), csr.perm_ptr, graph.n, graph.E, ptr(ew), ptr(ea),
+                 ptr(x1), C.byref(filt), ptr(g), ptr(parts), ptr(d_ew), ptr(d_ea), precision)
         red = torch.empty(plen, dtype=g.dtype, device=g.device)
         call("gmp_reduce_partials_f32", ptr(parts), nparts, plen, ptr(red))
         o = 0

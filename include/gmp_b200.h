@@ -198,6 +198,14 @@ int gmp_schnet_cfconv_fwd_tc2(const int32_t* rowptr, const int32_t* col, const i
                               int64_t n, int64_t num_edges, const float* edge_weight, const void* x1_bf16,
                               const gmp_schnet_filter* filter /* host */, float* agg, float* head, gmp_stream_t stream);
 
+/* Pipelined GMP_BF16_TC variant of the filter-side backward (weight gradients of the filter MLP only; same partial layout
+ * as gmp_schnet_cfconv_bwd: [dW1 128x64 | db1 | dW2 128x128 | db2] per CTA, `nparts` CTAs, each owning a contiguous range
+ * of the sorted edges).  Restrictions: 128 filters, <= 63 lazily expanded Gaussians, x1 passed as bf16 rows. */
+int gmp_schnet_cfconv_bwd_tc2(const int32_t* rowptr, const int32_t* col, const int32_t* perm, const int32_t* rowid,
+                              int64_t n, int64_t num_edges, const float* edge_weight, const void* x1_bf16,
+                              const gmp_schnet_filter* filter /* host */, const float* g_agg, float* wgrad_parts,
+                              int32_t nparts, gmp_stream_t stream);
+
 /* Parameter gradients of a node-side nn.Linear (PyG CFConv.lin1 / lin2, InteractionBlock.lin; called at
  * models/schnet.py:72) in the GMP_BF16_TC mode: dW [out,in] = g^T x and db [out] = column sums of g, g [n,out], x [n,in],
  * out = 128, in in {64,128}.  Rows are split over the SMs; parts [gmp_linear_wgrad_num_parts(n)][out*in + out] holds

@@ -44,6 +44,9 @@ for it in range(reps + 2):
     if which == "schnet_fwd2":
         call("gmp_schnet_cfconv_fwd_tc2", ptr(csr.rowptr), ptr(csr.col), csr.perm_ptr, ptr(rowid), N, E, ptr(ew), ptr(x1b),
              C.byref(filt), ptr(agg), ptr(head))
+    elif which == "schnet_bwd2":
+        call("gmp_schnet_cfconv_bwd_tc2", ptr(csr.rowptr), ptr(csr.col), csr.perm_ptr, ptr(rowid), N, E, ptr(ew), ptr(x1b),
+             C.byref(filt), ptr(gout), ptr(parts), parts.shape[0])
     elif which == "schnet_fwd":
         call("gmp_schnet_cfconv_fwd", ptr(csr.rowptr), ptr(csr.col), csr.perm_ptr, N, E, ptr(ew), None, ptr(x1), C.byref(filt),
              ptr(agg), prec)
