@@ -421,27 +421,30 @@ __global__ void __launch_bounds__(768, 1) schnet_fwd_tc2_kernel(Tc2Args a) {  //
     if (warp == 20) tmem_dealloc<512>(tm);
 }
 
-// rows that straddle a CTA boundary: add the later CTAs' head partials in CTA order
+// rows that straddle a CTA boundary: add the later CTAs' head partials in CTA order.  One block per chunk; the block of
+// the FIRST chunk whose head belongs to a row adds every consecutive head of that row, so rows are handled in parallel
+// and the order of the additions into one row is fixed.
+__device__ __forceinline__ int tc2_head_row(const int32_t* __restrict__ rowptr, int64_t n, int64_t E, int nchunks, int ch) {
+    if (ch <= 0 || ch >= nchunks) return -1;
+    const int64_t e0 = (E * ch) / nchunks, e1 = (E * (ch + 1)) / nchunks;
+    if (e0 >= e1) return -1;
+    int lo = 0, hi = (int)n;
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if ((int64_t)__ldg(rowptr + mid) <= e0) lo = mid; else hi = mid;
+    }
+    return (int64_t)__ldg(rowptr + lo) < e0 ? lo : -1;
+}
+
 __global__ void __launch_bounds__(128) schnet_tc2_fixup_kernel(const int32_t* __restrict__ rowptr, int64_t n, int64_t E, int nchunks,
                                                                const float* __restrict__ head, float* __restrict__ agg) {
-    __shared__ int hrow[1024];
-    for (int ch = threadIdx.x; ch < nchunks; ch += 128) {
-        const int64_t e0 = (E * ch) / nchunks, e1 = (E * (ch + 1)) / nchunks;
-        int row = -1;
-        if (ch > 0 && e0 < e1) {
-            int lo = 0, hi = (int)n;
-            while (hi - lo > 1) {
-                const int mid = (lo + hi) >> 1;
-                if ((int64_t)__ldg(rowptr + mid) <= e0) lo = mid; else hi = mid;
-            }
-            if ((int64_t)__ldg(rowptr + lo) < e0) row = lo;
-        }
-        hrow[ch] = row;
-    }
-    __syncthreads();
+    const int ch = blockIdx.x + 1;
+    const int row = tc2_head_row(rowptr, n, E, nchunks, ch);
+    if (row < 0 || tc2_head_row(rowptr, n, E, nchunks, ch - 1) == row) return;  // no head, or an earlier block owns this row
     const int c = threadIdx.x;
-    for (int ch = 1; ch < nchunks; ++ch)
-        if (hrow[ch] >= 0) agg[(int64_t)hrow[ch] * 128 + c] += head[(int64_t)ch * 128 + c];
+    float v = agg[(int64_t)row * 128 + c];
+    for (int c2 = ch; c2 < nchunks && (c2 == ch || tc2_head_row(rowptr, n, E, nchunks, c2) == row); ++c2) v += head[(int64_t)c2 * 128 + c];
+    agg[(int64_t)row * 128 + c] = v;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -788,7 +791,7 @@ int gmp_schnet_cfconv_fwd_tc2(const int32_t* rowptr, const int32_t* col, const i
     int rc = check_launch("schnet_fwd_tc2_kernel");
     if (rc != GMP_OK) return rc;
     if (nchunks > 1) {
-        schnet_tc2_fixup_kernel<<<1, 128, 0, stream>>>(rowptr, n, num_edges, nchunks, head, agg);
+        schnet_tc2_fixup_kernel<<<nchunks - 1, 128, 0, stream>>>(rowptr, n, num_edges, nchunks, head, agg);
         rc = check_launch("schnet_tc2_fixup_kernel");
     }
     return rc;
