@@ -66,6 +66,8 @@ _SIGS = {
     "gmp_schnet_cfconv_bwd_tc2": [P, P, P, P, I64, I64, P, P, P, P, P, I32, P],
     "gmp_linear_wgrad_tc": [P, P, I64, I32, I32, P, P],
     "gmp_egnn_tc_edge_fwd": [P, P, P, I64, I64, P, P, P, P, P, P, P],
+    "gmp_egnn_tc_edge_bwd_fused": [P, P, P, P, I64, I64, P, P, P, P, P, P, P, P, P, P, P, P],
+    "gmp_segment_sum_bf16_f32": [P, P, P, P, I64, I32, P],
     "gmp_egnn_tc_edge_bwd": [P, P, P, P, I64, I64, P, P, P, P, P, P, I32, P, P, P, P],
     "gmp_tp_contract": [P, P, P, I64, I64, P, I32, P, I32, P, I32, P, I32, P, P, P, P, I32, P, P, I32, I32, P, I32, P],
     "gmp_symcontract_fwd": [P, P, P, P, I64, I32, I32, I32, I32, P, I32, P],

@@ -26,7 +26,7 @@ constexpr int kGThreads = 512;
 constexpr int kGLd = 272;        // byte stride of a bf16 row in the gather tile (conflict-free 16-byte chunks per row)
 
 struct EgnnTcArgs {
-    const int32_t *rowptr, *col, *rowid, *deg_rowptr;
+    const int32_t *rowptr, *col, *rowid, *deg_rowptr, *perm;   // perm: caller's edge id of sorted edge k (NULL = identity)
     int64_t n, E;
     const float* rowt;              // [n,128] fp32, indexed by the CSR row: P (dst pass) / Q (src pass)
     const __nv_bfloat16* gath;      // [n,128] bf16, indexed by col:       Q (dst pass) / P (src pass)
@@ -34,6 +34,9 @@ struct EgnnTcArgs {
     const float *wd, *g1, *be1, *w1, *b1, *g2, *be2, *w2, *b2, *g3, *be3, *w3, *b3;
     int aggr_mean, nranges;
     float eps;
+    // fused single-pass backward: per-edge d(pre1) (bf16 rows) and d(delta) (float4), indexed by the caller's edge id
+    __nv_bfloat16* dpre_out;
+    float* ddelta_out;
 };
 
 // shared-memory map (bytes from the 1024-aligned base)
@@ -46,8 +49,8 @@ constexpr int oGG = 163840;                    // gathered rows -> xhat1 -> dpre
 constexpr int oGOnes = oGG + kGT * kGLd;       // 4 KB of bf16 ones (column sums through the tensor core)
 constexpr int oGVec = oGOnes + 4096;           // wd g1 be1 b1 g2 be2 b2 g3 be3 w3
 constexpr int oGSc = oGVec + 10 * kGF * 4;     // per-edge scalars [16][128]
-constexpr int oGInt = oGSc + 16 * kGT * 4;     // rrow[128] gcol[128] inode[128]
-constexpr int oGRed = oGInt + 3 * kGT * 4;     // partial-sum exchange: 2 buffers x [4 quarters][128] float2
+constexpr int oGInt = oGSc + 16 * kGT * 4;     // rrow[128] gcol[128] inode[128] eid[128]
+constexpr int oGRed = oGInt + 4 * kGT * 4;     // partial-sum exchange: 2 buffers x [4 quarters][128] float2
 constexpr int oGBar = oGRed + 2 * kGQ * kGT * 8; // mbarrier + tmem pointer
 constexpr int kEgnnTcSmem = oGBar + 64 + 1024;
 
@@ -146,6 +149,7 @@ __device__ __forceinline__ void egnn_tc_tile_forward(GCtx& c, const EgnnTcArgs& 
         c.ints[t] = rr;
         c.ints[kGT + t] = gc;
         c.ints[2 * kGT + t] = i;
+        c.ints[3 * kGT + t] = a.perm ? __ldg(a.perm + k) : (int)k;
         sc[TS_DX * kGT + t] = dx; sc[TS_DY * kGT + t] = dy; sc[TS_DZ * kGT + t] = dz; sc[TS_DIST * kGT + t] = dist;
     }
     __syncthreads();
@@ -389,6 +393,28 @@ __global__ void __launch_bounds__(kGThreads, 1) egnn_fwd_tc_kernel(EgnnTcArgs a,
     if (c.warp == 0) tmem_dealloc<256>(c.tm);
 }
 
+// Column sums over the 32 rows of a warp for 8 columns held per thread: a halving butterfly (lane bits 0-2 select the
+// column, 7 shuffles) plus two more steps across the four lane groups.  Returns, on every lane, the sum of column
+// (lane & 7) of this chunk; `v` is destroyed.
+__device__ __forceinline__ float gx_bfly8(float (&v)[8], int lane) {
+#pragma unroll
+    for (int s = 4; s >= 1; s >>= 1) {
+        const bool up = (lane & s) != 0;
+#pragma unroll
+        for (int i = 0; i < s; ++i) {
+            const float send = up ? v[i] : v[i + s];
+            const float keep = up ? v[i + s] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+        }
+    }
+    float r = v[0];
+    r += __shfl_xor_sync(0xffffffffu, r, 8);
+    r += __shfl_xor_sync(0xffffffffu, r, 16);
+    return r;
+}
+// chunk q (8 columns) of a thread's 32: lane l keeps the sum for column 8 * (l >> 3) + (l & 7) = l of its quarter
+#define GX_VACC(slot, arr, q) { const float r_ = gx_bfly8(arr, lane); if ((lane >> 3) == (q)) vacc[slot] += r_; }
+
 // ------------------------------------------------------------------------------------------------
 // backward: recompute the tile, then LN3 / LN2 / LN1 backward with the data-gradient GEMMs on the tensor cores.
 //   dst pass (SRC = false): d_node = dL/dP, d_pos = the pos_i part, and the weight gradients dW1 / dW2 accumulated in
@@ -429,7 +455,10 @@ __device__ __forceinline__ void gx_colsum(const GCtx& c, int vidx, int a_off, bo
 // slots of the vector gradients (order of the partial buffer, as in egnn.cu)
 enum { VG_DB1 = 0, VG_DB2, VG_DG1, VG_DBE1, VG_DG2, VG_DBE2, VG_DG3, VG_DBE3, VG_DW3, VG_DWD };
 
-template <int ACT, bool SRC>
+// FUSED (dst pass only): the ten vector gradients are taken here as well (warp-shuffle column sums accumulated in
+// registers), and d(pre1) / d(delta) are written per edge so that dL/dQ and the pos_j part follow from two segmented
+// sums over the src-sorted CSR instead of a second recompute pass.
+template <int ACT, bool SRC, bool FUSED>
 __global__ void __launch_bounds__(kGThreads, 1)
 egnn_bwd_tc_kernel(EgnnTcArgs a, const float* __restrict__ g_msg, const float* __restrict__ g_pos, float* __restrict__ dnode,
                    float* __restrict__ dpos, float* __restrict__ parts) {
@@ -442,6 +471,10 @@ egnn_bwd_tc_kernel(EgnnTcArgs a, const float* __restrict__ g_msg, const float* _
     const float* vec = c.vec;
     bool acc_w = false;   // the tensor-memory accumulators hold a previous tile's contribution
     float db3 = 0.f;
+    const int lane = t & 31;
+    float vacc[10];
+#pragma unroll
+    for (int v = 0; v < 10; ++v) vacc[v] = 0.f;
 
     for (int rg = blockIdx.x; rg < a.nranges; rg += gridDim.x) {
         const int r0 = lower_bound_row(a.rowptr, (int)a.n, (int64_t)rg * kGRange);
@@ -478,7 +511,7 @@ egnn_bwd_tc_kernel(EgnnTcArgs a, const float* __restrict__ g_msg, const float* _
             }
             __syncthreads();
             const float ds = sc[TS_GS * kGT + e];
-            if (SRC && hf == 0 && live) db3 += ds;
+            if ((SRC || FUSED) && hf == 0 && live) db3 += ds;
             // ================= stage 3 backward =================
             if (SRC) {  // first the two tiles that do not need the row statistics of dy: ds * a3 (dw3) and dy (dbe3)
                 float x[kGCW];
@@ -516,7 +549,7 @@ egnn_bwd_tc_kernel(EgnnTcArgs a, const float* __restrict__ g_msg, const float* _
                 float s1 = 0.f, s2 = 0.f;
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
-                    float tg[8];
+                    float tg[8], ta[8], tb[8];
 #pragma unroll
                     for (int u = 0; u < 8; ++u) {
                         const int k = 8 * q + u, col = kGCW * hf + k;
@@ -524,12 +557,14 @@ egnn_bwd_tc_kernel(EgnnTcArgs a, const float* __restrict__ g_msg, const float* _
                         const float y = fmaf(xh, vec[TV_G3 * kGF + col], vec[TV_BE3 * kGF + col]);
                         const float dy = ds * vec[TV_W3 * kGF + col] * tdact<ACT>(y);
                         tg[u] = live ? dy * xh : 0.f;
+                        if (FUSED) { ta[u] = live ? ds * tact<ACT>(y) : 0.f; tb[u] = live ? dy : 0.f; }
                         x[k] = xh;
                         d[k] = dy * vec[TV_G3 * kGF + col];
                         s1 += d[k];
                         s2 = fmaf(d[k], xh, s2);
                     }
                     if (SRC) *reinterpret_cast<uint4*>(sm + oGA1 + (hf >> 1) * 16384 + sw128_chunk_off(e, (hf & 1) * 4 + q)) = pack8(tg);
+                    if (FUSED) { GX_VACC(VG_DW3, ta, q) GX_VACC(VG_DBE3, tb, q) GX_VACC(VG_DG3, tg, q) }
                 }
                 const float2 tot = gx_exchange(c, s1, s2);
                 s1 = tot.x * (1.f / kGF);
@@ -540,6 +575,7 @@ egnn_bwd_tc_kernel(EgnnTcArgs a, const float* __restrict__ g_msg, const float* _
 #pragma unroll
                     for (int u = 0; u < 8; ++u) o[u] = live ? rstd * (d[8 * q + u] - s1 - x[8 * q + u] * s2) : 0.f;
                     *reinterpret_cast<uint4*>(sm + oGDT + (hf >> 1) * 16384 + sw128_chunk_off(e, (hf & 1) * 4 + q)) = pack8(o);
+                    if (FUSED) GX_VACC(VG_DB2, o, q)
                 }
             }
             gx_issue_begin(c);
@@ -593,6 +629,7 @@ egnn_bwd_tc_kernel(EgnnTcArgs a, const float* __restrict__ g_msg, const float* _
                         *reinterpret_cast<uint4*>(sm + oGA1 + (hf >> 1) * 16384 + sw128_chunk_off(e, (hf & 1) * 4 + q)) = pack8(tg);
                         *reinterpret_cast<uint4*>(sm + oGM + (hf >> 1) * 16384 + sw128_chunk_off(e, (hf & 1) * 4 + q)) = pack8(tb);
                     }
+                    if (FUSED) { GX_VACC(VG_DG2, tg, q) GX_VACC(VG_DBE2, tb, q) }
                 }
                 const float2 tot = gx_exchange(c, s1, s2);
                 s1 = tot.x * (1.f / kGF);
@@ -603,6 +640,7 @@ egnn_bwd_tc_kernel(EgnnTcArgs a, const float* __restrict__ g_msg, const float* _
 #pragma unroll
                     for (int u = 0; u < 8; ++u) o[u] = live ? rstd * (d[8 * q + u] - s1 - x[8 * q + u] * s2) : 0.f;
                     *reinterpret_cast<uint4*>(sm + oGDT + (hf >> 1) * 16384 + sw128_chunk_off(e, (hf & 1) * 4 + q)) = pack8(o);
+                    if (FUSED) GX_VACC(VG_DB1, o, q)
                 }
             }
             gx_issue_begin(c);
@@ -648,6 +686,7 @@ egnn_bwd_tc_kernel(EgnnTcArgs a, const float* __restrict__ g_msg, const float* _
                         *reinterpret_cast<uint4*>(sm + oGA1 + (hf >> 1) * 16384 + sw128_chunk_off(e, (hf & 1) * 4 + q)) = pack8(tg);
                         *reinterpret_cast<uint4*>(sm + oGM + (hf >> 1) * 16384 + sw128_chunk_off(e, (hf & 1) * 4 + q)) = pack8(tb);
                     }
+                    if (FUSED) { GX_VACC(VG_DG1, tg, q) GX_VACC(VG_DBE1, tb, q) }
                 }
                 const float2 tot = gx_exchange(c, s1, s2);
                 s1 = tot.x * (1.f / kGF);
@@ -662,8 +701,13 @@ egnn_bwd_tc_kernel(EgnnTcArgs a, const float* __restrict__ g_msg, const float* _
                         od[u] = dist * o[u];
                         dd = fmaf(o[u], vec[TV_WD * kGF + kGCW * hf + 8 * q + u], dd);
                     }
-                    *reinterpret_cast<uint4*>(sm + oGG + e * kGLd + (4 * hf + q) * 16) = pack8(o);   // dpre1, for the column walkers
+                    const uint4 po = pack8(o);
+                    *reinterpret_cast<uint4*>(sm + oGG + e * kGLd + (4 * hf + q) * 16) = po;   // dpre1, for the column walkers
                     if (SRC) *reinterpret_cast<uint4*>(sm + oGDT + (hf >> 1) * 16384 + sw128_chunk_off(e, (hf & 1) * 4 + q)) = pack8(od);
+                    if (FUSED) {
+                        if (live) *reinterpret_cast<uint4*>(a.dpre_out + (int64_t)c.ints[3 * kGT + e] * kGF + kGCW * hf + 8 * q) = po;
+                        GX_VACC(VG_DWD, od, q)
+                    }
                 }
                 const float2 dt = gx_exchange(c, dd, 0.f);
                 if (hf == 0) {
@@ -674,6 +718,9 @@ egnn_bwd_tc_kernel(EgnnTcArgs a, const float* __restrict__ g_msg, const float* _
                     sc[TS_GX * kGT + e] = live ? fmaf(k, sc[TS_DX * kGT + e], gx * s) : 0.f;
                     sc[TS_GY * kGT + e] = live ? fmaf(k, sc[TS_DY * kGT + e], gy * s) : 0.f;
                     sc[TS_GZ * kGT + e] = live ? fmaf(k, sc[TS_DZ * kGT + e], gz * s) : 0.f;
+                    if (FUSED && live)
+                        *reinterpret_cast<float4*>(a.ddelta_out + 4 * (int64_t)c.ints[3 * kGT + e]) =
+                            make_float4(sc[TS_GX * kGT + e], sc[TS_GY * kGT + e], sc[TS_GZ * kGT + e], 0.f);
                 }
             }
             gx_issue_begin(c);
@@ -707,6 +754,26 @@ egnn_bwd_tc_kernel(EgnnTcArgs a, const float* __restrict__ g_msg, const float* _
     const int64_t plen = 2 * kGF * kGF + 10 * kGF + 4;
     float* my = parts + (int64_t)blockIdx.x * plen;
     tc_fence_after();
+    if (FUSED) {   // vector gradients: registers -> sum over the four row quarters that share a column quarter
+        float* vout = my + 2 * kGF * kGF;
+        float* red = reinterpret_cast<float*>(sm + oGRed);
+#pragma unroll
+        for (int v = 0; v < 10; ++v) {
+            __syncthreads();
+            red[(c.warp & 3) * kGF + kGCW * hf + lane] = vacc[v];
+            __syncthreads();
+            if (t < kGF) vout[v * kGF + t] = (red[t] + red[kGF + t]) + (red[2 * kGF + t] + red[3 * kGF + t]);
+        }
+        __syncthreads();
+        if (hf == 0) red[e] = db3;
+        __syncthreads();
+        if (t == 0) {
+            float sacc = 0.f;
+            for (int k = 0; k < kGT; ++k) sacc += red[k];
+            vout[10 * kGF] = sacc;
+            vout[10 * kGF + 1] = vout[10 * kGF + 2] = vout[10 * kGF + 3] = 0.f;
+        }
+    }
     if (!SRC) {
         for (int w = 0; w < 2; ++w) {  // lane = output feature (row of W), columns = input features
             float v[kGCW];
@@ -743,7 +810,8 @@ egnn_bwd_tc_kernel(EgnnTcArgs a, const float* __restrict__ g_msg, const float* _
 static EgnnTcArgs egnn_tc_args(const int32_t* rowptr, const int32_t* col, const int32_t* rowid, const int32_t* deg_rowptr, int64_t n,
                                int64_t E, const float* rowt, const void* gath, const float* pos, const gmp_egnn_edge_params* p) {
     EgnnTcArgs a;
-    a.rowptr = rowptr; a.col = col; a.rowid = rowid; a.deg_rowptr = deg_rowptr; a.n = n; a.E = E; a.rowt = rowt;
+    a.rowptr = rowptr; a.col = col; a.rowid = rowid; a.deg_rowptr = deg_rowptr; a.perm = nullptr; a.n = n; a.E = E; a.rowt = rowt;
+    a.dpre_out = nullptr; a.ddelta_out = nullptr;
     a.gath = (const __nv_bfloat16*)gath; a.pos = pos;
     a.wd = p->wd; a.g1 = p->ln1_g; a.be1 = p->ln1_b; a.w1 = p->w1; a.b1 = p->b1; a.g2 = p->ln2_g; a.be2 = p->ln2_b;
     a.w2 = p->w2; a.b2 = p->b2; a.g3 = p->ln3_g; a.be3 = p->ln3_b; a.w3 = p->w3; a.b3 = p->b3;
@@ -803,13 +871,37 @@ int gmp_egnn_tc_edge_bwd(const int32_t* rowptr, const int32_t* col, const int32_
     const int grid = a.nranges < num_sms() ? a.nranges : num_sms();
 #define GMP_EGNN_TC_BWD(A_, S_)                                                                                              \
     {                                                                                                                        \
-        GMP_CUDA(cudaFuncSetAttribute(egnn_bwd_tc_kernel<A_, S_>, cudaFuncAttributeMaxDynamicSharedMemorySize, kEgnnTcSmem)); \
-        egnn_bwd_tc_kernel<A_, S_><<<grid, kGThreads, kEgnnTcSmem, stream>>>(a, g_msg, g_pos, d_node, d_pos, wgrad_parts);         \
+        GMP_CUDA(cudaFuncSetAttribute(egnn_bwd_tc_kernel<A_, S_, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kEgnnTcSmem)); \
+        egnn_bwd_tc_kernel<A_, S_, false><<<grid, kGThreads, kEgnnTcSmem, stream>>>(a, g_msg, g_pos, d_node, d_pos, wgrad_parts);  \
     }
     if (prm->act) { if (src_pass) GMP_EGNN_TC_BWD(1, true) else GMP_EGNN_TC_BWD(1, false) }
     else { if (src_pass) GMP_EGNN_TC_BWD(0, true) else GMP_EGNN_TC_BWD(0, false) }
 #undef GMP_EGNN_TC_BWD
     return check_launch("egnn_bwd_tc_kernel");
+}
+
+// Single-pass backward: the dst pass with everything (dL/dP, pos_i part, weight AND vector gradients) plus per-edge d(pre1)
+// (bf16 [E,128]) and d(delta) (float4 [E]) in the caller's edge order; dL/dQ and the pos_j part are then two segmented sums
+// over the src-sorted CSR (gmp_segment_sum_bf16_f32 / gmp_segment_reduce_f32), no second recompute pass.
+int gmp_egnn_tc_edge_bwd_fused(const int32_t* rowptr, const int32_t* col, const int32_t* perm, const int32_t* rowid, int64_t n,
+                               int64_t num_edges, const float* P, const void* Q_bf16, const float* pos, const gmp_egnn_edge_params* prm,
+                               const float* g_msg, const float* g_pos, float* dP, float* dpos_i, float* wgrad_parts, void* dpre1_bf16,
+                               float* ddelta, gmp_stream_t stream) {
+    if (int rc = egnn_tc_check(prm, n, num_edges)) return rc;
+    GMP_REQUIRE(rowptr && g_msg && g_pos && dP && dpos_i && pos && wgrad_parts &&
+                (num_edges == 0 || (col && rowid && P && Q_bf16 && dpre1_bf16 && ddelta)), "egnn_tc_edge_bwd_fused: NULL pointer");
+    if (n == 0) return GMP_OK;
+    EgnnTcArgs a = egnn_tc_args(rowptr, col, rowid, rowptr, n, num_edges, P, Q_bf16, pos, prm);
+    a.perm = perm; a.dpre_out = (__nv_bfloat16*)dpre1_bf16; a.ddelta_out = ddelta;
+    const int grid = a.nranges < num_sms() ? a.nranges : num_sms();
+    if (prm->act) {
+        GMP_CUDA(cudaFuncSetAttribute(egnn_bwd_tc_kernel<1, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kEgnnTcSmem));
+        egnn_bwd_tc_kernel<1, false, true><<<grid, kGThreads, kEgnnTcSmem, stream>>>(a, g_msg, g_pos, dP, dpos_i, wgrad_parts);
+    } else {
+        GMP_CUDA(cudaFuncSetAttribute(egnn_bwd_tc_kernel<0, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kEgnnTcSmem));
+        egnn_bwd_tc_kernel<0, false, true><<<grid, kGThreads, kEgnnTcSmem, stream>>>(a, g_msg, g_pos, dP, dpos_i, wgrad_parts);
+    }
+    return check_launch("egnn_bwd_tc_kernel<fused>");
 }
 
 }  // extern "C"

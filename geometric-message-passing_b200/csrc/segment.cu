@@ -173,7 +173,47 @@ __global__ void edge_geometry_kernel(const float* __restrict__ pos, const int64_
 
 using namespace gmp;
 
+// out[r, :] = sum_{k in row r} bf16 rows src[perm ? perm[k] : k, :]   (fp32 accumulation, F = 128: warp per row, 4 columns per lane)
+__global__ void __launch_bounds__(256) segsum_bf16_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ perm,
+                                                          const uint2* __restrict__ src, float* __restrict__ out, int64_t n) {
+    const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (row >= n) return;
+    const int64_t b = __ldg(rowptr + row), e = __ldg(rowptr + row + 1);
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    int64_t k = b;
+    for (; k + 4 <= e; k += 4) {  // four rows in flight
+        uint2 v[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int64_t idx = perm ? (int64_t)__ldg(perm + k + j) : k + j;
+            v[j] = __ldg(src + idx * 32 + lane);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            a0 += __uint_as_float(v[j].x << 16); a1 += __uint_as_float(v[j].x & 0xffff0000u);
+            a2 += __uint_as_float(v[j].y << 16); a3 += __uint_as_float(v[j].y & 0xffff0000u);
+        }
+    }
+    for (; k < e; ++k) {
+        const int64_t idx = perm ? (int64_t)__ldg(perm + k) : k;
+        const uint2 v = __ldg(src + idx * 32 + lane);
+        a0 += __uint_as_float(v.x << 16); a1 += __uint_as_float(v.x & 0xffff0000u);
+        a2 += __uint_as_float(v.y << 16); a3 += __uint_as_float(v.y & 0xffff0000u);
+    }
+    *reinterpret_cast<float4*>(out + row * 128 + 4 * lane) = make_float4(a0, a1, a2, a3);
+}
+
 extern "C" {
+
+int gmp_segment_sum_bf16_f32(const int32_t* rowptr, const int32_t* perm, const void* src_bf16, float* out, int64_t n, int32_t F,
+                             gmp_stream_t stream) {
+    GMP_REQUIRE(rowptr && out && n >= 0, "segment_sum_bf16: bad arguments");
+    GMP_REQUIRE(F == 128, "segment_sum_bf16: built for rows of 128 bf16 values (got %d)", F);
+    if (n == 0) return GMP_OK;
+    segsum_bf16_kernel<<<(unsigned)ceil_div(n * 32, 256), 256, 0, stream>>>(rowptr, perm, (const uint2*)src_bf16, out, n);
+    return check_launch("segsum_bf16_kernel");
+}
 
 int gmp_segment_reduce_f32(const int32_t* rowptr, const int32_t* perm, const float* src, float* out, int64_t n,
                            int32_t F, int32_t mean, gmp_stream_t stream) {

@@ -22,6 +22,8 @@ from .scatter import scatter, segment_reduce
 from .schnet import global_add_pool, global_mean_pool
 
 _PREC = {"fp32": _lib.FP32_STRICT, "bf16": _lib.BF16_TC}
+# bf16 mode: the single-pass backward needs 272 B of scratch per edge; above this budget the two-pass (recompute) scheme runs
+_FUSED_BWD_SCRATCH_BYTES = 24 << 30
 
 
 def _params_struct(tensors, d, act, eps, aggr_mean):
@@ -68,7 +70,20 @@ class _EGNNEdgeFn(torch.autograd.Function):
         dP, dQ = torch.empty_like(P), torch.empty_like(Q)
         dpos_i, dpos_j = torch.empty_like(pos), torch.empty_like(pos)
         cd, cs = graph.by_dst, graph.by_src
-        if tc:
+        if tc and graph.E * 272 <= _FUSED_BWD_SCRATCH_BYTES:
+            # single pass: per-edge d(pre1) (bf16) and d(delta) go through 272 B/edge of scratch, dL/dQ and the pos_j part
+            # are segmented sums over the src-sorted CSR
+            E = graph.E
+            dpre1 = torch.empty(max(E, 1), d, dtype=torch.bfloat16, device=P.device)
+            ddelta = torch.empty(max(E, 1), 4, dtype=P.dtype, device=P.device)
+            call("gmp_egnn_tc_edge_bwd_fused", ptr(cd.rowptr), ptr(cd.col), cd.perm_ptr, ptr(cd.row_ids()), graph.n, E, ptr(P),
+                 ptr(Q.to(torch.bfloat16)), ptr(pos), C.byref(prm), ptr(g_msg), ptr(g_pos), ptr(dP), ptr(dpos_i), ptr(parts),
+                 ptr(dpre1), ptr(ddelta))
+            call("gmp_segment_sum_bf16_f32", ptr(cs.rowptr), cs.perm_ptr, ptr(dpre1), ptr(dQ), graph.n, d)
+            dsum = torch.empty(graph.n, 4, dtype=P.dtype, device=P.device)
+            call("gmp_segment_reduce_f32", ptr(cs.rowptr), cs.perm_ptr, ptr(ddelta), ptr(dsum), graph.n, 4, 0)
+            dpos_j = -dsum[:, :3]
+        elif tc:
             call("gmp_egnn_tc_edge_bwd", ptr(cd.rowptr), ptr(cd.col), ptr(cd.row_ids()), ptr(cd.rowptr), graph.n, graph.E, ptr(P),
                  ptr(Q.to(torch.bfloat16)), ptr(pos), C.byref(prm), ptr(g_msg), ptr(g_pos), 0, ptr(dP), ptr(dpos_i), ptr(parts))
             call("gmp_egnn_tc_edge_bwd", ptr(cs.rowptr), ptr(cs.col), ptr(cs.row_ids()), ptr(cd.rowptr), graph.n, graph.E, ptr(Q),

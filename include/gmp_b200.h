@@ -108,6 +108,10 @@ int gmp_index_is_sorted(const int64_t* index, int64_t num_edges, int32_t* flag, 
 int gmp_segment_reduce_f32(const int32_t* rowptr, const int32_t* perm, const float* src, float* out,
                            int64_t n, int32_t F, int32_t mean, gmp_stream_t stream);
 
+/* Same reduction for bf16 rows (fp32 accumulation and output), F = 128: the per-edge d(pre1) rows of the fused EGNN backward. */
+int gmp_segment_sum_bf16_f32(const int32_t* rowptr, const int32_t* perm, const void* src_bf16, float* out, int64_t n,
+                             int32_t F, gmp_stream_t stream);
+
 /* K0: out[r,:] = sum_k x[col[k],:] * (w ? w[perm ? perm[k] : k, :] : 1).  The CFConv message with a
  * materialised filter (PyG CFConv.message, called at models/schnet.py:72).  F % 4 == 0. */
 int gmp_gather_mul_segsum_f32(const int32_t* rowptr, const int32_t* col, const int32_t* perm, const float* x,
@@ -273,6 +277,15 @@ int gmp_egnn_tc_edge_fwd(const int32_t* rowptr, const int32_t* col, const int32_
  * (dpre^T a1, dpre^T m accumulated in tensor memory), the src pass the ten vectors (column sums through the tensor
  * core) and db3; sum them with gmp_reduce_partials_f32. */
 int32_t gmp_egnn_tc_bwd_num_parts(int64_t num_edges);
+/* Single-pass variant: the dst pass computes every parameter gradient (full partial rows) and writes, per edge and in
+ * the caller's edge order (perm = that of the dst-sorted CSR), d(pre1) as bf16 rows [E,128] and d(delta) as float4 [E];
+ * dL/dQ = gmp_segment_sum_bf16_f32 over the src-sorted CSR, the pos_j part = -gmp_segment_reduce_f32(ddelta) likewise.
+ * Costs 272 B of scratch per edge; the two-pass entry point below needs none. */
+int gmp_egnn_tc_edge_bwd_fused(const int32_t* rowptr, const int32_t* col, const int32_t* perm, const int32_t* rowid,
+                               int64_t n, int64_t num_edges, const float* P, const void* Q_bf16, const float* pos,
+                               const gmp_egnn_edge_params* prm /* host */, const float* g_msg, const float* g_pos,
+                               float* dP, float* dpos_i, float* wgrad_parts, void* dpre1_bf16, float* ddelta,
+                               gmp_stream_t stream);
 int gmp_egnn_tc_edge_bwd(const int32_t* rowptr, const int32_t* col, const int32_t* rowid, const int32_t* dst_rowptr,
                          int64_t n, int64_t num_edges, const float* row_operand, const void* col_operand_bf16,
                          const float* pos, const gmp_egnn_edge_params* prm /* host */, const float* g_msg,

@@ -103,14 +103,18 @@ def _l2_rel(a, b):
     return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
 
 
-@pytest.mark.parametrize("act,aggr,n,side", [("swish", "mean", 1000, 5.0), ("swish", "add", 3000, 7.0), ("relu", "add", 3000, 7.0)])
-def test_egnn_bf16_tc_vs_fp32(act, aggr, n, side):
-    """EGNN layer, tcgen05 edge kernels (forward + both backward passes) against the fp32-strict kernels.
+@pytest.mark.parametrize("act,aggr,n,side,fused", [("swish", "mean", 1000, 5.0, True), ("swish", "add", 3000, 7.0, True),
+                                                   ("swish", "add", 3000, 7.0, False), ("relu", "add", 3000, 7.0, True)])
+def test_egnn_bf16_tc_vs_fp32(act, aggr, n, side, fused, monkeypatch):
+    """EGNN layer, tcgen05 edge kernels (forward; single-pass backward with per-edge scratch, or the two recompute
+    passes) against the fp32-strict kernels.
     Smooth activation: every output and gradient within 1e-2 (normwise, max).  ReLU: the forward holds 1e-2; its
     gradients are compared in the L2 norm with a 0.1 bound, because a bf16-level perturbation of a pre-activation that
     sits at the kink flips that unit's derivative -- the fp32 reference shows the same sensitivity (mlp_upd, a pure
     fp32 torch path, moves by 2-3e-2 when its input moves by 2e-3)."""
     import gmp_b200
+    if not fused:   # force the two-pass (recompute) backward that runs when the per-edge scratch would not fit
+        monkeypatch.setattr(gmp_b200.egnn, "_FUSED_BWD_SCRATCH_BYTES", 0)
     g = torch.Generator().manual_seed(n)
     pos = (torch.rand(n, 3, generator=g) * side).cuda()
     ei = gmp_b200.radius_graph(pos, 1.0, None, max_num_neighbors=128)
