@@ -33,6 +33,7 @@ pos = pos_all[rank * mine * 64:(rank + 1) * mine * 64].contiguous().to(dev)
 batch = torch.arange(mine).repeat_interleave(64).to(dev)
 ei = gmp_b200.radius_graph(pos, 2.0, batch, max_num_neighbors=64)
 atoms = torch.zeros(pos.shape[0], dtype=torch.long, device=dev)
+gmp_b200.set_fast_matmul(precision == "bf16")   # bf16 mode: node-side library GEMMs on TF32 tensor cores
 torch.manual_seed(0)
 if which == "tfn":
     model = gmp_b200.TFNModel(r_max=2.0, max_ell=2, emb_dim=64, num_layers=4, precision=precision).to(dev)

@@ -29,6 +29,7 @@ pos = pos[torch.argsort(pos[:, 0])].contiguous().to(dev)   # spatial sort: slabs
 part = gmp_b200.slab_partition(pos[:, 0], 1.0, rank, world)
 ei = gmp_b200.distributed.local_radius_graph(pos[part.local_global].contiguous(), 1.0, part)
 E_loc = torch.tensor([float(ei.shape[1])], device=dev, dtype=torch.float64)
+gmp_b200.set_fast_matmul(precision == "bf16")   # bf16 mode: node-side library GEMMs on TF32 tensor cores
 torch.manual_seed(0)
 model = gmp_b200.PartitionedEGNN(num_layers=layers, emb_dim=128, precision=precision).to(dev)
 params = list(model.parameters())

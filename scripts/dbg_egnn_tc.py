@@ -41,6 +41,7 @@ def check(act="relu", aggr="add", n=3000, side=7.0, bwd=True):
 
 
 def timing(n=2 ** 18, side=32.0, bwd=True):
+    gmp_b200.set_fast_matmul(True)
     pos, ei = make(side, n)
     E = ei.shape[1]
     for prec in ("bf16",):
