@@ -245,6 +245,24 @@ constexpr int kTcTpSmem = oBar2 + 16 * 8 + 16 + 1024;
 __device__ __forceinline__ float bf_lo(uint32_t w) { return __uint_as_float(w << 16); }
 __device__ __forceinline__ float bf_hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
 
+// ---- thread-block-cluster helpers (CTA pairs sharing the W2 stream: each CTA fetches half of every stage and multicasts it)
+__device__ __forceinline__ uint32_t cluster_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// bulk copy global -> the same shared offset in every CTA of `mask`; each destination's mbarrier receives the byte count
+__device__ __forceinline__ void bulk_g2s_mc(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar, uint16_t mask) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(
+                     smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)), "h"(mask)
+                 : "memory");
+}
+// all MMAs issued so far by this thread arrive on the barrier at this shared offset in every CTA of `mask`
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+                 "h"(mask)
+                 : "memory");
+}
+
 struct EpiCtx {
     const TcTpArgs* a;
     uint8_t* sm;
@@ -423,6 +441,10 @@ __device__ __forceinline__ void tc_ygroup(EpiCtx& c, const TcYGroup& G) {
     }
 }
 
+// CL2: launched as clusters of two CTAs that walk the N-tiles in lockstep (same rotation, same number of tiles); every W2
+// stage is fetched once per pair -- each CTA requests its half and multicasts it into both rings -- which halves the
+// L2 -> SM stream, the largest one of this kernel (128 KB per N-tile per CTA otherwise).
+template <bool CL2>
 __global__ void __launch_bounds__(kTcThreads, 1) tp_contract_tc_kernel(TcTpArgs a) {
     extern __shared__ __align__(16) uint8_t smraw[];
     uint8_t* sm = smraw + ((1024u - (smem_u32(smraw) & 1023u)) & 1023u);
@@ -434,7 +456,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tp_contract_tc_kernel(TcTpArgs 
     if (t == 0) {
         mbar_init(&bars[0], 1);
         mbar_init(&bars[1], 1);
-        for (int s = 0; s < kNB; ++s) { mbar_init(&bars[2 + s], 1); mbar_init(&bars[6 + s], 1); }
+        for (int s = 0; s < kNB; ++s) { mbar_init(&bars[2 + s], 1); mbar_init(&bars[6 + s], CL2 ? 2 : 1); }  // a slot is free when both CTAs' MMAs read it
         for (int s = 0; s < 4; ++s) mbar_init(&bars[10 + s], 1);
         mbar_init(&bars[14], kEpiThreads);
         mbar_init(&bars[15], kEpiThreads);
@@ -443,13 +465,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) tp_contract_tc_kernel(TcTpArgs 
     if (warp == 11) tmem_alloc<512>(tmem_ptr);
     tc_fence_before();
     __syncthreads();
+    if (CL2) cluster_sync_all();   // the peer's barriers are initialised before anything can arrive on them
     tc_fence_after();
     const uint32_t tm = *tmem_ptr;
 
-    const int64_t t0 = (a.ntiles * blockIdx.x) / gridDim.x, t1 = (a.ntiles * (blockIdx.x + 1)) / gridDim.x;
-    // every CTA walks the y-groups cyclically from its own starting point, so that at any moment the CTAs stream
+    // every CTA processes the same number of tile slots (slots beyond the last tile are empty: all edges invalid)
+    const int64_t tpc = (a.ntiles + gridDim.x - 1) / gridDim.x;
+    const int64_t t0 = tpc * blockIdx.x, t1 = t0 + tpc;
+    // every CTA (pair) walks the y-groups cyclically from its own starting point, so that at any moment the CTAs stream
     // different parts of the (L2-resident) w2 image instead of all hammering the same lines
-    const int y_start = (int)(((int64_t)a.nyg * blockIdx.x) / gridDim.x);
+    const int y_start = CL2 ? (int)(((int64_t)a.nyg * (blockIdx.x >> 1)) / (gridDim.x >> 1)) : (int)(((int64_t)a.nyg * blockIdx.x) / gridDim.x);
 
     if (warp < 8) {
         // ================= epilogue: thread = edge of the tile = TMEM lane =================
@@ -539,7 +564,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tp_contract_tc_kernel(TcTpArgs 
                 if (wt == 0) { seg_start[total] = kET; seg_start[131] = total; }
                 bar_sync_named(3, kWalkThreads);
             }
-            const int nseg = seg_start[131];
+            const int nseg = tile < a.ntiles ? seg_start[131] : 0;   // empty slot: nothing to store
             const bool head0 = (int64_t)__ldg(a.rowptr + seg_row[0]) < chunk_e0;
             for (int yy = 0; yy < a.nyg; ++yy) {
                 const TcYGroup G = a.yg[(y_start + yy) % a.nyg];
@@ -592,11 +617,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) tp_contract_tc_kernel(TcTpArgs 
         // ================= producer: bulk copies of the hidden tile and the W2 stages =================
         if (lane == 0) {
             uint32_t si = 0, ti = 0;
+            const uint32_t rank = CL2 ? cluster_rank() : 0u;
             for (int64_t tile = t0; tile < t1; ++tile, ++ti) {
+                const int64_t tsrc = tile < a.ntiles ? tile : a.ntiles - 1;   // empty slots reread the last tile (their edges are invalid)
                 mbar_wait(&bars[1], (ti & 1u) ^ 1u);
                 mbar_expect_tx(&bars[0], (uint32_t)(KS * kStage));
                 for (int ks = 0; ks < KS; ++ks)
-                    bulk_g2s(sm + oA + ks * kStage, a.hid_img + (tile * KS + ks) * (int64_t)kStage, kStage, &bars[0]);
+                    bulk_g2s(sm + oA + ks * kStage, a.hid_img + (tsrc * KS + ks) * (int64_t)kStage, kStage, &bars[0]);
                 for (int yy = 0; yy < a.nyg; ++yy) {
                     const TcYGroup G = a.yg[(y_start + yy) % a.nyg];
                     const uint8_t* src = a.w2_img + (int64_t)G.nt_begin * NST * kStage;
@@ -605,7 +632,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) tp_contract_tc_kernel(TcTpArgs 
                         const uint32_t slot = si % kNB, ph = (si / kNB) & 1u;
                         mbar_wait(&bars[6 + slot], ph ^ 1u);
                         mbar_expect_tx(&bars[2 + slot], kStage);
-                        bulk_g2s(sm + oB + slot * kStage, src + (int64_t)s * kStage, kStage, &bars[2 + slot]);
+                        if (CL2)   // my half of the stage, into both CTAs' rings
+                            bulk_g2s_mc(sm + oB + slot * kStage + rank * (kStage / 2), src + (int64_t)s * kStage + rank * (kStage / 2), kStage / 2,
+                                        &bars[2 + slot], (uint16_t)3);
+                        else
+                            bulk_g2s(sm + oB + slot * kStage, src + (int64_t)s * kStage, kStage, &bars[2 + slot]);
                     }
                 }
             }
@@ -634,7 +665,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tp_contract_tc_kernel(TcTpArgs 
                             umma_bf16(d, ad + 2, bd + 2, idesc, 1u);
                             umma_bf16(d, ad + 4, bd + 4, idesc, 1u);
                             umma_bf16(d, ad + 6, bd + 6, idesc, 1u);
-                            umma_commit(&bars[6 + ks]);
+                            if (CL2) umma_commit_mc(&bars[6 + ks], (uint16_t)3); else umma_commit(&bars[6 + ks]);
                             if (ks == 3) umma_commit(&bars[10 + buf * 2 + half]);
                         }
                         __syncwarp();
@@ -654,7 +685,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tp_contract_tc_kernel(TcTpArgs 
                             umma_bf16(d, ad + 2, bd + 2, idesc, 1u);
                             umma_bf16(d, ad + 4, bd + 4, idesc, 1u);
                             umma_bf16(d, ad + 6, bd + 6, idesc, 1u);
-                            umma_commit(&bars[6 + slot]);
+                            if (CL2) umma_commit_mc(&bars[6 + slot], (uint16_t)3); else umma_commit(&bars[6 + slot]);
                             if (ks == KS - 1) umma_commit(&bars[10 + buf * 2 + half]);
                         }
                         __syncwarp();
@@ -667,6 +698,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tp_contract_tc_kernel(TcTpArgs 
     }
     tc_fence_before();
     __syncthreads();
+    if (CL2) cluster_sync_all();   // no CTA leaves while its peer may still multicast into it or arrive on its barriers
     if (warp == 11) tmem_dealloc<512>(tm);
 }
 
@@ -1167,7 +1199,7 @@ __global__ void __launch_bounds__(128) tp_tc_fixup_kernel(const int32_t* __restr
                                                           const float* __restrict__ head, float* __restrict__ res, int r_len) {
     __shared__ int hrow[1024];  // row that chunk ch's head belongs to, or -1
     for (int ch = threadIdx.x; ch < nchunks; ch += 128) {
-        const int64_t e0 = ((ntiles * ch) / nchunks) * kET;
+        const int64_t e0 = ((ntiles + nchunks - 1) / nchunks) * ch * kET;
         int row = -1;
         if (ch > 0 && e0 < E) {
             const int lo = row_of_edge(rowptr, (int)n, e0);
@@ -1243,17 +1275,37 @@ int gmp_tp_tc_contract(const int32_t* rowptr, const int32_t* col, const int32_t*
     GMP_CUDA(cudaMemsetAsync(res, 0, (size_t)n * r_len * sizeof(float), stream));
     if (n == 0 || num_edges == 0 || nyg == 0) return GMP_OK;
     const int nchunks = gmp_tp_tc_num_chunks(num_edges);
+    int nchunks_launched = nchunks;
     GMP_CUDA(cudaMemsetAsync(head, 0, (size_t)nchunks * r_len * sizeof(float), stream));
     TcTpArgs a;
     a.rowptr = rowptr; a.col = col; a.perm = perm; a.n = n; a.E = num_edges; a.V = V; a.v_len = v_len; a.res = res; a.r_len = r_len;
     a.head = head; a.sh = edge_sh; a.S = S; a.hid_img = (const uint8_t*)hid_img; a.w2_img = (const uint8_t*)w2_img;
     a.yg = (const TcYGroup*)ygroups; a.nyg = nyg; a.NT = ntiles_n; a.KS = H / 64; a.cg = cg; a.ntiles = ceil_div(num_edges, kET);
-    GMP_CUDA(cudaFuncSetAttribute(tp_contract_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcTpSmem));
-    tp_contract_tc_kernel<<<nchunks, kTcThreads, kTcTpSmem, stream>>>(a);
+    if (nchunks >= 2) {
+        // CTA pairs (thread-block clusters of 2) share the W2 stream through multicast
+        const int grid = nchunks & ~1;
+        GMP_CUDA(cudaFuncSetAttribute(tp_contract_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcTpSmem));
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(grid);
+        cfg.blockDim = dim3(kTcThreads);
+        cfg.dynamicSmemBytes = kTcTpSmem;
+        cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        GMP_CUDA(cudaLaunchKernelEx(&cfg, tp_contract_tc_kernel<true>, a));
+        nchunks_launched = grid;
+    } else {
+        GMP_CUDA(cudaFuncSetAttribute(tp_contract_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcTpSmem));
+        tp_contract_tc_kernel<false><<<nchunks, kTcThreads, kTcTpSmem, stream>>>(a);
+        nchunks_launched = nchunks;
+    }
     int rc = check_launch("tp_contract_tc_kernel");
     if (rc != GMP_OK) return rc;
-    if (nchunks > 1) {
-        tp_tc_fixup_kernel<<<(unsigned)ceil_div(r_len, 128), 128, 0, stream>>>(rowptr, n, num_edges, a.ntiles, nchunks, head, res, r_len);
+    if (nchunks_launched > 1) {
+        tp_tc_fixup_kernel<<<(unsigned)ceil_div(r_len, 128), 128, 0, stream>>>(rowptr, n, num_edges, a.ntiles, nchunks_launched, head, res, r_len);
         rc = check_launch("tp_tc_fixup_kernel");
     }
     return rc;
