@@ -23,7 +23,7 @@ from .schnet import global_add_pool, global_mean_pool
 
 _PREC = {"fp32": _lib.FP32_STRICT, "bf16": _lib.BF16_TC}
 # bf16 mode: the single-pass backward needs 272 B of scratch per edge; above this budget the two-pass (recompute) scheme runs
-_FUSED_BWD_SCRATCH_BYTES = 24 << 30
+_FUSED_BWD_SCRATCH_BYTES = 64 << 30
 
 
 def _params_struct(tensors, d, act, eps, aggr_mean):
