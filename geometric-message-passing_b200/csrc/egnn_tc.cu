@@ -98,6 +98,12 @@ __device__ __forceinline__ void unpack8(const uint4 u, float (&f)[8]) {
     f[4] = __uint_as_float(u.z << 16); f[5] = __uint_as_float(u.z & 0xffff0000u);
     f[6] = __uint_as_float(u.w << 16); f[7] = __uint_as_float(u.w & 0xffff0000u);
 }
+// eight consecutive parameter values (32-byte aligned) with two 16-byte shared-memory loads
+struct V8 { float v[8]; };
+__device__ __forceinline__ V8 ldv8(const float* p) {
+    const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+    return V8{{a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w}};
+}
 __device__ __forceinline__ uint4 pack8(const float* f) {
     return make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
 }
@@ -184,12 +190,14 @@ __device__ __forceinline__ void egnn_tc_tile_forward(GCtx& c, const EgnnTcArgs& 
         if (hf == 0) sc[TS_R1 * kGT + e] = rstd;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
+            const V8 pG1 = ldv8(vec + TV_G1 * kGF + kGCW * hf + 8 * q);
+            const V8 pE1 = ldv8(vec + TV_BE1 * kGF + kGCW * hf + 8 * q);
             float xh[8], a1[8];
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
                 const int col = kGCW * hf + 8 * q + u;
                 xh[u] = (x[8 * q + u] - mean) * rstd;
-                a1[u] = tact<ACT>(fmaf(xh[u], vec[TV_G1 * kGF + col], vec[TV_BE1 * kGF + col]));
+                a1[u] = tact<ACT>(fmaf(xh[u], pG1.v[u], pE1.v[u]));
             }
             *reinterpret_cast<uint4*>(sm + oGG + e * kGLd + (4 * hf + q) * 16) = pack8(xh);
             *reinterpret_cast<uint4*>(sm + oGA1 + (hf >> 1) * 16384 + sw128_chunk_off(e, (hf & 1) * 4 + q)) = pack8(a1);
@@ -213,17 +221,23 @@ __device__ __forceinline__ void egnn_tc_tile_forward(GCtx& c, const EgnnTcArgs& 
         float x[kGCW];
         gx_ld64(c, 0, x);
 #pragma unroll
-        for (int k = 0; k < kGCW; ++k) x[k] += vec[TV_B1 * kGF + kGCW * hf + k];
+        for (int q = 0; q < 4; ++q) {
+            const V8 pb = ldv8(vec + TV_B1 * kGF + kGCW * hf + 8 * q);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) x[8 * q + u] += pb.v[u];
+        }
         float mean, rstd;
         gx_stats(c, x, a.eps, mean, rstd);
         if (hf == 0) { sc[TS_M2 * kGT + e] = mean; sc[TS_R2 * kGT + e] = rstd; }
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
+            const V8 pG2 = ldv8(vec + TV_G2 * kGF + kGCW * hf + 8 * q);
+            const V8 pE2 = ldv8(vec + TV_BE2 * kGF + kGCW * hf + 8 * q);
             float m[8];
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
                 const int col = kGCW * hf + 8 * q + u;
-                m[u] = tact<ACT>(fmaf((x[8 * q + u] - mean) * rstd, vec[TV_G2 * kGF + col], vec[TV_BE2 * kGF + col]));
+                m[u] = tact<ACT>(fmaf((x[8 * q + u] - mean) * rstd, pG2.v[u], pE2.v[u]));
             }
             *reinterpret_cast<uint4*>(sm + oGM + (hf >> 1) * 16384 + sw128_chunk_off(e, (hf & 1) * 4 + q)) = pack8(m);
         }
@@ -245,14 +259,20 @@ __device__ __forceinline__ void egnn_tc_tile_forward(GCtx& c, const EgnnTcArgs& 
         float x[kGCW];
         gx_ld64(c, 128, x);
 #pragma unroll
-        for (int k = 0; k < kGCW; ++k) x[k] += vec[TV_B2 * kGF + kGCW * hf + k];
+        for (int q = 0; q < 4; ++q) {
+            const V8 pb = ldv8(vec + TV_B2 * kGF + kGCW * hf + 8 * q);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) x[8 * q + u] += pb.v[u];
+        }
         float mean, rstd;
         gx_stats(c, x, a.eps, mean, rstd);
         float dot = 0.f;
 #pragma unroll
-        for (int k = 0; k < kGCW; ++k) {
-            const int col = kGCW * hf + k;
-            dot = fmaf(tact<ACT>(fmaf((x[k] - mean) * rstd, vec[TV_G3 * kGF + col], vec[TV_BE3 * kGF + col])), vec[TV_W3 * kGF + col], dot);
+        for (int q = 0; q < 4; ++q) {
+            const V8 pg = ldv8(vec + TV_G3 * kGF + kGCW * hf + 8 * q), pe = ldv8(vec + TV_BE3 * kGF + kGCW * hf + 8 * q),
+                     pw = ldv8(vec + TV_W3 * kGF + kGCW * hf + 8 * q);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) dot = fmaf(tact<ACT>(fmaf((x[8 * q + u] - mean) * rstd, pg.v[u], pe.v[u])), pw.v[u], dot);
         }
         const float2 tot = gx_exchange(c, dot, 0.f);
         if (hf == 0) {
@@ -519,13 +539,17 @@ egnn_bwd_tc_kernel(EgnnTcArgs a, const float* __restrict__ g_msg, const float* _
                 const float mean = sc[TS_M3 * kGT + e], rstd = sc[TS_R3 * kGT + e];
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
+                    const V8 pB2 = ldv8(vec + TV_B2 * kGF + kGCW * hf + 8 * q);
+                    const V8 pG3 = ldv8(vec + TV_G3 * kGF + kGCW * hf + 8 * q);
+                    const V8 pE3 = ldv8(vec + TV_BE3 * kGF + kGCW * hf + 8 * q);
+                    const V8 pW3 = ldv8(vec + TV_W3 * kGF + kGCW * hf + 8 * q);
                     float ta[8], tb[8];
 #pragma unroll
                     for (int u = 0; u < 8; ++u) {
                         const int col = kGCW * hf + 8 * q + u;
-                        const float y = fmaf((x[8 * q + u] + vec[TV_B2 * kGF + col] - mean) * rstd, vec[TV_G3 * kGF + col], vec[TV_BE3 * kGF + col]);
+                        const float y = fmaf((x[8 * q + u] + pB2.v[u] - mean) * rstd, pG3.v[u], pE3.v[u]);
                         ta[u] = live ? ds * tact<ACT>(y) : 0.f;
-                        tb[u] = live ? ds * vec[TV_W3 * kGF + col] * tdact<ACT>(y) : 0.f;
+                        tb[u] = live ? ds * pW3.v[u] * tdact<ACT>(y) : 0.f;
                     }
                     *reinterpret_cast<uint4*>(sm + oGA1 + (hf >> 1) * 16384 + sw128_chunk_off(e, (hf & 1) * 4 + q)) = pack8(ta);
                     *reinterpret_cast<uint4*>(sm + oGM + (hf >> 1) * 16384 + sw128_chunk_off(e, (hf & 1) * 4 + q)) = pack8(tb);
@@ -549,17 +573,21 @@ egnn_bwd_tc_kernel(EgnnTcArgs a, const float* __restrict__ g_msg, const float* _
                 float s1 = 0.f, s2 = 0.f;
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
+                    const V8 pB2 = ldv8(vec + TV_B2 * kGF + kGCW * hf + 8 * q);
+                    const V8 pG3 = ldv8(vec + TV_G3 * kGF + kGCW * hf + 8 * q);
+                    const V8 pE3 = ldv8(vec + TV_BE3 * kGF + kGCW * hf + 8 * q);
+                    const V8 pW3 = ldv8(vec + TV_W3 * kGF + kGCW * hf + 8 * q);
                     float tg[8], ta[8], tb[8];
 #pragma unroll
                     for (int u = 0; u < 8; ++u) {
                         const int k = 8 * q + u, col = kGCW * hf + k;
-                        const float xh = (x[k] + vec[TV_B2 * kGF + col] - mean) * rstd;
-                        const float y = fmaf(xh, vec[TV_G3 * kGF + col], vec[TV_BE3 * kGF + col]);
-                        const float dy = ds * vec[TV_W3 * kGF + col] * tdact<ACT>(y);
+                        const float xh = (x[k] + pB2.v[u] - mean) * rstd;
+                        const float y = fmaf(xh, pG3.v[u], pE3.v[u]);
+                        const float dy = ds * pW3.v[u] * tdact<ACT>(y);
                         tg[u] = live ? dy * xh : 0.f;
                         if (FUSED) { ta[u] = live ? ds * tact<ACT>(y) : 0.f; tb[u] = live ? dy : 0.f; }
                         x[k] = xh;
-                        d[k] = dy * vec[TV_G3 * kGF + col];
+                        d[k] = dy * pG3.v[u];
                         s1 += d[k];
                         s2 = fmaf(d[k], xh, s2);
                     }
@@ -604,6 +632,9 @@ egnn_bwd_tc_kernel(EgnnTcArgs a, const float* __restrict__ g_msg, const float* _
                 float s1 = 0.f, s2 = 0.f;
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
+                    const V8 pB1 = ldv8(vec + TV_B1 * kGF + kGCW * hf + 8 * q);
+                    const V8 pG2 = ldv8(vec + TV_G2 * kGF + kGCW * hf + 8 * q);
+                    const V8 pE2 = ldv8(vec + TV_BE2 * kGF + kGCW * hf + 8 * q);
                     float tg[8], tb[8], up[8];
                     if (live) {
                         const float4 u0 = __ldg(gm + 2 * q), u1 = __ldg(gm + 2 * q + 1);
@@ -615,13 +646,13 @@ egnn_bwd_tc_kernel(EgnnTcArgs a, const float* __restrict__ g_msg, const float* _
 #pragma unroll
                     for (int u = 0; u < 8; ++u) {
                         const int k = 8 * q + u, col = kGCW * hf + k;
-                        const float xh = (x[k] + vec[TV_B1 * kGF + col] - mean) * rstd;
-                        const float y = fmaf(xh, vec[TV_G2 * kGF + col], vec[TV_BE2 * kGF + col]);
+                        const float xh = (x[k] + pB1.v[u] - mean) * rstd;
+                        const float y = fmaf(xh, pG2.v[u], pE2.v[u]);
                         const float dy = live ? (d[k] + up[u] * scale) * tdact<ACT>(y) : 0.f;
                         tg[u] = dy * xh;
                         tb[u] = dy;
                         x[k] = xh;
-                        d[k] = dy * vec[TV_G2 * kGF + col];
+                        d[k] = dy * pG2.v[u];
                         s1 += d[k];
                         s2 = fmaf(d[k], xh, s2);
                     }
@@ -668,17 +699,19 @@ egnn_bwd_tc_kernel(EgnnTcArgs a, const float* __restrict__ g_msg, const float* _
                 float s1 = 0.f, s2 = 0.f;
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
+                    const V8 pG1 = ldv8(vec + TV_G1 * kGF + kGCW * hf + 8 * q);
+                    const V8 pE1 = ldv8(vec + TV_BE1 * kGF + kGCW * hf + 8 * q);
                     float xh[8], tg[8], tb[8];
                     unpack8(*reinterpret_cast<const uint4*>(sm + oGG + e * kGLd + (4 * hf + q) * 16), xh);
 #pragma unroll
                     for (int u = 0; u < 8; ++u) {
                         const int k = 8 * q + u, col = kGCW * hf + k;
-                        const float y = fmaf(xh[u], vec[TV_G1 * kGF + col], vec[TV_BE1 * kGF + col]);
+                        const float y = fmaf(xh[u], pG1.v[u], pE1.v[u]);
                         const float dy = live ? d[k] * tdact<ACT>(y) : 0.f;
                         tg[u] = dy * xh[u];
                         tb[u] = dy;
                         x[k] = xh[u];
-                        d[k] = dy * vec[TV_G1 * kGF + col];
+                        d[k] = dy * pG1.v[u];
                         s1 += d[k];
                         s2 = fmaf(d[k], xh[u], s2);
                     }
@@ -694,12 +727,13 @@ egnn_bwd_tc_kernel(EgnnTcArgs a, const float* __restrict__ g_msg, const float* _
                 float dd = 0.f;
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
+                    const V8 pWD = ldv8(vec + TV_WD * kGF + kGCW * hf + 8 * q);
                     float o[8], od[8];
 #pragma unroll
                     for (int u = 0; u < 8; ++u) {
                         o[u] = live ? rstd * (d[8 * q + u] - s1 - x[8 * q + u] * s2) : 0.f;
                         od[u] = dist * o[u];
-                        dd = fmaf(o[u], vec[TV_WD * kGF + kGCW * hf + 8 * q + u], dd);
+                        dd = fmaf(o[u], pWD.v[u], dd);
                     }
                     const uint4 po = pack8(o);
                     *reinterpret_cast<uint4*>(sm + oGG + e * kGLd + (4 * hf + q) * 16) = po;   // dpre1, for the column walkers
