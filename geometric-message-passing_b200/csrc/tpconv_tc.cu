@@ -1230,6 +1230,7 @@ int64_t gmp_tp_tc_w2_bytes(int32_t ntiles, int32_t H) { return (int64_t)ntiles *
 
 int gmp_tp_tc_pack_hid(const int32_t* perm, int64_t num_edges, const float* edge_feat, int32_t R, const float* w1, const float* b1,
                        int32_t H, void* hid_img, gmp_stream_t stream) {
+    if (num_edges == 0) return GMP_OK;
     GMP_REQUIRE(edge_feat && w1 && b1 && hid_img, "tp_tc_pack_hid: NULL pointer");
     GMP_REQUIRE(H >= 64 && H <= 256 && H % 64 == 0, "tp_tc_pack_hid: mlp_dim must be 64, 128, 192 or 256 (got %d)", H);
     GMP_REQUIRE(R >= 1 && R <= 16, "tp_tc_pack_hid: edge_feats_dim in [1, 16] (got %d)", R);
@@ -1315,6 +1316,7 @@ int gmp_tp_tc_dhid(const int32_t* rowptr, const int32_t* col, const int32_t* per
                    int32_t x_len, const float* g, int32_t g_len, const float* edge_sh, int32_t S, const float* edge_feat, int32_t R,
                    const float* w1, const float* b1, const void* w2_img, const void* ygroups, int32_t nyg, int32_t ntiles_n, int32_t H,
                    const float* cg, float* dpre, gmp_stream_t stream) {
+    if (num_edges == 0) return GMP_OK;
     GMP_REQUIRE(rowptr && ygroups && cg && w1 && b1 && dpre, "tp_tc_dhid: NULL pointer");
     GMP_REQUIRE(num_edges == 0 || (col && rowid && x && g && edge_sh && edge_feat && w2_img), "tp_tc_dhid: NULL edge/feature pointer");
     GMP_REQUIRE(H >= 64 && H <= 256 && H % 64 == 0, "tp_tc_dhid: mlp_dim must be 64, 128, 192 or 256 (got %d)", H);

@@ -178,3 +178,76 @@ def test_cfconv_pipelined_forward_edge_cases(n, deg, shuffle):
     (g16,) = torch.autograd.grad((o16 * cot).sum(), [x16])   # d/dx1 runs the same kernel over the transposed CSR
     assert rel_err(g16, g32) <= 1e-2
     assert torch.equal(o16, m16(x16, ei, ew, sm.lazy()))
+
+
+@pytest.mark.parametrize("case", ["empty", "isolated", "shuffled_small_mul"])
+def test_tp_conv_bf16_tc_corner_cases(case):
+    """tcgen05 tensor-product convolution on degenerate inputs: no edges at all, nodes without edges (rows that must
+    come out as the bias-free zero), multiplicities that do not fill an N-tile (12x0e+12x1o -> zero-padded columns)
+    with a shuffled edge list."""
+    import gmp_b200
+    g = torch.Generator().manual_seed(7)
+    n = 40
+    if case == "empty":
+        ei = torch.zeros(2, 0, dtype=torch.long)
+        irr_in = irr_out = "16x0e+16x1o+16x2e"
+    elif case == "isolated":
+        src = torch.randint(0, 20, (150,), generator=g)
+        dst = torch.randint(0, 20, (150,), generator=g)
+        ei = torch.stack([src, dst])            # nodes 20..39 never appear
+        irr_in = irr_out = "16x0e+16x1o+16x2e"
+    else:
+        src = torch.randint(0, n, (333,), generator=g)
+        dst = torch.randint(0, n, (333,), generator=g)
+        ei = torch.stack([src, dst])
+        irr_in, irr_out = "12x0e+12x1o", "12x0e+12x1o+4x2e"
+    ei = ei.cuda()
+    E = ei.shape[1]
+    sh_ir = "1x0e+1x1o+1x2e"
+    torch.manual_seed(3)
+    m32 = gmp_b200.TensorProductConvLayer(irr_in, irr_out, sh_ir, 8, 64).cuda()
+    with torch.no_grad():
+        m32.fc[2].bias.normal_(0, 0.1)
+    m16 = gmp_b200.TensorProductConvLayer(irr_in, irr_out, sh_ir, 8, 64, precision="bf16").cuda()
+    m16.load_state_dict(m32.state_dict())
+    vec = torch.randn(E, 3, generator=g)
+    esh = gmp_b200.SphericalHarmonics(2)(vec).cuda()
+    eft = torch.rand(E, 8, generator=g).cuda()
+    x = torch.randn(n, m32.in_irreps.dim, generator=g).cuda()
+    x32, x16 = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
+    o32, o16 = m32(x32, ei, esh, eft), m16(x16, ei, esh, eft)
+    assert o16.shape == o32.shape
+    if E == 0:
+        assert float(o16.detach().abs().max()) == 0.0
+    else:
+        assert rel_err(o16, o32) <= 1e-2
+    cot = torch.randn_like(o32)
+    g32 = torch.autograd.grad((o32 * cot).sum(), [x32] + list(m32.parameters()), allow_unused=True)
+    g16 = torch.autograd.grad((o16 * cot).sum(), [x16] + list(m16.parameters()), allow_unused=True)
+    for a, b in zip(g16, g32):
+        if b is None or float(b.abs().max()) == 0.0:
+            assert a is None or float(a.abs().max()) == 0.0
+        else:
+            assert rel_err(a, b) <= 1e-2
+
+
+def test_egnn_bf16_tc_empty_and_isolated():
+    """tcgen05 EGNN kernels with no edges at all, and with nodes that receive no edge (rows must come out as zeros)."""
+    import gmp_b200
+    torch.manual_seed(0)
+    m32 = gmp_b200.EGNNLayer(128, activation="swish").cuda()   # smooth activation: gradients comparable at 1e-2
+    m16 = gmp_b200.EGNNLayer(128, activation="swish", precision="bf16").cuda()
+    m16.load_state_dict(m32.state_dict())
+    n = 50
+    h, pos = torch.randn(n, 128, device="cuda"), torch.randn(n, 3, device="cuda")
+    for ei in (torch.zeros(2, 0, dtype=torch.long, device="cuda"),
+               torch.stack([torch.arange(0, 20), torch.arange(1, 21)]).cuda()):   # a chain on nodes 0..20, nodes 21..49 isolated
+        h32, h16 = h.clone().requires_grad_(True), h.clone().requires_grad_(True)
+        p32, p16 = pos.clone().requires_grad_(True), pos.clone().requires_grad_(True)
+        o32, q32 = m32(h32, p32, ei)
+        o16, q16 = m16(h16, p16, ei)
+        assert rel_err(o16, o32) <= 1e-2 and rel_err(q16, q32) <= 1e-2
+        g32 = torch.autograd.grad(o32.sum() + q32.sum(), [h32, p32])
+        g16 = torch.autograd.grad(o16.sum() + q16.sum(), [h16, p16])
+        for a, b in zip(g16, g32):
+            assert rel_err(a, b) <= 1e-2
