@@ -350,8 +350,9 @@ def dominant_kernel_roofline(model, b, E, N, dev, args):
         kname = "schnet_fwd_kernel<128> (fp32 FFMA) via gmp_schnet_cfconv_fwd"
         note = f"{flops / (ms * 1e-3) / 1e12:.1f} TFLOP/s on the filter-MLP GEMMs (fp32 FFMA)"
     return {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-            # no --set full capture of the pipelined kernel this round (the source-counter pass did not finish within 10 min)
-            "traffic": None, "peak_source": which, "ms_per_launch": ms, "algorithmic_bytes": alg, "note": note}
+            # dram__bytes_read.sum + dram__bytes_write.sum of schnet_fwd_tc2_kernel, one launch, ncu hardware-counter pass
+            # (profiles/r01_ncu_hw_schnet_fwd_tc2.csv: 124.3 + 28.6 MB; the bf16 x1 rows are L2-resident)
+            "traffic": 152.8e6 if prec == 1 else None, "peak_source": which, "ms_per_launch": ms, "algorithmic_bytes": alg, "note": note}
 
 
 if __name__ == "__main__":
