@@ -29,6 +29,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    extra = os.environ.get("GMP_NVCC_EXTRA", "").split()   # e.g. -DGMP_MBAR_WATCHDOG for a debug build
     objs = []
     procs = []
     os.makedirs(os.path.join(PKG, "build"), exist_ok=True)
@@ -39,7 +40,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
                 and all(os.path.getmtime(obj) > os.path.getmtime(h) for h in glob.glob(os.path.join(CSRC, "*.cuh"))
                         + glob.glob(os.path.join(os.path.dirname(PKG), "include", "*.h")))):
             continue
-        cmd = [nvcc, *NVCC_FLAGS, "-c", src, "-o", obj] + (["-Xptxas", "-v"] if verbose else [])
+        cmd = [nvcc, *NVCC_FLAGS, *extra, "-c", src, "-o", obj] + (["-Xptxas", "-v"] if verbose else [])
         procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     for cmd, p in procs:
         out, _ = p.communicate()
@@ -47,8 +48,10 @@ def build(force: bool = False, verbose: bool = False) -> str:
             print(out)
         if p.returncode != 0:
             raise RuntimeError(f"nvcc failed: {' '.join(cmd)}\n{out}")
-    cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB, *objs]
+    tmp = LIB + ".tmp"   # link beside the target and rename: a reader never sees a half-written library
+    cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", tmp, *objs]
     subprocess.run(cmd, check=True)
+    os.replace(tmp, LIB)
     return LIB
 
 

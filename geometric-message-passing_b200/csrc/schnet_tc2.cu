@@ -25,9 +25,10 @@ namespace gmp {
 
 using namespace tc;
 
-constexpr int kS2Threads = 736;   // 23 warps: meta 0-3, epi1 4-11, epi2 12-19 (two groups each: columns 0-63 / 64-127), MMA 20-22
+constexpr int kS2Threads = 864;   // 27 warps: meta 0-7, epi1 8-15, epi2 16-23 (two groups each: columns 0-63 / 64-127), MMA 24-26
 constexpr int kS2MaxSeg = 32;
-constexpr int kS2Stages = 3;      // gathered-row / msg stages, meta blocks, D3 accumulators
+constexpr int kS2Stages = 3;      // gathered-row / msg stages, D3 accumulators
+constexpr int kS2MetaStages = 6;  // meta blocks: small, so the scalar side of a tile can be published well ahead of its row stage
 
 struct Tc2Args {
     const int32_t *rowptr, *col, *perm, *rowid;
@@ -39,6 +40,7 @@ struct Tc2Args {
     float cutoff, gcoeff;
     float* agg;                      // [n,128], zeroed
     float* head;                     // [gridDim.x,128], zeroed
+    int* dbg;                        // debug builds (GMP_TC2_PROGRESS): host-mapped progress words, [gridDim.x][32 warps]
 };
 
 // shared-memory map (bytes from the 1024-aligned base)
@@ -49,38 +51,46 @@ constexpr int o2A2 = o2A1 + 16384;          // 32 KB
 constexpr int o2X = o2A2 + 32768;           // 3 stages x 32 KB: gathered rows -> msg
 constexpr int o2S = o2X + kS2Stages * 32768;  // 16 KB (rows of 128 B, first 64 B used: 32 segments)
 constexpr int o2Vec = o2S + 16384;          // b1[128] b2[128] goff[64]
-constexpr int o2Meta = o2Vec + 320 * 4;     // 3 x { C[128] f32, seg[128] i32, seg_row[32] i32, cnt, nseg, head0, pad }
-constexpr int kMetaBytes = (128 + 128 + 32 + 4) * 4;
-constexpr int o2Tmp = o2Meta + kS2Stages * kMetaBytes;   // meta scratch: wcount[4], first-overflow[4]; end-of-stream tile numbers
-constexpr int o2Bar = o2Tmp + 64;
+constexpr int o2Meta = o2Vec + 320 * 4;     // 3 x { C[128] f32, d[128] f32, seg[128] i32, seg_row[32] i32, cnt, nseg, head0, pad }
+constexpr int kMetaBytes = (128 + 128 + 128 + 32 + 4) * 4;
+constexpr int o2Tmp = o2Meta + kS2MetaStages * kMetaBytes;   // meta scratch per group: wcount[4], first-overflow[4]; then the end-of-stream tile numbers
+constexpr int o2Bar = o2Tmp + 128;
 // barriers
 enum { B_A1F = 0, B_A1E = 1, B_XF = 2, B_D1F = 5, B_D1E = 7, B_A2F = 9, B_A2E = 10, B_D2F = 12, B_D2E = 13, B_MSGF = 14,
-       B_D3F = 17, B_D3E = 20, B_DONE = 23, B_COUNT = 26 };
+       B_D3F = 17, B_D3E = 20, B_DONE = 23, B_MF = 29, B_COUNT = 35 };
 constexpr int kTc2Smem = o2Bar + B_COUNT * 8 + 16 + 1024;
 
 __device__ __forceinline__ float ex2a(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
-// softplus(x) - ln 2 = max(x, 0) + log1p(exp(-|x|)) - ln 2: one MUFU (ex2) and a degree-5 polynomial for log1p on [0, 1]
-// (Abramowitz & Stegun 4.1.44, |error| <= 1e-5: far inside the bf16 rounding of the result)
+// softplus(x) - ln 2 = max(x, 0) + log1p(exp(-|x|)) - ln 2: one MUFU (ex2) and u * (degree-3 polynomial) for log1p(u) on
+// [0, 1] (minimax fit, |error| <= 7.2e-5: far inside the bf16 rounding of the result, which is all the next GEMM sees)
 __device__ __forceinline__ float ssp2(float x) {
     const float u = ex2a(-fabsf(x) * 1.4426950408889634f);
-    float p = fmaf(u, 0.03215845f, -0.13606275f);
-    p = fmaf(u, p, 0.28947478f);
-    p = fmaf(u, p, -0.49190896f);
-    p = fmaf(u, p, 0.99949556f);
+    float p = fmaf(u, -0.058759499f, 0.22568959f);
+    p = fmaf(u, p, -0.47130314f);
+    p = fmaf(u, p, 0.99744922f);
     return fmaf(u, p, fmaxf(x, 0.f) - 0.6931471805599453f);
 }
 __device__ __forceinline__ void cp_async_arrive(uint64_t* bar) {
     asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+#ifdef GMP_TC2_PROGRESS
+// last wait site each warp entered: readable from the host while the kernel hangs
+#define TC2_MARK(site, tcv) do { if (lane == 0 && a.dbg) { *((volatile int*)a.dbg + blockIdx.x * 32 + warp) = ((site) << 20) | (int)((tcv) & 0xfffffu); __threadfence_system(); } } while (0)
+static int* g_tc2_dbg = nullptr;
+#else
+#define TC2_MARK(site, tcv) do { } while (0)
+#endif
+
 struct Meta {
     float C[128];
+    float d[128];     // edge length (1e18 for the padding slots: every Gaussian underflows to 0)
     int seg[128];
     int seg_row[32];
     int cnt, nseg, head0, pad;
 };
 
-__global__ void __launch_bounds__(768, 1) schnet_fwd_tc2_kernel(Tc2Args a) {  // 768: caps the registers at 80 (6 warps on a scheduler)
+__global__ void __launch_bounds__(kS2Threads, 1) schnet_fwd_tc2_kernel(Tc2Args a) {  // 864 threads: at most 72 registers
     extern __shared__ __align__(16) uint8_t smraw[];
     uint8_t* sm = smraw + ((1024u - (smem_u32(smraw) & 1023u)) & 1023u);
     float* b1s = reinterpret_cast<float*>(sm + o2Vec);
@@ -88,11 +98,12 @@ __global__ void __launch_bounds__(768, 1) schnet_fwd_tc2_kernel(Tc2Args a) {  //
     float* goff = b2s + 128;
     Meta* meta = reinterpret_cast<Meta*>(sm + o2Meta);
     int* tmp = reinterpret_cast<int*>(sm + o2Tmp);
-    volatile int* end_g1 = tmp + 8;   // tile number of the end-of-stream marker, passed G1 -> epi1 -> G2
-    volatile int* end_e1 = tmp + 9;
+    volatile int* end_g1 = tmp + 16;   // tile number of the end-of-stream marker, passed G1 -> epi1 -> G2
+    volatile int* end_e1 = tmp + 17;
     uint64_t* bars = reinterpret_cast<uint64_t*>(sm + o2Bar);
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(sm + o2Bar + B_COUNT * 8);
     const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+    TC2_MARK(199, 0);
 
     // ---- setup: weights -> bf16 images, vectors, barriers, tensor memory
     for (int x = t; x < 128 * 8; x += kS2Threads) {  // W1 [f][g], g padded to 64
@@ -120,124 +131,181 @@ __global__ void __launch_bounds__(768, 1) schnet_fwd_tc2_kernel(Tc2Args a) {  //
         *end_g1 = -1;
         *end_e1 = -1;
         for (int i = 0; i < B_COUNT; ++i) mbar_init(&bars[i], 1);
-        const int c128[] = {B_A1F, B_D3E, B_D3E + 1, B_D3E + 2, B_DONE, B_DONE + 1, B_DONE + 2};
-        for (int i = 0; i < 7; ++i) mbar_init(&bars[c128[i]], 128);
-        const int c256[] = {B_D1E, B_D1E + 1, B_A2F, B_D2E, B_MSGF, B_MSGF + 1, B_MSGF + 2};   // both column groups arrive
-        for (int i = 0; i < 7; ++i) mbar_init(&bars[c256[i]], 256);
-        for (int i = 0; i < kS2Stages; ++i) mbar_init(&bars[B_XF + i], 256);  // 128 cp.async completions + 128 plain arrives
+        for (int i = 0; i < kS2Stages; ++i) mbar_init(&bars[B_D3E + i], 128);
+        for (int i = 0; i < kS2MetaStages; ++i) { mbar_init(&bars[B_DONE + i], 128); mbar_init(&bars[B_MF + i], 128); }
+        const int c256[] = {B_A1F, B_D1E, B_D1E + 1, B_A2F, B_D2E, B_MSGF, B_MSGF + 1, B_MSGF + 2};   // both groups arrive
+        for (int i = 0; i < 8; ++i) mbar_init(&bars[c256[i]], 256);
+        for (int i = 0; i < kS2Stages; ++i) mbar_init(&bars[B_XF + i], 512);  // 256 cp.async completions + 256 plain arrives
         fence_mbar_init();
     }
-    if (warp == 20) tmem_alloc<512>(tmem_ptr);
+    if (warp == 24) tmem_alloc<512>(tmem_ptr);
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tm = *tmem_ptr;
     const uint32_t tmD1 = tm, tmD2 = tm + 256, tmD3 = tm + 384;  // D1[p] = tmD1 + 128 p, D3[st] = tmD3 + 32 st
+    TC2_MARK(200, 0);
 
     const int64_t e_begin = (a.E * blockIdx.x) / gridDim.x, e_end = (a.E * (blockIdx.x + 1)) / gridDim.x;
 
-    if (warp < 4) {
-        // ===================== meta: thread = edge slot =====================
-        const int e = t;
+    if (warp < 8) {
+        // ===================== meta: thread = (edge slot, half).  Both halves derive the tile's segmentation (cheap, and
+        // it saves a hand-off); half 0 publishes the meta block; each half gathers one K slab of the row and expands 32 of the
+        // 64 basis columns -- the meta work is the longest serial chain per tile, so it gets two threads per edge
+        const int e = t & 127, mh = t >> 7, mw = warp & 3;
+        int* mtmp = tmp + 8 * mh;
         const float cw = 3.14159265358979323846f / a.cutoff;
         const float c2 = a.gcoeff * 1.4426950408889634f;
         int64_t e_cur = e_begin;
+        // Scalars of a tile (CSR row, edge id, source, length, first row pointer) are fetched one tile ahead, speculating
+        // that the current tile is not cut short: two dependent L2 round trips per tile that would otherwise sit on the
+        // meta warps' critical path.  Level 1 = indexed by the sorted position, level 2 = indexed by what level 1 returned.
+        struct Pre { int rid, ridp, eid, src, rp0; float d; };
+        auto fetch1 = [&](int64_t e0, Pre& P) {
+            const int64_t rem = e_end - e0;
+            P.rid = 0; P.ridp = -1; P.eid = 0; P.src = 0;
+            if (rem > 0) {
+                const int c = (int)min((int64_t)128, rem);
+                const int64_t k = e0 + min(e, c - 1);
+                P.rid = __ldg(a.rowid + k);
+                if (e > 0 && e < c) P.ridp = __ldg(a.rowid + k - 1);
+                P.eid = a.perm ? __ldg(a.perm + k) : (int)k;
+                P.src = __ldg(a.col + k);
+            }
+        };
+        auto fetch2 = [&](int64_t e0, Pre& P) {
+            P.d = 1.0e18f; P.rp0 = 0;
+            if (e_end - e0 > 0) {
+                P.d = __ldg(a.ew + P.eid);
+                if (e == 0) P.rp0 = __ldg(a.rowptr + P.rid);
+            }
+        };
+        Pre cur, nxt;
+        fetch1(e_begin, cur);
+        fetch2(e_begin, cur);
         for (uint32_t tc = 0;; ++tc) {
             const uint32_t st = tc % kS2Stages, par = (tc / kS2Stages) & 1u;
             const int64_t remain = e_end - e_cur;
-            // ---- everything that only needs global memory comes first: its latency overlaps the buffer waits below
+            fetch1(e_cur + 128, nxt);
             int cnt = (int)min((int64_t)128, remain);
-            int rid = 0, seg = 0, src = 0;
+            const int rid = cur.rid, src = cur.src;
+            int seg = 0;
             bool flag = false, valid = false;
             float d = 1.0e18f, C = 0.f;
             if (remain > 0) {
-                const int64_t k = e_cur + min(e, cnt - 1);
-                rid = __ldg(a.rowid + k);
-                flag = e < cnt && (e == 0 || __ldg(a.rowid + k - 1) != rid);
+                flag = e < cnt && cur.ridp != rid;
                 const unsigned bal = __ballot_sync(0xffffffffu, flag);
-                if (lane == 0) tmp[warp] = __popc(bal);
-                bar_sync_named(1, 128);
+                if (lane == 0) mtmp[mw] = __popc(bal);
+                bar_sync_named(1 + mh, 128);
                 int base = 0;
 #pragma unroll
                 for (int w = 0; w < 4; ++w)
-                    if (w < warp) base += tmp[w];
+                    if (w < mw) base += mtmp[w];
                 seg = base + __popc(bal & ((2u << lane) - 1u)) - 1;   // 0-based segment of this slot
                 // at most 32 rows per tile: cut the tile in front of the 33rd row
                 const unsigned over = __ballot_sync(0xffffffffu, e < cnt && seg >= kS2MaxSeg);
-                if (lane == 0) tmp[4 + warp] = over ? warp * 32 + (__ffs(over) - 1) : 128;
-                bar_sync_named(1, 128);
-                cnt = min(cnt, min(min(tmp[4], tmp[5]), min(tmp[6], tmp[7])));
+                if (lane == 0) mtmp[4 + mw] = over ? mw * 32 + (__ffs(over) - 1) : 128;
+                bar_sync_named(1 + mh, 128);
+                cnt = min(cnt, min(min(mtmp[4], mtmp[5]), min(mtmp[6], mtmp[7])));
                 valid = e < cnt;
                 if (valid) {
-                    const int64_t kk = e_cur + e;
-                    const int eid = a.perm ? __ldg(a.perm + kk) : (int)kk;
-                    src = __ldg(a.col + kk);
-                    d = __ldg(a.ew + eid);
+                    d = cur.d;
                     C = 0.5f * (__cosf(d * cw) + 1.0f);
                 }
             }
-            const int head0 = (remain > 0 && e == 0) ? ((int64_t)__ldg(a.rowptr + rid) < e_begin ? 1 : 0) : 0;
-            mbar_wait(&bars[B_DONE + st], par ^ 1u);   // tile tc-3 read out: its meta block is free
+            const int head0 = (remain > 0 && e == 0) ? ((int64_t)cur.rp0 < e_begin ? 1 : 0) : 0;
+            // (the scratch words are not rewritten before every thread of the group has passed the first barrier of the
+            // next tile, which is after its last read here)
+            const uint32_t ms = tc % kS2MetaStages;
+            TC2_MARK(1, tc);
+            mbar_wait(&bars[B_DONE + ms], ((tc / kS2MetaStages) & 1u) ^ 1u);   // tile tc-6 read out: its meta block is free
+            TC2_MARK(2, tc);
             mbar_wait(&bars[B_D3F + st], par ^ 1u);    // G3 of tile tc-3 has read the msg image: the row stage is free
-            Meta& M = meta[st];
+            Meta& M = meta[ms];
             if (remain <= 0) {  // end-of-stream marker: cnt = 0
-                if (e == 0) { M.cnt = 0; M.nseg = 0; }
+                if (t == 0) { M.cnt = 0; M.nseg = 0; }
+                if (mh == 0) mbar_arrive(&bars[B_MF + ms]);
                 cp_async_arrive(&bars[B_XF + st]);
                 mbar_arrive(&bars[B_XF + st]);
-                mbar_wait(&bars[B_A1E], (tc & 1u) ^ 1u);
-                mbar_arrive(&bars[B_A1F]);
                 break;
             }
-            M.C[e] = C;
-            M.seg[e] = valid ? seg : -1;
-            if (flag && seg < kS2MaxSeg && valid) M.seg_row[seg] = rid;
-            if (e == cnt - 1) { M.cnt = cnt; M.nseg = seg + 1; }
-            if (e == 0) M.head0 = head0;
-            // gather x1[src] (bf16, 16 chunks of 16 B) into the swizzled row image
-            uint8_t* xs = sm + o2X + st * 32768;
+            if (mh == 0) {
+                M.C[e] = C;
+                M.d[e] = d;
+                M.seg[e] = valid ? seg : -1;
+                if (flag && seg < kS2MaxSeg && valid) M.seg_row[seg] = rid;
+                if (e == cnt - 1) { M.cnt = cnt; M.nseg = seg + 1; }
+                if (e == 0) M.head0 = head0;
+                mbar_arrive(&bars[B_MF + ms]);   // meta block published: epilogue 1 expands the basis from d
+            }
+            // gather x1[src] (bf16): this half's K slab = 8 chunks of 16 B, into the swizzled row image
+            uint8_t* xs = sm + o2X + st * 32768 + mh * 16384;
             if (valid) {
-                const __nv_bfloat16* row = a.x1 + (int64_t)src * 128;
+                const __nv_bfloat16* row = a.x1 + (int64_t)src * 128 + mh * 64;
 #pragma unroll
-                for (int ch = 0; ch < 16; ++ch)
-                    __pipeline_memcpy_async(xs + (ch >> 3) * 16384 + sw128_chunk_off(e, ch & 7), row + ch * 8, 16);
+                for (int ch = 0; ch < 8; ++ch) __pipeline_memcpy_async(xs + sw128_chunk_off(e, ch), row + ch * 8, 16);
             } else {
 #pragma unroll
-                for (int ch = 0; ch < 16; ++ch)
-                    *reinterpret_cast<uint4*>(xs + (ch >> 3) * 16384 + sw128_chunk_off(e, ch & 7)) = make_uint4(0u, 0u, 0u, 0u);
+                for (int ch = 0; ch < 8; ++ch) *reinterpret_cast<uint4*>(xs + sw128_chunk_off(e, ch)) = make_uint4(0u, 0u, 0u, 0u);
             }
             cp_async_arrive(&bars[B_XF + st]);   // fires when this thread's copies have landed
             mbar_arrive(&bars[B_XF + st]);       // releases the meta block and the zero rows (plain stores)
-            // Gaussian basis -> A1 (single buffer: G1 of the previous tile must have read it)
-            mbar_wait(&bars[B_A1E], (tc & 1u) ^ 1u);
-#pragma unroll
-            for (int ch = 0; ch < 8; ++ch) {
-                float v[8];
-#pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    const float u = d - goff[ch * 8 + q];
-                    v[q] = (ch * 8 + q == a.G) ? 1.0f : ex2a(c2 * u * u);   // column G = 1: picks up b1 from the W1 image
-                }
-                *reinterpret_cast<uint4*>(sm + o2A1 + sw128_chunk_off(e, ch)) =
-                    make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+            fetch2(e_cur + 128, nxt);
+            if (cnt != 128 && e_cur + cnt < e_end) {  // the tile was cut at 32 rows: the speculative fetch missed
+                fetch1(e_cur + cnt, nxt);
+                fetch2(e_cur + cnt, nxt);
             }
-            fence_proxy_async();
-            mbar_arrive(&bars[B_A1F]);
             e_cur += cnt;
+            cur = nxt;
         }
-    } else if (warp < 12) {
+    } else if (warp < 16) {
         // ===================== epilogue 1: h1 = ssp(D1 + b1) -> A2; group g owns columns [64 g, 64 g + 64) = K slab g =====================
-        const int e = (warp & 3) * 32 + lane, g = (warp - 4) >> 2;
+        const int e = (warp & 3) * 32 + lane, g = (warp - 8) >> 2;
         const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
         const bool add_b1 = a.G >= 64;   // otherwise b1 came through the spare basis column
+        const float c2 = a.gcoeff * 1.4426950408889634f;
+        // Gaussian basis of tile tq -> A1 (this group's 32 of the 64 columns).  Called when G1 of tile tq-1 is known to be
+        // complete (its D1F has been waited for), so the single A1 buffer is free; G1 of tile tq then runs on the tensor core
+        // while these threads apply the softplus to tile tq-1.
+        auto basis = [&](uint32_t tq) {
+            const uint32_t sq = tq % kS2MetaStages;
+            TC2_MARK(3, tq);
+            mbar_wait(&bars[B_MF + sq], (tq / kS2MetaStages) & 1u);
+            const Meta& M = meta[sq];
+            if (M.cnt != 0) {
+                const float d = M.d[e];
+#pragma unroll
+                for (int c4 = 0; c4 < 4; ++c4) {
+                    const int ch = 4 * g + c4;
+                    float v[8];
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        const float u = d - goff[ch * 8 + q];
+                        v[q] = (ch * 8 + q == a.G) ? 1.0f : ex2a(c2 * u * u);   // column G = 1: picks up b1 from the W1 image
+                    }
+                    *reinterpret_cast<uint4*>(sm + o2A1 + sw128_chunk_off(e, ch)) =
+                        make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+                }
+                fence_proxy_async();
+            }
+            mbar_arrive(&bars[B_A1F]);   // also for the end-of-stream marker: G1 passes it on
+        };
+        basis(0);
         for (uint32_t tc = 0;; ++tc) {
             const uint32_t p = tc & 1u, par = (tc >> 1) & 1u;
+            TC2_MARK(4, tc);
             mbar_wait(&bars[B_D1F + p], par);
             if (*end_g1 == (int)tc) {  // end of stream: pass it on to the G2 warp
-                if (t == 128) *end_e1 = (int)tc;
+                if (t == 256) *end_e1 = (int)tc;
+                // same back-pressure as a real tile: G2 must have consumed the previous phase of A2F before this arrival
+                // completes the next one -- a waiter that falls two phases behind sees the parity it is waiting for as
+                // "not yet complete" and never wakes (seen as a rare hang on one-tile chunks)
+                mbar_wait(&bars[B_A2E + g], (tc & 1u) ^ 1u);
                 mbar_arrive(&bars[B_A2F]);
                 break;
             }
+            basis(tc + 1);
             tc_fence_after();
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
@@ -245,6 +313,7 @@ __global__ void __launch_bounds__(768, 1) schnet_fwd_tc2_kernel(Tc2Args a) {  //
                 tmem_ld32(tmD1 + p * 128 + lane_base + 64 * g + 32 * j, v);
 #pragma unroll
                 for (int q = 0; q < 32; ++q) v[q] = ssp2(add_b1 ? v[q] + b1s[64 * g + 32 * j + q] : v[q]);
+                TC2_MARK(5, tc);
                 if (j == 0) mbar_wait(&bars[B_A2E + g], (tc & 1u) ^ 1u);  // G2 of the previous tile has read this K slab
 #pragma unroll
                 for (int q = 0; q < 4; ++q)
@@ -257,14 +326,14 @@ __global__ void __launch_bounds__(768, 1) schnet_fwd_tc2_kernel(Tc2Args a) {  //
             fence_proxy_async();
             mbar_arrive(&bars[B_A2F]);
         }
-    } else if (warp < 20) {
+    } else if (warp < 24) {
         // ===================== epilogue 2: msg (group g: columns [64 g, 64 g + 64)); group 0 also writes the one-hot tile,
         // group 1 reads out the previous tile (lane = feature column) =====================
-        const int e = (warp & 3) * 32 + lane, g = (warp - 12) >> 2;
+        const int e = (warp & 3) * 32 + lane, g = (warp - 16) >> 2;
         const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
         auto readout = [&](uint32_t tq) {  // D3 of tile tq: lane = feature column e, accumulator column = segment
-            const uint32_t st = tq % kS2Stages;
-            const Meta& M = meta[st];
+            const uint32_t st = tq % kS2Stages, ms = tq % kS2MetaStages;
+            const Meta& M = meta[ms];
             float v[32];
             tmem_ld32(tmD3 + st * 32 + lane_base, v);
             tc_fence_before();
@@ -293,23 +362,26 @@ __global__ void __launch_bounds__(768, 1) schnet_fwd_tc2_kernel(Tc2Args a) {  //
                 }
             }
             mbar_arrive(&bars[B_D3E + st]);
-            mbar_arrive(&bars[B_DONE + st]);
+            mbar_arrive(&bars[B_DONE + ms]);
         };
         uint32_t tc = 0;
         for (;; ++tc) {
             const uint32_t st = tc % kS2Stages, par = (tc / kS2Stages) & 1u;
+            TC2_MARK(6, tc);
             mbar_wait(&bars[B_XF + st], par);    // gathered rows (cp.async) + meta block (plain stores)
-            const Meta& M = meta[st];
+            const Meta& M = meta[tc % kS2MetaStages];
             const int cnt = M.cnt;
-            if (tc > 0) {   // G3 of the previous tile is done: its accumulator can be read out, the one-hot tile rewritten
-                mbar_wait(&bars[B_D3F + ((tc - 1) % kS2Stages)], ((tc - 1) / kS2Stages) & 1u);
-                tc_fence_after();
-                if (g == 1) readout(tc - 1);   // first: releases the meta block early (the meta warps wait for it)
-            }
-            if (cnt == 0) {  // end of stream: wake the G3 warp
+            if (cnt == 0) {  // end of stream: read out the last tile, wake the G3 warp
+                if (tc > 0) {
+                    TC2_MARK(7, tc);
+                    mbar_wait(&bars[B_D3F + ((tc - 1) % kS2Stages)], ((tc - 1) / kS2Stages) & 1u);
+                    tc_fence_after();
+                    if (g == 1) readout(tc - 1);
+                }
                 mbar_arrive(&bars[B_MSGF + st]);
                 break;
             }
+            TC2_MARK(8, tc);
             mbar_wait(&bars[B_D2F], tc & 1u);
             tc_fence_after();
             const float C = M.C[e];
@@ -335,8 +407,14 @@ __global__ void __launch_bounds__(768, 1) schnet_fwd_tc2_kernel(Tc2Args a) {  //
                 }
             }
             tc_fence_before();
-            mbar_arrive(&bars[B_D2E]);
-            // one-hot row-membership tile (single buffer: G3 of the previous tile has read it -- waited for above)
+            mbar_arrive(&bars[B_D2E]);   // G2 of the next tile may start: nothing below is on its path
+            // G3 of the previous tile is done (it has had a whole message phase to finish): the single one-hot tile can be
+            // rewritten and the previous accumulator read out
+            if (tc > 0) {
+                TC2_MARK(9, tc);
+                mbar_wait(&bars[B_D3F + ((tc - 1) % kS2Stages)], ((tc - 1) / kS2Stages) & 1u);
+                tc_fence_after();
+            }
             if (g == 0) {
                 const int seg = M.seg[e];
 #pragma unroll
@@ -348,15 +426,18 @@ __global__ void __launch_bounds__(768, 1) schnet_fwd_tc2_kernel(Tc2Args a) {  //
             }
             fence_proxy_async();
             mbar_arrive(&bars[B_MSGF + st]);
+            if (g == 1 && tc > 0) readout(tc - 1);   // global read-modify-write latency: off the G2 / G3 critical path
         }
-    } else if (warp == 20) {
+    } else if (warp == 24) {
         // ===================== G1 = rbf W1^T (whole warp, one elected lane issues) =====================
         const uint32_t id1 = umma_idesc_bf16(128, 128);
         const uint32_t w1b = smem_u32(sm + o2W1), a1b = smem_u32(sm + o2A1);
         for (uint32_t tc = 0;; ++tc) {
             const uint32_t p = tc & 1u, par = (tc >> 1) & 1u, st = tc % kS2Stages;
+            TC2_MARK(10, tc);
             mbar_wait(&bars[B_A1F], tc & 1u);
-            if (meta[st].cnt == 0) {  // end of stream: tell epilogue 1
+            if (meta[tc % kS2MetaStages].cnt == 0) {  // end of stream: tell epilogue 1
+                mbar_wait(&bars[B_D1E + p], par ^ 1u);   // epilogue 1 has consumed the previous phase of D1F[p] (see the note there)
                 if (elect_one()) {
                     *end_g1 = (int)tc;
                     __threadfence_block();
@@ -365,22 +446,24 @@ __global__ void __launch_bounds__(768, 1) schnet_fwd_tc2_kernel(Tc2Args a) {  //
                 __syncwarp();
                 break;
             }
+            TC2_MARK(11, tc);
             mbar_wait(&bars[B_D1E + p], par ^ 1u);
             tc_fence_after();
             if (elect_one()) {
                 umma_tile(tmD1 + p * 128, a1b, 16384, w1b, 16384, 64, id1);
                 umma_commit(&bars[B_D1F + p]);
-                umma_commit(&bars[B_A1E]);
             }
             __syncwarp();
         }
-    } else if (warp == 21) {
+    } else if (warp == 25) {
         // ===================== G2 = h1 W2^T =====================
         const uint32_t id1 = umma_idesc_bf16(128, 128);
         const uint32_t w2b = smem_u32(sm + o2W2), a2b = smem_u32(sm + o2A2);
         for (uint32_t tc = 0;; ++tc) {
+            TC2_MARK(12, tc);
             mbar_wait(&bars[B_A2F], tc & 1u);
             if (*end_e1 == (int)tc) break;
+            TC2_MARK(13, tc);
             mbar_wait(&bars[B_D2E], (tc & 1u) ^ 1u);
             tc_fence_after();
             if (elect_one()) {
@@ -402,8 +485,10 @@ __global__ void __launch_bounds__(768, 1) schnet_fwd_tc2_kernel(Tc2Args a) {  //
         const uint32_t sb = smem_u32(sm + o2S);
         for (uint32_t tc = 0;; ++tc) {
             const uint32_t st = tc % kS2Stages, par = (tc / kS2Stages) & 1u;
+            TC2_MARK(14, tc);
             mbar_wait(&bars[B_MSGF + st], par);
-            if (meta[st].cnt == 0) break;
+            if (meta[tc % kS2MetaStages].cnt == 0) break;
+            TC2_MARK(15, tc);
             mbar_wait(&bars[B_D3E + st], par ^ 1u);
             tc_fence_after();
             if (elect_one()) {
@@ -416,9 +501,11 @@ __global__ void __launch_bounds__(768, 1) schnet_fwd_tc2_kernel(Tc2Args a) {  //
             __syncwarp();
         }
     }
+    TC2_MARK(255, 0);
     tc_fence_before();
     __syncthreads();
-    if (warp == 20) tmem_dealloc<512>(tm);
+    TC2_MARK(256, 0);
+    if (warp == 24) tmem_dealloc<512>(tm);
 }
 
 // rows that straddle a CTA boundary: add the later CTAs' head partials in CTA order.  One block per chunk; the block of
@@ -537,19 +624,31 @@ __global__ void __launch_bounds__(896, 1) schnet_bwd_tc2_kernel(Tc2BwdArgs b) { 
         const int e = t;
         const float cw = 3.14159265358979323846f / a.cutoff;
         const float c2 = a.gcoeff * 1.4426950408889634f;
+        // scalars are fetched one tile ahead (two dependent L2 round trips: position -> edge id -> length)
+        struct Pre { int eid, src, grow; float d; };
+        auto fetch1 = [&](uint32_t tq, Pre& P) {
+            const int64_t k = e_begin + (int64_t)tq * 128 + e;
+            P.eid = 0; P.src = 0; P.grow = 0;
+            if (k < e_end) {
+                P.eid = a.perm ? __ldg(a.perm + k) : (int)k;
+                P.src = __ldg(a.col + k);
+                P.grow = __ldg(a.rowid + k);
+            }
+        };
+        auto fetch2 = [&](uint32_t tq, Pre& P) {
+            P.d = (e_begin + (int64_t)tq * 128 + e < e_end) ? __ldg(a.ew + P.eid) : 1.0e18f;
+        };
+        Pre cur, nxt;
+        fetch1(0, cur);
+        fetch2(0, cur);
         for (uint32_t tc = 0; tc < ntile; ++tc) {
             const uint32_t p = tc & 1u, par = (tc >> 1) & 1u;
             const int64_t k = e_begin + (int64_t)tc * 128 + e;
             const bool valid = k < e_end;
-            int src = 0, grow = 0;
-            float d = 1.0e18f, C = 0.f;
-            if (valid) {
-                const int eid = a.perm ? __ldg(a.perm + k) : (int)k;
-                src = __ldg(a.col + k);
-                grow = __ldg(a.rowid + k);
-                d = __ldg(a.ew + eid);
-                C = 0.5f * (__cosf(d * cw) + 1.0f);
-            }
+            fetch1(tc + 1, nxt);
+            const int src = cur.src, grow = cur.grow;
+            const float d = cur.d;
+            const float C = valid ? 0.5f * (__cosf(d * cw) + 1.0f) : 0.f;
             mbar_wait(&bars[C_DONE + p], par ^ 1u);   // G4 of tile tc-2 done: every buffer of stage p is free
             metaC(p)[e] = C;
             metaRow(p)[e] = grow;
@@ -566,6 +665,7 @@ __global__ void __launch_bounds__(896, 1) schnet_bwd_tc2_kernel(Tc2BwdArgs b) { 
             }
             cp_async_arrive(&bars[C_XF + p]);
             mbar_arrive(&bars[C_XF + p]);
+            fetch2(tc + 1, nxt);   // in flight during the basis phase
             uint8_t* rs = sm + o3R + p * 16384;
 #pragma unroll
             for (int ch = 0; ch < 8; ++ch) {
@@ -581,6 +681,7 @@ __global__ void __launch_bounds__(896, 1) schnet_bwd_tc2_kernel(Tc2BwdArgs b) { 
             }
             fence_proxy_async();
             mbar_arrive(&bars[C_RF + p]);
+            cur = nxt;
         }
     } else if (warp < 8) {
         // ===================== epiP: P = x1[src] * g[dst] * C over the gathered rows =====================
@@ -765,6 +866,10 @@ using namespace gmp;
 
 extern "C" {
 
+#ifdef GMP_TC2_PROGRESS
+void gmp_debug_tc2_progress(int* host_mapped) { g_tc2_dbg = host_mapped; }
+#endif
+
 int32_t gmp_schnet_tc2_num_chunks(int64_t num_edges) {
     const int64_t nt = ceil_div(num_edges, 128);
     return (int32_t)(nt < num_sms() ? (nt < 1 ? 1 : nt) : num_sms());
@@ -786,6 +891,11 @@ int gmp_schnet_cfconv_fwd_tc2(const int32_t* rowptr, const int32_t* col, const i
     a.rowptr = rowptr; a.col = col; a.perm = perm; a.rowid = rowid; a.n = n; a.E = num_edges; a.ew = edge_weight;
     a.x1 = (const __nv_bfloat16*)x1_bf16; a.w1 = f->w1; a.b1 = f->b1; a.w2 = f->w2; a.b2 = f->b2; a.goff = f->gauss_offset;
     a.G = f->num_gaussians; a.cutoff = f->cutoff; a.gcoeff = f->gauss_coeff; a.agg = agg; a.head = head;
+#ifdef GMP_TC2_PROGRESS
+    a.dbg = g_tc2_dbg;
+#else
+    a.dbg = nullptr;
+#endif
     GMP_CUDA(cudaFuncSetAttribute(schnet_fwd_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTc2Smem));
     schnet_fwd_tc2_kernel<<<nchunks, kS2Threads, kTc2Smem, stream>>>(a);
     int rc = check_launch("schnet_fwd_tc2_kernel");
@@ -810,6 +920,7 @@ int gmp_schnet_cfconv_bwd_tc2(const int32_t* rowptr, const int32_t* col, const i
     a.rowptr = rowptr; a.col = col; a.perm = perm; a.rowid = rowid; a.n = n; a.E = num_edges; a.ew = edge_weight;
     a.x1 = (const __nv_bfloat16*)x1_bf16; a.w1 = f->w1; a.b1 = f->b1; a.w2 = f->w2; a.b2 = f->b2; a.goff = f->gauss_offset;
     a.G = f->num_gaussians; a.cutoff = f->cutoff; a.gcoeff = f->gauss_coeff; a.agg = nullptr; a.head = nullptr;
+    a.dbg = nullptr;
     b.g_agg = g_agg; b.parts = wgrad_parts;
     GMP_CUDA(cudaFuncSetAttribute(schnet_bwd_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTc2BwdSmem));
     schnet_bwd_tc2_kernel<<<nparts, kB2Threads, kTc2BwdSmem, stream>>>(b);

@@ -395,14 +395,19 @@ __device__ __forceinline__ void tc_ygroup(EpiCtx& c, const TcYGroup& G) {
             mbar_wait(&c.bars[10 + buf * 2 + c.g], (c.gi >> 1) & 1u);
             tc_fence_after();
             const uint32_t tb = c.tm + c.lane_base + buf * 256 + c.g * 128;
+            // the load of block j+1 is in flight while block j is consumed
+            uint32_t va[32], vb[32];
+            tmem_ld32_issue(tb, va);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                float v[32];
-                tmem_ld32(tb + 32 * j, v);
+                uint32_t(&v)[32] = (j & 1) ? vb : va;
+                uint32_t(&vn)[32] = (j & 1) ? va : vb;
+                tmem_ld_wait(v);
+                if (j < 3) tmem_ld32_issue(tb + 32 * (j + 1), vn);
                 if constexpr (WS == 32) {
                     const float y = __uint_as_float(F[(q * HA + j) * 256]);
 #pragma unroll
-                    for (int b = 0; b < 32; ++b) r[b] = fmaf(v[b], y, r[b]);
+                    for (int b = 0; b < 32; ++b) r[b] = fmaf(__uint_as_float(v[b]), y, r[b]);
                 } else {
 #pragma unroll
                     for (int aa = 0; aa < 4; ++aa) {
@@ -412,7 +417,7 @@ __device__ __forceinline__ void tc_ygroup(EpiCtx& c, const TcYGroup& G) {
 #pragma unroll
                         for (int b = 0; b < 8; ++b)
 #pragma unroll
-                            for (int k = 0; k < M; ++k) r[b * M + k] = fmaf(v[aa * 8 + b], y[k], r[b * M + k]);
+                            for (int k = 0; k < M; ++k) r[b * M + k] = fmaf(__uint_as_float(v[aa * 8 + b]), y[k], r[b * M + k]);
                     }
                 }
             }
@@ -573,42 +578,50 @@ __global__ void __launch_bounds__(kTcThreads, 1) tp_contract_tc_kernel(TcTpArgs 
                     const int nb = min(WS, G.MB - sl * WS);
                     const int nv = nb * G.DB;
                     const int cbase = G.r_off + sl * WS * G.DB;
-                    const int npairs = nseg * nv;
                     bar_sync_named(1, kEpiThreads + kWalkThreads);  // O full
-                    bar_sync_named(3, kWalkThreads);                // the previous flush's stores are visible to all walkers
-                    // (segment, column) pairs in batches: the old values are requested first (L2 latency overlaps the
-                    // shared-memory sums), and O is handed back to the epilogue before the stores
-                    for (int p0 = 0; p0 < npairs || p0 == 0; p0 += kWalkThreads * kWalkBatch) {
-                        float* dst[kWalkBatch];
-                        float old[kWalkBatch], sum[kWalkBatch];
+                    // lane = result column, walker warp w takes segments w, w+2, ...  The old values are requested first (the L2
+                    // round trip overlaps the shared-memory sums) and O is handed back to the epilogue before the last stores.
+                    // No extra barrier between flushes: a thread's stores of flush f precede its own arrival at the O-full barrier
+                    // of flush f+1, which every walker thread passes before it loads for f+1.
+                    const int wl = wt & 31, ww = wt >> 5;
+                    bool released = false;
+                    for (int c0 = 0; c0 < nv; c0 += 32) {
+                        const int cc = c0 + wl;
+                        const bool colok = cc < nv;
+                        for (int s0 = ww; s0 < nseg; s0 += 2 * kWalkBatch) {
+                            float* dst[kWalkBatch];
+                            float old[kWalkBatch], sum[kWalkBatch];
 #pragma unroll
-                        for (int j = 0; j < kWalkBatch; ++j) {
-                            const int p = p0 + j * kWalkThreads + wt;
-                            dst[j] = nullptr;
-                            old[j] = 0.f;
-                            if (p < npairs) {
-                                const int sg = p / nv, cc = p - sg * nv;
-                                dst[j] = (sg == 0 && head0) ? a.head + (int64_t)blockIdx.x * a.r_len + cbase + cc
-                                                            : a.res + (int64_t)seg_row[sg] * a.r_len + cbase + cc;
-                                old[j] = __ldcg(dst[j]);
+                            for (int j = 0; j < kWalkBatch; ++j) {
+                                const int sg = s0 + 2 * j;
+                                dst[j] = nullptr;
+                                old[j] = 0.f;
+                                if (colok && sg < nseg) {
+                                    dst[j] = (sg == 0 && head0) ? a.head + (int64_t)blockIdx.x * a.r_len + cbase + cc
+                                                                : a.res + (int64_t)seg_row[sg] * a.r_len + cbase + cc;
+                                    old[j] = __ldcg(dst[j]);
+                                }
                             }
-                        }
 #pragma unroll
-                        for (int j = 0; j < kWalkBatch; ++j) {
-                            const int p = p0 + j * kWalkThreads + wt;
-                            float acc = 0.f;
-                            if (p < npairs) {
-                                const int sg = p / nv, cc = p - sg * nv;
-                                const int b = seg_start[sg], e = seg_start[sg + 1];
-                                for (int x = b; x < e; ++x) acc += O0[x * kOLd + cc] + O1[x * kOLd + cc];
+                            for (int j = 0; j < kWalkBatch; ++j) {
+                                const int sg = s0 + 2 * j;
+                                float acc = 0.f;
+                                if (colok && sg < nseg) {
+                                    const int b = seg_start[sg], e = seg_start[sg + 1];
+                                    for (int x = b; x < e; ++x) acc += O0[x * kOLd + cc] + O1[x * kOLd + cc];
+                                }
+                                sum[j] = acc;
                             }
-                            sum[j] = acc;
-                        }
-                        if (p0 + kWalkThreads * kWalkBatch >= npairs) bar_arrive_named(2, kEpiThreads + kWalkThreads);  // O free
+                            if (c0 + 32 >= nv && s0 + 2 * kWalkBatch >= nseg) {   // last reads of O for this flush (uniform per warp)
+                                bar_arrive_named(2, kEpiThreads + kWalkThreads);  // O free
+                                released = true;
+                            }
 #pragma unroll
-                        for (int j = 0; j < kWalkBatch; ++j)
-                            if (dst[j]) *dst[j] = old[j] + sum[j];
+                            for (int j = 0; j < kWalkBatch; ++j)
+                                if (dst[j]) *dst[j] = old[j] + sum[j];
+                        }
                     }
+                    if (!released) bar_arrive_named(2, kEpiThreads + kWalkThreads);  // nothing to do for this warp
                 }
             }
             bar_sync_named(3, kWalkThreads);  // seg table reusable

@@ -180,6 +180,41 @@ def test_cfconv_pipelined_forward_edge_cases(n, deg, shuffle):
     assert torch.equal(o16, m16(x16, ei, ew, sm.lazy()))
 
 
+@pytest.mark.timeout(180)
+def test_cfconv_pipelined_one_tile_chunks_stress():
+    """Regression for a rare hang of the pipelined CFConv forward on chunks that hold a single 128-edge tile: the
+    end-of-stream arrival of the softplus warps could complete a second phase of the barrier the G2 warp was still
+    waiting on (a waiter two phases behind never wakes).  12 000 edges = 94 one-tile chunks; both CSR directions,
+    launched back to back many times through the C ABI."""
+    import ctypes as C
+    import gmp_b200
+    from gmp_b200._lib import SchnetFilter, call, ptr
+    n, deg = 300, 40
+    g = torch.Generator().manual_seed(n + deg)
+    E = n * deg
+    dst = torch.randint(0, n - n // 7, (E,), generator=g).sort().values
+    src = torch.randint(0, n, (E,), generator=g)
+    gr = gmp_b200.get_graph(torch.stack([src, dst]).cuda(), n)
+    torch.manual_seed(0)
+    blk = gmp_b200.InteractionBlock(128, 50, 128, 5.0).cuda()
+    sm = gmp_b200.GaussianSmearing(0.0, 5.0, 50).cuda()
+    w1, b1, w2, b2 = blk.mlp[0].weight, blk.mlp[0].bias, blk.mlp[2].weight, blk.mlp[2].bias
+    filt = SchnetFilter(ptr(w1), ptr(b1), ptr(w2), ptr(b2), 50, 128, 5.0, ptr(sm.offset), sm.coeff)
+    ew = torch.rand(E, generator=g).cuda() * 5.0
+    x1b = torch.randn(n, 128, device="cuda").to(torch.bfloat16)
+    head = torch.empty(gmp_b200._lib.lib().gmp_schnet_tc2_num_chunks(E), 128, device="cuda")
+    first = {}
+    for it in range(1500):
+        for name, csr in (("dst", gr.by_dst), ("src", gr.by_src)):
+            agg = torch.empty(n, 128, device="cuda")
+            call("gmp_schnet_cfconv_fwd_tc2", ptr(csr.rowptr), ptr(csr.col), csr.perm_ptr, ptr(csr.row_ids()), n, E, ptr(ew),
+                 ptr(x1b), C.byref(filt), ptr(agg), ptr(head))
+            if it % 250 == 0:
+                torch.cuda.synchronize()
+                assert torch.equal(agg, first.setdefault(name, agg))   # and bit-identical every time
+    torch.cuda.synchronize()
+
+
 @pytest.mark.parametrize("case", ["empty", "isolated", "shuffled_small_mul"])
 def test_tp_conv_bf16_tc_corner_cases(case):
     """tcgen05 tensor-product convolution on degenerate inputs: no edges at all, nodes without edges (rows that must
