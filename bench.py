@@ -175,20 +175,41 @@ def main_gpu(args):
     atoms, pos, batch = atoms_h.to(dev), pos_h.to(dev), batch_h.to(dev)
     ei = gmp_b200.radius_graph(pos, CFG["cutoff"], batch, max_num_neighbors=CFG["max_num_neighbors"])
     E, N = ei.shape[1], pos.shape[0]
-    b = Bag(atoms=atoms, pos=pos, edge_index=ei, batch=batch)
+    # num_graphs: the field PyG's Batch carries; with it the pooling read-out needs no batch.max() read-back (a host sync)
+    b = Bag(atoms=atoms, pos=pos, edge_index=ei, batch=batch, num_graphs=CFG["molecules"])
 
-    def allreduce_grads():
+    def allreduce_grads(grads=None):
         if world > 1:
-            flat = torch.cat([p.grad.reshape(-1) for p in params if p.grad is not None])
+            grads = [p.grad for p in params if p.grad is not None] if grads is None else grads
+            flat = torch.cat([g.reshape(-1) for g in grads])
             dist.all_reduce(flat)
             # (gradients stay in `flat`; an optimizer would consume them from here)
 
-    def step(batch_obj):
+    def step_eager(batch_obj):
         for p in params:
             p.grad = None
         out = model(batch_obj)
         out.sum().backward()
         allreduce_grads()
+        return out
+
+    # The step is ~270 launches for ~11 ms of device work and the Python / ATen / ctypes launch path needs about as long
+    # to issue them, so forward + backward are captured once into a CUDA graph (gmp_b200.GraphedStep) and replayed; the
+    # gradient all-reduce stays outside the graph.  --eager (or a failed capture) falls back to launch-by-launch.
+    graph_note = None
+    gs = None
+    if not args.eager:
+        try:
+            gs = gmp_b200.GraphedStep(model, b, warmup=max(3, args.warmup))
+        except Exception as ex:  # noqa: BLE001 -- report and measure eagerly rather than lose the run
+            graph_note = f"capture failed: {type(ex).__name__}: {str(ex)[:200]}"
+            torch.cuda.synchronize()
+
+    def step(batch_obj):
+        if gs is None or batch_obj is not b:
+            return step_eager(batch_obj)
+        out = gs.replay()
+        allreduce_grads(gs.grads)
         return out
 
     def barrier():
@@ -213,7 +234,7 @@ def main_gpu(args):
     e.record()
     barrier()
     ms = s.elapsed_time(e) / K
-    launches = (_lib.kernel_launches() - launches0) // K
+    launches = gs.kernels_per_replay if gs is not None else (_lib.kernel_launches() - launches0) // K
 
     # ---- e2e: host buffers -> public API -> host result, copies inside the timed region ------------------
     pin = lambda t: t.pin_memory()
@@ -221,10 +242,26 @@ def main_gpu(args):
     h2d = sum(t.numel() * t.element_size() for t in (atoms_p, pos_p, batch_p, ei_p))
     out_host = torch.empty(CFG["molecules"], 1).pin_memory()
 
+    host_batch = gmp_b200.Batch(atoms=atoms_p, pos=pos_p, batch=batch_p, edge_index=ei_p, num_graphs=CFG["molecules"])
+    gs2 = None
+    if gs is not None:
+        # static device buffers that every step overwrites from the pinned host batch; the captured graph contains the
+        # CSR sort of the freshly copied edge_index as well as forward + backward (nothing is reused between steps)
+        try:
+            static = host_batch.to(dev)
+            torch.cuda.synchronize()
+            gs2 = gmp_b200.GraphedStep(model, static, warmup=2, rebuild_graph=True)
+        except Exception as ex:  # noqa: BLE001
+            graph_note = f"e2e capture failed: {type(ex).__name__}: {str(ex)[:200]}"
+            torch.cuda.synchronize()
+
     def e2e_step():
-        bb = Bag(atoms=atoms_p.to(dev, non_blocking=True), pos=pos_p.to(dev, non_blocking=True),
-                 batch=batch_p.to(dev, non_blocking=True), edge_index=ei_p.to(dev, non_blocking=True))
-        out = step(bb)
+        if gs2 is not None:
+            gs2.load(host_batch)
+            out = gs2.replay()
+            allreduce_grads(gs2.grads)
+        else:
+            out = step_eager(host_batch.to(dev, non_blocking=True))
         out_host.copy_(out.detach(), non_blocking=True)
 
     for _ in range(W + 3):  # also lets the caching allocator reach its steady state for the per-step buffers
@@ -258,12 +295,12 @@ def main_gpu(args):
         for blk in model.interactions:
             blk.conv.precision = "fp32"
         for _ in range(2):
-            step(b)
+            step_eager(b)
         barrier()
         s3, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s3.record()
         for _ in range(3):
-            step(b)
+            step_eager(b)
         e3.record()
         barrier()
         ms3 = s3.elapsed_time(e3) / 3
@@ -282,7 +319,10 @@ def main_gpu(args):
                             "precision": args.precision,
                             "tolerance_vs_fp32_reference": 1e-2 if args.precision == "bf16" else 1e-5,
                             "node_side_gemms": "cuBLAS TF32 forward / dx; dW, db on tcgen05 (linear_wgrad_tc_kernel)" if args.precision == "bf16" else "cuBLAS fp32", "parallelism": f"graph-sharded x{world}",
-                            "l2": "per-step working set (x1/agg/g rows of 6 layers, >2 GB) exceeds the 126 MB L2"},
+                            "l2": "per-step working set (x1/agg/g rows of 6 layers, >2 GB) exceeds the 126 MB L2",
+                            "cuda_graph": (gs is not None) if graph_note is None else graph_note,
+                            "e2e_path": "pinned host batch -> static device buffers -> one CUDA graph (CSR sort + forward + "
+                                        "backward) -> host result" if gs2 is not None else "host batch -> model(batch) eagerly -> host result"},
                     roofline=roof, cpu_baseline=cpu, fp32_strict=strict,
                     e2e={"value": E_total * L / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                          "d2h_bytes_per_step": out_host.numel() * 4, "ms_per_step": ms_e2e},
@@ -364,6 +404,7 @@ if __name__ == "__main__":
     ap.add_argument("--precision", default="bf16", choices=["fp32", "bf16"],
                     help="bf16: filter-MLP GEMMs on tcgen05 with bf16 operands / fp32 accumulation (1e-2 vs the fp32 reference, "
                          "the tolerance BASELINE.json states for bf16 MLP inputs); fp32: strict FFMA path (1e-5)")
+    ap.add_argument("--eager", action="store_true", help="launch the step kernel by kernel instead of replaying a CUDA graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-strict", action="store_true", help="skip the secondary fp32-strict measurement")
     a = ap.parse_args()

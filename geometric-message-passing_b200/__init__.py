@@ -22,6 +22,8 @@ from .tfn import (BatchNorm, Gate, RadialEmbeddingBlock, SphericalHarmonics, Ten
                   TensorProductPlan, TFNModel, edge_geometry, first_node_pooling)
 from .mace import (Contraction, EquivariantLinear, EquivariantProductBasisBlock, MACEModel,  # noqa: F401
                    SymmetricContraction, reshape_irreps)
+from .data import Batch, DevicePrefetcher  # noqa: F401,E402
+from .graphs import GraphedStep  # noqa: F401,E402
 from . import distributed  # noqa: F401,E402
 from .distributed import PartitionedEGNN, SlabPartition, allreduce_gradients, halo_exchange, slab_partition  # noqa: F401,E402
 

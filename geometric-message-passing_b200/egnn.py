@@ -15,6 +15,7 @@ from torch import nn
 from torch.nn import Linear, ReLU, Sequential, SiLU
 from torch.nn import functional as F
 
+from .embed import embedding_lookup
 from . import _lib
 from ._lib import EgnnParams, GmpError, call, ptr
 from .graph import Graph, get_graph
@@ -183,14 +184,14 @@ class EGNNModel(nn.Module):
                                             torch.nn.Linear(emb_dim, out_dim))
 
     def forward(self, batch):
-        h = self.emb_in(batch.atoms)
+        h = embedding_lookup(self.emb_in, batch.atoms)
         pos = batch.pos
         for conv in self.convs:
             h_update, pos_update = conv(h, pos, batch.edge_index)
             h = h + h_update if self.residual else h_update
             pos = pos_update
         if not self.equivariant_pred:
-            out = self.pool(h, batch.batch)
+            out = self.pool(h, batch.batch, getattr(batch, "num_graphs", None))
         else:
-            out = self.pool(torch.cat([h, pos], dim=-1), batch.batch)
+            out = self.pool(torch.cat([h, pos], dim=-1), batch.batch, getattr(batch, "num_graphs", None))
         return self.pred(out)

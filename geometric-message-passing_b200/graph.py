@@ -65,6 +65,7 @@ def radius_graph(x: torch.Tensor, r: float, batch: Optional[torch.Tensor] = None
         if E:
             call("gmp_radius_graph_fill", ptr(x), ptr(gptr), ngraphs, n, float(r), max_num_neighbors, int(loop),
                  ptr(rowptr), ptr(ei[0]), ptr(ei[1]))
+        ei._gmp_dst_sorted = True   # dst-major, ascending: Graph skips the permutation of the by_dst view
         return ei
     assert ngraphs == 1, "the cell-list path handles a single example"
     import ctypes as C
@@ -86,6 +87,7 @@ def radius_graph(x: torch.Tensor, r: float, batch: Optional[torch.Tensor] = None
     if E:
         call("gmp_radius_cells_fill", ptr(x), n, float(r), cell, origin, cdims, ptr(cell_start), ptr(cell_nodes),
              max_num_neighbors, int(loop), ptr(rowptr), ptr(ei[0]), ptr(ei[1]))
+    ei._gmp_dst_sorted = True
     return ei
 
 
@@ -106,23 +108,30 @@ class CSR:
         """int32[E]: aggregation row of each sorted edge (cached)."""
         if getattr(self, "_row_ids", None) is None:
             deg = (self.rowptr[1:] - self.rowptr[:-1]).long()
-            self._row_ids = torch.repeat_interleave(
-                torch.arange(self.n, device=self.rowptr.device, dtype=torch.int32), deg).contiguous()
+            self._row_ids = torch.repeat_interleave(   # output_size: no read-back of deg.sum(), capturable in a CUDA graph
+                torch.arange(self.n, device=self.rowptr.device, dtype=torch.int32), deg, output_size=self.E).contiguous()
         return self._row_ids
 
 
-def build_csr(index: torch.Tensor, other: torch.Tensor, n: int) -> CSR:
-    """Stable counting sort of the edges by `index` (int64[E]); `other` is the opposite endpoint."""
+def build_csr(index: torch.Tensor, other: torch.Tensor, n: int, assume_sorted: Optional[bool] = None) -> CSR:
+    """Stable counting sort of the edges by `index` (int64[E]); `other` is the opposite endpoint.
+
+    assume_sorted=True: the caller guarantees `index` is non-decreasing (our own radius_graph output is dst-major):
+    no permutation is stored.  None: no guarantee and no questions asked of the device -- the permutation is always built
+    (the identity when the input happens to be sorted), because reading a sortedness flag back would stall the host once
+    per graph and step.  False: check on the device and read the flag back (the exact perm-is-None-iff-sorted contract)."""
     assert index.dtype == torch.int64 and other.dtype == torch.int64
     index, other = index.contiguous(), other.contiguous()
     E, dev = index.numel(), index.device
     counts = _i32(max(n, 1), dev)
     call("gmp_csr_count", ptr(index), E, n, ptr(counts))
     rowptr = exclusive_scan(counts[:n]).to(torch.int32)
-    flag = _i32(1, dev)
-    call("gmp_index_is_sorted", ptr(index), E, ptr(flag))
     col = _i32(E, dev)
-    if int(flag.item()) == 1:
+    if assume_sorted is False:
+        flag = _i32(1, dev)
+        call("gmp_index_is_sorted", ptr(index), E, ptr(flag))
+        assume_sorted = int(flag.item()) == 1
+    if assume_sorted:
         perm = None
     else:
         perm, tmp, cursor = _i32(E, dev), _i32(E, dev), _i32(max(n, 1), dev)
@@ -143,13 +152,15 @@ class Graph:
         self.edge_index = edge_index.contiguous()
         self.n = n
         self.E = edge_index.shape[1]
+        # radius_graph (ours, like torch_cluster's) emits edges grouped by destination in ascending order and says so
+        self._dst_sorted = bool(getattr(edge_index, "_gmp_dst_sorted", False))
         self._by_dst: Optional[CSR] = None
         self._by_src: Optional[CSR] = None
 
     @property
     def by_dst(self) -> CSR:
         if self._by_dst is None:
-            self._by_dst = build_csr(self.edge_index[1], self.edge_index[0], self.n)
+            self._by_dst = build_csr(self.edge_index[1], self.edge_index[0], self.n, True if self._dst_sorted else None)
         return self._by_dst
 
     @property

@@ -1,0 +1,80 @@
+"""Whole-step CUDA graphs ("use CUDA graphs to kill launch latency").
+
+One SchNet training step at BASELINE config 2 is ~270 kernel launches (81 of them ours) for ~11 ms of device work, and the
+Python + ATen + ctypes launch path needs about as long to issue them: the step is host-bound.  `GraphedStep` captures
+`out = model(batch); loss(out).backward()` once into a `torch.cuda.CUDAGraph` and replays it, so a step costs one launch
+on the host.  Everything on the path is capture-safe: the C-ABI entry points only enqueue kernels / memsets on the current
+stream, the CSR build asks the device nothing (graph.build_csr), pooling takes `batch.num_graphs`.
+
+Two modes:
+* resident batch: the CSR views are built (and cached) before capture; a replay recomputes forward + backward.
+* `rebuild_graph=True`: the batch tensors are static device buffers that `load(host_batch)` overwrites; the capture then
+  contains the CSR sort as well, so a replay does everything a fresh batch of the same shapes needs."""
+from __future__ import annotations
+
+from typing import Callable, Optional
+
+import torch
+
+from . import _lib
+from .data import Batch
+
+
+class GraphedStep:
+    def __init__(self, model: torch.nn.Module, batch, loss: Optional[Callable] = None, warmup: int = 3,
+                 rebuild_graph: bool = False):
+        assert all(t.is_cuda for t in _tensors(batch).values()), "GraphedStep needs a device-resident (static) batch"
+        self.model, self.batch = model, batch
+        self.loss = loss or (lambda out: out.sum())
+        self.params = [p for p in model.parameters() if p.requires_grad]
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):          # warm-up off the capture stream: lazy inits, cuBLAS workspaces, autotuning
+            for _ in range(max(1, warmup)):
+                self._eager()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        for p in self.params:
+            p.grad = None                      # the captured backward then allocates the gradients in the graph's pool
+        if rebuild_graph:                      # new version counter -> the CSR cache misses -> the sort is captured too
+            batch.edge_index.add_(0)
+        k0, c0 = _lib.kernel_launches(), _lib.launches
+        self.graph = torch.cuda.CUDAGraph()
+        # (the parameters' AccumulateGrad nodes were created by earlier eager steps on the default stream; autograd warns
+        # about the stream change.  The accumulation itself is captured -- tests/test_gpu_schnet.py checks the replayed
+        # gradients against eager ones for changing inputs.)
+        warn = getattr(torch.autograd.graph, "set_warn_on_accumulate_grad_stream_mismatch", None)
+        if warn is not None:
+            warn(False)
+        try:
+            with torch.cuda.graph(self.graph):
+                self.out = model(batch)
+                self.loss(self.out).backward()
+        finally:
+            if warn is not None:
+                warn(True)
+        self.kernels_per_replay = _lib.kernel_launches() - k0   # our kernels inside one replay (counted at capture)
+        self.calls_per_replay = _lib.launches - c0
+        self.grads = [p.grad for p in self.params]
+
+    def _eager(self):
+        for p in self.params:
+            p.grad = None
+        out = self.model(self.batch)
+        self.loss(out).backward()
+        return out
+
+    def load(self, host_batch) -> None:
+        """Overwrite the static batch with a host batch of the same shapes (pinned memory makes the copies asynchronous)."""
+        for k, dst in _tensors(self.batch).items():
+            src = getattr(host_batch, k)
+            assert src.shape == dst.shape and src.dtype == dst.dtype, f"GraphedStep.load: {k} changed shape or dtype"
+            dst.copy_(src, non_blocking=True)
+
+    def replay(self) -> torch.Tensor:
+        self.graph.replay()
+        return self.out
+
+
+def _tensors(batch):
+    return batch.tensors() if isinstance(batch, Batch) else {k: v for k, v in vars(batch).items() if torch.is_tensor(v)}

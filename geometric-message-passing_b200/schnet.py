@@ -16,6 +16,7 @@ import torch
 from torch import nn
 from torch.nn import Embedding, Linear, ModuleList, Sequential
 
+from .embed import embedding_lookup
 from . import _lib
 from ._lib import SchnetFilter, call, ptr
 from .graph import Graph, get_graph
@@ -271,13 +272,14 @@ class SchNetModel(nn.Module):
         self.lin2 = Linear(hidden_channels // 2, out_dim)
 
     def forward(self, batch):
-        h = self.embedding(batch.atoms)
+        h = embedding_lookup(self.embedding, batch.atoms)
         graph = get_graph(batch.edge_index, h.shape[0])
         edge_weight = edge_length(batch.pos, graph)
         edge_attr = self.distance_expansion.lazy()
         for interaction in self.interactions:
             h = h + interaction(h, batch.edge_index, edge_weight, edge_attr)
-        out = self.pool(h, batch.batch)
+        # PyG's Batch carries num_graphs; without it the pool has to read batch.max() back (one host sync per step)
+        out = self.pool(h, batch.batch, getattr(batch, "num_graphs", None))
         out = self.lin1(out)
         out = self.act(out)
         return self.lin2(out)

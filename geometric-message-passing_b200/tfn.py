@@ -17,6 +17,7 @@ import torch
 from torch import nn
 from torch.nn import functional as F
 
+from .embed import embedding_lookup
 from . import _lib
 from ._lib import GmpError, call, ptr
 from .graph import Graph, get_graph
@@ -550,12 +551,12 @@ class TFNModel(nn.Module):
             self.pred = torch.nn.Sequential(torch.nn.Linear(emb_dim, emb_dim), torch.nn.ReLU(), torch.nn.Linear(emb_dim, out_dim))
 
     def forward(self, batch):
-        h = self.emb_in(batch.atoms)
+        h = embedding_lookup(self.emb_in, batch.atoms)
         edge_sh, edge_feats = edge_geometry(batch.pos, batch.edge_index, self.max_ell, self.radial_embedding)
         for conv in self.convs:
             h_update = conv(h, batch.edge_index, edge_sh, edge_feats)
             h = h_update + F.pad(h, (0, h_update.shape[-1] - h.shape[-1])) if self.residual else h_update
-        out = self.pool(h, batch.batch)
+        out = self.pool(h, batch.batch, getattr(batch, "num_graphs", None))
         if not self.equivariant_pred:
             out = out[:, :self.emb_dim]
         return self.pred(out)

@@ -12,7 +12,7 @@ model = gmp_b200.SchNetModel(hidden_channels=CFG["hidden"], num_filters=CFG["fil
                              num_gaussians=CFG["gaussians"], cutoff=CFG["cutoff"], precision="bf16").to(dev)
 atoms, pos, batch = (t.to(dev) for t in bench.synth(CFG["molecules"], seed=0))
 ei = gmp_b200.radius_graph(pos, CFG["cutoff"], batch, max_num_neighbors=CFG["max_num_neighbors"])
-b = bench.Bag(atoms=atoms, pos=pos, edge_index=ei, batch=batch)
+b = bench.Bag(atoms=atoms, pos=pos, edge_index=ei, batch=batch, num_graphs=CFG["molecules"])
 for _ in range(int(sys.argv[1]) if len(sys.argv) > 1 else 3):
     for p in model.parameters():
         p.grad = None

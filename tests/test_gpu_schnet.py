@@ -122,3 +122,69 @@ def test_k0_gather_mul_segsum():
     call("gmp_gather_mul_segsum_f32", ptr(g.rowptr), ptr(g.col), g.perm_ptr, ptr(x), ptr(w), ptr(out), n, F)
     ref = torch.zeros(n, F, dtype=torch.float64).index_add_(0, ei[1].cpu(), (x[ei[0]] * w).double().cpu())
     assert rel_err(out, ref) <= 1e-6
+
+
+@pytest.mark.gpu
+def test_device_prefetcher_matches_direct_upload():
+    """gmp_b200.DevicePrefetcher (next batch uploaded on a side stream under the current batch's compute): same
+    batches, same order, same model outputs as a synchronous `.to(device)` per step."""
+    import gmp_b200
+    from tests.helpers import random_clouds
+    torch.manual_seed(0)
+    model = gmp_b200.SchNetModel(hidden_channels=128, num_filters=128, num_layers=2, num_gaussians=50, cutoff=5.0).cuda()
+    hosts = []
+    for seed in range(5):
+        d = random_clouds(6, 20, 8.0, 5.0, 100 + seed, max_nb=32)
+        atoms = torch.randint(1, 10, (d["pos"].shape[0],), generator=torch.Generator().manual_seed(seed))
+        hosts.append(gmp_b200.Batch(atoms=atoms, pos=d["pos"], batch=d["batch"], edge_index=d["edge_index"]).pin_memory())
+    with torch.no_grad():
+        direct = [model(h.to("cuda")).cpu() for h in hosts]
+        fetched = [model(b).cpu() for b in gmp_b200.DevicePrefetcher(hosts, "cuda")]
+    assert len(fetched) == len(direct)
+    for a, b in zip(fetched, direct):
+        assert torch.equal(a, b)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_graphed_step_matches_eager(precision):
+    """gmp_b200.GraphedStep: forward + backward captured into one CUDA graph.  A replay reproduces the eager outputs and
+    gradients bit for bit (same kernels, same order); in rebuild mode a host batch of the same shapes but different
+    contents (atoms, positions, shuffled edge order) is loaded into the static buffers and the replay -- which then
+    contains the CSR sort -- equals an eager step on that batch."""
+    import gmp_b200
+    torch.manual_seed(0)
+    model = gmp_b200.SchNetModel(hidden_channels=128, num_filters=128, num_layers=2, num_gaussians=50, cutoff=5.0,
+                                 precision=precision).cuda()
+    params = [p for p in model.parameters()]
+    d = random_clouds(6, 24, 8.0, 5.0, 11, max_nb=32)
+    n = d["pos"].shape[0]
+    gen = torch.Generator().manual_seed(3)
+
+    def eager(b):
+        for p in params:
+            p.grad = None
+        out = model(b)
+        out.sum().backward()
+        return out.detach().clone(), [p.grad.detach().clone() for p in params]
+
+    b1 = gmp_b200.Batch(atoms=torch.randint(1, 10, (n,), generator=gen), pos=d["pos"], batch=d["batch"],
+                        edge_index=d["edge_index"], num_graphs=6)
+    perm = torch.randperm(d["edge_index"].shape[1], generator=gen)
+    b2 = gmp_b200.Batch(atoms=torch.randint(1, 10, (n,), generator=gen), pos=d["pos"] + 0.05 * torch.randn(n, 3, generator=gen),
+                        batch=d["batch"], edge_index=d["edge_index"][:, perm].contiguous(), num_graphs=6)
+    out1, g1 = eager(b1.to("cuda"))
+    out2, g2 = eager(b2.to("cuda"))
+
+    gs = gmp_b200.GraphedStep(model, b1.to("cuda"), warmup=2)                       # resident batch
+    assert gs.kernels_per_replay > 0
+    for _ in range(2):
+        assert torch.equal(gs.replay(), out1)
+        assert all(torch.equal(a, b) for a, b in zip(gs.grads, g1))
+
+    gs = gmp_b200.GraphedStep(model, b1.to("cuda"), warmup=2, rebuild_graph=True)    # static buffers, CSR sort captured
+    for host, out_ref, g_ref in ((b2, out2, g2), (b1, out1, g1), (b2, out2, g2)):
+        gs.load(host.pin_memory())
+        out = gs.replay()
+        assert torch.equal(out, out_ref)
+        assert all(torch.equal(a, b) for a, b in zip(gs.grads, g_ref))

@@ -138,3 +138,13 @@ def test_tc_tables_reproduce_the_tensor_product(cin, cout):
     mine_dx = _emulate_tc_contract(plan.tc_bwd, cg, dst.numpy(), src.numpy(), cot.numpy(), sh.numpy(), T.numpy(), b2.numpy(),
                                    n, plan.irreps_in.dim)
     assert np.abs(mine_dx - dx.numpy()).max() <= 1e-5 * np.abs(dx.numpy()).max()
+
+
+def test_batch_bag_keeps_the_reference_field_names():
+    """gmp_b200.Batch: the attribute bag the models read (`atoms`, `pos`, `edge_index`, `batch`)."""
+    import gmp_b200
+    b = gmp_b200.Batch(atoms=torch.zeros(4, dtype=torch.long), pos=torch.randn(4, 3),
+                       edge_index=torch.tensor([[0, 1], [1, 0]]), batch=torch.zeros(4, dtype=torch.long), name="x")
+    c = b.to("cpu")
+    assert set(c.tensors()) == {"atoms", "pos", "edge_index", "batch"} and c.name == "x"
+    assert torch.equal(c.pos, b.pos) and c.edge_index.dtype == torch.long
