@@ -27,6 +27,20 @@ class GraphedStep:
         self.model, self.batch = model, batch
         self.loss = loss or (lambda out: out.sum())
         self.params = [p for p in model.parameters() if p.requires_grad]
+        # (the parameters' AccumulateGrad nodes may have been created by earlier eager steps on the default stream; autograd
+        # warns when the side / capture stream meets them.  The accumulation itself is captured -- tests/test_gpu_schnet.py
+        # checks the replayed gradients against eager ones for changing inputs.)
+        warn = getattr(torch.autograd.graph, "set_warn_on_accumulate_grad_stream_mismatch", None)
+        if warn is not None:
+            warn(False)
+        try:
+            self._capture(model, batch, warmup, rebuild_graph)
+        finally:
+            if warn is not None:
+                warn(True)
+        self.grads = [p.grad for p in self.params]
+
+    def _capture(self, model, batch, warmup, rebuild_graph):
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):          # warm-up off the capture stream: lazy inits, cuBLAS workspaces, autotuning
@@ -40,22 +54,11 @@ class GraphedStep:
             batch.edge_index.add_(0)
         k0, c0 = _lib.kernel_launches(), _lib.launches
         self.graph = torch.cuda.CUDAGraph()
-        # (the parameters' AccumulateGrad nodes were created by earlier eager steps on the default stream; autograd warns
-        # about the stream change.  The accumulation itself is captured -- tests/test_gpu_schnet.py checks the replayed
-        # gradients against eager ones for changing inputs.)
-        warn = getattr(torch.autograd.graph, "set_warn_on_accumulate_grad_stream_mismatch", None)
-        if warn is not None:
-            warn(False)
-        try:
-            with torch.cuda.graph(self.graph):
-                self.out = model(batch)
-                self.loss(self.out).backward()
-        finally:
-            if warn is not None:
-                warn(True)
+        with torch.cuda.graph(self.graph):
+            self.out = model(batch)
+            self.loss(self.out).backward()
         self.kernels_per_replay = _lib.kernel_launches() - k0   # our kernels inside one replay (counted at capture)
         self.calls_per_replay = _lib.launches - c0
-        self.grads = [p.grad for p in self.params]
 
     def _eager(self):
         for p in self.params:
