@@ -19,7 +19,7 @@ _lib = None
 launches = 0  # number of C-ABI compute calls issued
 _kernels = 0  # number of CUDA kernels those calls launched (bench.py's gpu_launches)
 # kernels launched per entry point (default 1); memsets are not counted
-_KERNELS_PER_CALL = {"gmp_exclusive_scan_i32": 3, "gmp_csr_fill": 2, "gmp_cells_build": 3, "gmp_tp_tc_contract": 2, "gmp_schnet_cfconv_fwd_tc2": 2}
+_KERNELS_PER_CALL = {"gmp_exclusive_scan_i32": 3, "gmp_csr_fill": 2, "gmp_cells_build": 3, "gmp_tp_tc_contract": 2, "gmp_schnet_cfconv_fwd_tc2": 2, "gmp_schnet_cfconv_fwd_tc2_keep": 2}
 
 
 def kernel_launches() -> int:
@@ -51,6 +51,7 @@ _SIGS = {
     "gmp_index_is_sorted": [P, I64, P, P],
     "gmp_segment_reduce_f32": [P, P, P, P, I64, I32, I32, P],
     "gmp_gather_mul_segsum_f32": [P, P, P, P, P, P, I64, I32, P],
+    "gmp_gather_mul_segsum_wbf16": [P, P, P, P, P, P, I64, I32, P],
     "gmp_gather_rows_f32": [P, P, P, I64, I32, P],
     "gmp_reduce_partials_f32": [P, I32, I64, P, P],
     "gmp_edge_length_fwd": [P, P, P, I64, P, P],
@@ -63,6 +64,7 @@ _SIGS = {
     "gmp_egnn_edge_fwd": [P, P, I64, I64, P, P, P, P, P, P, I32, P],
     "gmp_egnn_edge_bwd": [P, P, P, I64, I64, P, P, P, P, P, P, I32, P, P, P, I32, P],
     "gmp_schnet_cfconv_fwd_tc2": [P, P, P, P, I64, I64, P, P, P, P, P, P],
+    "gmp_schnet_cfconv_fwd_tc2_keep": [P, P, P, P, I64, I64, P, P, P, P, P, P, P],
     "gmp_schnet_cfconv_bwd_tc2": [P, P, P, P, I64, I64, P, P, P, P, P, I32, P],
     "gmp_linear_wgrad_tc": [P, P, I64, I32, I32, P, P],
     "gmp_egnn_tc_edge_fwd": [P, P, P, I64, I64, P, P, P, P, P, P, P],

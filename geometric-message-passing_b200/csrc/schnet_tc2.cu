@@ -41,6 +41,7 @@ struct Tc2Args {
     float* agg;                      // [n,128], zeroed
     float* head;                     // [gridDim.x,128], zeroed
     int* dbg;                        // debug builds (GMP_TC2_PROGRESS): host-mapped progress words, [gridDim.x][32 warps]
+    __nv_bfloat16* wout;             // optional [E,128]: the filter value W(e) * C(e) of every edge, caller's edge order
 };
 
 // shared-memory map (bytes from the 1024-aligned base)
@@ -51,8 +52,8 @@ constexpr int o2A2 = o2A1 + 16384;          // 32 KB
 constexpr int o2X = o2A2 + 32768;           // 3 stages x 32 KB: gathered rows -> msg
 constexpr int o2S = o2X + kS2Stages * 32768;  // 16 KB (rows of 128 B, first 64 B used: 32 segments)
 constexpr int o2Vec = o2S + 16384;          // b1[128] b2[128] goff[64]
-constexpr int o2Meta = o2Vec + 320 * 4;     // 3 x { C[128] f32, d[128] f32, seg[128] i32, seg_row[32] i32, cnt, nseg, head0, pad }
-constexpr int kMetaBytes = (128 + 128 + 128 + 32 + 4) * 4;
+constexpr int o2Meta = o2Vec + 320 * 4;     // 6 x { C[128] f32, d[128] f32, seg[128] i32, eid[128] i32, seg_row[32] i32, cnt, nseg, head0, pad }
+constexpr int kMetaBytes = (128 + 128 + 128 + 128 + 32 + 4) * 4;
 constexpr int o2Tmp = o2Meta + kS2MetaStages * kMetaBytes;   // meta scratch per group: wcount[4], first-overflow[4]; then the end-of-stream tile numbers
 constexpr int o2Bar = o2Tmp + 128;
 // barriers
@@ -86,6 +87,7 @@ struct Meta {
     float C[128];
     float d[128];     // edge length (1e18 for the padding slots: every Gaussian underflows to 0)
     int seg[128];
+    int eid[128];     // caller's edge id of the slot (where the optional filter output goes)
     int seg_row[32];
     int cnt, nseg, head0, pad;
 };
@@ -234,6 +236,7 @@ __global__ void __launch_bounds__(kS2Threads, 1) schnet_fwd_tc2_kernel(Tc2Args a
                 M.C[e] = C;
                 M.d[e] = d;
                 M.seg[e] = valid ? seg : -1;
+                M.eid[e] = cur.eid;
                 if (flag && seg < kS2MaxSeg && valid) M.seg_row[seg] = rid;
                 if (e == cnt - 1) { M.cnt = cnt; M.nseg = seg + 1; }
                 if (e == 0) M.head0 = head0;
@@ -386,6 +389,9 @@ __global__ void __launch_bounds__(kS2Threads, 1) schnet_fwd_tc2_kernel(Tc2Args a
             tc_fence_after();
             const float C = M.C[e];
             uint8_t* xs = sm + o2X + st * 32768;
+            // optional: keep the filter value of this edge (bf16, 128 B per thread) for the backward pass, which then gets
+            // dL/dx1 from a plain gather-multiply-reduce instead of running this whole kernel again on the transposed CSR
+            uint4* wrow = (a.wout != nullptr && e < cnt) ? reinterpret_cast<uint4*>(a.wout + (int64_t)M.eid[e] * 128 + 64 * g) : nullptr;
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
                 float v[32];
@@ -395,15 +401,16 @@ __global__ void __launch_bounds__(kS2Threads, 1) schnet_fwd_tc2_kernel(Tc2Args a
                     uint4* px = reinterpret_cast<uint4*>(xs + g * 16384 + sw128_chunk_off(e, j * 4 + q));
                     const uint4 xr = *px;
                     const uint32_t w[4] = {xr.x, xr.y, xr.z, xr.w};
-                    uint32_t o[4];
+                    uint32_t o[4], fo[4];
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {
                         const int c0 = 64 * g + 32 * j + 8 * q + 2 * u;
-                        const float m0 = (v[8 * q + 2 * u] + b2s[c0]) * C * __uint_as_float(w[u] << 16);
-                        const float m1 = (v[8 * q + 2 * u + 1] + b2s[c0 + 1]) * C * __uint_as_float(w[u] & 0xffff0000u);
-                        o[u] = pack_bf16(m0, m1);   // C = 0 and zero rows for the padding slots
+                        const float f0 = (v[8 * q + 2 * u] + b2s[c0]) * C, f1 = (v[8 * q + 2 * u + 1] + b2s[c0 + 1]) * C;
+                        fo[u] = pack_bf16(f0, f1);
+                        o[u] = pack_bf16(f0 * __uint_as_float(w[u] << 16), f1 * __uint_as_float(w[u] & 0xffff0000u));   // C = 0 and zero rows for the padding slots
                     }
                     *px = make_uint4(o[0], o[1], o[2], o[3]);
+                    if (wrow) wrow[j * 4 + q] = make_uint4(fo[0], fo[1], fo[2], fo[3]);
                 }
             }
             tc_fence_before();
@@ -875,9 +882,9 @@ int32_t gmp_schnet_tc2_num_chunks(int64_t num_edges) {
     return (int32_t)(nt < num_sms() ? (nt < 1 ? 1 : nt) : num_sms());
 }
 
-int gmp_schnet_cfconv_fwd_tc2(const int32_t* rowptr, const int32_t* col, const int32_t* perm, const int32_t* rowid, int64_t n,
-                              int64_t num_edges, const float* edge_weight, const void* x1_bf16, const gmp_schnet_filter* f, float* agg,
-                              float* head, gmp_stream_t stream) {
+int gmp_schnet_cfconv_fwd_tc2_keep(const int32_t* rowptr, const int32_t* col, const int32_t* perm, const int32_t* rowid, int64_t n,
+                                   int64_t num_edges, const float* edge_weight, const void* x1_bf16, const gmp_schnet_filter* f,
+                                   float* agg, float* head, void* filter_out_bf16, gmp_stream_t stream) {
     GMP_REQUIRE(rowptr && f && agg && head, "schnet_cfconv_fwd_tc2: NULL pointer");
     GMP_REQUIRE(num_edges == 0 || (col && rowid && edge_weight && x1_bf16), "schnet_cfconv_fwd_tc2: NULL edge/feature pointer");
     GMP_REQUIRE(f->num_filters == 128 && f->num_gaussians >= 1 && f->num_gaussians <= 64 && f->gauss_offset,
@@ -890,7 +897,7 @@ int gmp_schnet_cfconv_fwd_tc2(const int32_t* rowptr, const int32_t* col, const i
     Tc2Args a;
     a.rowptr = rowptr; a.col = col; a.perm = perm; a.rowid = rowid; a.n = n; a.E = num_edges; a.ew = edge_weight;
     a.x1 = (const __nv_bfloat16*)x1_bf16; a.w1 = f->w1; a.b1 = f->b1; a.w2 = f->w2; a.b2 = f->b2; a.goff = f->gauss_offset;
-    a.G = f->num_gaussians; a.cutoff = f->cutoff; a.gcoeff = f->gauss_coeff; a.agg = agg; a.head = head;
+    a.G = f->num_gaussians; a.cutoff = f->cutoff; a.gcoeff = f->gauss_coeff; a.agg = agg; a.head = head; a.wout = (__nv_bfloat16*)filter_out_bf16;
 #ifdef GMP_TC2_PROGRESS
     a.dbg = g_tc2_dbg;
 #else
@@ -907,6 +914,12 @@ int gmp_schnet_cfconv_fwd_tc2(const int32_t* rowptr, const int32_t* col, const i
     return rc;
 }
 
+int gmp_schnet_cfconv_fwd_tc2(const int32_t* rowptr, const int32_t* col, const int32_t* perm, const int32_t* rowid, int64_t n,
+                              int64_t num_edges, const float* edge_weight, const void* x1_bf16, const gmp_schnet_filter* f, float* agg,
+                              float* head, gmp_stream_t stream) {
+    return gmp_schnet_cfconv_fwd_tc2_keep(rowptr, col, perm, rowid, n, num_edges, edge_weight, x1_bf16, f, agg, head, nullptr, stream);
+}
+
 int gmp_schnet_cfconv_bwd_tc2(const int32_t* rowptr, const int32_t* col, const int32_t* perm, const int32_t* rowid, int64_t n,
                               int64_t num_edges, const float* edge_weight, const void* x1_bf16, const gmp_schnet_filter* f,
                               const float* g_agg, float* wgrad_parts, int32_t nparts, gmp_stream_t stream) {
@@ -919,7 +932,7 @@ int gmp_schnet_cfconv_bwd_tc2(const int32_t* rowptr, const int32_t* col, const i
     Tc2Args& a = b.f;
     a.rowptr = rowptr; a.col = col; a.perm = perm; a.rowid = rowid; a.n = n; a.E = num_edges; a.ew = edge_weight;
     a.x1 = (const __nv_bfloat16*)x1_bf16; a.w1 = f->w1; a.b1 = f->b1; a.w2 = f->w2; a.b2 = f->b2; a.goff = f->gauss_offset;
-    a.G = f->num_gaussians; a.cutoff = f->cutoff; a.gcoeff = f->gauss_coeff; a.agg = nullptr; a.head = nullptr;
+    a.G = f->num_gaussians; a.cutoff = f->cutoff; a.gcoeff = f->gauss_coeff; a.agg = nullptr; a.head = nullptr; a.wout = nullptr;
     a.dbg = nullptr;
     b.g_agg = g_agg; b.parts = wgrad_parts;
     GMP_CUDA(cudaFuncSetAttribute(schnet_bwd_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTc2BwdSmem));

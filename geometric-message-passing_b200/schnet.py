@@ -86,16 +86,23 @@ def edge_length(pos: torch.Tensor, graph: Graph) -> torch.Tensor:
     return _EdgeLength.apply(pos, graph)
 
 
-def _cfconv_forward(csr, graph, edge_weight, edge_attr, x1, filt, w1, precision):
+def _tc2_ok(precision, edge_attr, F_, G) -> bool:
+    return precision == _lib.BF16_TC and edge_attr is None and F_ == 128 and G <= 64
+
+
+def _cfconv_forward(csr, graph, edge_weight, edge_attr, x1, filt, w1, precision, keep=None, x1_bf16=None):
     """agg[r] = sum_{e in CSR row r} x1[col_e] * W_e.  bf16 mode with the lazily expanded basis and 128 filters: the
-    pipelined three-MMA kernel (csrc/schnet_tc2.cu); otherwise the fp32 / first tensor-core kernels."""
+    pipelined three-MMA kernel (csrc/schnet_tc2.cu); otherwise the fp32 / first tensor-core kernels.
+    keep: optional bf16 [E,128] that receives every edge's filter value (caller's edge order) for the backward pass."""
     F_, G = w1.shape
     agg = torch.empty(graph.n, F_, dtype=x1.dtype, device=x1.device)
-    if precision == _lib.BF16_TC and edge_attr is None and F_ == 128 and G <= 64:
+    if _tc2_ok(precision, edge_attr, F_, G):
         head = torch.empty(int(_lib.lib().gmp_schnet_tc2_num_chunks(graph.E)), 128, dtype=x1.dtype, device=x1.device)
-        call("gmp_schnet_cfconv_fwd_tc2", ptr(csr.rowptr), ptr(csr.col), csr.perm_ptr, ptr(csr.row_ids()), graph.n, graph.E,
-             ptr(edge_weight), ptr(x1.to(torch.bfloat16)), C.byref(filt), ptr(agg), ptr(head))
+        x1_bf16 = x1.to(torch.bfloat16) if x1_bf16 is None else x1_bf16
+        call("gmp_schnet_cfconv_fwd_tc2_keep", ptr(csr.rowptr), ptr(csr.col), csr.perm_ptr, ptr(csr.row_ids()), graph.n, graph.E,
+             ptr(edge_weight), ptr(x1_bf16), C.byref(filt), ptr(agg), ptr(head), ptr(keep))
     else:
+        assert keep is None
         call("gmp_schnet_cfconv_fwd", ptr(csr.rowptr), ptr(csr.col), csr.perm_ptr, graph.n, graph.E, ptr(edge_weight),
              ptr(edge_attr), ptr(x1), C.byref(filt), ptr(agg), precision)
     return agg
@@ -110,7 +117,14 @@ class _CFConvFn(torch.autograd.Function):
         filt = SchnetFilter(ptr(w1), ptr(b1), ptr(w2), ptr(b2), w1.shape[1], w1.shape[0], float(cutoff),
                             ptr(offset), float(coeff))
         csr = graph.by_dst
-        agg = _cfconv_forward(csr, graph, edge_weight, edge_attr, x1, filt, w1, precision)
+        # Training through the pipelined kernel: keep the per-edge filter values (bf16, 256 B per edge) and the bf16 copy of
+        # x1.  The backward pass then gets dL/dx1 from a gather-multiply-reduce over them instead of re-running the filter
+        # MLP on the transposed CSR -- the kernel is bound by instruction issue, not by HBM, so the extra traffic is free.
+        tc2 = _tc2_ok(precision, edge_attr, w1.shape[0], w1.shape[1])
+        ctx.x1_bf16 = x1.to(torch.bfloat16) if tc2 else None
+        ctx.keep = (torch.empty(graph.E, 128, dtype=torch.bfloat16, device=x1.device)
+                    if (tc2 and ctx.needs_input_grad[0] and graph.E > 0) else None)
+        agg = _cfconv_forward(csr, graph, edge_weight, edge_attr, x1, filt, w1, precision, ctx.keep, ctx.x1_bf16)
         ctx.save_for_backward(x1, edge_weight, edge_attr if edge_attr is not None else x1.new_empty(0), w1, b1, w2, b2, offset)
         ctx.graph, ctx.meta, ctx.has_attr = graph, (float(cutoff), float(coeff), precision), edge_attr is not None
         return agg
@@ -127,9 +141,14 @@ class _CFConvFn(torch.autograd.Function):
         need = ctx.needs_input_grad
         dx1 = None
         if need[0]:
-            # d agg / d x1 is the same fused op over the transposed (src-sorted) CSR with g in place of x1
             t = graph.by_src
-            dx1 = _cfconv_forward(t, graph, ew, ea, g, filt, w1, precision)
+            if ctx.keep is not None:
+                # dx1[s] = sum_{e: src_e = s} W_e * g[dst_e] with the kept filter values (indexed by the caller's edge id)
+                dx1 = torch.empty(graph.n, F, dtype=g.dtype, device=g.device)
+                call("gmp_gather_mul_segsum_wbf16", ptr(t.rowptr), ptr(t.col), t.perm_ptr, ptr(g), ptr(ctx.keep), ptr(dx1), graph.n, F)
+            else:
+                # d agg / d x1 is the same fused op over the transposed (src-sorted) CSR with g in place of x1
+                dx1 = _cfconv_forward(t, graph, ew, ea, g, filt, w1, precision)
         csr = graph.by_dst
         lib = _lib.lib()
         nparts, plen = lib.gmp_schnet_bwd_num_parts(graph.E), lib.gmp_schnet_bwd_part_len(G, F)
@@ -138,7 +157,7 @@ class _CFConvFn(torch.autograd.Function):
         d_ea = torch.zeros_like(ea) if (need[2] and ea is not None) else None
         if (precision == _lib.BF16_TC and ea is None and d_ew is None and d_ea is None and F == 128 and G <= 63 and graph.E > 0):
             call("gmp_schnet_cfconv_bwd_tc2", ptr(csr.rowptr), ptr(csr.col), csr.perm_ptr, ptr(csr.row_ids()), graph.n, graph.E,
-                 ptr(ew), ptr(x1.to(torch.bfloat16)), C.byref(filt), ptr(g), ptr(parts), nparts)
+                 ptr(ew), ptr(ctx.x1_bf16 if ctx.x1_bf16 is not None else x1.to(torch.bfloat16)), C.byref(filt), ptr(g), ptr(parts), nparts)
         else:
             call("gmp_schnet_cfconv_bwd", ptr(csr.rowptr), ptr(csr.col), csr.perm_ptr, graph.n, graph.E, ptr(ew), ptr(ea),
                  ptr(x1), C.byref(filt), ptr(g), ptr(parts), ptr(d_ew), ptr(d_ea), precision)

@@ -117,6 +117,11 @@ int gmp_segment_sum_bf16_f32(const int32_t* rowptr, const int32_t* perm, const v
 int gmp_gather_mul_segsum_f32(const int32_t* rowptr, const int32_t* col, const int32_t* perm, const float* x,
                               const float* w, float* out, int64_t n, int32_t F, gmp_stream_t stream);
 
+/* K0 with the per-edge factor stored as bf16 rows (fp32 gather rows, fp32 accumulation and output; F = 128): dL/dx1 of the
+ * CFConv from the filter values the forward pass kept (gmp_schnet_cfconv_fwd_tc2_keep). */
+int gmp_gather_mul_segsum_wbf16(const int32_t* rowptr, const int32_t* col, const int32_t* perm, const float* x,
+                                const void* w_bf16, float* out, int64_t n, int32_t F, gmp_stream_t stream);
+
 /* out[k,:] = x[idx[k],:]  (backward of the reductions above; PyG propagate's index_select). */
 int gmp_gather_rows_f32(const int32_t* idx, const float* x, float* out, int64_t num_rows, int32_t F,
                         gmp_stream_t stream);
@@ -201,6 +206,15 @@ int32_t gmp_schnet_tc2_num_chunks(int64_t num_edges);
 int gmp_schnet_cfconv_fwd_tc2(const int32_t* rowptr, const int32_t* col, const int32_t* perm, const int32_t* rowid,
                               int64_t n, int64_t num_edges, const float* edge_weight, const void* x1_bf16,
                               const gmp_schnet_filter* filter /* host */, float* agg, float* head, gmp_stream_t stream);
+
+/* Same, and additionally stores the filter value of every edge, W(e) * C(e) as 128 bf16, at row (perm ? perm[k] : k) of
+ * filter_out_bf16 [E,128] (the caller's edge order; may be NULL = plain forward).  Training uses it so that the backward pass
+ * does not have to run the filter MLP again for dL/dx1 (PyG keeps the same [E,F] tensor alive for autograd,
+ * CFConv.forward called at models/schnet.py:72). */
+int gmp_schnet_cfconv_fwd_tc2_keep(const int32_t* rowptr, const int32_t* col, const int32_t* perm, const int32_t* rowid,
+                                   int64_t n, int64_t num_edges, const float* edge_weight, const void* x1_bf16,
+                                   const gmp_schnet_filter* filter /* host */, float* agg, float* head,
+                                   void* filter_out_bf16, gmp_stream_t stream);
 
 /* Pipelined GMP_BF16_TC variant of the filter-side backward (weight gradients of the filter MLP only; same partial layout
  * as gmp_schnet_cfconv_bwd: [dW1 128x64 | db1 | dW2 128x128 | db2] per CTA, `nparts` CTAs, each owning a contiguous range
