@@ -51,7 +51,7 @@ _SIGS = {
     "gmp_index_is_sorted": [P, I64, P, P],
     "gmp_segment_reduce_f32": [P, P, P, P, I64, I32, I32, P],
     "gmp_gather_mul_segsum_f32": [P, P, P, P, P, P, I64, I32, P],
-    "gmp_gather_mul_segsum_wbf16": [P, P, P, P, P, P, I64, I32, P],
+    "gmp_gather_mul_segsum_wbf16": [P, P, P, P, I32, P, P, I64, I32, P],
     "gmp_gather_rows_f32": [P, P, P, I64, I32, P],
     "gmp_reduce_partials_f32": [P, I32, I64, P, P],
     "gmp_edge_length_fwd": [P, P, P, I64, P, P],

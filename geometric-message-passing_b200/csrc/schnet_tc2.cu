@@ -395,22 +395,27 @@ __global__ void __launch_bounds__(kS2Threads, 1) schnet_fwd_tc2_kernel(Tc2Args a
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
                 float v[32];
+                uint32_t fo[8];
                 tmem_ld32(tmD2 + lane_base + 64 * g + 32 * j, v);
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     uint4* px = reinterpret_cast<uint4*>(xs + g * 16384 + sw128_chunk_off(e, j * 4 + q));
                     const uint4 xr = *px;
                     const uint32_t w[4] = {xr.x, xr.y, xr.z, xr.w};
-                    uint32_t o[4], fo[4];
+                    uint32_t o[4];
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {
                         const int c0 = 64 * g + 32 * j + 8 * q + 2 * u;
                         const float f0 = (v[8 * q + 2 * u] + b2s[c0]) * C, f1 = (v[8 * q + 2 * u + 1] + b2s[c0 + 1]) * C;
-                        fo[u] = pack_bf16(f0, f1);
+                        fo[4 * (q & 1) + u] = pack_bf16(f0, f1);
                         o[u] = pack_bf16(f0 * __uint_as_float(w[u] << 16), f1 * __uint_as_float(w[u] & 0xffff0000u));   // C = 0 and zero rows for the padding slots
                     }
                     *px = make_uint4(o[0], o[1], o[2], o[3]);
-                    if (wrow) wrow[j * 4 + q] = make_uint4(fo[0], fo[1], fo[2], fo[3]);
+                    // 32 B per lane and instruction (a whole sector): every lane of the warp writes a different row, so the
+                    // cost of these stores is the number of instructions, not the bytes
+                    if ((q & 1) && wrow)
+                        asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(wrow + j * 4 + q - 1), "r"(fo[0]), "r"(fo[1]),
+                                     "r"(fo[2]), "r"(fo[3]), "r"(fo[4]), "r"(fo[5]), "r"(fo[6]), "r"(fo[7]) : "memory");
                 }
             }
             tc_fence_before();

@@ -9,34 +9,45 @@ namespace gmp {
 // out[r,:] = sum_k x[col[k],:] * w[perm ? perm[k] : k, :] with the per-edge factor w stored as bf16 rows (F = 128): one warp per
 // row, one lane per four columns, eight edges in flight.  This is dL/dx1 of the CFConv once the forward pass has kept its
 // filter values (gmp_schnet_cfconv_fwd_tc2_keep): HBM sees 256 B per edge, the gathered fp32 rows come from L2.
+template <bool XBF16>
 __global__ void __launch_bounds__(256)
 segsum_wbf16_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, const int32_t* __restrict__ perm,
-                    const float* __restrict__ x, const __nv_bfloat16* __restrict__ w, float* __restrict__ out, int64_t n) {
+                    const void* __restrict__ xv_, const __nv_bfloat16* __restrict__ w, float* __restrict__ out, int64_t n) {
     const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (row >= n) return;
     const int b = __ldg(rowptr + row), e = __ldg(rowptr + row + 1);
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int k0 = b; k0 < e; k0 += 8) {
-        float4 xv[8];
+        float4 xv[XBF16 ? 1 : 8];
+        uint2 xb[XBF16 ? 8 : 1];
         uint2 wv[8];
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
             const int k = k0 + u;
-            xv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (XBF16) xb[u % (XBF16 ? 8 : 1)] = make_uint2(0u, 0u); else xv[u % (XBF16 ? 1 : 8)] = make_float4(0.f, 0.f, 0.f, 0.f);
             wv[u] = make_uint2(0u, 0u);
             if (k < e) {
                 const int64_t srow = __ldg(col + k), wrow = perm ? (int64_t)__ldg(perm + k) : (int64_t)k;
-                xv[u] = ldg4(x + srow * 128 + lane * 4);
+                if (XBF16) xb[u % (XBF16 ? 8 : 1)] = __ldg(reinterpret_cast<const uint2*>(static_cast<const __nv_bfloat16*>(xv_) + srow * 128 + lane * 4));
+                else xv[u % (XBF16 ? 1 : 8)] = ldg4(static_cast<const float*>(xv_) + srow * 128 + lane * 4);
                 wv[u] = __ldg(reinterpret_cast<const uint2*>(w + wrow * 128 + lane * 4));
             }
         }
 #pragma unroll
         for (int u = 0; u < 8; ++u) {   // fixed order of the additions: deterministic
-            acc.x = fmaf(xv[u].x, __uint_as_float(wv[u].x << 16), acc.x);
-            acc.y = fmaf(xv[u].y, __uint_as_float(wv[u].x & 0xffff0000u), acc.y);
-            acc.z = fmaf(xv[u].z, __uint_as_float(wv[u].y << 16), acc.z);
-            acc.w = fmaf(xv[u].w, __uint_as_float(wv[u].y & 0xffff0000u), acc.w);
+            float4 xx;
+            if (XBF16) {
+                const uint2 q = xb[u % (XBF16 ? 8 : 1)];
+                xx = make_float4(__uint_as_float(q.x << 16), __uint_as_float(q.x & 0xffff0000u), __uint_as_float(q.y << 16),
+                                 __uint_as_float(q.y & 0xffff0000u));
+            } else {
+                xx = xv[u % (XBF16 ? 1 : 8)];
+            }
+            acc.x = fmaf(xx.x, __uint_as_float(wv[u].x << 16), acc.x);
+            acc.y = fmaf(xx.y, __uint_as_float(wv[u].x & 0xffff0000u), acc.y);
+            acc.z = fmaf(xx.z, __uint_as_float(wv[u].y << 16), acc.z);
+            acc.w = fmaf(xx.w, __uint_as_float(wv[u].y & 0xffff0000u), acc.w);
         }
     }
     *reinterpret_cast<float4*>(out + row * 128 + lane * 4) = acc;
@@ -274,12 +285,14 @@ int gmp_gather_mul_segsum_f32(const int32_t* rowptr, const int32_t* col, const i
     return check_launch("gather_mul_segsum");
 }
 
-int gmp_gather_mul_segsum_wbf16(const int32_t* rowptr, const int32_t* col, const int32_t* perm, const float* x,
+int gmp_gather_mul_segsum_wbf16(const int32_t* rowptr, const int32_t* col, const int32_t* perm, const void* x, int32_t x_is_bf16,
                                 const void* w_bf16, float* out, int64_t n, int32_t F, gmp_stream_t stream) {
     GMP_REQUIRE(rowptr && col && x && w_bf16 && out && n >= 0, "gather_mul_segsum_wbf16: bad arguments");
     GMP_REQUIRE(F == 128, "gather_mul_segsum_wbf16: built for 128 columns (got %d)", F);
     if (n == 0) return GMP_OK;
-    segsum_wbf16_kernel<<<(unsigned)ceil_div(n * 32, 256), 256, 0, stream>>>(rowptr, col, perm, x, (const __nv_bfloat16*)w_bf16, out, n);
+    const unsigned grid = (unsigned)ceil_div(n * 32, 256);
+    if (x_is_bf16) segsum_wbf16_kernel<true><<<grid, 256, 0, stream>>>(rowptr, col, perm, x, (const __nv_bfloat16*)w_bf16, out, n);
+    else segsum_wbf16_kernel<false><<<grid, 256, 0, stream>>>(rowptr, col, perm, x, (const __nv_bfloat16*)w_bf16, out, n);
     return check_launch("segsum_wbf16_kernel");
 }
 

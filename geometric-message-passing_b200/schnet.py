@@ -145,7 +145,9 @@ class _CFConvFn(torch.autograd.Function):
             if ctx.keep is not None:
                 # dx1[s] = sum_{e: src_e = s} W_e * g[dst_e] with the kept filter values (indexed by the caller's edge id)
                 dx1 = torch.empty(graph.n, F, dtype=g.dtype, device=g.device)
-                call("gmp_gather_mul_segsum_wbf16", ptr(t.rowptr), ptr(t.col), t.perm_ptr, ptr(g), ptr(ctx.keep), ptr(dx1), graph.n, F)
+                # (g gathered as bf16 rows, as the transposed pass of the fused kernel did: halves the L2 -> SM traffic)
+                call("gmp_gather_mul_segsum_wbf16", ptr(t.rowptr), ptr(t.col), t.perm_ptr, ptr(g.to(torch.bfloat16)), 1, ptr(ctx.keep),
+                     ptr(dx1), graph.n, F)
             else:
                 # d agg / d x1 is the same fused op over the transposed (src-sorted) CSR with g in place of x1
                 dx1 = _cfconv_forward(t, graph, ew, ea, g, filt, w1, precision)

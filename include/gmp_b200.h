@@ -117,10 +117,10 @@ int gmp_segment_sum_bf16_f32(const int32_t* rowptr, const int32_t* perm, const v
 int gmp_gather_mul_segsum_f32(const int32_t* rowptr, const int32_t* col, const int32_t* perm, const float* x,
                               const float* w, float* out, int64_t n, int32_t F, gmp_stream_t stream);
 
-/* K0 with the per-edge factor stored as bf16 rows (fp32 gather rows, fp32 accumulation and output; F = 128): dL/dx1 of the
- * CFConv from the filter values the forward pass kept (gmp_schnet_cfconv_fwd_tc2_keep). */
-int gmp_gather_mul_segsum_wbf16(const int32_t* rowptr, const int32_t* col, const int32_t* perm, const float* x,
-                                const void* w_bf16, float* out, int64_t n, int32_t F, gmp_stream_t stream);
+/* K0 with the per-edge factor stored as bf16 rows (gathered rows x fp32 or, with x_is_bf16, bf16; fp32 accumulation and output;
+ * F = 128): dL/dx1 of the CFConv from the filter values the forward pass kept (gmp_schnet_cfconv_fwd_tc2_keep). */
+int gmp_gather_mul_segsum_wbf16(const int32_t* rowptr, const int32_t* col, const int32_t* perm, const void* x,
+                                int32_t x_is_bf16, const void* w_bf16, float* out, int64_t n, int32_t F, gmp_stream_t stream);
 
 /* out[k,:] = x[idx[k],:]  (backward of the reductions above; PyG propagate's index_select). */
 int gmp_gather_rows_f32(const int32_t* idx, const float* x, float* out, int64_t num_rows, int32_t F,
