@@ -12,13 +12,16 @@ namespace gmp {
 
 using namespace tc;
 
-constexpr int kLT = 128;        // rows per tile
+constexpr int kLT = 64;         // rows per tile (the K extent of one MMA group); small tiles so that several CTAs share an SM and
+                                // one CTA's load -> convert -> barrier bubble is covered by the others' loads
 constexpr int kLThreads = 256;
-constexpr int kLImg = 32768;    // one operand image: 2 slabs of [128 rows][64 columns] bf16
+constexpr int kLCtasPerSm = 3;  // 64 KB of shared memory and 128 tensor-memory columns each
+constexpr int kLSlab = kLT * 128;   // one slab: [kLT rows][64 columns] bf16
+constexpr int kLImg = 2 * kLSlab;   // one operand image: 2 slabs
 constexpr int oLBar = 4 * kLImg;  // 2 buffers x (g image, x image), then 2 mbarriers + tmem pointer
 constexpr int kLinSmem = oLBar + 64 + 1024;
 
-__global__ void __launch_bounds__(kLThreads, 1)
+__global__ void __launch_bounds__(kLThreads, kLCtasPerSm)
 linear_wgrad_tc_kernel(const float* __restrict__ g, const float* __restrict__ x, int64_t n, int in_dim, float* __restrict__ parts) {
     extern __shared__ __align__(16) uint8_t smraw[];
     uint8_t* sm = smraw + ((1024u - (smem_u32(smraw) & 1023u)) & 1023u);
@@ -51,7 +54,7 @@ linear_wgrad_tc_kernel(const float* __restrict__ g, const float* __restrict__ x,
         uint8_t* xi = gi + kLImg;
         const int64_t row0 = tile * kLT;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
+        for (int i = 0; i < kLT / 16; ++i) {
             const int r = r0 + 16 * i;
             const int64_t row = row0 + r;
             float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
@@ -61,7 +64,7 @@ linear_wgrad_tc_kernel(const float* __restrict__ g, const float* __restrict__ x,
             }
             bsum[0] += a.x; bsum[1] += a.y; bsum[2] += a.z; bsum[3] += a.w;
             bsum[4] += b.x; bsum[5] += b.y; bsum[6] += b.z; bsum[7] += b.w;
-            *reinterpret_cast<uint4*>(gi + (ch >> 3) * 16384 + sw128_chunk_off(r, ch & 7)) =
+            *reinterpret_cast<uint4*>(gi + (ch >> 3) * kLSlab + sw128_chunk_off(r, ch & 7)) =
                 make_uint4(pack_bf16(a.x, a.y), pack_bf16(a.z, a.w), pack_bf16(b.x, b.y), pack_bf16(b.z, b.w));
             if (ch < xch) {
                 float4 c = make_float4(0.f, 0.f, 0.f, 0.f), d = c;
@@ -69,7 +72,7 @@ linear_wgrad_tc_kernel(const float* __restrict__ g, const float* __restrict__ x,
                     c = ldg4(x + row * in_dim + ch * 8);
                     d = ldg4(x + row * in_dim + ch * 8 + 4);
                 }
-                *reinterpret_cast<uint4*>(xi + (ch >> 3) * 16384 + sw128_chunk_off(r, ch & 7)) =
+                *reinterpret_cast<uint4*>(xi + (ch >> 3) * kLSlab + sw128_chunk_off(r, ch & 7)) =
                     make_uint4(pack_bf16(c.x, c.y), pack_bf16(c.z, c.w), pack_bf16(d.x, d.y), pack_bf16(d.z, d.w));
             }
         }
@@ -79,7 +82,7 @@ linear_wgrad_tc_kernel(const float* __restrict__ g, const float* __restrict__ x,
         if (warp == 0) {
             tc_fence_after();
             if (elect_one()) {
-                umma_tile_mn(tm, smem_u32(gi), 16384, smem_u32(xi), 16384, kLT, idesc, it > 0);
+                umma_tile_mn(tm, smem_u32(gi), kLSlab, smem_u32(xi), kLSlab, kLT, idesc, it > 0);
                 umma_commit(&bars[buf]);
             }
             __syncwarp();
@@ -126,7 +129,8 @@ extern "C" {
 
 int32_t gmp_linear_wgrad_num_parts(int64_t n) {
     const int64_t nt = ceil_div(n, kLT);
-    return (int32_t)(nt < num_sms() ? (nt < 1 ? 1 : nt) : num_sms());
+    const int64_t cap = 2 * (int64_t)num_sms();   // two partials per SM: more would only lengthen the reduction
+    return (int32_t)(nt < cap ? (nt < 1 ? 1 : nt) : cap);
 }
 
 int gmp_linear_wgrad_tc(const float* g, const float* x, int64_t n, int32_t out_dim, int32_t in_dim, float* parts, gmp_stream_t stream) {

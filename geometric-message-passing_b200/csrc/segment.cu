@@ -135,12 +135,33 @@ __global__ void gather_rows_scalar_kernel(const int32_t* __restrict__ idx, const
     out[t] = x[(int64_t)idx[r] * F + (t - r * F)];
 }
 
-__global__ void reduce_partials_kernel(const float* __restrict__ part, int nparts, int64_t len, float* __restrict__ out) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= len) return;
+// out[i] = sum_p part[p][i]: 32 outputs x 8 groups of partials per block (the outputs are few -- one weight matrix -- and the
+// partials many, so the partial index is split over threads too); every group sums its contiguous range of partials in order,
+// the eight group sums are added in order: one fixed association, deterministic.
+__global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __restrict__ part, int nparts, int64_t len, float* __restrict__ out) {
+    __shared__ float red[8][32];
+    const int ix = threadIdx.x & 31, gy = threadIdx.x >> 5;
+    const int64_t i = (int64_t)blockIdx.x * 32 + ix;
+    const int p0 = (int)(((int64_t)nparts * gy) / 8), p1 = (int)(((int64_t)nparts * (gy + 1)) / 8);
     float acc = 0.f;
-    for (int p = 0; p < nparts; ++p) acc += part[(int64_t)p * len + i];  // fixed order: deterministic
-    out[i] = acc;
+    if (i < len) {
+        int p = p0;
+        for (; p + 4 <= p1; p += 4) {
+            float v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) v[u] = __ldcg(part + (int64_t)(p + u) * len + i);
+            acc += (v[0] + v[1]) + (v[2] + v[3]);
+        }
+        for (; p < p1; ++p) acc += __ldcg(part + (int64_t)p * len + i);
+    }
+    red[gy][ix] = acc;
+    __syncthreads();
+    if (gy == 0 && i < len) {
+        float s = red[0][ix];
+#pragma unroll
+        for (int g = 1; g < 8; ++g) s += red[g][ix];
+        out[i] = s;
+    }
 }
 
 __global__ void edge_length_kernel(const float* __restrict__ pos, const int64_t* __restrict__ src,
@@ -307,7 +328,7 @@ int gmp_gather_rows_f32(const int32_t* idx, const float* x, float* out, int64_t 
 int gmp_reduce_partials_f32(const float* part, int32_t nparts, int64_t len, float* out, gmp_stream_t stream) {
     GMP_REQUIRE(part && out && nparts >= 1 && len >= 0, "reduce_partials: bad arguments");
     if (len == 0) return GMP_OK;
-    reduce_partials_kernel<<<(unsigned)ceil_div(len, 256), 256, 0, stream>>>(part, nparts, len, out);
+    reduce_partials_kernel<<<(unsigned)ceil_div(len, 32), 256, 0, stream>>>(part, nparts, len, out);
     return check_launch("reduce_partials");
 }
 
