@@ -31,31 +31,58 @@ class Batch:
 class DevicePrefetcher:
     """Iterate over host batches (pinned memory for truly asynchronous copies), yielding device batches.  The upload of the
     next batch is issued on a side stream before the current one is handed out, so it overlaps whatever the caller
-    launches for the current batch; the consumer stream waits on the upload's event, and the tensors are registered with
-    it so the caching allocator does not recycle them early."""
+    launches for the current batch; the consumer stream waits on the upload's event.
 
-    def __init__(self, batches: Iterable, device: torch.device):
+    static=False: every batch gets fresh device tensors (registered with the consumer stream so that the caching
+    allocator does not recycle them early); shapes may differ from batch to batch.
+    static=True: two persistent sets of staging buffers, allocated for the shapes of the first batch and reused in turn (no
+    allocator traffic at all; a batch of another shape raises).  A yielded batch stays valid until the next-but-one is
+    requested -- which is what a consumer that copies it into its own static inputs (GraphedStep.load) needs."""
+
+    def __init__(self, batches: Iterable, device: torch.device, static: bool = False):
         self.batches = batches
         self.device = torch.device(device)
         self.stream = torch.cuda.Stream(device=self.device)
+        self.static = static
+        self._stage = [None, None]
+        self._free = [None, None]     # recorded on the consumer stream when it is done with that staging set
 
-    def _upload(self, host):
+    def _upload(self, host, slot):
         if host is None:
             return None
         with torch.cuda.stream(self.stream):
-            dev = host.to(self.device, non_blocking=True)
+            if self.static:
+                if self._stage[slot] is None:
+                    self._stage[slot] = host.to(self.device, non_blocking=True)
+                else:
+                    if self._free[slot] is not None:
+                        self.stream.wait_event(self._free[slot])
+                    for k, dst in self._stage[slot].tensors().items():
+                        src = getattr(host, k)
+                        if src.shape != dst.shape or src.dtype != dst.dtype:
+                            raise ValueError(f"DevicePrefetcher(static=True): {k} changed shape or dtype")
+                        dst.copy_(src, non_blocking=True)
+                dev = self._stage[slot]
+            else:
+                dev = host.to(self.device, non_blocking=True)
             ev = torch.cuda.Event()
             ev.record(self.stream)
         return dev, ev
 
     def __iter__(self) -> Iterator:
         it = iter(self.batches)
-        nxt = self._upload(next(it, None))
+        slot = 0
+        nxt = self._upload(next(it, None), slot)
         while nxt is not None:
             dev, ev = nxt
             cur = torch.cuda.current_stream(self.device)
             cur.wait_event(ev)
-            for t in dev.tensors().values():
-                t.record_stream(cur)
-            nxt = self._upload(next(it, None))   # in flight while the caller works on `dev`
+            if not self.static:
+                for t in dev.tensors().values():
+                    t.record_stream(cur)
+            nxt = self._upload(next(it, None), slot ^ 1)   # in flight while the caller works on `dev`
             yield dev
+            if self.static:   # whatever the consumer enqueued for `dev` precedes this event
+                self._free[slot] = torch.cuda.Event()
+                self._free[slot].record(torch.cuda.current_stream(self.device))
+            slot ^= 1

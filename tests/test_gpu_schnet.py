@@ -188,3 +188,11 @@ def test_graphed_step_matches_eager(precision):
         out = gs.replay()
         assert torch.equal(out, out_ref)
         assert all(torch.equal(a, b) for a, b in zip(gs.grads, g_ref))
+    # the same through the double-buffered uploader (two persistent staging sets, upload of batch i+1 under step i)
+    seq = [(b1, out1, g1), (b2, out2, g2), (b2, out2, g2), (b1, out1, g1), (b2, out2, g2)]
+    hosts = [h.pin_memory() for h, _, _ in seq]
+    for staged, (_, out_ref, g_ref) in zip(gmp_b200.DevicePrefetcher(hosts, "cuda", static=True), seq):
+        gs.load(staged)
+        out = gs.replay()
+        assert torch.equal(out, out_ref)
+        assert all(torch.equal(a, b) for a, b in zip(gs.grads, g_ref))
