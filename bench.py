@@ -340,6 +340,9 @@ def main_gpu(args):
         dist.destroy_process_group()
 
 
+TRAFFIC_FWD_KEEP = 124.33e6 + 477.71e6   # dram read + write of one launch (ncu, profiles/r01_ncu_hw_schnet_fwd_tc2_keep.csv)
+
+
 def dominant_kernel_roofline(model, b, E, N, dev, args):
     """Time the fused CFConv forward kernel (the kernel launched twice per layer per step: messages and
     dL/dx1) alone: CUDA events around each launch on torch's current stream.  Algorithmic bytes per
@@ -369,6 +372,7 @@ def dominant_kernel_roofline(model, b, E, N, dev, args):
     x1b = x1.to(torch.bfloat16)
     head = torch.empty(lib.gmp_schnet_tc2_num_chunks(E), F, device=dev)
     rowid = csr.row_ids()
+    keep = torch.empty(E, F, dtype=torch.bfloat16, device=dev)   # training keeps the per-edge filter values for the backward
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     times = []
     for it in range(3 + 10):
@@ -376,8 +380,8 @@ def dominant_kernel_roofline(model, b, E, N, dev, args):
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s.record()
         if prec == 1:   # the entry point the bf16 model path calls (zeroes agg, runs the pipelined kernel and the boundary fix-up)
-            call("gmp_schnet_cfconv_fwd_tc2", ptr(csr.rowptr), ptr(csr.col), csr.perm_ptr, ptr(rowid), N, E, ptr(ew), ptr(x1b),
-                 C.byref(filt), ptr(agg), ptr(head))
+            call("gmp_schnet_cfconv_fwd_tc2_keep", ptr(csr.rowptr), ptr(csr.col), csr.perm_ptr, ptr(rowid), N, E, ptr(ew), ptr(x1b),
+                 C.byref(filt), ptr(agg), ptr(head), ptr(keep))
         else:
             call("gmp_schnet_cfconv_fwd", ptr(csr.rowptr), ptr(csr.col), csr.perm_ptr, N, E, ptr(ew), None, ptr(x1),
                  C.byref(filt), ptr(agg), prec)
@@ -390,17 +394,20 @@ def dominant_kernel_roofline(model, b, E, N, dev, args):
     achieved = alg / (ms * 1e-3) / 1e9
     flops = E * (2 * 64 * F + 2 * F * F + 2 * F)  # padded-G GEMM1 + GEMM2 + message product
     if prec == 1:
-        kname = "schnet_fwd_tc2_kernel (tcgen05, bf16, pipelined; time includes the agg memset and the boundary fix-up) via gmp_schnet_cfconv_fwd_tc2"
+        kname = ("schnet_fwd_tc2_kernel (tcgen05, bf16, pipelined; the training variant that also stores the per-edge filter values; "
+                 "time includes the agg memset and the boundary fix-up) via gmp_schnet_cfconv_fwd_tc2_keep")
         note = (f"{flops / (ms * 1e-3) / 1e12:.1f} TFLOP/s on the filter-MLP GEMMs (bf16 tcgen05); algorithmic bytes are SURVEY 8d's "
-                "fp32 figure -- the kernel itself gathers x1 as bf16 rows (256 B/edge) and x1 (34 MB) is L2-resident; per ncu the "
-                "kernel is issue-bound (42 % issue slots busy, ALU 24 / XU 21 / FMA 21 / LSU 16 %, tensor 12 %), not HBM-bound")
+                "fp32 figure -- the kernel itself gathers x1 as bf16 rows (256 B/edge, L2-resident) and, in training, writes 256 B/edge of "
+                "filter values that are not algorithmic bytes (without them: 0.397 ms, 38.9 %); per PC sampling the kernel is bound "
+                "by instruction issue through the MIO / XU queues (tensor pipe 12 %), not by HBM (profiles/r01f_summary.md)")
     else:
         kname = "schnet_fwd_kernel<128> (fp32 FFMA) via gmp_schnet_cfconv_fwd"
         note = f"{flops / (ms * 1e-3) / 1e12:.1f} TFLOP/s on the filter-MLP GEMMs (fp32 FFMA)"
     return {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
             # dram__bytes_read.sum + dram__bytes_write.sum of schnet_fwd_tc2_kernel, one launch, ncu hardware-counter pass
-            # (profiles/r01_ncu_hw_schnet_fwd_tc2.csv: 124.3 + 28.6 MB; the bf16 x1 rows are L2-resident)
-            "traffic": 152.8e6 if prec == 1 else None, "peak_source": which, "ms_per_launch": ms, "algorithmic_bytes": alg, "note": note}
+            # (profiles/r01_ncu_hw_schnet_fwd_tc2_keep.csv; without the kept filter values 124.3 + 28.6 MB,
+            # profiles/r01_ncu_hw_schnet_fwd_tc2.csv)
+            "traffic": TRAFFIC_FWD_KEEP if prec == 1 else None, "peak_source": which, "ms_per_launch": ms, "algorithmic_bytes": alg, "note": note}
 
 
 if __name__ == "__main__":

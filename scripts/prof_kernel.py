@@ -1,5 +1,5 @@
 """Run one fused kernel standalone at the BASELINE config-2 size (for ncu captures and quick timing).
-usage: python scripts/prof_kernel.py schnet_fwd|schnet_fwd2|schnet_bwd [fp32|bf16] [reps]"""
+usage: python scripts/prof_kernel.py schnet_fwd|schnet_fwd2|schnet_fwd2k|schnet_bwd|schnet_bwd2 [fp32|bf16] [reps]"""
 import ctypes as C
 import os
 import sys
@@ -35,13 +35,17 @@ parts = torch.empty(lib.gmp_schnet_bwd_num_parts(E), lib.gmp_schnet_bwd_part_len
 x1b = x1.to(torch.bfloat16)
 head = torch.empty(lib.gmp_schnet_tc2_num_chunks(E), F, device=dev)
 rowid = csr.row_ids()
+keep = torch.empty(E, F, dtype=torch.bfloat16, device=dev)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 times = []
 for it in range(reps + 2):
     flush.zero_()
     s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     s.record()
-    if which == "schnet_fwd2":
+    if which == "schnet_fwd2k":   # the training variant: also stores the per-edge filter values
+        call("gmp_schnet_cfconv_fwd_tc2_keep", ptr(csr.rowptr), ptr(csr.col), csr.perm_ptr, ptr(rowid), N, E, ptr(ew), ptr(x1b),
+             C.byref(filt), ptr(agg), ptr(head), ptr(keep))
+    elif which == "schnet_fwd2":
         call("gmp_schnet_cfconv_fwd_tc2", ptr(csr.rowptr), ptr(csr.col), csr.perm_ptr, ptr(rowid), N, E, ptr(ew), ptr(x1b),
              C.byref(filt), ptr(agg), ptr(head))
     elif which == "schnet_bwd2":
