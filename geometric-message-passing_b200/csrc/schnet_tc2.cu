@@ -242,15 +242,21 @@ __global__ void __launch_bounds__(kS2Threads, 1) schnet_fwd_tc2_kernel(Tc2Args a
                 if (e == 0) M.head0 = head0;
                 mbar_arrive(&bars[B_MF + ms]);   // meta block published: epilogue 1 expands the basis from d
             }
-            // gather x1[src] (bf16): this half's K slab = 8 chunks of 16 B, into the swizzled row image
-            uint8_t* xs = sm + o2X + st * 32768 + mh * 16384;
-            if (valid) {
-                const __nv_bfloat16* row = a.x1 + (int64_t)src * 128 + mh * 64;
+            // gather x1[src] (bf16 rows of 256 B) into the swizzled row image, half a warp per row: one copy instruction then
+            // touches 4 cache lines instead of 32 (a lane-per-row gather costs the load/store unit one cycle per line, and this
+            // kernel is short of exactly those).  Meta half mh takes rows [16 mh, 16 mh + 16) of its warp's 32 edge slots.
+            {
+                uint8_t* xs = sm + o2X + st * 32768;
+                const unsigned vmask = __ballot_sync(0xffffffffu, valid);
+                const int cchunk = lane & 15, sub = lane >> 4;
 #pragma unroll
-                for (int ch = 0; ch < 8; ++ch) __pipeline_memcpy_async(xs + sw128_chunk_off(e, ch), row + ch * 8, 16);
-            } else {
-#pragma unroll
-                for (int ch = 0; ch < 8; ++ch) *reinterpret_cast<uint4*>(xs + sw128_chunk_off(e, ch)) = make_uint4(0u, 0u, 0u, 0u);
+                for (int i = 0; i < 8; ++i) {
+                    const int rl = mh * 16 + 2 * i + sub;                     // row within the warp's 32 slots
+                    const int srow = __shfl_sync(0xffffffffu, src, rl);
+                    uint8_t* dst = xs + (cchunk >> 3) * 16384 + sw128_chunk_off(mw * 32 + rl, cchunk & 7);
+                    if ((vmask >> rl) & 1u) __pipeline_memcpy_async(dst, a.x1 + (int64_t)srow * 128 + cchunk * 8, 16);
+                    else *reinterpret_cast<uint4*>(dst) = make_uint4(0u, 0u, 0u, 0u);
+                }
             }
             cp_async_arrive(&bars[B_XF + st]);   // fires when this thread's copies have landed
             mbar_arrive(&bars[B_XF + st]);       // releases the meta block and the zero rows (plain stores)
@@ -664,16 +670,18 @@ __global__ void __launch_bounds__(896, 1) schnet_bwd_tc2_kernel(Tc2BwdArgs b) { 
             mbar_wait(&bars[C_DONE + p], par ^ 1u);   // G4 of tile tc-2 done: every buffer of stage p is free
             metaC(p)[e] = C;
             metaRow(p)[e] = grow;
-            uint8_t* xs = sm + o3X + p * 32768;
-            if (valid) {
-                const __nv_bfloat16* row = a.x1 + (int64_t)src * 128;
+            {   // half a warp per gathered row (see the forward kernel): 4 cache lines per copy instruction instead of 32
+                uint8_t* xs = sm + o3X + p * 32768;
+                const unsigned vmask = __ballot_sync(0xffffffffu, valid);
+                const int cchunk = lane & 15, sub = lane >> 4;
 #pragma unroll
-                for (int ch = 0; ch < 16; ++ch)
-                    __pipeline_memcpy_async(xs + (ch >> 3) * 16384 + sw128_chunk_off(e, ch & 7), row + ch * 8, 16);
-            } else {
-#pragma unroll
-                for (int ch = 0; ch < 16; ++ch)
-                    *reinterpret_cast<uint4*>(xs + (ch >> 3) * 16384 + sw128_chunk_off(e, ch & 7)) = make_uint4(0u, 0u, 0u, 0u);
+                for (int i = 0; i < 16; ++i) {
+                    const int rl = 2 * i + sub;
+                    const int srow = __shfl_sync(0xffffffffu, src, rl);
+                    uint8_t* dst = xs + (cchunk >> 3) * 16384 + sw128_chunk_off(warp * 32 + rl, cchunk & 7);
+                    if ((vmask >> rl) & 1u) __pipeline_memcpy_async(dst, a.x1 + (int64_t)srow * 128 + cchunk * 8, 16);
+                    else *reinterpret_cast<uint4*>(dst) = make_uint4(0u, 0u, 0u, 0u);
+                }
             }
             cp_async_arrive(&bars[C_XF + p]);
             mbar_arrive(&bars[C_XF + p]);
