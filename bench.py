@@ -398,8 +398,9 @@ def dominant_kernel_roofline(model, b, E, N, dev, args):
                  "time includes the agg memset and the boundary fix-up) via gmp_schnet_cfconv_fwd_tc2_keep")
         note = (f"{flops / (ms * 1e-3) / 1e12:.1f} TFLOP/s on the filter-MLP GEMMs (bf16 tcgen05); algorithmic bytes are SURVEY 8d's "
                 "fp32 figure -- the kernel itself gathers x1 as bf16 rows (256 B/edge, L2-resident) and, in training, writes 256 B/edge of "
-                "filter values that are not algorithmic bytes (without them: 0.397 ms, 38.9 %); per PC sampling the kernel is bound "
-                "by instruction issue through the MIO / XU queues (tensor pipe 12 %), not by HBM (profiles/r01f_summary.md)")
+                "filter values that are not algorithmic bytes (the plain forward: 0.339 ms, 45.5 %); the kernel is bound by load/store-unit "
+                "and MIO cycles (lane-per-row accesses, one ex2 per softplus / Gaussian), tensor pipe 12 %, not by HBM "
+                "(profiles/r01f_summary.md)")
     else:
         kname = "schnet_fwd_kernel<128> (fp32 FFMA) via gmp_schnet_cfconv_fwd"
         note = f"{flops / (ms * 1e-3) / 1e12:.1f} TFLOP/s on the filter-MLP GEMMs (fp32 FFMA)"
