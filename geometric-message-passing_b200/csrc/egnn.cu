@@ -18,7 +18,9 @@
 namespace gmp {
 
 constexpr int kET = 32;                 // edges per tile
-constexpr int kERange = 1024;           // edges per work range
+constexpr int kERangeMax = 1024;        // edges per work range on large graphs; small graphs get shorter ranges so that
+                                        // the work still spreads over the SMs (the reference's own workloads are a few
+                                        // hundred edges: one 1024-edge range would run them on a single SM)
 constexpr int kRPT = 2;                 // rows per thread in the tile GEMMs (16 * 2 = 32 rows)
 
 struct EgnnArgs {
@@ -26,7 +28,7 @@ struct EgnnArgs {
     int64_t n, E;
     const float *P, *Q, *pos;
     const float *wd, *g1, *be1, *w1, *b1, *g2, *be2, *w2, *b2, *g3, *be3, *w3, *b3;
-    int act, aggr_mean, nranges;
+    int act, aggr_mean, nranges, erange;
     float eps;
 };
 
@@ -228,8 +230,8 @@ __global__ void __launch_bounds__(256, 1) egnn_fwd_kernel(EgnnArgs a, float* __r
     egnn_load_weights<F>(sm, a);
     __syncthreads();
     for (int rg = blockIdx.x; rg < a.nranges; rg += gridDim.x) {
-        const int r0 = lower_bound_row(a.rowptr, (int)a.n, (int64_t)rg * kERange);
-        const int r1 = (rg + 1 == a.nranges) ? (int)a.n : lower_bound_row(a.rowptr, (int)a.n, (int64_t)(rg + 1) * kERange);
+        const int r0 = lower_bound_row(a.rowptr, (int)a.n, (int64_t)rg * a.erange);
+        const int r1 = (rg + 1 == a.nranges) ? (int)a.n : lower_bound_row(a.rowptr, (int)a.n, (int64_t)(rg + 1) * a.erange);
         if (r0 >= r1) continue;
         const int64_t eb = __ldg(a.rowptr + r0), ee = __ldg(a.rowptr + r1);
         int cur = r0;
@@ -316,8 +318,8 @@ egnn_bwd_kernel(EgnnArgs a, const float* __restrict__ g_msg, const float* __rest
     for (int c = 0; c < CPL; ++c) dg1[c] = dbe1[c] = dg2[c] = dbe2[c] = dg3[c] = dbe3[c] = db1[c] = db2[c] = dw3[c] = dwd[c] = 0.f;
 
     for (int rg = blockIdx.x; rg < a.nranges; rg += gridDim.x) {
-        const int r0 = lower_bound_row(a.rowptr, (int)a.n, (int64_t)rg * kERange);
-        const int r1 = (rg + 1 == a.nranges) ? (int)a.n : lower_bound_row(a.rowptr, (int)a.n, (int64_t)(rg + 1) * kERange);
+        const int r0 = lower_bound_row(a.rowptr, (int)a.n, (int64_t)rg * a.erange);
+        const int r1 = (rg + 1 == a.nranges) ? (int)a.n : lower_bound_row(a.rowptr, (int)a.n, (int64_t)(rg + 1) * a.erange);
         if (r0 >= r1) continue;
         const int64_t eb = __ldg(a.rowptr + r0), ee = __ldg(a.rowptr + r1);
         int cur = r0;
@@ -525,6 +527,13 @@ static int egnn_check(const gmp_egnn_edge_params* p, int64_t n, int64_t E) {
     return GMP_OK;
 }
 
+// edges per work range: aim at two ranges per SM, between one 32-edge tile and kERangeMax, in whole tiles
+static int egnn_range(int64_t E) {
+    int64_t r = ceil_div(E > 0 ? E : 1, 2 * (int64_t)num_sms());
+    r = ceil_div(r, 32) * 32;
+    return (int)(r < 32 ? 32 : (r > kERangeMax ? kERangeMax : r));
+}
+
 static EgnnArgs egnn_args(const int32_t* rowptr, const int32_t* col, const int32_t* deg_rowptr, int64_t n, int64_t E,
                           const float* P, const float* Q, const float* pos, const gmp_egnn_edge_params* p) {
     EgnnArgs a;
@@ -532,7 +541,8 @@ static EgnnArgs egnn_args(const int32_t* rowptr, const int32_t* col, const int32
     a.wd = p->wd; a.g1 = p->ln1_g; a.be1 = p->ln1_b; a.w1 = p->w1; a.b1 = p->b1; a.g2 = p->ln2_g; a.be2 = p->ln2_b;
     a.w2 = p->w2; a.b2 = p->b2; a.g3 = p->ln3_g; a.be3 = p->ln3_b; a.w3 = p->w3; a.b3 = p->b3;
     a.act = p->act; a.aggr_mean = p->aggr_mean; a.eps = p->ln_eps;
-    a.nranges = (int)(E > 0 ? ceil_div(E, kERange) : 1);
+    a.erange = egnn_range(E);
+    a.nranges = (int)(E > 0 ? ceil_div(E, a.erange) : 1);
     return a;
 }
 
@@ -561,7 +571,7 @@ using namespace gmp;
 extern "C" {
 
 int32_t gmp_egnn_bwd_num_parts(int64_t num_edges) {
-    const int64_t nr = num_edges > 0 ? ceil_div(num_edges, kERange) : 1;
+    const int64_t nr = num_edges > 0 ? ceil_div(num_edges, egnn_range(num_edges)) : 1;
     return (int32_t)(nr < num_sms() ? nr : num_sms());
 }
 

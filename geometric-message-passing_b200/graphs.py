@@ -9,7 +9,10 @@ stream, the CSR build asks the device nothing (graph.build_csr), pooling takes `
 Two modes:
 * resident batch: the CSR views are built (and cached) before capture; a replay recomputes forward + backward.
 * `rebuild_graph=True`: the batch tensors are static device buffers that `load(host_batch)` overwrites; the capture then
-  contains the CSR sort as well, so a replay does everything a fresh batch of the same shapes needs."""
+  contains the CSR sort as well, so a replay does everything a fresh batch of the same shapes needs.
+
+Outputs of earlier eager steps must not be alive when a GraphedStep is built (their autograd graph pins the parameters'
+gradient accumulators to the default stream, which invalidates the capture)."""
 from __future__ import annotations
 
 from typing import Callable, Optional
@@ -54,9 +57,15 @@ class GraphedStep:
             batch.edge_index.add_(0)
         k0, c0 = _lib.kernel_launches(), _lib.launches
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
-            self.out = model(batch)
-            self.loss(self.out).backward()
+        try:
+            with torch.cuda.graph(self.graph):
+                self.out = model(batch)
+                self.loss(self.out).backward()
+        except RuntimeError as ex:
+            raise RuntimeError(
+                "GraphedStep: the capture was invalidated.  The usual cause is a live autograd graph from an earlier eager step "
+                "(e.g. its output tensor is still referenced): it pins the parameters' AccumulateGrad nodes to the default stream, "
+                "which cannot take part in a stream capture.  Drop those references (del out) before building a GraphedStep.") from ex
         self.kernels_per_replay = _lib.kernel_launches() - k0   # our kernels inside one replay (counted at capture)
         self.calls_per_replay = _lib.launches - c0
 

@@ -132,3 +132,26 @@ def test_egnn_equivariance_not_worse_than_oracle():
             worst_mine = max(worst_mine, rel_err(a2, a1), rel_err(q2.cpu(), q1.cpu() @ Rm.T + t))
     assert worst_mine <= max(2 * worst_ref, 2e-6), (worst_mine, worst_ref)
     assert worst_mine < 1e-4
+
+
+def test_graphed_step_config1_kchains():
+    """BASELINE config 1 replayed as one CUDA graph (gmp_b200.GraphedStep): outputs and gradients bit-identical to the
+    eager step, and still equal to the golden fixture."""
+    import gmp_b200
+    fx = load_golden("egnn_model_kchains")
+    m = load_params(gmp_b200.EGNNModel(**fx["ctor"]), fx["state"]).cuda()
+    i = fx["inputs"]
+    b = gmp_b200.Batch(atoms=i["atoms"].cuda(), pos=i["pos"].cuda(), edge_index=i["edge_index"].cuda(), batch=i["batch"].cuda(),
+                       num_graphs=int(i["batch"].max()) + 1)
+    params = [p for p in m.parameters()]
+    for p in params:
+        p.grad = None
+    out = m(b)
+    out.sum().backward()
+    out_e, g_e = out.detach().clone(), [p.grad.detach().clone() for p in params]
+    del out   # a live autograd graph from an eager step would pin the gradient accumulators to the default stream
+    gs = gmp_b200.GraphedStep(m, b)
+    for _ in range(2):
+        assert torch.equal(gs.replay(), out_e)
+        assert all(torch.equal(a, c) for a, c in zip(gs.grads, g_e))
+    assert rel_err(gs.replay().cpu(), fx["outputs"][0]) <= 5 * TOL
