@@ -308,9 +308,13 @@ int gmp_gather_mul_segsum_f32(const int32_t* rowptr, const int32_t* col, const i
 
 int gmp_gather_mul_segsum_wbf16(const int32_t* rowptr, const int32_t* col, const int32_t* perm, const void* x, int32_t x_is_bf16,
                                 const void* w_bf16, float* out, int64_t n, int32_t F, gmp_stream_t stream) {
-    GMP_REQUIRE(rowptr && col && x && w_bf16 && out && n >= 0, "gather_mul_segsum_wbf16: bad arguments");
+    GMP_REQUIRE(rowptr && x && out && n >= 0, "gather_mul_segsum_wbf16: bad arguments");
     GMP_REQUIRE(F == 128, "gather_mul_segsum_wbf16: built for 128 columns (got %d)", F);
     if (n == 0) return GMP_OK;
+    if (!col || !w_bf16) {   // only an edgeless graph has no column / factor arrays: every row is an empty sum
+        GMP_CUDA(cudaMemsetAsync(out, 0, (size_t)n * 128 * sizeof(float), stream));
+        return GMP_OK;
+    }
     const unsigned grid = (unsigned)ceil_div(n * 32, 256);
     if (x_is_bf16) segsum_wbf16_kernel<true><<<grid, 256, 0, stream>>>(rowptr, col, perm, x, (const __nv_bfloat16*)w_bf16, out, n);
     else segsum_wbf16_kernel<false><<<grid, 256, 0, stream>>>(rowptr, col, perm, x, (const __nv_bfloat16*)w_bf16, out, n);

@@ -118,7 +118,8 @@ int gmp_gather_mul_segsum_f32(const int32_t* rowptr, const int32_t* col, const i
                               const float* w, float* out, int64_t n, int32_t F, gmp_stream_t stream);
 
 /* K0 with the per-edge factor stored as bf16 rows (gathered rows x fp32 or, with x_is_bf16, bf16; fp32 accumulation and output;
- * F = 128): dL/dx1 of the CFConv from the filter values the forward pass kept (gmp_schnet_cfconv_fwd_tc2_keep). */
+ * F = 128): dL/dx1 of the CFConv from the filter values the forward pass kept (gmp_schnet_cfconv_fwd_tc2_keep).
+ * col / w_bf16 may be NULL for an edgeless graph (out = 0). */
 int gmp_gather_mul_segsum_wbf16(const int32_t* rowptr, const int32_t* col, const int32_t* perm, const void* x,
                                 int32_t x_is_bf16, const void* w_bf16, float* out, int64_t n, int32_t F, gmp_stream_t stream);
 

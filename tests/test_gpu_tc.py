@@ -286,3 +286,60 @@ def test_egnn_bf16_tc_empty_and_isolated():
         g16 = torch.autograd.grad(o16.sum() + q16.sum(), [h16, p16])
         for a, b in zip(g16, g32):
             assert rel_err(a, b) <= 1e-2
+
+
+@pytest.mark.parametrize("n,deg,xbf16", [(700, 9, True), (300, 40, False), (50, 0, True)])
+def test_gather_mul_segsum_wbf16(n, deg, xbf16):
+    """K0 with a bf16 per-edge factor (dL/dx1 of the CFConv from kept filter values): against the same sum in torch on the
+    bf16-rounded inputs -- the kernel only differs in the order of the fp32 additions."""
+    import gmp_b200
+    from gmp_b200._lib import call, ptr
+    g = torch.Generator().manual_seed(n + deg)
+    E = n * deg
+    src, dst = torch.randint(0, n, (E,), generator=g), torch.randint(0, max(n - n // 5, 1), (E,), generator=g)
+    gr = gmp_b200.get_graph(torch.stack([src, dst]).cuda(), n)
+    csr = gr.by_src
+    x = torch.randn(n, 128, generator=g).cuda()
+    w = torch.randn(E, 128, generator=g).cuda().to(torch.bfloat16)
+    xin = x.to(torch.bfloat16) if xbf16 else x
+    out = torch.full((n, 128), float("nan"), device="cuda")
+    call("gmp_gather_mul_segsum_wbf16", ptr(csr.rowptr), ptr(csr.col), csr.perm_ptr, ptr(xin), int(xbf16), ptr(w), ptr(out), n, 128)
+    ref = torch.zeros(n, 128, device="cuda", dtype=torch.float64)
+    ref.index_add_(0, src.cuda(), (xin.double()[dst.cuda()] * w.double()))
+    assert torch.isfinite(out).all()
+    assert (out.double() - ref).abs().max().item() <= 1e-5 * max(1.0, ref.abs().max().item())
+
+
+def test_cfconv_kept_filter_values():
+    """The training variant of the pipelined forward stores W(e) C(e) per edge (caller's edge order): against the filter MLP in
+    torch (fp32), 1e-2; and the aggregate is bit-identical to the plain variant's."""
+    import ctypes as C
+    import gmp_b200
+    from gmp_b200._lib import SchnetFilter, call, ptr
+    n, E = 900, 11000
+    g = torch.Generator().manual_seed(5)
+    ei = torch.stack([torch.randint(0, n, (E,), generator=g), torch.randint(0, n, (E,), generator=g)]).cuda()
+    gr = gmp_b200.get_graph(ei, n)
+    csr = gr.by_dst
+    torch.manual_seed(0)
+    blk = gmp_b200.InteractionBlock(128, 50, 128, 5.0).cuda()
+    sm = gmp_b200.GaussianSmearing(0.0, 5.0, 50).cuda()
+    w1, b1, w2, b2 = blk.mlp[0].weight, blk.mlp[0].bias, blk.mlp[2].weight, blk.mlp[2].bias
+    filt = SchnetFilter(ptr(w1), ptr(b1), ptr(w2), ptr(b2), 50, 128, 5.0, ptr(sm.offset), sm.coeff)
+    ew = torch.rand(E, generator=g).cuda() * 5.5      # some edges beyond the cutoff of the cosine window? no: C(d) is smooth, > 5 wraps
+    ew = ew.clamp(max=5.0)
+    x1b = torch.randn(n, 128, device="cuda").to(torch.bfloat16)
+    head = torch.empty(gmp_b200._lib.lib().gmp_schnet_tc2_num_chunks(E), 128, device="cuda")
+    agg0, agg1 = torch.empty(n, 128, device="cuda"), torch.empty(n, 128, device="cuda")
+    keep = torch.full((E, 128), float("nan"), device="cuda", dtype=torch.bfloat16)
+    call("gmp_schnet_cfconv_fwd_tc2", ptr(csr.rowptr), ptr(csr.col), csr.perm_ptr, ptr(csr.row_ids()), n, E, ptr(ew), ptr(x1b),
+         C.byref(filt), ptr(agg0), ptr(head))
+    call("gmp_schnet_cfconv_fwd_tc2_keep", ptr(csr.rowptr), ptr(csr.col), csr.perm_ptr, ptr(csr.row_ids()), n, E, ptr(ew), ptr(x1b),
+         C.byref(filt), ptr(agg1), ptr(head), ptr(keep))
+    assert torch.equal(agg0, agg1)
+    with torch.no_grad():
+        rbf = torch.exp(sm.coeff * (ew[:, None] - sm.offset[None, :]) ** 2)
+        h = torch.nn.functional.softplus(rbf @ w1.t() + b1) - 0.6931471805599453
+        ref = (h @ w2.t() + b2) * (0.5 * (torch.cos(ew * 3.141592653589793 / 5.0) + 1.0))[:, None]
+    assert torch.isfinite(keep.float()).all()
+    assert rel_err(keep.float(), ref) <= 1e-2
