@@ -19,7 +19,8 @@ using namespace tc;
 
 constexpr int kGF = 128;         // emb_dim
 constexpr int kGT = 128;         // edges per tile
-constexpr int kGRange = 2048;    // edges per work range (whole rows)
+constexpr int kGRangeMax = 2048; // edges per work range (whole rows) on large graphs; smaller graphs get shorter ranges (two per SM,
+                                 // at least one 128-edge tile) so that they still spread over the machine
 constexpr int kGQ = 4;          // column quarters: a thread owns (edge row, 32 columns); 16 warps per CTA
 constexpr int kGCW = 32;        // columns per thread
 constexpr int kGThreads = 512;
@@ -32,7 +33,7 @@ struct EgnnTcArgs {
     const __nv_bfloat16* gath;      // [n,128] bf16, indexed by col:       Q (dst pass) / P (src pass)
     const float* pos;
     const float *wd, *g1, *be1, *w1, *b1, *g2, *be2, *w2, *b2, *g3, *be3, *w3, *b3;
-    int aggr_mean, nranges;
+    int aggr_mean, nranges, grange;
     float eps;
     // fused single-pass backward: per-edge d(pre1) (bf16 rows) and d(delta) (float4), indexed by the caller's edge id
     __nv_bfloat16* dpre_out;
@@ -375,8 +376,8 @@ __global__ void __launch_bounds__(kGThreads, 1) egnn_fwd_tc_kernel(EgnnTcArgs a,
     egnn_tc_setup<256>(c, a, sm);
     const int t = c.t;
     for (int rg = blockIdx.x; rg < a.nranges; rg += gridDim.x) {
-        const int r0 = lower_bound_row(a.rowptr, (int)a.n, (int64_t)rg * kGRange);
-        const int r1 = (rg + 1 == a.nranges) ? (int)a.n : lower_bound_row(a.rowptr, (int)a.n, (int64_t)(rg + 1) * kGRange);
+        const int r0 = lower_bound_row(a.rowptr, (int)a.n, (int64_t)rg * a.grange);
+        const int r1 = (rg + 1 == a.nranges) ? (int)a.n : lower_bound_row(a.rowptr, (int)a.n, (int64_t)(rg + 1) * a.grange);
         if (r0 >= r1) continue;
         const int64_t eb = __ldg(a.rowptr + r0), ee = __ldg(a.rowptr + r1);
         int cur = r0;
@@ -497,8 +498,8 @@ egnn_bwd_tc_kernel(EgnnTcArgs a, const float* __restrict__ g_msg, const float* _
     for (int v = 0; v < 10; ++v) vacc[v] = 0.f;
 
     for (int rg = blockIdx.x; rg < a.nranges; rg += gridDim.x) {
-        const int r0 = lower_bound_row(a.rowptr, (int)a.n, (int64_t)rg * kGRange);
-        const int r1 = (rg + 1 == a.nranges) ? (int)a.n : lower_bound_row(a.rowptr, (int)a.n, (int64_t)(rg + 1) * kGRange);
+        const int r0 = lower_bound_row(a.rowptr, (int)a.n, (int64_t)rg * a.grange);
+        const int r1 = (rg + 1 == a.nranges) ? (int)a.n : lower_bound_row(a.rowptr, (int)a.n, (int64_t)(rg + 1) * a.grange);
         if (r0 >= r1) continue;
         const int64_t eb = __ldg(a.rowptr + r0), ee = __ldg(a.rowptr + r1);
         int cur = r0;
@@ -841,6 +842,13 @@ egnn_bwd_tc_kernel(EgnnTcArgs a, const float* __restrict__ g_msg, const float* _
     if (c.warp == 0) tmem_dealloc<512>(c.tm);
 }
 
+// edges per work range: two ranges per SM, in whole 128-edge tiles, between one tile and kGRangeMax
+static int egnn_tc_range(int64_t E) {
+    int64_t r = ceil_div(E > 0 ? E : 1, 2 * (int64_t)num_sms());
+    r = ceil_div(r, 128) * 128;
+    return (int)(r < 128 ? 128 : (r > kGRangeMax ? kGRangeMax : r));
+}
+
 static EgnnTcArgs egnn_tc_args(const int32_t* rowptr, const int32_t* col, const int32_t* rowid, const int32_t* deg_rowptr, int64_t n,
                                int64_t E, const float* rowt, const void* gath, const float* pos, const gmp_egnn_edge_params* p) {
     EgnnTcArgs a;
@@ -850,7 +858,8 @@ static EgnnTcArgs egnn_tc_args(const int32_t* rowptr, const int32_t* col, const 
     a.wd = p->wd; a.g1 = p->ln1_g; a.be1 = p->ln1_b; a.w1 = p->w1; a.b1 = p->b1; a.g2 = p->ln2_g; a.be2 = p->ln2_b;
     a.w2 = p->w2; a.b2 = p->b2; a.g3 = p->ln3_g; a.be3 = p->ln3_b; a.w3 = p->w3; a.b3 = p->b3;
     a.aggr_mean = p->aggr_mean; a.eps = p->ln_eps;
-    a.nranges = (int)(E > 0 ? ceil_div(E, kGRange) : 1);
+    a.grange = egnn_tc_range(E);
+    a.nranges = (int)(E > 0 ? ceil_div(E, a.grange) : 1);
     return a;
 }
 
@@ -889,7 +898,7 @@ int gmp_egnn_tc_edge_fwd(const int32_t* rowptr, const int32_t* col, const int32_
 }
 
 int32_t gmp_egnn_tc_bwd_num_parts(int64_t num_edges) {
-    const int64_t nr = num_edges > 0 ? ceil_div(num_edges, kGRange) : 1;
+    const int64_t nr = num_edges > 0 ? ceil_div(num_edges, egnn_tc_range(num_edges)) : 1;
     return (int32_t)(nr < num_sms() ? nr : num_sms());
 }
 
