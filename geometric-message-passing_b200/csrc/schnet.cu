@@ -1,7 +1,7 @@
 // SchNet continuous-filter convolution, fused: per-edge filter MLP -> x1[src] * W_e -> segmented sum.
 // fp32 strict path (CUDA-core FFMA).  The per-edge filter W_e [E,F] never touches HBM.
 //
-// Work decomposition: the dst-sorted edge list is cut into ranges of kEdgesPerRange edges at row
+// Work decomposition: the dst-sorted edge list is cut into ranges of up to kEdgesPerRangeMax edges at row
 // granularity (a CTA owns whole destination rows, so no cross-CTA reduction exists); a persistent
 // grid of <= #SM CTAs walks ranges b, b+grid, ...  Inside a range, 64-edge tiles go through
 //   rbf tile -> GEMM1 (+b1, ssp) -> GEMM2 (+b2, *C) -> * gathered x1 rows -> column-thread segmented sum.
@@ -12,7 +12,7 @@
 namespace gmp {
 
 constexpr int kTile = 64;             // edges per tile
-constexpr int kEdgesPerRange = 1024;  // edges per work range (16 tiles)
+constexpr int kEdgesPerRangeMax = 1024;  // edges per work range (16 tiles) on large graphs; small graphs: two ranges per SM, >= 1 tile
 constexpr int kGP = 64;               // Gaussian dimension padded (G <= 64)
 constexpr int kLdR = kGP + 4;
 
@@ -23,7 +23,7 @@ struct SchnetArgs {
     const float *w1, *b1, *w2, *b2, *goff;
     int G;
     float cutoff, gcoeff;
-    int nranges;
+    int nranges, erange;
 };
 
 template <int F>
@@ -122,8 +122,8 @@ __global__ void __launch_bounds__(256, 1) schnet_fwd_kernel(SchnetArgs a, float*
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
 
     for (int rg = blockIdx.x; rg < a.nranges; rg += gridDim.x) {
-        const int r0 = lower_bound_row(a.rowptr, (int)a.n, (int64_t)rg * kEdgesPerRange);
-        const int r1 = (rg + 1 == a.nranges) ? (int)a.n : lower_bound_row(a.rowptr, (int)a.n, (int64_t)(rg + 1) * kEdgesPerRange);
+        const int r0 = lower_bound_row(a.rowptr, (int)a.n, (int64_t)rg * a.erange);
+        const int r1 = (rg + 1 == a.nranges) ? (int)a.n : lower_bound_row(a.rowptr, (int)a.n, (int64_t)(rg + 1) * a.erange);
         if (r0 >= r1) continue;
         const int64_t eb = __ldg(a.rowptr + r0), ee = __ldg(a.rowptr + r1);
         // column-thread reduction state
@@ -222,8 +222,8 @@ schnet_bwd_kernel(SchnetArgs a, const float* __restrict__ g_agg, float* __restri
     float db1 = 0.f, db2 = 0.f;  // threads < F own one bias column each
 
     for (int rg = blockIdx.x; rg < a.nranges; rg += gridDim.x) {
-        const int r0 = lower_bound_row(a.rowptr, (int)a.n, (int64_t)rg * kEdgesPerRange);
-        const int r1 = (rg + 1 == a.nranges) ? (int)a.n : lower_bound_row(a.rowptr, (int)a.n, (int64_t)(rg + 1) * kEdgesPerRange);
+        const int r0 = lower_bound_row(a.rowptr, (int)a.n, (int64_t)rg * a.erange);
+        const int r1 = (rg + 1 == a.nranges) ? (int)a.n : lower_bound_row(a.rowptr, (int)a.n, (int64_t)(rg + 1) * a.erange);
         if (r0 >= r1) continue;
         const int64_t eb = __ldg(a.rowptr + r0), ee = __ldg(a.rowptr + r1);
         for (int64_t e0 = eb; e0 < ee; e0 += kTile) {
@@ -378,6 +378,12 @@ static int schnet_check(const gmp_schnet_filter* f, int64_t n, int64_t E) {
     return GMP_OK;
 }
 
+static int schnet_range(int64_t E) {
+    int64_t r = ceil_div(E > 0 ? E : 1, 2 * (int64_t)num_sms());
+    r = ceil_div(r, kTile) * kTile;
+    return (int)(r < kTile ? kTile : (r > kEdgesPerRangeMax ? kEdgesPerRangeMax : r));
+}
+
 static SchnetArgs make_args(const int32_t* rowptr, const int32_t* col, const int32_t* perm, int64_t n, int64_t E,
                             const float* ew, const float* ea, const float* x1, const gmp_schnet_filter* f) {
     SchnetArgs a;
@@ -385,7 +391,8 @@ static SchnetArgs make_args(const int32_t* rowptr, const int32_t* col, const int
     a.ew = ew; a.ea = ea; a.x1 = x1;
     a.w1 = f->w1; a.b1 = f->b1; a.w2 = f->w2; a.b2 = f->b2; a.goff = f->gauss_offset;
     a.G = f->num_gaussians; a.cutoff = f->cutoff; a.gcoeff = f->gauss_coeff;
-    a.nranges = (int)(E > 0 ? ceil_div(E, kEdgesPerRange) : 1);
+    a.erange = schnet_range(E);
+    a.nranges = (int)(E > 0 ? ceil_div(E, a.erange) : 1);
     return a;
 }
 
@@ -433,7 +440,7 @@ using namespace gmp;
 extern "C" {
 
 int32_t gmp_schnet_bwd_num_parts(int64_t num_edges) {
-    const int64_t nr = num_edges > 0 ? ceil_div(num_edges, kEdgesPerRange) : 1;
+    const int64_t nr = num_edges > 0 ? ceil_div(num_edges, schnet_range(num_edges)) : 1;
     return (int32_t)(nr < num_sms() ? nr : num_sms());
 }
 
