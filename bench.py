@@ -372,7 +372,8 @@ def dominant_kernel_roofline(model, b, E, N, dev, args):
     x1b = x1.to(torch.bfloat16)
     head = torch.empty(lib.gmp_schnet_tc2_num_chunks(E), F, device=dev)
     rowid = csr.row_ids()
-    keep = torch.empty(E, F, dtype=torch.bfloat16, device=dev)   # training keeps the per-edge filter values for the backward
+    keep = torch.empty(E, F, dtype=torch.bfloat16, device=dev)   # training keeps the per-edge filter values for the backward,
+    keep_row = g.by_src.inv_perm()                               # in the order its gather-multiply-reduce reads them
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     times = []
     for it in range(3 + 10):
@@ -381,7 +382,7 @@ def dominant_kernel_roofline(model, b, E, N, dev, args):
         s.record()
         if prec == 1:   # the entry point the bf16 model path calls (zeroes agg, runs the pipelined kernel and the boundary fix-up)
             call("gmp_schnet_cfconv_fwd_tc2_keep", ptr(csr.rowptr), ptr(csr.col), csr.perm_ptr, ptr(rowid), N, E, ptr(ew), ptr(x1b),
-                 C.byref(filt), ptr(agg), ptr(head), ptr(keep))
+                 C.byref(filt), ptr(agg), ptr(head), ptr(keep), ptr(keep_row))
         else:
             call("gmp_schnet_cfconv_fwd", ptr(csr.rowptr), ptr(csr.col), csr.perm_ptr, N, E, ptr(ew), None, ptr(x1),
                  C.byref(filt), ptr(agg), prec)

@@ -64,7 +64,7 @@ _SIGS = {
     "gmp_egnn_edge_fwd": [P, P, I64, I64, P, P, P, P, P, P, I32, P],
     "gmp_egnn_edge_bwd": [P, P, P, I64, I64, P, P, P, P, P, P, I32, P, P, P, I32, P],
     "gmp_schnet_cfconv_fwd_tc2": [P, P, P, P, I64, I64, P, P, P, P, P, P],
-    "gmp_schnet_cfconv_fwd_tc2_keep": [P, P, P, P, I64, I64, P, P, P, P, P, P, P],
+    "gmp_schnet_cfconv_fwd_tc2_keep": [P, P, P, P, I64, I64, P, P, P, P, P, P, P, P],
     "gmp_schnet_cfconv_bwd_tc2": [P, P, P, P, I64, I64, P, P, P, P, P, I32, P],
     "gmp_linear_wgrad_tc": [P, P, I64, I32, I32, P, P],
     "gmp_egnn_tc_edge_fwd": [P, P, P, I64, I64, P, P, P, P, P, P, P],

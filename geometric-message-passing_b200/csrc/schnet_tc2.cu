@@ -41,7 +41,8 @@ struct Tc2Args {
     float* agg;                      // [n,128], zeroed
     float* head;                     // [gridDim.x,128], zeroed
     int* dbg;                        // debug builds (GMP_TC2_PROGRESS): host-mapped progress words, [gridDim.x][32 warps]
-    __nv_bfloat16* wout;             // optional [E,128]: the filter value W(e) * C(e) of every edge, caller's edge order
+    __nv_bfloat16* wout;             // optional [E,128]: the filter value W(e) * C(e) of every edge ...
+    const int32_t* wrow;             // ... at row wrow[edge id] (NULL: the caller's edge id itself)
 };
 
 // shared-memory map (bytes from the 1024-aligned base)
@@ -87,7 +88,7 @@ struct Meta {
     float C[128];
     float d[128];     // edge length (1e18 for the padding slots: every Gaussian underflows to 0)
     int seg[128];
-    int eid[128];     // caller's edge id of the slot (where the optional filter output goes)
+    int eid[128];     // row of the optional filter output that belongs to the slot
     int seg_row[32];
     int cnt, nseg, head0, pad;
 };
@@ -163,7 +164,7 @@ __global__ void __launch_bounds__(kS2Threads, 1) schnet_fwd_tc2_kernel(Tc2Args a
         // Scalars of a tile (CSR row, edge id, source, length, first row pointer) are fetched one tile ahead, speculating
         // that the current tile is not cut short: two dependent L2 round trips per tile that would otherwise sit on the
         // meta warps' critical path.  Level 1 = indexed by the sorted position, level 2 = indexed by what level 1 returned.
-        struct Pre { int rid, ridp, eid, src, rp0; float d; };
+        struct Pre { int rid, ridp, eid, src, rp0, wpos; float d; };
         auto fetch1 = [&](int64_t e0, Pre& P) {
             const int64_t rem = e_end - e0;
             P.rid = 0; P.ridp = -1; P.eid = 0; P.src = 0;
@@ -177,9 +178,10 @@ __global__ void __launch_bounds__(kS2Threads, 1) schnet_fwd_tc2_kernel(Tc2Args a
             }
         };
         auto fetch2 = [&](int64_t e0, Pre& P) {
-            P.d = 1.0e18f; P.rp0 = 0;
+            P.d = 1.0e18f; P.rp0 = 0; P.wpos = P.eid;
             if (e_end - e0 > 0) {
                 P.d = __ldg(a.ew + P.eid);
+                if (a.wrow) P.wpos = __ldg(a.wrow + P.eid);
                 if (e == 0) P.rp0 = __ldg(a.rowptr + P.rid);
             }
         };
@@ -236,7 +238,7 @@ __global__ void __launch_bounds__(kS2Threads, 1) schnet_fwd_tc2_kernel(Tc2Args a
                 M.C[e] = C;
                 M.d[e] = d;
                 M.seg[e] = valid ? seg : -1;
-                M.eid[e] = cur.eid;
+                M.eid[e] = cur.wpos;
                 if (flag && seg < kS2MaxSeg && valid) M.seg_row[seg] = rid;
                 if (e == cnt - 1) { M.cnt = cnt; M.nseg = seg + 1; }
                 if (e == 0) M.head0 = head0;
@@ -897,7 +899,7 @@ int32_t gmp_schnet_tc2_num_chunks(int64_t num_edges) {
 
 int gmp_schnet_cfconv_fwd_tc2_keep(const int32_t* rowptr, const int32_t* col, const int32_t* perm, const int32_t* rowid, int64_t n,
                                    int64_t num_edges, const float* edge_weight, const void* x1_bf16, const gmp_schnet_filter* f,
-                                   float* agg, float* head, void* filter_out_bf16, gmp_stream_t stream) {
+                                   float* agg, float* head, void* filter_out_bf16, const int32_t* filter_row, gmp_stream_t stream) {
     GMP_REQUIRE(rowptr && f && agg && head, "schnet_cfconv_fwd_tc2: NULL pointer");
     GMP_REQUIRE(num_edges == 0 || (col && rowid && edge_weight && x1_bf16), "schnet_cfconv_fwd_tc2: NULL edge/feature pointer");
     GMP_REQUIRE(f->num_filters == 128 && f->num_gaussians >= 1 && f->num_gaussians <= 64 && f->gauss_offset,
@@ -910,7 +912,7 @@ int gmp_schnet_cfconv_fwd_tc2_keep(const int32_t* rowptr, const int32_t* col, co
     Tc2Args a;
     a.rowptr = rowptr; a.col = col; a.perm = perm; a.rowid = rowid; a.n = n; a.E = num_edges; a.ew = edge_weight;
     a.x1 = (const __nv_bfloat16*)x1_bf16; a.w1 = f->w1; a.b1 = f->b1; a.w2 = f->w2; a.b2 = f->b2; a.goff = f->gauss_offset;
-    a.G = f->num_gaussians; a.cutoff = f->cutoff; a.gcoeff = f->gauss_coeff; a.agg = agg; a.head = head; a.wout = (__nv_bfloat16*)filter_out_bf16;
+    a.G = f->num_gaussians; a.cutoff = f->cutoff; a.gcoeff = f->gauss_coeff; a.agg = agg; a.head = head; a.wout = (__nv_bfloat16*)filter_out_bf16; a.wrow = filter_row;
 #ifdef GMP_TC2_PROGRESS
     a.dbg = g_tc2_dbg;
 #else
@@ -930,7 +932,7 @@ int gmp_schnet_cfconv_fwd_tc2_keep(const int32_t* rowptr, const int32_t* col, co
 int gmp_schnet_cfconv_fwd_tc2(const int32_t* rowptr, const int32_t* col, const int32_t* perm, const int32_t* rowid, int64_t n,
                               int64_t num_edges, const float* edge_weight, const void* x1_bf16, const gmp_schnet_filter* f, float* agg,
                               float* head, gmp_stream_t stream) {
-    return gmp_schnet_cfconv_fwd_tc2_keep(rowptr, col, perm, rowid, n, num_edges, edge_weight, x1_bf16, f, agg, head, nullptr, stream);
+    return gmp_schnet_cfconv_fwd_tc2_keep(rowptr, col, perm, rowid, n, num_edges, edge_weight, x1_bf16, f, agg, head, nullptr, nullptr, stream);
 }
 
 int gmp_schnet_cfconv_bwd_tc2(const int32_t* rowptr, const int32_t* col, const int32_t* perm, const int32_t* rowid, int64_t n,
@@ -945,7 +947,7 @@ int gmp_schnet_cfconv_bwd_tc2(const int32_t* rowptr, const int32_t* col, const i
     Tc2Args& a = b.f;
     a.rowptr = rowptr; a.col = col; a.perm = perm; a.rowid = rowid; a.n = n; a.E = num_edges; a.ew = edge_weight;
     a.x1 = (const __nv_bfloat16*)x1_bf16; a.w1 = f->w1; a.b1 = f->b1; a.w2 = f->w2; a.b2 = f->b2; a.goff = f->gauss_offset;
-    a.G = f->num_gaussians; a.cutoff = f->cutoff; a.gcoeff = f->gauss_coeff; a.agg = nullptr; a.head = nullptr; a.wout = nullptr;
+    a.G = f->num_gaussians; a.cutoff = f->cutoff; a.gcoeff = f->gauss_coeff; a.agg = nullptr; a.head = nullptr; a.wout = nullptr; a.wrow = nullptr;
     a.dbg = nullptr;
     b.g_agg = g_agg; b.parts = wgrad_parts;
     GMP_CUDA(cudaFuncSetAttribute(schnet_bwd_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTc2BwdSmem));

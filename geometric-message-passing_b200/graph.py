@@ -104,6 +104,16 @@ class CSR:
     def perm_ptr(self):
         return ptr(self.perm)
 
+    def inv_perm(self) -> Optional[torch.Tensor]:
+        """int32[E]: sorted position of the edge with caller's id i (None when the CSR order is the caller's order); cached."""
+        if self.perm is None:
+            return None
+        if getattr(self, "_inv_perm", None) is None:
+            inv = torch.empty_like(self.perm)
+            inv[self.perm.long()] = torch.arange(self.E, device=self.perm.device, dtype=torch.int32)
+            self._inv_perm = inv
+        return self._inv_perm
+
     def row_ids(self) -> torch.Tensor:
         """int32[E]: aggregation row of each sorted edge (cached)."""
         if getattr(self, "_row_ids", None) is None:

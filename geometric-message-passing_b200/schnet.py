@@ -90,7 +90,7 @@ def _tc2_ok(precision, edge_attr, F_, G) -> bool:
     return precision == _lib.BF16_TC and edge_attr is None and F_ == 128 and G <= 64
 
 
-def _cfconv_forward(csr, graph, edge_weight, edge_attr, x1, filt, w1, precision, keep=None, x1_bf16=None):
+def _cfconv_forward(csr, graph, edge_weight, edge_attr, x1, filt, w1, precision, keep=None, x1_bf16=None, keep_row=None):
     """agg[r] = sum_{e in CSR row r} x1[col_e] * W_e.  bf16 mode with the lazily expanded basis and 128 filters: the
     pipelined three-MMA kernel (csrc/schnet_tc2.cu); otherwise the fp32 / first tensor-core kernels.
     keep: optional bf16 [E,128] that receives every edge's filter value (caller's edge order) for the backward pass."""
@@ -100,7 +100,7 @@ def _cfconv_forward(csr, graph, edge_weight, edge_attr, x1, filt, w1, precision,
         head = torch.empty(int(_lib.lib().gmp_schnet_tc2_num_chunks(graph.E)), 128, dtype=x1.dtype, device=x1.device)
         x1_bf16 = x1.to(torch.bfloat16) if x1_bf16 is None else x1_bf16
         call("gmp_schnet_cfconv_fwd_tc2_keep", ptr(csr.rowptr), ptr(csr.col), csr.perm_ptr, ptr(csr.row_ids()), graph.n, graph.E,
-             ptr(edge_weight), ptr(x1_bf16), C.byref(filt), ptr(agg), ptr(head), ptr(keep))
+             ptr(edge_weight), ptr(x1_bf16), C.byref(filt), ptr(agg), ptr(head), ptr(keep), ptr(keep_row))
     else:
         assert keep is None
         call("gmp_schnet_cfconv_fwd", ptr(csr.rowptr), ptr(csr.col), csr.perm_ptr, graph.n, graph.E, ptr(edge_weight),
@@ -124,7 +124,10 @@ class _CFConvFn(torch.autograd.Function):
         ctx.x1_bf16 = x1.to(torch.bfloat16) if tc2 else None
         ctx.keep = (torch.empty(graph.E, 128, dtype=torch.bfloat16, device=x1.device)
                     if (tc2 and ctx.needs_input_grad[0] and graph.E > 0) else None)
-        agg = _cfconv_forward(csr, graph, edge_weight, edge_attr, x1, filt, w1, precision, ctx.keep, ctx.x1_bf16)
+        # the kept rows go where the backward pass will read them: in the order of the source-sorted CSR, so that its
+        # gather-multiply-reduce streams them front to back
+        keep_row = graph.by_src.inv_perm() if ctx.keep is not None else None
+        agg = _cfconv_forward(csr, graph, edge_weight, edge_attr, x1, filt, w1, precision, ctx.keep, ctx.x1_bf16, keep_row)
         ctx.save_for_backward(x1, edge_weight, edge_attr if edge_attr is not None else x1.new_empty(0), w1, b1, w2, b2, offset)
         ctx.graph, ctx.meta, ctx.has_attr = graph, (float(cutoff), float(coeff), precision), edge_attr is not None
         return agg
@@ -143,10 +146,10 @@ class _CFConvFn(torch.autograd.Function):
         if need[0]:
             t = graph.by_src
             if ctx.keep is not None:
-                # dx1[s] = sum_{e: src_e = s} W_e * g[dst_e] with the kept filter values (indexed by the caller's edge id)
+                # dx1[s] = sum_{e: src_e = s} W_e * g[dst_e] with the kept filter values (stored in this CSR's own order)
                 dx1 = torch.empty(graph.n, F, dtype=g.dtype, device=g.device)
                 # (g gathered as bf16 rows, as the transposed pass of the fused kernel did: halves the L2 -> SM traffic)
-                call("gmp_gather_mul_segsum_wbf16", ptr(t.rowptr), ptr(t.col), t.perm_ptr, ptr(g.to(torch.bfloat16)), 1, ptr(ctx.keep),
+                call("gmp_gather_mul_segsum_wbf16", ptr(t.rowptr), ptr(t.col), None, ptr(g.to(torch.bfloat16)), 1, ptr(ctx.keep),
                      ptr(dx1), graph.n, F)
             else:
                 # d agg / d x1 is the same fused op over the transposed (src-sorted) CSR with g in place of x1

@@ -208,14 +208,15 @@ int gmp_schnet_cfconv_fwd_tc2(const int32_t* rowptr, const int32_t* col, const i
                               int64_t n, int64_t num_edges, const float* edge_weight, const void* x1_bf16,
                               const gmp_schnet_filter* filter /* host */, float* agg, float* head, gmp_stream_t stream);
 
-/* Same, and additionally stores the filter value of every edge, W(e) * C(e) as 128 bf16, at row (perm ? perm[k] : k) of
- * filter_out_bf16 [E,128] (the caller's edge order; may be NULL = plain forward).  Training uses it so that the backward pass
- * does not have to run the filter MLP again for dL/dx1 (PyG keeps the same [E,F] tensor alive for autograd,
- * CFConv.forward called at models/schnet.py:72). */
+/* Same, and additionally stores the filter value of every edge, W(e) * C(e) as 128 bf16, into filter_out_bf16 [E,128] (may be
+ * NULL = plain forward) at row filter_row[id] of the edge with caller's id (perm ? perm[k] : k); filter_row = NULL: at row id.
+ * Training uses it so that the backward pass does not have to run the filter MLP again for dL/dx1 (PyG keeps the same [E,F]
+ * tensor alive for autograd, CFConv.forward called at models/schnet.py:72); with filter_row = the position of each edge in
+ * the source-sorted CSR, gmp_gather_mul_segsum_wbf16 then streams the factors in order (perm = NULL there). */
 int gmp_schnet_cfconv_fwd_tc2_keep(const int32_t* rowptr, const int32_t* col, const int32_t* perm, const int32_t* rowid,
                                    int64_t n, int64_t num_edges, const float* edge_weight, const void* x1_bf16,
                                    const gmp_schnet_filter* filter /* host */, float* agg, float* head,
-                                   void* filter_out_bf16, gmp_stream_t stream);
+                                   void* filter_out_bf16, const int32_t* filter_row, gmp_stream_t stream);
 
 /* Pipelined GMP_BF16_TC variant of the filter-side backward (weight gradients of the filter MLP only; same partial layout
  * as gmp_schnet_cfconv_bwd: [dW1 128x64 | db1 | dW2 128x128 | db2] per CTA, `nparts` CTAs, each owning a contiguous range

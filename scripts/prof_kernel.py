@@ -44,7 +44,7 @@ for it in range(reps + 2):
     s.record()
     if which == "schnet_fwd2k":   # the training variant: also stores the per-edge filter values
         call("gmp_schnet_cfconv_fwd_tc2_keep", ptr(csr.rowptr), ptr(csr.col), csr.perm_ptr, ptr(rowid), N, E, ptr(ew), ptr(x1b),
-             C.byref(filt), ptr(agg), ptr(head), ptr(keep))
+             C.byref(filt), ptr(agg), ptr(head), ptr(keep), ptr(g.by_src.inv_perm()))
     elif which == "schnet_fwd2":
         call("gmp_schnet_cfconv_fwd_tc2", ptr(csr.rowptr), ptr(csr.col), csr.perm_ptr, ptr(rowid), N, E, ptr(ew), ptr(x1b),
              C.byref(filt), ptr(agg), ptr(head))

@@ -335,8 +335,14 @@ def test_cfconv_kept_filter_values():
     call("gmp_schnet_cfconv_fwd_tc2", ptr(csr.rowptr), ptr(csr.col), csr.perm_ptr, ptr(csr.row_ids()), n, E, ptr(ew), ptr(x1b),
          C.byref(filt), ptr(agg0), ptr(head))
     call("gmp_schnet_cfconv_fwd_tc2_keep", ptr(csr.rowptr), ptr(csr.col), csr.perm_ptr, ptr(csr.row_ids()), n, E, ptr(ew), ptr(x1b),
-         C.byref(filt), ptr(agg1), ptr(head), ptr(keep))
+         C.byref(filt), ptr(agg1), ptr(head), ptr(keep), None)
     assert torch.equal(agg0, agg1)
+    # the same values at caller-chosen rows (the model passes the position of each edge in the source-sorted CSR)
+    inv = gr.by_src.inv_perm()
+    keep2 = torch.full((E, 128), float("nan"), device="cuda", dtype=torch.bfloat16)
+    call("gmp_schnet_cfconv_fwd_tc2_keep", ptr(csr.rowptr), ptr(csr.col), csr.perm_ptr, ptr(csr.row_ids()), n, E, ptr(ew), ptr(x1b),
+         C.byref(filt), ptr(agg1), ptr(head), ptr(keep2), ptr(inv))
+    assert torch.equal(agg0, agg1) and torch.equal(keep2[inv.long()], keep)
     with torch.no_grad():
         rbf = torch.exp(sm.coeff * (ew[:, None] - sm.offset[None, :]) ** 2)
         h = torch.nn.functional.softplus(rbf @ w1.t() + b1) - 0.6931471805599453
