@@ -290,9 +290,11 @@ __global__ void __launch_bounds__(kS2Threads, 1) schnet_fwd_tc2_kernel(Tc2Args a
                 for (int c4 = 0; c4 < 4; ++c4) {
                     const int ch = 4 * g + c4;
                     float v[8];
+                    const float4 g0 = *reinterpret_cast<const float4*>(goff + ch * 8), g1 = *reinterpret_cast<const float4*>(goff + ch * 8 + 4);
+                    const float go[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};   // two 16-byte broadcast loads, not eight predicated ones
 #pragma unroll
                     for (int q = 0; q < 8; ++q) {
-                        const float u = d - goff[ch * 8 + q];
+                        const float u = d - go[q];
                         v[q] = (ch * 8 + q == a.G) ? 1.0f : ex2a(c2 * u * u);   // column G = 1: picks up b1 from the W1 image
                     }
                     *reinterpret_cast<uint4*>(sm + o2A1 + sw128_chunk_off(e, ch)) =
@@ -692,9 +694,11 @@ __global__ void __launch_bounds__(896, 1) schnet_bwd_tc2_kernel(Tc2BwdArgs b) { 
 #pragma unroll
             for (int ch = 0; ch < 8; ++ch) {
                 float v[8];
+                const float4 g0 = *reinterpret_cast<const float4*>(goff + ch * 8), g1 = *reinterpret_cast<const float4*>(goff + ch * 8 + 4);
+                const float go[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
-                    const float u = d - goff[ch * 8 + q];
+                    const float u = d - go[q];
                     v[q] = ex2a(c2 * u * u);
                 }
                 if (ch == 7) v[7] = 1.0f;   // ones column: bias of GEMM 1, and the column sums db1 in the dW1 accumulator
