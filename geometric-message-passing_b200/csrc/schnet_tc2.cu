@@ -129,6 +129,15 @@ __global__ void __launch_bounds__(kS2Threads, 1) schnet_fwd_tc2_kernel(Tc2Args a
             make_uint4(pack_bf16(lo.x, lo.y), pack_bf16(lo.z, lo.w), pack_bf16(hi.x, hi.y), pack_bf16(hi.z, hi.w));
     }
     if (t < 128) { b1s[t] = a.G < 64 ? 0.f : __ldg(a.b1 + t); b2s[t] = __ldg(a.b2 + t); }
+    if (t < 128) {
+        // b2 rides in GEMM 2 as one more K16 step: A slab = a column of ones, B slab = b2 in its first K column.  Both live in
+        // the half of the one-hot tile's 128-byte rows that the 32 segments never use (logical 16-byte chunks 4-5 and 6-7).
+        const uint32_t one = 0x00003f80u;   // bf16 1.0 in the low half
+        *reinterpret_cast<uint4*>(sm + o2S + sw128_chunk_off(t, 4)) = make_uint4(one, 0u, 0u, 0u);
+        *reinterpret_cast<uint4*>(sm + o2S + sw128_chunk_off(t, 5)) = make_uint4(0u, 0u, 0u, 0u);
+        *reinterpret_cast<uint4*>(sm + o2S + sw128_chunk_off(t, 6)) = make_uint4(pack_bf16(__ldg(a.b2 + t), 0.f), 0u, 0u, 0u);
+        *reinterpret_cast<uint4*>(sm + o2S + sw128_chunk_off(t, 7)) = make_uint4(0u, 0u, 0u, 0u);
+    }
     if (t < 64) goff[t] = t < a.G ? __ldg(a.goff + t) : 1.0e18f;  // padding columns: the Gaussian underflows to exactly 0
     if (t == 0) {
         *end_g1 = -1;
@@ -415,8 +424,7 @@ __global__ void __launch_bounds__(kS2Threads, 1) schnet_fwd_tc2_kernel(Tc2Args a
                     uint32_t o[4];
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {
-                        const int c0 = 64 * g + 32 * j + 8 * q + 2 * u;
-                        const float f0 = (v[8 * q + 2 * u] + b2s[c0]) * C, f1 = (v[8 * q + 2 * u + 1] + b2s[c0 + 1]) * C;
+                        const float f0 = v[8 * q + 2 * u] * C, f1 = v[8 * q + 2 * u + 1] * C;   // b2 came through the GEMM
                         fo[4 * (q & 1) + u] = pack_bf16(f0, f1);
                         o[u] = pack_bf16(f0 * __uint_as_float(w[u] << 16), f1 * __uint_as_float(w[u] & 0xffff0000u));   // C = 0 and zero rows for the padding slots
                     }
@@ -480,7 +488,7 @@ __global__ void __launch_bounds__(kS2Threads, 1) schnet_fwd_tc2_kernel(Tc2Args a
     } else if (warp == 25) {
         // ===================== G2 = h1 W2^T =====================
         const uint32_t id1 = umma_idesc_bf16(128, 128);
-        const uint32_t w2b = smem_u32(sm + o2W2), a2b = smem_u32(sm + o2A2);
+        const uint32_t w2b = smem_u32(sm + o2W2), a2b = smem_u32(sm + o2A2), sbias = smem_u32(sm + o2S);
         for (uint32_t tc = 0;; ++tc) {
             TC2_MARK(12, tc);
             mbar_wait(&bars[B_A2F], tc & 1u);
@@ -497,6 +505,7 @@ __global__ void __launch_bounds__(kS2Threads, 1) schnet_fwd_tc2_kernel(Tc2Args a
                                   (ks | k16) ? 1u : 0u);
                     umma_commit(&bars[B_A2E + ks]);
                 }
+                umma_bf16(tmD2, umma_desc_k128(sbias + 64), umma_desc_k128(sbias + 96), id1, 1u);   // + 1 * b2^T
                 umma_commit(&bars[B_D2F]);
             }
             __syncwarp();
