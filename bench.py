@@ -399,7 +399,7 @@ def dominant_kernel_roofline(model, b, E, N, dev, args):
                  "time includes the agg memset and the boundary fix-up) via gmp_schnet_cfconv_fwd_tc2_keep")
         note = (f"{flops / (ms * 1e-3) / 1e12:.1f} TFLOP/s on the filter-MLP GEMMs (bf16 tcgen05); algorithmic bytes are SURVEY 8d's "
                 "fp32 figure -- the kernel itself gathers x1 as bf16 rows (256 B/edge, L2-resident) and, in training, writes 256 B/edge of "
-                "filter values that are not algorithmic bytes (the plain forward: 0.339 ms, 45.5 %); the kernel is bound by load/store-unit "
+                "filter values that are not algorithmic bytes (the plain forward: 0.321 ms, 48.1 %); the kernel is bound by load/store-unit "
                 "and MIO cycles (lane-per-row accesses, one ex2 per softplus / Gaussian), tensor pipe 12 %, not by HBM "
                 "(profiles/r01f_summary.md)")
     else:
