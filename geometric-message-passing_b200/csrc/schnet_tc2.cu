@@ -132,10 +132,12 @@ __global__ void __launch_bounds__(kS2Threads, 1) schnet_fwd_tc2_kernel(Tc2Args a
     if (t < 128) {
         // b2 rides in GEMM 2 as one more K16 step: A slab = a column of ones, B slab = b2 in its first K column.  Both live in
         // the half of the one-hot tile's 128-byte rows that the 32 segments never use (logical 16-byte chunks 4-5 and 6-7).
-        const uint32_t one = 0x00003f80u;   // bf16 1.0 in the low half
-        *reinterpret_cast<uint4*>(sm + o2S + sw128_chunk_off(t, 4)) = make_uint4(one, 0u, 0u, 0u);
+        // (two K columns: b2 = hi + lo in bf16, so the bias keeps ~16 mantissa bits)
+        const float bias = __ldg(a.b2 + t);
+        const float hi = __bfloat162float(__float2bfloat16_rn(bias));
+        *reinterpret_cast<uint4*>(sm + o2S + sw128_chunk_off(t, 4)) = make_uint4(0x3f803f80u, 0u, 0u, 0u);   // bf16 1.0, 1.0
         *reinterpret_cast<uint4*>(sm + o2S + sw128_chunk_off(t, 5)) = make_uint4(0u, 0u, 0u, 0u);
-        *reinterpret_cast<uint4*>(sm + o2S + sw128_chunk_off(t, 6)) = make_uint4(pack_bf16(__ldg(a.b2 + t), 0.f), 0u, 0u, 0u);
+        *reinterpret_cast<uint4*>(sm + o2S + sw128_chunk_off(t, 6)) = make_uint4(pack_bf16(hi, bias - hi), 0u, 0u, 0u);
         *reinterpret_cast<uint4*>(sm + o2S + sw128_chunk_off(t, 7)) = make_uint4(0u, 0u, 0u, 0u);
     }
     if (t < 64) goff[t] = t < a.G ? __ldg(a.goff + t) : 1.0e18f;  // padding columns: the Gaussian underflows to exactly 0
