@@ -19,7 +19,7 @@ _lib = None
 launches = 0  # number of C-ABI compute calls issued
 _kernels = 0  # number of CUDA kernels those calls launched (bench.py's gpu_launches)
 # kernels launched per entry point (default 1); memsets are not counted
-_KERNELS_PER_CALL = {"gmp_exclusive_scan_i32": 3, "gmp_csr_fill": 2, "gmp_cells_build": 3, "gmp_tp_tc_contract": 2, "gmp_schnet_cfconv_fwd_tc2": 2, "gmp_schnet_cfconv_fwd_tc2_keep": 2}
+_KERNELS_PER_CALL = {"gmp_exclusive_scan_i32": 3, "gmp_csr_fill": 3, "gmp_cells_build": 3, "gmp_tp_tc_contract": 2, "gmp_schnet_cfconv_fwd_tc2": 2, "gmp_schnet_cfconv_fwd_tc2_keep": 2}
 
 
 def kernel_launches() -> int:

@@ -2,6 +2,8 @@
 // Integer / byte path: results are bit-exact by construction (no floating-point reductions).
 #include <stdarg.h>
 
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace gmp {
@@ -259,18 +261,102 @@ __global__ void csr_bucket_kernel(const int64_t* __restrict__ index, int64_t E, 
     tmp[rowptr[r] + slot] = (int32_t)e;
 }
 
-// one warp per row: rank-sort the (unique) edge ids of the row ascending -> stable order
+// Rows up to kLongRow edges: one warp per row rank-sorts the (unique) edge ids of the row ascending -> stable order.
+// Longer rows (pooling one large graph puts every node into one row) are left to csr_sort_long_rows_kernel: the rank
+// sort is quadratic in the row length.
+constexpr int kLongRow = 1024;
+
 __global__ void csr_rank_kernel(const int32_t* __restrict__ rowptr, int64_t n, const int32_t* __restrict__ tmp,
                                 int32_t* __restrict__ perm) {
     const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (row >= n) return;
     const int b = rowptr[row], d = rowptr[row + 1] - b;
+    if (d > kLongRow) return;
     for (int k = lane; k < d; k += 32) {
         const int32_t mine = tmp[b + k];
         int rank = 0;
         for (int m = 0; m < d; ++m) rank += (tmp[b + m] < mine);
         perm[b + rank] = mine;
+    }
+}
+
+// Long rows: a block-wide LSD radix sort (8 bits per pass) of the row's edge ids, ping-ponging between the bucketed
+// array `tmp` and `perm`, so the result is the ascending (= stable) order in linear time.  A pass streams the row in
+// tiles of 1024 keys: thread = key (tile order = current order, which is what makes the pass stable); the rank of a key
+// among the equal digits of its tile comes from __match_any_sync inside the warp plus a scan of the per-warp counts.
+struct LongRowSmem {
+    int wcount[32][257];   // per-warp digit counts of the current tile (257: digit 256 = "no key", and bank spread)
+    int base[256];         // running output offset of every digit within the row
+    int hist[256];
+    int rows[1024];
+    int n_rows;
+};
+
+__device__ void sort_long_row(LongRowSmem& S, int b, int d, int32_t* tmp, int32_t* perm, int passes) {
+    const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+    int32_t *src = tmp + b, *dst = perm + b;
+    for (int ps = 0; ps < passes; ++ps) {
+        const int shift = 8 * ps;
+        if (t < 256) S.hist[t] = 0;
+        __syncthreads();
+        for (int k = t; k < d; k += 1024) atomicAdd(&S.hist[(src[k] >> shift) & 255], 1);   // integer histogram
+        __syncthreads();
+        if (t == 0) {
+            int acc = 0;
+            for (int q = 0; q < 256; ++q) { S.base[q] = acc; acc += S.hist[q]; }
+        }
+        __syncthreads();
+        for (int k0 = 0; k0 < d; k0 += 1024) {
+            const int k = k0 + t;
+            const bool ok = k < d;
+            const int32_t key = ok ? src[k] : 0;
+            const int dg = ok ? ((key >> shift) & 255) : 256;
+            for (int q = lane; q < 257; q += 32) S.wcount[warp][q] = 0;
+            __syncwarp();
+            const unsigned peers = __match_any_sync(0xffffffffu, dg);
+            const int rank_w = __popc(peers & ((1u << lane) - 1u));
+            if (rank_w == 0) S.wcount[warp][dg] = __popc(peers);
+            __syncthreads();
+            if (ok) {
+                int off = 0;
+                for (int w = 0; w < warp; ++w) off += S.wcount[w][dg];
+                dst[S.base[dg] + off + rank_w] = key;
+            }
+            __syncthreads();
+            if (t < 256) {
+                int tot = 0;
+                for (int w = 0; w < 32; ++w) tot += S.wcount[w][t];
+                S.base[t] += tot;
+            }
+            __syncthreads();
+        }
+        int32_t* sw = src; src = dst; dst = sw;
+    }
+    if (src != perm + b)
+        for (int k = t; k < d; k += 1024) perm[b + k] = src[k];
+    __syncthreads();
+}
+
+// each block owns a contiguous range of rows, finds the long ones 1024 rows at a time and sorts them one after the other
+__global__ void __launch_bounds__(1024) csr_sort_long_rows_kernel(const int32_t* __restrict__ rowptr, int64_t n, int32_t* tmp,
+                                                                  int32_t* perm, int passes) {
+    __shared__ LongRowSmem S;
+    const int t = threadIdx.x;
+    const int64_t rows_per_block = (n + gridDim.x - 1) / gridDim.x;
+    const int64_t r_lo = rows_per_block * blockIdx.x, r_hi = min(n, r_lo + rows_per_block);
+    for (int64_t r0 = r_lo; r0 < r_hi; r0 += 1024) {
+        if (t == 0) S.n_rows = 0;
+        __syncthreads();
+        const int64_t mine = r0 + t;
+        if (mine < r_hi && rowptr[mine + 1] - rowptr[mine] > kLongRow) S.rows[atomicAdd(&S.n_rows, 1)] = t;
+        __syncthreads();
+        const int nl = S.n_rows;
+        for (int i = 0; i < nl; ++i) {
+            const int64_t row = r0 + S.rows[i];
+            sort_long_row(S, rowptr[row], rowptr[row + 1] - rowptr[row], tmp, perm, passes);
+        }
+        __syncthreads();
     }
 }
 
@@ -397,6 +483,12 @@ int gmp_csr_fill(const int64_t* index, int64_t num_edges, int64_t n, const int32
     GMP_CUDA(cudaMemsetAsync(cursor_ws, 0, n * sizeof(int32_t), stream));
     csr_bucket_kernel<<<(unsigned)ceil_div(num_edges, 256), 256, 0, stream>>>(index, num_edges, n, rowptr, cursor_ws, tmp_ws);
     csr_rank_kernel<<<(unsigned)ceil_div(n * 32, 256), 256, 0, stream>>>(rowptr, n, tmp_ws, perm);
+    if (num_edges > kLongRow) {   // rows longer than kLongRow: linear-time radix sort of their edge ids (edge ids < num_edges)
+        int passes = 1;
+        while (passes < 4 && (num_edges >> (8 * passes)) != 0) ++passes;
+        const unsigned blocks = (unsigned)std::min<int64_t>(ceil_div(n, 1024), 148 * 2);
+        csr_sort_long_rows_kernel<<<blocks, 1024, 0, stream>>>(rowptr, n, tmp_ws, perm, passes);
+    }
     return check_launch("csr_fill");
 }
 

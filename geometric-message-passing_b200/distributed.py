@@ -21,9 +21,10 @@ import torch
 import torch.distributed as dist
 
 
-def allreduce_gradients(params, group=None) -> Optional[torch.Tensor]:
-    """Sum the gradients of `params` across ranks through one flat buffer; writes the sums back in place."""
-    grads = [p.grad for p in params if p.grad is not None]
+def allreduce_gradients(params, group=None, grads=None) -> Optional[torch.Tensor]:
+    """Sum the gradients of `params` across ranks through one flat buffer; writes the sums back in place.
+    `grads`: the gradient tensors themselves when they do not hang off `p.grad` (GraphedStep.grads)."""
+    grads = [p.grad for p in params if p.grad is not None] if grads is None else [g for g in grads if g is not None]
     if not grads or not dist.is_initialized() or dist.get_world_size(group) == 1:
         return None
     flat = torch.cat([g.reshape(-1) for g in grads])
@@ -66,17 +67,19 @@ def slab_partition(x_sorted: torch.Tensor, r: float, rank: int, world: int) -> S
     Equal-count slabs; the halo window of a slab is [x_first_owned - r, x_last_owned + r]."""
     n = x_sorted.numel()
     bounds = [(n * p) // world for p in range(world + 1)]
-    xs = x_sorted.detach().double().cpu()
-
-    def window(p):
-        lo, hi = bounds[p], bounds[p + 1]
-        if hi == lo:
-            return lo, lo
-        a = int(torch.searchsorted(xs, xs[lo] - r, right=False))
-        b = int(torch.searchsorted(xs, xs[hi - 1] + r, right=True))
-        return a, b  # global index window [a, b) that slab p needs (includes its own nodes)
-
-    wins = [window(p) for p in range(world)]
+    # the 2 * world window edges are located on the device the array lives on (two searchsorted calls over the sorted
+    # array, 2 * world values read back once); nothing of size n crosses to the host
+    xs = x_sorted.detach()
+    nonempty = [p for p in range(world) if bounds[p + 1] > bounds[p]]
+    wins = [(bounds[p], bounds[p]) for p in range(world)]
+    if nonempty:
+        first = xs[torch.tensor([bounds[p] for p in nonempty], device=xs.device)]
+        last = xs[torch.tensor([bounds[p + 1] - 1 for p in nonempty], device=xs.device)]
+        rw = r * (1.0 + 1e-6)        # the subtraction below rounds in the array's dtype: widen the window by more than that
+        a = torch.searchsorted(xs, first - rw, right=False)
+        b = torch.searchsorted(xs, last + rw, right=True)
+        for p, ai, bi in zip(nonempty, a.tolist(), b.tolist()):
+            wins[p] = (min(int(ai), bounds[p]), max(int(bi), bounds[p + 1]))   # a window always contains its own slab
     own_lo, own_hi = bounds[rank], bounds[rank + 1]
     a, b = wins[rank]
     n_left, n_right = own_lo - a, b - own_hi
@@ -177,7 +180,7 @@ class PartitionedEGNN(torch.nn.Module):
         for conv in self.convs:
             h_loc = halo_exchange(h_own, part, group)
             pos_loc = halo_exchange(pos_own, part, group)
-            h_upd, pos_upd = conv(h_loc, pos_loc, edge_index_local)
-            h_own = h_own + h_upd[own] if self.residual else h_upd[own]
-            pos_own = pos_upd[own]
+            h_upd, pos_upd = conv(h_loc, pos_loc, edge_index_local, rows=own)   # node-side work on owned rows only
+            h_own = h_own + h_upd if self.residual else h_upd
+            pos_own = pos_upd
         return h_own, pos_own

@@ -125,12 +125,19 @@ class EGNNLayer(nn.Module):
         self.mlp_upd = Sequential(Linear(2 * emb_dim, emb_dim), self.norm(emb_dim), self.activation,
                                   Linear(emb_dim, emb_dim), self.norm(emb_dim), self.activation)
 
-    def forward(self, h, pos, edge_index):
+    def forward(self, h, pos, edge_index, rows: slice = None):
+        """rows (not in the reference signature): restrict the destination side to h[rows] -- the destination-partitioned
+        path passes its owned slice, every edge of `edge_index` then ends in it and only those rows are returned, so no
+        node-side work is spent on halo rows (they are message sources only)."""
         d = self.emb_dim
-        graph = get_graph(edge_index, h.shape[0])
+        n = h.shape[0]
+        graph = get_graph(edge_index, n)
         lin0 = self.mlp_msg[0]
         W0 = lin0.weight
-        P = F.linear(h, W0[:, :d], lin0.bias)          # h_i half (+ bias)
+        h_dst = h if rows is None else h[rows]
+        P = F.linear(h_dst, W0[:, :d], lin0.bias)      # h_i half (+ bias)
+        if rows is not None:                           # the edge kernel indexes P by local row id: zero rows for the halo
+            P = F.pad(P, (0, 0, rows.start, n - rows.stop))
         Q = F.linear(h, W0[:, d:2 * d])                # h_j half
         wd = W0[:, 2 * d]                              # distance column
         ln1, lin1, ln2 = self.mlp_msg[1], self.mlp_msg[3], self.mlp_msg[4]
@@ -139,7 +146,9 @@ class EGNNLayer(nn.Module):
             P, Q, pos, graph, self._act_id, float(ln1.eps), int(self.aggr == "mean"), _PREC[self.precision],
             wd, ln1.weight, ln1.bias, lin1.weight, lin1.bias, ln2.weight, ln2.bias, lin2.weight, lin2.bias,
             ln3.weight, ln3.bias, lin3.weight, lin3.bias)
-        upd_out = self.mlp_upd(torch.cat([h, msg_aggr], dim=-1))
+        if rows is not None:
+            msg_aggr, pos_aggr, pos = msg_aggr[rows], pos_aggr[rows], pos[rows]
+        upd_out = self.mlp_upd(torch.cat([h_dst, msg_aggr], dim=-1))
         return upd_out, pos + pos_aggr
 
     def __repr__(self) -> str:

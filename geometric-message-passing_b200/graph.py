@@ -65,7 +65,7 @@ def radius_graph(x: torch.Tensor, r: float, batch: Optional[torch.Tensor] = None
         if E:
             call("gmp_radius_graph_fill", ptr(x), ptr(gptr), ngraphs, n, float(r), max_num_neighbors, int(loop),
                  ptr(rowptr), ptr(ei[0]), ptr(ei[1]))
-        ei._gmp_dst_sorted = True   # dst-major, ascending: Graph skips the permutation of the by_dst view
+        _tag_dst_sorted(ei)   # dst-major, ascending: Graph skips the permutation of the by_dst view
         return ei
     assert ngraphs == 1, "the cell-list path handles a single example"
     import ctypes as C
@@ -87,8 +87,19 @@ def radius_graph(x: torch.Tensor, r: float, batch: Optional[torch.Tensor] = None
     if E:
         call("gmp_radius_cells_fill", ptr(x), n, float(r), cell, origin, cdims, ptr(cell_start), ptr(cell_nodes),
              max_num_neighbors, int(loop), ptr(rowptr), ptr(ei[0]), ptr(ei[1]))
-    ei._gmp_dst_sorted = True
+    _tag_dst_sorted(ei)
     return ei
+
+
+def _tag_dst_sorted(ei: torch.Tensor) -> None:
+    """Mark a radius_graph output as grouped by destination in ascending order.  The tag is bound to the tensor's
+    version counter: an in-place edit of the edge list invalidates it."""
+    ei._gmp_dst_sorted = True
+    ei._gmp_dst_sorted_version = ei._version
+
+
+def _is_tagged_dst_sorted(ei: torch.Tensor) -> bool:
+    return bool(getattr(ei, "_gmp_dst_sorted", False)) and getattr(ei, "_gmp_dst_sorted_version", None) == ei._version
 
 
 @dataclass
@@ -159,11 +170,12 @@ class Graph:
 
     def __init__(self, edge_index: torch.Tensor, n: int):
         assert edge_index.dim() == 2 and edge_index.shape[0] == 2 and edge_index.dtype == torch.int64
+        self._orig = edge_index                    # keeps the caller's storage alive while this Graph is cached (see get_graph)
         self.edge_index = edge_index.contiguous()
         self.n = n
         self.E = edge_index.shape[1]
         # radius_graph (ours, like torch_cluster's) emits edges grouped by destination in ascending order and says so
-        self._dst_sorted = bool(getattr(edge_index, "_gmp_dst_sorted", False))
+        self._dst_sorted = _is_tagged_dst_sorted(edge_index)
         self._by_dst: Optional[CSR] = None
         self._by_src: Optional[CSR] = None
 
@@ -185,10 +197,11 @@ _GRAPH_CACHE_SIZE = 4  # a training step touches one or two graphs; a small cach
 
 
 def get_graph(edge_index: torch.Tensor, n: int) -> Graph:
-    """Graph for this edge_index, cached on (storage pointer, shape, version, n) so that the layers of a
-    model, which all receive the same tensor, sort it once.  The cache keeps the tensor alive, so the pointer
-    cannot be recycled for a different edge list while its entry exists."""
-    key = (edge_index.data_ptr(), tuple(edge_index.shape), edge_index._version, n, str(edge_index.device))
+    """Graph for this edge_index, cached on (storage pointer, shape, strides, version, n) so that the layers of a
+    model, which all receive the same tensor, sort it once.  The cached Graph holds a reference to the caller's tensor
+    itself (not only to a contiguous copy of it), so its storage cannot be freed and recycled for a different edge list
+    while the entry exists."""
+    key = (edge_index.data_ptr(), tuple(edge_index.shape), tuple(edge_index.stride()), edge_index._version, n, str(edge_index.device))
     g = _GRAPH_CACHE.get(key)
     if g is None:
         while len(_GRAPH_CACHE) >= _GRAPH_CACHE_SIZE:

@@ -28,6 +28,7 @@ class GraphedStep:
                  rebuild_graph: bool = False):
         assert all(t.is_cuda for t in _tensors(batch).values()), "GraphedStep needs a device-resident (static) batch"
         self.model, self.batch = model, batch
+        self.rebuild_graph = rebuild_graph
         self.loss = loss or (lambda out: out.sum())
         self.params = [p for p in model.parameters() if p.requires_grad]
         # (the parameters' AccumulateGrad nodes may have been created by earlier eager steps on the default stream; autograd
@@ -55,8 +56,15 @@ class GraphedStep:
             p.grad = None                      # the captured backward then allocates the gradients in the graph's pool
         if rebuild_graph:                      # new version counter -> the CSR cache misses -> the sort is captured too
             batch.edge_index.add_(0)
+            # load() may later put ANY edge list into this buffer: the captured CSR build must not rely on the capture-time
+            # tensor having been dst-sorted (a radius_graph output says so through this attribute), so the permutation of the
+            # by_dst view is always built inside the graph
+            batch.edge_index._gmp_dst_sorted = False
         k0, c0 = _lib.kernel_launches(), _lib.launches
-        self.graph = torch.cuda.CUDAGraph()
+        try:
+            self.graph = torch.cuda.CUDAGraph(keep_graph=True)   # keeps the cudaGraph_t: kernel_nodes() counts its nodes
+        except TypeError:
+            self.graph = torch.cuda.CUDAGraph()
         try:
             with torch.cuda.graph(self.graph):
                 self.out = model(batch)
@@ -77,11 +85,44 @@ class GraphedStep:
         return out
 
     def load(self, host_batch) -> None:
-        """Overwrite the static batch with a host batch of the same shapes (pinned memory makes the copies asynchronous)."""
+        """Overwrite the static batch with a host batch of the same shapes (pinned memory makes the copies asynchronous).
+
+        rebuild_graph=True: every field is replaced, edge_index included -- the replay re-sorts it.
+        rebuild_graph=False: the replay runs against the CSR views built before capture, so the edge list is part of the
+        captured state: node fields (atoms, pos, batch, ...) are replaced, `edge_index` is left alone, and a host batch
+        that carries a different edge list raises (the comparison reads one flag back; pass a batch without `edge_index`
+        to skip it)."""
         for k, dst in _tensors(self.batch).items():
-            src = getattr(host_batch, k)
+            src = getattr(host_batch, k, None)
+            if k == "edge_index" and not self.rebuild_graph:
+                if src is not None and src is not dst:
+                    same = src.shape == dst.shape and bool(torch.equal(src.to(dst.device), dst))
+                    if not same:
+                        raise ValueError("GraphedStep.load: this step was captured with rebuild_graph=False, i.e. for one fixed edge "
+                                         "list; build it with rebuild_graph=True to load batches with other edges")
+                continue
+            assert src is not None, f"GraphedStep.load: the host batch has no field {k!r}"
             assert src.shape == dst.shape and src.dtype == dst.dtype, f"GraphedStep.load: {k} changed shape or dtype"
             dst.copy_(src, non_blocking=True)
+
+    def kernel_nodes(self):
+        """Number of kernel nodes of the captured graph (ours + ATen + cuBLAS), counted from the graph itself with
+        cudaGraphGetNodes / cudaGraphNodeGetType; None when the handle or the CUDA bindings are unavailable."""
+        try:
+            from cuda.bindings import runtime as rt
+            raw = self.graph.raw_cuda_graph()
+            err, _, num = rt.cudaGraphGetNodes(raw, 0)
+            if int(err) != 0:
+                return None
+            err, nodes, num = rt.cudaGraphGetNodes(raw, num)
+            kernels = 0
+            for nd in nodes[:num]:
+                err, ty = rt.cudaGraphNodeGetType(nd)
+                if int(err) == 0 and int(ty) == int(rt.cudaGraphNodeType.cudaGraphNodeTypeKernel):
+                    kernels += 1
+            return kernels
+        except Exception:  # noqa: BLE001
+            return None
 
     def replay(self) -> torch.Tensor:
         self.graph.replay()

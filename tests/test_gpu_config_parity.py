@@ -1,0 +1,194 @@
+"""GPU parity at the BASELINE.json sizes ("no parity check at any BASELINE size except config 1").
+
+The GPU side runs the bench batch itself (bench.synth / synth_clouds / synth_cube: the generators bench.py times); the
+oracle runs the part of it that it can hold in host memory, which is exact because of how the workloads decompose:
+
+* configs 2, 3: graphs are independent, so rows of the model output that belong to the first k graphs depend on those
+  graphs only.  The whole batch goes through the GPU model, the cotangent is non-zero on the first k graphs only, and the
+  oracle model is run on those k graphs: outputs, parameter gradients (and position gradients for SchNet) must agree.
+  k = 64 molecules for SchNet (1 KB of oracle state per edge and layer); k = 4 clouds for TFN (the oracle materialises
+  fc(edge_feat) = 272 KB per edge and layer).
+* config 4 (MACE): e3nn BatchNorm (the model default, models/mace.py:35) couples the graphs of a batch in training
+  mode, so both sides run the same 2-cloud subset of the bench batch (704 KB of oracle state per edge and layer).
+* config 5: one EGNN layer on a 2^18-node cube of the bench geometry -- the launch shape the bench times per layer.  The
+  cotangent is non-zero on 4096 sampled destination rows (plus the last row); the oracle layer is evaluated on the
+  sub-edge-list that ends in those rows (all 2^18 nodes are present as sources), which gives the exact outputs of the
+  sampled rows and the exact gradients of that loss w.r.t. h, pos and every parameter.
+
+Tolerances, normwise relative, stated per config:  fp32-strict 1e-5 per layer (x number of layers through a model);
+bf16 (tcgen05) 1e-2 per layer -- whole models: 1e-2 on the output, 2e-2 on gradients through 4-6 layers; EGNN ReLU
+gradients: within RELU_SENS_FACTOR x the oracle's own bf16-input sensitivity (tests/test_gpu_tc.py)."""
+import pytest
+import torch
+
+import bench
+from oracle import ref_layers as R
+from tests.helpers import Bag, rel_err
+
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(600)]
+
+
+def _l2_rel(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+def _load_same_state(mine, ref):
+    own = dict(mine.named_parameters())
+    state = ref.state_dict()
+    missing = [k for k in own if k not in state]
+    assert not missing, missing
+    mine.load_state_dict(state, strict=False)
+
+
+def _model_subset_parity(which, k_graphs, nodes_per_graph, precision, synth_fn, radius, max_nb, tol_out, tol_grad,
+                         full_batch=True, pos_grad=False, randomize_1d=0.0):
+    """Whole model: GPU on the bench batch (or the same subset when full_batch=False), oracle on the first k graphs."""
+    import gmp_b200
+    from oracle.thirdparty import cluster
+    gmp_b200.set_fast_matmul(precision == "bf16")
+    try:
+        atoms, pos, batch = synth_fn()
+        n_sub = k_graphs * nodes_per_graph
+        torch.manual_seed(0)
+        ref = bench.make_oracle_model(which)
+        if randomize_1d:
+            with torch.no_grad():
+                for p_ in ref.parameters():
+                    if p_.dim() == 1:
+                        p_.add_(randomize_1d * torch.randn_like(p_))
+        ref.train()
+        a_s, p_s, b_s = atoms[:n_sub], pos[:n_sub].clone().requires_grad_(pos_grad), batch[:n_sub]
+        ei_s = torch.from_numpy(cluster.radius_graph(pos[:n_sub].numpy(), radius, b_s.numpy(), False, max_nb))
+        out_ref = ref(Bag(atoms=a_s, pos=p_s, edge_index=ei_s, batch=b_s))
+        cot = torch.randn(out_ref.shape, generator=torch.Generator().manual_seed(11))
+        names = [k for k, _ in ref.named_parameters()]
+        wrt = list(ref.parameters()) + ([p_s] if pos_grad else [])
+        g_ref = torch.autograd.grad((out_ref * cot).sum(), wrt, allow_unused=True)
+
+        mine = bench.make_model(which, precision)
+        _load_same_state(mine, ref)
+        mine = mine.cuda().train()
+        assert [k for k, _ in mine.named_parameters()] == names
+        if not full_batch:
+            atoms, pos, batch = atoms[:n_sub], pos[:n_sub], batch[:n_sub]
+        graphs = int(batch[-1]) + 1
+        pos_c = pos.cuda().requires_grad_(pos_grad)
+        batch_c = batch.cuda()
+        ei = gmp_b200.radius_graph(pos.cuda(), radius, batch_c, max_num_neighbors=max_nb)
+        n_edges_sub = int((ei[1] < n_sub).sum())
+        assert torch.equal(ei[:, :n_edges_sub].cpu(), ei_s)          # bit-exact graph of the subset inside the batch
+        out = mine(Bag(atoms=atoms.cuda(), pos=pos_c, edge_index=ei, batch=batch_c, num_graphs=graphs))
+        assert out.shape[0] == graphs
+        e_out = rel_err(out[:k_graphs], out_ref)
+        cot_full = torch.zeros(out.shape, device="cuda")
+        cot_full[:k_graphs] = cot.cuda()
+        g = torch.autograd.grad((out * cot_full).sum(), list(mine.parameters()) + ([pos_c] if pos_grad else []), allow_unused=True)
+        errs = {}
+        for name, a, b_ in zip(names + (["pos"] if pos_grad else []), g, g_ref):
+            if b_ is None or float(b_.abs().max()) == 0.0:
+                assert a is None or float(a.abs().max()) <= 1e-12, name
+                continue
+            if name == "pos":
+                assert float(a[n_sub:].abs().max()) == 0.0 if a.shape[0] > n_sub else True
+                a = a[:n_sub]
+            errs[name] = rel_err(a, b_)
+        worst = max(errs, key=errs.get)
+        print(f"\\n[{which} {precision}] graphs={graphs} (oracle: {k_graphs}), E={ei.shape[1]}  out {e_out:.2e}  worst grad {worst} {errs[worst]:.2e}")
+        assert e_out <= tol_out, e_out
+        assert errs[worst] <= tol_grad, (worst, errs[worst])
+    finally:
+        gmp_b200.set_fast_matmul(False)
+
+
+@pytest.mark.parametrize("precision,tol_out,tol_grad", [("fp32", 5e-5, 1e-4), ("bf16", 1e-2, 2e-2)])
+def test_config2_schnet_bench_batch_vs_oracle(precision, tol_out, tol_grad):
+    """BASELINE.json configs[1]: the 4096-molecule bench batch through SchNetModel (6 interactions), 64 molecules of it
+    through the oracle (models/schnet.py:62-80).  fp32-strict: 1e-5 per layer -> 5e-5 / 1e-4 through 6 residual layers;
+    bf16: 1e-2 on the output, 2e-2 on gradients (per-layer 1e-2 is asserted in tests/test_gpu_tc.py)."""
+    c = bench.CFG
+    _model_subset_parity("schnet", 64, c["atoms"], precision, lambda: bench.synth(c["molecules"], 0), c["cutoff"],
+                         c["max_num_neighbors"], tol_out, tol_grad, pos_grad=True)
+
+
+@pytest.mark.parametrize("precision,tol_out,tol_grad", [("fp32", 5e-5, 2e-4), ("bf16", 1e-2, 2e-2)])
+def test_config3_tfn_bench_batch_vs_oracle(precision, tol_out, tol_grad):
+    """BASELINE.json configs[2]: TFN 4 layers C = 64 on the bench clouds (the fp32-strict kernels are FFMA-bound, so that
+    mode runs 64 clouds of the batch; bf16 runs all 2048); 4 clouds through the oracle (models/tfn.py:166-190)."""
+    clouds = bench.CLOUDS["tfn"]["clouds"] if precision == "bf16" else 64
+
+    def synth():
+        a, p, b = bench.synth_clouds(bench.CLOUDS["tfn"]["clouds"], 0)
+        return a[:clouds * 64], p[:clouds * 64], b[:clouds * 64]
+    _model_subset_parity("tfn", 4, 64, precision, synth, 2.0, 64, tol_out, tol_grad)
+
+
+@pytest.mark.parametrize("precision,tol_out,tol_grad", [("fp32", 5e-5, 2e-4), ("bf16", 1e-2, 2e-2)])
+def test_config4_mace_bench_clouds_vs_oracle(precision, tol_out, tol_grad):
+    """BASELINE.json configs[3]: MACE 2 interactions C = 128, correlation 3, e3nn BatchNorm in training mode; the first 2
+    clouds of the bench batch on both sides (models/mace.py:165-190)."""
+    _model_subset_parity("mace", 2, 64, precision, lambda: bench.synth_clouds(bench.CLOUDS["mace"]["clouds"], 0), 2.0, 64,
+                         tol_out, tol_grad, full_batch=False)
+
+
+@pytest.mark.parametrize("precision,act", [("fp32", "relu"), ("bf16", "swish"), ("bf16", "relu")])
+def test_config5_egnn_layer_2p18_cube_vs_oracle(precision, act):
+    """BASELINE.json configs[4] geometry at 2^18 nodes (E ~ 8.5 M): one EGNN layer forward + backward on the whole graph;
+    the oracle (models/layers/egnn_layer.py:50-86) on the sub-edge-list ending in 4096 sampled rows (+ the last row)."""
+    import gmp_b200
+    from tests.test_gpu_tc import RELU_SENS_FACTOR
+    gmp_b200.set_fast_matmul(False)
+    pos = bench.synth_cube(18)
+    n = pos.shape[0]
+    ei = gmp_b200.radius_graph(pos.cuda(), 1.0, None, max_num_neighbors=128)
+    E = ei.shape[1]
+    assert 7.5e6 < E < 9.5e6
+    g = torch.Generator().manual_seed(18)
+    rows = torch.cat([torch.randperm(n, generator=g)[:4096], torch.tensor([n - 1])]).unique()
+    sel = torch.zeros(n, dtype=torch.bool)
+    sel[rows] = True
+    ei_cpu = ei.cpu()
+    ei_sub = ei_cpu[:, sel[ei_cpu[1]]].contiguous()
+    assert int(ei_sub[1].max()) == n - 1     # the reference's scatter has no dim_size
+    torch.manual_seed(1)
+    ref = R.EGNNLayer(128, act, "layer", "add")
+    with torch.no_grad():
+        for p_ in ref.parameters():
+            if p_.dim() == 1:
+                p_.add_(0.2 * torch.randn_like(p_))
+    h = torch.randn(n, 128, generator=g)
+    c1, c2 = torch.zeros(n, 128), torch.zeros(n, 3)
+    c1[rows], c2[rows] = torch.randn(rows.numel(), 128, generator=g), torch.randn(rows.numel(), 3, generator=g)
+
+    def oracle(hh):
+        hr, pr = hh.clone().requires_grad_(True), pos.clone().requires_grad_(True)
+        o, q = ref(hr, pr, ei_sub)
+        gs = torch.autograd.grad((o * c1).sum() + (q * c2).sum(), [hr, pr] + list(ref.parameters()))
+        return o.detach(), q.detach(), gs
+
+    o_ref, q_ref, g_ref = oracle(h)
+    names = ["h", "pos"] + [k for k, _ in ref.named_parameters()]
+
+    mine = gmp_b200.EGNNLayer(128, activation=act, aggr="add", precision=precision)
+    mine.load_state_dict(ref.state_dict())
+    mine = mine.cuda()
+    hc, pc = h.cuda().requires_grad_(True), pos.cuda().requires_grad_(True)
+    o, q = mine(hc, pc, ei)
+    tol = 1e-5 if precision == "fp32" else 1e-2
+    e_o, e_q = rel_err(o[rows.cuda()], o_ref[rows]), rel_err((q - pc)[rows.cuda()], (q_ref - pos)[rows])
+    gm = torch.autograd.grad((o * c1.cuda()).sum() + (q * c2.cuda()).sum(), [hc, pc] + list(mine.parameters()))
+    errs = {k: (rel_err(a, b_), _l2_rel(a, b_)) for k, a, b_ in zip(names, gm, g_ref)}
+    worst = max(errs, key=lambda k: errs[k][0])
+    print(f"\\n[egnn 2^18 {precision} {act}] E={E} rows={rows.numel()} out {e_o:.2e} pos {e_q:.2e} worst grad {worst} max {errs[worst][0]:.2e} l2 {errs[worst][1]:.2e}")
+    assert e_o <= tol and e_q <= tol, (e_o, e_q)
+    if precision == "fp32":
+        for k, (e_max, _) in errs.items():
+            assert e_max <= 5e-5, (k, e_max)
+    elif act == "swish":
+        for k, (e_max, _) in errs.items():
+            assert e_max <= 1e-2, (k, e_max)
+    else:
+        _, _, g_probe = oracle(h.bfloat16().float())     # the oracle's own movement under bf16-rounded inputs
+        for k, b_, pr in zip(names, g_ref, g_probe):
+            s_k = _l2_rel(pr, b_)
+            assert errs[k][1] <= max(1e-2, RELU_SENS_FACTOR * s_k), (k, errs[k], s_k)

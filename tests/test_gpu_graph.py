@@ -73,6 +73,42 @@ def test_csr_stable_sort_bit_exact(E, n, seed):
     assert np.all(np.diff(idx.numpy()[got_perm]) >= 0) and np.array_equal(np.sort(got_perm), np.arange(E))
 
 
+@pytest.mark.parametrize("E,n,hot", [(1_000_000, 1, 1.0), (300_000, 7, 0.0), (1_200_000, 5000, 0.5), (70_000, 3, 0.9)])
+def test_csr_stable_sort_long_rows(E, n, hot):
+    """Rows far longer than a warp's rank sort can handle (pooling one large graph puts every node into one
+    row): the block-wide radix sort of csrc/graph.cu.  `hot` = fraction of the edges that land in row 0; the rest is
+    spread uniformly, so short and long rows mix.  Bit-exact against the numpy stable sort; must finish in seconds."""
+    import time
+    import gmp_b200
+    g = torch.Generator().manual_seed(E % 977)
+    idx = torch.randint(0, n, (E,), generator=g)
+    idx[torch.rand(E, generator=g) < hot] = 0
+    other = torch.randint(0, 1000, (E,), generator=g)
+    rowptr, perm = cluster.csr_from_coo(idx.numpy(), n)
+    ic, oc = idx.cuda(), other.cuda()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    csr = gmp_b200.build_csr(ic, oc, n)
+    torch.cuda.synchronize()
+    assert time.perf_counter() - t0 < 5.0
+    assert np.array_equal(csr.rowptr.cpu().numpy(), rowptr)
+    assert np.array_equal(csr.perm.cpu().numpy(), perm)
+    assert np.array_equal(csr.col.cpu().numpy(), other.numpy()[perm].astype(np.int32))
+
+
+def test_global_pool_single_large_graph():
+    """global_add_pool / global_mean_pool over one graph of 2^20 nodes (config-5 shape through EGNNModel's read-out)."""
+    import gmp_b200
+    n = 1 << 20
+    x = torch.randn(n, 16, generator=torch.Generator().manual_seed(3)).cuda()
+    batch = torch.zeros(n, dtype=torch.long, device="cuda")
+    s = gmp_b200.global_add_pool(x, batch, 1)
+    m = gmp_b200.global_mean_pool(x, batch, 1)
+    ref = x.double().sum(0, keepdim=True)
+    assert (s.double() - ref).abs().max() <= 1e-5 * ref.abs().max().clamp_min(1.0) * 40
+    assert (m.double() - ref / n).abs().max() <= 1e-6
+
+
 def test_csr_sorted_input_is_identity():
     import gmp_b200
     pos = _cloud(256, 4.0, 5).cuda()

@@ -178,6 +178,8 @@ def test_graphed_step_matches_eager(precision):
 
     gs = gmp_b200.GraphedStep(model, b1.to("cuda"), warmup=2)                       # resident batch
     assert gs.kernels_per_replay > 0
+    kn = gs.kernel_nodes()     # counted from the captured cudaGraph_t itself: ours + ATen + cuBLAS
+    assert kn is None or kn >= gs.kernels_per_replay
     for _ in range(2):
         assert torch.equal(gs.replay(), out1)
         assert all(torch.equal(a, b) for a, b in zip(gs.grads, g1))
@@ -196,3 +198,37 @@ def test_graphed_step_matches_eager(precision):
         out = gs.replay()
         assert torch.equal(out, out_ref)
         assert all(torch.equal(a, b) for a, b in zip(gs.grads, g_ref))
+
+
+def test_graphed_step_load_guards_the_edge_list():
+    """a step captured for one fixed edge list (rebuild_graph=False) must not silently accept another one; with
+    rebuild_graph=True a non-dst-sorted edge list loaded into a buffer that came from radius_graph must give the same
+    result as the eager model (the captured CSR build may not trust the capture-time sortedness tag)."""
+    import gmp_b200
+    d = random_clouds(6, 20, 8.0, 5.0, 321, max_nb=32, atoms_hi=10)
+    n = d["pos"].shape[0]
+    torch.manual_seed(0)
+    model = gmp_b200.SchNetModel(hidden_channels=128, num_filters=128, num_layers=2, num_gaussians=50, cutoff=5.0).cuda()
+    ei = gmp_b200.radius_graph(d["pos"].cuda(), 5.0, d["batch"].cuda(), max_num_neighbors=32)
+    perm = torch.randperm(ei.shape[1], generator=torch.Generator().manual_seed(1)).cuda()
+    shuffled = ei[:, perm].contiguous()
+    mk = lambda e: gmp_b200.Batch(atoms=d["atoms"].cuda(), pos=d["pos"].cuda(), batch=d["batch"].cuda(), edge_index=e, num_graphs=6)
+    fixed = gmp_b200.GraphedStep(model, mk(ei.clone()), warmup=1)
+    with pytest.raises(ValueError):
+        fixed.load(mk(shuffled))
+    fixed.load(mk(ei.clone()))                       # same edges: accepted, node fields refreshed
+    out_fixed = fixed.replay().clone()
+    del fixed
+    static = mk(ei)                                  # the radius_graph output itself (tagged dst-sorted) becomes the static buffer
+    gs = gmp_b200.GraphedStep(model, static, warmup=1, rebuild_graph=True)
+    gs.load(mk(shuffled))
+    out = gs.replay().clone()
+    grads = [g.clone() for g in gs.grads]
+    del gs
+    for p in model.parameters():
+        p.grad = None
+    ref = model(mk(shuffled))
+    ref.sum().backward()
+    assert rel_err(out, ref) <= 1e-5 and rel_err(out_fixed, ref) <= 1e-5
+    for g, p in zip(grads, model.parameters()):
+        assert rel_err(g, p.grad) <= 5e-5

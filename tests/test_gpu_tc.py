@@ -1,12 +1,22 @@
-"""GPU: the tcgen05 / TMEM path.  (1) hardware self test of the hand-built UMMA descriptors and 128-byte swizzle;
-(2) the bf16 tensor-core CFConv forward against the fp32-strict kernel: 1e-2 normwise relative, the tolerance
-BASELINE.json states for bf16 MLP inputs."""
+"""GPU: the tcgen05 / TMEM path (precision="bf16", the mode bench.py measures).
+
+(1) hardware self test of the hand-built UMMA descriptors and 128-byte swizzle;
+(2) every bf16 layer against the CPU ORACLE (oracle/ref_layers.py, oracle/thirdparty/pyg.py -- the restatement of
+    the reference pinned by tests/golden/), forward and every gradient, 1e-2 normwise relative: the tolerance
+    BASELINE.json states where bf16 MLP inputs are used.  The repo's own fp32-strict kernels are a second comparison
+    only where that is cheap (they are themselves checked against the oracle at 1e-5 in test_gpu_{egnn,schnet,tfn}.py);
+(3) corner cases of the pipelined kernels (tile cuts, CTA-boundary rows, empty rows, the empty graph)."""
 import ctypes as C
 
 import pytest
 import torch
 
+from oracle import ref_layers as R
+from oracle.thirdparty import o3
+from oracle.thirdparty import pyg as PYG
 from tests.helpers import random_clouds, rel_err
+
+BF16_TOL = 1e-2   # north star: "1e-2 where bf16 MLP inputs are used"
 
 pytestmark = [pytest.mark.gpu, pytest.mark.timeout(120)]
 
@@ -38,64 +48,84 @@ def test_umma_selftest_mn_major(N):
 
 
 @pytest.mark.parametrize("graphs,nodes,lazy", [(64, 32, True), (9, 21, False)])
-def test_cfconv_bf16_tc_vs_fp32(graphs, nodes, lazy):
+def test_cfconv_bf16_tc_vs_oracle(graphs, nodes, lazy):
+    """SchNet InteractionBlock, bf16 tcgen05 kernels vs the oracle's PyG InteractionBlock (called at
+    models/schnet.py:72): output, dL/dx and every parameter gradient within 1e-2."""
     import gmp_b200
     d = random_clouds(graphs, nodes, 8.0, 5.0, 500 + graphs, max_nb=32)
-    ei, pos = d["edge_index"].cuda(), d["pos"].cuda()
+    ei, pos = d["edge_index"], d["pos"]
     torch.manual_seed(0)
-    m32 = gmp_b200.InteractionBlock(128, 50, 128, 5.0).cuda()
+    ref = PYG.InteractionBlock(128, 50, 128, 5.0)
     with torch.no_grad():
-        for p in m32.parameters():
+        for p in ref.parameters():
             if p.dim() == 1:
                 p.normal_(0, 0.3)
-    m16 = gmp_b200.InteractionBlock(128, 50, 128, 5.0, precision="bf16").cuda()
-    m16.load_state_dict(m32.state_dict())
-    sm = gmp_b200.GaussianSmearing(0.0, 5.0, 50).cuda()
-    x = torch.randn(pos.shape[0], 128, device="cuda")
+    x = torch.randn(pos.shape[0], 128)
     ew = (pos[ei[0]] - pos[ei[1]]).norm(dim=-1)
-    attr = sm.lazy() if lazy else sm(ew)
-    x32, x16 = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
-    o32, o16 = m32(x32, ei, ew, attr), m16(x16, ei, ew, attr)
-    assert rel_err(o16, o32) <= 1e-2
-    cot = torch.randn_like(o32)
-    g32 = torch.autograd.grad((o32 * cot).sum(), [x32] + list(m32.parameters()))
-    g16 = torch.autograd.grad((o16 * cot).sum(), [x16] + list(m16.parameters()))
-    for a, b in zip(g16, g32):
-        assert rel_err(a, b) <= 1e-2
+    xr = x.clone().requires_grad_(True)
+    o_ref = ref(xr, ei, ew, PYG.GaussianSmearing(0.0, 5.0, 50)(ew))
+    cot = torch.randn_like(o_ref)
+    names = ["x"] + [k for k, _ in ref.named_parameters()]
+    g_ref = torch.autograd.grad((o_ref * cot).sum(), [xr] + list(ref.parameters()))
+
+    m16 = gmp_b200.InteractionBlock(128, 50, 128, 5.0, precision="bf16")
+    m16.load_state_dict(ref.state_dict())
+    m16 = m16.cuda()
+    assert [k for k, _ in m16.named_parameters()] == names[1:]
+    sm = gmp_b200.GaussianSmearing(0.0, 5.0, 50).cuda()
+    eic, ewc = ei.cuda(), ew.cuda()
+    attr = sm.lazy() if lazy else sm(ewc)
+    x16 = x.cuda().requires_grad_(True)
+    o16 = m16(x16, eic, ewc, attr)
+    assert rel_err(o16, o_ref) <= BF16_TOL
+    g16 = torch.autograd.grad((o16 * cot.cuda()).sum(), [x16] + list(m16.parameters()))
+    for a, b, k in zip(g16, g_ref, names):
+        assert rel_err(a, b) <= BF16_TOL, k
     # deterministic
-    assert torch.equal(o16, m16(x16, ei, ew, attr))
+    assert torch.equal(o16, m16(x16, eic, ewc, attr))
 
 
 @pytest.mark.parametrize("C,gate,graphs,nodes,shuffle,mlp", [(64, True, 6, 24, True, 256), (16, False, 3, 12, False, 64),
-                                                            (128, False, 40, 16, False, 256)])
-def test_tp_conv_bf16_tc_vs_fp32(C, gate, graphs, nodes, shuffle, mlp):
-    """TFN / MACE tensor-product convolution: tcgen05 path (bf16 operands of fc's second Linear, bf16 factor) against
-    the fp32-strict kernels, forward, d/d node_attr and parameter gradients: 1e-2 normwise relative."""
+                                                            (128, False, 4, 16, False, 256)])
+def test_tp_conv_bf16_tc_vs_oracle(C, gate, graphs, nodes, shuffle, mlp):
+    """TFN / MACE tensor-product convolution (models/layers/tfn_layer.py:82-93): tcgen05 path (bf16 operands of fc's
+    second Linear, bf16 factor) against the oracle layer (e3nn FullyConnectedTensorProduct restated):
+    forward, d/d node_attr and all four parameter gradients of fc within 1e-2 normwise relative."""
     import gmp_b200
     d = random_clouds(graphs, nodes, 3.0, 1.9, 700 + C)
     ei, pos = d["edge_index"], d["pos"]
     if shuffle:
         ei = ei[:, torch.randperm(ei.shape[1], generator=torch.Generator().manual_seed(1))]
-    ei, pos = ei.cuda(), pos.cuda()
+    n = pos.shape[0]
+    assert int(ei[0].max()) == n - 1    # the reference omits dim_size (SURVEY A.1): keep the last node connected
     hid, sh_ir = f"{C}x0e+{C}x1o+{C}x2e", "1x0e+1x1o+1x2e"
     torch.manual_seed(C)
-    m32 = gmp_b200.TensorProductConvLayer(hid, hid, sh_ir, 8, mlp, gate=gate).cuda()
+    ref = R.TensorProductConvLayer(hid, hid, sh_ir, 8, mlp, gate=gate)
     with torch.no_grad():
-        m32.fc[2].bias.normal_(0, 0.05)
-    m16 = gmp_b200.TensorProductConvLayer(hid, hid, sh_ir, 8, mlp, gate=gate, precision="bf16").cuda()
-    m16.load_state_dict(m32.state_dict())
-    esh, eft = gmp_b200.edge_geometry(pos, ei, 2, gmp_b200.RadialEmbeddingBlock(2.0, 8, 5))
-    x = torch.randn(pos.shape[0], 9 * C, device="cuda")
-    x32, x16 = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
-    o32, o16 = m32(x32, ei, esh, eft), m16(x16, ei, esh, eft)
+        ref.fc[2].bias.normal_(0, 0.05)
+    shm = o3.SphericalHarmonics(o3.Irreps(sh_ir), True, "component")
+    esh, eft = R.edge_geometry(pos, ei, shm, R.RadialEmbeddingBlock(2.0, 8, 5))
+    x = torch.randn(n, 9 * C, generator=torch.Generator().manual_seed(2))
+    xr = x.clone().requires_grad_(True)
+    o_ref = ref(xr, ei, esh, eft)
+    cot = torch.randn(o_ref.shape, generator=torch.Generator().manual_seed(3))
+    g_ref = torch.autograd.grad((o_ref * cot).sum(), [xr] + list(ref.parameters()))
+    names = ["node_attr"] + [k for k, _ in ref.named_parameters()]
+
+    m16 = gmp_b200.TensorProductConvLayer(hid, hid, sh_ir, 8, mlp, gate=gate, precision="bf16")
+    m16.load_state_dict(ref.state_dict(), strict=False)
+    m16 = m16.cuda()
+    assert [k for k, _ in m16.named_parameters()] == names[1:]
+    eic = ei.cuda()
+    esh_c, eft_c = gmp_b200.edge_geometry(pos.cuda(), eic, 2, gmp_b200.RadialEmbeddingBlock(2.0, 8, 5))
+    x16 = x.cuda().requires_grad_(True)
+    o16 = m16(x16, eic, esh_c, eft_c)
     torch.cuda.synchronize()
-    assert rel_err(o16, o32) <= 1e-2
-    cot = torch.randn_like(o32)
-    g32 = torch.autograd.grad((o32 * cot).sum(), [x32] + list(m32.parameters()))
-    g16 = torch.autograd.grad((o16 * cot).sum(), [x16] + list(m16.parameters()))
-    for a, b, name in zip(g16, g32, ["node_attr"] + [k for k, _ in m32.named_parameters()]):
-        assert rel_err(a, b) <= 1e-2, name
-    assert torch.equal(o16, m16(x16, ei, esh, eft))  # deterministic
+    assert rel_err(o16, o_ref) <= BF16_TOL
+    g16 = torch.autograd.grad((o16 * cot.cuda()).sum(), [x16] + list(m16.parameters()))
+    for a, b, name in zip(g16, g_ref, names):
+        assert rel_err(a, b) <= BF16_TOL, name
+    assert torch.equal(o16, m16(x16, eic, esh_c, eft_c))  # deterministic
 
 
 def _l2_rel(a, b):
@@ -103,53 +133,80 @@ def _l2_rel(a, b):
     return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
 
 
+def _egnn_oracle_run(ref, h, pos, ei, c1, c2):
+    hr, pr = h.clone().requires_grad_(True), pos.clone().requires_grad_(True)
+    o, q = ref(hr, pr, ei)
+    gs = torch.autograd.grad((o * c1).sum() + (q * c2).sum(), [hr, pr] + list(ref.parameters()))
+    return o.detach(), q.detach(), gs
+
+
+RELU_SENS_FACTOR = 3.0   # the kernel rounds three operands per edge (Q row, a1, m) where the probe below rounds one (h)
+
+
 @pytest.mark.parametrize("act,aggr,n,side,fused", [("swish", "mean", 1000, 5.0, True), ("swish", "add", 3000, 7.0, True),
-                                                   ("swish", "add", 3000, 7.0, False), ("relu", "add", 3000, 7.0, True)])
-def test_egnn_bf16_tc_vs_fp32(act, aggr, n, side, fused, monkeypatch):
-    """EGNN layer, tcgen05 edge kernels (forward; single-pass backward with per-edge scratch, or the two recompute
-    passes) against the fp32-strict kernels.
-    Smooth activation: every output and gradient within 1e-2 (normwise, max).  ReLU: the forward holds 1e-2; its
-    gradients are compared in the L2 norm with a 0.1 bound, because a bf16-level perturbation of a pre-activation that
-    sits at the kink flips that unit's derivative -- the fp32 reference shows the same sensitivity (mlp_upd, a pure
-    fp32 torch path, moves by 2-3e-2 when its input moves by 2e-3)."""
+                                                   ("swish", "add", 3000, 7.0, False), ("relu", "add", 3000, 7.0, True),
+                                                   ("relu", "add", 3000, 7.0, False)])
+def test_egnn_bf16_tc_vs_oracle(act, aggr, n, side, fused, monkeypatch):
+    """EGNN layer (models/layers/egnn_layer.py:50-86), tcgen05 edge kernels (forward; single-pass backward with per-edge
+    scratch, or the two recompute passes) against the ORACLE layer on a radius graph at config 5's density.
+
+    Outputs: 1e-2 for both activations.  Gradients, smooth activation: every one within 1e-2.  Gradients, ReLU (the
+    reference default): the reference function itself is not 1e-2-stable under bf16-level input changes -- a
+    pre-activation sitting within 2^-9 of the kink flips that unit's derivative.  The bound is therefore measured, not
+    assumed: the oracle is run a second time with h rounded to bf16 (one rounding, relative 2^-9, exactly what "bf16 MLP
+    inputs" means) and its own fp32 gradients move by s_k (L2 relative, per tensor; ~3e-2 here, against ~1e-3 with
+    SiLU, tests/test_oracle_sensitivity.py).  The kernel must stay within RELU_SENS_FACTOR * s_k of the oracle (it
+    rounds three operands per edge, not one), and within 1e-2 where s_k is small."""
     import gmp_b200
+    from oracle.thirdparty import cluster
     if not fused:   # force the two-pass (recompute) backward that runs when the per-edge scratch would not fit
         monkeypatch.setattr(gmp_b200.egnn, "_FUSED_BWD_SCRATCH_BYTES", 0)
     g = torch.Generator().manual_seed(n)
-    pos = (torch.rand(n, 3, generator=g) * side).cuda()
-    ei = gmp_b200.radius_graph(pos, 1.0, None, max_num_neighbors=128)
+    pos = torch.rand(n, 3, generator=g) * side
+    ei = torch.from_numpy(cluster.radius_graph(pos.numpy(), 1.0, None, False, 128))
+    ei_c = gmp_b200.radius_graph(pos.cuda(), 1.0, None, max_num_neighbors=128)
+    assert torch.equal(ei_c.cpu(), ei)
     torch.manual_seed(1)
-    m32 = gmp_b200.EGNNLayer(128, activation=act, aggr=aggr).cuda()
+    ref = R.EGNNLayer(128, act, "layer", aggr)
     with torch.no_grad():
-        for p in m32.parameters():
+        for p in ref.parameters():
             if p.dim() == 1:
                 p.add_(torch.randn_like(p) * 0.2)
-    m16 = gmp_b200.EGNNLayer(128, activation=act, aggr=aggr, precision="bf16").cuda()
-    m16.load_state_dict(m32.state_dict())
-    h = torch.randn(n, 128, device="cuda")
-    h32, h16 = h.clone().requires_grad_(True), h.clone().requires_grad_(True)
-    p32, p16 = pos.clone().requires_grad_(True), pos.clone().requires_grad_(True)
-    o32, q32 = m32(h32, p32, ei)
-    o16, q16 = m16(h16, p16, ei)
-    assert rel_err(o16, o32) <= 1e-2 and rel_err(q16 - pos, q32 - pos) <= 1e-2
-    c1, c2 = torch.randn_like(o32), torch.randn_like(q32)
-    g32 = torch.autograd.grad((o32 * c1).sum() + (q32 * c2).sum(), [h32, p32] + list(m32.parameters()))
-    g16 = torch.autograd.grad((o16 * c1).sum() + (q16 * c2).sum(), [h16, p16] + list(m16.parameters()))
-    names = ["h", "pos"] + [k for k, _ in m32.named_parameters()]
-    for a, b, k in zip(g16, g32, names):
-        if act == "swish":
-            assert rel_err(a, b) <= 1e-2, k
-        else:
-            assert _l2_rel(a, b) <= 0.1, k
-    o16b, q16b = m16(h16, p16, ei)
+    h = torch.randn(n, 128)
+    c1, c2 = torch.randn(n, 128), torch.randn(n, 3)
+    nrows = int(ei[1].max()) + 1      # the reference omits dim_size (SURVEY A.1); isolated tail nodes would shorten its output
+    assert nrows == n
+    o_ref, q_ref, g_ref = _egnn_oracle_run(ref, h, pos, ei, c1, c2)
+    names = ["h", "pos"] + [k for k, _ in ref.named_parameters()]
+
+    m16 = gmp_b200.EGNNLayer(128, activation=act, aggr=aggr, precision="bf16")
+    m16.load_state_dict(ref.state_dict())
+    m16 = m16.cuda()
+    h16, p16 = h.cuda().requires_grad_(True), pos.cuda().requires_grad_(True)
+    o16, q16 = m16(h16, p16, ei_c)
+    assert rel_err(o16, o_ref) <= BF16_TOL and rel_err(q16.cpu() - pos, q_ref - pos) <= BF16_TOL
+    g16 = torch.autograd.grad((o16 * c1.cuda()).sum() + (q16 * c2.cuda()).sum(), [h16, p16] + list(m16.parameters()))
+    if act == "swish":
+        for a, b, k in zip(g16, g_ref, names):
+            assert rel_err(a, b) <= BF16_TOL, k
+    else:
+        _, _, g_probe = _egnn_oracle_run(ref, h.bfloat16().float(), pos, ei, c1, c2)
+        rows = []
+        for a, b, pr, k in zip(g16, g_ref, g_probe, names):
+            s_k = _l2_rel(pr, b)
+            e_k = _l2_rel(a, b)
+            rows.append((k, e_k, s_k))
+        for k, e_k, s_k in rows:
+            assert e_k <= max(BF16_TOL, RELU_SENS_FACTOR * s_k), (k, e_k, s_k, rows)
+    o16b, q16b = m16(h16, p16, ei_c)
     assert torch.equal(o16, o16b) and torch.equal(q16, q16b)  # deterministic
 
 
 @pytest.mark.parametrize("n,deg,shuffle", [(5000, 2, True), (300, 40, False), (70000, 9, True), (64, 0, False)])
 def test_cfconv_pipelined_forward_edge_cases(n, deg, shuffle):
-    """The pipelined three-MMA CFConv forward (csrc/schnet_tc2.cu) against the fp32 kernel on graphs that exercise its
-    corners: low degree (more than 32 destination rows per 128 edges: tiles are cut), isolated nodes (empty rows),
-    rows straddling tile and CTA boundaries (head buffer + fix-up; 70 000 x 9 edges = enough tiles for every SM),
+    """The pipelined three-MMA CFConv forward (csrc/schnet_tc2.cu) against the ORACLE InteractionBlock on graphs that
+    exercise its corners: low degree (more than 32 destination rows per 128 edges: tiles are cut), isolated nodes (empty
+    rows), rows straddling tile and CTA boundaries (head buffer + fix-up; 70 000 x 9 edges = enough tiles for every SM),
     shuffled edge order (perm), high degree (one row spanning tiles), and the empty graph."""
     import gmp_b200
     g = torch.Generator().manual_seed(n + deg)
@@ -158,26 +215,29 @@ def test_cfconv_pipelined_forward_edge_cases(n, deg, shuffle):
     src = torch.randint(0, n, (E,), generator=g)
     if not shuffle:
         dst = dst.sort().values
-    ei = torch.stack([src, dst]).cuda()
+    ei = torch.stack([src, dst])
     torch.manual_seed(0)
-    m32 = gmp_b200.InteractionBlock(128, 50, 128, 5.0).cuda()
+    ref = PYG.InteractionBlock(128, 50, 128, 5.0)
     with torch.no_grad():
-        for p in m32.parameters():
+        for p in ref.parameters():
             if p.dim() == 1:
                 p.normal_(0, 0.3)
-    m16 = gmp_b200.InteractionBlock(128, 50, 128, 5.0, precision="bf16").cuda()
-    m16.load_state_dict(m32.state_dict())
+    m16 = gmp_b200.InteractionBlock(128, 50, 128, 5.0, precision="bf16")
+    m16.load_state_dict(ref.state_dict())
+    m16 = m16.cuda()
     sm = gmp_b200.GaussianSmearing(0.0, 5.0, 50).cuda()
-    x = torch.randn(n, 128, device="cuda")
-    ew = torch.rand(E, generator=g).cuda() * 5.0
-    x32, x16 = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
-    o32, o16 = m32(x32, ei, ew, sm.lazy()), m16(x16, ei, ew, sm.lazy())
-    assert rel_err(o16, o32) <= 1e-2
-    cot = torch.randn_like(o32)
-    (g32,) = torch.autograd.grad((o32 * cot).sum(), [x32])
-    (g16,) = torch.autograd.grad((o16 * cot).sum(), [x16])   # d/dx1 runs the same kernel over the transposed CSR
-    assert rel_err(g16, g32) <= 1e-2
-    assert torch.equal(o16, m16(x16, ei, ew, sm.lazy()))
+    x = torch.randn(n, 128)
+    ew = torch.rand(E, generator=g) * 5.0
+    xr, x16 = x.clone().requires_grad_(True), x.cuda().requires_grad_(True)
+    o_ref = ref(xr, ei, ew, PYG.GaussianSmearing(0.0, 5.0, 50)(ew))
+    eic, ewc = ei.cuda(), ew.cuda()
+    o16 = m16(x16, eic, ewc, sm.lazy())
+    assert rel_err(o16, o_ref) <= BF16_TOL
+    cot = torch.randn_like(o_ref)
+    (g_ref,) = torch.autograd.grad((o_ref * cot).sum(), [xr])
+    (g16,) = torch.autograd.grad((o16 * cot.cuda()).sum(), [x16])   # d/dx1: kept filter values over the transposed CSR
+    assert rel_err(g16, g_ref) <= BF16_TOL
+    assert torch.equal(o16, m16(x16, eic, ewc, sm.lazy()))
 
 
 @pytest.mark.timeout(180)
@@ -236,56 +296,69 @@ def test_tp_conv_bf16_tc_corner_cases(case):
         dst = torch.randint(0, n, (333,), generator=g)
         ei = torch.stack([src, dst])
         irr_in, irr_out = "12x0e+12x1o", "12x0e+12x1o+4x2e"
-    ei = ei.cuda()
     E = ei.shape[1]
     sh_ir = "1x0e+1x1o+1x2e"
     torch.manual_seed(3)
-    m32 = gmp_b200.TensorProductConvLayer(irr_in, irr_out, sh_ir, 8, 64).cuda()
+    ref = R.TensorProductConvLayer(irr_in, irr_out, sh_ir, 8, 64)
     with torch.no_grad():
-        m32.fc[2].bias.normal_(0, 0.1)
-    m16 = gmp_b200.TensorProductConvLayer(irr_in, irr_out, sh_ir, 8, 64, precision="bf16").cuda()
-    m16.load_state_dict(m32.state_dict())
+        ref.fc[2].bias.normal_(0, 0.1)
+    m16 = gmp_b200.TensorProductConvLayer(irr_in, irr_out, sh_ir, 8, 64, precision="bf16")
+    m16.load_state_dict(ref.state_dict(), strict=False)
+    m16 = m16.cuda()
     vec = torch.randn(E, 3, generator=g)
-    esh = gmp_b200.SphericalHarmonics(2)(vec).cuda()
-    eft = torch.rand(E, 8, generator=g).cuda()
-    x = torch.randn(n, m32.in_irreps.dim, generator=g).cuda()
-    x32, x16 = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
-    o32, o16 = m32(x32, ei, esh, eft), m16(x16, ei, esh, eft)
-    assert o16.shape == o32.shape
+    esh = o3.SphericalHarmonics(o3.Irreps(sh_ir), True, "component")(vec)
+    assert rel_err(gmp_b200.SphericalHarmonics(2)(vec), esh) <= 2e-6
+    eft = torch.rand(E, 8, generator=g)
+    x = torch.randn(n, ref.in_irreps.dim, generator=g)
+    xr, x16 = x.clone().requires_grad_(True), x.cuda().requires_grad_(True)
+    o_short = ref(xr, ei, esh, eft)     # the reference's scatter has no dim_size: rows = max index + 1
+    o_ref = torch.cat([o_short, o_short.new_zeros(n - o_short.shape[0], o_short.shape[1])])
+    o16 = m16(x16, ei.cuda(), esh.cuda(), eft.cuda())
+    assert o16.shape == o_ref.shape
     if E == 0:
         assert float(o16.detach().abs().max()) == 0.0
     else:
-        assert rel_err(o16, o32) <= 1e-2
-    cot = torch.randn_like(o32)
-    g32 = torch.autograd.grad((o32 * cot).sum(), [x32] + list(m32.parameters()), allow_unused=True)
-    g16 = torch.autograd.grad((o16 * cot).sum(), [x16] + list(m16.parameters()), allow_unused=True)
-    for a, b in zip(g16, g32):
+        assert rel_err(o16, o_ref) <= BF16_TOL
+    cot = torch.randn_like(o_ref)
+    g_ref = torch.autograd.grad((o_ref * cot).sum(), [xr] + list(ref.parameters()), allow_unused=True)
+    g16 = torch.autograd.grad((o16 * cot.cuda()).sum(), [x16] + list(m16.parameters()), allow_unused=True)
+    for a, b in zip(g16, g_ref):
         if b is None or float(b.abs().max()) == 0.0:
             assert a is None or float(a.abs().max()) == 0.0
         else:
-            assert rel_err(a, b) <= 1e-2
+            assert rel_err(a, b) <= BF16_TOL
 
 
 def test_egnn_bf16_tc_empty_and_isolated():
-    """tcgen05 EGNN kernels with no edges at all, and with nodes that receive no edge (rows must come out as zeros)."""
+    """tcgen05 EGNN kernels with no edges at all, and with nodes that receive no edge (rows must come out as zeros):
+    against the oracle layer (whose scatter is given the node count)."""
     import gmp_b200
+    from oracle.thirdparty.scatter import scatter as oscatter
     torch.manual_seed(0)
-    m32 = gmp_b200.EGNNLayer(128, activation="swish").cuda()   # smooth activation: gradients comparable at 1e-2
-    m16 = gmp_b200.EGNNLayer(128, activation="swish", precision="bf16").cuda()
-    m16.load_state_dict(m32.state_dict())
+    ref = R.EGNNLayer(128, "swish")   # smooth activation: gradients comparable at 1e-2
+    m16 = gmp_b200.EGNNLayer(128, activation="swish", precision="bf16")
+    m16.load_state_dict(ref.state_dict())
+    m16 = m16.cuda()
     n = 50
-    h, pos = torch.randn(n, 128, device="cuda"), torch.randn(n, 3, device="cuda")
-    for ei in (torch.zeros(2, 0, dtype=torch.long, device="cuda"),
-               torch.stack([torch.arange(0, 20), torch.arange(1, 21)]).cuda()):   # a chain on nodes 0..20, nodes 21..49 isolated
-        h32, h16 = h.clone().requires_grad_(True), h.clone().requires_grad_(True)
-        p32, p16 = pos.clone().requires_grad_(True), pos.clone().requires_grad_(True)
-        o32, q32 = m32(h32, p32, ei)
-        o16, q16 = m16(h16, p16, ei)
-        assert rel_err(o16, o32) <= 1e-2 and rel_err(q16, q32) <= 1e-2
-        g32 = torch.autograd.grad(o32.sum() + q32.sum(), [h32, p32])
+    h, pos = torch.randn(n, 128), torch.randn(n, 3)
+
+    def oracle_with_dim_size(hh, pp, ei):
+        m, shift = R.egnn_edge_message(ref, hh, pp, ei)
+        m_aggr = oscatter(m, ei[1], dim=-2, dim_size=n, reduce=ref.aggr)
+        p_aggr = oscatter(shift, ei[1], dim=-2, dim_size=n, reduce="mean")
+        return ref.mlp_upd(torch.cat([hh, m_aggr], dim=-1)), pp + p_aggr
+
+    for ei in (torch.zeros(2, 0, dtype=torch.long),
+               torch.stack([torch.arange(0, 20), torch.arange(1, 21)])):   # a chain on nodes 0..20, nodes 21..49 isolated
+        hr, pr = h.clone().requires_grad_(True), pos.clone().requires_grad_(True)
+        h16, p16 = h.cuda().requires_grad_(True), pos.cuda().requires_grad_(True)
+        o_ref, q_ref = oracle_with_dim_size(hr, pr, ei)
+        o16, q16 = m16(h16, p16, ei.cuda())
+        assert rel_err(o16, o_ref) <= BF16_TOL and rel_err(q16, q_ref) <= BF16_TOL
+        g_ref = torch.autograd.grad(o_ref.sum() + q_ref.sum(), [hr, pr])
         g16 = torch.autograd.grad(o16.sum() + q16.sum(), [h16, p16])
-        for a, b in zip(g16, g32):
-            assert rel_err(a, b) <= 1e-2
+        for a, b in zip(g16, g_ref):
+            assert rel_err(a, b) <= BF16_TOL
 
 
 @pytest.mark.parametrize("n,deg,xbf16", [(700, 9, True), (300, 40, False), (50, 0, True)])
