@@ -22,7 +22,7 @@ from .tfn import (BatchNorm, Gate, RadialEmbeddingBlock, SphericalHarmonics, Ten
                   TensorProductPlan, TFNModel, edge_geometry, first_node_pooling)
 from .mace import (Contraction, EquivariantLinear, EquivariantProductBasisBlock, MACEModel,  # noqa: F401
                    SymmetricContraction, reshape_irreps)
-from .data import Batch, DevicePrefetcher  # noqa: F401,E402
+from .data import Batch, Data, DataLoader, DevicePrefetcher, coalesce, to_undirected  # noqa: F401,E402
 from .graphs import GraphedStep  # noqa: F401,E402
 from . import distributed  # noqa: F401,E402
 from .distributed import PartitionedEGNN, SlabPartition, allreduce_gradients, halo_exchange, slab_partition  # noqa: F401,E402
@@ -37,4 +37,20 @@ def set_fast_matmul(enabled: bool = True) -> None:
     torch.backends.cudnn.allow_tf32 = bool(enabled)
 
 
-__version__ = "0.1.0"
+def load_reference_checkpoint(module, state_dict: dict):
+    """Load a `state_dict` saved from the reference's module of the same name into a gmp_b200 module.
+
+    Every parameter and buffer of `module` must be present in `state_dict` (else KeyError: the checkpoint is for another
+    architecture).  Keys the fused modules do not own are dropped and returned: the reference's TFN / MACE checkpoints
+    carry constructor-time e3nn buffers (`tp.*`, `gate.*`, `linear.*` output masks) and the Bessel / cutoff constants
+    (`radial_embedding.bessel_fn.{bessel_weights,r_max,prefactor}`, `cutoff_fn.{p,r_max}`) that are recomputed here from
+    the constructor arguments, so a plain `load_state_dict(strict=True)` raises on them."""
+    own = set(module.state_dict().keys())
+    missing = sorted(own - set(state_dict))
+    if missing:
+        raise KeyError(f"load_reference_checkpoint: absent from the checkpoint: {missing}")
+    module.load_state_dict({k: v for k, v in state_dict.items() if k in own}, strict=True)
+    return sorted(set(state_dict) - own)
+
+
+__version__ = "0.2.0"

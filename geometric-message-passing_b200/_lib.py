@@ -49,6 +49,8 @@ _SIGS = {
     "gmp_csr_fill": [P, I64, I64, P, P, P, P, P],
     "gmp_gather_i64_to_i32": [P, P, I64, P, P],
     "gmp_index_is_sorted": [P, I64, P, P],
+    "gmp_mark_unique_pairs": [P, P, P, I64, P, P],
+    "gmp_compact_pairs": [P, P, P, P, P, I64, P, P, P],
     "gmp_segment_reduce_f32": [P, P, P, P, I64, I32, I32, P],
     "gmp_gather_mul_segsum_f32": [P, P, P, P, P, P, I64, I32, P],
     "gmp_gather_mul_segsum_wbf16": [P, P, P, P, I32, P, P, I64, I32, P],

@@ -371,6 +371,32 @@ __global__ void is_sorted_kernel(const int64_t* __restrict__ index, int64_t E, i
     if (e + 1 < E && index[e] > index[e + 1]) *flag = 0;
 }
 
+// coalesce (torch_geometric.utils.to_undirected / coalesce): after the lexicographic sort, keep the first of every run of
+// equal (row, col) pairs
+__global__ void mark_unique_pairs_kernel(const int64_t* __restrict__ row, const int64_t* __restrict__ col,
+                                         const int32_t* __restrict__ perm, int64_t E, int32_t* __restrict__ keep) {
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= E) return;
+    const int64_t a = perm ? perm[k] : k;
+    int flag = 1;
+    if (k > 0) {
+        const int64_t b = perm ? perm[k - 1] : k - 1;
+        flag = (row[a] != row[b]) || (col[a] != col[b]);
+    }
+    keep[k] = flag;
+}
+
+__global__ void compact_pairs_kernel(const int64_t* __restrict__ row, const int64_t* __restrict__ col,
+                                     const int32_t* __restrict__ perm, const int32_t* __restrict__ keep,
+                                     const int64_t* __restrict__ pos, int64_t E, int64_t* __restrict__ out_row,
+                                     int64_t* __restrict__ out_col) {
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= E || !keep[k]) return;
+    const int64_t a = perm ? perm[k] : k;
+    out_row[pos[k]] = row[a];
+    out_col[pos[k]] = col[a];
+}
+
 static Cells make_cells(float cell, const float* origin, const int32_t* dims) {
     Cells c;
     c.ox = origin[0]; c.oy = origin[1]; c.oz = origin[2];
@@ -497,6 +523,22 @@ int gmp_gather_i64_to_i32(const int64_t* src, const int32_t* perm, int64_t num_e
     if (num_edges == 0) return GMP_OK;
     gather_i64_i32_kernel<<<(unsigned)ceil_div(num_edges, 256), 256, 0, stream>>>(src, perm, num_edges, out);
     return check_launch("gather_i64_i32_kernel");
+}
+
+int gmp_mark_unique_pairs(const int64_t* row, const int64_t* col, const int32_t* perm, int64_t num_edges, int32_t* keep,
+                          gmp_stream_t stream) {
+    GMP_REQUIRE(num_edges == 0 || (row && col && keep), "mark_unique_pairs: bad arguments");
+    if (num_edges == 0) return GMP_OK;
+    mark_unique_pairs_kernel<<<(unsigned)ceil_div(num_edges, 256), 256, 0, stream>>>(row, col, perm, num_edges, keep);
+    return check_launch("mark_unique_pairs_kernel");
+}
+
+int gmp_compact_pairs(const int64_t* row, const int64_t* col, const int32_t* perm, const int32_t* keep, const int64_t* pos,
+                      int64_t num_edges, int64_t* out_row, int64_t* out_col, gmp_stream_t stream) {
+    GMP_REQUIRE(num_edges == 0 || (row && col && keep && pos && out_row && out_col), "compact_pairs: bad arguments");
+    if (num_edges == 0) return GMP_OK;
+    compact_pairs_kernel<<<(unsigned)ceil_div(num_edges, 256), 256, 0, stream>>>(row, col, perm, keep, pos, num_edges, out_row, out_col);
+    return check_launch("compact_pairs_kernel");
 }
 
 int gmp_index_is_sorted(const int64_t* index, int64_t num_edges, int32_t* flag, gmp_stream_t stream) {

@@ -43,16 +43,22 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
 }
 #else
+// try_wait suspends the thread until the phase completes or a time limit expires.  Without the optional suspend-time
+// hint the limit is a short system default: a waiting warp then comes back every few hundred cycles to re-issue
+// try_wait + two branches, and in a warp-specialised kernel where most of the 27 warps wait most of the time that spin
+// took 37 % of all issued instructions (profiles/r02_summary.md: BRA + SYNCS.PHASECHK + YIELD in schnet_fwd_tc2_kernel).
+// With the hint (10 ms, the value CUTLASS's ClusterBarrier::wait passes) the warp sleeps until the barrier wakes it.
+constexpr uint32_t kMbarSuspendHintNs = 0x989680u;
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     asm volatile(
         "{\n\t"
         ".reg .pred p;\n\t"
         "WAIT_LOOP:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
         "@p bra WAIT_DONE;\n\t"
         "bra WAIT_LOOP;\n\t"
         "WAIT_DONE:\n\t"
-        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity), "r"(kMbarSuspendHintNs) : "memory");
 }
 
 #endif

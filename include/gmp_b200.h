@@ -98,6 +98,17 @@ int gmp_gather_i64_to_i32(const int64_t* src, const int32_t* perm, int64_t num_e
                           gmp_stream_t stream);
 int gmp_index_is_sorted(const int64_t* index, int64_t num_edges, int32_t* flag, gmp_stream_t stream);
 
+/* Coalescing of an edge list (torch_geometric.utils.to_undirected / coalesce, called for every reference dataset at
+ * experiments/utils/create_graphs.py:79,158,249,330): the pairs are first sorted lexicographically by (row, col) with two
+ * stable counting-sort passes (gmp_csr_count / gmp_csr_fill: by col, then by row); `perm` is the composed permutation
+ * (NULL = already in order).
+ *   mark_unique_pairs: keep[k] = 1 iff sorted pair k differs from sorted pair k-1  (int32[E])
+ *   compact_pairs    : out_row/out_col[pos[k]] = pair k for every kept k, pos = exclusive scan of keep (int64[E+1]). */
+int gmp_mark_unique_pairs(const int64_t* row, const int64_t* col, const int32_t* perm, int64_t num_edges, int32_t* keep,
+                          gmp_stream_t stream);
+int gmp_compact_pairs(const int64_t* row, const int64_t* col, const int32_t* perm, const int32_t* keep, const int64_t* pos,
+                      int64_t num_edges, int64_t* out_row, int64_t* out_col, gmp_stream_t stream);
+
 /* ============================================================================================ */
 /* Segmented reductions (torch_scatter.scatter / scatter_sum)                      */
 /* ============================================================================================ */

@@ -148,3 +148,30 @@ def test_batch_bag_keeps_the_reference_field_names():
     c = b.to("cpu")
     assert set(c.tensors()) == {"atoms", "pos", "edge_index", "batch"} and c.name == "x"
     assert torch.equal(c.pos, b.pos) and c.edge_index.dtype == torch.long
+
+
+def test_data_batch_dataloader_match_the_pyg_restatement():
+    """Data / Batch.from_data_list / DataLoader / to_undirected on host tensors (where the reference builds
+    its datasets, experiments/utils/create_graphs.py:78-79) against oracle/thirdparty/pyg.py."""
+    import gmp_b200
+    from oracle.thirdparty import pyg
+    g = torch.Generator().manual_seed(0)
+    for n, E in ((50, 300), (7, 0), (3, 40)):
+        ei = torch.randint(0, n, (2, E), generator=g)
+        got = gmp_b200.to_undirected(ei)
+        assert torch.equal(got, pyg.to_undirected(ei))
+        if E:
+            assert bool((got[0][1:] >= got[0][:-1]).all())           # row-ascending, duplicates dropped
+            assert torch.equal(gmp_b200.coalesce(got), got)          # idempotent
+    ds = [gmp_b200.Data(atoms=torch.randint(0, 5, (n,), generator=g), pos=torch.randn(n, 3, generator=g),
+                        edge_index=torch.randint(0, n, (2, 2 * n), generator=g), y=torch.tensor(float(n)))
+          for n in (5, 7, 3, 9, 4)]
+    b = gmp_b200.Batch.from_data_list(ds)
+    ob = pyg.Batch.from_data_list([pyg.Data(**d.__dict__) for d in ds])
+    for k in ("atoms", "pos", "edge_index", "y", "batch"):
+        assert torch.equal(getattr(b, k), getattr(ob, k)), k
+    assert b.num_graphs == ob.num_graphs == 5 and b.num_nodes == 28
+    loader = gmp_b200.DataLoader(ds, batch_size=2)
+    assert len(loader) == 3 and [x.num_graphs for x in loader] == [2, 2, 1]
+    assert sum(x.num_nodes for x in gmp_b200.DataLoader(ds, batch_size=2, shuffle=True)) == 28
+    assert len(gmp_b200.DataLoader(ds, batch_size=2, drop_last=True)) == 2
