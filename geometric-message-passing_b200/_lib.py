@@ -19,7 +19,7 @@ _lib = None
 launches = 0  # number of C-ABI compute calls issued
 _kernels = 0  # number of CUDA kernels those calls launched (bench.py's gpu_launches)
 # kernels launched per entry point (default 1); memsets are not counted
-_KERNELS_PER_CALL = {"gmp_exclusive_scan_i32": 3, "gmp_csr_fill": 3, "gmp_cells_build": 3, "gmp_tp_tc_contract": 2, "gmp_schnet_cfconv_fwd_tc2": 2, "gmp_schnet_cfconv_fwd_tc2_keep": 2}
+_KERNELS_PER_CALL = {"gmp_exclusive_scan_i32": 3, "gmp_csr_fill": 3, "gmp_cells_build": 3, "gmp_tp_tc_contract": 2, "gmp_schnet_cfconv_fwd_tc2": 2, "gmp_schnet_cfconv_fwd_tc2_keep": 2, "gmp_egnn_tc2_edge_fwd": 2}
 
 
 def kernel_launches() -> int:
@@ -70,6 +70,7 @@ _SIGS = {
     "gmp_schnet_cfconv_bwd_tc2": [P, P, P, P, I64, I64, P, P, P, P, P, I32, P],
     "gmp_linear_wgrad_tc": [P, P, I64, I32, I32, P, P],
     "gmp_egnn_tc_edge_fwd": [P, P, P, I64, I64, P, P, P, P, P, P, P],
+    "gmp_egnn_tc2_edge_fwd": [P, P, P, I64, I64, P, P, P, P, P, P, P, P],
     "gmp_egnn_tc_edge_bwd_fused": [P, P, P, P, I64, I64, P, P, P, P, P, P, P, P, P, P, P, P],
     "gmp_segment_sum_bf16_f32": [P, P, P, P, I64, I32, P],
     "gmp_egnn_tc_edge_bwd": [P, P, P, P, I64, I64, P, P, P, P, P, P, I32, P, P, P, P],
@@ -86,7 +87,7 @@ _SIGS = {
 }
 _PLAIN = {"gmp_version": (I32, []), "gmp_last_error": (C.c_char_p, []),
           "gmp_schnet_bwd_num_parts": (I32, [I64]), "gmp_schnet_bwd_part_len": (I64, [I32, I32]),
-          "gmp_egnn_bwd_num_parts": (I32, [I64]), "gmp_egnn_tc_bwd_num_parts": (I32, [I64]), "gmp_linear_wgrad_num_parts": (I32, [I64]), "gmp_schnet_tc2_num_chunks": (I32, [I64]), "gmp_egnn_bwd_part_len": (I64, [I32]),
+          "gmp_egnn_bwd_num_parts": (I32, [I64]), "gmp_egnn_tc_bwd_num_parts": (I32, [I64]), "gmp_egnn_tc2_num_chunks": (I32, [I64]), "gmp_linear_wgrad_num_parts": (I32, [I64]), "gmp_schnet_tc2_num_chunks": (I32, [I64]), "gmp_egnn_bwd_part_len": (I64, [I32]),
           "gmp_tp_contract_smem_bytes": (I64, [I32, I32]), "gmp_symcontract_bwd_num_parts": (I32, [I64]), "gmp_tp_wgrad_part_len": (I64, [I32]),
           "gmp_tp_tc_num_chunks": (I32, [I64]), "gmp_tp_tc_hid_bytes": (I64, [I64, I32]), "gmp_tp_tc_w2_bytes": (I64, [I32, I32])}
 

@@ -235,12 +235,15 @@ __global__ void __launch_bounds__(kS2Threads, 1) schnet_fwd_tc2_kernel(Tc2Args a
             const uint32_t ms = tc % kS2MetaStages;
             TC2_MARK(1, tc);
             mbar_wait(&bars[B_DONE + ms], ((tc / kS2MetaStages) & 1u) ^ 1u);   // tile tc-6 read out: its meta block is free
-            TC2_MARK(2, tc);
-            mbar_wait(&bars[B_D3F + st], par ^ 1u);    // G3 of tile tc-3 has read the msg image: the row stage is free
+            // The meta block is published BEFORE the wait for the row stage: the scalar side of the tile (basis -> G1 -> softplus
+            // -> G2) then runs while the stage is still held by tile tc-3, i.e. a row stage is occupied from the gather to G3
+            // only, not through the first half of the chain (epilogue 1 spent 15 % of its samples waiting for this block).
             Meta& M = meta[ms];
             if (remain <= 0) {  // end-of-stream marker: cnt = 0
                 if (t == 0) { M.cnt = 0; M.nseg = 0; }
                 if (mh == 0) mbar_arrive(&bars[B_MF + ms]);
+                TC2_MARK(2, tc);
+                mbar_wait(&bars[B_D3F + st], par ^ 1u);
                 cp_async_arrive(&bars[B_XF + st]);
                 mbar_arrive(&bars[B_XF + st]);
                 break;
@@ -255,6 +258,8 @@ __global__ void __launch_bounds__(kS2Threads, 1) schnet_fwd_tc2_kernel(Tc2Args a
                 if (e == 0) M.head0 = head0;
                 mbar_arrive(&bars[B_MF + ms]);   // meta block published: epilogue 1 expands the basis from d
             }
+            TC2_MARK(2, tc);
+            mbar_wait(&bars[B_D3F + st], par ^ 1u);    // G3 of tile tc-3 has read the msg image: the row stage is free
             // gather x1[src] (bf16 rows of 256 B) into the swizzled row image, half a warp per row: one copy instruction then
             // touches 4 cache lines instead of 32 (a lane-per-row gather costs the load/store unit one cycle per line, and this
             // kernel is short of exactly those).  Meta half mh takes rows [16 mh, 16 mh + 16) of its warp's 32 edge slots.
@@ -355,34 +360,43 @@ __global__ void __launch_bounds__(kS2Threads, 1) schnet_fwd_tc2_kernel(Tc2Args a
         // group 1 reads out the previous tile (lane = feature column) =====================
         const int e = (warp & 3) * 32 + lane, g = (warp - 16) >> 2;
         const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
-        auto readout = [&](uint32_t tq) {  // D3 of tile tq: lane = feature column e, accumulator column = segment
+        // Read-out of D3 (lane = feature column e, accumulator column = segment).  A row can continue across tiles, so the
+        // LAST segment of a tile is not stored but carried in a register (value, row, head flag) into the next read-out,
+        // where it is either completed by that tile's first segment (same row) or stored; every other segment is a
+        // finished row and goes out with one plain store.  Nothing is read back from global memory (the earlier
+        // read-modify-write cost four dependent L2 round trips per tile on the critical path, profiles/r02_summary.md);
+        // every agg element is still written by exactly one thread, in tile order: deterministic, no atomics.
+        float carry = 0.f;
+        int carry_row = -1;
+        bool carry_head = false;
+        auto store_row = [&](int row, bool head, float val) {
+            float* dst = head ? a.head + (int64_t)blockIdx.x * 128 + e : a.agg + (int64_t)row * 128 + e;
+            *dst = val;
+        };
+        auto readout = [&](uint32_t tq) {
             const uint32_t st = tq % kS2Stages, ms = tq % kS2MetaStages;
             const Meta& M = meta[ms];
             float v[32];
             tmem_ld32(tmD3 + st * 32 + lane_base, v);
             tc_fence_before();
             const int nseg = M.nseg;
-            const bool h0 = M.head0 != 0;
-            // read-modify-write of the rows of this tile, 8 segments at a time: all old values are requested before the
-            // first store so that the L2 round trips overlap (only this thread ever touches these addresses)
+            if (nseg > 0) {
+                const int row0 = M.seg_row[0];
+                float first = v[0];
+                bool first_head = M.head0 != 0;
+                if (carry_row == row0) { first += carry; first_head = carry_head; }
+                else if (carry_row >= 0) store_row(carry_row, carry_head, carry);
+                if (nseg == 1) {
+                    carry = first; carry_row = row0; carry_head = first_head;
+                } else {
+                    store_row(row0, first_head, first);
+                    float last = 0.f;
 #pragma unroll
-            for (int s0 = 0; s0 < kS2MaxSeg; s0 += 8) {
-                if (s0 < nseg) {
-                    float* dst[8];
-                    float old[8];
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const int s = s0 + j;
-                        dst[j] = nullptr;
-                        old[j] = 0.f;
-                        if (s < nseg) {
-                            dst[j] = (s == 0 && h0) ? a.head + (int64_t)blockIdx.x * 128 + e : a.agg + (int64_t)M.seg_row[s] * 128 + e;
-                            old[j] = __ldcg(dst[j]);
-                        }
+                    for (int s = 1; s < kS2MaxSeg; ++s) {
+                        if (s < nseg - 1) a.agg[(int64_t)M.seg_row[s] * 128 + e] = v[s];
+                        if (s == nseg - 1) last = v[s];
                     }
-#pragma unroll
-                    for (int j = 0; j < 8; ++j)
-                        if (dst[j]) *dst[j] = old[j] + v[s0 + j];
+                    carry = last; carry_row = M.seg_row[nseg - 1]; carry_head = false;
                 }
             }
             mbar_arrive(&bars[B_D3E + st]);
@@ -402,6 +416,7 @@ __global__ void __launch_bounds__(kS2Threads, 1) schnet_fwd_tc2_kernel(Tc2Args a
                     tc_fence_after();
                     if (g == 1) readout(tc - 1);
                 }
+                if (g == 1 && carry_row >= 0) store_row(carry_row, carry_head, carry);   // the row left open by the last tile
                 mbar_arrive(&bars[B_MSGF + st]);
                 break;
             }
@@ -577,6 +592,9 @@ __global__ void __launch_bounds__(128) schnet_tc2_fixup_kernel(const int32_t* __
 //   G4  [dW1 | db1] += Q^T R
 // Warps: meta 0-3 | epiP 4-7 | epiH 8-15 | epiQ 16-23 | MMA issue 24 (G1), 25 (G3), 26 (G4).  Stages R, rows/P/Q, H two deep;
 // D1, D3 single.  TMEM: D1 @0 | D3 @128 | dW2 @256 | dW1|db1 @384 (64) | db2 @448 (16).
+// Tried in round 2 and measured slower (profiles/r02_summary.md): g read as bf16 rows in two batches of eight loads (0.372 ->
+// 0.382 ms), epiP on eight warps with epiH on four (0.407 ms).  The kernel is bound by the latency of the per-stage chain
+// gather -> P -> G3 -> Q -> G4 with two stages in flight (212 KB of shared memory), not by any one role.
 // ------------------------------------------------------------------------------------------------
 constexpr int kB2Threads = 864;   // 27 warps
 constexpr int o3W1 = 0;                    // [128 f][64 g], column 63 = b1          16 KB

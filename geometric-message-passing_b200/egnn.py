@@ -22,7 +22,12 @@ from .graph import Graph, get_graph
 from .scatter import scatter, segment_reduce
 from .schnet import global_add_pool, global_mean_pool
 
+import os
+
 _PREC = {"fp32": _lib.FP32_STRICT, "bf16": _lib.BF16_TC}
+# bf16 forward: csrc/egnn_tc2.cu (thread-per-row, three tile streams per SM).  GMP_EGNN_TC2=0 selects the first tcgen05
+# kernel (csrc/egnn_tc.cu) for A/B timing.
+_TC2_FWD = os.environ.get("GMP_EGNN_TC2", "1") != "0"
 # bf16 mode: the single-pass backward needs 272 B of scratch per edge; above this budget the two-pass (recompute) scheme runs
 _FUSED_BWD_SCRATCH_BYTES = 64 << 30
 
@@ -46,8 +51,13 @@ class _EGNNEdgeFn(torch.autograd.Function):
         if precision == _lib.BF16_TC:
             if d != 128:
                 raise NotImplementedError("precision='bf16': the tensor-core EGNN kernels are built for emb_dim = 128")
-            call("gmp_egnn_tc_edge_fwd", ptr(csr.rowptr), ptr(csr.col), ptr(csr.row_ids()), graph.n, graph.E, ptr(P),
-                 ptr(Q.to(torch.bfloat16)), ptr(pos), C.byref(prm), ptr(msg), ptr(pag))
+            if _TC2_FWD:
+                head = torch.empty(int(_lib.lib().gmp_egnn_tc2_num_chunks(graph.E)), 132, dtype=P.dtype, device=P.device)
+                call("gmp_egnn_tc2_edge_fwd", ptr(csr.rowptr), ptr(csr.col), ptr(csr.row_ids()), graph.n, graph.E, ptr(P),
+                     ptr(Q.to(torch.bfloat16)), ptr(pos), C.byref(prm), ptr(msg), ptr(pag), ptr(head))
+            else:
+                call("gmp_egnn_tc_edge_fwd", ptr(csr.rowptr), ptr(csr.col), ptr(csr.row_ids()), graph.n, graph.E, ptr(P),
+                     ptr(Q.to(torch.bfloat16)), ptr(pos), C.byref(prm), ptr(msg), ptr(pag))
         else:
             call("gmp_egnn_edge_fwd", ptr(csr.rowptr), ptr(csr.col), graph.n, graph.E, ptr(P), ptr(Q), ptr(pos),
                  C.byref(prm), ptr(msg), ptr(pag), precision)

@@ -298,6 +298,16 @@ int gmp_egnn_tc_edge_fwd(const int32_t* rowptr, const int32_t* col, const int32_
                          const float* P, const void* Q_bf16, const float* pos,
                          const gmp_egnn_edge_params* prm /* host */, float* msg_aggr, float* pos_aggr,
                          gmp_stream_t stream);
+/* Second design of the same forward (csrc/egnn_tc2.cu; models/layers/egnn_layer.py:62-80): a thread owns a whole edge row
+ * (LayerNorm statistics are thread-local, no barrier inside a tile), three independent tile streams per SM, aggregation
+ * as a one-hot MMA with rows carried across tiles.  The sorted edge list is cut into gmp_egnn_tc2_num_chunks(E) contiguous
+ * chunks; rows that straddle a chunk boundary are completed by a fix-up kernel from `head`
+ * (float [num_chunks][132], scratch).  msg_aggr / pos_aggr are zeroed here (rows without edges stay zero). */
+int32_t gmp_egnn_tc2_num_chunks(int64_t num_edges);
+int gmp_egnn_tc2_edge_fwd(const int32_t* rowptr, const int32_t* col, const int32_t* rowid, int64_t n, int64_t num_edges,
+                          const float* P, const void* Q_bf16, const float* pos,
+                          const gmp_egnn_edge_params* prm /* host */, float* msg_aggr, float* pos_aggr, float* head,
+                          gmp_stream_t stream);
 /* Backward, two recompute passes as gmp_egnn_edge_bwd.  row_operand (fp32) / col_operand_bf16 are P / bf16(Q) in the
  * dst pass (src_pass = 0) and Q / bf16(P) in the src pass.  Both passes write per-CTA partials into the SAME
  * wgrad_parts [gmp_egnn_tc_bwd_num_parts(E)][gmp_egnn_bwd_part_len(128)]: the dst pass the two weight matrices

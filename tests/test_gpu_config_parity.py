@@ -22,9 +22,11 @@ bf16 (tcgen05) 1e-2 per layer (asserted layer by layer in tests/test_gpu_tc.py) 
 ReLU kinks.  The derivative of ReLU is discontinuous, so a unit whose pre-activation lies within the forward error of
 zero can come out with the other derivative; the affected gradient entries then differ by O(1) no matter how small the
 forward error is.  Two places, both handled explicitly rather than by loosening the bound:
-  * the prediction heads of TFN / MACE (Linear-ReLU-Linear on k pooled rows): rows of `pred.0.{weight,bias}` that belong
-    to units whose ORACLE pre-activation is within KINK_MARGIN x the measured output error of zero for any of the k
-    graphs are left out of the comparison (a few of the 64-128 units; counted and bounded by 1/8 of them);
+  * the prediction heads of TFN / MACE (`pred` = Linear-ReLU-Linear on the k pooled rows, plain torch.nn modules on both
+    sides, not part of the hot path): with 4 graphs x 64 units, a few units always sit within the bf16 forward error of
+    the kink, and one flipped unit moves every upstream gradient by ~1/sqrt(active units) (measured 14 %).  The model
+    OUTPUT is compared through the head; the GRADIENTS are taken from a cotangent applied to the head's input (the
+    pooled body output, captured with a forward hook on both sides), so that they measure the message-passing layers;
   * EGNN with ReLU at 2^18 nodes (3e9 ReLU evaluations per layer pass): outputs keep the strict bound in both modes;
     gradients are held to the strict bound with SiLU, and with ReLU to an L2 bound -- 1e-3 in fp32 (flips at fp32
     round-off distance from the kink), RELU_SENS_FACTOR x the oracle's own bf16-input sensitivity in bf16
@@ -37,7 +39,6 @@ from oracle import ref_layers as R
 from tests.helpers import Bag, rel_err
 
 pytestmark = [pytest.mark.gpu, pytest.mark.timeout(600)]
-KINK_MARGIN = 4.0      # x the measured relative output error
 
 
 def _l2_rel(a, b):
@@ -72,24 +73,26 @@ def _model_subset_parity(which, k_graphs, nodes_per_graph, precision, synth_fn, 
         ref.train()
         a_s, p_s, b_s = atoms[:n_sub], pos[:n_sub].clone().requires_grad_(pos_grad), batch[:n_sub]
         ei_s = torch.from_numpy(cluster.radius_graph(pos[:n_sub].numpy(), radius, b_s.numpy(), False, max_nb))
-        head_pre = []
-        hook = None
-        if isinstance(getattr(ref, "pred", None), torch.nn.Sequential) and isinstance(ref.pred[1], torch.nn.ReLU):
-            hook = ref.pred[0].register_forward_hook(lambda m, i, o: head_pre.append(o.detach()))
+        # Models with a Linear-ReLU-Linear prediction head (TFN, MACE): the gradient comparison applies the cotangent to the
+        # head's INPUT (the pooled body output), see the module docstring; the model output is compared through the head.
+        relu_head = isinstance(getattr(ref, "pred", None), torch.nn.Sequential) and isinstance(ref.pred[1], torch.nn.ReLU)
+        body_ref = []
+        hook = ref.pred.register_forward_hook(lambda m, i, o: body_ref.append(i[0])) if relu_head else None
         out_ref = ref(Bag(atoms=a_s, pos=p_s, edge_index=ei_s, batch=b_s))
         if hook is not None:
             hook.remove()
-        cot = torch.randn(out_ref.shape, generator=torch.Generator().manual_seed(11))
+        target_ref = body_ref[0] if relu_head else out_ref
+        cot = torch.randn(target_ref.shape, generator=torch.Generator().manual_seed(11))
         ref_params = dict(ref.named_parameters())
-        names = sorted(ref_params)
+        names = sorted(k for k in ref_params if not (relu_head and k.startswith("pred.")))
         wrt = [ref_params[k] for k in names] + ([p_s] if pos_grad else [])
-        g_ref = torch.autograd.grad((out_ref * cot).sum(), wrt, allow_unused=True)
+        g_ref = torch.autograd.grad((target_ref * cot).sum(), wrt, allow_unused=True)
 
         mine = bench.make_model(which, precision)
         _load_same_state(mine, ref)
         mine = mine.cuda().train()
         my_params = dict(mine.named_parameters())
-        assert sorted(my_params) == names          # same parameter names as the reference modules (order may differ)
+        assert sorted(my_params) == sorted(ref_params)          # same parameter names as the reference modules (order may differ)
         if not full_batch:
             atoms, pos, batch = atoms[:n_sub], pos[:n_sub], batch[:n_sub]
         graphs = int(batch[-1]) + 1
@@ -98,18 +101,18 @@ def _model_subset_parity(which, k_graphs, nodes_per_graph, precision, synth_fn, 
         ei = gmp_b200.radius_graph(pos.cuda(), radius, batch_c, max_num_neighbors=max_nb)
         n_edges_sub = int((ei[1] < n_sub).sum())
         assert torch.equal(ei[:, :n_edges_sub].cpu(), ei_s)          # bit-exact graph of the subset inside the batch
+        body = []
+        hook = mine.pred.register_forward_hook(lambda m, i, o: body.append(i[0])) if relu_head else None
         out = mine(Bag(atoms=atoms.cuda(), pos=pos_c, edge_index=ei, batch=batch_c, num_graphs=graphs))
+        if hook is not None:
+            hook.remove()
         assert out.shape[0] == graphs
         e_out = rel_err(out[:k_graphs], out_ref)
-        cot_full = torch.zeros(out.shape, device="cuda")
+        target = body[0] if relu_head else out
+        e_body = rel_err(target[:k_graphs], target_ref)
+        cot_full = torch.zeros(target.shape, device="cuda")
         cot_full[:k_graphs] = cot.cuda()
-        g = torch.autograd.grad((out * cot_full).sum(), [my_params[k] for k in names] + ([pos_c] if pos_grad else []), allow_unused=True)
-        # ReLU units of the prediction head that sit on the kink for one of the k graphs (see the module docstring)
-        safe_units = None
-        if head_pre:
-            pre = head_pre[0]
-            safe_units = (pre.abs() >= KINK_MARGIN * max(e_out, 1e-6) * pre.abs().max()).all(dim=0)
-            assert int((~safe_units).sum()) <= max(2, safe_units.numel() // 8), "too many head units on the ReLU kink"
+        g = torch.autograd.grad((target * cot_full).sum(), [my_params[k] for k in names] + ([pos_c] if pos_grad else []), allow_unused=True)
         errs = {}
         for name, a, b_ in zip(names + (["pos"] if pos_grad else []), g, g_ref):
             if b_ is None or float(b_.abs().max()) == 0.0:
@@ -118,15 +121,12 @@ def _model_subset_parity(which, k_graphs, nodes_per_graph, precision, synth_fn, 
             if name == "pos":
                 assert float(a[n_sub:].abs().max()) == 0.0 if a.shape[0] > n_sub else True
                 a = a[:n_sub]
-            if safe_units is not None and name in ("pred.0.weight", "pred.0.bias"):
-                a, b_ = a.cpu()[safe_units], b_[safe_units]
             errs[name] = rel_err(a, b_)
         worst = max(errs, key=errs.get)
         top = sorted(errs.items(), key=lambda kv: -kv[1])[:4]
         print(f"\\n[{which} {precision}] graphs={graphs} (oracle: {k_graphs}), E={ei.shape[1]}  out {e_out:.2e}  worst grads "
-              + ", ".join(f"{k} {v:.2e}" for k, v in top)
-              + (f"  head units on the kink: {int((~safe_units).sum())}" if safe_units is not None else ""))
-        assert e_out <= tol_out, e_out
+              + ", ".join(f"{k} {v:.2e}" for k, v in top) + (f"  body output {e_body:.2e}" if relu_head else ""))
+        assert e_out <= tol_out and e_body <= tol_out, (e_out, e_body)
         assert errs[worst] <= tol_grad, (worst, errs[worst])
     finally:
         gmp_b200.set_fast_matmul(False)

@@ -334,6 +334,53 @@ def test_tp_conv_bf16_tc_corner_cases(case):
             assert rel_err(a, b) <= BF16_TOL
 
 
+@pytest.mark.parametrize("n,deg,shuffle,aggr", [(5000, 2, True, "add"), (300, 40, False, "mean"), (70000, 9, True, "add"),
+                                                (4, 700, False, "mean"), (900, 1, False, "add")])
+def test_egnn_tc2_forward_edge_cases(n, deg, shuffle, aggr):
+    """The thread-per-row EGNN forward (csrc/egnn_tc2.cu) against the ORACLE layer on graphs that exercise its corners: more
+    than 32 destination rows per 128-edge tile (several one-hot windows), rows spanning many tiles and chunk boundaries
+    (carried rows, head buffer + fix-up; 70 000 x 9 edges = more tiles than the 3 x 148 chunks), nodes without edges,
+    shuffled edge order, mean aggregation; forward 1e-2, and the gradients (SiLU) through the layer 1e-2."""
+    import gmp_b200
+    from oracle.thirdparty.scatter import scatter as oscatter
+    g = torch.Generator().manual_seed(n + deg)
+    E = n * deg
+    dst = torch.randint(0, max(n - n // 7, 1), (E,), generator=g)      # the last n/7 nodes never receive an edge
+    src = torch.randint(0, n, (E,), generator=g)
+    if not shuffle:
+        dst = dst.sort().values
+    ei = torch.stack([src, dst])
+    torch.manual_seed(1)
+    ref = R.EGNNLayer(128, "swish", "layer", aggr)
+    with torch.no_grad():
+        for p in ref.parameters():
+            if p.dim() == 1:
+                p.add_(0.2 * torch.randn_like(p))
+    m16 = gmp_b200.EGNNLayer(128, activation="swish", aggr=aggr, precision="bf16")
+    m16.load_state_dict(ref.state_dict())
+    m16 = m16.cuda()
+    h, pos = torch.randn(n, 128, generator=g), torch.randn(n, 3, generator=g) * 2.0
+
+    def oracle(hh, pp):    # the reference's scatter has no dim_size (SURVEY A.1): give it the node count
+        m, shift = R.egnn_edge_message(ref, hh, pp, ei)
+        m_aggr = oscatter(m, ei[1], dim=-2, dim_size=n, reduce=ref.aggr)
+        p_aggr = oscatter(shift, ei[1], dim=-2, dim_size=n, reduce="mean")
+        return ref.mlp_upd(torch.cat([hh, m_aggr], dim=-1)), pp + p_aggr
+
+    hr, pr = h.clone().requires_grad_(True), pos.clone().requires_grad_(True)
+    o_ref, q_ref = oracle(hr, pr)
+    h16, p16 = h.cuda().requires_grad_(True), pos.cuda().requires_grad_(True)
+    o16, q16 = m16(h16, p16, ei.cuda())
+    assert rel_err(o16, o_ref) <= BF16_TOL and rel_err(q16.cpu() - pos, q_ref.detach() - pos) <= BF16_TOL
+    c1, c2 = torch.randn(n, 128, generator=g), torch.randn(n, 3, generator=g)
+    g_ref = torch.autograd.grad((o_ref * c1).sum() + (q_ref * c2).sum(), [hr, pr])
+    g16 = torch.autograd.grad((o16 * c1.cuda()).sum() + (q16 * c2.cuda()).sum(), [h16, p16])
+    for a, b, k in zip(g16, g_ref, ("h", "pos")):
+        assert rel_err(a, b) <= BF16_TOL, k
+    o16b, q16b = m16(h16, p16, ei.cuda())
+    assert torch.equal(o16, o16b) and torch.equal(q16, q16b)  # deterministic
+
+
 def test_egnn_bf16_tc_empty_and_isolated():
     """tcgen05 EGNN kernels with no edges at all, and with nodes that receive no edge (rows must come out as zeros):
     against the oracle layer (whose scatter is given the node count)."""
