@@ -88,7 +88,7 @@ _SIGS = {
 _PLAIN = {"gmp_version": (I32, []), "gmp_last_error": (C.c_char_p, []),
           "gmp_schnet_bwd_num_parts": (I32, [I64]), "gmp_schnet_bwd_part_len": (I64, [I32, I32]),
           "gmp_egnn_bwd_num_parts": (I32, [I64]), "gmp_egnn_tc_bwd_num_parts": (I32, [I64]), "gmp_egnn_tc2_num_chunks": (I32, [I64]), "gmp_linear_wgrad_num_parts": (I32, [I64]), "gmp_schnet_tc2_num_chunks": (I32, [I64]), "gmp_egnn_bwd_part_len": (I64, [I32]),
-          "gmp_tp_contract_smem_bytes": (I64, [I32, I32]), "gmp_symcontract_bwd_num_parts": (I32, [I64]), "gmp_tp_wgrad_part_len": (I64, [I32]),
+          "gmp_tp_contract_smem_bytes": (I64, [I32, I32]), "gmp_symcontract_bwd_num_parts": (I32, [I64]), "gmp_symcontract_fast_path": (I32, [I32, I32, I32, I32, I32]), "gmp_tp_wgrad_part_len": (I64, [I32]),
           "gmp_tp_tc_num_chunks": (I32, [I64]), "gmp_tp_tc_hid_bytes": (I64, [I64, I32]), "gmp_tp_tc_w2_bytes": (I64, [I32, I32])}
 
 

@@ -146,6 +146,278 @@ __global__ void __launch_bounds__(256) symcontract_bwd_kernel(SCArgs a, const fl
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Fast path for the model shape (D = 9 input components, K = 9 outputs, correlation 3: M = 9 + 45 + 165 = 219 monomials
+// in the order of gmp_b200.irreps.monomials): the monomial loops are fully unrolled, so x, the running products and the
+// accumulators live in registers with compile-time indices, the channel's coefficients are read as three 16-byte
+// broadcast loads per monomial (layout [M][12]), and nothing is indexed dynamically.  The generic kernels above spent
+// ~27 instructions per monomial for 9 FMAs in the forward and 45 in the backward (dynamic shared-memory indexing of x
+// and dx): 6.9 ms + 49.7 ms per block at N = 65 536, C = 128 (profiles/r02j_launches.csv).
+// ------------------------------------------------------------------------------------------------
+constexpr int kS9M = 219;
+constexpr int kS9CS = 12;     // coefficient row stride in shared memory (9 padded to 12: three float4)
+
+__device__ __forceinline__ void s9_load_coef(const float* __restrict__ coef_c, float* __restrict__ cs, int t, int nthreads) {
+    // global [K = 9][M = 219] -> shared [M][12]
+    for (int i = t; i < 9 * kS9M; i += nthreads) {
+        const int k = i / kS9M, m = i - k * kS9M;
+        cs[m * kS9CS + k] = __ldg(coef_c + i);
+    }
+}
+
+// acc.{x,y} += a.{x,y} * b: one packed FFMA2 (sm_100a) instead of two FFMA -- the kernels are bound by instruction issue
+__device__ __forceinline__ void ffma2(float2& acc, const float2 a, const float b) {
+    uint64_t pa, pb, pc;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(pa) : "f"(a.x), "f"(a.y));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(pb) : "f"(b), "f"(b));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(pc) : "f"(acc.x), "f"(acc.y));
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(pc) : "l"(pa), "l"(pb));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(acc.x), "=f"(acc.y) : "l"(pc));
+}
+// acc.{x,y} += a.{x,y} * b.{x,y}
+__device__ __forceinline__ void ffma2v(float2& acc, const float2 a, const float2 b) {
+    uint64_t pa, pb, pc;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(pa) : "f"(a.x), "f"(a.y));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(pb) : "f"(b.x), "f"(b.y));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(pc) : "f"(acc.x), "f"(acc.y));
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(pc) : "l"(pa), "l"(pb));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(acc.x), "=f"(acc.y) : "l"(pc));
+}
+
+#define S9_COEF(m)                                                                         \
+    const float4 c0_ = *reinterpret_cast<const float4*>(cs + (m) * kS9CS);                 \
+    const float4 c1_ = *reinterpret_cast<const float4*>(cs + (m) * kS9CS + 4);             \
+    const float c8_ = cs[(m) * kS9CS + 8];                                                  \
+    const float2 cp_[4] = {make_float2(c0_.x, c0_.y), make_float2(c0_.z, c0_.w), make_float2(c1_.x, c1_.y), make_float2(c1_.z, c1_.w)}; \
+    const float cf_[9] = {c0_.x, c0_.y, c0_.z, c0_.w, c1_.x, c1_.y, c1_.z, c1_.w, c8_}; (void)cp_; (void)cf_;
+
+// forward: grid = (node tiles of 128 * R, channel groups); a CTA walks the channels of its group, thread = R nodes
+template <int R>
+__global__ void __launch_bounds__(128, 4) symcontract9_fwd_kernel(SCArgs a, float* __restrict__ out, int ch_per_group) {
+    __shared__ __align__(16) float cs[kS9M * kS9CS];
+    const int t = threadIdx.x;
+    const int c_lo = blockIdx.y * ch_per_group, c_hi = min(a.C, c_lo + ch_per_group);
+    int64_t node[R];
+    bool ok[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) { node[r] = ((int64_t)blockIdx.x * R + r) * 128 + t; ok[r] = node[r] < a.N; }
+    for (int c = c_lo; c < c_hi; ++c) {
+        __syncthreads();
+        s9_load_coef(a.coef + (int64_t)c * 9 * kS9M, cs, t, 128);
+        float x[R][9], acc8[R];
+        float2 acc2[R][4];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const float* xr = a.x + (node[r] * a.C + c) * 9;
+#pragma unroll
+            for (int i = 0; i < 9; ++i) x[r][i] = ok[r] ? __ldg(xr + i) : 0.f;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) acc2[r][k] = make_float2(0.f, 0.f);
+            acc8[r] = 0.f;
+        }
+        __syncthreads();
+        int m = 0;
+#pragma unroll
+        for (int i = 0; i < 9; ++i) {
+            S9_COEF(m)
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) ffma2(acc2[r][k], cp_[k], x[r][i]);
+                acc8[r] = fmaf(c8_, x[r][i], acc8[r]);
+            }
+            ++m;
+        }
+#pragma unroll
+        for (int i = 0; i < 9; ++i)
+#pragma unroll
+            for (int j = i; j < 9; ++j) {
+                S9_COEF(m)
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    const float v = x[r][i] * x[r][j];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) ffma2(acc2[r][k], cp_[k], v);
+                    acc8[r] = fmaf(c8_, v, acc8[r]);
+                }
+                ++m;
+            }
+#pragma unroll
+        for (int i = 0; i < 9; ++i)
+#pragma unroll
+            for (int j = i; j < 9; ++j) {
+                float pij[R];
+#pragma unroll
+                for (int r = 0; r < R; ++r) pij[r] = x[r][i] * x[r][j];
+#pragma unroll
+                for (int kk = j; kk < 9; ++kk) {
+                    S9_COEF(m)
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+                        const float v = pij[r] * x[r][kk];
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) ffma2(acc2[r][k], cp_[k], v);
+                        acc8[r] = fmaf(c8_, v, acc8[r]);
+                    }
+                    ++m;
+                }
+            }
+        // out[b][C*off + c*d + kl]: 0e at [0, C), 1o at [C, 4C), 2e at [4C, 9C)  (out_map of the model shape)
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+            if (ok[r]) {
+                float* o = out + node[r] * a.out_len;
+                const float acc[9] = {acc2[r][0].x, acc2[r][0].y, acc2[r][1].x, acc2[r][1].y, acc2[r][2].x, acc2[r][2].y,
+                                      acc2[r][3].x, acc2[r][3].y, acc8[r]};
+                o[c] = acc[0];
+#pragma unroll
+                for (int k = 0; k < 3; ++k) o[a.C + 3 * c + k] = acc[1 + k];
+#pragma unroll
+                for (int k = 0; k < 5; ++k) o[4 * a.C + 5 * c + k] = acc[4 + k];
+            }
+    }
+}
+
+// backward: grid = (parts, C), 256 threads, tile = 64 nodes.
+// Phase 1 (all 256 threads: thread = (node, quarter of the monomials)): monomials -> shared tile, q_m = sum_K g_K coef[K][m],
+// dx by the product rule, everything in registers; the four partial dx of a node are summed through shared memory in a fixed
+// order.  The quarters are compile-time slices of the unrolled loops (by the first index i), one slice per warp pair, so no
+// warp diverges.  Phase 2 (thread = monomial column): dcoef[K][m] += sum_n g[n][K] * mono[n][m] with the g row as broadcast
+// float4 loads.
+constexpr int kS9Tile = 64;
+constexpr int kS9LM = 221;    // odd row stride of the monomial tile
+
+__host__ __device__ constexpr int s9_owner(int i) { return i == 0 ? 0 : ((i == 1 || i >= 7) ? 1 : (i <= 3 ? 2 : 3)); }   // 54 / 51 / 62 / 43+9 monomials
+
+template <int S>
+__device__ __forceinline__ void s9_bwd_slice(const float* __restrict__ cs, const float (&x)[9], const float (&gk)[9], float (&d)[9],
+                                             float* __restrict__ mrow) {
+    int m = 0;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) {
+        if (S == 3) {   // the degree-1 monomials go to the lightest slice
+            S9_COEF(m)
+            float q = 0.f;
+#pragma unroll
+            for (int k = 0; k < 9; ++k) q = fmaf(gk[k], cf_[k], q);
+            mrow[m] = x[i];
+            d[i] += q;
+        }
+        ++m;
+    }
+#pragma unroll
+    for (int i = 0; i < 9; ++i)
+#pragma unroll
+        for (int j = i; j < 9; ++j) {
+            if (s9_owner(i) == S) {
+                S9_COEF(m)
+                float q = 0.f;
+#pragma unroll
+                for (int k = 0; k < 9; ++k) q = fmaf(gk[k], cf_[k], q);
+                mrow[m] = x[i] * x[j];
+                d[i] = fmaf(q, x[j], d[i]);
+                d[j] = fmaf(q, x[i], d[j]);
+            }
+            ++m;
+        }
+#pragma unroll
+    for (int i = 0; i < 9; ++i)
+#pragma unroll
+        for (int j = i; j < 9; ++j) {
+            const float pij = x[i] * x[j];
+#pragma unroll
+            for (int kk = j; kk < 9; ++kk) {
+                if (s9_owner(i) == S) {
+                    S9_COEF(m)
+                    float q = 0.f;
+#pragma unroll
+                    for (int k = 0; k < 9; ++k) q = fmaf(gk[k], cf_[k], q);
+                    mrow[m] = pij * x[kk];
+                    const float qk = q * x[kk];
+                    d[kk] = fmaf(q, pij, d[kk]);
+                    d[i] = fmaf(qk, x[j], d[i]);
+                    d[j] = fmaf(qk, x[i], d[j]);
+                }
+                ++m;
+            }
+        }
+}
+
+__global__ void __launch_bounds__(256, 2) symcontract9_bwd_kernel(SCArgs a, const float* __restrict__ g, float* __restrict__ dx,
+                                                                  float* __restrict__ dcoef_parts) {
+    extern __shared__ __align__(16) float sm9[];
+    float* cs = sm9;                                  // [219][12]
+    float* gs = cs + kS9M * kS9CS;                    // [64][12]
+    float* dred = gs + kS9Tile * kS9CS;               // [4][64][9]
+    float* Ms = dred + 4 * kS9Tile * 9;               // [64][221]
+    const int c = blockIdx.y, t = threadIdx.x;
+    const int node_l = t & 63, slice = t >> 6;        // warps 0-1: slice 0, 2-3: slice 1, ...
+    s9_load_coef(a.coef + (int64_t)c * 9 * kS9M, cs, t, 256);
+    float dacc[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) dacc[k] = 0.f;
+    const int64_t ntiles = (a.N + kS9Tile - 1) / kS9Tile;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        __syncthreads();   // the previous tile's phase 2 is done with Ms / gs (and cs is loaded)
+        {
+            const int64_t b = tile * kS9Tile + node_l;
+            const bool ok = b < a.N;
+            float x[9], gk[9], d[9];
+            const float* xr = a.x + (b * a.C + c) * 9;
+            const float* gr = g + b * a.out_len;
+#pragma unroll
+            for (int i = 0; i < 9; ++i) { x[i] = ok ? __ldg(xr + i) : 0.f; d[i] = 0.f; }
+            gk[0] = ok ? __ldg(gr + c) : 0.f;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) gk[1 + k] = ok ? __ldg(gr + a.C + 3 * c + k) : 0.f;
+#pragma unroll
+            for (int k = 0; k < 5; ++k) gk[4 + k] = ok ? __ldg(gr + 4 * a.C + 5 * c + k) : 0.f;
+            if (slice == 0) {
+#pragma unroll
+                for (int k = 0; k < 9; ++k) gs[node_l * kS9CS + k] = gk[k];
+            }
+            float* mrow = Ms + node_l * kS9LM;
+            if (slice == 0) s9_bwd_slice<0>(cs, x, gk, d, mrow);
+            else if (slice == 1) s9_bwd_slice<1>(cs, x, gk, d, mrow);
+            else if (slice == 2) s9_bwd_slice<2>(cs, x, gk, d, mrow);
+            else s9_bwd_slice<3>(cs, x, gk, d, mrow);
+#pragma unroll
+            for (int i = 0; i < 9; ++i) dred[(slice * kS9Tile + node_l) * 9 + i] = d[i];
+        }
+        __syncthreads();
+        if (t < kS9Tile) {   // dx of node t: the four partial sums in slice order
+            const int64_t b = tile * kS9Tile + t;
+            if (b < a.N) {
+                float* dr = dx + (b * a.C + c) * 9;
+#pragma unroll
+                for (int i = 0; i < 9; ++i)
+                    dr[i] = (dred[(0 * kS9Tile + t) * 9 + i] + dred[(1 * kS9Tile + t) * 9 + i]) +
+                            (dred[(2 * kS9Tile + t) * 9 + i] + dred[(3 * kS9Tile + t) * 9 + i]);
+            }
+        }
+        if (t < kS9M) {
+#pragma unroll 4
+            for (int n = 0; n < kS9Tile; ++n) {   // rows beyond N hold g = 0
+                const float mv = Ms[n * kS9LM + t];
+                const float4 g0 = *reinterpret_cast<const float4*>(gs + n * kS9CS), g1 = *reinterpret_cast<const float4*>(gs + n * kS9CS + 4);
+                const float g8 = gs[n * kS9CS + 8];
+                dacc[0] = fmaf(g0.x, mv, dacc[0]); dacc[1] = fmaf(g0.y, mv, dacc[1]); dacc[2] = fmaf(g0.z, mv, dacc[2]);
+                dacc[3] = fmaf(g0.w, mv, dacc[3]); dacc[4] = fmaf(g1.x, mv, dacc[4]); dacc[5] = fmaf(g1.y, mv, dacc[5]);
+                dacc[6] = fmaf(g1.z, mv, dacc[6]); dacc[7] = fmaf(g1.w, mv, dacc[7]); dacc[8] = fmaf(g8, mv, dacc[8]);
+            }
+        }
+    }
+    if (t < kS9M) {
+        float* my = dcoef_parts + ((int64_t)blockIdx.x * a.C + c) * 9 * kS9M;
+#pragma unroll
+        for (int k = 0; k < 9; ++k) my[k * kS9M + t] = dacc[k];
+    }
+}
+
+// the fast path needs the model's output layout: out_map = (0,1,0), (1,3,0..2), (4,5,0..4)
+static bool s9_shape(int32_t C, int32_t D, int32_t K, int32_t M, int32_t out_len) { return D == 9 && K == 9 && M == kS9M && out_len == 9 * C; }
+
 static int sc_check(int64_t N, int32_t C, int32_t D, int32_t K, int32_t M) {
     GMP_REQUIRE(N >= 0 && C >= 1 && C <= 65535, "symcontract: bad N / C");
     GMP_REQUIRE(D >= 1 && D <= kSCMaxD && K >= 1 && K <= kSCMaxK && M >= 1 && M <= 256,
@@ -161,8 +433,12 @@ extern "C" {
 
 int32_t gmp_symcontract_bwd_num_parts(int64_t num_nodes) {
     const int64_t tiles = ceil_div(num_nodes > 0 ? num_nodes : 1, kSCNodes);
-    return (int32_t)(tiles < 8 ? tiles : 8);
+    return (int32_t)(tiles < 13 ? tiles : 13);   // 13 x 128 channels = 1664 CTAs = 5.6 waves of 2 CTAs per SM (94 % full)
 }
+
+// 1 when the unrolled kernels for the model shape (l_max = 2 features, correlation 3, the standard irrep-major output
+// layout) take the call, 0 when the generic kernels do
+int32_t gmp_symcontract_fast_path(int32_t C, int32_t D, int32_t K, int32_t M, int32_t out_len) { return s9_shape(C, D, K, M, out_len) ? 1 : 0; }
 
 int gmp_symcontract_fwd(const float* x, const float* coef, const int32_t* mono, const int32_t* out_map, int64_t num_nodes,
                         int32_t C, int32_t D, int32_t K, int32_t M, float* out, int32_t out_len, gmp_stream_t stream) {
@@ -170,6 +446,17 @@ int gmp_symcontract_fwd(const float* x, const float* coef, const int32_t* mono, 
     GMP_REQUIRE(coef && mono && out_map && (num_nodes == 0 || (x && out)), "symcontract_fwd: NULL pointer");
     if (num_nodes == 0) return GMP_OK;
     SCArgs a{x, coef, mono, out_map, num_nodes, C, D, K, M, out_len};
+    if (s9_shape(C, D, K, M, out_len)) {
+        constexpr int R = 2;
+        const int64_t tiles9 = ceil_div(num_nodes, 128 * R);
+        // enough CTAs for every SM: split the channels into groups when there are few node tiles
+        int groups = (int)ceil_div(8 * 4 * (int64_t)num_sms(), tiles9);   // ~8 waves of 4 CTAs per SM: a short tail
+        groups = groups < 1 ? 1 : (groups > C ? C : groups);
+        const int per = (int)ceil_div(C, groups);
+        dim3 grid9((unsigned)tiles9, (unsigned)ceil_div(C, per));
+        symcontract9_fwd_kernel<R><<<grid9, 128, 0, stream>>>(a, out, per);
+        return check_launch("symcontract9_fwd_kernel");
+    }
     const size_t smem = ((size_t)K * M + kSCNodes * (kSCMaxD + 1) + 3 * M) * sizeof(float);
     GMP_CUDA(cudaFuncSetAttribute(symcontract_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t tiles = ceil_div(num_nodes, kSCNodes);
@@ -184,6 +471,13 @@ int gmp_symcontract_bwd(const float* x, const float* coef, const int32_t* mono, 
     if (int rc = sc_check(num_nodes, C, D, K, M)) return rc;
     GMP_REQUIRE(coef && mono && out_map && dcoef_parts && (num_nodes == 0 || (x && g_out && dx)), "symcontract_bwd: NULL pointer");
     SCArgs a{x, coef, mono, out_map, num_nodes, C, D, K, M, out_len};
+    if (s9_shape(C, D, K, M, out_len)) {
+        dim3 grid9((unsigned)gmp_symcontract_bwd_num_parts(num_nodes), (unsigned)C);
+        const int smem9 = (kS9M * kS9CS + kS9Tile * kS9CS + 4 * kS9Tile * 9 + kS9Tile * kS9LM) * (int)sizeof(float);
+        GMP_CUDA(cudaFuncSetAttribute(symcontract9_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem9));
+        symcontract9_bwd_kernel<<<grid9, 256, smem9, stream>>>(a, g_out, dx, dcoef_parts);
+        return check_launch("symcontract9_bwd_kernel");
+    }
     const size_t smem = ((size_t)K * M + (size_t)kSCNodes * (M + 3) + 2 * kSCNodes * (kSCMaxD + 1) + kSCNodes * kSCMaxK + 3 * M) * sizeof(float);
     GMP_CUDA(cudaFuncSetAttribute(symcontract_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((unsigned)gmp_symcontract_bwd_num_parts(num_nodes), (unsigned)C);

@@ -417,6 +417,9 @@ int gmp_tp_ysum(const int32_t* rowptr, const int32_t* col, const int32_t* perm, 
  *   mono [M, 3]      component indices, value D = the constant 1 (pads monomials of degree < 3); M <= 256
  *   out_map [K, 3]   (component offset of the output irrep block, its dim d, local k), K <= 16
  * Replaces the three opt_einsum.contract calls per output irrep of Contraction.forward. */
+/* 1 when the fully unrolled kernels for the model shape take the call (D = 9 components of l <= 2 features, K = 9,
+ * correlation 3 = 219 monomials, irrep-major output of length 9 C), 0 when the generic kernels do. */
+int32_t gmp_symcontract_fast_path(int32_t C, int32_t D, int32_t K, int32_t M, int32_t out_len);
 int gmp_symcontract_fwd(const float* x, const float* coef, const int32_t* mono, const int32_t* out_map,
                         int64_t num_nodes, int32_t C, int32_t D, int32_t K, int32_t M, float* out, int32_t out_len,
                         gmp_stream_t stream);

@@ -26,9 +26,13 @@ def test_product_block_golden():
         check_against_digest(v.cpu(), fx["grads"][k], 2 * TOL, k)
 
 
-@pytest.mark.parametrize("C,N,corr", [(128, 200, 3), (16, 1000, 2), (8, 5, 1)])
+@pytest.mark.parametrize("C,N,corr", [(128, 200, 3), (16, 1000, 2), (8, 5, 1), (32, 777, 3), (3, 1, 3)])
 def test_symmetric_contraction_vs_oracle(C, N, corr):
+    """models/mace_modules/symmetric_contraction.py:81-85, 169-185 against the oracle.  correlation 3 on l <= 2 features is
+    the model shape and takes the unrolled kernels (ragged node counts: 777 = 3 tiles + 9, a single node); the other
+    cases take the generic ones."""
     import gmp_b200
+    assert gmp_b200._lib.lib().gmp_symcontract_fast_path(C, 9, 9, {1: 9, 2: 54, 3: 219}[corr], 9 * C) == int(corr == 3)
     ir = f"{C}x0e+{C}x1o+{C}x2e"
     torch.manual_seed(C)
     ref = R.SymmetricContraction(ir, ir, corr)
