@@ -9,6 +9,7 @@ Layout
   egnn.py      EGNNLayer / MPNNLayer / EGNNModel                   (models/layers/egnn_layer.py, models/egnn.py)
   tfn.py       TensorProductConvLayer / TFNModel                   (models/layers/tfn_layer.py, models/tfn.py)
   mace.py      SymmetricContraction / EquivariantProductBasisBlock / MACEModel (models/mace_modules, models/mace.py)
+  mace_blocks.py  the ACEsuit-style 'uvu' interaction blocks       (models/mace_modules/blocks.py:136-530)
 """
 from . import _lib  # noqa: F401
 from .graph import CSR, Graph, build_csr, get_graph, radius_graph  # noqa: F401
@@ -22,6 +23,10 @@ from .tfn import (BatchNorm, Gate, RadialEmbeddingBlock, SphericalHarmonics, Ten
                   TensorProductPlan, TFNModel, edge_geometry, first_node_pooling)
 from .mace import (Contraction, EquivariantLinear, EquivariantProductBasisBlock, MACEModel,  # noqa: F401
                    SymmetricContraction, reshape_irreps)
+from . import mace_blocks  # noqa: F401,E402
+from .mace_blocks import (AgnosticNonlinearInteractionBlock, AgnosticResidualNonlinearInteractionBlock,  # noqa: F401,E402
+                          RealAgnosticInteractionBlock, RealAgnosticResidualInteractionBlock,
+                          ResidualElementDependentInteractionBlock, UVUTensorProduct)
 from .data import Batch, Data, DataLoader, DevicePrefetcher, coalesce, to_undirected  # noqa: F401,E402
 from .graphs import GraphedStep  # noqa: F401,E402
 from . import distributed  # noqa: F401,E402

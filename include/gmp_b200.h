@@ -429,6 +429,27 @@ int gmp_symcontract_bwd(const float* x, const float* coef, const int32_t* mono, 
                         int64_t num_nodes, int32_t C, int32_t D, int32_t K, int32_t M, const float* g_out,
                         int32_t out_len, float* dx, float* dcoef_parts, gmp_stream_t stream);
 
+/* ============================================================================================ */
+/* ACEsuit-style MACE interaction: 'uvu' tensor product + scatter_sum           */
+/* ============================================================================================ */
+
+/* message[i] = sum_{e: receiver_e = i} TP_uvu(node_feats[sender_e], edge_attrs_e, w_e): replaces
+ *   mji = self.conv_tp(node_feats[sender], edge_attrs, tp_weights); scatter_sum(mji, receiver, dim=0, dim_size=N)
+ * (models/mace_modules/blocks.py:257-263, 319-325, 384-390, 446-455, 516-525) for node features C x (0e + 1o + 2e),
+ * edge attributes 0e + 1o + 2e and the 11 'uvu' instructions of irreps_tools.py:14-44 (mid blocks sorted by irrep).
+ *   rowptr/col/perm  CSR over the receivers (rows = edge_index[1], col = sender; perm = position in the caller's edge
+ *                    order or NULL when already sorted)
+ *   x          [N, 9 C]    e3nn layout          edge_attrs [E, 9]       w [E, 11 C] (instruction order, [path][channel])
+ *   out        [N, 35 C]   3 x (C x 0e) + 4 x (C x 1o) + 4 x (C x 2e), every element written once (empty rows = 0) */
+int gmp_uvu_conv_fwd(const int32_t* rowptr, const int32_t* col, const int32_t* perm, int64_t num_nodes, int64_t num_edges,
+                     const float* x, const float* edge_attrs, const float* w, int32_t C, float* out, gmp_stream_t stream);
+/* dL/dx [N, 9 C] from g = dL/dmessage [N, 35 C]; the CSR is the transposed one (rows = senders, col = receivers). */
+int gmp_uvu_conv_dx(const int32_t* rowptr, const int32_t* col, const int32_t* perm, int64_t num_nodes, int64_t num_edges,
+                    const float* g, const float* edge_attrs, const float* w, int32_t C, float* dx, gmp_stream_t stream);
+/* dL/dw [E, 11 C] in the caller's edge order; sender / receiver = the two rows of edge_index (int64). */
+int gmp_uvu_conv_dw(const int64_t* sender, const int64_t* receiver, int64_t num_edges, const float* x, const float* g,
+                    const float* edge_attrs, int32_t C, float* dw, gmp_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -422,6 +422,109 @@ class MACEModel(_EquivariantBase):
 # =========================================================================== #
 # Fixtures from the reference experiments
 # =========================================================================== #
+
+# ----------------------------------------------------------------------------------------------------------------------
+# ACEsuit-style interaction blocks -- models/mace_modules/blocks.py:136-530
+# ----------------------------------------------------------------------------------------------------------------------
+def tp_out_irreps_with_instructions(irreps1, irreps2, target_irreps):
+    """irreps_tools.py:14-44: one 'uvu' instruction per (feature block, edge block, admissible l_out in the target); the
+    output blocks are then sorted by irrep and the instruction's output index follows the permutation."""
+    irreps1, irreps2, target_irreps = o3.Irreps(irreps1), o3.Irreps(irreps2), o3.Irreps(target_irreps)
+    blocks, ins = [], []
+    for i, (mul, ir_in) in enumerate(irreps1):
+        for j, (_, ir_edge) in enumerate(irreps2):
+            for ir_out in ir_in * ir_edge:
+                if ir_out in target_irreps:
+                    ins.append((i, j, len(blocks), "uvu", True))
+                    blocks.append((mul, ir_out))
+    mid, permut, _ = o3.Irreps(blocks).sort()
+    return mid, [(a, b, permut[c], mode, train) for a, b, c, mode, train in ins]
+
+
+def linear_out_irreps(irreps, target_irreps):
+    """irreps_tools.py:47-62."""
+    out = []
+    for _, ir_in in o3.Irreps(irreps):
+        hit = [(mul, ir_out) for mul, ir_out in o3.Irreps(target_irreps) if ir_in == ir_out]
+        if not hit:
+            raise RuntimeError(f"{ir_in} not in {target_irreps}")
+        out.append(hit[0])
+    return o3.Irreps(out)
+
+
+class TensorProductWeightsBlock(nn.Module):
+    """blocks.py:177-203."""
+
+    def __init__(self, num_elements, num_edge_feats, num_feats_out):
+        super().__init__()
+        w = torch.empty(num_elements, num_edge_feats, num_feats_out)
+        nn.init.xavier_uniform_(w)
+        self.weights = nn.Parameter(w)
+
+    def forward(self, sender_or_receiver_node_attrs, edge_feats):
+        return torch.einsum("be,ba,aek->bk", edge_feats, sender_or_receiver_node_attrs, self.weights)
+
+
+class InteractionBlock(nn.Module):
+    """The five concrete blocks of blocks.py:206-530 differ in three choices, given here as ``kind``:
+    ================================================  ==========  ==================  =========================================
+    kind (reference class, blocks.py line)            radial net  irreps_out          skip_tp / return
+    ================================================  ==========  ==================  =========================================
+    residual_element (ResidualElementDependent, 206)  per element linear_out_irreps   msg + skip_tp(node_feats, attrs)
+    agnostic_nonlinear (AgnosticNonlinear, 276)       MLP         linear_out_irreps   skip_tp(msg, attrs)
+    agnostic_residual_nonlinear (..., 330)            MLP         linear_out_irreps   msg + skip_tp(node_feats, attrs)
+    real_agnostic (RealAgnostic, 396)                 MLP         target_irreps       (reshape(skip_tp(msg, attrs)), None)
+    real_agnostic_residual (..., 462)                 MLP         target_irreps       (reshape(msg), skip_tp(node_feats, attrs) -> hidden)
+    ================================================  ==========  ==================  =========================================
+    Common body (e.g. :440-455): linear_up -> conv_tp(node_feats[sender], edge_attrs, w(edge_feats)) -> scatter_sum over the
+    receivers with dim_size = N -> linear -> / avg_num_neighbors."""
+
+    def __init__(self, kind, node_attrs_irreps, node_feats_irreps, edge_attrs_irreps, edge_feats_irreps, target_irreps,
+                 hidden_irreps, avg_num_neighbors):
+        super().__init__()
+        from .thirdparty.e3nn_nn import FullyConnectedNet
+        I = o3.Irreps
+        self.kind, self.avg_num_neighbors = kind, avg_num_neighbors
+        node_attrs_irreps, node_feats_irreps, target_irreps = I(node_attrs_irreps), I(node_feats_irreps), I(target_irreps)
+        self.linear_up = o3.Linear(node_feats_irreps, node_feats_irreps, internal_weights=True, shared_weights=True)
+        irreps_mid, instructions = tp_out_irreps_with_instructions(node_feats_irreps, edge_attrs_irreps, target_irreps)
+        self.conv_tp = o3.TensorProduct(node_feats_irreps, I(edge_attrs_irreps), irreps_mid, instructions=instructions,
+                                        shared_weights=False, internal_weights=False)
+        n_edge = I(edge_feats_irreps).num_irreps
+        if kind == "residual_element":
+            self.conv_tp_weights = TensorProductWeightsBlock(node_attrs_irreps.num_irreps, n_edge, self.conv_tp.weight_numel)
+        else:
+            self.conv_tp_weights = FullyConnectedNet([n_edge] + 3 * [64] + [self.conv_tp.weight_numel], F.silu)
+        irreps_mid = irreps_mid.simplify()
+        self.irreps_out = target_irreps if kind.startswith("real") else linear_out_irreps(irreps_mid, target_irreps).simplify()
+        self.linear = o3.Linear(irreps_mid, self.irreps_out, internal_weights=True, shared_weights=True)
+        skip_in = self.irreps_out if kind in ("agnostic_nonlinear", "real_agnostic") else node_feats_irreps
+        skip_out = I(hidden_irreps) if kind == "real_agnostic_residual" else self.irreps_out
+        self.skip_tp = o3.FullyConnectedTensorProduct(skip_in, node_attrs_irreps, skip_out)
+
+    def forward(self, node_attrs, node_feats, edge_attrs, edge_feats, edge_index):
+        sender, receiver = edge_index
+        n = node_feats.shape[0]
+        sc = None
+        if self.kind in ("residual_element", "agnostic_residual_nonlinear", "real_agnostic_residual"):
+            sc = self.skip_tp(node_feats, node_attrs)
+        node_feats = self.linear_up(node_feats)
+        if self.kind == "residual_element":
+            w = self.conv_tp_weights(node_attrs[sender], edge_feats)
+        else:
+            w = self.conv_tp_weights(edge_feats)
+        mji = self.conv_tp(node_feats[sender], edge_attrs, w)
+        message = scatter(mji, receiver, dim=0, dim_size=n, reduce="sum")
+        message = self.linear(message) / self.avg_num_neighbors
+        if self.kind == "real_agnostic":
+            return reshape_irreps_fn(self.skip_tp(message, node_attrs), self.irreps_out), None
+        if self.kind == "real_agnostic_residual":
+            return reshape_irreps_fn(message, self.irreps_out), sc
+        if self.kind == "agnostic_nonlinear":
+            return self.skip_tp(message, node_attrs)
+        return message + sc
+
+
 def create_kchains(k: int):
     """experiments/kchains.ipynb:71-107: two (k+2)-node chains whose k centre nodes sit at
     (0, 5i, 0); the first end node is at (-4,-3,0) in graph 0 and (+4,-3,0) in graph 1;

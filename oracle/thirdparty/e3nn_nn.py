@@ -138,7 +138,33 @@ class BatchNorm(torch.nn.Module):
         return torch.cat(fields, dim=2).reshape(batch, dim) if x.shape[1] == 1 else torch.cat(fields, dim=2)
 
 
-class FullyConnectedNet(torch.nn.Module):  # only referenced by reference dead code
-    def __init__(self, *a, **k):
+class FullyConnectedNet(torch.nn.Sequential):
+    """e3nn 0.4.4 ``nn.FullyConnectedNet(hs, act=None, variance_in=1, variance_out=1, out_act=False)`` (SURVEY.md 8f.2:
+    the radial MLP of the ACEsuit interaction blocks, models/mace_modules/blocks.py:243-246, 299-302, 428-431).
+    [upstream-recalled] A stack of bias-free layers, weight ~ randn(h_in, h_out); a layer computes
+    ``act(x @ (W / sqrt(h_in * var_in))) * sqrt(var_out)`` with ``act = normalize2mom(act)`` (second moment 1 under a
+    standard normal input), the last one without activation unless ``out_act``: ``x @ (W / sqrt(h_in * var_in / var_out))``.
+    State-dict keys ``layer{i}.weight``."""
+
+    class _Layer(torch.nn.Module):
+        def __init__(self, h_in, h_out, act, var_in, var_out):
+            super().__init__()
+            self.weight = torch.nn.Parameter(torch.randn(h_in, h_out))
+            self.act, self.h_in, self.var_in, self.var_out = act, h_in, var_in, var_out
+
+        def forward(self, x):
+            if self.act is not None:
+                x = x @ (self.weight / (self.h_in * self.var_in) ** 0.5)
+                return self.act(x) * self.var_out ** 0.5
+            return x @ (self.weight / (self.h_in * self.var_in / self.var_out) ** 0.5)
+
+    def __init__(self, hs, act=None, variance_in=1, variance_out=1, out_act=False):
         super().__init__()
-        raise NotImplementedError("e3nn.nn.FullyConnectedNet is outside the hot path (SURVEY.md §2 row 7)")
+        self.hs = list(hs)
+        act = normalize2mom(act) if act is not None else None
+        var_in = variance_in
+        for i, (h1, h2) in enumerate(zip(self.hs, self.hs[1:])):
+            last = i == len(self.hs) - 2
+            a = act if (not last or out_act) else None
+            setattr(self, f"layer{i}", FullyConnectedNet._Layer(h1, h2, a, var_in, variance_out if last else 1))
+            var_in = 1

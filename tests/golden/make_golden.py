@@ -42,6 +42,7 @@ from models.egnn import EGNNModel  # noqa: E402
 from models.layers.egnn_layer import EGNNLayer, MPNNLayer  # noqa: E402
 from models.layers.tfn_layer import TensorProductConvLayer  # noqa: E402
 from models.mace import MACEModel  # noqa: E402
+from models.mace_modules import blocks as ref_blocks  # noqa: E402
 from models.mace_modules.blocks import EquivariantProductBasisBlock, RadialEmbeddingBlock  # noqa: E402
 from models.mace_modules.cg import U_matrix_real  # noqa: E402
 from models.mace_modules.irreps_tools import irreps2gate, reshape_irreps  # noqa: E402
@@ -259,6 +260,51 @@ def main():
         save(tag, ctor=ctor, state=strip_buffers(m._state0),
              inputs=dict(atoms=d.atoms, pos=pos.detach(), edge_index=d.edge_index, batch=d.batch),
              outputs=outs, cotangent=cots, grads=grads)
+
+    interaction_blocks()
+
+
+def interaction_blocks():
+    """the five ACEsuit-style interaction blocks (models/mace_modules/blocks.py:206-530), C = 8 channels,
+    3 elements, on a 2-cloud radius graph."""
+    I = e3nn.o3.Irreps
+    C = 8
+    feats, sh_ir = I(f"{C}x0e+{C}x1o+{C}x2e"), I("1x0e+1x1o+1x2e")
+    d = random_clouds(2, 10, 3.0, 2.0, 31)
+    N, E = d.pos.shape[0], d.edge_index.shape[1]
+    vec = d.pos[d.edge_index[0]] - d.pos[d.edge_index[1]]
+    sh = e3nn.o3.SphericalHarmonics(sh_ir, normalize=True, normalization="component")
+    rad = RadialEmbeddingBlock(r_max=2.0, num_bessel=8, num_polynomial_cutoff=5)
+    for cls in ("ResidualElementDependentInteractionBlock", "AgnosticNonlinearInteractionBlock", "AgnosticResidualNonlinearInteractionBlock",
+                "RealAgnosticInteractionBlock", "RealAgnosticResidualInteractionBlock"):
+        torch.manual_seed(32)
+        ctor = dict(node_attrs_irreps="3x0e", node_feats_irreps=str(feats), edge_attrs_irreps=str(sh_ir), edge_feats_irreps="8x0e",
+                    target_irreps=str(feats), hidden_irreps=str(feats), avg_num_neighbors=5.5)
+        blk = getattr(ref_blocks, cls)(**{k: (I(v) if k.endswith("irreps") else v) for k, v in ctor.items()})
+        g = _gen(33)
+        attrs = torch.eye(3)[torch.randint(0, 3, (N,), generator=g)]
+        x = torch.randn(N, feats.dim, generator=g)
+        e_sh, e_ft = sh(vec).clone(), rad(vec.norm(dim=-1, keepdim=True)).clone()
+        outs, cots, grads = run(_NoNone(blk), (attrs, x, e_sh, e_ft, d.edge_index), {"node_feats": x, "edge_feats": e_ft}, 34)
+        grads = {k.replace("param.m.", "param."): v for k, v in grads.items()}
+        save("mace_interaction_" + cls, cls=cls, ctor=ctor, state={k[2:]: v for k, v in blk._wrap_state0.items()},
+             inputs=dict(node_attrs=attrs, node_feats=x.detach(), edge_attrs=e_sh.detach(), edge_feats=e_ft.detach(), edge_index=d.edge_index),
+             outputs=outs, cotangent=cots, grads=grads,
+             extra=dict(irreps_mid=str(blk.conv_tp.irreps_out), weight_numel=blk.conv_tp.weight_numel, irreps_out=str(blk.irreps_out),
+                        instructions=[(i.i_in1, i.i_in2, i.i_out) for i in blk.conv_tp.instructions]))
+
+
+class _NoNone(torch.nn.Module):
+    """Drops the ``None`` some blocks return as their second output (run() takes tensors only)."""
+
+    def __init__(self, m):
+        super().__init__()
+        self.m = m
+
+    def forward(self, *a):
+        out = self.m(*a)
+        self.m._wrap_state0 = self._state0
+        return tuple(o for o in out if o is not None) if isinstance(out, tuple) else out
 
 
 if __name__ == "__main__":

@@ -175,3 +175,34 @@ def test_data_batch_dataloader_match_the_pyg_restatement():
     assert len(loader) == 3 and [x.num_graphs for x in loader] == [2, 2, 1]
     assert sum(x.num_nodes for x in gmp_b200.DataLoader(ds, batch_size=2, shuffle=True)) == 28
     assert len(gmp_b200.DataLoader(ds, batch_size=2, drop_last=True)) == 2
+
+
+def test_uvu_tables_match():
+    """csrc/uvu_cg.cuh is generated (scripts/gen_uvu_cg.py) from the same wigner_3j the oracle pins; the committed header
+    must be the current render, and the instruction list / mid irreps must equal the reference run's (golden `extra`)."""
+    import importlib.util
+    import os
+    from tests.helpers import load_golden
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("gen_uvu_cg", os.path.join(root, "scripts", "gen_uvu_cg.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    assert open(os.path.join(root, "geometric-message-passing_b200", "csrc", "uvu_cg.cuh")).read() == mod.render()
+    from gmp_b200.mace_blocks import linear_out_irreps, tp_out_irreps_with_instructions
+    fx = load_golden("mace_interaction_RealAgnosticInteractionBlock")
+    mid, ins = tp_out_irreps_with_instructions(fx["ctor"]["node_feats_irreps"], fx["ctor"]["edge_attrs_irreps"], fx["ctor"]["target_irreps"])
+    assert str(mid) == fx["extra"]["irreps_mid"]
+    assert [tuple(t[:3]) for t in ins] == [tuple(t) for t in fx["extra"]["instructions"]]
+    assert str(linear_out_irreps(mid.simplify(), fx["ctor"]["target_irreps"]).simplify()) == fx["extra"]["irreps_out"]
+
+
+def test_interaction_block_state_dict_keys_match_the_reference():
+    import gmp_b200
+    from tests.helpers import load_golden
+    for cls in ("ResidualElementDependentInteractionBlock", "AgnosticNonlinearInteractionBlock", "AgnosticResidualNonlinearInteractionBlock",
+                "RealAgnosticInteractionBlock", "RealAgnosticResidualInteractionBlock"):
+        fx = load_golden("mace_interaction_" + cls)
+        m = getattr(gmp_b200, cls)(**fx["ctor"])
+        ref = {k: tuple(v.shape) for k, v in fx["state"].items() if "output_mask" not in k and not k.startswith("conv_tp.")}
+        own = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+        assert own == ref, (cls, set(own) ^ set(ref))

@@ -152,3 +152,34 @@ def test_equivariant_models(name, cls):
     b = Bag(atoms=i["atoms"], pos=i["pos"].clone(), edge_index=i["edge_index"], batch=i["batch"])
     outs, grads = _run(m, (b,), {}, fx["cotangent"])
     _check(fx, outs, grads, tol=1e-5)
+
+
+_KINDS = {"ResidualElementDependentInteractionBlock": "residual_element", "AgnosticNonlinearInteractionBlock": "agnostic_nonlinear",
+          "AgnosticResidualNonlinearInteractionBlock": "agnostic_residual_nonlinear", "RealAgnosticInteractionBlock": "real_agnostic",
+          "RealAgnosticResidualInteractionBlock": "real_agnostic_residual"}
+
+
+@pytest.mark.parametrize("cls", sorted(_KINDS))
+def test_mace_interaction_block(cls):
+    """the oracle's restatement of models/mace_modules/blocks.py:206-530 against the reference run."""
+    fx = load_golden("mace_interaction_" + cls)
+    m = load_params(R.InteractionBlock(_KINDS[cls], **fx["ctor"]), fx["state"])
+    assert str(m.conv_tp.irreps_out) == fx["extra"]["irreps_mid"] and m.conv_tp.weight_numel == fx["extra"]["weight_numel"]
+    assert [(i.i_in1, i.i_in2, i.i_out) for i in m.conv_tp.instructions] == [tuple(t) for t in fx["extra"]["instructions"]]
+    i = fx["inputs"]
+    x, ef = i["node_feats"].clone(), i["edge_feats"].clone()
+
+    def fwd(*a):
+        out = m(*a)
+        return tuple(o for o in out if o is not None) if isinstance(out, tuple) else out
+
+    class W(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.m = m
+
+        def forward(self, *a):
+            return fwd(*a)
+
+    outs, grads = _run(W(), (i["node_attrs"], x, i["edge_attrs"], ef, i["edge_index"]), {"node_feats": x, "edge_feats": ef}, fx["cotangent"])
+    _check(fx, outs, {k.replace("param.m.", "param."): v for k, v in grads.items()})
