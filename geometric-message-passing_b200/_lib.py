@@ -83,9 +83,9 @@ _SIGS = {
     "gmp_tp_tc_contract": [P, P, P, I64, I64, P, I32, P, I32, P, P, I32, P, P, P, I32, I32, I32, P, P],
     "gmp_tp_tc_dhid": [P, P, P, P, I64, I64, P, I32, P, I32, P, I32, P, I32, P, P, P, P, I32, I32, I32, P, P, P],
     "gmp_tp_tc_dw2": [P, P, P, P, I64, I64, P, I32, P, I32, P, I32, P, P, I32, I32, P, I64, I32, P, P],
-    "gmp_uvu_conv_fwd": [P, P, P, I64, I64, P, P, P, I32, P],
-    "gmp_uvu_conv_dx": [P, P, P, I64, I64, P, P, P, I32, P],
-    "gmp_uvu_conv_dw": [P, P, I64, P, P, P, I32, P],
+    "gmp_uvu_conv_fwd": [P, P, P, I64, I64, P, P, P, I32, P, P],
+    "gmp_uvu_conv_dx": [P, P, P, I64, I64, P, P, P, I32, P, P],
+    "gmp_uvu_conv_dw": [P, P, I64, P, P, P, I32, P, P],
     "gmp_tp_wgrad": [P, P, P, I64, I64, P, I32, P, I32, P, I32, P, I32, P, P, P, I32, P, I32, P, P, P, P, I32, P],
 }
 _PLAIN = {"gmp_version": (I32, []), "gmp_last_error": (C.c_char_p, []),

@@ -51,3 +51,18 @@ def test_no_cpu_fallback():
     import gmp_b200
     with pytest.raises(gmp_b200._lib.GmpError):
         gmp_b200.scatter(torch.zeros(4, 4), torch.zeros(4, dtype=torch.long), dim=0, dim_size=2)
+
+
+def test_binding_arity_matches_header():
+    """Every ctypes signature has as many arguments as the header's declaration (a missing trailing stream argument makes
+    ctypes read a garbage pointer: a host-side crash, not an error code)."""
+    import gmp_b200
+    txt = re.sub(r"/\*.*?\*/", "", open(HEADER).read(), flags=re.S)
+    arity = {}
+    for name, params in re.findall(r"\b(gmp_[a-z0-9_]+)\s*\(([^)]*)\)\s*;", txt):
+        params = params.strip()
+        arity[name] = 0 if params in ("", "void") else params.count(",") + 1
+    sigs = dict(gmp_b200._lib._SIGS)
+    sigs.update({k: v[1] for k, v in gmp_b200._lib._PLAIN.items()})
+    bad = {k: (len(v), arity.get(k)) for k, v in sigs.items() if arity.get(k) != len(v)}
+    assert not bad, f"ctypes arity != header arity: {bad}"
