@@ -33,6 +33,11 @@ class SchnetFilter(C.Structure):
                 ("cutoff", F32), ("gauss_offset", P), ("gauss_coeff", F32)]
 
 
+class NodeStage(C.Structure):
+    _fields_ = [("w_img", P), ("bias", P), ("ln_g", P), ("ln_b", P), ("ln_eps", F32), ("act", I32), ("mul_aux", P), ("mul_mode", I32),
+                ("add_res", P), ("out_f32", P), ("out_bf16", P), ("out_pre", P)]
+
+
 class EgnnParams(C.Structure):
     _fields_ = [(k, P) for k in ("wd", "ln1_g", "ln1_b", "w1", "b1", "ln2_g", "ln2_b", "w2", "b2", "ln3_g", "ln3_b",
                                  "w3", "b3")] + [("d", I32), ("act", I32), ("ln_eps", F32), ("aggr_mean", I32)]
@@ -86,13 +91,15 @@ _SIGS = {
     "gmp_uvu_conv_fwd": [P, P, P, I64, I64, P, P, P, I32, P, P],
     "gmp_uvu_conv_dx": [P, P, P, I64, I64, P, P, P, I32, P, P],
     "gmp_uvu_conv_dw": [P, P, I64, P, P, P, I32, P, P],
+    "gmp_node_pack_w": [P, I32, I32, I32, P, P],
+    "gmp_node_chain_tc": [P, P, I64, I32, P, P],
     "gmp_tp_wgrad": [P, P, P, I64, I64, P, I32, P, I32, P, I32, P, I32, P, P, P, I32, P, I32, P, P, P, P, I32, P],
 }
 _PLAIN = {"gmp_version": (I32, []), "gmp_last_error": (C.c_char_p, []),
           "gmp_schnet_bwd_num_parts": (I32, [I64]), "gmp_schnet_bwd_part_len": (I64, [I32, I32]),
           "gmp_egnn_bwd_num_parts": (I32, [I64]), "gmp_egnn_tc_bwd_num_parts": (I32, [I64]), "gmp_egnn_tc2_num_chunks": (I32, [I64]), "gmp_linear_wgrad_num_parts": (I32, [I64]), "gmp_schnet_tc2_num_chunks": (I32, [I64]), "gmp_egnn_bwd_part_len": (I64, [I32]),
           "gmp_tp_contract_smem_bytes": (I64, [I32, I32]), "gmp_symcontract_bwd_num_parts": (I32, [I64]), "gmp_symcontract_fast_path": (I32, [I32, I32, I32, I32, I32]), "gmp_tp_wgrad_part_len": (I64, [I32]),
-          "gmp_tp_tc_num_chunks": (I32, [I64]), "gmp_tp_tc_hid_bytes": (I64, [I64, I32]), "gmp_tp_tc_w2_bytes": (I64, [I32, I32])}
+          "gmp_node_w_image_bytes": (I64, [I32, I32, I32]), "gmp_tp_tc_num_chunks": (I32, [I64]), "gmp_tp_tc_hid_bytes": (I64, [I64, I32]), "gmp_tp_tc_w2_bytes": (I64, [I32, I32])}
 
 
 def exported_symbols():

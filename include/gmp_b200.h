@@ -450,6 +450,43 @@ int gmp_uvu_conv_dx(const int32_t* rowptr, const int32_t* col, const int32_t* pe
 int gmp_uvu_conv_dw(const int64_t* sender, const int64_t* receiver, int64_t num_edges, const float* x, const float* g,
                     const float* edge_attrs, int32_t C, float* dw, gmp_stream_t stream);
 
+/* ============================================================================================ */
+/* Node-side dense chains on tcgen05 (GMP_BF16_TC): nn.Linear layers with fused epilogues         */
+/* ============================================================================================ */
+
+/* Replaces, per 128-row tile and without intermediate HBM round trips, chains of up to three 128-wide nn.Linear layers
+ * and their elementwise neighbours:
+ *   SchNet  CFConv.lin2 -> ShiftedSoftplus -> InteractionBlock.lin -> residual -> next CFConv.lin1   (PyG blocks built at
+ *           models/schnet.py:41-54, residual at :72) and the transposed chain of the backward pass;
+ *   EGNN    mlp_upd = Linear(2d, d), LayerNorm, act, Linear(d, d), LayerNorm, act   (models/layers/egnn_layer.py:41-48, 82-86);
+ *   single layers (EGNN P / Q projections, o3.Linear blocks).
+ * Stage s computes  v = A_s W_s^T + bias;  [out_pre = v];  v = LayerNorm(v) * ln_g + ln_b;  v = act(v);
+ *                   v *= f(mul_aux);  v += add_res;  [out_f32 = v];  [out_bf16 = bf16(v)];  A_{s+1} = bf16(v)
+ * with bf16 operands and fp32 accumulation.  A_0 = a0 (fp32 [n,128]) or cat[a0, a1] along the columns (K = 256). */
+enum { GMP_NODE_ACT_NONE = 0, GMP_NODE_ACT_SSP = 1, GMP_NODE_ACT_RELU = 2, GMP_NODE_ACT_SILU = 3 };
+enum { GMP_NODE_MUL_PLAIN = 0, GMP_NODE_MUL_DSSP = 1 };   /* DSSP: multiply by 1 - exp(-(aux + ln 2)) = ssp'(pre) given aux = ssp(pre) */
+typedef struct gmp_node_stage {
+    const void* w_img;      /* operand image from gmp_node_pack_w (stage 0 with two sources: both images, contiguous) */
+    const float* bias;      /* [128] or NULL */
+    const float* ln_g;      /* LayerNorm weight / bias [128], both or neither */
+    const float* ln_b;
+    float ln_eps;
+    int32_t act;            /* GMP_NODE_ACT_* */
+    const float* mul_aux;   /* [n,128] or NULL */
+    int32_t mul_mode;       /* GMP_NODE_MUL_* */
+    const float* add_res;   /* [n,128] or NULL */
+    float* out_f32;         /* [n,128] or NULL */
+    void* out_bf16;         /* [n,128] bf16 or NULL */
+    float* out_pre;         /* [n,128] pre-LayerNorm values (for the backward pass) or NULL */
+} gmp_node_stage;
+/* bytes of the operand image of W [out_dim, in_dim] (fp32, row-major, nn.Linear layout); -1 if the shape is not served.
+ * transpose = 0: the image of W itself (y = x W^T, out_dim = 128, in_dim = 128 or 256);
+ * transpose = 1: the image of W^T (dx = g W, in_dim = 128, out_dim = 128 or 256). */
+int64_t gmp_node_w_image_bytes(int32_t out_dim, int32_t in_dim, int32_t transpose);
+int gmp_node_pack_w(const float* w, int32_t out_dim, int32_t in_dim, int32_t transpose, void* img, gmp_stream_t stream);
+int gmp_node_chain_tc(const float* a0, const float* a1, int64_t num_rows, int32_t nstage, const gmp_node_stage* stages,
+                      gmp_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
