@@ -30,14 +30,15 @@ def pack_w(weight: torch.Tensor, transpose: bool = False) -> torch.Tensor:
 def stage(w_img: torch.Tensor, bias: Optional[torch.Tensor] = None, ln: Optional[Sequence] = None, act: Optional[str] = None,
           mul_aux: Optional[torch.Tensor] = None, mul_mode: int = MUL_PLAIN, add_res: Optional[torch.Tensor] = None,
           out_f32: Optional[torch.Tensor] = None, out_bf16: Optional[torch.Tensor] = None, out_pre: Optional[torch.Tensor] = None):
-    """One stage description; ``ln`` = (weight, bias, eps).  The tensors must stay alive until the launch (the caller's
-    locals do)."""
+    """One stage description; ``ln`` = (weight, bias, eps).  The returned struct keeps its tensors alive (``_keep``)."""
     g, b, eps = (ln[0], ln[1], float(ln[2])) if ln is not None else (None, None, 0.0)
     for t_ in (out_f32, out_pre, mul_aux, add_res):
         assert t_ is None or (t_.dtype == torch.float32 and t_.shape[-1] == 128)
     assert out_bf16 is None or out_bf16.dtype == torch.bfloat16
-    return NodeStage(ptr(w_img), ptr(bias), ptr(g), ptr(b), eps, ACT[act], ptr(mul_aux), mul_mode, ptr(add_res), ptr(out_f32),
-                     ptr(out_bf16), ptr(out_pre))
+    st = NodeStage(ptr(w_img), ptr(bias), ptr(g), ptr(b), eps, ACT[act], ptr(mul_aux), mul_mode, ptr(add_res), ptr(out_f32),
+                   ptr(out_bf16), ptr(out_pre))
+    st._keep = (w_img, bias, g, b, mul_aux, add_res, out_f32, out_bf16, out_pre)   # the struct holds raw pointers only
+    return st
 
 
 def run(a0: torch.Tensor, stages: Sequence[NodeStage], a1: Optional[torch.Tensor] = None) -> None:

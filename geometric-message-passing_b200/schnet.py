@@ -210,6 +210,115 @@ def node_linear(lin: Linear, x: torch.Tensor, precision: str) -> torch.Tensor:
     return lin(x)
 
 
+
+class _SchNetBodyFn(torch.autograd.Function):
+    """All interaction blocks of the model (models/schnet.py:71-72: ``h = h + interaction(h, edge_index, edge_weight, edge_attr)``)
+    as one autograd node in the bf16 mode: per block one pipelined CFConv edge kernel (csrc/schnet_tc2.cu) and ONE node-side
+    chain kernel (csrc/node_chain.cu: lin2 -> ssp -> lin -> + h -> the next block's lin1, rows resident on the SM between
+    the three GEMMs), and the mirrored pair in the backward pass plus the tensor-core weight-gradient reductions.  Nothing
+    elementwise is left to ATen and no node-side GEMM to cuBLAS.  Parameters per block, in order: mlp.0.weight, mlp.0.bias,
+    mlp.2.weight, mlp.2.bias, conv.lin1.weight, conv.lin2.weight, conv.lin2.bias, lin.weight, lin.bias."""
+
+    NP = 9
+
+    @staticmethod
+    def forward(ctx, h0, edge_weight, graph: Graph, cutoff, offset, coeff, *params):
+        from . import nodechain as nc
+        L = len(params) // _SchNetBodyFn.NP
+        P = [[t.detach().contiguous() for t in params[l * 9:(l + 1) * 9]] for l in range(L)]
+        n, E, dev = graph.n, graph.E, h0.device
+        train = torch.is_grad_enabled() and (h0.requires_grad or any(p.requires_grad for p in params))
+        csr = graph.by_dst
+        keep_row = graph.by_src.inv_perm() if train else None
+        nchunks = int(_lib.lib().gmp_schnet_tc2_num_chunks(E))
+        f32 = dict(dtype=torch.float32, device=dev)
+        h = h0.contiguous()
+        x1 = torch.empty(n, 128, dtype=torch.bfloat16, device=dev)
+        nc.run(h, [nc.stage(nc.pack_w(P[0][4]), out_bf16=x1)])
+        saved = []
+        for l in range(L):
+            w1f, b1f, w2f, b2f, _, w_lin2, b_lin2, w_lin, b_lin = P[l]
+            filt = SchnetFilter(ptr(w1f), ptr(b1f), ptr(w2f), ptr(b2f), w1f.shape[1], w1f.shape[0], float(cutoff), ptr(offset), float(coeff))
+            agg = torch.empty(n, 128, **f32)
+            head = torch.empty(nchunks, 128, **f32)
+            keep = torch.empty(E, 128, dtype=torch.bfloat16, device=dev) if train else None
+            call("gmp_schnet_cfconv_fwd_tc2_keep", ptr(csr.rowptr), ptr(csr.col), csr.perm_ptr, ptr(csr.row_ids()), n, E,
+                 ptr(edge_weight), ptr(x1), C.byref(filt), ptr(agg), ptr(head), ptr(keep), ptr(keep_row))
+            y, hn = torch.empty(n, 128, **f32), torch.empty(n, 128, **f32)
+            stages = [nc.stage(nc.pack_w(w_lin2), b_lin2, act="ssp", out_f32=y), nc.stage(nc.pack_w(w_lin), b_lin, add_res=h, out_f32=hn)]
+            x1n = None
+            if l + 1 < L:
+                x1n = torch.empty(n, 128, dtype=torch.bfloat16, device=dev)
+                stages.append(nc.stage(nc.pack_w(P[l + 1][4]), out_bf16=x1n))
+            nc.run(agg, stages)
+            if train:
+                saved.append((h, x1, agg, y, keep))
+            h, x1 = hn, x1n
+        ctx.saved, ctx.P, ctx.graph, ctx.meta, ctx.ew = saved, P, graph, (float(cutoff), float(coeff)), edge_weight
+        ctx.offset = offset
+        return h
+
+    @staticmethod
+    def backward(ctx, G):
+        from . import nodechain as nc
+        graph: Graph = ctx.graph
+        P, saved, ew, offset = ctx.P, ctx.saved, ctx.ew, ctx.offset
+        cutoff, coeff = ctx.meta
+        L, n, E, dev = len(P), graph.n, graph.E, G.device
+        f32 = dict(dtype=torch.float32, device=dev)
+        lib = _lib.lib()
+        csr, t = graph.by_dst, graph.by_src
+        G = G.contiguous()
+
+        def wgrad(g, x, bias=True):
+            nparts, plen = lib.gmp_linear_wgrad_num_parts(n), 128 * 128 + 128
+            parts = torch.empty(nparts, plen, **f32)
+            call("gmp_linear_wgrad_tc", ptr(g), ptr(x), n, 128, 128, ptr(parts))
+            red = torch.empty(plen, **f32)
+            call("gmp_reduce_partials_f32", ptr(parts), nparts, plen, ptr(red))
+            return red[:128 * 128].view(128, 128), (red[128 * 128:] if bias else None)
+
+        grads = [None] * (L * 9)
+        dx1_next = None     # dL/dx1 of block l + 1 (fp32)
+        for l in range(L - 1, -1, -1):
+            w1f, b1f, w2f, b2f, w_lin1, w_lin2, b_lin2, w_lin, b_lin = P[l]
+            h, x1, agg, y, keep = saved[l]
+            dT, dagg = torch.empty(n, 128, **f32), torch.empty(n, 128, **f32)
+            dagg16 = torch.empty(n, 128, dtype=torch.bfloat16, device=dev)
+            tail = [nc.stage(nc.pack_w(w_lin, True), mul_aux=y, mul_mode=nc.MUL_DSSP, out_f32=dT),
+                    nc.stage(nc.pack_w(w_lin2, True), out_f32=dagg, out_bf16=dagg16)]
+            if dx1_next is None:
+                Gt = G
+                nc.run(G, tail)
+            else:
+                Gt = torch.empty(n, 128, **f32)
+                nc.run(dx1_next, [nc.stage(nc.pack_w(P[l + 1][4], True), add_res=G, out_f32=Gt)] + tail)
+                grads[(l + 1) * 9 + 4], _ = wgrad(dx1_next, saved[l + 1][0], bias=False)
+            grads[l * 9 + 7], grads[l * 9 + 8] = wgrad(Gt, y)
+            grads[l * 9 + 5], grads[l * 9 + 6] = wgrad(dT, agg)
+            # CFConv backward: dL/dx1 over the kept filter values, filter-MLP gradients from the pipelined kernel
+            dx1 = torch.empty(n, 128, **f32)
+            call("gmp_gather_mul_segsum_wbf16", ptr(t.rowptr), ptr(t.col), None, ptr(dagg16), 1, ptr(keep), ptr(dx1), n, 128)
+            F_, G_ = w1f.shape
+            filt = SchnetFilter(ptr(w1f), ptr(b1f), ptr(w2f), ptr(b2f), G_, F_, cutoff, ptr(offset), coeff)
+            nparts, plen = lib.gmp_schnet_bwd_num_parts(E), lib.gmp_schnet_bwd_part_len(G_, F_)
+            parts = torch.empty(nparts, plen, **f32)
+            call("gmp_schnet_cfconv_bwd_tc2", ptr(csr.rowptr), ptr(csr.col), csr.perm_ptr, ptr(csr.row_ids()), n, E, ptr(ew), ptr(x1),
+                 C.byref(filt), ptr(dagg), ptr(parts), nparts)
+            red = torch.empty(plen, **f32)
+            call("gmp_reduce_partials_f32", ptr(parts), nparts, plen, ptr(red))
+            o = 0
+            grads[l * 9 + 0] = red[o:o + F_ * 64].view(F_, 64)[:, :G_].contiguous(); o += F_ * 64
+            grads[l * 9 + 1] = red[o:o + F_]; o += F_
+            grads[l * 9 + 2] = red[o:o + F_ * F_].view(F_, F_); o += F_ * F_
+            grads[l * 9 + 3] = red[o:o + F_]
+            G, dx1_next = Gt, dx1
+        dh0 = torch.empty(n, 128, **f32)
+        nc.run(dx1_next, [nc.stage(nc.pack_w(P[0][4], True), add_res=G, out_f32=dh0)])
+        grads[4], _ = wgrad(dx1_next, saved[0][0], bias=False)
+        return (dh0, None, None, None, None, None, *grads)
+
+
 class CFConv(nn.Module):
     """PyG ``CFConv`` (aggr='add', flow source_to_target): gather x1[edge_index[0]], reduce at edge_index[1]."""
 
@@ -294,14 +403,29 @@ class SchNetModel(nn.Module):
         self.lin1.bias.data.fill_(0)
         self.pool = {"mean": global_mean_pool, "sum": global_add_pool}[pool]
         self.lin2 = Linear(hidden_channels // 2, out_dim)
+        self.fuse_body = True   # bf16 mode: all interaction blocks as one autograd node on the chain kernels (_SchNetBodyFn)
+
+    def _fused_body_ok(self, h, edge_weight, graph) -> bool:
+        """bf16 mode at the width the chain / pipelined kernels are built for, no gradient w.r.t. the distances."""
+        return (self.fuse_body and self.interactions[0].conv.precision == "bf16" and h.is_cuda and self.hidden_channels == 128
+                and self.num_filters == 128 and self.num_gaussians <= 63 and graph.E > 0 and graph.n > 0
+                and not (torch.is_grad_enabled() and edge_weight.requires_grad))
 
     def forward(self, batch):
         h = embedding_lookup(self.embedding, batch.atoms)
         graph = get_graph(batch.edge_index, h.shape[0])
         edge_weight = edge_length(batch.pos, graph)
         edge_attr = self.distance_expansion.lazy()
-        for interaction in self.interactions:
-            h = h + interaction(h, batch.edge_index, edge_weight, edge_attr)
+        if self._fused_body_ok(h, edge_weight, graph):
+            params = []
+            for it in self.interactions:
+                params += [it.mlp[0].weight, it.mlp[0].bias, it.mlp[2].weight, it.mlp[2].bias, it.conv.lin1.weight, it.conv.lin2.weight,
+                           it.conv.lin2.bias, it.lin.weight, it.lin.bias]
+            sm = self.distance_expansion
+            h = _SchNetBodyFn.apply(h, edge_weight, graph, self.cutoff, sm.offset, sm.coeff, *params)
+        else:
+            for interaction in self.interactions:
+                h = h + interaction(h, batch.edge_index, edge_weight, edge_attr)
         # PyG's Batch carries num_graphs; without it the pool has to read batch.max() back (one host sync per step)
         out = self.pool(h, batch.batch, getattr(batch, "num_graphs", None))
         out = self.lin1(out)
