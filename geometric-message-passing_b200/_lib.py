@@ -93,13 +93,14 @@ _SIGS = {
     "gmp_uvu_conv_dw": [P, P, I64, P, P, P, I32, P, P],
     "gmp_node_pack_w": [P, I32, I32, I32, P, P],
     "gmp_node_chain_tc": [P, P, I64, I32, P, P],
+    "gmp_ln_act_bwd": [P, P, P, P, F32, I32, I64, P, P, P, P],
     "gmp_tp_wgrad": [P, P, P, I64, I64, P, I32, P, I32, P, I32, P, I32, P, P, P, I32, P, I32, P, P, P, P, I32, P],
 }
 _PLAIN = {"gmp_version": (I32, []), "gmp_last_error": (C.c_char_p, []),
           "gmp_schnet_bwd_num_parts": (I32, [I64]), "gmp_schnet_bwd_part_len": (I64, [I32, I32]),
           "gmp_egnn_bwd_num_parts": (I32, [I64]), "gmp_egnn_tc_bwd_num_parts": (I32, [I64]), "gmp_egnn_tc2_num_chunks": (I32, [I64]), "gmp_linear_wgrad_num_parts": (I32, [I64]), "gmp_schnet_tc2_num_chunks": (I32, [I64]), "gmp_egnn_bwd_part_len": (I64, [I32]),
           "gmp_tp_contract_smem_bytes": (I64, [I32, I32]), "gmp_symcontract_bwd_num_parts": (I32, [I64]), "gmp_symcontract_fast_path": (I32, [I32, I32, I32, I32, I32]), "gmp_tp_wgrad_part_len": (I64, [I32]),
-          "gmp_node_w_image_bytes": (I64, [I32, I32, I32]), "gmp_tp_tc_num_chunks": (I32, [I64]), "gmp_tp_tc_hid_bytes": (I64, [I64, I32]), "gmp_tp_tc_w2_bytes": (I64, [I32, I32])}
+          "gmp_node_w_image_bytes": (I64, [I32, I32, I32]), "gmp_ln_act_bwd_num_parts": (I32, [I64]), "gmp_tp_tc_num_chunks": (I32, [I64]), "gmp_tp_tc_hid_bytes": (I64, [I64, I32]), "gmp_tp_tc_w2_bytes": (I64, [I32, I32])}
 
 
 def exported_symbols():

@@ -41,11 +41,20 @@ struct NodeChainArgs {
     gmp_node_stage st[kNcMaxStages];
 };
 
+// MUFU-based transcendentals (ex2 / lg2 / rcp approximations, ~1e-6 relative): this kernel only exists in the bf16-operand mode,
+// whose next GEMM rounds these values to 8 mantissa bits anyway; the precise expf / log1pf forms cost 60 us per 16 M elements.
+__device__ __forceinline__ float ex2_fast(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float lg2_fast(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+// softplus(x) - ln 2 = max(x, 0) + ln(1 + exp(-|x|)) - ln 2
+__device__ __forceinline__ float ssp_fast(float x) {
+    const float u = ex2_fast(-fabsf(x) * 1.4426950408889634f);
+    return fmaf(lg2_fast(1.f + u), 0.6931471805599453f, fmaxf(x, 0.f) - 0.6931471805599453f);
+}
 __device__ __forceinline__ float act_apply(float v, int act) {
     switch (act) {
-        case GMP_NODE_ACT_SSP: return ssp(v);
+        case GMP_NODE_ACT_SSP: return ssp_fast(v);
         case GMP_NODE_ACT_RELU: return fmaxf(v, 0.f);
-        case GMP_NODE_ACT_SILU: return v * sigmoidf_(v);
+        case GMP_NODE_ACT_SILU: return __fdividef(v, 1.f + ex2_fast(-1.4426950408889634f * v));
         default: return v;
     }
 }
@@ -53,12 +62,13 @@ __device__ __forceinline__ float act_apply(float v, int act) {
 // 128 rows x 128 fp32 columns of `src` starting at row0 -> bf16 K-major swizzled image; 128 threads (r = 0..127)
 __device__ __forceinline__ void load_tile_image(const float* __restrict__ src, int64_t row0, int64_t n, uint8_t* img, int r) {
     const int ch = r & 15, rr0 = r >> 4;
+    // two batches of 8 rows per thread: 16 independent 16-byte loads in flight per thread (the tile load is latency-bound)
 #pragma unroll
-    for (int b = 0; b < 4; ++b) {
-        float4 lo[4], hi[4];
+    for (int b = 0; b < 2; ++b) {
+        float4 lo[8], hi[8];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int64_t row = row0 + rr0 + 8 * (4 * b + i);
+        for (int i = 0; i < 8; ++i) {
+            const int64_t row = row0 + rr0 + 8 * (8 * b + i);
             lo[i] = hi[i] = make_float4(0.f, 0.f, 0.f, 0.f);
             if (row < n) {
                 lo[i] = ldg4(src + row * 128 + ch * 8);
@@ -66,12 +76,57 @@ __device__ __forceinline__ void load_tile_image(const float* __restrict__ src, i
             }
         }
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int rr = rr0 + 8 * (4 * b + i);
+        for (int i = 0; i < 8; ++i) {
+            const int rr = rr0 + 8 * (8 * b + i);
             *reinterpret_cast<uint4*>(img + (ch >> 3) * kNcSlab + sw128_chunk_off(rr, ch & 7)) =
                 make_uint4(pack_bf16(lo[i].x, lo[i].y), pack_bf16(lo[i].z, lo[i].w), pack_bf16(hi[i].x, hi[i].y), pack_bf16(hi[i].z, hi[i].w));
         }
     }
+}
+
+// one quarter (32 of the 128 rows: 4 per thread) of the next tile's image, split into issue (registers) and commit, so that
+// the loads are in flight while the caller works on something else
+__device__ __forceinline__ void tile_quarter_issue(const float* __restrict__ src, int64_t row0, int64_t n, int r, int q, float4 (&lo)[4], float4 (&hi)[4]) {
+    const int ch = r & 15, rr0 = r >> 4;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int64_t row = row0 + rr0 + 8 * (4 * q + i);
+        lo[i] = hi[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (row < n) {
+            lo[i] = ldg4(src + row * 128 + ch * 8);
+            hi[i] = ldg4(src + row * 128 + ch * 8 + 4);
+        }
+    }
+}
+__device__ __forceinline__ void tile_quarter_commit(uint8_t* img, int r, int q, const float4 (&lo)[4], const float4 (&hi)[4]) {
+    const int ch = r & 15, rr0 = r >> 4;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int rr = rr0 + 8 * (4 * q + i);
+        *reinterpret_cast<uint4*>(img + (ch >> 3) * kNcSlab + sw128_chunk_off(rr, ch & 7)) =
+            make_uint4(pack_bf16(lo[i].x, lo[i].y), pack_bf16(lo[i].z, lo[i].w), pack_bf16(hi[i].x, hi[i].y), pack_bf16(hi[i].z, hi[i].w));
+    }
+}
+
+// the same block read in two halves: issue the coalesced loads early (registers), hand them to the owning threads later
+__device__ __forceinline__ void aux_issue(const float* __restrict__ src, int64_t rbase, int64_t n, int c0, int lane, float4 (&p)[8]) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int64_t row = rbase + i * 4 + (lane >> 3);
+        p[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (row < n) p[i] = ldg4(src + row * 128 + c0 + (lane & 7) * 4);
+    }
+}
+__device__ __forceinline__ void aux_commit(const float4 (&p)[8], float* stg, int lane, float (&v)[32]) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) *reinterpret_cast<float4*>(stg + (i * 4 + (lane >> 3)) * kNcStgRow + (lane & 7) * 4) = p[i];
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const float4 q = *reinterpret_cast<const float4*>(stg + lane * kNcStgRow + j * 4);
+        v[4 * j] = q.x; v[4 * j + 1] = q.y; v[4 * j + 2] = q.z; v[4 * j + 3] = q.w;
+    }
+    __syncwarp();
 }
 
 // coalesced read of a [32 rows][32 cols] block of a [n,128] fp32 array into the calling thread's row (lane = row)
@@ -161,8 +216,10 @@ __global__ void __launch_bounds__(NS * 128, 1) node_chain_kernel(const NodeChain
     const uint32_t idesc = umma_idesc_bf16(128, 128);
     const int64_t ntiles = (a.n + 127) / 128;
     uint32_t phase = 0;
+    bool have_img = false;   // the image of this tile's first source was already built under the previous tile's last epilogue
     for (int64_t tile = (int64_t)blockIdx.x * NS + wg; tile < ntiles; tile += (int64_t)gridDim.x * NS) {
         const int64_t row0 = tile * 128;
+        const int64_t next_row0 = (tile + (int64_t)gridDim.x * NS) * 128;   // >= n: no next tile
         const int64_t rbase = row0 + wq * 32;   // first row of this warp's 32 x 32 staging blocks
         int wi = 0;                              // weight image index of the current stage
         for (int s = 0; s < a.nstage; ++s) {
@@ -174,7 +231,7 @@ __global__ void __launch_bounds__(NS * 128, 1) node_chain_kernel(const NodeChain
                         mbar_wait(bar, phase);
                         phase ^= 1u;
                     }
-                    load_tile_image(src == 0 ? a.a0 : a.a1, row0, a.n, aimg, r);
+                    if (src > 0 || !have_img) load_tile_image(src == 0 ? a.a0 : a.a1, row0, a.n, aimg, r);
                 }
                 fence_proxy_async();
                 tc_fence_before();
@@ -189,6 +246,12 @@ __global__ void __launch_bounds__(NS * 128, 1) node_chain_kernel(const NodeChain
                 }
             }
             wi += nsrc;
+            if (s + 1 == a.nstage) have_img = next_row0 < a.n;
+            // the auxiliary rows of the first chunk are requested before the wait for the MMAs, those of chunk c + 1 while
+            // chunk c is processed (one of the two when a stage has both a multiplier and a residual)
+            const float* aux = S.mul_aux ? S.mul_aux : S.add_res;
+            float4 pf[8];
+            if (aux) aux_issue(aux, rbase, a.n, 0, lane, pf);
             mbar_wait(bar, phase);
             phase ^= 1u;
             tc_fence_after();
@@ -220,7 +283,12 @@ __global__ void __launch_bounds__(NS * 128, 1) node_chain_kernel(const NodeChain
                 }
                 rstd = rsqrtf(sq * (1.f / 128.f) + S.ln_eps);
             }
+            // last stage: its MMAs were the last readers of the A image, so the next tile's image is built here, a quarter per
+            // chunk, the loads in flight under the chunk's epilogue work (the read stream never pauses for the epilogues)
+            const bool pre_next = (s + 1 == a.nstage) && next_row0 < a.n;
             for (int c0 = 0; c0 < 128; c0 += 32) {
+                float4 nlo[4], nhi[4];
+                if (pre_next) tile_quarter_issue(a.a0, next_row0, a.n, r, c0 >> 5, nlo, nhi);
                 float v[32];
                 tmem_ld32(tacc + c0, v);
 #pragma unroll
@@ -234,24 +302,27 @@ __global__ void __launch_bounds__(NS * 128, 1) node_chain_kernel(const NodeChain
 #pragma unroll
                     for (int j = 0; j < 32; ++j) v[j] = act_apply(v[j], S.act);
                 }
-                if (S.mul_aux) {
+                if (aux) {
                     float x[32];
-                    staged_load(S.mul_aux, rbase, a.n, c0, stg, lane, x);
-                    if (S.mul_mode == GMP_NODE_MUL_DSSP) {   // d ssp / d pre from the saved ssp output y: 1 - exp(-(y + ln 2))
+                    aux_commit(pf, stg, lane, x);
+                    if (c0 + 32 < 128) aux_issue(aux, rbase, a.n, c0 + 32, lane, pf);
+                    if (S.mul_aux) {
+                        if (S.mul_mode == GMP_NODE_MUL_DSSP) {   // d ssp / d pre from the saved ssp output y: 1 - exp(-(y + ln 2)) = 1 - 2^(-y log2 e) / 2
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] *= -expm1f(-(x[j] + 0.6931471805599453f));
-                    } else {
+                            for (int j = 0; j < 32; ++j) v[j] *= fmaf(-0.5f, ex2_fast(-1.4426950408889634f * x[j]), 1.f);
+                        } else {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] *= x[j];
+                            for (int j = 0; j < 32; ++j) v[j] *= x[j];
+                        }
+                        if (S.add_res) staged_load(S.add_res, rbase, a.n, c0, stg, lane, x);
+                    }
+                    if (S.add_res) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] += x[j];
                     }
                 }
-                if (S.add_res) {
-                    float x[32];
-                    staged_load(S.add_res, rbase, a.n, c0, stg, lane, x);
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] += x[j];
-                }
                 if (S.out_f32 || S.out_bf16) staged_store(v, S.out_f32, reinterpret_cast<__nv_bfloat16*>(S.out_bf16), rbase, a.n, c0, stg, lane);
+                if (pre_next) tile_quarter_commit(aimg, r, c0 >> 5, nlo, nhi);
                 if (s + 1 < a.nstage) {   // this stage's result is the next stage's A operand
 #pragma unroll
                     for (int q = 0; q < 4; ++q)
@@ -280,6 +351,79 @@ __global__ void node_pack_w_kernel(const float* __restrict__ w, int out_dim, int
     // image (k0 / 128) holds k in [128 i, 128 i + 128): two slabs of 64
     uint8_t* dst = img + (k0 >> 7) * kNcImg + ((k0 & 127) >> 6) * kNcSlab + sw128_chunk_off(r, (k0 & 63) >> 3);
     *reinterpret_cast<uint4*>(dst) = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+}
+
+
+// Backward of  a = act(LayerNorm(pre) * gamma + beta)  over 128-wide rows (EGNN mlp_upd, models/layers/egnn_layer.py:41-48):
+//   d_pre = rstd * (gamma dy - mean(gamma dy) - xhat mean(gamma dy xhat)),   dy = g * act'(y)
+// plus the per-CTA partial sums of d gamma = sum dy xhat and d beta = sum dy, and optionally the recomputed activations
+// (the weight gradient of the following Linear needs them; they are not kept by the forward pass).
+// One warp per row, a lane owns 4 consecutive columns: fully coalesced 512-byte rows, shuffle reductions, fp32 throughout.
+constexpr int kLnbThreads = 256;
+__global__ void __launch_bounds__(kLnbThreads) ln_act_bwd_kernel(const float* __restrict__ g, const float* __restrict__ pre,
+                                                                 const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                                                                 int act, int64_t n, float* __restrict__ d_pre, float* __restrict__ act_out,
+                                                                 float* __restrict__ parts) {
+    __shared__ float red[kLnbThreads / 32][256];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const float4 gm = ldg4(gamma + lane * 4), bt = ldg4(beta + lane * 4);
+    const float gmv[4] = {gm.x, gm.y, gm.z, gm.w}, btv[4] = {bt.x, bt.y, bt.z, bt.w};
+    float dgam[4] = {0.f, 0.f, 0.f, 0.f}, dbet[4] = {0.f, 0.f, 0.f, 0.f};
+    const int64_t wstride = (int64_t)gridDim.x * (kLnbThreads / 32);
+    for (int64_t row = (int64_t)blockIdx.x * (kLnbThreads / 32) + warp; row < n; row += wstride) {
+        const float4 xq = ldg4(pre + row * 128 + lane * 4), gq = ldg4(g + row * 128 + lane * 4);
+        const float x[4] = {xq.x, xq.y, xq.z, xq.w}, gi[4] = {gq.x, gq.y, gq.z, gq.w};
+        const float mean = warp_sum(x[0] + x[1] + x[2] + x[3]) * (1.f / 128.f);
+        float sq = 0.f;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) sq = fmaf(x[k] - mean, x[k] - mean, sq);
+        const float rstd = rsqrtf(warp_sum(sq) * (1.f / 128.f) + eps);
+        float xh[4], gdy[4], av[4], s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            xh[k] = (x[k] - mean) * rstd;
+            const float y = fmaf(xh[k], gmv[k], btv[k]);
+            float da;
+            if (act == GMP_NODE_ACT_RELU) {
+                da = y > 0.f ? 1.f : 0.f;
+                av[k] = fmaxf(y, 0.f);
+            } else if (act == GMP_NODE_ACT_SILU) {
+                const float sg = sigmoidf_(y);
+                da = sg * fmaf(y, 1.f - sg, 1.f);
+                av[k] = y * sg;
+            } else {
+                da = 1.f;
+                av[k] = y;
+            }
+            const float dy = gi[k] * da;
+            dgam[k] = fmaf(dy, xh[k], dgam[k]);
+            dbet[k] += dy;
+            gdy[k] = dy * gmv[k];
+            s1 += gdy[k];
+            s2 = fmaf(gdy[k], xh[k], s2);
+        }
+        s1 = warp_sum(s1) * (1.f / 128.f);
+        s2 = warp_sum(s2) * (1.f / 128.f);
+        float4 o;
+        o.x = rstd * (gdy[0] - s1 - xh[0] * s2);
+        o.y = rstd * (gdy[1] - s1 - xh[1] * s2);
+        o.z = rstd * (gdy[2] - s1 - xh[2] * s2);
+        o.w = rstd * (gdy[3] - s1 - xh[3] * s2);
+        *reinterpret_cast<float4*>(d_pre + row * 128 + lane * 4) = o;
+        if (act_out) *reinterpret_cast<float4*>(act_out + row * 128 + lane * 4) = make_float4(av[0], av[1], av[2], av[3]);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        red[warp][lane * 4 + k] = dgam[k];
+        red[warp][128 + lane * 4 + k] = dbet[k];
+    }
+    __syncthreads();
+    {   // fixed-order sum over the CTA's warps: thread t owns element t of [d gamma | d beta]
+        float sacc = 0.f;
+#pragma unroll
+        for (int w = 0; w < kLnbThreads / 32; ++w) sacc += red[w][threadIdx.x];
+        parts[(int64_t)blockIdx.x * 256 + threadIdx.x] = sacc;
+    }
 }
 
 template <int NS>
@@ -336,6 +480,20 @@ int gmp_node_chain_tc(const float* a0, const float* a1, int64_t n, int32_t nstag
     if (nimg <= 1) return launch_chain<3>(a, nimg, stream);
     if (nimg <= 3) return launch_chain<2>(a, nimg, stream);
     return launch_chain<1>(a, nimg, stream);
+}
+
+int32_t gmp_ln_act_bwd_num_parts(int64_t n) {
+    const int64_t want = ceil_div(n, kLnbThreads / 32);
+    const int64_t cap = 4 * (int64_t)num_sms();
+    return (int32_t)(want < 1 ? 1 : (want < cap ? want : cap));
+}
+
+int gmp_ln_act_bwd(const float* g_out, const float* pre, const float* gamma, const float* beta, float eps, int32_t act, int64_t n,
+                   float* d_pre, float* act_out, float* parts, gmp_stream_t stream) {
+    GMP_REQUIRE(g_out && pre && gamma && beta && d_pre && parts && n >= 1, "ln_act_bwd: bad arguments");
+    GMP_REQUIRE(act == GMP_NODE_ACT_NONE || act == GMP_NODE_ACT_RELU || act == GMP_NODE_ACT_SILU, "ln_act_bwd: activation %d", act);
+    ln_act_bwd_kernel<<<gmp_ln_act_bwd_num_parts(n), kLnbThreads, 0, stream>>>(g_out, pre, gamma, beta, eps, act, n, d_pre, act_out, parts);
+    return check_launch("ln_act_bwd_kernel");
 }
 
 }  // extern "C"

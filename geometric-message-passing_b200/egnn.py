@@ -42,7 +42,9 @@ class _EGNNEdgeFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, P, Q, pos, graph: Graph, act: int, eps: float, aggr_mean: int, precision: int, *w):
         P, Q, pos = P.contiguous(), Q.contiguous(), pos.contiguous()
+        *w, Q16 = w      # last extra argument: a bf16 copy of Q when the producer already made one (else None)
         w = tuple(t.contiguous() for t in w)
+        Q16 = Q.to(torch.bfloat16) if (Q16 is None and precision == _lib.BF16_TC) else Q16
         d = P.shape[1]
         prm = _params_struct(w, d, act, eps, aggr_mean)
         csr = graph.by_dst
@@ -54,15 +56,15 @@ class _EGNNEdgeFn(torch.autograd.Function):
             if _TC2_FWD:
                 head = torch.empty(int(_lib.lib().gmp_egnn_tc2_num_chunks(graph.E)), 132, dtype=P.dtype, device=P.device)
                 call("gmp_egnn_tc2_edge_fwd", ptr(csr.rowptr), ptr(csr.col), ptr(csr.row_ids()), graph.n, graph.E, ptr(P),
-                     ptr(Q.to(torch.bfloat16)), ptr(pos), C.byref(prm), ptr(msg), ptr(pag), ptr(head))
+                     ptr(Q16), ptr(pos), C.byref(prm), ptr(msg), ptr(pag), ptr(head))
             else:
                 call("gmp_egnn_tc_edge_fwd", ptr(csr.rowptr), ptr(csr.col), ptr(csr.row_ids()), graph.n, graph.E, ptr(P),
-                     ptr(Q.to(torch.bfloat16)), ptr(pos), C.byref(prm), ptr(msg), ptr(pag))
+                     ptr(Q16), ptr(pos), C.byref(prm), ptr(msg), ptr(pag))
         else:
             call("gmp_egnn_edge_fwd", ptr(csr.rowptr), ptr(csr.col), graph.n, graph.E, ptr(P), ptr(Q), ptr(pos),
                  C.byref(prm), ptr(msg), ptr(pag), precision)
         ctx.save_for_backward(P, Q, pos, *w)
-        ctx.graph, ctx.meta = graph, (act, eps, aggr_mean, precision)
+        ctx.graph, ctx.meta, ctx.Q16 = graph, (act, eps, aggr_mean, precision), Q16
         return msg, pag
 
     @staticmethod
@@ -88,7 +90,7 @@ class _EGNNEdgeFn(torch.autograd.Function):
             dpre1 = torch.empty(max(E, 1), d, dtype=torch.bfloat16, device=P.device)
             ddelta = torch.empty(max(E, 1), 4, dtype=P.dtype, device=P.device)
             call("gmp_egnn_tc_edge_bwd_fused", ptr(cd.rowptr), ptr(cd.col), cd.perm_ptr, ptr(cd.row_ids()), graph.n, E, ptr(P),
-                 ptr(Q.to(torch.bfloat16)), ptr(pos), C.byref(prm), ptr(g_msg), ptr(g_pos), ptr(dP), ptr(dpos_i), ptr(parts),
+                 ptr(ctx.Q16), ptr(pos), C.byref(prm), ptr(g_msg), ptr(g_pos), ptr(dP), ptr(dpos_i), ptr(parts),
                  ptr(dpre1), ptr(ddelta))
             call("gmp_segment_sum_bf16_f32", ptr(cs.rowptr), cs.perm_ptr, ptr(dpre1), ptr(dQ), graph.n, d)
             dsum = torch.empty(graph.n, 4, dtype=P.dtype, device=P.device)
@@ -96,7 +98,7 @@ class _EGNNEdgeFn(torch.autograd.Function):
             dpos_j = -dsum[:, :3]
         elif tc:
             call("gmp_egnn_tc_edge_bwd", ptr(cd.rowptr), ptr(cd.col), ptr(cd.row_ids()), ptr(cd.rowptr), graph.n, graph.E, ptr(P),
-                 ptr(Q.to(torch.bfloat16)), ptr(pos), C.byref(prm), ptr(g_msg), ptr(g_pos), 0, ptr(dP), ptr(dpos_i), ptr(parts))
+                 ptr(ctx.Q16), ptr(pos), C.byref(prm), ptr(g_msg), ptr(g_pos), 0, ptr(dP), ptr(dpos_i), ptr(parts))
             call("gmp_egnn_tc_edge_bwd", ptr(cs.rowptr), ptr(cs.col), ptr(cs.row_ids()), ptr(cd.rowptr), graph.n, graph.E, ptr(Q),
                  ptr(P.to(torch.bfloat16)), ptr(pos), C.byref(prm), ptr(g_msg), ptr(g_pos), 1, ptr(dQ), ptr(dpos_j), ptr(parts))
         else:
@@ -112,7 +114,7 @@ class _EGNNEdgeFn(torch.autograd.Function):
         # order of *w: wd, ln1_g, ln1_b, w1, b1, ln2_g, ln2_b, w2, b2, ln3_g, ln3_b, w3, b3
         grads_w = (v(9), v(2), v(3), red[:dd].view(d, d), v(0), v(4), v(5), red[dd:2 * dd].view(d, d), v(1), v(6), v(7),
                    v(8).view_as(w[11]), vec[10 * d:10 * d + 1].view_as(w[12]))
-        return (dP, dQ, dpos_i + dpos_j, None, None, None, None, None, *grads_w)
+        return (dP, dQ, dpos_i + dpos_j, None, None, None, None, None, *grads_w, None)
 
 
 class EGNNLayer(nn.Module):
@@ -126,6 +128,8 @@ class EGNNLayer(nn.Module):
         if aggr not in ("add", "sum", "mean"):
             raise NotImplementedError(f"aggr={aggr!r}: the fused reduction implements add/sum/mean")
         self.emb_dim, self.aggr, self.precision = emb_dim, aggr, precision
+        # bf16 mode: P / Q projections and mlp_upd on the tcgen05 chain kernel (GMP_EGNN_NODE_CHAIN=0: library GEMMs, for A/B timing)
+        self.node_chain = os.environ.get("GMP_EGNN_NODE_CHAIN", "1") != "0"
         self._act_id = {"relu": 0, "swish": 1}[activation]
         self.activation = {"swish": SiLU(), "relu": ReLU()}[activation]
         self.norm = torch.nn.LayerNorm
@@ -145,20 +149,33 @@ class EGNNLayer(nn.Module):
         lin0 = self.mlp_msg[0]
         W0 = lin0.weight
         h_dst = h if rows is None else h[rows]
-        P = F.linear(h_dst, W0[:, :d], lin0.bias)      # h_i half (+ bias)
+        # bf16 mode: the node-side Linears run on the tcgen05 chain kernel (csrc/node_chain.cu) instead of library GEMMs
+        chain = self.node_chain and self.precision == "bf16" and h.is_cuda and d == 128 and n > 0 and h.dtype == torch.float32
+        Q16 = None
+        if chain:
+            from . import nodechain as nc
+            P, _ = nc.ChainLinearFn.apply(h_dst, W0[:, :d], lin0.bias, False)
+            Q, Q16 = nc.ChainLinearFn.apply(h, W0[:, d:2 * d], None, True)     # the edge kernels gather Q as bf16 rows
+        else:
+            P = F.linear(h_dst, W0[:, :d], lin0.bias)      # h_i half (+ bias)
+            Q = F.linear(h, W0[:, d:2 * d])                # h_j half
         if rows is not None:                           # the edge kernel indexes P by local row id: zero rows for the halo
             P = F.pad(P, (0, 0, rows.start, n - rows.stop))
-        Q = F.linear(h, W0[:, d:2 * d])                # h_j half
         wd = W0[:, 2 * d]                              # distance column
         ln1, lin1, ln2 = self.mlp_msg[1], self.mlp_msg[3], self.mlp_msg[4]
         lin2, ln3, lin3 = self.mlp_pos[0], self.mlp_pos[1], self.mlp_pos[3]
         msg_aggr, pos_aggr = _EGNNEdgeFn.apply(
             P, Q, pos, graph, self._act_id, float(ln1.eps), int(self.aggr == "mean"), _PREC[self.precision],
             wd, ln1.weight, ln1.bias, lin1.weight, lin1.bias, ln2.weight, ln2.bias, lin2.weight, lin2.bias,
-            ln3.weight, ln3.bias, lin3.weight, lin3.bias)
+            ln3.weight, ln3.bias, lin3.weight, lin3.bias, Q16)
         if rows is not None:
             msg_aggr, pos_aggr, pos = msg_aggr[rows], pos_aggr[rows], pos[rows]
-        upd_out = self.mlp_upd(torch.cat([h_dst, msg_aggr], dim=-1))
+        if chain:
+            u0, uln0, u1, uln1 = self.mlp_upd[0], self.mlp_upd[1], self.mlp_upd[3], self.mlp_upd[4]
+            upd_out = nc.EGNNUpdateFn.apply(h_dst, msg_aggr, u0.weight, u0.bias, uln0.weight, uln0.bias, u1.weight, u1.bias,
+                                            uln1.weight, uln1.bias, "relu" if self._act_id == 0 else "silu", float(uln0.eps))
+        else:
+            upd_out = self.mlp_upd(torch.cat([h_dst, msg_aggr], dim=-1))
         return upd_out, pos + pos_aggr
 
     def __repr__(self) -> str:

@@ -58,3 +58,95 @@ def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] =
         x, x2 = x[:, :128].contiguous(), x[:, 128:].contiguous()
     run(x.contiguous(), [stage(img, bias, act=act, add_res=res, out_f32=out, out_bf16=o16)], x2)
     return out, o16
+
+
+def wgrad(g: torch.Tensor, x: torch.Tensor):
+    """(dW [128,128], db [128]) = (g^T x, column sums of g) over all rows: tensor-core reduction kernel + fixed-order sum."""
+    n = g.shape[0]
+    nparts, plen = _lib.lib().gmp_linear_wgrad_num_parts(n), 128 * 128 + 128
+    parts = torch.empty(nparts, plen, dtype=torch.float32, device=g.device)
+    call("gmp_linear_wgrad_tc", ptr(g), ptr(x), n, 128, 128, ptr(parts))
+    red = torch.empty(plen, dtype=torch.float32, device=g.device)
+    call("gmp_reduce_partials_f32", ptr(parts), nparts, plen, ptr(red))
+    return red[:128 * 128].view(128, 128), red[128 * 128:]
+
+
+class ChainLinearFn(torch.autograd.Function):
+    """y = x W^T (+ b) for a 128 x 128 weight on the chain kernel, optionally with a bf16 copy of y as a second
+    (non-differentiable) output; dx on the chain kernel (transposed image), dW / db on the reduction kernel."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, want_bf16: bool):
+        x = x.contiguous()
+        y, y16 = linear(x, w, b, want_bf16=want_bf16)
+        ctx.save_for_backward(x, w)
+        ctx.has_bias = b is not None
+        if y16 is None:
+            y16 = x.new_empty(0, dtype=torch.bfloat16)
+        ctx.mark_non_differentiable(y16)
+        return y, y16
+
+    @staticmethod
+    def backward(ctx, g, _g16):
+        x, w = ctx.saved_tensors
+        g = g.contiguous()
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty_like(x)
+            run(g, [stage(pack_w(w, True), out_f32=dx)])
+        dw = db = None
+        if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
+            dw, db = wgrad(g, x)
+        return dx, dw, (db if ctx.has_bias else None), None
+
+
+def ln_act_bwd(g, pre, gamma, beta, eps, act: str, want_act: bool):
+    """(d_pre, recomputed activations or None, d gamma, d beta) of a = act(LayerNorm(pre) * gamma + beta)."""
+    n = pre.shape[0]
+    d_pre = torch.empty_like(pre)
+    a = torch.empty_like(pre) if want_act else None
+    nparts = _lib.lib().gmp_ln_act_bwd_num_parts(n)
+    parts = torch.empty(nparts, 256, dtype=torch.float32, device=pre.device)
+    call("gmp_ln_act_bwd", ptr(g), ptr(pre), ptr(gamma), ptr(beta), float(eps), ACT[act], n, ptr(d_pre), ptr(a), ptr(parts))
+    red = torch.empty(256, dtype=torch.float32, device=pre.device)
+    call("gmp_reduce_partials_f32", ptr(parts), nparts, 256, ptr(red))
+    return d_pre, a, red[:128], red[128:]
+
+
+class EGNNUpdateFn(torch.autograd.Function):
+    """``mlp_upd(cat[h, msg_aggr])`` of models/layers/egnn_layer.py:41-48, 82-86 (Linear(2d, d), LayerNorm, act, Linear(d, d),
+    LayerNorm, act; d = 128) as one chain launch; the backward pass is two LayerNorm/activation kernels, three chain
+    launches for the data gradients and three weight-gradient reductions.  Kept for the backward: the two pre-LayerNorm
+    tensors (the activations are recomputed from them)."""
+
+    @staticmethod
+    def forward(ctx, h, agg, w0, b0, g0, be0, w1, b1, g1, be1, act: str, eps: float):
+        h, agg = h.contiguous(), agg.contiguous()
+        n = h.shape[0]
+        train = any(ctx.needs_input_grad)
+        pre0 = torch.empty_like(h) if train else None
+        pre1 = torch.empty_like(h) if train else None
+        out = torch.empty_like(h)
+        run(h, [stage(pack_w(w0), b0, ln=(g0, be0, eps), act=act, out_pre=pre0),
+                stage(pack_w(w1), b1, ln=(g1, be1, eps), act=act, out_f32=out, out_pre=pre1)], a1=agg)
+        ctx.save_for_backward(h, agg, w0, g0, be0, w1, g1, be1, pre0, pre1)
+        ctx.act, ctx.eps = act, eps
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        h, agg, w0, g0, be0, w1, g1, be1, pre0, pre1 = ctx.saved_tensors
+        act, eps = ctx.act, ctx.eps
+        g = g.contiguous()
+        dpre1, _, dg1, dbe1 = ln_act_bwd(g, pre1, g1, be1, eps, act, False)
+        da0 = torch.empty_like(h)
+        run(dpre1, [stage(pack_w(w1, True), out_f32=da0)])
+        dpre0, a0, dg0, dbe0 = ln_act_bwd(da0, pre0, g0, be0, eps, act, True)
+        dw1, db1 = wgrad(dpre1, a0)
+        dh, dagg = torch.empty_like(h), torch.empty_like(h)
+        w0c = w0.detach()
+        run(dpre0, [stage(pack_w(w0c[:, :128].contiguous(), True), out_f32=dh)])
+        run(dpre0, [stage(pack_w(w0c[:, 128:].contiguous(), True), out_f32=dagg)])
+        dwa, db0 = wgrad(dpre0, h)
+        dwb, _ = wgrad(dpre0, agg)
+        return dh, dagg, torch.cat([dwa, dwb], dim=1), db0, dg0, dbe0, dw1, db1, dg1, dbe1, None, None

@@ -227,7 +227,7 @@ class _SchNetBodyFn(torch.autograd.Function):
         L = len(params) // _SchNetBodyFn.NP
         P = [[t.detach().contiguous() for t in params[l * 9:(l + 1) * 9]] for l in range(L)]
         n, E, dev = graph.n, graph.E, h0.device
-        train = torch.is_grad_enabled() and (h0.requires_grad or any(p.requires_grad for p in params))
+        train = any(ctx.needs_input_grad)   # (grad mode is off inside Function.forward: needs_input_grad is the signal)
         csr = graph.by_dst
         keep_row = graph.by_src.inv_perm() if train else None
         nchunks = int(_lib.lib().gmp_schnet_tc2_num_chunks(E))

@@ -487,6 +487,13 @@ int gmp_node_pack_w(const float* w, int32_t out_dim, int32_t in_dim, int32_t tra
 int gmp_node_chain_tc(const float* a0, const float* a1, int64_t num_rows, int32_t nstage, const gmp_node_stage* stages,
                       gmp_stream_t stream);
 
+/* Backward of a = act(LayerNorm(pre) * gamma + beta) over rows of 128 (EGNN mlp_upd, models/layers/egnn_layer.py:41-48):
+ * d_pre [n,128]; optional act_out [n,128] = the recomputed activations; parts [num_parts, 256] = per-CTA partial
+ * [d gamma | d beta] (sum with gmp_reduce_partials_f32).  act: GMP_NODE_ACT_NONE / _RELU / _SILU. */
+int32_t gmp_ln_act_bwd_num_parts(int64_t num_rows);
+int gmp_ln_act_bwd(const float* g_out, const float* pre, const float* gamma, const float* beta, float eps, int32_t act,
+                   int64_t num_rows, float* d_pre, float* act_out, float* parts, gmp_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
