@@ -456,7 +456,9 @@ def bench_config2(D, args):
                             "precision": args.precision,
                             "tolerance_vs_fp32_reference": 1e-2 if args.precision == "bf16" else 1e-5,
                             "parity": "tests/test_gpu_config_parity.py::test_config2_* : 64 molecules of this batch, whole model, vs the oracle",
-                            "node_side_gemms": "cuBLAS TF32 forward / dx; dW, db on tcgen05 (linear_wgrad_tc_kernel)" if args.precision == "bf16" else "cuBLAS fp32", "parallelism": f"graph-sharded x{world}",
+                            "node_side_gemms": ("tcgen05 chain kernel (node_chain_kernel: lin2 -> ssp -> lin -> + h -> next lin1 per launch, and the transposed chain "
+                                                "backward); dW, db on tcgen05 (linear_wgrad_tc_kernel); no cuBLAS / ATen elementwise inside the interaction blocks")
+                            if args.precision == "bf16" else "cuBLAS fp32", "parallelism": f"graph-sharded x{world}",
                             "l2": "per-step working set (x1/agg/g rows of 6 layers, >2 GB) exceeds the 126 MB L2",
                             "cuda_graph": (graph_nodes is not None) if graph_note is None else graph_note,
                             "e2e_path": "pinned host batch -> staging buffers (upload of batch i+1 under step i) -> graph inputs -> one CUDA graph "

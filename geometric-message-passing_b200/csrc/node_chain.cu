@@ -50,14 +50,6 @@ __device__ __forceinline__ float ssp_fast(float x) {
     const float u = ex2_fast(-fabsf(x) * 1.4426950408889634f);
     return fmaf(lg2_fast(1.f + u), 0.6931471805599453f, fmaxf(x, 0.f) - 0.6931471805599453f);
 }
-__device__ __forceinline__ float act_apply(float v, int act) {
-    switch (act) {
-        case GMP_NODE_ACT_SSP: return ssp_fast(v);
-        case GMP_NODE_ACT_RELU: return fmaxf(v, 0.f);
-        case GMP_NODE_ACT_SILU: return __fdividef(v, 1.f + ex2_fast(-1.4426950408889634f * v));
-        default: return v;
-    }
-}
 
 // 128 rows x 128 fp32 columns of `src` starting at row0 -> bf16 K-major swizzled image; 128 threads (r = 0..127)
 __device__ __forceinline__ void load_tile_image(const float* __restrict__ src, int64_t row0, int64_t n, uint8_t* img, int r) {
@@ -298,9 +290,16 @@ __global__ void __launch_bounds__(NS * 128, 1) node_chain_kernel(const NodeChain
 #pragma unroll
                     for (int j = 0; j < 32; ++j) v[j] = fmaf((v[j] - mean) * rstd, gam[c0 + j], bet[c0 + j]);
                 }
-                if (S.act != GMP_NODE_ACT_NONE) {
+                // (the activation id is uniform: one branch per chunk, not one per element)
+                if (S.act == GMP_NODE_ACT_SSP) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = act_apply(v[j], S.act);
+                    for (int j = 0; j < 32; ++j) v[j] = ssp_fast(v[j]);
+                } else if (S.act == GMP_NODE_ACT_RELU) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+                } else if (S.act == GMP_NODE_ACT_SILU) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = __fdividef(v[j], 1.f + ex2_fast(-1.4426950408889634f * v[j]));
                 }
                 if (aux) {
                     float x[32];
