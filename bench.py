@@ -667,7 +667,6 @@ def bench_cube(D, args, log2n: int = None, layers: int = 4):
     rank, world, dev = D.rank, D.world, D.dev
     log2n = log2n or args.cube_log2n
     gmp_b200.set_fast_matmul(args.precision == "bf16")
-    check = partition_self_check(D) if world > 1 else None
     pos = synth_cube(log2n).to(dev)
     n = pos.shape[0]
     part = gmp_b200.slab_partition(pos[:, 0], 1.0, rank, world)
@@ -676,7 +675,10 @@ def bench_cube(D, args, log2n: int = None, layers: int = 4):
     torch.cuda.synchronize()
     t_graph = time.perf_counter() - t0
     torch.manual_seed(0)
-    model = gmp_b200.PartitionedEGNN(num_layers=layers, emb_dim=128, precision=args.precision).to(dev)
+    # halo rows: pulled out of the owners' symmetric-memory buffers by our own kernel (P2P loads over NVLink, csrc/halo.cu);
+    # if symmetric memory cannot be set up on this box the grouped ncclSend / ncclRecv exchange runs instead (reported)
+    halo, halo_note = ("peer" if world > 1 and args.halo == "peer" else "nccl"), None
+    model = gmp_b200.PartitionedEGNN(num_layers=layers, emb_dim=128, precision=args.precision, halo=halo).to(dev)
     params = list(model.parameters())
     h_own = torch.randn(part.n_own, 128, device=dev)
     p_own = pos[part.own_lo:part.own_hi].clone()
@@ -689,10 +691,21 @@ def bench_cube(D, args, log2n: int = None, layers: int = 4):
         (ho.sum() + po.sum()).backward()
         gmp_b200.allreduce_gradients(params)
 
+    if halo == "peer":
+        ok = 1.0
+        try:
+            step()
+            torch.cuda.synchronize()
+        except Exception as ex:  # noqa: BLE001 -- e.g. no P2P mapping between the devices
+            ok, halo_note = 0.0, f"{type(ex).__name__}: {str(ex)[:160]}"
+        if D.reduce([ok], "max")[0] != 1.0 or D.reduce([-ok], "max")[0] != -1.0:   # any rank failed: all fall back together
+            halo = "nccl"
+            model.halo, model._peer = "nccl", None
+    check = partition_self_check(D, halo=halo) if world > 1 else None
     K = max(2, min(args.steps, 3))
     ms = D.timed(step, 2, K)
     E_tot = D.reduce([float(ei.shape[1])], "sum")[0]
-    halo = D.reduce([float(part.n_left + part.n_right)], "max")[0]
+    halo_rows = D.reduce([float(part.n_left + part.n_right)], "max")[0]
     pk = peaks()
     flops = 3.0 * layers * (131584.0 * E_tot + 98304.0 * n)
     byts = 3.0 * layers * (528.0 * E_tot + 1052.0 * n)
@@ -700,9 +713,12 @@ def bench_cube(D, args, log2n: int = None, layers: int = 4):
     f_tc, f_hbm = tf / (pk["tc_sustained"] * world), gbs / (pk["hbm"] * world)
     out = {"workload": f"EGNN {layers} layers d=128 on one radius graph N=2^{log2n}, r=1, density 8 (BASELINE.json configs[4] geometry; 2^24 nodes do "
                        f"not fit one GPU's 180 GB for a training step, so every N runs 2^{log2n}), destination-partitioned x{world}"
-                       + (", halo exchange over NCCL" if world > 1 else ""),
+                       + (", halo exchange per layer" if world > 1 else ""),
            "n_gpus": world, "scaling": "strong", "precision": "fp32-strict (1e-5)" if args.precision == "fp32" else "bf16 tcgen05 (1e-2; ReLU gradients: see tests)",
-           "nodes": n, "edges": int(E_tot), "halo_nodes_max": int(halo), "steps": K, "ms_per_step": ms,
+           "nodes": n, "edges": int(E_tot), "halo_nodes_max": int(halo_rows),
+           "halo_exchange": None if world == 1 else ("peer-memory pull kernel (symmetric memory, P2P loads over NVLink; csrc/halo.cu)" if halo == "peer"
+                                                     else "grouped ncclSend / ncclRecv" + (f" (peer path unavailable: {halo_note})" if halo_note else "")),
+           "steps": K, "ms_per_step": ms,
            "edges_per_s_per_layer": E_tot * layers / (ms * 1e-3), "graph_build_s": t_graph,
            "roofline": {"bound": "tensor" if f_tc >= f_hbm else "hbm", "achieved": tf if f_tc >= f_hbm else gbs,
                         "peak": (pk["tc_sustained"] if f_tc >= f_hbm else pk["hbm"]) * world, "unit": "TFLOP/s" if f_tc >= f_hbm else "GB/s",
@@ -712,7 +728,7 @@ def bench_cube(D, args, log2n: int = None, layers: int = 4):
     return out if rank == 0 else None
 
 
-def partition_self_check(D, log2n: int = 15):
+def partition_self_check(D, log2n: int = 15, halo: str = "nccl"):
     """N >= 2 only: the destination-partitioned 2-layer EGNN (fp32-strict) against the same model on the whole graph on one
     GPU -- owned rows of h and pos and the parameter gradients must agree to fp32 round-off (the local edge order equals
     the global one, so the sums are the same sums)."""
@@ -726,7 +742,7 @@ def partition_self_check(D, log2n: int = 15):
         pos = synth_cube(log2n, seed=1).to(dev)
         n = pos.shape[0]
         torch.manual_seed(3)
-        model = gmp_b200.PartitionedEGNN(num_layers=2, emb_dim=128, precision="fp32").to(dev)
+        model = gmp_b200.PartitionedEGNN(num_layers=2, emb_dim=128, precision="fp32", halo=halo).to(dev)
         g = torch.Generator().manual_seed(5)
         h = torch.randn(n, 128, generator=g).to(dev)
         ch, cp = torch.randn(n, 128, generator=g).to(dev), torch.randn(n, 3, generator=g).to(dev)
@@ -751,7 +767,7 @@ def partition_self_check(D, log2n: int = 15):
         e_out, e_grad = D.reduce([e_out, e_grad])
         for p in params:
             p.grad = None
-        return {"nodes": n, "layers": 2, "precision": "fp32", "max_rel_err_outputs": e_out, "max_rel_err_param_grads": e_grad,
+        return {"nodes": n, "layers": 2, "precision": "fp32", "halo": halo, "max_rel_err_outputs": e_out, "max_rel_err_param_grads": e_grad,
                 "ok": bool(e_out <= 1e-5 and e_grad <= 1e-4)}
     finally:
         gmp_b200.set_fast_matmul(was)
@@ -771,6 +787,7 @@ if __name__ == "__main__":
     ap.add_argument("--no-strict", action="store_true", help="skip the secondary fp32-strict measurement")
     ap.add_argument("--only", default="", help="comma-separated config numbers to run (2 = headline SchNet, 3 = TFN, 4 = MACE, 5 = EGNN large graph)")
     ap.add_argument("--cube-log2n", type=int, default=CUBE_LOG2N, help="config 5: log2 of the node count of the radius graph")
+    ap.add_argument("--halo", default="peer", choices=["peer", "nccl"], help="config 5 at N > 1: halo rows through the peer-memory pull kernel or NCCL send/recv")
     ap.add_argument("--cpu-molecules", type=int, default=0, help="--impl reference: molecules of the bench batch to time (default: all 4096)")
     a = ap.parse_args()
     if a.impl == "reference":

@@ -91,6 +91,9 @@ _SIGS = {
     "gmp_uvu_conv_fwd": [P, P, P, I64, I64, P, P, P, I32, P, P],
     "gmp_uvu_conv_dx": [P, P, P, I64, I64, P, P, P, I32, P, P],
     "gmp_uvu_conv_dw": [P, P, I64, P, P, P, I32, P, P],
+    "gmp_halo_pull": [P, P, P, I32, I32, P],
+    "gmp_gate_fwd": [P, P, I64, I32, I32, I32, F32, F32, P, P],
+    "gmp_gate_bwd": [P, P, P, P, P, I64, I32, I32, I32, F32, F32, P, P],
     "gmp_node_pack_w": [P, I32, I32, I32, P, P],
     "gmp_node_chain_tc": [P, P, I64, I32, P, P],
     "gmp_ln_act_bwd": [P, P, P, P, F32, I32, I64, P, P, P, P],

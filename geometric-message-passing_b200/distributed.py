@@ -48,6 +48,11 @@ class SlabPartition:
     send_ranges: List[Tuple[int, int]]   # per peer q: slice [a, b) of the OWNED rows this rank sends to q
     recv_counts: List[int]               # per peer q: rows received from q (q < rank -> left halo, q > rank -> right halo)
     local_global: torch.Tensor           # int64 [n_local]: global index of every local node (ascending)
+    # peer-memory exchange (every rank computes every rank's window, so these need no communication):
+    peer_send_start: Optional[List[int]] = None   # per peer q: first row, among q's OWNED rows, of the range q sends to this rank
+    peer_halo_offset: Optional[List[int]] = None  # per peer q: offset, inside q's [left halo | right halo] rows, of the rows this rank owns
+    n_own_max: int = 0                            # max over ranks of the owned / halo row counts (symmetric buffer sizes)
+    halo_max: int = 0
 
     @property
     def n_own(self) -> int:
@@ -96,7 +101,107 @@ def slab_partition(x_sorted: torch.Tensor, r: float, rank: int, world: int) -> S
         recv.append(max(r_hi - r_lo, 0))
     assert sum(recv[:rank]) == n_left and sum(recv[rank + 1:]) == n_right
     local_global = torch.arange(a, b, dtype=torch.int64, device=x_sorted.device)
-    return SlabPartition(rank, world, n, own_lo, own_hi, n_left, n_right, send, recv, local_global)
+
+    def recv_count(p, q):   # rows rank p receives from rank q
+        return max(min(bounds[q + 1], wins[p][1]) - max(bounds[q], wins[p][0]), 0) if p != q else 0
+
+    peer_send_start = [max(bounds[q], a) - bounds[q] if (q != rank and recv[q] > 0) else 0 for q in range(world)]
+    peer_halo_offset = [sum(recv_count(q, p2) for p2 in range(rank) if p2 != q) for q in range(world)]
+    n_own_max = max(bounds[p + 1] - bounds[p] for p in range(world))
+    halo_max = max((bounds[p] - wins[p][0]) + (wins[p][1] - bounds[p + 1]) for p in range(world))
+    return SlabPartition(rank, world, n, own_lo, own_hi, n_left, n_right, send, recv, local_global, peer_send_start,
+                         peer_halo_offset, n_own_max, max(halo_max, 1))
+
+
+class PeerHalo:
+    """Symmetric-memory staging for the halo exchange of one partition: every rank's buffers are mapped into every other
+    rank's address space (torch.distributed._symmetric_memory: CUDA VMM + NVLink P2P), so a rank PULLS its halo rows out of
+    the owners' memory with its own kernel (csrc/halo.cu) after a device-side barrier -- no ncclSend / ncclRecv, no
+    concatenation.  Buffers are double-buffered per (direction, row width): one barrier per exchange is enough, because a
+    rank that writes buffer k again has passed the barrier of exchange k + 1, which every peer enters only after its pull
+    from buffer k."""
+
+    def __init__(self, part: SlabPartition, device, group=None):
+        self.part, self.device = part, device
+        self.group = dist.group.WORLD if group is None else group
+        self._bufs = {}
+        self._turn = {}
+
+    def buffer(self, rows: int, feat: int, tag: str):
+        import torch.distributed._symmetric_memory as symm
+        key = (rows, feat, tag)
+        if key not in self._bufs:
+            pair = []
+            for _ in range(2):
+                t = symm.empty(max(rows, 1) * feat, dtype=torch.float32, device=self.device)
+                pair.append((t, symm.rendezvous(t, self.group)))
+            self._bufs[key] = pair
+            self._turn[key] = 0
+        k = self._turn[key]
+        self._turn[key] = k ^ 1
+        return self._bufs[key][k]
+
+
+def _pull(src_ptrs, dst_ptrs, nbytes, add: bool):
+    import ctypes as C
+    from ._lib import call
+    n = len(src_ptrs)
+    call("gmp_halo_pull", (C.c_void_p * n)(*src_ptrs), (C.c_void_p * n)(*dst_ptrs), (C.c_int64 * n)(*nbytes), n, int(add))
+
+
+class _PeerHaloExchange(torch.autograd.Function):
+    """_HaloExchange over peer memory: forward pulls the halo rows out of the owners' staging buffers, backward lets the
+    owners pull the halo gradients and add them onto the rows they had exposed, peer by peer in rank order."""
+
+    @staticmethod
+    def forward(ctx, x_own: torch.Tensor, part: SlabPartition, peer: PeerHalo):
+        ctx.part, ctx.peer = part, peer
+        x_own = x_own.contiguous()
+        assert x_own.dtype == torch.float32 and x_own.dim() == 2
+        feat = x_own.shape[1]
+        rb = feat * 4
+        buf, hdl = peer.buffer(part.n_own_max, feat, "fwd")
+        stage = buf.view(-1, feat)
+        for q in range(part.world):          # expose the boundary rows the neighbours read
+            a, b = part.send_ranges[q]
+            if b > a:
+                stage[a:b].copy_(x_own[a:b])
+        hdl.barrier()
+        out = x_own.new_empty(part.n_local, feat)
+        src, dst, nb, off = [], [], [], 0
+        for q in range(part.world):
+            if q == part.rank:
+                src.append(x_own.data_ptr()); dst.append(out.data_ptr() + off * rb); nb.append(part.n_own * rb)
+                off += part.n_own
+                continue
+            c = part.recv_counts[q]
+            if c > 0:
+                src.append(int(hdl.buffer_ptrs[q]) + part.peer_send_start[q] * rb); dst.append(out.data_ptr() + off * rb); nb.append(c * rb)
+            off += c
+        for i in range(0, len(src), 16):
+            _pull(src[i:i + 16], dst[i:i + 16], nb[i:i + 16], add=False)
+        return out
+
+    @staticmethod
+    def backward(ctx, g_local: torch.Tensor):
+        part: SlabPartition = ctx.part
+        peer: PeerHalo = ctx.peer
+        g_local = g_local.contiguous()
+        feat = g_local.shape[1]
+        rb = feat * 4
+        buf, hdl = peer.buffer(part.halo_max, feat, "bwd")
+        stage = buf.view(-1, feat)
+        if part.n_left:
+            stage[:part.n_left].copy_(g_local[:part.n_left])
+        if part.n_right:
+            stage[part.n_left:part.n_left + part.n_right].copy_(g_local[part.n_left + part.n_own:])
+        hdl.barrier()
+        g_own = g_local[part.own_slice].clone()
+        for q in range(part.world):          # one launch per peer, in rank order: overlapping ranges are added in a fixed order
+            a, b = part.send_ranges[q]
+            if b > a:
+                _pull([int(hdl.buffer_ptrs[q]) + part.peer_halo_offset[q] * rb], [g_own.data_ptr() + a * rb], [(b - a) * rb], add=True)
+        return g_own, None, None
 
 
 class _HaloExchange(torch.autograd.Function):
@@ -148,9 +253,12 @@ class _HaloExchange(torch.autograd.Function):
         return g_own, None, None
 
 
-def halo_exchange(x_own: torch.Tensor, part: SlabPartition, group=None) -> torch.Tensor:
+def halo_exchange(x_own: torch.Tensor, part: SlabPartition, group=None, peer: Optional[PeerHalo] = None) -> torch.Tensor:
+    """`peer`: a PeerHalo of this partition selects the peer-memory pull kernels (CUDA, NVLink P2P); None = grouped send/recv."""
     if part.world == 1:
         return x_own
+    if peer is not None:
+        return _PeerHaloExchange.apply(x_own, part, peer)
     return _HaloExchange.apply(x_own, part, group)
 
 
@@ -169,17 +277,29 @@ class PartitionedEGNN(torch.nn.Module):
     EGNNLayer applied to the local node set."""
 
     def __init__(self, num_layers: int = 4, emb_dim: int = 128, activation: str = "relu", aggr: str = "sum",
-                 residual: bool = True, precision: str = "fp32"):
+                 residual: bool = True, precision: str = "fp32", halo: str = "nccl"):
+        """halo: "nccl" = grouped send/recv (also what the gloo CPU tests run); "peer" = pull kernels over symmetric
+        memory (P2P loads over NVLink, csrc/halo.cu)."""
         super().__init__()
         from .egnn import EGNNLayer
-        self.residual = residual
+        assert halo in ("nccl", "peer")
+        self.residual, self.halo = residual, halo
+        self._peer = None
         self.convs = torch.nn.ModuleList([EGNNLayer(emb_dim, activation, "layer", aggr, precision) for _ in range(num_layers)])
+
+    def _peer_for(self, part: SlabPartition, device, group):
+        if self.halo != "peer" or part.world == 1:
+            return None
+        if self._peer is None or self._peer.part is not part:
+            self._peer = PeerHalo(part, device, group)
+        return self._peer
 
     def forward(self, h_own, pos_own, edge_index_local, part: SlabPartition, group=None):
         own = part.own_slice
+        peer = self._peer_for(part, h_own.device, group)
         for conv in self.convs:
-            h_loc = halo_exchange(h_own, part, group)
-            pos_loc = halo_exchange(pos_own, part, group)
+            h_loc = halo_exchange(h_own, part, group, peer)
+            pos_loc = halo_exchange(pos_own, part, group, peer)
             h_upd, pos_upd = conv(h_loc, pos_loc, edge_index_local, rows=own)   # node-side work on owned rows only
             h_own = h_own + h_upd if self.residual else h_upd
             pos_own = pos_upd

@@ -30,11 +30,34 @@ _SLICE = 128
 
 
 # ------------------------------------------------------------------------------------------------
-# node-side equivariant non-linearities (elementwise; plain torch ops)
+# node-side equivariant non-linearities (Gate / Activation: fused elementwise kernels, csrc/gate.cu)
 # ------------------------------------------------------------------------------------------------
+class _GateFn(torch.autograd.Function):
+    """[scalars | gates | gated] -> [silu(s) c | gated * sigmoid(gate) c]: one elementwise kernel each way (csrc/gate.cu)."""
+
+    @staticmethod
+    def forward(ctx, x, expand, gstart, gdim, ns: int, ng: int, nv: int):
+        x = x.contiguous()
+        out = torch.empty(x.shape[0], ns + nv, dtype=x.dtype, device=x.device)
+        call("gmp_gate_fwd", ptr(x), ptr(expand), x.shape[0], ns, ng, nv, NORM2MOM["silu"], NORM2MOM["sigmoid"], ptr(out))
+        ctx.save_for_backward(x, expand, gstart, gdim)
+        ctx.dims = (ns, ng, nv)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        x, expand, gstart, gdim = ctx.saved_tensors
+        ns, ng, nv = ctx.dims
+        dx = torch.empty_like(x)
+        call("gmp_gate_bwd", ptr(x), ptr(g.contiguous()), ptr(expand), ptr(gstart), ptr(gdim), x.shape[0], ns, ng, nv,
+             NORM2MOM["silu"], NORM2MOM["sigmoid"], ptr(dx))
+        return dx, None, None, None, None, None, None
+
+
 class Gate(nn.Module):
     """e3nn.nn.Gate with silu scalars / sigmoid gates (models/layers/tfn_layer.py:45-63): input laid out as
-    [scalars | gates | gated]; out = [silu(s) * c_silu | gated_u * sigmoid(gate_u) * c_sigmoid]."""
+    [scalars | gates | gated]; out = [silu(s) * c_silu | gated_u * sigmoid(gate_u) * c_sigmoid].  Fused: one kernel
+    forward, one backward (fp32, CUDA, 2-D input); other inputs take the equivalent torch expression."""
 
     def __init__(self, irreps_scalars, irreps_gates, irreps_gated):
         super().__init__()
@@ -42,16 +65,23 @@ class Gate(nn.Module):
         assert self.irreps_gates.num_irreps == self.irreps_gated.num_irreps
         self.irreps_in = (self.irreps_scalars + self.irreps_gates + self.irreps_gated).simplify()
         self.irreps_out = (self.irreps_scalars + self.irreps_gated)
-        expand = []
+        expand, gstart, gdim = [], [], []
         g = 0
         for m, ir in self.irreps_gated:
             for _ in range(m):
+                gstart.append(len(expand))
+                gdim.append(ir.dim)
                 expand += [g] * ir.dim
                 g += 1
         self.register_buffer("_expand", torch.tensor(expand, dtype=torch.long), persistent=False)
+        self.register_buffer("_expand32", torch.tensor(expand, dtype=torch.int32), persistent=False)
+        self.register_buffer("_gstart", torch.tensor(gstart, dtype=torch.int32), persistent=False)
+        self.register_buffer("_gdim", torch.tensor(gdim, dtype=torch.int32), persistent=False)
 
     def forward(self, x):
         ns, ng = self.irreps_scalars.dim, self.irreps_gates.dim
+        if x.is_cuda and x.dim() == 2 and x.dtype == torch.float32:
+            return _GateFn.apply(x, self._expand32, self._gstart, self._gdim, ns, ng, self.irreps_gated.dim)
         s, g, v = x[..., :ns], x[..., ns:ns + ng], x[..., ns + ng:]
         s = F.silu(s) * NORM2MOM["silu"]
         if ng == 0:
@@ -64,6 +94,8 @@ class ScalarActivation(nn.Module):
     """e3nn.nn.Activation(out_irreps, [silu]) for an all-scalar output (tfn_layer.py:52-53)."""
 
     def forward(self, x):
+        if x.is_cuda and x.dim() == 2 and x.dtype == torch.float32:
+            return _GateFn.apply(x, None, None, None, x.shape[1], 0, 0)
         return F.silu(x) * NORM2MOM["silu"]
 
 

@@ -494,6 +494,31 @@ int32_t gmp_ln_act_bwd_num_parts(int64_t num_rows);
 int gmp_ln_act_bwd(const float* g_out, const float* pre, const float* gamma, const float* beta, float eps, int32_t act,
                    int64_t num_rows, float* d_pre, float* act_out, float* parts, gmp_stream_t stream);
 
+/* ============================================================================================ */
+/* e3nn Gate / scalar Activation of the TFN layer (models/layers/tfn_layer.py:45-63, 89-90)       */
+/* ============================================================================================ */
+
+/* x [n, ns + ng + nv] = [scalars | gates | gated] -> out [n, ns + nv] = [silu(s) c_silu | gated_j sigmoid(gate_expand[j]) c_sigmoid]
+ * (c_* = e3nn's normalize2mom constants).  expand [nv]: gate index of every gated element; gate_start / gate_dim [ng]: the
+ * contiguous range of gated elements each gate multiplies.  ng = nv = 0 is the all-scalar Activation. */
+int gmp_gate_fwd(const float* x, const int32_t* expand, int64_t num_rows, int32_t num_scalars, int32_t num_gates,
+                 int32_t num_gated, float c_silu, float c_sigmoid, float* out, gmp_stream_t stream);
+int gmp_gate_bwd(const float* x, const float* g_out, const int32_t* expand, const int32_t* gate_start, const int32_t* gate_dim,
+                 int64_t num_rows, int32_t num_scalars, int32_t num_gates, int32_t num_gated, float c_silu, float c_sigmoid,
+                 float* dx, gmp_stream_t stream);
+
+/* ============================================================================================ */
+/* Destination-partitioned graph: halo rows over peer memory                 */
+/* ============================================================================================ */
+
+/* Copies (add_f32 = 0) or adds as fp32 (add_f32 = 1) up to 16 segments src[k] -> dst[k] of bytes[k] bytes (multiples of 4;
+ * 16-byte vector path when every pointer and size is 16-byte aligned) in one launch.  src pointers may be peer-GPU
+ * addresses mapped into this process (symmetric memory): the loads then travel over NVLink.  The caller orders the launch
+ * after the peers' writes with a cross-GPU barrier.  Replaces the ncclSend / ncclRecv halo exchange + concatenation of the
+ * partitioned EGNN (there is no reference counterpart: the reference is single-process). */
+int gmp_halo_pull(const void* const* src, void* const* dst, const int64_t* bytes, int32_t num_segments, int32_t add_f32,
+                  gmp_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

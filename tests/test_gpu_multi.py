@@ -21,7 +21,7 @@ def _data():
     return pos, h, cot_h, cot_p
 
 
-def _worker(rank, world, port, q):
+def _worker(rank, world, port, q, halo="nccl"):
     sys.path.insert(0, ROOT)
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
     torch.cuda.set_device(rank)
@@ -32,7 +32,7 @@ def _worker(rank, world, port, q):
     part = gmp_b200.slab_partition(pos[:, 0], 1.0, rank, world)
     ei = gmp_b200.distributed.local_radius_graph(pos[part.local_global], 1.0, part)
     torch.manual_seed(1)
-    model = gmp_b200.PartitionedEGNN(num_layers=2, emb_dim=128).to(dev)
+    model = gmp_b200.PartitionedEGNN(num_layers=2, emb_dim=128, halo=halo).to(dev)
     h_own = h[part.own_lo:part.own_hi].clone().requires_grad_(True)
     p_own = pos[part.own_lo:part.own_hi].clone().requires_grad_(True)
     ho, po = model(h_own, p_own, ei, part)
@@ -46,16 +46,19 @@ def _worker(rank, world, port, q):
     dist.destroy_process_group()
 
 
-def test_partitioned_egnn_matches_single_gpu():
+@pytest.mark.parametrize("halo", ["nccl", "peer"])
+def test_partitioned_egnn_matches_single_gpu(halo):
+    """halo = "peer": the halo rows are pulled out of the owners' symmetric-memory buffers by csrc/halo.cu (P2P loads over
+    NVLink) instead of ncclSend / ncclRecv; same numbers either way (the local edge order equals the global one)."""
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     import gmp_b200
     from tests.helpers import rel_err
     world = 2
-    port = 33500 + os.getpid() % 2000
+    port = 33500 + os.getpid() % 2000 + (7 if halo == "peer" else 0)
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q, halo)) for r in range(world)]
     for p in procs:
         p.start()
     res = sorted([q.get(timeout=250) for _ in range(world)], key=lambda t: t[0])

@@ -97,3 +97,33 @@ def test_tfn_model_golden():
         if ref is None:
             continue
         check_against_digest(g.cpu(), ref, 1e-4, k)
+
+
+@pytest.mark.parametrize("n,C", [(1, 8), (333, 64), (5000, 16)])
+def test_fused_gate_matches_oracle_gate(n, C):
+    """e3nn Gate as built by models/layers/tfn_layer.py:45-63 (silu scalars, sigmoid gates): the fused kernels (csrc/gate.cu)
+    against the oracle's Gate, forward and input gradient; and the all-scalar Activation (:52-53)."""
+    import gmp_b200
+    from oracle.thirdparty import e3nn_nn, o3
+    from oracle import ref_layers as R
+    scal, gates, gated = R.irreps2gate(o3.Irreps(f"{C}x0e+{C}x1o+{C}x2e"))
+    ref = e3nn_nn.Gate(scal, [torch.nn.functional.silu], gates, [torch.sigmoid], gated)
+    mine = gmp_b200.Gate(str(scal), str(gates), str(gated)).cuda()
+    g = torch.Generator().manual_seed(n)
+    x = torch.randn(n, ref.irreps_in.dim, generator=g) * 2
+    cot = torch.randn(n, ref.irreps_out.dim, generator=g)
+    xr = x.clone().requires_grad_(True)
+    out_r = ref(xr)
+    (gr,) = torch.autograd.grad((out_r * cot).sum(), xr)
+    xm = x.cuda().requires_grad_(True)
+    out_m = mine(xm)
+    (gm,) = torch.autograd.grad((out_m * cot.cuda()).sum(), xm)
+    assert rel_err(out_m, out_r) <= 1e-5 and rel_err(gm, gr) <= 1e-5
+    act = gmp_b200.tfn.ScalarActivation()
+    xs = x[:, :C].contiguous()
+    ref_a = e3nn_nn.Activation(o3.Irreps(f"{C}x0e"), [torch.nn.functional.silu])
+    xr2, xm2 = xs.clone().requires_grad_(True), xs.cuda().requires_grad_(True)
+    o_r, o_m = ref_a(xr2), act(xm2)
+    (g2r,) = torch.autograd.grad(o_r.sum(), xr2)
+    (g2m,) = torch.autograd.grad(o_m.sum(), xm2)
+    assert rel_err(o_m, o_r) <= 1e-5 and rel_err(g2m, g2r) <= 1e-5

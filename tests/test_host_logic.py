@@ -206,3 +206,29 @@ def test_interaction_block_state_dict_keys_match_the_reference():
         ref = {k: tuple(v.shape) for k, v in fx["state"].items() if "output_mask" not in k and not k.startswith("conv_tp.")}
         own = {k: tuple(v.shape) for k, v in m.state_dict().items()}
         assert own == ref, (cls, set(own) ^ set(ref))
+
+
+@pytest.mark.parametrize("world,n,r", [(2, 1000, 1.0), (3, 500, 2.5), (5, 300, 6.0), (4, 4, 1.0)])
+def test_slab_partition_peer_tables_are_mutually_consistent(world, n, r):
+    """The peer-memory halo exchange reads, on rank p, rows out of rank q's buffers at offsets p computes by itself
+    (gmp_b200.distributed.slab_partition: peer_send_start, peer_halo_offset).  They must equal what q does with its own
+    tables: the start of q's send range towards p, and where p's rows sit inside q's [left halo | right halo] rows --
+    also when slabs are thinner than the radius (halo rows from several ranks, world = 5 here)."""
+    import gmp_b200
+    g = torch.Generator().manual_seed(world * 1000 + n)
+    xs = torch.sort(torch.rand(n, generator=g) * 20.0).values
+    parts = [gmp_b200.slab_partition(xs, r, p, world) for p in range(world)]
+    assert len({pt.n_own_max for pt in parts}) == 1 and len({pt.halo_max for pt in parts}) == 1
+    assert parts[0].n_own_max == max(pt.n_own for pt in parts)
+    assert parts[0].halo_max == max(max(pt.n_left + pt.n_right for pt in parts), 1)
+    for p in range(world):
+        for q in range(world):
+            if p == q:
+                continue
+            a, b = parts[q].send_ranges[p]
+            assert parts[p].recv_counts[q] == b - a
+            if b > a:
+                assert parts[p].peer_send_start[q] == a
+            # rows owned by p inside q's halo rows: q's halo is [from rank 0 | from rank 1 | ...] without q itself
+            off = sum(parts[q].recv_counts[p2] for p2 in range(p) if p2 != q)
+            assert parts[p].peer_halo_offset[q] == off
