@@ -74,7 +74,7 @@ def slab_partition(x_sorted: torch.Tensor, r: float, rank: int, world: int) -> S
     bounds = [(n * p) // world for p in range(world + 1)]
     # the 2 * world window edges are located on the device the array lives on (two searchsorted calls over the sorted
     # array, 2 * world values read back once); nothing of size n crosses to the host
-    xs = x_sorted.detach()
+    xs = x_sorted.detach().contiguous()   # (a column view such as pos[:, 0] is strided)
     nonempty = [p for p in range(world) if bounds[p + 1] > bounds[p]]
     wins = [(bounds[p], bounds[p]) for p in range(world)]
     if nonempty:
