@@ -49,6 +49,29 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 // took 37 % of all issued instructions (profiles/r02_summary.md: BRA + SYNCS.PHASECHK + YIELD in schnet_fwd_tc2_kernel).
 // With the hint (10 ms, the value CUTLASS's ClusterBarrier::wait passes) the warp sleeps until the barrier wakes it.
 constexpr uint32_t kMbarSuspendHintNs = 0x989680u;
+#if defined(GMP_MBAR_SLEEP_NS) && GMP_MBAR_SLEEP_NS > 0
+// Variant with a fixed sleep between probes (profiles/r02_summary.md, "mbarrier wait loops"): NANOSLEEP.SYNCS -- what the
+// suspend-time hint compiles to -- is cut short by the traffic on the CTA's other barriers, so a waiting warp still probes
+// every ~20 cycles; a plain nanosleep is not.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}\n" : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    while (!done) {
+        __nanosleep(GMP_MBAR_SLEEP_NS);
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}\n" : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    }
+}
+#else
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     asm volatile(
         "{\n\t"
@@ -60,6 +83,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "WAIT_DONE:\n\t"
         "}\n" ::"r"(smem_u32(bar)), "r"(parity), "r"(kMbarSuspendHintNs) : "memory");
 }
+#endif
 
 #endif
 
