@@ -85,3 +85,17 @@ def test_schnet_chains(n):
     dagg_r = dT_r @ w2
     assert rel_err(gt, gt_r) <= TOL and rel_err(dT, dT_r) <= TOL and rel_err(dagg, dagg_r) <= 2 * TOL
     assert rel_err(dagg16.float(), dagg_r) <= 2 * TOL
+
+
+@pytest.mark.parametrize("n", [1, 31, 32, 33, 1000, 4097, 131072])
+def test_wgrad_bulk_pipeline(n):
+    """dW = g^T x, db = column sums of g (nn.Linear parameter gradients, 128 x 128) on the bulk-copy pipelined reduction kernel:
+    ragged row counts around the 32-row tile, fewer tiles than CTAs, the config-2 node count."""
+    from gmp_b200 import nodechain as nc
+    gen = torch.Generator().manual_seed(n)
+    g, x = torch.randn(n, 128, generator=gen).cuda(), torch.randn(n, 128, generator=gen).cuda()
+    dw, db = nc.wgrad(g, x)
+    ref_w, ref_b = g.double().t() @ x.double(), g.double().sum(0)
+    assert rel_err(dw, ref_w) <= TOL and rel_err(db, ref_b) <= 1e-5
+    dw2, db2 = nc.wgrad(g, x)
+    assert torch.equal(dw, dw2) and torch.equal(db, db2)
