@@ -686,7 +686,9 @@ def bench_cube(D, args, log2n: int = None, layers: int = 4, self_check: bool = T
     torch.manual_seed(0)
     # halo rows: pulled out of the owners' symmetric-memory buffers by our own kernel (P2P loads over NVLink, csrc/halo.cu);
     # if symmetric memory cannot be set up on this box the grouped ncclSend / ncclRecv exchange runs instead (reported)
-    halo, halo_note = ("peer" if world > 1 and args.halo == "peer" else "nccl"), None
+    halo, halo_note = (args.halo if world > 1 else "nccl"), None
+    if halo == "fused" and args.precision != "bf16":
+        halo = "peer"
     model = gmp_b200.PartitionedEGNN(num_layers=layers, emb_dim=128, precision=args.precision, halo=halo).to(dev)
     params = list(model.parameters())
     h_own = torch.randn(part.n_own, 128, device=dev)
@@ -700,16 +702,17 @@ def bench_cube(D, args, log2n: int = None, layers: int = 4, self_check: bool = T
         (ho.sum() + po.sum()).backward()
         gmp_b200.allreduce_gradients(params)
 
-    if halo == "peer":
+    while halo != "nccl":       # fused -> peer -> nccl: every rank takes the same fallback
         ok = 1.0
         try:
             step()
             torch.cuda.synchronize()
-        except Exception as ex:  # noqa: BLE001 -- e.g. no P2P mapping between the devices
-            ok, halo_note = 0.0, f"{type(ex).__name__}: {str(ex)[:160]}"
-        if D.reduce([ok], "max")[0] != 1.0 or D.reduce([-ok], "max")[0] != -1.0:   # any rank failed: all fall back together
-            halo = "nccl"
-            model.halo, model._peer = "nccl", None
+        except Exception as ex:  # noqa: BLE001 -- e.g. no P2P mapping between the devices, slabs thinner than the radius
+            ok, halo_note = 0.0, f"{halo}: {type(ex).__name__}: {str(ex)[:160]}"
+        if D.reduce([-ok], "max")[0] == -1.0:
+            break
+        halo = "peer" if halo == "fused" else "nccl"
+        model.halo, model._peer, model._peer_q = halo, None, None
     check = partition_self_check(D, halo=halo) if (world > 1 and self_check) else None
     K = max(2, min(args.steps, 3))
     ms = D.timed(step, 2, K)
@@ -726,8 +729,11 @@ def bench_cube(D, args, log2n: int = None, layers: int = 4, self_check: bool = T
                        + (", halo exchange per layer" if world > 1 else ""),
            "n_gpus": world, "scaling": "strong", "precision": "fp32-strict (1e-5)" if args.precision == "fp32" else "bf16 tcgen05 (1e-2; ReLU gradients: see tests)",
            "nodes": n, "edges": int(E_tot), "halo_nodes_max": int(halo_rows),
-           "halo_exchange": None if world == 1 else ("peer-memory pull kernel (symmetric memory, P2P loads over NVLink; csrc/halo.cu)" if halo == "peer"
-                                                     else "grouped ncclSend / ncclRecv" + (f" (peer path unavailable: {halo_note})" if halo_note else "")),
+           "halo_exchange": None if world == 1 else (
+               {"fused": "features: none -- the edge kernels' gather reads halo sources' projected rows out of the neighbours' symmetric-memory "
+                         "buffers (P2P loads over NVLink inside egnn_fwd_tc2 / egnn_bwd_tc); positions and returning gradients: pull kernel (csrc/halo.cu)",
+                "peer": "peer-memory pull kernel (symmetric memory, P2P loads over NVLink; csrc/halo.cu)",
+                "nccl": "grouped ncclSend / ncclRecv"}[halo] + (f" (fell back: {halo_note})" if halo_note else "")),
            "steps": K, "ms_per_step": ms,
            "edges_per_s_per_layer": E_tot * layers / (ms * 1e-3), "graph_build_s": t_graph,
            "roofline": {"bound": "tensor" if f_tc >= f_hbm else "hbm", "achieved": tf if f_tc >= f_hbm else gbs,
@@ -752,6 +758,7 @@ def partition_self_check(D, log2n: int = 15, halo: str = "nccl"):
         pos = synth_cube(log2n, seed=1).to(dev)
         n = pos.shape[0]
         torch.manual_seed(3)
+        halo = "peer" if halo == "fused" else halo     # the fp32 check has no bf16 rows to read across: it validates the partition + pull kernels
         model = gmp_b200.PartitionedEGNN(num_layers=2, emb_dim=128, precision="fp32", halo=halo).to(dev)
         g = torch.Generator().manual_seed(5)
         h = torch.randn(n, 128, generator=g).to(dev)
@@ -797,7 +804,8 @@ if __name__ == "__main__":
     ap.add_argument("--no-strict", action="store_true", help="skip the secondary fp32-strict measurement")
     ap.add_argument("--only", default="", help="comma-separated config numbers to run (2 = headline SchNet, 3 = TFN, 4 = MACE, 5 = EGNN large graph)")
     ap.add_argument("--cube-log2n", type=int, default=CUBE_LOG2N, help="config 5: log2 of the node count of the radius graph")
-    ap.add_argument("--halo", default="peer", choices=["peer", "nccl"], help="config 5 at N > 1: halo rows through the peer-memory pull kernel or NCCL send/recv")
+    ap.add_argument("--halo", default="fused", choices=["fused", "peer", "nccl"],
+                    help="config 5 at N > 1: halo rows read inside the gather from the neighbours' memory (fused), through the peer-memory pull kernel, or NCCL send/recv")
     ap.add_argument("--cpu-molecules", type=int, default=0, help="--impl reference: molecules of the bench batch to time (default: all 4096)")
     a = ap.parse_args()
     if a.impl == "reference":

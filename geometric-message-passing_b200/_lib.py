@@ -38,6 +38,10 @@ class NodeStage(C.Structure):
                 ("add_res", P), ("out_f32", P), ("out_bf16", P), ("out_pre", P)]
 
 
+class PeerRows(C.Structure):
+    _fields_ = [("left", P), ("right", P), ("n_left", I64), ("n_own", I64)]
+
+
 class EgnnParams(C.Structure):
     _fields_ = [(k, P) for k in ("wd", "ln1_g", "ln1_b", "w1", "b1", "ln2_g", "ln2_b", "w2", "b2", "ln3_g", "ln3_b",
                                  "w3", "b3")] + [("d", I32), ("act", I32), ("ln_eps", F32), ("aggr_mean", I32)]
@@ -75,8 +79,8 @@ _SIGS = {
     "gmp_schnet_cfconv_bwd_tc2": [P, P, P, P, I64, I64, P, P, P, P, P, I32, P],
     "gmp_linear_wgrad_tc": [P, P, I64, I32, I32, P, P],
     "gmp_egnn_tc_edge_fwd": [P, P, P, I64, I64, P, P, P, P, P, P, P],
-    "gmp_egnn_tc2_edge_fwd": [P, P, P, I64, I64, P, P, P, P, P, P, P, P],
-    "gmp_egnn_tc_edge_bwd_fused": [P, P, P, P, I64, I64, P, P, P, P, P, P, P, P, P, P, P, P],
+    "gmp_egnn_tc2_edge_fwd": [P, P, P, I64, I64, P, P, P, P, P, P, P, P, P],
+    "gmp_egnn_tc_edge_bwd_fused": [P, P, P, P, I64, I64, P, P, P, P, P, P, P, P, P, P, P, P, P],
     "gmp_segment_sum_bf16_f32": [P, P, P, P, I64, I32, P],
     "gmp_egnn_tc_edge_bwd": [P, P, P, P, I64, I64, P, P, P, P, P, P, I32, P, P, P, P],
     "gmp_tp_contract": [P, P, P, I64, I64, P, I32, P, I32, P, I32, P, I32, P, P, P, P, I32, P, P, I32, I32, P, I32, P],

@@ -56,6 +56,26 @@ __device__ __forceinline__ float warp_sum(float v) {
 
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 
+// gathered bf16 row j of a destination-partitioned operand (include/gmp_b200.h, gmp_peer_rows): own rows local, halo rows in
+// the neighbouring ranks' memory.  n_own == 0: not partitioned, every row is local.
+struct PeerRows {
+    const uint8_t* left;
+    const uint8_t* right;
+    int64_t n_left, n_own;
+};
+__device__ __forceinline__ const uint8_t* peer_row(const void* own, const PeerRows& p, int64_t j, int row_bytes) {
+    if (p.n_own == 0) return reinterpret_cast<const uint8_t*>(own) + j * row_bytes;
+    if (j < p.n_left) return p.left + j * row_bytes;
+    j -= p.n_left;
+    if (j < p.n_own) return reinterpret_cast<const uint8_t*>(own) + j * row_bytes;
+    return p.right + (j - p.n_own) * row_bytes;
+}
+inline PeerRows make_peer_rows(const gmp_peer_rows* p) {
+    PeerRows r{nullptr, nullptr, 0, 0};
+    if (p) { r.left = (const uint8_t*)p->left; r.right = (const uint8_t*)p->right; r.n_left = p->n_left; r.n_own = p->n_own; }
+    return r;
+}
+
 // first row r in [0, n] with rowptr[r] >= target  (rowptr non-decreasing, rowptr[n] = E)
 __device__ __forceinline__ int lower_bound_row(const int32_t* __restrict__ rowptr, int n, int64_t target) {
     int lo = 0, hi = n;

@@ -31,6 +31,7 @@ struct EgnnTcArgs {
     int64_t n, E;
     const float* rowt;              // [n,128] fp32, indexed by the CSR row: P (dst pass) / Q (src pass)
     const __nv_bfloat16* gath;      // [n,128] bf16, indexed by col:       Q (dst pass) / P (src pass)
+    PeerRows peer;                  // fused dst pass on a partitioned graph: halo rows of Q in the neighbours' memory
     const float* pos;
     const float *wd, *g1, *be1, *w1, *b1, *g2, *be2, *w2, *b2, *g3, *be3, *w3, *b3;
     int aggr_mean, nranges, grange;
@@ -164,7 +165,7 @@ __device__ __forceinline__ void egnn_tc_tile_forward(GCtx& c, const EgnnTcArgs& 
     for (int x = t; x < kGT * 16; x += kGThreads) {
         const int r = x >> 4, ch = x & 15;
         uint8_t* dst = sm + oGG + r * kGLd + ch * 16;
-        if (r < cnt) __pipeline_memcpy_async(dst, a.gath + (int64_t)c.ints[kGT + r] * kGF + ch * 8, 16);
+        if (r < cnt) __pipeline_memcpy_async(dst, peer_row(a.gath, a.peer, c.ints[kGT + r], kGF * 2) + ch * 16, 16);
         else *reinterpret_cast<uint4*>(dst) = make_uint4(0u, 0u, 0u, 0u);
     }
     __pipeline_commit();
@@ -854,6 +855,7 @@ static EgnnTcArgs egnn_tc_args(const int32_t* rowptr, const int32_t* col, const 
     EgnnTcArgs a;
     a.rowptr = rowptr; a.col = col; a.rowid = rowid; a.deg_rowptr = deg_rowptr; a.perm = nullptr; a.n = n; a.E = E; a.rowt = rowt;
     a.dpre_out = nullptr; a.ddelta_out = nullptr;
+    a.peer = make_peer_rows(nullptr);
     a.gath = (const __nv_bfloat16*)gath; a.pos = pos;
     a.wd = p->wd; a.g1 = p->ln1_g; a.be1 = p->ln1_b; a.w1 = p->w1; a.b1 = p->b1; a.g2 = p->ln2_g; a.be2 = p->ln2_b;
     a.w2 = p->w2; a.b2 = p->b2; a.g3 = p->ln3_g; a.be3 = p->ln3_b; a.w3 = p->w3; a.b3 = p->b3;
@@ -929,13 +931,16 @@ int gmp_egnn_tc_edge_bwd(const int32_t* rowptr, const int32_t* col, const int32_
 int gmp_egnn_tc_edge_bwd_fused(const int32_t* rowptr, const int32_t* col, const int32_t* perm, const int32_t* rowid, int64_t n,
                                int64_t num_edges, const float* P, const void* Q_bf16, const float* pos, const gmp_egnn_edge_params* prm,
                                const float* g_msg, const float* g_pos, float* dP, float* dpos_i, float* wgrad_parts, void* dpre1_bf16,
-                               float* ddelta, gmp_stream_t stream) {
+                               float* ddelta, const gmp_peer_rows* peer, gmp_stream_t stream) {
     if (int rc = egnn_tc_check(prm, n, num_edges)) return rc;
+    GMP_REQUIRE(!peer || (peer->n_left >= 0 && peer->n_own > 0 && peer->n_left + peer->n_own <= n && (peer->n_left == 0 || peer->left) &&
+                          (peer->n_left + peer->n_own == n || peer->right)), "egnn_tc_edge_bwd_fused: inconsistent peer rows");
     GMP_REQUIRE(rowptr && g_msg && g_pos && dP && dpos_i && pos && wgrad_parts &&
                 (num_edges == 0 || (col && rowid && P && Q_bf16 && dpre1_bf16 && ddelta)), "egnn_tc_edge_bwd_fused: NULL pointer");
     if (n == 0) return GMP_OK;
     EgnnTcArgs a = egnn_tc_args(rowptr, col, rowid, rowptr, n, num_edges, P, Q_bf16, pos, prm);
     a.perm = perm; a.dpre_out = (__nv_bfloat16*)dpre1_bf16; a.ddelta_out = ddelta;
+    a.peer = make_peer_rows(peer);
     const int grid = a.nranges < num_sms() ? a.nranges : num_sms();
     if (prm->act) {
         GMP_CUDA(cudaFuncSetAttribute(egnn_bwd_tc_kernel<1, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kEgnnTcSmem));

@@ -46,7 +46,8 @@ struct Egnn2Args {
     const int32_t *rowptr, *col, *rowid;
     int64_t n, E;
     const float* P;                  // [n,128] fp32, indexed by the CSR row (destination i): h_i half of the first Linear (+ bias)
-    const __nv_bfloat16* Q;          // [n,128] bf16, indexed by col (source j)
+    const __nv_bfloat16* Q;          // [n,128] bf16, indexed by col (source j); with `peer`: the owned rows only
+    PeerRows peer;                   // halo rows of Q in the neighbouring ranks' memory (n_own = 0: none)
     const float* pos;
     const float *wd, *g1, *be1, *w1, *b1, *g2, *be2, *w2, *b2, *g3, *be3, *w3, *b3;
     int aggr_mean;
@@ -211,7 +212,7 @@ __global__ void __launch_bounds__(kE2Threads, 1) egnn_fwd_tc2_kernel(Egnn2Args a
             const bool flag = valid && (r == 0 || ridp != rid);
             // gather this edge's Q row (bf16, 256 B) into its own row of the operand image: 16 asynchronous 16-byte copies
             {
-                const __nv_bfloat16* qrow = a.Q + (int64_t)src * 128;
+                const __nv_bfloat16* qrow = reinterpret_cast<const __nv_bfloat16*>(peer_row(a.Q, a.peer, src, 256));
 #pragma unroll
                 for (int c16 = 0; c16 < 16; ++c16) cp_async16(A + img_chunk(r, c16), qrow + c16 * 8);
             }
@@ -466,8 +467,10 @@ int32_t gmp_egnn_tc2_num_chunks(int64_t num_edges) { return egnn2_grid(num_edges
 
 int gmp_egnn_tc2_edge_fwd(const int32_t* rowptr, const int32_t* col, const int32_t* rowid, int64_t n, int64_t num_edges, const float* P,
                           const void* Q_bf16, const float* pos, const gmp_egnn_edge_params* p, float* msg_aggr, float* pos_aggr,
-                          float* head, gmp_stream_t stream) {
+                          float* head, const gmp_peer_rows* peer, gmp_stream_t stream) {
     GMP_REQUIRE(p, "egnn_tc2: params is NULL");
+    GMP_REQUIRE(!peer || (peer->n_left >= 0 && peer->n_own > 0 && peer->n_left + peer->n_own <= n && (peer->n_left == 0 || peer->left) &&
+                          (peer->n_left + peer->n_own == n || peer->right)), "egnn_tc2: inconsistent peer rows");
     GMP_REQUIRE(p->d == 128, "egnn_tc2: the tensor-core path is built for emb_dim = 128 (got %d)", p->d);
     GMP_REQUIRE(p->act == 0 || p->act == 1, "egnn_tc2: act must be 0 (relu) or 1 (swish)");
     GMP_REQUIRE(p->wd && p->ln1_g && p->ln1_b && p->w1 && p->b1 && p->ln2_g && p->ln2_b && p->w2 && p->b2 && p->ln3_g && p->ln3_b &&
@@ -482,6 +485,7 @@ int gmp_egnn_tc2_edge_fwd(const int32_t* rowptr, const int32_t* col, const int32
     GMP_CUDA(cudaMemsetAsync(head, 0, (size_t)nchunks * kE2Head * sizeof(float), stream));
     Egnn2Args a;
     a.rowptr = rowptr; a.col = col; a.rowid = rowid; a.n = n; a.E = num_edges; a.P = P; a.Q = (const __nv_bfloat16*)Q_bf16; a.pos = pos;
+    a.peer = make_peer_rows(peer);
     a.wd = p->wd; a.g1 = p->ln1_g; a.be1 = p->ln1_b; a.w1 = p->w1; a.b1 = p->b1; a.g2 = p->ln2_g; a.be2 = p->ln2_b;
     a.w2 = p->w2; a.b2 = p->b2; a.g3 = p->ln3_g; a.be3 = p->ln3_b; a.w3 = p->w3; a.b3 = p->b3;
     a.aggr_mean = p->aggr_mean; a.eps = p->ln_eps; a.msg_aggr = msg_aggr; a.pos_aggr = pos_aggr; a.head = head;

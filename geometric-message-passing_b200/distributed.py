@@ -127,18 +127,18 @@ class PeerHalo:
         self._bufs = {}
         self._turn = {}
 
-    def buffer(self, rows: int, feat: int, tag: str):
+    def buffer(self, rows: int, feat: int, tag: str, dtype=torch.float32, copies: int = 2):
         import torch.distributed._symmetric_memory as symm
         key = (rows, feat, tag)
         if key not in self._bufs:
             pair = []
-            for _ in range(2):
-                t = symm.empty(max(rows, 1) * feat, dtype=torch.float32, device=self.device)
+            for _ in range(copies):
+                t = symm.empty(max(rows, 1) * feat, dtype=dtype, device=self.device)
                 pair.append((t, symm.rendezvous(t, self.group)))
             self._bufs[key] = pair
             self._turn[key] = 0
         k = self._turn[key]
-        self._turn[key] = k ^ 1
+        self._turn[key] = (k + 1) % len(self._bufs[key])
         return self._bufs[key][k]
 
 
@@ -184,24 +184,72 @@ class _PeerHaloExchange(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g_local: torch.Tensor):
-        part: SlabPartition = ctx.part
-        peer: PeerHalo = ctx.peer
-        g_local = g_local.contiguous()
-        feat = g_local.shape[1]
-        rb = feat * 4
-        buf, hdl = peer.buffer(part.halo_max, feat, "bwd")
-        stage = buf.view(-1, feat)
-        if part.n_left:
-            stage[:part.n_left].copy_(g_local[:part.n_left])
-        if part.n_right:
-            stage[part.n_left:part.n_left + part.n_right].copy_(g_local[part.n_left + part.n_own:])
+        return _return_halo_gradients(g_local, ctx.part, ctx.peer), None, None
+
+
+def _return_halo_gradients(g_local: torch.Tensor, part: SlabPartition, peer: PeerHalo) -> torch.Tensor:
+    """g_local [n_local, F] -> g_own [n_own, F]: the halo rows go back to their owners, which pull them out of this rank's
+    staging buffer and add them onto the rows they had exposed, peer by peer in rank order."""
+    g_local = g_local.contiguous()
+    feat = g_local.shape[1]
+    rb = feat * 4
+    buf, hdl = peer.buffer(part.halo_max, feat, "bwd")
+    stage = buf.view(-1, feat)
+    if part.n_left:
+        stage[:part.n_left].copy_(g_local[:part.n_left])
+    if part.n_right:
+        stage[part.n_left:part.n_left + part.n_right].copy_(g_local[part.n_left + part.n_own:])
+    hdl.barrier()
+    g_own = g_local[part.own_slice].clone()
+    for q in range(part.world):          # one launch per peer, in rank order: overlapping ranges are added in a fixed order
+        a, b = part.send_ranges[q]
+        if b > a:
+            _pull([int(hdl.buffer_ptrs[q]) + part.peer_halo_offset[q] * rb], [g_own.data_ptr() + a * rb], [(b - a) * rb], add=True)
+    return g_own
+
+
+class _PeerQFn(torch.autograd.Function):
+    """Autograd edge of the fused gather: forward publishes nothing itself (the projection already wrote the owned bf16 rows
+    into the peer-visible buffer) -- it orders that write before the neighbours' reads with the device-side barrier and
+    returns a shape-only placeholder for `Q` over the local rows; backward receives dL/dQ for every local row (segment sums
+    over the source-sorted CSR, halo rows included) and returns the halo rows' part to their owners."""
+
+    @staticmethod
+    def forward(ctx, q_own: torch.Tensor, part: SlabPartition, peer: PeerHalo, hdl):
+        ctx.part, ctx.peer = part, peer
         hdl.barrier()
-        g_own = g_local[part.own_slice].clone()
-        for q in range(part.world):          # one launch per peer, in rank order: overlapping ranges are added in a fixed order
-            a, b = part.send_ranges[q]
-            if b > a:
-                _pull([int(hdl.buffer_ptrs[q]) + part.peer_halo_offset[q] * rb], [g_own.data_ptr() + a * rb], [(b - a) * rb], add=True)
-        return g_own, None, None
+        return q_own.new_zeros(1, 1).expand(part.n_local, q_own.shape[1])
+
+    @staticmethod
+    def backward(ctx, g_local: torch.Tensor):
+        return _return_halo_gradients(g_local, ctx.part, ctx.peer), None, None, None
+
+
+class PeerQ:
+    """Per layer: the peer-visible bf16 buffer of the projected rows Q = h W0b^T of the OWNED nodes (kept from the forward to
+    the backward pass of the same step: the backward kernel gathers the same rows again), and the gmp_peer_rows the edge
+    kernels need to find a halo source's row in the left / right neighbour's buffer.  Only neighbouring ranks may
+    contribute halo rows (slabs at least one radius thick)."""
+
+    def __init__(self, peer: PeerHalo, layer: int):
+        from ._lib import PeerRows
+        part = peer.part
+        for q in range(part.world):
+            if part.recv_counts[q] > 0 and abs(q - part.rank) != 1:
+                raise NotImplementedError("fused halo gather: halo rows from non-adjacent ranks (slabs thinner than the radius)")
+        self.peer, self.part = peer, part
+        self.buf, self.hdl = peer.buffer(part.n_own_max, 128, f"q16.{layer}", dtype=torch.bfloat16, copies=1)
+        r = part.rank
+        left = (int(self.hdl.buffer_ptrs[r - 1]) + part.peer_send_start[r - 1] * 256) if part.n_left else None
+        right = (int(self.hdl.buffer_ptrs[r + 1]) + part.peer_send_start[r + 1] * 256) if part.n_right else None
+        self.rows = PeerRows(left, right, part.n_left, part.n_own)
+
+    def project(self, h_own: torch.Tensor, w: torch.Tensor):
+        """(Q placeholder over the local rows, bf16 owned rows in the peer-visible buffer, gmp_peer_rows)."""
+        from . import nodechain as nc
+        q16 = self.buf.view(-1, 128)[:self.part.n_own]
+        q_own, _ = nc.ChainLinearFn.apply(h_own, w, None, True, q16)
+        return _PeerQFn.apply(q_own, self.part, self.peer, self.hdl), q16, self.rows
 
 
 class _HaloExchange(torch.autograd.Function):
@@ -279,27 +327,35 @@ class PartitionedEGNN(torch.nn.Module):
     def __init__(self, num_layers: int = 4, emb_dim: int = 128, activation: str = "relu", aggr: str = "sum",
                  residual: bool = True, precision: str = "fp32", halo: str = "nccl"):
         """halo: "nccl" = grouped send/recv (also what the gloo CPU tests run); "peer" = pull kernels over symmetric
-        memory (P2P loads over NVLink, csrc/halo.cu)."""
+        memory (P2P loads over NVLink, csrc/halo.cu); "fused" (bf16 mode) = as "peer" for the positions and the returning
+        gradients, while the feature rows are not exchanged at all: each rank projects Q for its owned rows into a
+        peer-visible buffer and the edge kernels' gather reads halo sources' rows out of the neighbours' memory."""
         super().__init__()
         from .egnn import EGNNLayer
-        assert halo in ("nccl", "peer")
+        assert halo in ("nccl", "peer", "fused")
         self.residual, self.halo = residual, halo
-        self._peer = None
+        self._peer, self._peer_q = None, None
         self.convs = torch.nn.ModuleList([EGNNLayer(emb_dim, activation, "layer", aggr, precision) for _ in range(num_layers)])
 
     def _peer_for(self, part: SlabPartition, device, group):
-        if self.halo != "peer" or part.world == 1:
+        if self.halo == "nccl" or part.world == 1:
             return None
         if self._peer is None or self._peer.part is not part:
             self._peer = PeerHalo(part, device, group)
+            self._peer_q = [PeerQ(self._peer, l) for l in range(len(self.convs))] if self.halo == "fused" else None
         return self._peer
 
     def forward(self, h_own, pos_own, edge_index_local, part: SlabPartition, group=None):
         own = part.own_slice
         peer = self._peer_for(part, h_own.device, group)
-        for conv in self.convs:
-            h_loc = halo_exchange(h_own, part, group, peer)
+        for l, conv in enumerate(self.convs):
             pos_loc = halo_exchange(pos_own, part, group, peer)
+            if peer is not None and self._peer_q is not None:
+                h_upd, pos_upd = conv(h_own, pos_loc, edge_index_local, rows=own, peer_q=self._peer_q[l])
+                h_own = h_own + h_upd if self.residual else h_upd
+                pos_own = pos_upd
+                continue
+            h_loc = halo_exchange(h_own, part, group, peer)
             h_upd, pos_upd = conv(h_loc, pos_loc, edge_index_local, rows=own)   # node-side work on owned rows only
             h_own = h_own + h_upd if self.residual else h_upd
             pos_own = pos_upd

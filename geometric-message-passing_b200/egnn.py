@@ -41,10 +41,18 @@ class _EGNNEdgeFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, P, Q, pos, graph: Graph, act: int, eps: float, aggr_mean: int, precision: int, *w):
-        P, Q, pos = P.contiguous(), Q.contiguous(), pos.contiguous()
-        *w, Q16 = w      # last extra argument: a bf16 copy of Q when the producer already made one (else None)
+        # last two extra arguments: a bf16 copy of Q when the producer already made one (else None), and -- destination-
+        # partitioned graph with the gather fused with the halo transfer -- the peer rows (Q16 then holds the owned rows only,
+        # Q is a shape-only placeholder that carries the autograd edge: gmp_b200.distributed._PeerQFn)
+        *w, Q16, peer = w
+        P, pos = P.contiguous(), pos.contiguous()
+        if peer is None:
+            Q = Q.contiguous()
+        elif precision != _lib.BF16_TC or Q16 is None or not _TC2_FWD:
+            raise GmpError("peer rows need the bf16 tensor-core path with a bf16 copy of Q")
         w = tuple(t.contiguous() for t in w)
         Q16 = Q.to(torch.bfloat16) if (Q16 is None and precision == _lib.BF16_TC) else Q16
+        pr = C.byref(peer) if peer is not None else None
         d = P.shape[1]
         prm = _params_struct(w, d, act, eps, aggr_mean)
         csr = graph.by_dst
@@ -56,7 +64,7 @@ class _EGNNEdgeFn(torch.autograd.Function):
             if _TC2_FWD:
                 head = torch.empty(int(_lib.lib().gmp_egnn_tc2_num_chunks(graph.E)), 132, dtype=P.dtype, device=P.device)
                 call("gmp_egnn_tc2_edge_fwd", ptr(csr.rowptr), ptr(csr.col), ptr(csr.row_ids()), graph.n, graph.E, ptr(P),
-                     ptr(Q16), ptr(pos), C.byref(prm), ptr(msg), ptr(pag), ptr(head))
+                     ptr(Q16), ptr(pos), C.byref(prm), ptr(msg), ptr(pag), ptr(head), pr)
             else:
                 call("gmp_egnn_tc_edge_fwd", ptr(csr.rowptr), ptr(csr.col), ptr(csr.row_ids()), graph.n, graph.E, ptr(P),
                      ptr(Q16), ptr(pos), C.byref(prm), ptr(msg), ptr(pag))
@@ -64,7 +72,7 @@ class _EGNNEdgeFn(torch.autograd.Function):
             call("gmp_egnn_edge_fwd", ptr(csr.rowptr), ptr(csr.col), graph.n, graph.E, ptr(P), ptr(Q), ptr(pos),
                  C.byref(prm), ptr(msg), ptr(pag), precision)
         ctx.save_for_backward(P, Q, pos, *w)
-        ctx.graph, ctx.meta, ctx.Q16 = graph, (act, eps, aggr_mean, precision), Q16
+        ctx.graph, ctx.meta, ctx.Q16, ctx.peer = graph, (act, eps, aggr_mean, precision), Q16, peer
         return msg, pag
 
     @staticmethod
@@ -80,7 +88,10 @@ class _EGNNEdgeFn(torch.autograd.Function):
         nparts = lib.gmp_egnn_tc_bwd_num_parts(graph.E) if tc else lib.gmp_egnn_bwd_num_parts(graph.E)
         plen = lib.gmp_egnn_bwd_part_len(d)
         parts = torch.empty(nparts, plen, dtype=P.dtype, device=P.device)
-        dP, dQ = torch.empty_like(P), torch.empty_like(Q)
+        dP, dQ = torch.empty_like(P), torch.empty(graph.n, d, dtype=P.dtype, device=P.device)
+        if ctx.peer is not None and not (tc and graph.E * 272 <= _FUSED_BWD_SCRATCH_BYTES):
+            raise GmpError("peer rows: only the single-pass backward reads halo rows from the neighbours' memory "
+                           "(the per-edge scratch exceeds _FUSED_BWD_SCRATCH_BYTES)")
         dpos_i, dpos_j = torch.empty_like(pos), torch.empty_like(pos)
         cd, cs = graph.by_dst, graph.by_src
         if tc and graph.E * 272 <= _FUSED_BWD_SCRATCH_BYTES:
@@ -91,7 +102,7 @@ class _EGNNEdgeFn(torch.autograd.Function):
             ddelta = torch.empty(max(E, 1), 4, dtype=P.dtype, device=P.device)
             call("gmp_egnn_tc_edge_bwd_fused", ptr(cd.rowptr), ptr(cd.col), cd.perm_ptr, ptr(cd.row_ids()), graph.n, E, ptr(P),
                  ptr(ctx.Q16), ptr(pos), C.byref(prm), ptr(g_msg), ptr(g_pos), ptr(dP), ptr(dpos_i), ptr(parts),
-                 ptr(dpre1), ptr(ddelta))
+                 ptr(dpre1), ptr(ddelta), C.byref(ctx.peer) if ctx.peer is not None else None)
             call("gmp_segment_sum_bf16_f32", ptr(cs.rowptr), cs.perm_ptr, ptr(dpre1), ptr(dQ), graph.n, d)
             dsum = torch.empty(graph.n, 4, dtype=P.dtype, device=P.device)
             call("gmp_segment_reduce_f32", ptr(cs.rowptr), cs.perm_ptr, ptr(ddelta), ptr(dsum), graph.n, 4, 0)
@@ -114,7 +125,7 @@ class _EGNNEdgeFn(torch.autograd.Function):
         # order of *w: wd, ln1_g, ln1_b, w1, b1, ln2_g, ln2_b, w2, b2, ln3_g, ln3_b, w3, b3
         grads_w = (v(9), v(2), v(3), red[:dd].view(d, d), v(0), v(4), v(5), red[dd:2 * dd].view(d, d), v(1), v(6), v(7),
                    v(8).view_as(w[11]), vec[10 * d:10 * d + 1].view_as(w[12]))
-        return (dP, dQ, dpos_i + dpos_j, None, None, None, None, None, *grads_w, None)
+        return (dP, dQ, dpos_i + dpos_j, None, None, None, None, None, *grads_w, None, None)
 
 
 class EGNNLayer(nn.Module):
@@ -139,20 +150,32 @@ class EGNNLayer(nn.Module):
         self.mlp_upd = Sequential(Linear(2 * emb_dim, emb_dim), self.norm(emb_dim), self.activation,
                                   Linear(emb_dim, emb_dim), self.norm(emb_dim), self.activation)
 
-    def forward(self, h, pos, edge_index, rows: slice = None):
+    def forward(self, h, pos, edge_index, rows: slice = None, peer_q=None):
         """rows (not in the reference signature): restrict the destination side to h[rows] -- the destination-partitioned
         path passes its owned slice, every edge of `edge_index` then ends in it and only those rows are returned, so no
-        node-side work is spent on halo rows (they are message sources only)."""
+        node-side work is spent on halo rows (they are message sources only).
+        peer_q (with rows): a gmp_b200.distributed.PeerQ; `h` then holds the owned rows only and the halo sources' projected
+        rows are read from the neighbouring ranks' memory inside the edge kernels' gather."""
         d = self.emb_dim
-        n = h.shape[0]
+        n = pos.shape[0] if peer_q is not None else h.shape[0]     # (peer_q: h = owned rows, pos = every local row)
         graph = get_graph(edge_index, n)
         lin0 = self.mlp_msg[0]
         W0 = lin0.weight
         h_dst = h if rows is None else h[rows]
         # bf16 mode: the node-side Linears run on the tcgen05 chain kernel (csrc/node_chain.cu) instead of library GEMMs
         chain = self.node_chain and self.precision == "bf16" and h.is_cuda and d == 128 and n > 0 and h.dtype == torch.float32
-        Q16 = None
-        if chain:
+        Q16 = peer = None
+        if peer_q is not None:
+            # destination-partitioned graph, gather fused with the halo transfer: `h` holds the OWNED rows only (`pos` every local
+            # row); Q is projected for the owned rows straight into a peer-visible buffer and the edge kernels read the halo
+            # sources' rows out of the neighbouring ranks' buffers (gmp_b200.distributed.PeerQ)
+            if not chain:
+                raise GmpError("peer_q needs the bf16 chain path (precision='bf16', emb_dim 128)")
+            from . import nodechain as nc
+            h_dst = h
+            P, _ = nc.ChainLinearFn.apply(h, W0[:, :d], lin0.bias, False)
+            Q, Q16, peer = peer_q.project(h, W0[:, d:2 * d])
+        elif chain:
             from . import nodechain as nc
             P, _ = nc.ChainLinearFn.apply(h_dst, W0[:, :d], lin0.bias, False)
             Q, Q16 = nc.ChainLinearFn.apply(h, W0[:, d:2 * d], None, True)     # the edge kernels gather Q as bf16 rows
@@ -167,7 +190,7 @@ class EGNNLayer(nn.Module):
         msg_aggr, pos_aggr = _EGNNEdgeFn.apply(
             P, Q, pos, graph, self._act_id, float(ln1.eps), int(self.aggr == "mean"), _PREC[self.precision],
             wd, ln1.weight, ln1.bias, lin1.weight, lin1.bias, ln2.weight, ln2.bias, lin2.weight, lin2.bias,
-            ln3.weight, ln3.bias, lin3.weight, lin3.bias, Q16)
+            ln3.weight, ln3.bias, lin3.weight, lin3.bias, Q16, peer)
         if rows is not None:
             msg_aggr, pos_aggr, pos = msg_aggr[rows], pos_aggr[rows], pos[rows]
         if chain:

@@ -48,10 +48,12 @@ def run(a0: torch.Tensor, stages: Sequence[NodeStage], a1: Optional[torch.Tensor
 
 
 def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None, act: Optional[str] = None,
-           res: Optional[torch.Tensor] = None, want_bf16: bool = False):
-    """act(x W^T + b) (+ res) as one launch; returns (fp32 result, bf16 copy or None).  No autograd."""
+           res: Optional[torch.Tensor] = None, want_bf16: bool = False, out16: Optional[torch.Tensor] = None):
+    """act(x W^T + b) (+ res) as one launch; returns (fp32 result, bf16 copy or None).  No autograd.
+    out16: caller-provided bf16 [n,128] destination of the copy (e.g. a peer-visible symmetric-memory buffer)."""
     out = torch.empty(x.shape[0], 128, dtype=torch.float32, device=x.device)
-    o16 = torch.empty(x.shape[0], 128, dtype=torch.bfloat16, device=x.device) if want_bf16 else None
+    o16 = out16 if out16 is not None else (torch.empty(x.shape[0], 128, dtype=torch.bfloat16, device=x.device) if want_bf16 else None)
+    assert o16 is None or (o16.dtype == torch.bfloat16 and tuple(o16.shape) == (x.shape[0], 128) and o16.is_contiguous())
     img = pack_w(weight)
     x2 = None
     if weight.shape[1] == 256:
@@ -76,12 +78,12 @@ class ChainLinearFn(torch.autograd.Function):
     (non-differentiable) output; dx on the chain kernel (transposed image), dW / db on the reduction kernel."""
 
     @staticmethod
-    def forward(ctx, x, w, b, want_bf16: bool):
+    def forward(ctx, x, w, b, want_bf16: bool, out16=None):
         x = x.contiguous()
-        y, y16 = linear(x, w, b, want_bf16=want_bf16)
+        y, y16 = linear(x, w, b, want_bf16=want_bf16, out16=out16)
         ctx.save_for_backward(x, w)
         ctx.has_bias = b is not None
-        if y16 is None:
+        if y16 is None or out16 is not None:     # (a caller-provided buffer is not handed back: the caller holds it)
             y16 = x.new_empty(0, dtype=torch.bfloat16)
         ctx.mark_non_differentiable(y16)
         return y, y16
@@ -97,7 +99,7 @@ class ChainLinearFn(torch.autograd.Function):
         dw = db = None
         if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
             dw, db = wgrad(g, x)
-        return dx, dw, (db if ctx.has_bias else None), None
+        return dx, dw, (db if ctx.has_bias else None), None, None
 
 
 def ln_act_bwd(g, pre, gamma, beta, eps, act: str, want_act: bool):

@@ -304,10 +304,20 @@ int gmp_egnn_tc_edge_fwd(const int32_t* rowptr, const int32_t* col, const int32_
  * chunks; rows that straddle a chunk boundary are completed by a fix-up kernel from `head`
  * (float [num_chunks][132], scratch).  msg_aggr / pos_aggr are zeroed here (rows without edges stay zero). */
 int32_t gmp_egnn_tc2_num_chunks(int64_t num_edges);
+/* Destination-partitioned graph, gather fused with the halo transfer: with local numbering
+ * [left halo | owned | right halo], Q_bf16 then holds the OWNED rows only and the rows of halo sources are read, inside the
+ * kernel's gather, from the neighbouring ranks' Q arrays through peer-mapped pointers (NVLink loads; symmetric memory):
+ * row j < n_left -> left + j, j < n_left + n_own -> Q_bf16 + (j - n_left), else right + (j - n_left - n_own), 128 bf16 each.
+ * left / right already point at the first row this rank reads.  NULL = Q_bf16 holds every local row (single GPU). */
+typedef struct gmp_peer_rows {
+    const void* left;
+    const void* right;
+    int64_t n_left, n_own;
+} gmp_peer_rows;
 int gmp_egnn_tc2_edge_fwd(const int32_t* rowptr, const int32_t* col, const int32_t* rowid, int64_t n, int64_t num_edges,
                           const float* P, const void* Q_bf16, const float* pos,
                           const gmp_egnn_edge_params* prm /* host */, float* msg_aggr, float* pos_aggr, float* head,
-                          gmp_stream_t stream);
+                          const gmp_peer_rows* peer /* host, may be NULL */, gmp_stream_t stream);
 /* Backward, two recompute passes as gmp_egnn_edge_bwd.  row_operand (fp32) / col_operand_bf16 are P / bf16(Q) in the
  * dst pass (src_pass = 0) and Q / bf16(P) in the src pass.  Both passes write per-CTA partials into the SAME
  * wgrad_parts [gmp_egnn_tc_bwd_num_parts(E)][gmp_egnn_bwd_part_len(128)]: the dst pass the two weight matrices
@@ -322,7 +332,7 @@ int gmp_egnn_tc_edge_bwd_fused(const int32_t* rowptr, const int32_t* col, const 
                                int64_t n, int64_t num_edges, const float* P, const void* Q_bf16, const float* pos,
                                const gmp_egnn_edge_params* prm /* host */, const float* g_msg, const float* g_pos,
                                float* dP, float* dpos_i, float* wgrad_parts, void* dpre1_bf16, float* ddelta,
-                               gmp_stream_t stream);
+                               const gmp_peer_rows* peer /* host, may be NULL: as in gmp_egnn_tc2_edge_fwd */, gmp_stream_t stream);
 int gmp_egnn_tc_edge_bwd(const int32_t* rowptr, const int32_t* col, const int32_t* rowid, const int32_t* dst_rowptr,
                          int64_t n, int64_t num_edges, const float* row_operand, const void* col_operand_bf16,
                          const float* pos, const gmp_egnn_edge_params* prm /* host */, const float* g_msg,
