@@ -804,8 +804,10 @@ if __name__ == "__main__":
     ap.add_argument("--no-strict", action="store_true", help="skip the secondary fp32-strict measurement")
     ap.add_argument("--only", default="", help="comma-separated config numbers to run (2 = headline SchNet, 3 = TFN, 4 = MACE, 5 = EGNN large graph)")
     ap.add_argument("--cube-log2n", type=int, default=CUBE_LOG2N, help="config 5: log2 of the node count of the radius graph")
-    ap.add_argument("--halo", default="fused", choices=["fused", "peer", "nccl"],
-                    help="config 5 at N > 1: halo rows read inside the gather from the neighbours' memory (fused), through the peer-memory pull kernel, or NCCL send/recv")
+    ap.add_argument("--halo", default="peer", choices=["fused", "peer", "nccl"],
+                    help="config 5 at N > 1: halo rows through the peer-memory pull kernel (default: fastest), read inside the gather from the "
+                         "neighbours' memory (fused: every halo row then crosses NVLink once per incident edge, ~16x, instead of once: "
+                         "584.8 vs 568.5 ms at 2 GPUs, profiles/r02_summary.md), or NCCL send/recv")
     ap.add_argument("--cpu-molecules", type=int, default=0, help="--impl reference: molecules of the bench batch to time (default: all 4096)")
     a = ap.parse_args()
     if a.impl == "reference":
