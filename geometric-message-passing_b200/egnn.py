@@ -206,22 +206,50 @@ class EGNNLayer(nn.Module):
 
 
 class MPNNLayer(nn.Module):
-    """Vanilla message-passing layer (models/layers/egnn_layer.py:92-155): the same scatter without geometry.
-    Not fused (a by-product of the EGNN path): node rows are gathered, the MLP is library GEMMs, the
-    aggregation is the deterministic segmented reduction."""
+    """Vanilla message-passing layer (models/layers/egnn_layer.py:92-155): the EGNN message without geometry.
+    With LayerNorm its message MLP ``Linear(2d, d), LN, act, Linear(d, d), LN, act`` over ``cat[h_i, h_j]`` followed by the
+    sum / mean over destination rows is exactly the feature half of the EGNN edge kernel (csrc/egnn.cu) with a zero distance
+    column, so it runs there -- fused gather, MLP and atomics-free segmented reduction, nothing per-edge in HBM -- with an
+    all-zero coordinate branch (its results and gradients are discarded).  norm="batch" (statistics over all edges between
+    the two Linears) takes the unfused path: gathered rows, library GEMMs, the deterministic segmented reduction."""
 
     def __init__(self, emb_dim, activation="relu", norm="layer", aggr="add"):
         super().__init__()
-        self.emb_dim, self.aggr = emb_dim, aggr
+        self.emb_dim, self.aggr, self._norm = emb_dim, aggr, norm
+        self._act_id = {"relu": 0, "swish": 1}[activation]
         act = {"swish": SiLU(), "relu": ReLU()}[activation]
         nrm = {"layer": torch.nn.LayerNorm, "batch": torch.nn.BatchNorm1d}[norm]
         self.mlp_msg = Sequential(Linear(2 * emb_dim, emb_dim), nrm(emb_dim), act, Linear(emb_dim, emb_dim), nrm(emb_dim), act)
         self.mlp_upd = Sequential(Linear(2 * emb_dim, emb_dim), nrm(emb_dim), act, Linear(emb_dim, emb_dim), nrm(emb_dim), act)
+        self._zeros = {}
+
+    def _coordinate_branch_stub(self, n, d, like):
+        """Parameters of an EGNN coordinate branch that contributes nothing, and positions with non-zero edge lengths."""
+        key = (n, d, str(like.device))
+        if key not in self._zeros:
+            z = lambda *shape: torch.zeros(*shape, dtype=like.dtype, device=like.device)
+            pos = z(n, 3)
+            pos[:, 0] = torch.arange(n, dtype=like.dtype, device=like.device)
+            self._zeros = {key: dict(pos=pos, wd=z(d), w2=z(d, d), b2=z(d), g3=torch.ones(d, dtype=like.dtype, device=like.device),
+                                     be3=z(d), w3=z(1, d), b3=z(1))}
+        return self._zeros[key]
 
     def forward(self, h, edge_index):
-        graph = get_graph(edge_index, h.shape[0])
-        msg = self.mlp_msg(torch.cat([h[edge_index[1]], h[edge_index[0]]], dim=-1))
-        aggr = segment_reduce(msg, graph.by_dst, self.aggr)
+        n, d = h.shape[0], self.emb_dim
+        graph = get_graph(edge_index, n)
+        if (self._norm == "layer" and d in (64, 128) and h.is_cuda and h.dtype == torch.float32 and self.aggr in ("add", "sum", "mean")
+                and n > 0):
+            lin0, ln1, lin1, ln2 = self.mlp_msg[0], self.mlp_msg[1], self.mlp_msg[3], self.mlp_msg[4]
+            W0 = lin0.weight
+            P = F.linear(h, W0[:, :d], lin0.bias)      # h_i half (+ bias): h[edge_index[1]] comes first in the reference's cat
+            Q = F.linear(h, W0[:, d:2 * d])            # h_j half
+            st = self._coordinate_branch_stub(n, d, h)
+            aggr, _ = _EGNNEdgeFn.apply(P, Q, st["pos"], graph, self._act_id, float(ln1.eps), int(self.aggr == "mean"), _lib.FP32_STRICT,
+                                        st["wd"], ln1.weight, ln1.bias, lin1.weight, lin1.bias, ln2.weight, ln2.bias,
+                                        st["w2"], st["b2"], st["g3"], st["be3"], st["w3"], st["b3"], None, None)
+        else:
+            msg = self.mlp_msg(torch.cat([h[edge_index[1]], h[edge_index[0]]], dim=-1))
+            aggr = segment_reduce(msg, graph.by_dst, self.aggr)
         return self.mlp_upd(torch.cat([h, aggr], dim=-1))
 
 
