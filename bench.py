@@ -423,6 +423,21 @@ def bench_config2(D, args):
     ms_e2e = s2.elapsed_time(e2) / K
     clk = clocks.stop() if rank == 0 else None
 
+    # ---- graph construction (not part of the step: the reference receives edge_index ready-made): bit-exact radius_graph + both CSR sorts
+    def build_graph():
+        e = gmp_b200.radius_graph(pos, CFG["cutoff"], batch, max_num_neighbors=CFG["max_num_neighbors"])
+        g_ = gmp_b200.Graph(e, N)
+        return g_.by_dst.rowptr, g_.by_src.rowptr
+    build_graph()
+    torch.cuda.synchronize()
+    s4, e4 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s4.record()
+    for _ in range(3):
+        build_graph()
+    e4.record()
+    torch.cuda.synchronize()
+    ms_graph = s4.elapsed_time(e4) / 3
+
     # ---- roofline of the dominant kernels, each timed alone with CUDA events on the launch stream ---------------
     roof = dominant_kernel_roofline(model, b, E, N, dev, args) if rank == 0 else None
 
@@ -475,6 +490,8 @@ def bench_config2(D, args):
                     roofline=roof, cpu_baseline=cpu, fp32_strict=strict,
                     e2e={"value": E_total * L / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                          "d2h_bytes_per_step": out_host.numel() * 4, "ms_per_step": ms_e2e},
+                    graph_build={"ms": ms_graph, "edges_per_s": float(E) / (ms_graph * 1e-3),
+                                 "what": "gmp_b200.radius_graph (torch_cluster order, bit-exact) + dst- and src-sorted CSR, per GPU, outside the timed step"},
                     gpu_launches=int(launches), graph_kernel_nodes=graph_nodes, clocks=clk)
     return line
 

@@ -10,6 +10,7 @@ Layout
   tfn.py       TensorProductConvLayer / TFNModel                   (models/layers/tfn_layer.py, models/tfn.py)
   mace.py      SymmetricContraction / EquivariantProductBasisBlock / MACEModel (models/mace_modules, models/mace.py)
   mace_blocks.py  the ACEsuit-style 'uvu' interaction blocks       (models/mace_modules/blocks.py:136-530)
+  gvp.py       GVP / GVPConvLayer / GVPGNNModel                     (models/layers/gvp_layer.py, models/gvpgnn.py)
 """
 from . import _lib  # noqa: F401
 from .graph import CSR, Graph, build_csr, get_graph, radius_graph  # noqa: F401
@@ -27,6 +28,8 @@ from . import mace_blocks  # noqa: F401,E402
 from .mace_blocks import (AgnosticNonlinearInteractionBlock, AgnosticResidualNonlinearInteractionBlock,  # noqa: F401,E402
                           RealAgnosticInteractionBlock, RealAgnosticResidualInteractionBlock,
                           ResidualElementDependentInteractionBlock, UVUTensorProduct)
+from . import gvp  # noqa: F401,E402
+from .gvp import GVP, GVPConv, GVPConvLayer, GVPGNNModel  # noqa: F401,E402
 from .data import Batch, Data, DataLoader, DevicePrefetcher, coalesce, to_undirected  # noqa: F401,E402
 from .graphs import GraphedStep  # noqa: F401,E402
 from . import distributed  # noqa: F401,E402

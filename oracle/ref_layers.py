@@ -525,6 +525,149 @@ class InteractionBlock(nn.Module):
         return message + sc
 
 
+
+# ----------------------------------------------------------------------------------------------------------------------
+# GVP-GNN -- models/layers/gvp_layer.py:101-438, models/gvpgnn.py:9-126
+# ----------------------------------------------------------------------------------------------------------------------
+def _clamped_norm(x, axis=-1, keepdims=False, eps=1e-8, sqrt=True):
+    """gvp_layer.py:66-73."""
+    out = torch.clamp(torch.sum(torch.square(x), axis, keepdims), min=eps)
+    return torch.sqrt(out) if sqrt else out
+
+
+class GVP(nn.Module):
+    """gvp_layer.py:101-170.  Parameter names (wh, ws, wv, wsv, dummy_param) are the reference's."""
+
+    def __init__(self, in_dims, out_dims, h_dim=None, activations=(F.relu, torch.sigmoid), vector_gate=True):
+        super().__init__()
+        (self.si, self.vi), (self.so, self.vo) = in_dims, out_dims
+        self.vector_gate, (self.scalar_act, self.vector_act) = vector_gate, activations
+        if self.vi:
+            self.h_dim = h_dim or max(self.vi, self.vo)
+            self.wh = nn.Linear(self.vi, self.h_dim, bias=False)
+            self.ws = nn.Linear(self.h_dim + self.si, self.so)
+            if self.vo:
+                self.wv = nn.Linear(self.h_dim, self.vo, bias=False)
+                if vector_gate:
+                    self.wsv = nn.Linear(self.so, self.vo)
+        else:
+            self.ws = nn.Linear(self.si, self.so)
+        self.dummy_param = nn.Parameter(torch.empty(0))
+
+    def forward(self, x):
+        if not self.vi:                                            # :161-164
+            s = self.ws(x)
+            v = torch.zeros(s.shape[0], self.vo, 3) if self.vo else None
+        else:                                                      # :146-160
+            s, v = x
+            vh = torch.einsum("hc,ncx->nxh", self.wh.weight, v)
+            s = self.ws(torch.cat([s, _clamped_norm(vh, axis=-2)], -1))
+            if self.vo:
+                v = torch.einsum("oh,nxh->nox", self.wv.weight, vh)
+                if self.vector_gate:
+                    v = v * torch.sigmoid(self.wsv(self.vector_act(s) if self.vector_act else s)).unsqueeze(-1)
+                elif self.vector_act:
+                    v = v * self.vector_act(_clamped_norm(v, axis=-1, keepdims=True))
+        if self.scalar_act:
+            s = self.scalar_act(s)
+        return (s, v) if self.vo else s
+
+
+class GVPLayerNorm(nn.Module):
+    """gvp_layer.py:221-243."""
+
+    def __init__(self, dims):
+        super().__init__()
+        self.s, self.v = dims
+        self.scalar_norm = nn.LayerNorm(self.s)
+
+    def forward(self, x):
+        if not self.v:
+            return self.scalar_norm(x)
+        s, v = x
+        vn = torch.sqrt(torch.mean(_clamped_norm(v, axis=-1, keepdims=True, sqrt=False), dim=-2, keepdim=True))
+        return self.scalar_norm(s), v / vn
+
+
+class _GVPDropout(nn.Module):
+    """gvp_layer.py:173-218 in eval mode (identity); keeps the reference's parameter key."""
+
+    def __init__(self, drop_rate):
+        super().__init__()
+        self.sdropout = nn.Dropout(drop_rate)
+        self.vdropout = nn.Module()
+        self.vdropout.dummy_param = nn.Parameter(torch.empty(0))
+
+    def forward(self, x):
+        assert not self.training, "the oracle restates the deterministic (eval) path of the GVP dropout"
+        return x
+
+
+class GVPConvLayer(nn.Module):
+    """gvp_layer.py:246-438 (GVPConv inlined as `conv`): messages over cat[(s_j, V_j), edge, (s_i, V_i)] (:319-324), scatter mean
+    over edge_index[1] with dim_size = N (PyG propagate), then the two residual + LayerNorm steps (:432-435)."""
+
+    def __init__(self, node_dims, edge_dims, n_message=3, n_feedforward=2, drop_rate=0.1, activations=(F.relu, torch.sigmoid),
+                 vector_gate=True, residual=True):
+        super().__init__()
+        mk = lambda i, o, **kw: GVP(i, o, **{"activations": activations, "vector_gate": vector_gate, **kw})
+        (si, vi), (se, ve) = node_dims, edge_dims
+        cat_dims = (2 * si + se, 2 * vi + ve)
+        self.conv = nn.Module()
+        if n_message == 1:
+            msg = [mk(cat_dims, node_dims, activations=(None, None))]
+        else:
+            msg = [mk(cat_dims, node_dims)] + [mk(node_dims, node_dims) for _ in range(n_message - 2)] + [mk(node_dims, node_dims, activations=(None, None))]
+        self.conv.message_func = nn.Sequential(*msg)
+        self.norm = nn.ModuleList([GVPLayerNorm(node_dims) for _ in range(2)])
+        self.dropout = nn.ModuleList([_GVPDropout(drop_rate) for _ in range(2)])
+        if n_feedforward == 1:
+            ff = [mk(node_dims, node_dims, activations=(None, None))]
+        else:
+            hid = (4 * si, 2 * vi)
+            ff = [mk(node_dims, hid)] + [mk(hid, hid) for _ in range(n_feedforward - 2)] + [mk(hid, node_dims, activations=(None, None))]
+        self.ff_func = nn.Sequential(*ff)
+        self.residual, self.vo = residual, vi
+
+    def forward(self, x, edge_index, edge_attr):
+        s, v = x
+        j, i = edge_index[0], edge_index[1]
+        ms, mv = self.conv.message_func((torch.cat([s[j], edge_attr[0], s[i]], -1), torch.cat([v[j], edge_attr[1], v[i]], -2)))
+        agg = scatter(torch.cat([ms, mv.reshape(mv.shape[0], -1)], -1), i, dim=0, dim_size=s.shape[0], reduce="mean")
+        dh = (agg[:, :-3 * self.vo], agg[:, -3 * self.vo:].reshape(-1, self.vo, 3))
+        x = self.norm[0]((s + dh[0], v + dh[1])) if self.residual else dh
+        dh = self.ff_func(x)
+        return self.norm[1]((x[0] + dh[0], x[1] + dh[1])) if self.residual else dh
+
+
+class GVPGNNModel(nn.Module):
+    """models/gvpgnn.py:9-126."""
+
+    def __init__(self, r_max=10.0, num_bessel=8, num_polynomial_cutoff=5, num_layers=5, in_dim=1, out_dim=1, s_dim=128, v_dim=16,
+                 s_dim_edge=32, v_dim_edge=1, pool="sum", residual=True, equivariant_pred=False):
+        super().__init__()
+        self.s_dim, self.equivariant_pred = s_dim, equivariant_pred
+        self.emb_in = nn.Embedding(in_dim, s_dim)
+        self.W_v = nn.Sequential(GVPLayerNorm((s_dim, 0)), GVP((s_dim, 0), (s_dim, v_dim), activations=(None, None)))
+        self.radial_embedding = RadialEmbeddingBlock(r_max, num_bessel, num_polynomial_cutoff)
+        self.W_e = nn.Sequential(GVPLayerNorm((num_bessel, 1)), GVP((num_bessel, 1), (s_dim_edge, v_dim_edge), activations=(None, None)))
+        self.layers = nn.ModuleList(GVPConvLayer((s_dim, v_dim), (s_dim_edge, v_dim_edge), activations=(F.relu, None), residual=residual)
+                                    for _ in range(num_layers))
+        self.pool = _POOL[pool]
+        self.pred = (nn.Linear(s_dim + v_dim * 3, out_dim) if equivariant_pred else
+                     nn.Sequential(nn.Linear(s_dim, s_dim), nn.ReLU(), nn.Linear(s_dim, out_dim)))
+
+    def forward(self, batch):
+        vec = batch.pos[batch.edge_index[0]] - batch.pos[batch.edge_index[1]]        # :102-103
+        length = torch.linalg.norm(vec, dim=-1, keepdim=True)
+        h_v = self.W_v(self.emb_in(batch.atoms))
+        h_e = self.W_e((self.radial_embedding(length), torch.nan_to_num(vec / length).unsqueeze(-2)))
+        for layer in self.layers:
+            h_v = layer(h_v, batch.edge_index, h_e)
+        out = self.pool(torch.cat([h_v[0], h_v[1].reshape(h_v[1].shape[0], -1)], -1), batch.batch)
+        return self.pred(out if self.equivariant_pred else out[:, :self.s_dim])
+
+
 def create_kchains(k: int):
     """experiments/kchains.ipynb:71-107: two (k+2)-node chains whose k centre nodes sit at
     (0, 5i, 0); the first end node is at (-4,-3,0) in graph 0 and (+4,-3,0) in graph 1;

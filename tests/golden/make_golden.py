@@ -262,6 +262,7 @@ def main():
              outputs=outs, cotangent=cots, grads=grads)
 
     interaction_blocks()
+    gvp_fixtures()
 
 
 def interaction_blocks():
@@ -292,6 +293,46 @@ def interaction_blocks():
              outputs=outs, cotangent=cots, grads=grads,
              extra=dict(irreps_mid=str(blk.conv_tp.irreps_out), weight_numel=blk.conv_tp.weight_numel, irreps_out=str(blk.irreps_out),
                         instructions=[(i.i_in1, i.i_in2, i.i_out) for i in blk.conv_tp.instructions]))
+
+
+def gvp_fixtures():
+    """GVPConvLayer (models/layers/gvp_layer.py:327-438) and GVPGNNModel (models/gvpgnn.py), eval mode (dropout off)."""
+    import models.layers.gvp_layer as ref_gvp
+    from models.gvpgnn import GVPGNNModel
+    d = random_clouds(3, 12, 3.0, 2.0, 41)
+    N, E = d.pos.shape[0], d.edge_index.shape[1]
+    g = _gen(42)
+    torch.manual_seed(43)
+    ctor = dict(node_dims=(16, 4), edge_dims=(8, 1), drop_rate=0.1, vector_gate=True, residual=True)
+    layer = ref_gvp.GVPConvLayer(activations=(torch.nn.functional.relu, None), **ctor)
+    layer.eval()
+    s, v = torch.randn(N, 16, generator=g), torch.randn(N, 4, 3, generator=g)
+    es, ev = torch.randn(E, 8, generator=g), torch.randn(E, 1, 3, generator=g)
+
+    class Wrap(torch.nn.Module):
+        def __init__(self, m):
+            super().__init__()
+            self.m = m
+
+        def forward(self, s_, v_, es_, ev_, ei):
+            return self.m((s_, v_), ei, (es_, ev_))
+
+    w = Wrap(layer)
+    w.eval()
+    outs, cots, grads = run(w, (s, v, es, ev, d.edge_index), {"s": s, "v": v, "edge_s": es, "edge_v": ev}, 44)
+    save("gvp_conv_layer", ctor=ctor, state={k[2:]: t for k, t in w._state0.items()},
+         inputs=dict(s=s.detach(), v=v.detach(), edge_s=es.detach(), edge_v=ev.detach(), edge_index=d.edge_index),
+         outputs=outs, cotangent=cots, grads={k.replace("param.m.", "param."): t for k, t in grads.items()})
+
+    torch.manual_seed(45)
+    mctor = dict(r_max=2.0, num_layers=2, s_dim=16, v_dim=4, s_dim_edge=8, v_dim_edge=1, out_dim=2)
+    m = GVPGNNModel(**mctor)
+    m.eval()
+    pos = d.pos.clone()
+    d.pos = pos
+    outs, cots, grads = run(m, (d,), {}, 46)
+    save("gvp_model", ctor=mctor, state=strip_buffers(m._state0),
+         inputs=dict(atoms=d.atoms, pos=pos.detach(), edge_index=d.edge_index, batch=d.batch), outputs=outs, cotangent=cots, grads=grads)
 
 
 class _NoNone(torch.nn.Module):

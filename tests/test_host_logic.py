@@ -232,3 +232,12 @@ def test_slab_partition_peer_tables_are_mutually_consistent(world, n, r):
             # rows owned by p inside q's halo rows: q's halo is [from rank 0 | from rank 1 | ...] without q itself
             off = sum(parts[q].recv_counts[p2] for p2 in range(p) if p2 != q)
             assert parts[p].peer_halo_offset[q] == off
+
+
+def test_gvp_state_dict_keys_match_the_reference():
+    import gmp_b200
+    from tests.helpers import load_golden
+    fx = load_golden("gvp_model")
+    own = {k: tuple(v.shape) for k, v in gmp_b200.GVPGNNModel(**fx["ctor"]).state_dict().items()}
+    ref = {k: tuple(v.shape) for k, v in fx["state"].items()}
+    assert own == ref, set(own) ^ set(ref)

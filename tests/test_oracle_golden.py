@@ -183,3 +183,35 @@ def test_mace_interaction_block(cls):
 
     outs, grads = _run(W(), (i["node_attrs"], x, i["edge_attrs"], ef, i["edge_index"]), {"node_feats": x, "edge_feats": ef}, fx["cotangent"])
     _check(fx, outs, {k.replace("param.m.", "param."): v for k, v in grads.items()})
+
+
+def test_gvp_conv_layer():
+    """oracle GVPConvLayer against the reference run (models/layers/gvp_layer.py:327-438, eval mode)."""
+    import torch.nn.functional as F
+    fx = load_golden("gvp_conv_layer")
+    c = fx["ctor"]
+    m = R.GVPConvLayer(c["node_dims"], c["edge_dims"], drop_rate=c["drop_rate"], activations=(F.relu, None), vector_gate=c["vector_gate"],
+                       residual=c["residual"])
+    m = load_params(m, fx["state"]).eval()
+    i = fx["inputs"]
+    s, v, es, ev = (i[k].clone() for k in ("s", "v", "edge_s", "edge_v"))
+
+    class W(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.m = m
+
+        def forward(self, s_, v_, es_, ev_, ei):
+            return self.m((s_, v_), ei, (es_, ev_))
+
+    outs, grads = _run(W(), (s, v, es, ev, i["edge_index"]), {"s": s, "v": v, "edge_s": es, "edge_v": ev}, fx["cotangent"])
+    _check(fx, outs, {k.replace("param.m.", "param."): g for k, g in grads.items()})
+
+
+def test_gvp_model():
+    fx = load_golden("gvp_model")
+    m = load_params(R.GVPGNNModel(**fx["ctor"]), fx["state"]).eval()
+    i = fx["inputs"]
+    b = Bag(atoms=i["atoms"], pos=i["pos"].clone(), edge_index=i["edge_index"], batch=i["batch"])
+    outs, grads = _run(m, (b,), {}, fx["cotangent"])
+    _check(fx, outs, grads)
