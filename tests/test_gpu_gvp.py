@@ -82,3 +82,39 @@ def test_gvp_model_vs_oracle_default_widths():
         assert l2 <= 5e-4 and rel_err(a, b) <= 5e-3, (k, l2)
     o2 = mine(Bag(atoms=d["atoms"].cuda(), pos=d["pos"].cuda(), edge_index=ei.cuda(), batch=d["batch"].cuda(), num_graphs=6))
     assert torch.equal(o_m, o2)   # deterministic aggregation
+
+
+def test_gvp_layer_equivariance():
+    """GVPConvLayer: scalars invariant, vector channels rotate with the input under random O(3) elements; error not above
+    2x the oracle's."""
+    import gmp_b200
+    from oracle.thirdparty import o3
+    torch.manual_seed(1)
+    ref = R.GVPConvLayer((32, 8), (8, 1), activations=(F.relu, None)).eval()
+    mine = load_params(gmp_b200.GVPConvLayer((32, 8), (8, 1), activations=(F.relu, None)), ref.state_dict()).cuda().eval()
+    d = random_clouds(2, 14, 3.0, 1.8, 4)
+    pos, ei = d["pos"], d["edge_index"]
+    n, E = pos.shape[0], ei.shape[1]
+    g = torch.Generator().manual_seed(5)
+    s, v = torch.randn(n, 32, generator=g), torch.randn(n, 8, 3, generator=g)
+    es = torch.randn(E, 8, generator=g)
+    worst_r = worst_m = 0.0
+    for seed in range(4):
+        Rm = o3.rand_matrix(generator=torch.Generator().manual_seed(seed)).float() * (-1 if seed % 2 else 1)
+
+        def run(layer, p, vv, dev):
+            vec = p[ei[0]] - p[ei[1]]
+            ev = torch.nn.functional.normalize(vec, dim=-1).unsqueeze(-2)
+            with torch.no_grad():
+                os_, ov = layer((s.to(dev), vv.to(dev)), ei.to(dev), (es.to(dev), ev.to(dev)))
+            return os_.cpu(), ov.cpu()
+
+        for layer, dev, which in ((ref, "cpu", "r"), (mine, "cuda", "m")):
+            s0, v0 = run(layer, pos, v, dev)
+            s1, v1 = run(layer, pos @ Rm.T, v @ Rm.T, dev)
+            err = max(rel_err(s1, s0), rel_err(v1, v0 @ Rm.T))
+            if which == "r":
+                worst_r = max(worst_r, err)
+            else:
+                worst_m = max(worst_m, err)
+    assert worst_m <= max(2 * worst_r, 5e-6), (worst_m, worst_r)

@@ -92,3 +92,40 @@ def test_uvu_conv_deterministic():
     x, sh, w = torch.randn(N, 9 * C, generator=g).cuda(), torch.randn(E, 9, generator=g).cuda(), torch.randn(E, 11 * C, generator=g).cuda()
     a, b = tp(x, ei, sh, w), tp(x, ei, sh, w)
     assert a.shape == (N, 35 * C) and torch.equal(a, b)
+
+
+def test_interaction_block_equivariance():
+    """RealAgnosticInteractionBlock on the fused uvu kernels: the output transforms with D^l under a random O(3) element
+    (proper rotations and reflections), error not above 2x the oracle's (SURVEY.md 8c equivariance bar)."""
+    import gmp_b200
+    from oracle.thirdparty import o3
+    C = 16
+    ir = f"{C}x0e+{C}x1o+{C}x2e"
+    ctor = dict(node_attrs_irreps="2x0e", node_feats_irreps=ir, edge_attrs_irreps="1x0e+1x1o+1x2e", edge_feats_irreps="8x0e",
+                target_irreps=ir, hidden_irreps=ir, avg_num_neighbors=6.0)
+    torch.manual_seed(4)
+    ref = R.InteractionBlock("real_agnostic", **ctor)
+    mine = load_params(gmp_b200.RealAgnosticInteractionBlock(**ctor), ref.state_dict()).cuda()
+    d = random_clouds(3, 12, 3.0, 1.8, 9)
+    pos, ei = d["pos"], d["edge_index"]
+    n = pos.shape[0]
+    g = torch.Generator().manual_seed(2)
+    attrs = torch.eye(2)[torch.randint(0, 2, (n,), generator=g)]
+    x = torch.randn(n, 9 * C, generator=g)
+    shm, rad = o3.SphericalHarmonics(o3.Irreps("1x0e+1x1o+1x2e"), True, "component"), R.RadialEmbeddingBlock(2.0, 8, 5)
+    rs = R.reshape_irreps(ir)
+    inv_rs = lambda t: torch.cat([t[:, :, 0:1].reshape(n, -1), t[:, :, 1:4].reshape(n, -1), t[:, :, 4:9].reshape(n, -1)], dim=1)
+    worst_r = worst_m = 0.0
+    for seed in range(4):
+        Rm = o3.rand_matrix(generator=torch.Generator().manual_seed(seed)).float() * (-1 if seed % 2 else 1)
+        D = o3.irreps_D(ir, Rm.double()).float()
+
+        def run(block, p, xx, dev):
+            vec = p[ei[0]] - p[ei[1]]
+            with torch.no_grad():
+                out, _ = block(attrs.to(dev), xx.to(dev), shm(vec).to(dev), rad(vec.norm(dim=-1, keepdim=True)).to(dev), ei.to(dev))
+            return inv_rs(out.cpu())     # [n, C, 9] -> e3nn layout, on which D acts
+
+        worst_r = max(worst_r, rel_err(run(ref, pos @ Rm.T, x @ D.T, "cpu"), run(ref, pos, x, "cpu") @ D.T))
+        worst_m = max(worst_m, rel_err(run(mine, pos @ Rm.T, x @ D.T, "cuda"), run(mine, pos, x, "cuda") @ D.T))
+    assert worst_m <= max(2 * worst_r, 5e-6), (worst_m, worst_r)
