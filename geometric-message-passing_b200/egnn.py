@@ -133,17 +133,19 @@ class EGNNLayer(nn.Module):
 
     def __init__(self, emb_dim, activation="relu", norm="layer", aggr="add", precision: str = "fp32"):
         super().__init__()
-        if norm != "layer":
-            raise NotImplementedError("gmp_b200.EGNNLayer fuses LayerNorm; norm='batch' needs statistics over all "
-                                      "edges before the second Linear and is not built (DESIGN.md, out of scope)")
-        if aggr not in ("add", "sum", "mean"):
-            raise NotImplementedError(f"aggr={aggr!r}: the fused reduction implements add/sum/mean")
+        if norm not in ("layer", "batch") or aggr not in ("add", "sum", "mean", "max"):
+            raise ValueError(f"EGNNLayer: norm={norm!r}, aggr={aggr!r} (the reference takes layer/batch and add/sum/mean/max)")
+        # The fused edge kernels implement the reference defaults' family: LayerNorm with add / sum / mean.  norm="batch"
+        # (statistics over ALL edges between two Linears: a grid-wide dependency in the middle of the fused MLP) and aggr="max"
+        # take the unfused path below: gathered rows, library GEMMs, the deterministic segmented reduction (max: an index
+        # reduction, order-independent by construction).
+        self._fused = norm == "layer" and aggr != "max"
         self.emb_dim, self.aggr, self.precision = emb_dim, aggr, precision
         # bf16 mode: P / Q projections and mlp_upd on the tcgen05 chain kernel (GMP_EGNN_NODE_CHAIN=0: library GEMMs, for A/B timing)
         self.node_chain = os.environ.get("GMP_EGNN_NODE_CHAIN", "1") != "0"
         self._act_id = {"relu": 0, "swish": 1}[activation]
         self.activation = {"swish": SiLU(), "relu": ReLU()}[activation]
-        self.norm = torch.nn.LayerNorm
+        self.norm = {"layer": torch.nn.LayerNorm, "batch": torch.nn.BatchNorm1d}[norm]
         self.mlp_msg = Sequential(Linear(2 * emb_dim + 1, emb_dim), self.norm(emb_dim), self.activation,
                                   Linear(emb_dim, emb_dim), self.norm(emb_dim), self.activation)
         self.mlp_pos = Sequential(Linear(emb_dim, emb_dim), self.norm(emb_dim), self.activation, Linear(emb_dim, 1))
@@ -156,6 +158,10 @@ class EGNNLayer(nn.Module):
         node-side work is spent on halo rows (they are message sources only).
         peer_q (with rows): a gmp_b200.distributed.PeerQ; `h` then holds the owned rows only and the halo sources' projected
         rows are read from the neighbouring ranks' memory inside the edge kernels' gather."""
+        if not self._fused:
+            if rows is not None or peer_q is not None:
+                raise NotImplementedError("norm='batch' / aggr='max' run unfused and are not partition-aware")
+            return self._forward_unfused(h, pos, edge_index)
         d = self.emb_dim
         n = pos.shape[0] if peer_q is not None else h.shape[0]     # (peer_q: h = owned rows, pos = every local row)
         graph = get_graph(edge_index, n)
@@ -200,6 +206,22 @@ class EGNNLayer(nn.Module):
         else:
             upd_out = self.mlp_upd(torch.cat([h_dst, msg_aggr], dim=-1))
         return upd_out, pos + pos_aggr
+
+    def _forward_unfused(self, h, pos, edge_index):
+        """models/layers/egnn_layer.py:50-86 op by op (the options the fused kernels do not cover)."""
+        n = h.shape[0]
+        j, i = edge_index[0], edge_index[1]
+        delta = pos[i] - pos[j]
+        dist = delta.norm(dim=-1, keepdim=True)
+        m = self.mlp_msg(torch.cat([h[i], h[j], dist], dim=-1))
+        shift = delta * self.mlp_pos(m)
+        csr = get_graph(edge_index, n).by_dst
+        if self.aggr == "max":     # rows without edges are 0, as torch_scatter.scatter(reduce="max") leaves them
+            m_aggr = torch.zeros(n, m.shape[1], dtype=m.dtype, device=m.device).scatter_reduce(
+                0, i.unsqueeze(-1).expand_as(m), m, "amax", include_self=False)
+        else:
+            m_aggr = segment_reduce(m, csr, "mean" if self.aggr == "mean" else "sum")
+        return self.mlp_upd(torch.cat([h, m_aggr], dim=-1)), pos + segment_reduce(shift, csr, "mean")
 
     def __repr__(self) -> str:
         return f"{self.__class__.__name__}(emb_dim={self.emb_dim}, aggr={self.aggr})"

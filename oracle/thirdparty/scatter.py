@@ -60,4 +60,12 @@ def scatter(src, index, dim: int = -1, out=None, dim_size=None, reduce: str = "s
         return scatter_sum(src, index, dim, out, dim_size)
     if reduce == "mean":
         return scatter_mean(src, index, dim, out, dim_size)
+    if reduce == "max":
+        # torch_scatter.scatter_max()[0] [upstream-recalled]: rows that receive nothing are 0 (the kernel fills them after the
+        # reduction: `out.masked_fill_(arg_out == src.size(dim), 0)`); the gradient goes to the arg-max entry
+        assert out is None
+        index = _broadcast(index, src, dim)
+        size = list(src.size())
+        size[dim] = dim_size if dim_size is not None else (int(index.max()) + 1 if index.numel() else 0)
+        return torch.zeros(size, dtype=src.dtype, device=src.device).scatter_reduce(dim, index, src, "amax", include_self=False)
     raise ValueError(f"oracle scatter: reduce={reduce!r} is outside the hot path")

@@ -185,3 +185,37 @@ def test_mpnn_layer_fused_vs_oracle(d, act, aggr):
     assert rel_err(out_m, out_r) <= TOL
     for name, a, b in zip(["h"] + list(pr), gm, gr):
         assert rel_err(a, b) <= (5 * TOL if act == "swish" else 2e-4), name   # ReLU: a unit at round-off distance from the kink may flip
+
+
+@pytest.mark.parametrize("norm,aggr", [("batch", "add"), ("layer", "max"), ("batch", "max")])
+def test_egnn_layer_batchnorm_and_max_options(norm, aggr):
+    """The two constructor options outside the fused kernels (models/layers/egnn_layer.py:24-25: norm='batch', aggr='max') run
+    the unfused path: same numbers as the oracle (training-mode batch statistics), forward and every gradient."""
+    import gmp_b200
+    g = random_clouds(12, 16, 4.0, 1.8, 21, max_nb=64)
+    ei, pos = g["edge_index"], g["pos"]
+    n = pos.shape[0]
+    assert int(ei[1].max()) == n - 1
+    torch.manual_seed(7)
+    ref = R.EGNNLayer(64, "swish", norm, aggr)
+    mine = gmp_b200.EGNNLayer(64, "swish", norm, aggr)
+    mine.load_state_dict(ref.state_dict())
+    mine = mine.cuda()
+    gen = torch.Generator().manual_seed(1)
+    h, ch, cp = torch.randn(n, 64, generator=gen), torch.randn(n, 64, generator=gen), torch.randn(n, 3, generator=gen)
+    hr, pr_ = h.clone().requires_grad_(True), pos.clone().requires_grad_(True)
+    o_r, p_r = ref(hr, pr_, ei)
+    prm_r = dict(ref.named_parameters())
+    gr = torch.autograd.grad((o_r * ch).sum() + (p_r * cp).sum(), [hr, pr_] + list(prm_r.values()))
+    hm, pm_ = h.cuda().requires_grad_(True), pos.cuda().requires_grad_(True)
+    o_m, p_m = mine(hm, pm_, ei.cuda())
+    prm_m = dict(mine.named_parameters())
+    gm = torch.autograd.grad((o_m * ch.cuda()).sum() + (p_m * cp.cuda()).sum(), [hm, pm_] + [prm_m[k] for k in prm_r])
+    assert rel_err(o_m, o_r) <= 5 * TOL and rel_err(p_m - pm_, p_r - pr_) <= 5 * TOL
+    for name, a, b in zip(["h", "pos"] + list(prm_r), gm, gr):
+        if float(b.abs().max()) <= 1e-4:     # a Linear bias in front of a BatchNorm: its gradient is zero up to round-off on both sides
+            assert float(a.abs().max()) <= 1e-3, name
+            continue
+        assert rel_err(a, b) <= 2e-4, name
+    if norm == "batch":     # running statistics updated as nn.BatchNorm1d does
+        assert rel_err(mine.mlp_msg[1].running_mean, ref.mlp_msg[1].running_mean) <= 1e-5
