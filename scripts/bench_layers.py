@@ -124,3 +124,66 @@ if "symc" in which:
     ms = timeit(step)
     print(json.dumps({"layer": "EquivariantProductBasisBlock C=128 corr=3 (config 4 node side)", "workload": f"N={N}",
                       "ms_fwd_bwd": ms, "nodes_per_s": N / (ms * 1e-3)}))
+
+if "uvu" in which:
+    # the ACEsuit-style interaction on the config-4 graph (1024 clouds x 64 points, C = 128): the fused uvu
+    # kernels alone (HBM-bound: per edge 11 C fp32 radial weights streamed once, a 9 C row gathered; per node 35 C written)
+    # and the whole RealAgnosticInteractionBlock
+    graphs, C = 1024, 128
+    pos, batch = clouds(graphs, 64, 4.0)
+    ei = gmp_b200.radius_graph(pos, 2.0, batch, max_num_neighbors=64)
+    N, E = pos.shape[0], ei.shape[1]
+    ir = f"{C}x0e+{C}x1o+{C}x2e"
+    tp = gmp_b200.UVUTensorProduct(ir, "1x0e+1x1o+1x2e", ir).to(dev)
+    x = torch.randn(N, 9 * C, device=dev, requires_grad=True)
+    sh, _ = gmp_b200.edge_geometry(pos, ei, 2, gmp_b200.RadialEmbeddingBlock(2.0, 8, 5))
+    w = torch.randn(E, 11 * C, device=dev, requires_grad=True)
+    HBM = 6545.0
+
+    def fwd():
+        return tp(x, ei, sh, w)
+
+    def step():
+        x.grad = w.grad = None
+        fwd().sum().backward()
+    with torch.no_grad():
+        ms_f = timeit(fwd)
+    ms = timeit(step)
+    b_f = E * (11 * C * 4 + 36 + 8) + N * (35 * C * 4 + 9 * C * 4)
+    b_all = b_f + E * (2 * 11 * C * 4 + 2 * 36) + N * (2 * 35 * C * 4 + 9 * C * 4)   # dx pass re-reads w, dw pass writes [E, 11 C]
+    print(json.dumps({"layer": "uvu tensor product + receiver sum (csrc/uvu.cu), C = 128", "workload": f"N={N} E={E}",
+                      "ms_fwd": ms_f, "ms_fwd_bwd": ms, "edges_per_s": E / (ms * 1e-3),
+                      "roofline": {"bound": "hbm", "peak": HBM, "unit": "GB/s", "frac_fwd": b_f / (ms_f * 1e-3) / 1e9 / HBM,
+                                   "frac_fwd_bwd": b_all / (ms * 1e-3) / 1e9 / HBM, "algorithmic_bytes_fwd": b_f}}))
+    blk = gmp_b200.RealAgnosticInteractionBlock(node_attrs_irreps="4x0e", node_feats_irreps=ir, edge_attrs_irreps="1x0e+1x1o+1x2e",
+                                                edge_feats_irreps="8x0e", target_irreps=ir, hidden_irreps=ir, avg_num_neighbors=17.0).to(dev)
+    attrs = torch.eye(4, device=dev)[torch.randint(0, 4, (N,), device=dev)]
+    feats = gmp_b200.RadialEmbeddingBlock(2.0, 8, 5)((pos[ei[0]] - pos[ei[1]]).norm(dim=-1, keepdim=True))
+
+    def bstep():
+        blk.zero_grad(set_to_none=True)
+        x.grad = None
+        blk(attrs, x, sh, feats, ei)[0].sum().backward()
+    msb = timeit(bstep)
+    print(json.dumps({"layer": "RealAgnosticInteractionBlock C = 128 (blocks.py:396-459)", "workload": f"N={N} E={E}", "ms_fwd_bwd": msb,
+                      "edges_per_s": E / (msb * 1e-3)}))
+
+if "gvp" in which:
+    # GVPConvLayer at the reference defaults (s 128, v 16, edge 32 / 1) on the config-2 graph
+    pos, batch = clouds(4096, 32, 8.0)
+    ei = gmp_b200.radius_graph(pos, 5.0, batch, max_num_neighbors=32)
+    N, E = pos.shape[0], ei.shape[1]
+    import torch.nn.functional as F_
+    layer = gmp_b200.GVPConvLayer((128, 16), (32, 1), activations=(F_.relu, None)).to(dev).eval()
+    s = torch.randn(N, 128, device=dev, requires_grad=True)
+    v = torch.randn(N, 16, 3, device=dev, requires_grad=True)
+    es, ev = torch.randn(E, 32, device=dev), torch.randn(E, 1, 3, device=dev)
+
+    def gstep():
+        layer.zero_grad(set_to_none=True)
+        s.grad = v.grad = None
+        os_, ov = layer((s, v), ei, (es, ev))
+        (os_.sum() + ov.sum()).backward()
+    msg = timeit(gstep)
+    print(json.dumps({"layer": "GVPConvLayer (128, 16) / (32, 1), unfused perceptron stack + deterministic mean aggregation",
+                      "workload": f"N={N} E={E}", "ms_fwd_bwd": msg, "edges_per_s": E / (msg * 1e-3)}))
