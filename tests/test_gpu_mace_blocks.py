@@ -40,7 +40,7 @@ def test_interaction_block_golden(cls):
         check_against_digest(got[k].cpu(), ref, 10 * TOL, k)
 
 
-@pytest.mark.parametrize("C,graphs,nodes,shuffle", [(128, 3, 40, True), (64, 1, 1, False), (32, 4, 33, True)])
+@pytest.mark.parametrize("C,graphs,nodes,shuffle", [(128, 3, 40, True), (64, 1, 1, False), (32, 4, 33, True), (40, 2, 20, True)])
 def test_real_agnostic_block_vs_oracle(C, graphs, nodes, shuffle):
     """RealAgnosticInteractionBlock (blocks.py:396-459) at the MACE widths; edge order shuffled (perm path of the CSR),
     a single isolated node (E = 0), nodes without in-edges."""
