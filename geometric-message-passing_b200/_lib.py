@@ -100,6 +100,7 @@ _SIGS = {
     "gmp_gate_bwd": [P, P, P, P, P, I64, I32, I32, I32, F32, F32, P, P],
     "gmp_node_pack_w": [P, I32, I32, I32, P, P],
     "gmp_node_chain_tc": [P, P, I64, I32, P, P],
+    "gmp_node_pack_w_batch": [P, P, P, I32, P],
     "gmp_ln_act_bwd": [P, P, P, P, F32, I32, I64, P, P, P, P],
     "gmp_tp_wgrad": [P, P, P, I64, I64, P, I32, P, I32, P, I32, P, I32, P, P, P, I32, P, I32, P, P, P, P, I32, P],
 }

@@ -353,6 +353,26 @@ __global__ void node_pack_w_kernel(const float* __restrict__ w, int out_dim, int
 }
 
 
+// many 128 x 128 weights in one launch (a model packs every operand image of a step at once: 36 launches -> 1 for SchNet)
+constexpr int kPackBatchMax = 48;
+struct PackBatch {
+    const float* w[kPackBatchMax];
+    uint8_t* img[kPackBatchMax];
+    int transpose[kPackBatchMax];
+};
+__global__ void __launch_bounds__(256) node_pack_w_batch_kernel(const PackBatch b) {
+    const int m = blockIdx.x >> 3;                                   // 8 blocks of 256 chunks per matrix
+    const int idx = (blockIdx.x & 7) * 256 + threadIdx.x;            // one 8-element chunk each: 128 rows x 16 chunks
+    const int r = idx >> 4, k0 = (idx & 15) * 8;
+    const float* w = b.w[m];
+    const int tr = b.transpose[m];
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = tr ? __ldg(w + (k0 + j) * 128 + r) : __ldg(w + r * 128 + k0 + j);
+    uint8_t* dst = b.img[m] + ((k0 & 127) >> 6) * kNcSlab + sw128_chunk_off(r, (k0 & 63) >> 3);
+    *reinterpret_cast<uint4*>(dst) = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+}
+
 // Backward of  a = act(LayerNorm(pre) * gamma + beta)  over 128-wide rows (EGNN mlp_upd, models/layers/egnn_layer.py:41-48):
 //   d_pre = rstd * (gamma dy - mean(gamma dy) - xhat mean(gamma dy xhat)),   dy = g * act'(y)
 // plus the per-CTA partial sums of d gamma = sum dy xhat and d beta = sum dy, and optionally the recomputed activations
@@ -457,6 +477,23 @@ int gmp_node_pack_w(const float* w, int32_t out_dim, int32_t in_dim, int32_t tra
     const int chunks = out_dim * in_dim / 8;
     node_pack_w_kernel<<<(unsigned)ceil_div(chunks, 256), 256, 0, stream>>>(w, out_dim, in_dim, transpose, reinterpret_cast<uint8_t*>(img));
     return check_launch("node_pack_w_kernel");
+}
+
+int gmp_node_pack_w_batch(const float* const* w, const int32_t* transpose, void* const* img, int32_t count, gmp_stream_t stream) {
+    GMP_REQUIRE(count >= 0 && (count == 0 || (w && transpose && img)), "node_pack_w_batch: bad arguments");
+    for (int base = 0; base < count; base += kPackBatchMax) {
+        PackBatch b;
+        const int m = count - base < kPackBatchMax ? count - base : kPackBatchMax;
+        for (int i = 0; i < m; ++i) {
+            GMP_REQUIRE(w[base + i] && img[base + i], "node_pack_w_batch: NULL pointer at %d", base + i);
+            b.w[i] = w[base + i];
+            b.img[i] = reinterpret_cast<uint8_t*>(img[base + i]);
+            b.transpose[i] = transpose[base + i];
+        }
+        node_pack_w_batch_kernel<<<(unsigned)(m * 8), 256, 0, stream>>>(b);
+        if (int rc = check_launch("node_pack_w_batch_kernel")) return rc;
+    }
+    return GMP_OK;
 }
 
 int gmp_node_chain_tc(const float* a0, const float* a1, int64_t n, int32_t nstage, const gmp_node_stage* stages, gmp_stream_t stream) {

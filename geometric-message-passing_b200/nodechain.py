@@ -27,6 +27,17 @@ def pack_w(weight: torch.Tensor, transpose: bool = False) -> torch.Tensor:
     return img
 
 
+def pack_w_batch(weights: Sequence[torch.Tensor], transposes: Sequence[bool]):
+    """Operand images of many [128, 128] weights in ONE launch; returns the images (views of one buffer) in order."""
+    n = len(weights)
+    assert n == len(transposes) and all(tuple(w.shape) == (128, 128) for w in weights)
+    ws = [w.detach().contiguous() for w in weights]
+    buf = torch.empty(n, 32768, dtype=torch.uint8, device=ws[0].device)
+    call("gmp_node_pack_w_batch", (C.c_void_p * n)(*[w.data_ptr() for w in ws]), (C.c_int32 * n)(*[int(t) for t in transposes]),
+         (C.c_void_p * n)(*[buf[i].data_ptr() for i in range(n)]), n)
+    return [buf[i] for i in range(n)]
+
+
 def stage(w_img: torch.Tensor, bias: Optional[torch.Tensor] = None, ln: Optional[Sequence] = None, act: Optional[str] = None,
           mul_aux: Optional[torch.Tensor] = None, mul_mode: int = MUL_PLAIN, add_res: Optional[torch.Tensor] = None,
           out_f32: Optional[torch.Tensor] = None, out_bf16: Optional[torch.Tensor] = None, out_pre: Optional[torch.Tensor] = None):

@@ -233,8 +233,12 @@ class _SchNetBodyFn(torch.autograd.Function):
         nchunks = int(_lib.lib().gmp_schnet_tc2_num_chunks(E))
         f32 = dict(dtype=torch.float32, device=dev)
         h = h0.contiguous()
+        # every operand image of the step in one launch: per block lin1, lin2, lin and (training) their transposes
+        ws = [P[l][k] for l in range(L) for k in (4, 5, 7)]
+        imgs = nc.pack_w_batch(ws + (ws if train else []), [False] * len(ws) + ([True] * len(ws) if train else []))
+        I = lambda l, k, t=False: imgs[(len(ws) if t else 0) + 3 * l + {4: 0, 5: 1, 7: 2}[k]]
         x1 = torch.empty(n, 128, dtype=torch.bfloat16, device=dev)
-        nc.run(h, [nc.stage(nc.pack_w(P[0][4]), out_bf16=x1)])
+        nc.run(h, [nc.stage(I(0, 4), out_bf16=x1)])
         saved = []
         for l in range(L):
             w1f, b1f, w2f, b2f, _, w_lin2, b_lin2, w_lin, b_lin = P[l]
@@ -245,15 +249,16 @@ class _SchNetBodyFn(torch.autograd.Function):
             call("gmp_schnet_cfconv_fwd_tc2_keep", ptr(csr.rowptr), ptr(csr.col), csr.perm_ptr, ptr(csr.row_ids()), n, E,
                  ptr(edge_weight), ptr(x1), C.byref(filt), ptr(agg), ptr(head), ptr(keep), ptr(keep_row))
             y, hn = torch.empty(n, 128, **f32), torch.empty(n, 128, **f32)
-            stages = [nc.stage(nc.pack_w(w_lin2), b_lin2, act="ssp", out_f32=y), nc.stage(nc.pack_w(w_lin), b_lin, add_res=h, out_f32=hn)]
+            stages = [nc.stage(I(l, 5), b_lin2, act="ssp", out_f32=y), nc.stage(I(l, 7), b_lin, add_res=h, out_f32=hn)]
             x1n = None
             if l + 1 < L:
                 x1n = torch.empty(n, 128, dtype=torch.bfloat16, device=dev)
-                stages.append(nc.stage(nc.pack_w(P[l + 1][4]), out_bf16=x1n))
+                stages.append(nc.stage(I(l + 1, 4), out_bf16=x1n))
             nc.run(agg, stages)
             if train:
                 saved.append((h, x1, agg, y, keep))
             h, x1 = hn, x1n
+        ctx.imgT = (lambda l, k: I(l, k, True)) if train else None
         ctx.saved, ctx.P, ctx.graph, ctx.meta, ctx.ew = saved, P, graph, (float(cutoff), float(coeff)), edge_weight
         ctx.offset = offset
         return h
@@ -285,14 +290,15 @@ class _SchNetBodyFn(torch.autograd.Function):
             h, x1, agg, y, keep = saved[l]
             dT, dagg = torch.empty(n, 128, **f32), torch.empty(n, 128, **f32)
             dagg16 = torch.empty(n, 128, dtype=torch.bfloat16, device=dev)
-            tail = [nc.stage(nc.pack_w(w_lin, True), mul_aux=y, mul_mode=nc.MUL_DSSP, out_f32=dT),
-                    nc.stage(nc.pack_w(w_lin2, True), out_f32=dagg, out_bf16=dagg16)]
+            IT = ctx.imgT
+            tail = [nc.stage(IT(l, 7), mul_aux=y, mul_mode=nc.MUL_DSSP, out_f32=dT),
+                    nc.stage(IT(l, 5), out_f32=dagg, out_bf16=dagg16)]
             if dx1_next is None:
                 Gt = G
                 nc.run(G, tail)
             else:
                 Gt = torch.empty(n, 128, **f32)
-                nc.run(dx1_next, [nc.stage(nc.pack_w(P[l + 1][4], True), add_res=G, out_f32=Gt)] + tail)
+                nc.run(dx1_next, [nc.stage(IT(l + 1, 4), add_res=G, out_f32=Gt)] + tail)
                 grads[(l + 1) * 9 + 4], _ = wgrad(dx1_next, saved[l + 1][0], bias=False)
             grads[l * 9 + 7], grads[l * 9 + 8] = wgrad(Gt, y)
             grads[l * 9 + 5], grads[l * 9 + 6] = wgrad(dT, agg)
@@ -314,7 +320,7 @@ class _SchNetBodyFn(torch.autograd.Function):
             grads[l * 9 + 3] = red[o:o + F_]
             G, dx1_next = Gt, dx1
         dh0 = torch.empty(n, 128, **f32)
-        nc.run(dx1_next, [nc.stage(nc.pack_w(P[0][4], True), add_res=G, out_f32=dh0)])
+        nc.run(dx1_next, [nc.stage(ctx.imgT(0, 4), add_res=G, out_f32=dh0)])
         grads[4], _ = wgrad(dx1_next, saved[0][0], bias=False)
         return (dh0, None, None, None, None, None, *grads)
 

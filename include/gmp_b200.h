@@ -494,6 +494,8 @@ typedef struct gmp_node_stage {
  * transpose = 1: the image of W^T (dx = g W, in_dim = 128, out_dim = 128 or 256). */
 int64_t gmp_node_w_image_bytes(int32_t out_dim, int32_t in_dim, int32_t transpose);
 int gmp_node_pack_w(const float* w, int32_t out_dim, int32_t in_dim, int32_t transpose, void* img, gmp_stream_t stream);
+/* `count` weights of shape [128, 128] in one launch (host arrays of pointers / flags; images of 32 KB each). */
+int gmp_node_pack_w_batch(const float* const* w, const int32_t* transpose, void* const* img, int32_t count, gmp_stream_t stream);
 int gmp_node_chain_tc(const float* a0, const float* a1, int64_t num_rows, int32_t nstage, const gmp_node_stage* stages,
                       gmp_stream_t stream);
 
