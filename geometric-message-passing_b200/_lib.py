@@ -65,6 +65,7 @@ _SIGS = {
     "gmp_gather_mul_segsum_wbf16": [P, P, P, P, I32, P, P, I64, I32, P],
     "gmp_gather_rows_f32": [P, P, P, I64, I32, P],
     "gmp_reduce_partials_f32": [P, I32, I64, P, P],
+    "gmp_reduce_partials_batch_f32": [P, P, P, P, I32, P],
     "gmp_edge_length_fwd": [P, P, P, I64, P, P],
     "gmp_edge_geometry_fwd": [P, P, P, I64, I32, F32, I32, F32, P, P, P],
     "gmp_edge_length_bwd": [P, P, P, P, P, P, P, P, I64, P, P],

@@ -164,6 +164,46 @@ __global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __res
     }
 }
 
+// several independent reductions in one launch (blockIdx.y = problem): a backward pass collects the partial buffers of all its
+// parameter gradients and reduces them together (SchNet: 25 launches -> 1); same association per problem as the kernel above
+constexpr int kReduceBatchMax = 32;
+struct ReduceBatch {
+    const float* part[kReduceBatchMax];
+    float* out[kReduceBatchMax];
+    int64_t len[kReduceBatchMax];
+    int nparts[kReduceBatchMax];
+};
+__global__ void __launch_bounds__(256) reduce_partials_batch_kernel(const ReduceBatch b) {
+    __shared__ float red[8][32];
+    const int m = blockIdx.y;
+    const float* __restrict__ part = b.part[m];
+    const int64_t len = b.len[m];
+    const int nparts = b.nparts[m];
+    if ((int64_t)blockIdx.x * 32 >= len) return;
+    const int ix = threadIdx.x & 31, gy = threadIdx.x >> 5;
+    const int64_t i = (int64_t)blockIdx.x * 32 + ix;
+    const int p0 = (int)(((int64_t)nparts * gy) / 8), p1 = (int)(((int64_t)nparts * (gy + 1)) / 8);
+    float acc = 0.f;
+    if (i < len) {
+        int p = p0;
+        for (; p + 4 <= p1; p += 4) {
+            float v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) v[u] = __ldcg(part + (int64_t)(p + u) * len + i);
+            acc += (v[0] + v[1]) + (v[2] + v[3]);
+        }
+        for (; p < p1; ++p) acc += __ldcg(part + (int64_t)p * len + i);
+    }
+    red[gy][ix] = acc;
+    __syncthreads();
+    if (gy == 0 && i < len) {
+        float s_ = red[0][ix];
+#pragma unroll
+        for (int g = 1; g < 8; ++g) s_ += red[g][ix];
+        b.out[m][i] = s_;
+    }
+}
+
 __global__ void edge_length_kernel(const float* __restrict__ pos, const int64_t* __restrict__ src,
                                    const int64_t* __restrict__ dst, int64_t E, float* __restrict__ dist) {
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -334,6 +374,25 @@ int gmp_reduce_partials_f32(const float* part, int32_t nparts, int64_t len, floa
     if (len == 0) return GMP_OK;
     reduce_partials_kernel<<<(unsigned)ceil_div(len, 32), 256, 0, stream>>>(part, nparts, len, out);
     return check_launch("reduce_partials");
+}
+
+int gmp_reduce_partials_batch_f32(const float* const* parts, const int32_t* nparts, const int64_t* lens, float* const* outs, int32_t count,
+                                  gmp_stream_t stream) {
+    GMP_REQUIRE(count >= 0 && (count == 0 || (parts && nparts && lens && outs)), "reduce_partials_batch: bad arguments");
+    for (int base = 0; base < count; base += kReduceBatchMax) {
+        ReduceBatch b;
+        const int m = count - base < kReduceBatchMax ? count - base : kReduceBatchMax;
+        int64_t maxlen = 0;
+        for (int i = 0; i < m; ++i) {
+            GMP_REQUIRE(parts[base + i] && outs[base + i] && nparts[base + i] >= 1 && lens[base + i] >= 0, "reduce_partials_batch: problem %d", base + i);
+            b.part[i] = parts[base + i]; b.out[i] = outs[base + i]; b.len[i] = lens[base + i]; b.nparts[i] = nparts[base + i];
+            if (lens[base + i] > maxlen) maxlen = lens[base + i];
+        }
+        if (maxlen == 0) continue;
+        reduce_partials_batch_kernel<<<dim3((unsigned)ceil_div(maxlen, 32), (unsigned)m), 256, 0, stream>>>(b);
+        if (int rc = check_launch("reduce_partials_batch")) return rc;
+    }
+    return GMP_OK;
 }
 
 int gmp_edge_length_fwd(const float* pos, const int64_t* src, const int64_t* dst, int64_t num_edges, float* dist,

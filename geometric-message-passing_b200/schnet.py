@@ -275,12 +275,22 @@ class _SchNetBodyFn(torch.autograd.Function):
         csr, t = graph.by_dst, graph.by_src
         G = G.contiguous()
 
+        pending = []     # (partials, reduced): the per-CTA partial buffers of one block are summed by ONE launch, while they are still in L2
+
+        def flush():
+            k = len(pending)
+            if k:
+                call("gmp_reduce_partials_batch_f32", (C.c_void_p * k)(*[p_.data_ptr() for p_, _ in pending]),
+                     (C.c_int32 * k)(*[p_.shape[0] for p_, _ in pending]), (C.c_int64 * k)(*[p_.shape[1] for p_, _ in pending]),
+                     (C.c_void_p * k)(*[r_.data_ptr() for _, r_ in pending]), k)
+                pending.clear()
+
         def wgrad(g, x, bias=True):
             nparts, plen = lib.gmp_linear_wgrad_num_parts(n), 128 * 128 + 128
             parts = torch.empty(nparts, plen, **f32)
             call("gmp_linear_wgrad_tc", ptr(g), ptr(x), n, 128, 128, ptr(parts))
             red = torch.empty(plen, **f32)
-            call("gmp_reduce_partials_f32", ptr(parts), nparts, plen, ptr(red))
+            pending.append((parts, red))
             return red[:128 * 128].view(128, 128), (red[128 * 128:] if bias else None)
 
         grads = [None] * (L * 9)
@@ -312,16 +322,20 @@ class _SchNetBodyFn(torch.autograd.Function):
             call("gmp_schnet_cfconv_bwd_tc2", ptr(csr.rowptr), ptr(csr.col), csr.perm_ptr, ptr(csr.row_ids()), n, E, ptr(ew), ptr(x1),
                  C.byref(filt), ptr(dagg), ptr(parts), nparts)
             red = torch.empty(plen, **f32)
-            call("gmp_reduce_partials_f32", ptr(parts), nparts, plen, ptr(red))
+            pending.append((parts, red))
             o = 0
-            grads[l * 9 + 0] = red[o:o + F_ * 64].view(F_, 64)[:, :G_].contiguous(); o += F_ * 64
+            grads[l * 9 + 0] = red[o:o + F_ * 64].view(F_, 64)[:, :G_]; o += F_ * 64
             grads[l * 9 + 1] = red[o:o + F_]; o += F_
             grads[l * 9 + 2] = red[o:o + F_ * F_].view(F_, F_); o += F_ * F_
             grads[l * 9 + 3] = red[o:o + F_]
             G, dx1_next = Gt, dx1
+            flush()
         dh0 = torch.empty(n, 128, **f32)
         nc.run(dx1_next, [nc.stage(ctx.imgT(0, 4), add_res=G, out_f32=dh0)])
         grads[4], _ = wgrad(dx1_next, saved[0][0], bias=False)
+        flush()
+        for l in range(L):     # (a strided view of the reduced buffer: materialise after the reduction)
+            grads[l * 9 + 0] = grads[l * 9 + 0].contiguous()
         return (dh0, None, None, None, None, None, *grads)
 
 

@@ -140,6 +140,9 @@ int gmp_gather_rows_f32(const int32_t* idx, const float* x, float* out, int64_t 
 
 /* deterministic sum of `nparts` partial buffers of `len` floats each: out[i] = sum_p part[p*len+i]. */
 int gmp_reduce_partials_f32(const float* part, int32_t nparts, int64_t len, float* out, gmp_stream_t stream);
+/* `count` independent reductions of that kind in one launch (host arrays: parts[k] is [nparts[k]][lens[k]], outs[k] is [lens[k]]). */
+int gmp_reduce_partials_batch_f32(const float* const* parts, const int32_t* nparts, const int64_t* lens, float* const* outs,
+                                  int32_t count, gmp_stream_t stream);
 
 /* Edge lengths and their backward (models/schnet.py:66-67; models/tfn.py:171-172):
  *   fwd: dist[e] = || pos[src[e]] - pos[dst[e]] ||_2            (edge order of the caller)
